@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- particle push+search throughput of the B200-native PUMI-PIC hot path.
+
+Workload (BASELINE.json configs[1], "search_mesh_3d adjacency walk only, 10M particles on
+1M-tet synthetic cube mesh, 1xB200"): Kuhn cube N=55 (998 250 tets), 10 M particles placed by
+test_adj.cpp's seeded generator, push distance L/(3*nelems^(1/3)).  One step = ONE fused kernel:
+xtgt = x + d*dir followed by the search_mesh BCC walk; the two position buffers swap roles and
+the sign of d flips every step so particles oscillate and the population is stationary after
+the first step (particles that leave the domain are deleted, as in the reference).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N>1 (torchrun): every rank owns an identical-size independent shard (its own PICpart-sized
+mesh + particles); push+search has no exchange step, so there is no data-path collective and
+scaling is weak.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle push+search steps/s"
+UNIT = "particle-steps/s"
+# push 49 B + BCC search 53 B + mesh 7 B per particle-step (unfused accounting)
+ALGO_BYTES_PER_PARTICLE_STEP = 109.0
+MEMBERS = [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float64, 3)]
+
+
+def load_module(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class HostMesh:
+    pass
+
+
+def build_workload(pp, wl, cube_n, nptcls):
+    """Host-side synthetic inputs (seeded, identical on every rank and for the CPU arm)."""
+    coords, ev = pp.host_kuhn_cube(cube_n, 1.0)
+    e2s, s2v = pp.host_derive_sides(3, ev)
+    m = HostMesh()
+    m.dim, m.coords, m.elem2verts, m.elem2sides, m.side2verts = 3, coords, ev, e2s, s2v
+    m.nelems, m.nverts, m.nsides = ev.shape[0], coords.shape[0], s2v.shape[0]
+    m.class_id = np.ones(m.nelems, np.int32)
+    ppe = wl.even_ppe(m.nelems, nptcls)
+    return m, ppe
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().split("\n") if r.strip()]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        os.unlink(self.f.name)
+        return out
+
+
+def cpu_reference_leg(orc, om, wl, m, ppe, sample, steps, warmup):
+    """The reference algorithm (CPU oracle, OpenMP, kernel-per-phase) on a bounded sample:
+    push (xtgt = x + d*dir) + search_mesh BCC per step, ping-pong buffers like the GPU arm."""
+    cap = int(sample)
+    slot_elem = np.repeat(np.arange(m.nelems, dtype=np.int32), ppe)[:cap]
+    mask = np.ones(cap, np.uint8)
+    X, D = wl.init3d_internal(m, slot_elem, mask)
+    dist = wl.push_distance(m)
+    A, B = X, np.zeros_like(X)
+    ids = None
+    times, active = [], []
+    for it in range(warmup + steps):
+        sgn = dist if it % 2 == 0 else -dist
+        t0 = time.perf_counter()
+        np.copyto(B, A)                       # xtgt = x ...
+        orc.push_direction(mask, B, D, sgn)   # ... + d*dir   (same arithmetic as the fused push)
+        found, ids, _, _, st = om.search_mesh(slot_elem, mask, A, B, elem_ids=ids)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            active.append(int((ids >= 0).sum()))
+        A, B = B, A
+    return float(sum(active)) / sum(times), 1e3 * sum(times) / len(times), cap
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cube-n", type=int, default=55)
+    ap.add_argument("--particles", type=int, default=10_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="particles per CPU step (0 = all)")
+    ap.add_argument("--ps", default="dps", choices=["dps", "scs", "csr"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    if a.cpu_sample <= 0:
+        a.cpu_sample = a.particles
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    wl = load_module("pp_workloads", os.path.join(ROOT, "pumi-pic_b200", "workloads.py"))
+    config = {"workload": "search_mesh BCC walk + push, %d particles on Kuhn cube N=%d (%d tets) per GPU"
+                          % (a.particles, a.cube_n, 6 * a.cube_n ** 3),
+              "particles_per_gpu": a.particles, "tets_per_gpu": 6 * a.cube_n ** 3,
+              "push": "xtgt = x + d*dir, d = L/(3*nelems^(1/3)), sign alternates per step",
+              "l2": "inputs (>=0.8 GB of particle columns per step) are larger than the 126 MB L2",
+              "particle_structure": a.ps, "parallelism": "independent shard per GPU (no exchange in push+search)"}
+
+    if a.impl == "reference":
+        # CPU arm: rank 0 only; the reference's own CPU algorithm via the oracle port (the real
+        # Kokkos/Omega_h reference cannot be built here, DESIGN.md "Oracle").
+        if rank != 0:
+            return 0
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as orc
+        pp = importlib.import_module("pumi-pic_b200")
+        m, ppe = build_workload(pp, wl, a.cube_n, a.particles)
+        from meshes import Mesh as TMesh
+        tm = TMesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
+        om = orc.OracleMesh(tm)
+        cores = orc.lib().orc_get_max_threads()
+        val, ms, cap = cpu_reference_leg(orc, om, wl, tm, ppe, a.cpu_sample, a.steps, a.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "first %d particles of the workload per step, OpenMP oracle "
+                                           "(CPU restatement of the reference algorithm)" % cap},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pp = importlib.import_module("pumi-pic_b200")
+    P = pp
+    m, ppe = build_workload(pp, wl, a.cube_n, a.particles)
+    gm = pp.Mesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
+    kind = {"dps": P.capi.PP_PS_DPS, "scs": P.capi.PP_PS_SCS, "csr": P.capi.PP_PS_CSR}[a.ps]
+    ps = pp.ParticleStructure(kind, MEMBERS, ppe)
+    slot_elem, mask = ps.slot_elem_and_mask()
+    X, D = wl.init3d_internal(m, slot_elem, mask)
+    d = wl.push_distance(m)
+    cap = ps.capacity
+    xa = torch.as_tensor(X).cuda()
+    xb = torch.zeros_like(xa)
+    dr = torch.as_tensor(D).cuda()
+    ids = torch.zeros(cap, dtype=torch.int32, device="cuda")
+
+    def step(it, a_, b_, sync=False):
+        return P.push_direction_search(gm, ps, dr, d if it % 2 == 0 else -d, a_, b_, ids,
+                                       elem_ids_empty=False, from_orig=True, sync=sync)
+
+    # seed element ids from the structure rows, then warm up
+    P.push_direction_search(gm, ps, dr, 0.0, xa, xb, ids, elem_ids_empty=True, from_orig=True, sync=True)
+    A, B = xa, xb
+    it = 0
+    for _ in range(a.warmup):
+        step(it, A, B); A, B = B, A; it += 1
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    active_steps = 0
+    stream = torch.cuda.current_stream()
+    ev[0].record(stream)
+    for k in range(a.steps):
+        step(it, A, B); A, B = B, A; it += 1
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
+    # stationary population: count live particles once (the oscillation keeps it constant)
+    live = int((ids >= 0).sum().item())
+    st = P.capi.SearchStats()
+    P.capi.check(P.lib().pp_search_last_stats(gm.h, st, None))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    n = torch.tensor([float(live)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    live_all = float(n.item())
+    value = live_all * a.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the C ABI with HOST (pinned) buffers: H2D of the step's inputs and
+    # D2H of its results inside the timed region.
+    e2e = None
+    if not a.no_e2e:
+        hx = torch.empty_like(A, device="cpu").pin_memory(); hx.copy_(A)
+        hd = torch.empty_like(dr, device="cpu").pin_memory(); hd.copy_(dr)
+        hi = torch.empty_like(ids, device="cpu").pin_memory(); hi.copy_(ids)
+        ht = torch.empty_like(A, device="cpu").pin_memory()
+        dx, dd, dt_, di = (torch.empty_like(A), torch.empty_like(dr), torch.empty_like(A),
+                           torch.empty_like(ids))
+        e2e_steps = max(3, min(a.steps, 5))
+
+        def e2e_step(k):
+            dx.copy_(hx, non_blocking=True); dd.copy_(hd, non_blocking=True)
+            di.copy_(hi, non_blocking=True)
+            P.push_direction_search(gm, ps, dd, d if (it + k) % 2 == 0 else -d, dx, dt_, di,
+                                    from_orig=True, sync=False)
+            ht.copy_(dt_, non_blocking=True); hi.copy_(di, non_blocking=True)
+            torch.cuda.synchronize()
+            hx.copy_(ht)   # the caller's next step starts from the pushed positions
+        e2e_step(0)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(1, e2e_steps + 1):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        et = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        live2 = torch.tensor([float((hi >= 0).sum().item())], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(live2, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(live2.item()) * e2e_steps / float(et.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(hx.numel() * 8 + hd.numel() * 8 + hi.numel() * 4),
+               "d2h_bytes_per_step": int(ht.numel() * 8 + hi.numel() * 4),
+               "steps": e2e_steps,
+               "note": "pinned host buffers, cudaMemcpyAsync H2D -> fused kernel -> D2H per step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    kavg_ms = float(np.mean(kernel_ms))
+    live_rank0 = live
+    achieved = ALGO_BYTES_PER_PARTICLE_STEP * live_rank0 / (kavg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("k_search_dram_bytes_per_launch")
+    cpu = None
+    if not a.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as orc
+        from meshes import Mesh as TMesh
+        tm = TMesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
+        om = orc.OracleMesh(tm)
+        cores = orc.lib().orc_get_max_threads()
+        val, ms, ncap = cpu_reference_leg(orc, om, wl, tm, ppe, min(a.cpu_sample, 4_000_000), 4, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "first %d particles of the workload, 4 timed steps after 1 warm-up, "
+                         "OpenMP oracle (CPU restatement of the reference algorithm)" % ncap,
+               "ms_per_step": ms}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k_search<3,BCC,PUSH> (fused push + walk)",
+                         "algorithmic_bytes_per_particle_step": ALGO_BYTES_PER_PARTICLE_STEP,
+                         "kernel_ms": kavg_ms, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "detail": {"live_particles_per_gpu": live_rank0, "capacity": cap,
+                       "walk_iterations_last_step": st.loops, "hops_last_step": int(st.hops),
+                       "active_last_step": st.active}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,266 @@
+/*
+ * pumipic_b200.h -- C ABI of libpumipic_b200.so: the B200-native (sm_100a CUDA + NCCL)
+ * implementation of PUMI-PIC's per-timestep particle hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / opaque handles and
+ * returns a pp_status; pp_last_error() gives the message of the last failure on the calling
+ * thread.  Unless a parameter says "host", array pointers are DEVICE pointers (the reference's
+ * Kokkos views and Omega_h arrays are device-resident in a CUDA build, and a binding passes
+ * `view.data()`).  Each entry cites the reference interface it replaces
+ * (paths relative to SCOREC/pumi-pic @ c09ad045).  The reference-side binding is shown in
+ * INTEGRATION.md; the header-only C++ mirror of the reference API lives in
+ * pumi-pic_b200/cpp/.
+ *
+ * Layout conventions (identical to the reference):
+ *   - a particle member with N components is component-major SoA ("LayoutLeft"):
+ *     value(slot, i) lives at base[i * stride + slot]
+ *   - per-slot user arrays (elem_ids, inter_faces, ...) have capacity() entries, indexed by slot
+ *   - inter_points is AoS: inter_points[dim * slot + i]
+ *   - lid_t = int32, gid_t = int64, fp_t = double
+ *
+ * Handles are not thread-safe; all work of a call is enqueued on the `stream` argument
+ * (a cudaStream_t; NULL = the legacy default stream).  Calls that return values to the host
+ * synchronise that stream, the others are asynchronous.
+ */
+#ifndef PUMIPIC_B200_H
+#define PUMIPIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pp_mesh pp_mesh;
+typedef struct pp_ps pp_ps;
+typedef void* pp_stream; /* cudaStream_t */
+
+typedef enum pp_status {
+  PP_OK = 0,
+  PP_ERR_INVALID = 1,     /* bad argument */
+  PP_ERR_CUDA = 2,        /* CUDA runtime failure (no device, launch error, ...) */
+  PP_ERR_NCCL = 3,
+  PP_ERR_NOMEM = 4,
+  PP_ERR_UNSUPPORTED = 5
+} pp_status;
+
+typedef enum pp_memspace { PP_HOST = 0, PP_DEVICE = 1 } pp_memspace;
+
+const char* pp_last_error(void);
+/* library version "major.minor.patch" and the GPU architecture it was built for ("sm_100a") */
+const char* pp_version(void);
+const char* pp_build_arch(void);
+
+/* ============================== mesh ==================================================== */
+
+/* The arrays an Omega_h mesh hands to the reference's searches:
+ *   coords      = mesh.coords()                 (adjacency.tpp:79,238-241)
+ *   elem2verts  = mesh.ask_elem_verts()         (adjacency.tpp:78)
+ *   elem2sides  = mesh.ask_down(dim,dim-1).ab2b (adjacency.tpp:240-241)
+ *   side2verts  = mesh.ask_verts_of(dim-1)      (adjacency.tpp:282,501)
+ *   elem_class  = mesh.get_array<ClassId>(dim,"class_id") (ellipticalPush.hpp:43), optional
+ * Everything else the reference recomputes per search call (measure_elements_real,
+ * mark_exposed_sides, ask_up(dim-1,dim), ask_dual, compute_tolerance_from_area;
+ * adjacency.tpp:489-501,621) is derived ONCE here, on the device, and cached in the handle. */
+typedef struct pp_mesh_desc {
+  int32_t dim;       /* 2 (triangles) or 3 (tets) */
+  int32_t nverts, nelems, nsides;
+  const double* coords;       /* [nverts*dim]         */
+  const int32_t* elem2verts;  /* [nelems*(dim+1)]     */
+  const int32_t* elem2sides;  /* [nelems*(dim+1)]     */
+  const int32_t* side2verts;  /* [nsides*dim]         */
+  const int32_t* elem_class;  /* [nelems] or NULL     */
+  int32_t memspace;           /* pp_memspace of the five arrays above */
+} pp_mesh_desc;
+
+pp_status pp_mesh_create(const pp_mesh_desc* desc, pp_stream stream, pp_mesh** out);
+pp_status pp_mesh_destroy(pp_mesh* mesh);
+
+typedef struct pp_mesh_info {
+  int32_t dim, nverts, nelems, nsides;
+  double tol;               /* compute_tolerance_from_area, adjacency.tpp:419-428 */
+  double min_measure;       /* min element area / volume */
+  int32_t n_exposed_sides;
+  int64_t walk_table_bytes; /* size of the packed per-element walk records in HBM */
+} pp_mesh_info;
+pp_status pp_mesh_get_info(const pp_mesh* mesh, pp_mesh_info* out);
+
+/* Device pointers to the derived arrays (valid until pp_mesh_destroy):
+ *   measure      double[nelems]   == measure_elements_real(&mesh)
+ *   exposed      int8[nsides]     == mark_exposed_sides(&mesh)
+ *   side2elem    int32[2*nsides]  == ask_up(dim-1,dim): (lower id, higher id or -1) per side
+ *   dual_off/dual                 == ask_dual().a2ab / .ab2b                                  */
+typedef struct pp_mesh_arrays {
+  const double* coords;
+  const int32_t* elem2verts;
+  const int32_t* elem2sides;
+  const int32_t* side2verts;
+  const int32_t* elem_class;
+  const double* measure;
+  const int8_t* exposed;
+  const int32_t* side2elem;
+  const int32_t* dual_off;
+  const int32_t* dual;
+} pp_mesh_arrays;
+pp_status pp_mesh_get_arrays(const pp_mesh* mesh, pp_mesh_arrays* out);
+
+/* PICpart tags used by setUnsafeProcs (pumipic_ptcl_ops.hpp:33-53): safe = Mesh::safeTag(),
+ * owner = Mesh::entOwners(dim).  Copied into the walk records so the fused search tail needs
+ * no extra gather.  memspace as above. */
+pp_status pp_mesh_set_picpart(pp_mesh* mesh, const int32_t* safe, const int32_t* owner,
+                              int32_t self_rank, int32_t memspace, pp_stream stream);
+
+/* ---- host-side mesh utilities (no GPU needed; caller owns the outputs, free with pp_host_free)
+ * Derive sides of a simplicial mesh from element->vertex connectivity.  Sides are numbered by
+ * the lexicographic order of their sorted vertex tuple; a side's own vertex order is the
+ * template order seen from its lowest-numbered adjacent element. */
+pp_status pp_host_derive_sides(int32_t dim, int32_t nelems, const int32_t* elem2verts,
+                               int32_t* nsides_out, int32_t** elem2sides_out,
+                               int32_t** side2verts_out);
+/* n^3 cubes on [0,length]^3, six positively oriented tets per cube (Kuhn split). */
+pp_status pp_host_kuhn_cube(int32_t n, double length, int32_t* nverts_out, double** coords_out,
+                            int32_t* nelems_out, int32_t** elem2verts_out);
+/* n^2 squares on [0,length]^2, two counter-clockwise triangles per square. */
+pp_status pp_host_plate(int32_t n, double length, int32_t* nverts_out, double** coords_out,
+                        int32_t* nelems_out, int32_t** elem2verts_out);
+void pp_host_free(void* p);
+
+/* ============================== particle structure ====================================== */
+
+typedef enum pp_ps_kind {
+  PP_PS_SCS = 0,  /* particle_structs/src/scs/SellCSigma.h  */
+  PP_PS_CSR = 1,  /* particle_structs/src/csr/CSR.hpp       */
+  PP_PS_CABM = 2, /* particle_structs/src/cabm/cabm.hpp (API-compatible, SCS storage engine) */
+  PP_PS_DPS = 3   /* particle_structs/src/dps/dps.hpp  (flat: parent array + mask)           */
+} pp_ps_kind;
+
+typedef enum pp_padding { PP_PAD_EVENLY = 0, PP_PAD_PROPORTIONALLY = 1, PP_PAD_INVERSELY = 2 } pp_padding;
+
+/* One entry per member of MemberTypes<...> (support/MemberTypes.h:21-60): scalar size in bytes
+ * (BaseType<T>::type) and number of scalars (BaseType<T>::size). */
+typedef struct pp_member_desc {
+  int32_t scalar_bytes;
+  int32_t ncomp;
+} pp_member_desc;
+
+/* Mirrors SCS_Input (scs/scs_input.hpp:4-36) and the constructor arguments
+ * (SellCSigma.h:66-71, CSR.hpp:37-44, dps.hpp:41-48). */
+typedef struct pp_ps_config {
+  int32_t kind;            /* pp_ps_kind */
+  int32_t team_size;       /* policy.team_size(): maximum chunk height C (SCS) */
+  int32_t sigma;           /* sorting window; INT_MAX = full sort */
+  int32_t V;               /* vertical slice width */
+  double shuffle_padding;  /* default 0.1  */
+  double extra_padding;    /* default 0.05 */
+  double minimize_size;    /* default 0.8  */
+  int32_t padding_strat;   /* pp_padding, default PP_PAD_EVENLY */
+  int32_t always_realloc;  /* default 0 */
+} pp_ps_config;
+void pp_ps_config_default(pp_ps_config* cfg, int32_t kind);
+
+/* Build a structure with `ne` elements and `np` particles.
+ *   ppe[ne]                particles per element
+ *   elem_gids[ne]          element global ids, or NULL
+ *   particle_elements[np]  parent element of each initial particle, or NULL
+ *   particle_info[nmembers] one array per member, each [ncomp][np] component-major, or NULL
+ * memspace tells where ppe / elem_gids / particle_elements / particle_info live. */
+pp_status pp_ps_create(const pp_ps_config* cfg, int32_t nmembers, const pp_member_desc* members,
+                       int32_t ne, int32_t np, const int32_t* ppe, const int64_t* elem_gids,
+                       const int32_t* particle_elements, const void* const* particle_info,
+                       int32_t memspace, pp_stream stream, pp_ps** out);
+pp_status pp_ps_destroy(pp_ps* ps);
+
+/* particle_structure.hpp:71-75 nElems / nPtcls / capacity / numRows */
+int32_t pp_ps_nelems(const pp_ps* ps);
+int32_t pp_ps_nptcls(const pp_ps* ps);
+int32_t pp_ps_capacity(const pp_ps* ps);
+int32_t pp_ps_numrows(const pp_ps* ps);
+int32_t pp_ps_kind_of(const pp_ps* ps);
+
+/* get<N>() (particle_structure.hpp:83-97): device base pointer and slot stride of member N.
+ * Invalidated by rebuild / migrate, exactly like the reference's Segment handles. */
+pp_status pp_ps_member(const pp_ps* ps, int32_t member, void** base_out, int64_t* stride_out);
+
+/* Slot geometry for user kernels (what SellCSigma::parallel_for iterates, SellCSigma.h:528-558).
+ * mask_bits: bit (slot & 31) of word (slot >> 5) is the particle_mask of the slot.
+ * slot_elem: int32[capacity] element of the row that owns each slot (materialised on demand). */
+typedef struct pp_ps_layout {
+  int32_t kind, C, V, nchunks, nslices, nrows, capacity, nelems, nptcls;
+  const int32_t* offsets;        /* [nslices+1]  (SCS) / [nelems+1] (CSR) */
+  const int32_t* slice_to_chunk; /* [nslices]    (SCS) */
+  const int32_t* row_to_element; /* [nrows]      (SCS) */
+  const int32_t* element_to_row; /* [nrows]      (SCS) */
+  const uint32_t* mask_bits;     /* [(capacity+31)/32] */
+  const int32_t* slot_elem;      /* [capacity] */
+} pp_ps_layout;
+pp_status pp_ps_get_layout(pp_ps* ps, pp_stream stream, pp_ps_layout* out);
+
+/* ============================== push ===================================================== */
+
+/* test/pseudoPushAndSearch.cpp:87-118: xtgt = x + distance*(dx,dy,dz) for masked slots */
+pp_status pp_push_constant(pp_ps* ps, const double* x, double* xtgt, int64_t stride,
+                           double distance, double dx, double dy, double dz, pp_stream stream);
+/* test/test_adj.cpp:550-562: tgt += distance*dir for masked slots */
+pp_status pp_push_direction(pp_ps* ps, double* tgt, const double* dir, int64_t stride,
+                            double distance, pp_stream stream);
+/* test/pseudoPushAndSearch.cpp:142-154 updatePtclPositions: x = xtgt; xtgt = 0 (all slots) */
+pp_status pp_update_positions(pp_ps* ps, double* x, double* xtgt, int64_t stride,
+                              pp_stream stream);
+
+/* ============================== search =================================================== */
+
+typedef enum pp_search_variant {
+  PP_SEARCH_NEW = 0,       /* adjacency.tpp:642 search_mesh (BCC or ray intersection, 2D/3D) */
+  PP_SEARCH_2D_LEGACY = 1, /* adjacency.hpp:1013 search_mesh_2d */
+  PP_SEARCH_3D_LEGACY = 2  /* adjacency.hpp:559 search_mesh (line-triangle + dual graph) */
+} pp_search_variant;
+
+typedef struct pp_search_args {
+  int32_t variant;               /* pp_search_variant */
+  const double* x_orig;          /* [3][stride] start positions  (x_ps_orig) */
+  const double* x_tgt;           /* [3][stride] target positions (x_ps_tgt)  */
+  int64_t stride;
+  int32_t* elem_ids;             /* [capacity] in/out parent element per slot */
+  int32_t elem_ids_empty;        /* !=0: behave as if elem_ids.size()==0 (seed from the row element) */
+  int32_t require_intersection;  /* PP_SEARCH_NEW only */
+  int32_t* inter_faces;          /* [capacity] or NULL (required when require_intersection / legacy 3D xface) */
+  double* inter_points;          /* [dim*capacity] AoS or NULL (legacy 3D: xpoints [3*capacity]) */
+  int32_t looplimit;             /* 0 = unlimited */
+} pp_search_args;
+
+typedef struct pp_search_stats {
+  int32_t found;        /* the reference's bool return value */
+  int32_t loops;        /* walk iterations the reference would have executed */
+  int32_t not_in_elem;  /* deleted by check_initial_parents (adjacency.tpp:73-145) */
+  int32_t not_found;    /* deleted by the loop limit */
+  int32_t aborted;      /* legacy 3D: particles whose origin is outside their element (reference aborts) */
+  int32_t active;       /* particles that entered the walk */
+  int64_t hops;         /* total element hops */
+} pp_search_stats;
+
+/* Replaces search_mesh / search_mesh_2d / legacy search_mesh: ONE fused kernel (setup, origin
+ * check, walk to completion, boundary handling), no per-iteration host round trip.
+ * stats_host may be NULL (fully asynchronous); otherwise the stream is synchronised and the
+ * counters copied out. */
+pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                         pp_search_stats* stats_host, pp_stream stream);
+/* Counters of the most recent search on this mesh handle (synchronises the stream). */
+pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host, pp_stream stream);
+
+/* Fused push + search: the push immediately followed by the new-API walk on the freshly pushed
+ * target, positions kept in registers (x_tgt is written once, never re-read).
+ *   push_from_orig == 0: x_tgt += distance*dir           (test/test_adj.cpp:550-562)
+ *   push_from_orig != 0: x_tgt  = x_orig + distance*dir  (the PIC form of
+ *                        test/pseudoPushAndSearch.cpp:104-114 with a per-particle direction)
+ * Same results as the separate push followed by pp_search_mesh. */
+pp_status pp_push_direction_search(pp_mesh* mesh, pp_ps* ps, const double* dir, double distance,
+                                   int32_t push_from_orig, const pp_search_args* args,
+                                   pp_search_stats* stats_host, pp_stream stream);
+/* Unfused PIC-form push: xtgt = x + distance*dir for masked slots. */
+pp_status pp_push_from(pp_ps* ps, const double* x, double* xtgt, const double* dir,
+                       int64_t stride, double distance, pp_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PUMIPIC_B200_H */

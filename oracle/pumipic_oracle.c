@@ -292,8 +292,9 @@ int orc_is_face_flipped_2d(const int ev[2], const int tv[3]) {
   return ev[1] != tv[idx];
 }
 
-static inline double dmin(double a, double b) { return a < b ? a : b; }
-static inline double dmax(double a, double b) { return a > b ? a : b; }
+/* Kokkos::min / Kokkos::max follow std::min / std::max: (b<a)?b:a and (a<b)?b:a */
+static inline double dmin(double a, double b) { return (b < a) ? b : a; }
+static inline double dmax(double a, double b) { return (a < b) ? b : a; }
 
 /* adjacency.tpp:152-178 ray_intersects_triangle.  face = 3 vertices x 3 coords */
 int orc_ray_intersects_triangle(const double face[9], const double orig[3], const double dest[3],

@@ -1,0 +1,12 @@
+"""pumi-pic_b200: B200-native implementation of PUMI-PIC's particle hot path.
+
+The product is libpumipic_b200.so (hand-written sm_100a CUDA behind the C ABI in
+include/pumipic_b200.h) plus the header-only C++ mirror of the reference API in cpp/.
+This Python package only binds the C ABI for tests and bench.py: torch tensors provide device
+memory and streams.  Import with importlib.import_module("pumi-pic_b200").
+"""
+from . import capi                                    # noqa: F401
+from .capi import PumipicError, lib                  # noqa: F401
+from .api import (Mesh, ParticleStructure, SearchResult, search_mesh, push_constant,  # noqa: F401
+                  push_direction, update_positions, push_direction_search, host_kuhn_cube,
+                  host_plate, host_derive_sides, push_from)

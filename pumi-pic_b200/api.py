@@ -1,0 +1,279 @@
+"""Python handles over the C ABI (tests / bench plumbing).  Device arrays are torch tensors."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+# ------------------------------------------------------------------ host utilities
+def host_derive_sides(dim, elem2verts):
+    ev = np.ascontiguousarray(elem2verts, np.int32)
+    ns = C.c_int32()
+    e2s = capi.c_i32p()
+    s2v = capi.c_i32p()
+    check(lib().pp_host_derive_sides(dim, ev.shape[0], ev.ctypes.data_as(capi.c_i32p),
+                                     C.byref(ns), C.byref(e2s), C.byref(s2v)))
+    a = np.ctypeslib.as_array(e2s, shape=(ev.shape[0], dim + 1)).copy()
+    b = np.ctypeslib.as_array(s2v, shape=(ns.value, dim)).copy()
+    lib().pp_host_free(e2s)
+    lib().pp_host_free(s2v)
+    return a, b
+
+
+def _host_gen(fn, n, length, dim):
+    nv, ne = C.c_int32(), C.c_int32()
+    co = capi.c_dp()
+    ev = capi.c_i32p()
+    check(fn(n, length, C.byref(nv), C.byref(co), C.byref(ne), C.byref(ev)))
+    coords = np.ctypeslib.as_array(co, shape=(nv.value, dim)).copy()
+    elems = np.ctypeslib.as_array(ev, shape=(ne.value, dim + 1)).copy()
+    lib().pp_host_free(co)
+    lib().pp_host_free(ev)
+    return coords, elems
+
+
+def host_kuhn_cube(n, length=1.0):
+    return _host_gen(lib().pp_host_kuhn_cube, n, length, 3)
+
+
+def host_plate(n, length=1.0):
+    return _host_gen(lib().pp_host_plate, n, length, 2)
+
+
+# ------------------------------------------------------------------ mesh
+class Mesh:
+    """pumipic::Mesh / o::Mesh stand-in: owns a pp_mesh built from host numpy arrays."""
+
+    def __init__(self, dim, coords, elem2verts, elem2sides, side2verts, elem_class=None):
+        coords = np.ascontiguousarray(coords, np.float64)
+        ev = np.ascontiguousarray(elem2verts, np.int32)
+        es = np.ascontiguousarray(elem2sides, np.int32)
+        sv = np.ascontiguousarray(side2verts, np.int32)
+        cls = None if elem_class is None else np.ascontiguousarray(elem_class, np.int32)
+        d = capi.MeshDesc(dim, coords.shape[0], ev.shape[0], sv.shape[0], coords.ctypes.data,
+                          ev.ctypes.data, es.ctypes.data, sv.ctypes.data,
+                          0 if cls is None else cls.ctypes.data, capi.PP_HOST)
+        self.h = C.c_void_p()
+        check(lib().pp_mesh_create(C.byref(d), _stream(), C.byref(self.h)))
+        self.dim = dim
+        self.nelems = ev.shape[0]
+        self.nverts = coords.shape[0]
+        self.nsides = sv.shape[0]
+
+    def info(self):
+        i = capi.MeshInfo()
+        check(lib().pp_mesh_get_info(self.h, C.byref(i)))
+        return i
+
+    def arrays(self):
+        """Derived device arrays copied back to host numpy (test helper)."""
+        torch = _torch()
+        a = capi.MeshArrays()
+        check(lib().pp_mesh_get_arrays(self.h, C.byref(a)))
+        torch.cuda.synchronize()
+
+        def fetch(ptr, n, dtype):
+            out = np.empty(n, dtype)
+            rc = torch.cuda.cudart().cudaMemcpy(out.ctypes.data, ptr, out.nbytes, 2)
+            assert int(rc) == 0
+            return out
+        res = {
+            "measure": fetch(a.measure, self.nelems, np.float64),
+            "exposed": fetch(a.exposed, self.nsides, np.int8),
+            "side2elem": fetch(a.side2elem, 2 * self.nsides, np.int32).reshape(-1, 2),
+            "dual_off": fetch(a.dual_off, self.nelems + 1, np.int32),
+        }
+        res["dual"] = fetch(a.dual, int(res["dual_off"][-1]), np.int32)
+        return res
+
+    def set_picpart(self, safe, owner, self_rank):
+        s = np.ascontiguousarray(safe, np.int32)
+        o = np.ascontiguousarray(owner, np.int32)
+        check(lib().pp_mesh_set_picpart(self.h, _np_ptr(s), _np_ptr(o), self_rank, capi.PP_HOST,
+                                        _stream()))
+        _torch().cuda.synchronize()
+
+    def __del__(self):
+        try:
+            lib().pp_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ particle structure
+_NP_OF = {(8, "f"): np.float64, (4, "f"): np.float32, (4, "i"): np.int32, (8, "i"): np.int64}
+
+
+class ParticleStructure:
+    """ps::ParticleStructure<MemberTypes<...>> stand-in.
+
+    members: list of (numpy dtype, ncomp), e.g. [(np.float64, 3), (np.float64, 3), (np.int32, 1)]
+    """
+
+    def __init__(self, kind, members, ppe, elem_gids=None, particle_elements=None,
+                 particle_info=None, team_size=32, sigma=0x7fffffff, V=1024, config=None):
+        self.members = [(np.dtype(dt), int(nc)) for dt, nc in members]
+        ppe = np.ascontiguousarray(ppe, np.int32)
+        cfg = capi.PsConfig()
+        lib().pp_ps_config_default(C.byref(cfg), kind)
+        cfg.team_size, cfg.sigma, cfg.V = team_size, sigma, V
+        for k, v in (config or {}).items():
+            setattr(cfg, k, v)
+        md = (capi.MemberDesc * len(members))(*[capi.MemberDesc(dt.itemsize, nc)
+                                                for dt, nc in self.members])
+        np_ = int(ppe.sum()) if particle_elements is None else len(particle_elements)
+        gids = None if elem_gids is None else np.ascontiguousarray(elem_gids, np.int64)
+        pel = None if particle_elements is None else np.ascontiguousarray(particle_elements, np.int32)
+        info = None
+        keep = []
+        if particle_info is not None:
+            info = (C.c_void_p * len(members))()
+            for i, a in enumerate(particle_info):
+                a = np.ascontiguousarray(a, self.members[i][0])
+                keep.append(a)
+                info[i] = a.ctypes.data
+        self.h = C.c_void_p()
+        check(lib().pp_ps_create(C.byref(cfg), len(members), md, ppe.shape[0], np_, _np_ptr(ppe),
+                                 None if gids is None else _np_ptr(gids),
+                                 None if pel is None else _np_ptr(pel), info, capi.PP_HOST,
+                                 _stream(), C.byref(self.h)))
+
+    nelems = property(lambda self: lib().pp_ps_nelems(self.h))
+    nptcls = property(lambda self: lib().pp_ps_nptcls(self.h))
+    capacity = property(lambda self: lib().pp_ps_capacity(self.h))
+    numrows = property(lambda self: lib().pp_ps_numrows(self.h))
+
+    def get(self, i):
+        """Segment of member i as a torch view [ncomp, stride] over the structure's own memory."""
+        torch = _torch()
+        base = C.c_void_p()
+        stride = C.c_int64()
+        check(lib().pp_ps_member(self.h, i, C.byref(base), C.byref(stride)))
+        dt, nc = self.members[i]
+        tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+               np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}[dt]
+        n = nc * stride.value
+        if n == 0:
+            return torch.empty((nc, 0), dtype=tdt, device="cuda")
+        return _tensor_from_ptr(base.value, (nc, stride.value), tdt, self)
+
+    def layout(self):
+        lay = capi.PsLayout()
+        check(lib().pp_ps_get_layout(self.h, _stream(), C.byref(lay)))
+        return lay
+
+    def slot_elem_and_mask(self):
+        """(slot_elem[cap] int32, mask[cap] uint8) on the host (test helper)."""
+        torch = _torch()
+        lay = self.layout()
+        torch.cuda.synchronize()
+        cap = lay.capacity
+        if cap == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.uint8)
+        se = _tensor_from_ptr(lay.slot_elem, (cap,), torch.int32, self).cpu().numpy()
+        nw = (cap + 31) // 32
+        mb = _tensor_from_ptr(lay.mask_bits, (nw,), torch.int32, self).cpu().numpy().view(np.uint32)
+        bits = ((mb[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(np.uint8)
+        return se, bits.ravel()[:cap].copy()
+
+    def __del__(self):
+        try:
+            lib().pp_ps_destroy(self.h)
+        except Exception:
+            pass
+
+
+class _CudaArrayView:
+    """Exposes foreign device memory through __cuda_array_interface__ so torch can wrap it."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": tuple(shape),
+                                         "typestr": typestr, "version": 2, "strides": None}
+
+
+def _tensor_from_ptr(ptr, shape, tdt, owner):
+    torch = _torch()
+    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4",
+               torch.int64: "<i8"}[tdt]
+    return torch.as_tensor(_CudaArrayView(ptr, shape, typestr, owner), device="cuda")
+
+
+# ------------------------------------------------------------------ hot path calls
+class SearchResult:
+    def __init__(self, stats):
+        for f, _ in capi.SearchStats._fields_:
+            setattr(self, f, getattr(stats, f))
+
+    def __repr__(self):
+        return "SearchResult(" + ", ".join("%s=%s" % (f, getattr(self, f))
+                                           for f, _ in capi.SearchStats._fields_) + ")"
+
+
+def _search_args(x_orig, x_tgt, elem_ids, elem_ids_empty, variant, require_intersection,
+                 inter_faces, inter_points, looplimit):
+    return capi.SearchArgs(variant, _ptr(x_orig).value, _ptr(x_tgt).value, x_tgt.shape[1],
+                           _ptr(elem_ids).value, int(bool(elem_ids_empty)),
+                           int(bool(require_intersection)), _ptr(inter_faces).value,
+                           _ptr(inter_points).value, looplimit)
+
+
+def search_mesh(mesh, ps, x_orig, x_tgt, elem_ids, elem_ids_empty=False,
+                variant=capi.PP_SEARCH_NEW, require_intersection=False, inter_faces=None,
+                inter_points=None, looplimit=0, sync=True):
+    a = _search_args(x_orig, x_tgt, elem_ids, elem_ids_empty, variant, require_intersection,
+                     inter_faces, inter_points, looplimit)
+    st = capi.SearchStats()
+    check(lib().pp_search_mesh(mesh.h, ps.h, C.byref(a), C.byref(st) if sync else None, _stream()))
+    return SearchResult(st) if sync else None
+
+
+def push_direction_search(mesh, ps, direction, distance, x_orig, x_tgt, elem_ids,
+                          elem_ids_empty=False, require_intersection=False, inter_faces=None,
+                          inter_points=None, looplimit=0, sync=True, from_orig=False):
+    a = _search_args(x_orig, x_tgt, elem_ids, elem_ids_empty, capi.PP_SEARCH_NEW,
+                     require_intersection, inter_faces, inter_points, looplimit)
+    st = capi.SearchStats()
+    check(lib().pp_push_direction_search(mesh.h, ps.h, _ptr(direction), distance,
+                                         int(bool(from_orig)), C.byref(a),
+                                         C.byref(st) if sync else None, _stream()))
+    return SearchResult(st) if sync else None
+
+
+def push_constant(ps, x, xtgt, distance, d):
+    check(lib().pp_push_constant(ps.h, _ptr(x), _ptr(xtgt), x.shape[1], distance, d[0], d[1], d[2],
+                                 _stream()))
+
+
+def push_direction(ps, tgt, direction, distance):
+    check(lib().pp_push_direction(ps.h, _ptr(tgt), _ptr(direction), tgt.shape[1], distance,
+                                  _stream()))
+
+
+def update_positions(ps, x, xtgt):
+    check(lib().pp_update_positions(ps.h, _ptr(x), _ptr(xtgt), x.shape[1], _stream()))
+
+
+def push_from(ps, x, xtgt, direction, distance):
+    check(lib().pp_push_from(ps.h, _ptr(x), _ptr(xtgt), _ptr(direction), x.shape[1], distance,
+                             _stream()))

@@ -1,0 +1,146 @@
+"""ctypes view of include/pumipic_b200.h (the C ABI of libpumipic_b200.so).
+
+Thin plumbing only: structs, prototypes and a status check.  PyTorch supplies device memory
+(tensor.data_ptr()) and streams; no compute happens in Python.  The library must exist:
+there is no CPU fallback and importing this module without the built .so raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpumipic_b200.so")
+
+PP_OK = 0
+PP_HOST, PP_DEVICE = 0, 1
+PP_PS_SCS, PP_PS_CSR, PP_PS_CABM, PP_PS_DPS = 0, 1, 2, 3
+PP_SEARCH_NEW, PP_SEARCH_2D_LEGACY, PP_SEARCH_3D_LEGACY = 0, 1, 2
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_dp = C.POINTER(C.c_double)
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("nverts", C.c_int32), ("nelems", C.c_int32),
+                ("nsides", C.c_int32), ("coords", C.c_void_p), ("elem2verts", C.c_void_p),
+                ("elem2sides", C.c_void_p), ("side2verts", C.c_void_p),
+                ("elem_class", C.c_void_p), ("memspace", C.c_int32)]
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("nverts", C.c_int32), ("nelems", C.c_int32),
+                ("nsides", C.c_int32), ("tol", C.c_double), ("min_measure", C.c_double),
+                ("n_exposed_sides", C.c_int32), ("walk_table_bytes", C.c_int64)]
+
+
+class MeshArrays(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("coords", "elem2verts", "elem2sides", "side2verts", "elem_class", "measure",
+                 "exposed", "side2elem", "dual_off", "dual")]
+
+
+class MemberDesc(C.Structure):
+    _fields_ = [("scalar_bytes", C.c_int32), ("ncomp", C.c_int32)]
+
+
+class PsConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("team_size", C.c_int32), ("sigma", C.c_int32),
+                ("V", C.c_int32), ("shuffle_padding", C.c_double), ("extra_padding", C.c_double),
+                ("minimize_size", C.c_double), ("padding_strat", C.c_int32),
+                ("always_realloc", C.c_int32)]
+
+
+class PsLayout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("kind", "C", "V", "nchunks", "nslices", "nrows", "capacity", "nelems", "nptcls")] + \
+               [(n, C.c_void_p) for n in
+                ("offsets", "slice_to_chunk", "row_to_element", "element_to_row", "mask_bits",
+                 "slot_elem")]
+
+
+class SearchArgs(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("x_orig", C.c_void_p), ("x_tgt", C.c_void_p),
+                ("stride", C.c_int64), ("elem_ids", C.c_void_p), ("elem_ids_empty", C.c_int32),
+                ("require_intersection", C.c_int32), ("inter_faces", C.c_void_p),
+                ("inter_points", C.c_void_p), ("looplimit", C.c_int32)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("found", C.c_int32), ("loops", C.c_int32), ("not_in_elem", C.c_int32),
+                ("not_found", C.c_int32), ("aborted", C.c_int32), ("active", C.c_int32),
+                ("hops", C.c_int64)]
+
+
+# every symbol include/pumipic_b200.h declares: name -> (restype, argtypes)
+PROTOTYPES = {
+    "pp_last_error": (C.c_char_p, []),
+    "pp_version": (C.c_char_p, []),
+    "pp_build_arch": (C.c_char_p, []),
+    "pp_mesh_create": (C.c_int, [C.POINTER(MeshDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pp_mesh_destroy": (C.c_int, [C.c_void_p]),
+    "pp_mesh_get_info": (C.c_int, [C.c_void_p, C.POINTER(MeshInfo)]),
+    "pp_mesh_get_arrays": (C.c_int, [C.c_void_p, C.POINTER(MeshArrays)]),
+    "pp_mesh_set_picpart": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_void_p]),
+    "pp_host_derive_sides": (C.c_int, [C.c_int32, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i32p),
+                                       C.POINTER(c_i32p)]),
+    "pp_host_kuhn_cube": (C.c_int, [C.c_int32, C.c_double, c_i32p, C.POINTER(c_dp), c_i32p,
+                                    C.POINTER(c_i32p)]),
+    "pp_host_plate": (C.c_int, [C.c_int32, C.c_double, c_i32p, C.POINTER(c_dp), c_i32p,
+                                C.POINTER(c_i32p)]),
+    "pp_host_free": (None, [C.c_void_p]),
+    "pp_ps_config_default": (None, [C.POINTER(PsConfig), C.c_int32]),
+    "pp_ps_create": (C.c_int, [C.POINTER(PsConfig), C.c_int32, C.POINTER(MemberDesc), C.c_int32,
+                               C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                               C.POINTER(C.c_void_p)]),
+    "pp_ps_destroy": (C.c_int, [C.c_void_p]),
+    "pp_ps_nelems": (C.c_int32, [C.c_void_p]),
+    "pp_ps_nptcls": (C.c_int32, [C.c_void_p]),
+    "pp_ps_capacity": (C.c_int32, [C.c_void_p]),
+    "pp_ps_numrows": (C.c_int32, [C.c_void_p]),
+    "pp_ps_kind_of": (C.c_int32, [C.c_void_p]),
+    "pp_ps_member": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), c_i64p]),
+    "pp_ps_get_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PsLayout)]),
+    "pp_push_constant": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                   C.c_double, C.c_double, C.c_double, C.c_void_p]),
+    "pp_push_direction": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                    C.c_void_p]),
+    "pp_update_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pp_search_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs),
+                                 C.POINTER(SearchStats), C.c_void_p]),
+    "pp_search_last_stats": (C.c_int, [C.c_void_p, C.POINTER(SearchStats), C.c_void_p]),
+    "pp_push_direction_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                           C.c_int32, C.POINTER(SearchArgs),
+                                           C.POINTER(SearchStats), C.c_void_p]),
+    "pp_push_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                               C.c_double, C.c_void_p]),
+}
+
+_lib = None
+
+
+class PumipicError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libpumipic_b200.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PumipicError(
+                "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != PP_OK:
+        raise PumipicError("pumipic_b200 status %d: %s" % (status, lib().pp_last_error().decode()))

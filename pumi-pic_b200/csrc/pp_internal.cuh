@@ -1,0 +1,220 @@
+// pp_internal.cuh -- shared internals of libpumipic_b200.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "pumipic_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+void pp_set_error(const char* fmt, ...);
+
+#define PP_CUDA(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      pp_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                     \
+                   cudaGetErrorString(e__));                                              \
+      return PP_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define PP_REQUIRE(cond, msg)                                                             \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      pp_set_error("%s:%d: %s", __FILE__, __LINE__, msg);                                 \
+      return PP_ERR_INVALID;                                                              \
+    }                                                                                     \
+  } while (0)
+
+#define PP_TRY(call)                                                                      \
+  do {                                                                                    \
+    pp_status s__ = (call);                                                               \
+    if (s__ != PP_OK) return s__;                                                         \
+  } while (0)
+
+#define PP_KERNEL_CHECK() PP_CUDA(cudaGetLastError())
+
+static inline int pp_div_up(long a, long b) { return (int)((a + b - 1) / b); }
+
+// Stream-ordered device allocation helpers.
+template <class T>
+static inline pp_status pp_dev_alloc(T** p, size_t n, cudaStream_t s) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  PP_CUDA(cudaMallocAsync((void**)p, n * sizeof(T), s));
+  return PP_OK;
+}
+template <class T>
+static inline void pp_dev_free(T* p, cudaStream_t s) {
+  if (p) cudaFreeAsync((void*)p, s);
+}
+// copy `n` elements from `src` (host or device per memspace) into fresh device memory
+template <class T>
+static inline pp_status pp_dev_import(T** dst, const T* src, size_t n, int memspace,
+                                      cudaStream_t s) {
+  PP_TRY(pp_dev_alloc(dst, n, s));
+  if (n && src)
+    PP_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T),
+                            memspace == PP_HOST ? cudaMemcpyHostToDevice
+                                                : cudaMemcpyDeviceToDevice, s));
+  return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// walk records: everything one hop of the adjacency walk needs, in one aligned gather.
+// ------------------------------------------------------------------------------------------
+// adj[f] >= 0 : element across local side f
+// adj[f] <  0 : side is exposed (domain boundary); side id = -adj[f]-1
+// codes: 8 bits per local side f:
+//    3D: bits0-1,2-3,4-5 = tet-local index of the side's own vertices fv0,fv1,fv2
+//        bit6 = isFaceFlipped (pumipic_utils.hpp:501-507), bit7 = legacy flip (adjacency.hpp:662-664)
+//    2D: bits0-1,2-3 = triangle-local index of ev0,ev1; bit6 = isFaceFlipped (utils.hpp:495-499)
+// aux: owner rank of the element if it is NOT safe on this PICpart, else -1 (pp_mesh_set_picpart)
+struct __align__(16) PPTetRec {   // 128 B = one L2 line
+  double c[12];                   // 4 vertices x 3 coordinates
+  double vol;                     // measure_elements_real
+  int adj[4];
+  unsigned codes;
+  int aux;
+};
+struct __align__(16) PPTriRec {   // 96 B = three 32 B sectors
+  double c[6];                    // 3 vertices x 2 coordinates
+  double area;
+  int adj[3];
+  unsigned codes;
+  int cls;                        // element class id (ellipticalPush)
+  int aux;
+  int pad[2];
+};
+static_assert(sizeof(PPTetRec) == 128, "tet walk record must be 128 bytes");
+static_assert(sizeof(PPTriRec) == 96, "tri walk record must be 96 bytes");
+
+struct pp_mesh {
+  int dim, nverts, nelems, nsides;
+  double tol, min_measure;
+  int n_exposed;
+  int self_rank;
+  // device arrays (owned)
+  double* coords;
+  int* elem2verts;
+  int* elem2sides;
+  int* side2verts;
+  int* elem_class;
+  double* measure;
+  int8_t* exposed;
+  int* side2elem;   // [2*nsides] (lo, hi|-1)
+  int* dual_off;
+  int* dual;
+  int* safe;        // [nelems] or null
+  int* owner;       // [nelems] or null
+  void* walk;       // PPTetRec[nelems] or PPTriRec[nelems]
+  // search scratch
+  int* stats_dev;   // device counters (see SearchCounters)
+};
+
+// device-side counters of one search
+struct SearchCounters {
+  int max_iters;
+  int not_in_elem;
+  int not_found;
+  int aborted;
+  int active;
+  int pad;
+  unsigned long long hops;
+};
+
+// ------------------------------------------------------------------------------------------
+// particle structure
+// ------------------------------------------------------------------------------------------
+struct PsView {  // what kernels need to map slot -> (row element, mask)
+  int kind;
+  int capacity;
+  const uint32_t* mask_bits;
+  const int* slot_elem;  // DPS / CSR (and materialised SCS): element per slot, or null
+  // SCS geometry
+  const int* offsets;
+  const int* slice_to_chunk;
+  const int* row_to_element;
+  const int* tile_slice;  // slice holding the first slot of each 32-slot tile
+  int C;
+  int nslices;
+};
+
+struct pp_ps {
+  pp_ps_config cfg;
+  int nmembers;
+  std::vector<pp_member_desc> members;
+  int nelems, nptcls, capacity, nrows;
+  long stride;              // allocated slots per member component (>= capacity)
+  std::vector<void*> data;  // one device array per member: [ncomp][stride]
+  std::vector<void*> swap;  // SCS double buffer
+  long swap_stride;
+  uint32_t* mask_bits;
+  long mask_words_alloc;
+  int* slot_elem;           // [capacity] (DPS parent array; CSR/SCS materialised map)
+  bool slot_elem_valid;
+  // SCS
+  int C, V, nchunks, nslices;
+  int* offsets;
+  int* slice_to_chunk;
+  int* row_to_element;
+  int* element_to_row;
+  int* tile_slice;
+  int64_t* elem_gids;       // [nelems] or null
+  PsView view() const;
+};
+
+// slot -> (element of owning row, mask).  Works for every structure kind.
+__device__ __forceinline__ bool pp_slot_lookup(const PsView& v, int slot, int& elem) {
+  const uint32_t w = __ldg(v.mask_bits + (slot >> 5));
+  const bool m = (w >> (slot & 31)) & 1u;
+  if (v.slot_elem) {
+    elem = __ldg(v.slot_elem + slot);
+  } else {
+    int S = __ldg(v.tile_slice + (slot >> 5));
+    while (slot >= __ldg(v.offsets + S + 1)) ++S;
+    const int r = (slot - __ldg(v.offsets + S)) % v.C;
+    elem = __ldg(v.row_to_element + __ldg(v.slice_to_chunk + S) * v.C + r);
+  }
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// Omega_h small-vector arithmetic, same evaluation order as the reference's CPU path.
+// The library is compiled with -fmad=false so no multiply-add is ever contracted.
+// ------------------------------------------------------------------------------------------
+struct d3 { double x, y, z; };
+struct d2 { double x, y; };
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ d3 cross3(d3 a, d3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ double dot3(d3 a, d3 b) {
+  double c = a.x * b.x;
+  c = c + a.y * b.y;
+  c = c + a.z * b.z;
+  return c;
+}
+__device__ __forceinline__ double norm3(d3 a) { return sqrt(dot3(a, a)); }
+__device__ __forceinline__ d2 operator-(d2 a, d2 b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ double dot2(d2 a, d2 b) {
+  double c = a.x * b.x;
+  c = c + a.y * b.y;
+  return c;
+}
+__device__ __forceinline__ double cross2(d2 a, d2 b) { return a.x * b.y - a.y * b.x; }
+
+// Omega_h::are_close(a, 0, tol, tol) || a > 0   (pumipic_utils.hpp:78-86)
+__device__ __forceinline__ bool pp_gtez(double a, double tol) {
+  const double am = fabs(a);
+  bool close;
+  if (am <= tol) close = true;          // both |a| and |0| under the floor
+  else close = (am / am) <= tol;        // |0-a| / max(|a|,0) = 1 <= tol
+  return close || a > 0;
+}

@@ -1,0 +1,593 @@
+// pp_search.cu -- particle-to-element adjacency search, one fused kernel per call.
+//
+// Replaces (all in src/): pumipic_adjacency.tpp search_mesh :642 / trace_particle_through_mesh
+// :461 (setInitial :504-522, finishUnmoved :525-533, initializeIntersection :535-549,
+// check_initial_parents :73-145, find_exit_face :232-364, check_model_intersection :366-387,
+// set_new_element :390-416, the per-iteration get_min :568-572 and the loop-limit sweep
+// :584-606); pumipic_adjacency.hpp search_mesh_2d :1013-1158 and the legacy 3D search_mesh
+// :559-768.  The reference launches 3 kernels + 1 device->host reduction per walk iteration
+// over the whole capacity; here each thread owns one slot and walks to completion, every hop
+// being ONE aligned gather of a packed walk record (pp_internal.cuh).  Arithmetic follows the
+// reference operation by operation (the library is built with -fmad=false) so element ids are
+// bit-identical to the CPU oracle.
+#include <type_traits>
+
+#include "pp_internal.cuh"
+
+namespace {
+
+enum Mode { M_BCC = 0, M_RAY = 1, M_LEG2D = 2, M_LEG3D = 3 };
+
+struct SearchParams {
+  PsView ps;
+  const void* walk;
+  const double* xo;
+  const double* xt;
+  long stride;
+  int* elem_ids;
+  int ids_empty;
+  int* inter_faces;
+  double* inter_points;
+  int looplimit;
+  double tol;
+  int nelems;
+  SearchCounters* counters;
+  // fused direction push (test_adj.cpp:550-562): xt += distance*dir before the walk
+  const double* dir;
+  double distance;
+  double* xt_rw;
+  int push_from_orig;   // 1: xt = xo + distance*dir (PIC form), 0: xt += distance*dir (test_adj)
+  // legacy 3D fallback (adjacency.hpp:726 indexes the dual graph by face id)
+  const int* elem2sides;
+  const int* dual;
+  int ndual;
+};
+
+constexpr double kEps = 1e-10;  // pumipic_constants.hpp:6
+
+// ---------------------------------------------------------------- record loads
+struct Tet {
+  d3 M[4];
+  double vol;
+  int adj[4];
+  unsigned codes;
+  int aux;
+};
+struct Tri {
+  d2 M[3];
+  double area;
+  int adj[3];
+  unsigned codes;
+  int cls, aux;
+};
+
+__device__ __forceinline__ void load_rec(const void* walk, int E, Tet& t) {
+  const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const PPTetRec*>(walk) + E);
+  const double2 a0 = __ldg(p + 0), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+  const double2 a3 = __ldg(p + 3), a4 = __ldg(p + 4), a5 = __ldg(p + 5);
+  const int4 q6 = __ldg(reinterpret_cast<const int4*>(p + 6));
+  const int4 q7 = __ldg(reinterpret_cast<const int4*>(p + 7));
+  t.M[0] = {a0.x, a0.y, a1.x};
+  t.M[1] = {a1.y, a2.x, a2.y};
+  t.M[2] = {a3.x, a3.y, a4.x};
+  t.M[3] = {a4.y, a5.x, a5.y};
+  t.vol = __hiloint2double(q6.y, q6.x);
+  t.adj[0] = q6.z; t.adj[1] = q6.w; t.adj[2] = q7.x; t.adj[3] = q7.y;
+  t.codes = (unsigned)q7.z;
+  t.aux = q7.w;
+}
+__device__ __forceinline__ void load_rec(const void* walk, int E, Tri& t) {
+  const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const PPTriRec*>(walk) + E);
+  const double2 a0 = __ldg(p + 0), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+  const int4 q3 = __ldg(reinterpret_cast<const int4*>(p + 3));
+  const int4 q4 = __ldg(reinterpret_cast<const int4*>(p + 4));
+  t.M[0] = {a0.x, a0.y};
+  t.M[1] = {a1.x, a1.y};
+  t.M[2] = {a2.x, a2.y};
+  t.area = __hiloint2double(q3.y, q3.x);
+  t.adj[0] = q3.z; t.adj[1] = q3.w; t.adj[2] = q4.x;
+  t.codes = (unsigned)q4.y;
+  t.cls = q4.z;
+  t.aux = q4.w;
+}
+
+// ---------------------------------------------------------------- barycentric coordinates
+// adjacency.tpp:41-69 barycentric_tet.  Faces (0,2,1),(0,1,3),(1,2,3),(2,0,3):
+// vals[f] = (p - a) . cross(c - a, b - a);  bcc = (1/vol) * vals  (sums to 6)
+__device__ __forceinline__ void bcc_tet(const Tet& t, d3 p, double bcc[4]) {
+  const d3 n0 = cross3(t.M[1] - t.M[0], t.M[2] - t.M[0]);
+  const d3 n1 = cross3(t.M[3] - t.M[0], t.M[1] - t.M[0]);
+  const d3 n2 = cross3(t.M[3] - t.M[1], t.M[2] - t.M[1]);
+  const d3 n3 = cross3(t.M[3] - t.M[2], t.M[0] - t.M[2]);
+  const d3 p0 = p - t.M[0];
+  double v[4];
+  v[0] = dot3(p0, n0);
+  v[1] = dot3(p0, n1);
+  v[2] = dot3(p - t.M[1], n2);
+  v[3] = dot3(p - t.M[2], n3);
+  if (t.vol > 0) {
+    const double inv = 1.0 / t.vol;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bcc[i] = inv * v[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bcc[i] = -1;
+  }
+}
+// adjacency.hpp:97-133 find_barycentric_tet: same vals, own vol6 (> 1e-20), sums to 1
+__device__ __forceinline__ bool bcc_tet_legacy(const Tet& t, d3 p, double bcc[4]) {
+  const d3 n0 = cross3(t.M[1] - t.M[0], t.M[2] - t.M[0]);
+  const d3 n1 = cross3(t.M[3] - t.M[0], t.M[1] - t.M[0]);
+  const d3 n2 = cross3(t.M[3] - t.M[1], t.M[2] - t.M[1]);
+  const d3 n3 = cross3(t.M[3] - t.M[2], t.M[0] - t.M[2]);
+  const d3 p0 = p - t.M[0];
+  double v[4];
+  v[0] = dot3(p0, n0);
+  v[1] = dot3(p0, n1);
+  v[2] = dot3(p - t.M[1], n2);
+  v[3] = dot3(p - t.M[2], n3);
+  const double vol6 = dot3(t.M[3] - t.M[0], n0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) bcc[i] = -1;
+  if (!(vol6 > 1.0e-20)) return false;
+  const double inv = 1.0 / vol6;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) bcc[i] = inv * v[i];
+  return true;
+}
+// adjacency.tpp:23-39 barycentric_tri: edges (0,1),(1,2),(2,0)
+__device__ __forceinline__ void bcc_tri(const Tri& t, d2 p, double bcc[3]) {
+  bcc[0] = (cross2(t.M[1] - t.M[0], p - t.M[0]) / 2.0) / t.area;
+  bcc[1] = (cross2(t.M[2] - t.M[1], p - t.M[1]) / 2.0) / t.area;
+  bcc[2] = (cross2(t.M[0] - t.M[2], p - t.M[2]) / 2.0) / t.area;
+}
+template <int N>
+__device__ __forceinline__ bool all_positive(const double* b, double tol) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < N; ++i) ok = ok && pp_gtez(b[i], tol);
+  return ok;
+}
+// pumipic_utils.hpp:125-136 min_index (first strict minimum)
+__device__ __forceinline__ int min_index4(const double* a) {
+  int ind = 0;
+  double mn = a[0];
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (mn > a[i]) { mn = a[i]; ind = i; }
+  return ind;
+}
+// pumipic_utils.hpp:138-149 max_index (first strict maximum)
+__device__ __forceinline__ int max_index4(const double* a) {
+  int ind = 0;
+  double mx = a[0];
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (mx < a[i]) { mx = a[i]; ind = i; }
+  return ind;
+}
+// pumipic_utils.hpp:88-92 min3
+__device__ __forceinline__ int min3(const double* a) {
+  int idx = (a[0] < a[1]) ? 0 : 1;
+  idx = (a[idx] < a[2]) ? idx : 2;
+  return idx;
+}
+
+// ---------------------------------------------------------------- intersections
+// Kokkos::min / Kokkos::max follow std::min / std::max (matters only for NaN operands)
+__device__ __forceinline__ double kmin(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double kmax(double a, double b) { return (a < b) ? b : a; }
+// adjacency.tpp:152-178 ray_intersects_triangle; dir and seg_length hoisted by the caller
+__device__ __forceinline__ bool ray_tri(d3 V0, d3 V1, d3 V2, d3 orig, d3 dir, double tol,
+                                        int flip, d3& xp, double& dproj, double& closeness) {
+  const d3 edge1 = (flip ? V1 : V2) - V0;   // faceVerts[2-flip]
+  const d3 edge2 = (flip ? V2 : V1) - V0;   // faceVerts[flip+1]
+  const d3 fnorm = cross3(edge2, edge1);
+  const d3 pvec = cross3(dir, edge2);
+  dproj = dot3(dir, fnorm);
+  const double invdet = 1.0 / dproj;
+  const d3 tvec = orig - V0;
+  const double u = invdet * dot3(tvec, pvec);
+  const d3 qvec = cross3(tvec, edge1);
+  const double v = invdet * dot3(dir, qvec);
+  const double t = invdet * dot3(edge2, qvec);
+  xp = {orig.x + dir.x * t, orig.y + dir.y * t, orig.z + dir.z * t};
+  closeness = kmax(kmax(kmin(fabs(u), fabs(1 - u)), kmin(fabs(v), fabs(1 - v))),
+                   kmin(fabs(u + v), fabs(1 - u - v)));
+  return (dproj >= tol) && (t >= -tol) && (u >= -tol) && (v >= -tol) && (u + v <= 1.0 + 2 * tol);
+}
+// adjacency.tpp:204-218 line_edge_2d
+__device__ __forceinline__ bool line_edge(d2 E0, d2 E1, d2 orig, d2 dest, double tol, int flip,
+                                          d2& xp) {
+  const d2 A = flip ? E1 : E0;  // edgeVerts[vtx1 = flip]
+  const d2 B = flip ? E0 : E1;  // edgeVerts[vtx2 = !flip]
+  const d2 path = dest - orig;
+  const d2 edge = B - A;
+  const d2 nrm = {-edge.y, edge.x};
+  const d2 nrmp = {-path.y, path.x};
+  const double det = -dot2(nrm, path);
+  const d2 rel = orig - A;
+  const double s = dot2(nrmp, rel);
+  const double t = dot2(nrm, rel);
+  const double r = t / det;
+  xp = {orig.x + r * path.x, orig.y + r * path.y};
+  return det >= tol && s >= -tol && s <= det + tol && t >= -tol && t <= det + tol;
+}
+// adjacency.hpp:163-183 find_barycentric_tri_simple
+__device__ __forceinline__ bool bcc_tri_simple(d3 a, d3 b, d3 c, d3 xp, double bc[3]) {
+  const d3 ba = b - a, ca = c - a;
+  d3 cr = cross3(ba, ca);
+  cr = {cr.x * (1 / 2.0), cr.y * (1 / 2.0), cr.z * (1 / 2.0)};
+  const double len = norm3(cr);
+  const d3 nrm = {cr.x / len, cr.y / len, cr.z / len};
+  const double area = dot3(nrm, cr);
+  if (fabs(area) < 1e-20) return false;
+  const double fac = 1 / (area * 2.0);
+  const d3 xa = xp - a;
+  bc[0] = fac * dot3(nrm, cross3(ba, xa));
+  bc[1] = fac * dot3(nrm, cross3(c - b, xp - b));
+  bc[2] = fac * dot3(nrm, cross3(xa, ca));
+  return true;
+}
+// adjacency.hpp:230-273 line_triangle_intx_simple (dproj written only if both projections pass)
+__device__ __forceinline__ bool line_tri_simple(d3 A, d3 B, d3 C, d3 origin, d3 dest, d3& xp,
+                                                double& dproj, bool reverse, double tol) {
+  xp = {0, 0, 0};
+  bool found = false;
+  const d3 line = dest - origin;
+  d3 normv = cross3(B - A, C - A);
+  if (reverse) normv = {-1 * normv.x, -1 * normv.y, -1 * normv.z};
+  const double len = norm3(normv);
+  const d3 unit = {normv.x / len, normv.y / len, normv.z / len};
+  const double dist2plane = dot3(A - origin, unit);
+  const double proj_end = dot3(unit, dest - A);
+  if (dist2plane >= -tol && proj_end >= -tol) {
+    dproj = dot3(line, unit);
+    const double par_t = (dproj > 0) ? dist2plane / dproj : 0;
+    xp = {origin.x + par_t * line.x, origin.y + par_t * line.y, origin.z + par_t * line.z};
+    if (dproj > 0) {
+      double bc[3];
+      const bool res = bcc_tri_simple(A, B, C, xp, bc);
+      if (res && bc[0] >= 0 && bc[0] <= 1 && bc[1] >= 0 && bc[1] <= 1 && bc[2] >= 0 && bc[2] <= 1)
+        found = true;
+    }
+  }
+  return found;
+}
+
+struct ThreadStats {
+  int iters = 0, not_in = 0, not_found = 0, aborted = 0, active = 0, hops = 0;
+};
+
+// ---------------------------------------------------------------- the walk
+template <int DIM, int MODE, bool PUSH>
+__global__ void __launch_bounds__(128) k_search(SearchParams p) {
+  using Rec = typename std::conditional<DIM == 3, Tet, Tri>::type;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  ThreadStats st;
+  if (s < p.ps.capacity) {
+    int erow;
+    const bool mask = pp_slot_lookup(p.ps, s, erow);
+    constexpr bool kNew = (MODE == M_BCC || MODE == M_RAY);
+    int E = -1;
+    bool live = false;
+    if (mask) {
+      if (kNew) {
+        E = p.ids_empty ? erow : p.elem_ids[s];
+        live = (E != -1);
+      } else if (MODE == M_LEG2D) {          // adjacency.hpp:1045-1062
+        E = p.elem_ids[s];
+        if (E == -1) E = erow;
+        live = true;
+        if (E == -p.nelems) { E = -1; live = false; }
+      } else {                                // adjacency.hpp:586-598
+        E = p.ids_empty ? erow : p.elem_ids[s];
+        live = (E != -1);
+      }
+    }
+    d3 xp_out = {0, 0, 0};
+    int xface = -1;
+    bool write_x = false;
+    d3 tgt = {0, 0, 0}, org = {0, 0, 0};
+    if (mask) {
+      const bool from_orig = PUSH && p.push_from_orig;
+      if ((live && MODE != M_LEG2D) || from_orig)
+        org = {p.xo[s], p.xo[p.stride + s], p.xo[2 * p.stride + s]};
+      // a masked particle is always pushed, even if it already left the domain (the reference's
+      // push lambdas only test the mask)
+      if (PUSH) {
+        const d3 base = from_orig ? org : d3{p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+        const d3 dr = {p.dir[s], p.dir[p.stride + s], p.dir[2 * p.stride + s]};
+        tgt = {base.x + p.distance * dr.x, base.y + p.distance * dr.y, base.z + p.distance * dr.z};
+        p.xt_rw[s] = tgt.x; p.xt_rw[p.stride + s] = tgt.y; p.xt_rw[2 * p.stride + s] = tgt.z;
+      } else if (live) {
+        tgt = {p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+      }
+    }
+    if (live && kNew) {
+      // finishUnmoved (adjacency.tpp:525-533): 3-component norm even in 2D
+      if (norm3(tgt - org) < p.tol) live = false;
+    }
+    if (live) {
+      st.active = 1;
+      Rec rec;
+      load_rec(p.walk, E, rec);
+      bool done = false;
+      if (kNew) {
+        // check_initial_parents (adjacency.tpp:73-145)
+        bool inside;
+        if constexpr (DIM == 3) {
+          double b[4];
+          bcc_tet(rec, org, b);
+          inside = all_positive<4>(b, p.tol);
+        } else {
+          double b[3];
+          bcc_tri(rec, d2{org.x, org.y}, b);
+          inside = all_positive<3>(b, p.tol);
+        }
+        if (!inside) { st.not_in = 1; E = -1; done = true; }
+      }
+      // hoisted ray direction (ray_intersects_triangle computes it per face from the same inputs)
+      d3 dir = {0, 0, 0};
+      if (MODE == M_RAY && DIM == 3) {
+        const d3 disp = tgt - org;
+        const double seg = norm3(disp);
+        dir = {disp.x / seg, disp.y / seg, disp.z / seg};
+      }
+      int prevE = -1;
+      int it = 0;
+      while (!done) {
+        ++it;
+        int next = -1;
+        if constexpr (MODE == M_BCC || MODE == M_LEG2D) {
+          int f;
+          int a;
+          if constexpr (DIM == 3) {
+            double b[4];
+            bcc_tet(rec, tgt, b);
+            done = all_positive<4>(b, kEps);
+            f = min_index4(b);
+            a = rec.adj[f];
+          } else {
+            double b[3];
+            bcc_tri(rec, d2{tgt.x, tgt.y}, b);
+            done = all_positive<3>(b, kEps);
+            f = min3(b);
+            a = rec.adj[f];
+          }
+          if (done) break;
+          if (a < 0) { E = -1; done = true; break; }   // exposed side: particle leaves the domain
+          next = a;
+        } else if constexpr (MODE == M_RAY && DIM == 3) {
+          // adjacency.tpp:316-361
+          int exitf = -1, best = -1;
+          double quality = -1;
+#pragma unroll
+          for (int fi = 0; fi < 4; ++fi) {
+            const int a = rec.adj[fi];
+            if (prevE >= 0 && a == prevE) continue;   // face_id == prevExit
+            const unsigned code = (rec.codes >> (8 * fi)) & 0xffu;
+            const d3 V0 = rec.M[code & 3], V1 = rec.M[(code >> 2) & 3], V2 = rec.M[(code >> 4) & 3];
+            d3 xp;
+            double dproj, closeness;
+            const bool hit = ray_tri(V0, V1, V2, org, dir, p.tol, (code >> 6) & 1, xp, dproj, closeness);
+            if (hit) { exitf = fi; xp_out = xp; write_x = true; }
+            if (dproj > -p.tol && (quality < 0 || closeness < quality) && exitf == -1) {
+              quality = closeness; best = fi; xp_out = xp; write_x = true;
+            }
+          }
+          if (exitf == -1) exitf = best;
+          if (exitf == -1) { done = true; break; }
+          const int a = rec.adj[exitf];
+          if (a < 0) { xface = -a - 1; done = true; break; }  // wall hit: element id kept
+          next = a;
+        } else if constexpr (MODE == M_RAY && DIM == 2) {
+          // adjacency.tpp:285-313
+          int exitf = -1;
+#pragma unroll
+          for (int ei = 0; ei < 3; ++ei) {
+            const int a = rec.adj[ei];
+            if (prevE >= 0 && a == prevE) continue;
+            const unsigned code = (rec.codes >> (8 * ei)) & 0xffu;
+            d2 xp;
+            const bool hit = line_edge(rec.M[code & 3], rec.M[(code >> 2) & 3], d2{org.x, org.y},
+                                       d2{tgt.x, tgt.y}, p.tol, (code >> 6) & 1, xp);
+            if (hit) { exitf = ei; xp_out = {xp.x, xp.y, 0}; write_x = true; }
+          }
+          if (exitf == -1) { done = true; break; }
+          const int a = rec.adj[exitf];
+          if (a < 0) { xface = -a - 1; done = true; break; }
+          next = a;
+        } else if constexpr (MODE == M_LEG3D) {
+          // adjacency.hpp:607-740
+          double b[4];
+          if (it == 1) {
+            bcc_tet_legacy(rec, org, b);
+            if (!all_positive<4>(b, 1.0e-10)) st.aborted = 1;   // OMEGA_H_CHECK(false) :626
+          }
+          bcc_tet_legacy(rec, tgt, b);
+          if (all_positive<4>(b, 1.0e-10)) { done = true; break; }
+          double dproj[4] = {-1, -1, -1, -1};
+          d3 xpts[4];
+          bool intersected = false;
+          bool decided = false;
+#pragma unroll
+          for (int fi = 0; fi < 4; ++fi) {
+            if (decided) continue;
+            const int a = rec.adj[fi];
+            const unsigned code = (rec.codes >> (8 * fi)) & 0xffu;
+            const d3 V0 = rec.M[code & 3], V1 = rec.M[(code >> 2) & 3], V2 = rec.M[(code >> 4) & 3];
+            d3 xp;
+            intersected = line_tri_simple(V0, V1, V2, org, tgt, xp, dproj[fi], (code >> 7) & 1, 1.0e-10);
+            xpts[fi] = xp;
+            if (intersected && a < 0) {
+              done = true; xp_out = xp; write_x = true; xface = -a - 1; E = -1; decided = true;
+            } else if (intersected) {
+              next = a; decided = true;
+            }
+          }
+          if (done) break;
+          if (!intersected) {                       // :714-738
+            const int mi = max_index4(dproj);
+            if (dproj[mi] >= 0) {
+              const int a = rec.adj[mi];
+              if (a < 0) {
+                E = -1; xp_out = xpts[mi]; write_x = true; xface = -a - 1; done = true; break;
+              }
+              const int fid = p.elem2sides[4 * (long)E + mi];   // reference bug reproduced (:726)
+              if (fid < p.ndual) next = p.dual[fid];
+              else { E = -1; done = true; break; }
+            } else {
+              E = -1; done = true; break;           // "leaked"
+            }
+          }
+        }
+        // set_new_element + loop limit
+        prevE = E;
+        E = next;
+        ++st.hops;
+        if (MODE == M_LEG3D) {
+          if (p.looplimit && it > p.looplimit) { st.not_found = 1; break; }     // :756
+        } else {
+          if (p.looplimit && it >= p.looplimit) { st.not_found = 1; E = -1; break; }  // tpp:584-606
+        }
+        load_rec(p.walk, E, rec);
+      }
+      st.iters = it;
+    }
+    // ---- outputs
+    if (mask || p.ids_empty || MODE == M_LEG2D || MODE == M_LEG3D) p.elem_ids[s] = mask ? E : -1;
+    if (MODE == M_RAY) {
+      // initializeIntersection resets every slot (tpp:535-549); hits overwrite
+      p.inter_faces[s] = xface;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+        p.inter_points[(long)DIM * s + i] = write_x ? (i == 0 ? xp_out.x : i == 1 ? xp_out.y : xp_out.z) : 0.0;
+    } else if (MODE == M_LEG3D && xface >= 0) {
+      p.inter_faces[s] = xface;
+      p.inter_points[3 * (long)s] = xp_out.x;
+      p.inter_points[3 * (long)s + 1] = xp_out.y;
+      p.inter_points[3 * (long)s + 2] = xp_out.z;
+    }
+  }
+  // ---- warp-aggregated counters
+  const unsigned full = 0xffffffffu;
+  const int iters = __reduce_max_sync(full, st.iters);
+  const int nin = __reduce_add_sync(full, st.not_in);
+  const int nnf = __reduce_add_sync(full, st.not_found);
+  const int nab = __reduce_add_sync(full, st.aborted);
+  const int nac = __reduce_add_sync(full, st.active);
+  const int nh = __reduce_add_sync(full, st.hops);
+  if ((threadIdx.x & 31) == 0) {
+    if (iters) atomicMax(&p.counters->max_iters, iters);
+    if (nin) atomicAdd(&p.counters->not_in_elem, nin);
+    if (nnf) atomicAdd(&p.counters->not_found, nnf);
+    if (nab) atomicAdd(&p.counters->aborted, nab);
+    if (nac) atomicAdd(&p.counters->active, nac);
+    if (nh) atomicAdd(&p.counters->hops, (unsigned long long)nh);
+  }
+}
+
+template <int DIM, int MODE>
+void launch(const SearchParams& p, bool push, cudaStream_t s) {
+  const int block = 128;
+  const int grid = pp_div_up(p.ps.capacity, block);
+  if (push) k_search<DIM, MODE, true><<<grid, block, 0, s>>>(p);
+  else k_search<DIM, MODE, false><<<grid, block, 0, s>>>(p);
+}
+
+pp_status read_stats(pp_mesh* mesh, int variant, int looplimit, pp_search_stats* out, cudaStream_t s) {
+  SearchCounters h;
+  PP_CUDA(cudaMemcpyAsync(&h, mesh->stats_dev, sizeof(h), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  out->not_in_elem = h.not_in_elem;
+  out->not_found = h.not_found;
+  out->aborted = h.aborted;
+  out->active = h.active;
+  out->hops = (int64_t)h.hops;
+  // the reference's loop runs at least once and stops at the limit
+  int loops = h.max_iters > 1 ? h.max_iters : 1;
+  out->loops = loops;
+  out->found = h.not_found == 0;
+  (void)variant; (void)looplimit;
+  return PP_OK;
+}
+
+pp_status do_search(pp_mesh* mesh, pp_ps* ps, const pp_search_args* a, const double* dir,
+                    double distance, bool push, int push_from_orig, pp_search_stats* stats_host,
+                    cudaStream_t s) {
+  PP_REQUIRE(mesh && ps && a, "null argument");
+  PP_REQUIRE(a->x_tgt && a->elem_ids, "x_tgt and elem_ids are required");
+  PP_REQUIRE(a->stride >= ps->capacity, "stride smaller than capacity");
+  PP_REQUIRE(ps->nelems == mesh->nelems, "particle structure and mesh disagree on nelems");
+  SearchParams p;
+  p.ps = ps->view();
+  p.walk = mesh->walk;
+  p.xo = a->x_orig; p.xt = a->x_tgt; p.stride = a->stride;
+  p.elem_ids = a->elem_ids; p.ids_empty = a->elem_ids_empty;
+  p.inter_faces = a->inter_faces; p.inter_points = a->inter_points;
+  p.looplimit = a->looplimit; p.tol = mesh->tol; p.nelems = mesh->nelems;
+  p.counters = (SearchCounters*)mesh->stats_dev;
+  p.dir = dir; p.distance = distance; p.xt_rw = const_cast<double*>(a->x_tgt);
+  p.push_from_orig = push_from_orig;
+  p.elem2sides = mesh->elem2sides; p.dual = mesh->dual; p.ndual = 0;
+  PP_CUDA(cudaMemsetAsync(mesh->stats_dev, 0, sizeof(SearchCounters), s));
+  if (ps->capacity > 0) {
+    switch (a->variant) {
+      case PP_SEARCH_NEW:
+        PP_REQUIRE(a->x_orig, "x_orig is required");
+        if (a->require_intersection) {
+          PP_REQUIRE(a->inter_faces && a->inter_points, "intersection outputs are required");
+          if (mesh->dim == 3) launch<3, M_RAY>(p, push, s); else launch<2, M_RAY>(p, push, s);
+        } else {
+          if (mesh->dim == 3) launch<3, M_BCC>(p, push, s); else launch<2, M_BCC>(p, push, s);
+        }
+        break;
+      case PP_SEARCH_2D_LEGACY:
+        PP_REQUIRE(mesh->dim == 2, "search_mesh_2d needs a 2D mesh");
+        PP_REQUIRE(!push, "fused push is only available for the new search API");
+        launch<2, M_LEG2D>(p, false, s);
+        break;
+      case PP_SEARCH_3D_LEGACY: {
+        PP_REQUIRE(mesh->dim == 3, "legacy search_mesh needs a 3D mesh");
+        PP_REQUIRE(!push, "fused push is only available for the new search API");
+        PP_REQUIRE(a->x_orig && a->inter_faces && a->inter_points, "xpoints / xface are required");
+        int nd = 0;
+        PP_CUDA(cudaMemcpyAsync(&nd, mesh->dual_off + mesh->nelems, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PP_CUDA(cudaStreamSynchronize(s));
+        p.ndual = nd;
+        launch<3, M_LEG3D>(p, false, s);
+        break;
+      }
+      default:
+        PP_REQUIRE(false, "unknown search variant");
+    }
+    PP_KERNEL_CHECK();
+  }
+  if (stats_host) PP_TRY(read_stats(mesh, a->variant, a->looplimit, stats_host, s));
+  return PP_OK;
+}
+
+}  // namespace
+
+extern "C" pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                                    pp_search_stats* stats_host, pp_stream stream) {
+  return do_search(mesh, ps, args, nullptr, 0.0, false, 0, stats_host, (cudaStream_t)stream);
+}
+
+extern "C" pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host,
+                                          pp_stream stream) {
+  PP_REQUIRE(mesh && stats_host, "null argument");
+  return read_stats(mesh, 0, 0, stats_host, (cudaStream_t)stream);
+}
+
+extern "C" pp_status pp_push_direction_search(pp_mesh* mesh, pp_ps* ps, const double* dir,
+                                              double distance, int32_t push_from_orig,
+                                              const pp_search_args* args,
+                                              pp_search_stats* stats_host, pp_stream stream) {
+  PP_REQUIRE(dir, "null direction array");
+  PP_REQUIRE(args && args->variant == PP_SEARCH_NEW, "fused push needs PP_SEARCH_NEW");
+  PP_REQUIRE(args->x_orig, "x_orig is required");
+  return do_search(mesh, ps, args, dir, distance, true, push_from_orig ? 1 : 0, stats_host,
+                   (cudaStream_t)stream);
+}

@@ -1,0 +1,18 @@
+// pp_util.cu -- error string, version.
+#include <stdarg.h>
+#include <string.h>
+
+#include "pp_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void pp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* pp_last_error(void) { return g_err; }
+extern "C" const char* pp_version(void) { return "0.1.0"; }
+extern "C" const char* pp_build_arch(void) { return "sm_100a"; }
