@@ -67,45 +67,74 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Polls NVML (SM clock, max clock, power, clock-event reasons) from a thread while the timed
+    region runs; the steps take milliseconds, far below nvidia-smi's start-up time."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.samples = []
+        self.stop_flag = False
+        self.h = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = gpu_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except Exception:
+                    idx = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.p = None
+            self.h = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.window = [None, None]
+        self.t.start()
+
+    def _run(self):
+        if self.h is None:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, rs, pw))
+            except Exception:
+                break
+            time.sleep(0.001)
+
+    def begin(self):
+        self.window[0] = time.perf_counter()
+
+    def end(self):
+        self.window[1] = time.perf_counter()
 
     def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=2)
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        if self.h is None or not self.samples:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().split("\n") if r.strip()]
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for n, v in zip(names, r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(n)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
-                       reasons=sorted(reasons), samples=len(sm))
-        os.unlink(self.f.name)
+        lo, hi = self.window
+        inside = [s for s in self.samples if lo is not None and lo <= s[0] <= hi]
+        use = inside if inside else self.samples[-5:]
+        reasons = set()
+        for _, _, rs, _ in use:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        out.update(sm_mhz=float(np.median([s[1] for s in use])), sm_max_mhz=float(self.max_sm),
+                   reasons=sorted(reasons), samples=len(use),
+                   power_w_max=float(max(s[3] for s in use)),
+                   window="timed region" if inside else "last samples before the end of the timed region")
         return out
 
 
@@ -211,6 +240,7 @@ def main():
         return P.push_direction_search(gm, ps, dr, d if it % 2 == 0 else -d, a_, b_, ids,
                                        elem_ids_empty=False, from_orig=True, sync=sync)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     # seed element ids from the structure rows, then warm up
     P.push_direction_search(gm, ps, dr, 0.0, xa, xb, ids, elem_ids_empty=True, from_orig=True, sync=True)
     A, B = xa, xb
@@ -221,15 +251,18 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     active_steps = 0
     stream = torch.cuda.current_stream()
+    if sampler:
+        sampler.begin()
     ev[0].record(stream)
     for k in range(a.steps):
         step(it, A, B); A, B = B, A; it += 1
         ev[k + 1].record(stream)
     torch.cuda.synchronize()
+    if sampler:
+        sampler.end()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -93,10 +93,10 @@ class Mesh:
         torch.cuda.synchronize()
 
         def fetch(ptr, n, dtype):
-            out = np.empty(n, dtype)
-            rc = torch.cuda.cudart().cudaMemcpy(out.ctypes.data, ptr, out.nbytes, 2)
-            assert int(rc) == 0
-            return out
+            tdt = {np.float64: torch.float64, np.int8: torch.int8, np.int32: torch.int32}[dtype]
+            if n == 0:
+                return np.zeros(0, dtype)
+            return _tensor_from_ptr(ptr, (n,), tdt, self).cpu().numpy()
         res = {
             "measure": fetch(a.measure, self.nelems, np.float64),
             "exposed": fetch(a.exposed, self.nsides, np.int8),
@@ -215,7 +215,7 @@ class _CudaArrayView:
 def _tensor_from_ptr(ptr, shape, tdt, owner):
     torch = _torch()
     typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4",
-               torch.int64: "<i8"}[tdt]
+               torch.int64: "<i8", torch.int8: "|i1"}[tdt]
     return torch.as_tensor(_CudaArrayView(ptr, shape, typestr, owner), device="cuda")
 
 
