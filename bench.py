@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--ps", default="dps", choices=["dps", "scs", "csr"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-staged", action="store_true", help="use the simple thread-per-slot kernel")
     a = ap.parse_args()
     if a.cpu_sample <= 0:
         a.cpu_sample = a.particles
@@ -223,6 +224,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pp = importlib.import_module("pumi-pic_b200")
     P = pp
+    if a.no_staged:
+        P.lib().pp_search_set_staged(0)
     m, ppe = build_workload(pp, wl, a.cube_n, a.particles)
     gm = pp.Mesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
     kind = {"dps": P.capi.PP_PS_DPS, "scs": P.capi.PP_PS_SCS, "csr": P.capi.PP_PS_CSR}[a.ps]

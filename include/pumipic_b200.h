@@ -244,6 +244,10 @@ typedef struct pp_search_stats {
  * counters copied out. */
 pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
                          pp_search_stats* stats_host, pp_stream stream);
+/* Kernel selection for the barycentric walks: 1 (default) = block-staged kernel (cooperative
+ * record fetch + shared-memory compaction), 0 = the simple thread-per-slot kernel.  Both give
+ * identical results; the switch exists for A/B measurements. */
+void pp_search_set_staged(int32_t on);
 /* Counters of the most recent search on this mesh handle (synchronises the stream). */
 pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host, pp_stream stream);
 

@@ -27,7 +27,13 @@ def _newer(src, dst, deps):
     return any(os.path.getmtime(d) > t for d in [src] + deps)
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, extra_flags=(), lib=None, obj=None):
+    """extra_flags/lib/obj let experiments build side-by-side variants (see tools/)."""
+    global LIB, OBJ
+    if lib:
+        LIB = lib
+    if obj:
+        OBJ = obj
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
     hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
@@ -36,7 +42,8 @@ def build(verbose=False, force=False):
         o = os.path.join(OBJ, os.path.basename(s) + ".o")
         objs.append(o)
         if force or _newer(s, o, hdrs):
-            cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = ([NVCC] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+                   + ["-c", s, "-o", o])
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for s, p in procs:

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpumipic_b200.so")
+LIB_PATH = os.environ.get("PUMIPIC_B200_LIB", os.path.join(HERE, "libpumipic_b200.so"))
 
 PP_OK = 0
 PP_HOST, PP_DEVICE = 0, 1
@@ -109,6 +109,7 @@ PROTOTYPES = {
     "pp_update_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_search_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs),
                                  C.POINTER(SearchStats), C.c_void_p]),
+    "pp_search_set_staged": (None, [C.c_int32]),
     "pp_search_last_stats": (C.c_int, [C.c_void_p, C.POINTER(SearchStats), C.c_void_p]),
     "pp_push_direction_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                            C.c_int32, C.POINTER(SearchArgs),

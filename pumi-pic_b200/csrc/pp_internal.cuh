@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -92,6 +93,16 @@ struct __align__(16) PPTriRec {   // 96 B = three 32 B sectors
   int aux;
   int pad[2];
 };
+// BCC walk record of a tet: the particle-independent half of barycentric_tet
+// (adjacency.tpp:41-69) computed once per element with the reference's own operations, so the
+// per-particle part is 9 subtractions + 4 dot products + 4 multiplies.  12 x 16 B pieces.
+struct __align__(16) PPBccRec3 {  // 192 B
+  double a[9];                    // anchors of faces 0/1, 2, 3: M0, M1, M2
+  double n[12];                   // n[f] = cross(c - a, b - a) of face f = (a, b, c)
+  double inv_vol;                 // 1.0 / vol if vol > 0, else -1.0 (barycentric_tet fails)
+  int adj[4];
+};
+static_assert(sizeof(PPBccRec3) == 192, "BCC walk record must be 192 bytes");
 static_assert(sizeof(PPTetRec) == 128, "tet walk record must be 128 bytes");
 static_assert(sizeof(PPTriRec) == 96, "tri walk record must be 96 bytes");
 
@@ -114,6 +125,8 @@ struct pp_mesh {
   int* safe;        // [nelems] or null
   int* owner;       // [nelems] or null
   void* walk;       // PPTetRec[nelems] or PPTriRec[nelems]
+  PPBccRec3* walk_bcc;  // [nelems] (3D only)
+  int* aux;         // [nelems] owner rank if the element is not safe here, else -1
   // search scratch
   int* stats_dev;   // device counters (see SearchCounters)
 };
@@ -211,10 +224,16 @@ __device__ __forceinline__ double dot2(d2 a, d2 b) {
 __device__ __forceinline__ double cross2(d2 a, d2 b) { return a.x * b.y - a.y * b.x; }
 
 // Omega_h::are_close(a, 0, tol, tol) || a > 0   (pumipic_utils.hpp:78-86)
+// are_close(a,0,tol,tol): |a| <= tol, else |0-a|/max(|a|,0) = |a|/|a| <= tol, which is 1 <= tol for
+// finite a and NaN (false) for infinite a -- evaluated without the division.
 __device__ __forceinline__ bool pp_gtez(double a, double tol) {
   const double am = fabs(a);
+#ifdef PP_AB_OLD_GTEZ
   bool close;
-  if (am <= tol) close = true;          // both |a| and |0| under the floor
-  else close = (am / am) <= tol;        // |0-a| / max(|a|,0) = 1 <= tol
+  if (am <= tol) close = true;
+  else close = (am / am) <= tol;
+#else
+  const bool close = (am <= tol) || (tol >= 1.0 && am < CUDART_INF);
+#endif
   return close || a > 0;
 }

@@ -98,7 +98,7 @@ __global__ void k_build_walk(const double* __restrict__ coords, const int* __res
                              const int* __restrict__ e2s, const int* __restrict__ s2v,
                              const int* __restrict__ side2elem, const int* __restrict__ cls,
                              const double* __restrict__ measure, const int* __restrict__ dual_off,
-                             int nelems, int* dual, void* walk_out) {
+                             int nelems, int* dual, void* walk_out, PPBccRec3* bcc_out) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nelems) return;
   constexpr int NV = DIM + 1;
@@ -139,7 +139,7 @@ __global__ void k_build_walk(const double* __restrict__ coords, const int* __res
     }
     codes |= code << (8 * f);
   }
-  if (DIM == 3) {
+  if constexpr (DIM == 3) {
     PPTetRec r;
     for (int k = 0; k < 4; ++k)
       for (int i = 0; i < 3; ++i) r.c[3 * k + i] = coords[3 * (long)tv[k] + i];
@@ -148,6 +148,20 @@ __global__ void k_build_walk(const double* __restrict__ coords, const int* __res
     r.codes = codes;
     r.aux = -1;
     ((PPTetRec*)walk_out)[e] = r;
+    PPBccRec3 b;
+    for (int i = 0; i < 9; ++i) b.a[i] = r.c[i];
+    for (int f = 0; f < 4; ++f) {   // barycentric_tet: cross(vac, vab), (a,b,c) = face template
+      const double* pa = r.c + 3 * c_tet_face[f][0];
+      const double* pb = r.c + 3 * c_tet_face[f][1];
+      const double* pc = r.c + 3 * c_tet_face[f][2];
+      const d3 vab = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+      const d3 vac = {pc[0] - pa[0], pc[1] - pa[1], pc[2] - pa[2]};
+      const d3 n = cross3(vac, vab);
+      b.n[3 * f] = n.x; b.n[3 * f + 1] = n.y; b.n[3 * f + 2] = n.z;
+    }
+    b.inv_vol = r.vol > 0 ? 1.0 / r.vol : -1.0;
+    for (int f = 0; f < 4; ++f) b.adj[f] = adj[f];
+    bcc_out[e] = b;
   } else {
     PPTriRec r;
     for (int k = 0; k < 3; ++k)
@@ -163,10 +177,11 @@ __global__ void k_build_walk(const double* __restrict__ coords, const int* __res
 }
 
 __global__ void k_set_aux(void* walk, int dim, int nelems, const int* __restrict__ safe,
-                          const int* __restrict__ owner) {
+                          const int* __restrict__ owner, int* aux_out) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nelems) return;
   const int aux = safe[e] ? -1 : owner[e];
+  aux_out[e] = aux;
   if (dim == 3) ((PPTetRec*)walk)[e].aux = aux;
   else ((PPTriRec*)walk)[e].aux = aux;
 }
@@ -235,14 +250,20 @@ extern "C" pp_status pp_mesh_create(const pp_mesh_desc* d, pp_stream stream_, pp
   PP_TRY(pp_dev_alloc(&m->dual, (size_t)ndual + 1, s));
   const size_t rec = dim == 3 ? sizeof(PPTetRec) : sizeof(PPTriRec);
   PP_CUDA(cudaMallocAsync(&m->walk, rec * (size_t)ne, s));
-  if (dim == 3)
+  PP_TRY(pp_dev_alloc(&m->aux, ne, s));
+  k_fill_int<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(m->aux, ne, -1);
+  if (dim == 3) {
+    PP_TRY(pp_dev_alloc(&m->walk_bcc, ne, s));
     k_build_walk<3><<<pp_div_up(ne, 128), 128, 0, s>>>(m->coords, m->elem2verts, m->elem2sides,
                                                        m->side2verts, m->side2elem, m->elem_class,
-                                                       m->measure, m->dual_off, ne, m->dual, m->walk);
-  else
+                                                       m->measure, m->dual_off, ne, m->dual, m->walk,
+                                                       m->walk_bcc);
+  } else {
     k_build_walk<2><<<pp_div_up(ne, 128), 128, 0, s>>>(m->coords, m->elem2verts, m->elem2sides,
                                                        m->side2verts, m->side2elem, m->elem_class,
-                                                       m->measure, m->dual_off, ne, m->dual, m->walk);
+                                                       m->measure, m->dual_off, ne, m->dual, m->walk,
+                                                       nullptr);
+  }
   PP_KERNEL_CHECK();
   pp_dev_free(lo, s); pp_dev_free(hi, s); pp_dev_free(cnt, s); pp_dev_free(scal, s);
   pp_dev_free(min_key, s); pp_dev_free((char*)tmp, s);
@@ -256,7 +277,7 @@ extern "C" pp_status pp_mesh_destroy(pp_mesh* m) {
   cudaFree(m->coords); cudaFree(m->elem2verts); cudaFree(m->elem2sides); cudaFree(m->side2verts);
   cudaFree(m->elem_class); cudaFree(m->measure); cudaFree(m->exposed); cudaFree(m->side2elem);
   cudaFree(m->dual_off); cudaFree(m->dual); cudaFree(m->safe); cudaFree(m->owner);
-  cudaFree(m->walk); cudaFree(m->stats_dev);
+  cudaFree(m->walk); cudaFree(m->walk_bcc); cudaFree(m->aux); cudaFree(m->stats_dev);
   delete m;
   return PP_OK;
 }
@@ -265,7 +286,8 @@ extern "C" pp_status pp_mesh_get_info(const pp_mesh* m, pp_mesh_info* o) {
   PP_REQUIRE(m && o, "null argument");
   o->dim = m->dim; o->nverts = m->nverts; o->nelems = m->nelems; o->nsides = m->nsides;
   o->tol = m->tol; o->min_measure = m->min_measure; o->n_exposed_sides = m->n_exposed;
-  o->walk_table_bytes = (int64_t)m->nelems * (m->dim == 3 ? sizeof(PPTetRec) : sizeof(PPTriRec));
+  o->walk_table_bytes = (int64_t)m->nelems *
+                        (m->dim == 3 ? sizeof(PPTetRec) + sizeof(PPBccRec3) : sizeof(PPTriRec));
   return PP_OK;
 }
 
@@ -287,7 +309,7 @@ extern "C" pp_status pp_mesh_set_picpart(pp_mesh* m, const int32_t* safe, const 
   PP_TRY(pp_dev_import(&m->safe, safe, (size_t)m->nelems, memspace, s));
   PP_TRY(pp_dev_import(&m->owner, owner, (size_t)m->nelems, memspace, s));
   m->self_rank = self_rank;
-  k_set_aux<<<pp_div_up(m->nelems, kBlock), kBlock, 0, s>>>(m->walk, m->dim, m->nelems, m->safe, m->owner);
+  k_set_aux<<<pp_div_up(m->nelems, kBlock), kBlock, 0, s>>>(m->walk, m->dim, m->nelems, m->safe, m->owner, m->aux);
   PP_KERNEL_CHECK();
   return PP_OK;
 }

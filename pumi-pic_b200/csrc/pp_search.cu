@@ -21,6 +21,8 @@ enum Mode { M_BCC = 0, M_RAY = 1, M_LEG2D = 2, M_LEG3D = 3 };
 struct SearchParams {
   PsView ps;
   const void* walk;
+  const void* walk_bcc;
+  int staged;           // 1: block-staged BCC walk (default), 0: thread-per-slot reference kernel
   const double* xo;
   const double* xt;
   long stride;
@@ -60,6 +62,24 @@ struct Tri {
   unsigned codes;
   int cls, aux;
 };
+
+template <class R>
+__device__ __forceinline__ int adj_of(const R& r, int f) {   // no dynamic register indexing
+#ifdef PP_AB_OLD_ADJ
+  return r.adj[f];
+#else
+  return f == 0 ? r.adj[0] : f == 1 ? r.adj[1] : f == 2 ? r.adj[2] : r.adj[3];
+#endif
+}
+__device__ __forceinline__ int adj_of(const Tri& r, int f) {
+  return f == 0 ? r.adj[0] : f == 1 ? r.adj[1] : r.adj[2];
+}
+__device__ __forceinline__ d3 vert_of(const Tet& t, unsigned i) {
+  return i == 0 ? t.M[0] : i == 1 ? t.M[1] : i == 2 ? t.M[2] : t.M[3];
+}
+__device__ __forceinline__ d2 vert_of(const Tri& t, unsigned i) {
+  return i == 0 ? t.M[0] : i == 1 ? t.M[1] : t.M[2];
+}
 
 __device__ __forceinline__ void load_rec(const void* walk, int E, Tet& t) {
   const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const PPTetRec*>(walk) + E);
@@ -347,13 +367,13 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
             bcc_tet(rec, tgt, b);
             done = all_positive<4>(b, kEps);
             f = min_index4(b);
-            a = rec.adj[f];
+            a = adj_of(rec, f);
           } else {
             double b[3];
             bcc_tri(rec, d2{tgt.x, tgt.y}, b);
             done = all_positive<3>(b, kEps);
             f = min3(b);
-            a = rec.adj[f];
+            a = adj_of(rec, f);
           }
           if (done) break;
           if (a < 0) { E = -1; done = true; break; }   // exposed side: particle leaves the domain
@@ -367,7 +387,8 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
             const int a = rec.adj[fi];
             if (prevE >= 0 && a == prevE) continue;   // face_id == prevExit
             const unsigned code = (rec.codes >> (8 * fi)) & 0xffu;
-            const d3 V0 = rec.M[code & 3], V1 = rec.M[(code >> 2) & 3], V2 = rec.M[(code >> 4) & 3];
+            const d3 V0 = vert_of(rec, code & 3), V1 = vert_of(rec, (code >> 2) & 3),
+                     V2 = vert_of(rec, (code >> 4) & 3);
             d3 xp;
             double dproj, closeness;
             const bool hit = ray_tri(V0, V1, V2, org, dir, p.tol, (code >> 6) & 1, xp, dproj, closeness);
@@ -378,7 +399,7 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
           }
           if (exitf == -1) exitf = best;
           if (exitf == -1) { done = true; break; }
-          const int a = rec.adj[exitf];
+          const int a = adj_of(rec, exitf);
           if (a < 0) { xface = -a - 1; done = true; break; }  // wall hit: element id kept
           next = a;
         } else if constexpr (MODE == M_RAY && DIM == 2) {
@@ -390,12 +411,12 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
             if (prevE >= 0 && a == prevE) continue;
             const unsigned code = (rec.codes >> (8 * ei)) & 0xffu;
             d2 xp;
-            const bool hit = line_edge(rec.M[code & 3], rec.M[(code >> 2) & 3], d2{org.x, org.y},
-                                       d2{tgt.x, tgt.y}, p.tol, (code >> 6) & 1, xp);
+            const bool hit = line_edge(vert_of(rec, code & 3), vert_of(rec, (code >> 2) & 3),
+                                       d2{org.x, org.y}, d2{tgt.x, tgt.y}, p.tol, (code >> 6) & 1, xp);
             if (hit) { exitf = ei; xp_out = {xp.x, xp.y, 0}; write_x = true; }
           }
           if (exitf == -1) { done = true; break; }
-          const int a = rec.adj[exitf];
+          const int a = adj_of(rec, exitf);
           if (a < 0) { xface = -a - 1; done = true; break; }
           next = a;
         } else if constexpr (MODE == M_LEG3D) {
@@ -416,7 +437,8 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
             if (decided) continue;
             const int a = rec.adj[fi];
             const unsigned code = (rec.codes >> (8 * fi)) & 0xffu;
-            const d3 V0 = rec.M[code & 3], V1 = rec.M[(code >> 2) & 3], V2 = rec.M[(code >> 4) & 3];
+            const d3 V0 = vert_of(rec, code & 3), V1 = vert_of(rec, (code >> 2) & 3),
+                     V2 = vert_of(rec, (code >> 4) & 3);
             d3 xp;
             intersected = line_tri_simple(V0, V1, V2, org, tgt, xp, dproj[fi], (code >> 7) & 1, 1.0e-10);
             xpts[fi] = xp;
@@ -429,10 +451,13 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
           if (done) break;
           if (!intersected) {                       // :714-738
             const int mi = max_index4(dproj);
-            if (dproj[mi] >= 0) {
-              const int a = rec.adj[mi];
+            const double dmax = mi == 0 ? dproj[0] : mi == 1 ? dproj[1] : mi == 2 ? dproj[2] : dproj[3];
+            if (dmax >= 0) {
+              const int a = adj_of(rec, mi);
               if (a < 0) {
-                E = -1; xp_out = xpts[mi]; write_x = true; xface = -a - 1; done = true; break;
+                E = -1; xface = -a - 1; done = true; write_x = true;
+                xp_out = mi == 0 ? xpts[0] : mi == 1 ? xpts[1] : mi == 2 ? xpts[2] : xpts[3];
+                break;
               }
               const int fid = p.elem2sides[4 * (long)E + mi];   // reference bug reproduced (:726)
               if (fid < p.ndual) next = p.dual[fid];
@@ -488,6 +513,285 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
   }
 }
 
+// ---------------------------------------------------------------- staged BCC walk
+// The barycentric walk (search_mesh with requireIntersection=false, and search_mesh_2d) as a
+// block-synchronous pipeline.  A block owns BLOCK consecutive slots.  Every round:
+//   1. the block fetches the walk records of all queued particles COOPERATIVELY: 16-byte piece
+//      k of record i is loaded by thread i*PIECES+k, so each record costs one or two coalesced
+//      L1 wavefronts instead of one wavefront per piece per lane;
+//   2. records are staged in shared memory (stride chosen bank-conflict free for 128-bit reads);
+//   3. each queued particle is evaluated by one thread; particles that must hop are pushed
+//      into a shared-memory queue with a warp-aggregated slot claim, so the next round runs on
+//      densely packed warps (walk lengths differ: ~49 % stop in round 0, ~2 % need >= 4 hops).
+template <int DIM> struct StageCfg;
+template <> struct StageCfg<3> {
+  static constexpr int PIECES = 12, STRIDE = 208;   // 52 words: 8 lanes x 4 banks, conflict free
+  using Raw = PPBccRec3;
+};
+template <> struct StageCfg<2> {
+  static constexpr int PIECES = 5, STRIDE = 80;     // 20 words: conflict free as well
+  using Raw = PPTriRec;
+};
+
+struct Bcc3 {
+  d3 a0, a1, a2, n0, n1, n2, n3;
+  double inv_vol;
+  int adj[4];
+};
+__device__ __forceinline__ void read_stage(const unsigned char* st, Bcc3& r) {
+  const double2* q = reinterpret_cast<const double2*>(st);
+  const double2 p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3], p4 = q[4], p5 = q[5];
+  const double2 p6 = q[6], p7 = q[7], p8 = q[8], p9 = q[9], p10 = q[10];
+  const int4 p11 = *reinterpret_cast<const int4*>(q + 11);
+  r.a0 = {p0.x, p0.y, p1.x};
+  r.a1 = {p1.y, p2.x, p2.y};
+  r.a2 = {p3.x, p3.y, p4.x};
+  r.n0 = {p4.y, p5.x, p5.y};
+  r.n1 = {p6.x, p6.y, p7.x};
+  r.n2 = {p7.y, p8.x, p8.y};
+  r.n3 = {p9.x, p9.y, p10.x};
+  r.inv_vol = p10.y;
+  r.adj[0] = p11.x; r.adj[1] = p11.y; r.adj[2] = p11.z; r.adj[3] = p11.w;
+}
+__device__ __forceinline__ void read_stage(const unsigned char* st, Tri& t) {
+  const double2* q = reinterpret_cast<const double2*>(st);
+  const double2 a0 = q[0], a1 = q[1], a2 = q[2];
+  const int4 q3 = *reinterpret_cast<const int4*>(q + 3);
+  const int4 q4 = *reinterpret_cast<const int4*>(q + 4);
+  t.M[0] = {a0.x, a0.y};
+  t.M[1] = {a1.x, a1.y};
+  t.M[2] = {a2.x, a2.y};
+  t.area = __hiloint2double(q3.y, q3.x);
+  t.adj[0] = q3.z; t.adj[1] = q3.w; t.adj[2] = q4.x;
+  t.codes = (unsigned)q4.y;
+  t.cls = q4.z;
+  t.aux = q4.w;
+}
+// barycentric_tet with the particle-independent half read from the record (bit-identical)
+__device__ __forceinline__ void bcc_tet(const Bcc3& t, d3 p, double bcc[4]) {
+  const d3 p0 = p - t.a0;
+  double v[4];
+  v[0] = dot3(p0, t.n0);
+  v[1] = dot3(p0, t.n1);
+  v[2] = dot3(p - t.a1, t.n2);
+  v[3] = dot3(p - t.a2, t.n3);
+  if (t.inv_vol > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bcc[i] = t.inv_vol * v[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bcc[i] = -1;
+  }
+}
+
+template <int DIM, int BLOCK>
+__device__ __forceinline__ void stage_fetch(const typename StageCfg<DIM>::Raw* table,
+                                            const int* q_E, int n, unsigned char* stage) {
+  using Cfg = StageCfg<DIM>;
+  constexpr int HALF = (Cfg::PIECES + 1) / 2;
+  const int total = n * Cfg::PIECES;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    int4 v[HALF];
+    int dst[HALF];
+#pragma unroll
+    for (int k = 0; k < HALF; ++k) {
+      const int idx = threadIdx.x + (h * HALF + k) * BLOCK;
+      dst[k] = -1;
+      if (h * HALF + k < Cfg::PIECES && idx < total) {
+        const int item = idx / Cfg::PIECES;
+        const int piece = idx - item * Cfg::PIECES;
+        const int e = q_E[item];
+        if (e >= 0) {
+          v[k] = __ldg(reinterpret_cast<const int4*>(table + e) + piece);
+          dst[k] = item * Cfg::STRIDE + piece * 16;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < HALF; ++k)
+      if (dst[k] >= 0) *reinterpret_cast<int4*>(stage + dst[k]) = v[k];
+  }
+}
+
+template <int DIM, bool LEG2D, bool PUSH, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (DIM == 3 ? 3 : 4)) k_walk_bcc(SearchParams p) {
+  using Cfg = StageCfg<DIM>;
+  using Rec = typename std::conditional<DIM == 3, Bcc3, Tri>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* stage = smem;
+  double* q_tx = reinterpret_cast<double*>(smem + BLOCK * Cfg::STRIDE);
+  double* q_ty = q_tx + BLOCK;
+  double* q_tz = q_ty + BLOCK;
+  int* q_E = reinterpret_cast<int*>(q_tz + BLOCK);
+  int* q_slot = q_E + BLOCK;
+  int* q_it = q_slot + BLOCK;
+  __shared__ int q_count;
+  const auto* table = reinterpret_cast<const typename Cfg::Raw*>(DIM == 3 ? p.walk_bcc : p.walk);
+
+  const int tid = threadIdx.x;
+  const int slot = blockIdx.x * BLOCK + tid;
+  if (tid == 0) q_count = 0;
+  ThreadStats st;
+  int E = -1;
+  bool live = false;
+  d3 tgt = {0, 0, 0}, org = {0, 0, 0};
+  // ---- setup: setInitial / fill, push, finishUnmoved (same rules as k_search)
+  if (slot < p.ps.capacity) {
+    int erow;
+    const bool mask = pp_slot_lookup(p.ps, slot, erow);
+    if (mask) {
+      if (!LEG2D) {
+        E = p.ids_empty ? erow : p.elem_ids[slot];
+        live = (E != -1);
+      } else {                                  // adjacency.hpp:1045-1062
+        E = p.elem_ids[slot];
+        if (E == -1) E = erow;
+        live = true;
+        if (E == -p.nelems) { E = -1; live = false; }
+      }
+      const bool from_orig = PUSH && p.push_from_orig;
+      if ((live && !LEG2D) || from_orig)
+        org = {p.xo[slot], p.xo[p.stride + slot], p.xo[2 * p.stride + slot]};
+      if (PUSH) {
+        const d3 base = from_orig ? org
+                                  : d3{p.xt[slot], p.xt[p.stride + slot], p.xt[2 * p.stride + slot]};
+        const d3 dr = {p.dir[slot], p.dir[p.stride + slot], p.dir[2 * p.stride + slot]};
+        tgt = {base.x + p.distance * dr.x, base.y + p.distance * dr.y, base.z + p.distance * dr.z};
+        p.xt_rw[slot] = tgt.x; p.xt_rw[p.stride + slot] = tgt.y; p.xt_rw[2 * p.stride + slot] = tgt.z;
+      } else if (live) {
+        tgt = {p.xt[slot], p.xt[p.stride + slot], p.xt[2 * p.stride + slot]};
+      }
+      if (live && !LEG2D && norm3(tgt - org) < p.tol) live = false;   // finishUnmoved
+    }
+    if (!live && (mask || p.ids_empty || LEG2D)) p.elem_ids[slot] = mask ? E : -1;
+  }
+  q_E[tid] = live ? E : -1;
+  __syncthreads();
+  // ---- round 0: every live slot is an item; origin check + first target test share a record
+  stage_fetch<DIM, BLOCK>(table, q_E, BLOCK, stage);
+  __syncthreads();
+  auto advance = [&](const Rec& rec, int myslot, int& e, int it, d3 t) {
+    // one walk iteration: find_exit_face (BCC) + check_model_intersection + set_new_element
+    bool done;
+    int f;
+    if constexpr (DIM == 3) {
+      double b[4];
+      bcc_tet(rec, t, b);
+      done = all_positive<4>(b, kEps);
+      f = min_index4(b);
+    } else {
+      double b[3];
+      bcc_tri(rec, d2{t.x, t.y}, b);
+      done = all_positive<3>(b, kEps);
+      f = min3(b);
+    }
+    bool push = false;
+    int next = -1;
+    if (!done) {
+      const int a = adj_of(rec, f);
+      if (a < 0) {
+        e = -1;                       // exposed side: the particle leaves the domain
+      } else {
+        ++st.hops;
+        if (p.looplimit && it >= p.looplimit) { st.not_found = 1; e = -1; }  // tpp:584-606
+        else { push = true; next = a; }
+      }
+    }
+    // warp-aggregated claim of queue positions
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, push);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      int base = 0;
+      if ((tid & 31) == leader) base = atomicAdd(&q_count, __popc(m));
+      base = __shfl_sync(act, base, leader);
+      if (push) {
+        const int pos = base + __popc(m & ((1u << (tid & 31)) - 1u));
+        q_E[pos] = next; q_slot[pos] = myslot; q_it[pos] = it;
+        q_tx[pos] = t.x; q_ty[pos] = t.y; q_tz[pos] = t.z;
+      }
+    }
+    if (!push) p.elem_ids[myslot] = e;
+    st.iters = it > st.iters ? it : st.iters;
+  };
+  if (live) {
+    st.active = 1;
+    Rec rec;
+    read_stage(stage + tid * Cfg::STRIDE, rec);
+    bool inside = true;
+    if (!LEG2D) {                                 // check_initial_parents (tpp:73-145)
+      if constexpr (DIM == 3) {
+        double b[4];
+        bcc_tet(rec, org, b);
+        inside = all_positive<4>(b, p.tol);
+      } else {
+        double b[3];
+        bcc_tri(rec, d2{org.x, org.y}, b);
+        inside = all_positive<3>(b, p.tol);
+      }
+    }
+    if (!inside) {
+      st.not_in = 1;
+      p.elem_ids[slot] = -1;
+    } else {
+      advance(rec, slot, E, 1, tgt);
+    }
+  }
+  // ---- rounds >= 1 on the compacted queue
+  while (true) {
+    __syncthreads();
+    const int n = q_count;
+    if (n == 0) break;
+    const bool has = tid < n;
+    int myslot = 0, it = 0;
+    if (has) {
+      E = q_E[tid]; myslot = q_slot[tid]; it = q_it[tid];
+      tgt = {q_tx[tid], q_ty[tid], q_tz[tid]};
+    }
+    __syncthreads();
+    if (tid == 0) q_count = 0;
+    stage_fetch<DIM, BLOCK>(table, q_E, n, stage);
+    __syncthreads();
+    if (has) {
+      Rec rec;
+      read_stage(stage + tid * Cfg::STRIDE, rec);
+      advance(rec, myslot, E, it + 1, tgt);
+    }
+  }
+  // ---- warp-aggregated counters
+  const unsigned full = 0xffffffffu;
+  const int iters = __reduce_max_sync(full, st.iters);
+  const int nin = __reduce_add_sync(full, st.not_in);
+  const int nnf = __reduce_add_sync(full, st.not_found);
+  const int nac = __reduce_add_sync(full, st.active);
+  const int nh = __reduce_add_sync(full, st.hops);
+  if ((tid & 31) == 0) {
+    if (iters) atomicMax(&p.counters->max_iters, iters);
+    if (nin) atomicAdd(&p.counters->not_in_elem, nin);
+    if (nnf) atomicAdd(&p.counters->not_found, nnf);
+    if (nac) atomicAdd(&p.counters->active, nac);
+    if (nh) atomicAdd(&p.counters->hops, (unsigned long long)nh);
+  }
+}
+
+template <int DIM, bool LEG2D>
+pp_status launch_walk_bcc(const SearchParams& p, bool push, cudaStream_t s) {
+  constexpr int BLOCK = 256;
+  constexpr size_t smem = (size_t)BLOCK * StageCfg<DIM>::STRIDE + (size_t)BLOCK * (3 * 8 + 3 * 4);
+  const int grid = pp_div_up(p.ps.capacity, BLOCK);
+  if (push) {
+    auto k = k_walk_bcc<DIM, LEG2D, true, BLOCK>;
+    PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, BLOCK, smem, s>>>(p);
+  } else {
+    auto k = k_walk_bcc<DIM, LEG2D, false, BLOCK>;
+    PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, BLOCK, smem, s>>>(p);
+  }
+  return PP_OK;
+}
+
 template <int DIM, int MODE>
 void launch(const SearchParams& p, bool push, cudaStream_t s) {
   const int block = 128;
@@ -495,6 +799,8 @@ void launch(const SearchParams& p, bool push, cudaStream_t s) {
   if (push) k_search<DIM, MODE, true><<<grid, block, 0, s>>>(p);
   else k_search<DIM, MODE, false><<<grid, block, 0, s>>>(p);
 }
+
+int g_staged_walk = 1;
 
 pp_status read_stats(pp_mesh* mesh, int variant, int looplimit, pp_search_stats* out, cudaStream_t s) {
   SearchCounters h;
@@ -523,6 +829,8 @@ pp_status do_search(pp_mesh* mesh, pp_ps* ps, const pp_search_args* a, const dou
   SearchParams p;
   p.ps = ps->view();
   p.walk = mesh->walk;
+  p.walk_bcc = mesh->walk_bcc;
+  p.staged = g_staged_walk;
   p.xo = a->x_orig; p.xt = a->x_tgt; p.stride = a->stride;
   p.elem_ids = a->elem_ids; p.ids_empty = a->elem_ids_empty;
   p.inter_faces = a->inter_faces; p.inter_points = a->inter_points;
@@ -539,6 +847,9 @@ pp_status do_search(pp_mesh* mesh, pp_ps* ps, const pp_search_args* a, const dou
         if (a->require_intersection) {
           PP_REQUIRE(a->inter_faces && a->inter_points, "intersection outputs are required");
           if (mesh->dim == 3) launch<3, M_RAY>(p, push, s); else launch<2, M_RAY>(p, push, s);
+        } else if (p.staged) {
+          if (mesh->dim == 3) PP_TRY((launch_walk_bcc<3, false>(p, push, s)));
+          else PP_TRY((launch_walk_bcc<2, false>(p, push, s)));
         } else {
           if (mesh->dim == 3) launch<3, M_BCC>(p, push, s); else launch<2, M_BCC>(p, push, s);
         }
@@ -546,7 +857,8 @@ pp_status do_search(pp_mesh* mesh, pp_ps* ps, const pp_search_args* a, const dou
       case PP_SEARCH_2D_LEGACY:
         PP_REQUIRE(mesh->dim == 2, "search_mesh_2d needs a 2D mesh");
         PP_REQUIRE(!push, "fused push is only available for the new search API");
-        launch<2, M_LEG2D>(p, false, s);
+        if (p.staged) PP_TRY((launch_walk_bcc<2, true>(p, false, s)));
+        else launch<2, M_LEG2D>(p, false, s);
         break;
       case PP_SEARCH_3D_LEGACY: {
         PP_REQUIRE(mesh->dim == 3, "legacy search_mesh needs a 3D mesh");
@@ -574,6 +886,8 @@ extern "C" pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_ar
                                     pp_search_stats* stats_host, pp_stream stream) {
   return do_search(mesh, ps, args, nullptr, 0.0, false, 0, stats_host, (cudaStream_t)stream);
 }
+
+extern "C" void pp_search_set_staged(int32_t on) { g_staged_walk = on ? 1 : 0; }
 
 extern "C" pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host,
                                           pp_stream stream) {
