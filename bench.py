@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--cube-n", type=int, default=55)
     ap.add_argument("--particles", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles per CPU step (0 = all)")
-    ap.add_argument("--ps", default="dps", choices=["dps", "scs", "csr"])
+    ap.add_argument("--ps", default="scs", choices=["dps", "scs", "csr"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-staged", action="store_true", help="use the simple thread-per-slot kernel")

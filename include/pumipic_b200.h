@@ -195,6 +195,16 @@ typedef struct pp_ps_layout {
 } pp_ps_layout;
 pp_status pp_ps_get_layout(pp_ps* ps, pp_stream stream, pp_ps_layout* out);
 
+/* rebuild (particle_structure.hpp:99-100; SCS_rebuild.h:123, CSR_rebuild.hpp:18, dps_rebuild.hpp):
+ *   new_element[capacity]       new parent element per slot, -1 deletes the particle
+ *   new_particle_elements[n_new], new_particle_info[nmembers] (each [ncomp][n_new]) particles to add
+ * All pointers are device pointers (new_particle_info itself is a host array of device pointers).
+ * Slot numbering, capacity and member pointers change; re-fetch them afterwards.  Returns
+ * PP_ERR_INVALID if a new particle has element -1 (the reference exits the process). */
+pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
+                        const int32_t* new_particle_elements,
+                        const void* const* new_particle_info, pp_stream stream);
+
 /* ============================== push ===================================================== */
 
 /* test/pseudoPushAndSearch.cpp:87-118: xtgt = x + distance*(dx,dy,dz) for masked slots */

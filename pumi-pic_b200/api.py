@@ -177,6 +177,15 @@ class ParticleStructure:
             return torch.empty((nc, 0), dtype=tdt, device="cuda")
         return _tensor_from_ptr(base.value, (nc, stride.value), tdt, self)
 
+    def rebuild(self, new_element, new_particle_elements=None, new_particle_info=None):
+        """ParticleStructure::rebuild: all arguments are device tensors ([ncomp, n_new] members)."""
+        n_new = 0 if new_particle_elements is None else int(new_particle_elements.shape[0])
+        info = None
+        if n_new:
+            info = (C.c_void_p * len(self.members))(*[t.data_ptr() for t in new_particle_info])
+        check(lib().pp_ps_rebuild(self.h, _ptr(new_element), n_new, _ptr(new_particle_elements),
+                                  info, _stream()))
+
     def layout(self):
         lay = capi.PsLayout()
         check(lib().pp_ps_get_layout(self.h, _stream(), C.byref(lay)))

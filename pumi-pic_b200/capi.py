@@ -102,6 +102,8 @@ PROTOTYPES = {
     "pp_ps_kind_of": (C.c_int32, [C.c_void_p]),
     "pp_ps_member": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), c_i64p]),
     "pp_ps_get_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PsLayout)]),
+    "pp_ps_rebuild": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                C.POINTER(C.c_void_p), C.c_void_p]),
     "pp_push_constant": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                    C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "pp_push_direction": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,

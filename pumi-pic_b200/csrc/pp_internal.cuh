@@ -171,7 +171,8 @@ struct pp_ps {
   uint32_t* mask_bits;
   long mask_words_alloc;
   int* slot_elem;           // [capacity] (DPS parent array; CSR/SCS materialised map)
-  bool slot_elem_valid;
+  bool slot_elem_valid;     // kernels read slot_elem (DPS / CSR)
+  bool slot_elem_materialized;  // SCS: slot_elem filled on demand for pp_ps_get_layout
   // SCS
   int C, V, nchunks, nslices;
   int* offsets;
@@ -179,6 +180,8 @@ struct pp_ps {
   int* row_to_element;
   int* element_to_row;
   int* tile_slice;
+  int* chunk_start;         // [nchunks] first slot of each chunk
+  int* row_ppe;             // [nrows] particles per row at the last (re)build
   int64_t* elem_gids;       // [nelems] or null
   PsView view() const;
 };

@@ -175,7 +175,8 @@ extern "C" pp_status pp_ps_create(const pp_ps_config* cfg, int32_t nmembers,
   ps->members.assign(members, members + nmembers);
   ps->nelems = ne; ps->nptcls = np; ps->capacity = 0; ps->nrows = 0; ps->stride = 0;
   ps->swap_stride = 0; ps->mask_bits = nullptr; ps->mask_words_alloc = 0;
-  ps->slot_elem = nullptr; ps->slot_elem_valid = false;
+  ps->slot_elem = nullptr; ps->slot_elem_valid = false; ps->slot_elem_materialized = false;
+  ps->chunk_start = nullptr; ps->row_ppe = nullptr;
   ps->C = 1; ps->V = cfg->V; ps->nchunks = 0; ps->nslices = 0;
   ps->offsets = ps->slice_to_chunk = ps->row_to_element = ps->element_to_row = ps->tile_slice = nullptr;
   ps->elem_gids = nullptr;
@@ -203,7 +204,7 @@ extern "C" pp_status pp_ps_destroy(pp_ps* ps) {
   for (void* p : ps->swap) cudaFree(p);
   cudaFree(ps->mask_bits); cudaFree(ps->slot_elem); cudaFree(ps->offsets);
   cudaFree(ps->slice_to_chunk); cudaFree(ps->row_to_element); cudaFree(ps->element_to_row);
-  cudaFree(ps->tile_slice); cudaFree(ps->elem_gids);
+  cudaFree(ps->tile_slice); cudaFree(ps->elem_gids); cudaFree(ps->chunk_start); cudaFree(ps->row_ppe);
   delete ps;
   return PP_OK;
 }
@@ -235,11 +236,12 @@ __global__ void k_materialize_slot_elem(PsView v, int* out) {
 extern "C" pp_status pp_ps_get_layout(pp_ps* ps, pp_stream stream_, pp_ps_layout* o) {
   PP_REQUIRE(ps && o, "null argument");
   cudaStream_t s = (cudaStream_t)stream_;
-  if (!ps->slot_elem_valid && ps->capacity > 0) {
+  if (!ps->slot_elem_valid && !ps->slot_elem_materialized && ps->capacity > 0) {
     if (!ps->slot_elem) PP_TRY(pp_dev_alloc(&ps->slot_elem, ps->capacity + 1, s));
     k_materialize_slot_elem<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), ps->slot_elem);
     PP_KERNEL_CHECK();
-    // keep the SCS fast path (tile lookup) for kernels: slot_elem_valid stays false for SCS
+    // kernels keep the SCS tile lookup: slot_elem_valid stays false, the copy is for callers
+    ps->slot_elem_materialized = true;
   }
   o->kind = ps->cfg.kind; o->C = ps->C; o->V = ps->V; o->nchunks = ps->nchunks;
   o->nslices = ps->nslices; o->nrows = ps->nrows; o->capacity = ps->capacity;

@@ -1,7 +1,718 @@
-// pp_scs.cu -- Sell-C-sigma construction (placeholder until the device build lands).
+// pp_scs.cu -- Sell-C-sigma layout construction and the rebuild of every structure kind.
+//
+// Replaces particle_structs/src/scs: chooseChunkHeight SCS_buildFns.h:4-16, sigmaSort
+// SCS_sort.h:4-49 (CUDA branch: ascending thrust::sort_by_key per sigma window),
+// constructChunks :19-98 (with the three padding strategies), constructOffsets :115-153,
+// setupParticleMask :155-199, initSCSData :202-225 and rebuild SCS_rebuild.h:123-314;
+// CSR_rebuild.hpp:18-118 and dps_rebuild.hpp for the flat kinds.
+//
+// B200-first differences: (1) the mask is a bit per slot; (2) a rebuild moves ALL members of a
+// particle in one kernel (the reference launches one gather/scatter kernel per member type);
+// (3) the per-32-slot `tile_slice` table lets any kernel map slot -> row without the
+// slice-per-team launch shape of SellCSigma::parallel_for.
+#include <cub/cub.cuh>
+
 #include "pp_internal.cuh"
 
-pp_status pp_scs_build(pp_ps*, const int*, const int*, const void* const*, int, cudaStream_t) {
-  pp_set_error("Sell-C-sigma construction is not implemented yet");
-  return PP_ERR_UNSUPPORTED;
+pp_status pp_ps_alloc_members(pp_ps* ps, std::vector<void*>& arrs, long stride, cudaStream_t s);
+
+namespace {
+constexpr int kBlock = 256;
+
+struct ScsLayout {
+  int C = 1, nchunks = 0, nrows = 0, nslices = 0, capacity = 0;
+  int* offsets = nullptr;
+  int* slice_to_chunk = nullptr;
+  int* row_to_element = nullptr;
+  int* element_to_row = nullptr;
+  int* chunk_start = nullptr;   // first slot of each chunk
+  int* tile_slice = nullptr;
+  int* row_ppe = nullptr;       // particles per row (sorted order)
+  uint32_t* mask = nullptr;
+  long mask_words = 0;
+};
+
+__global__ void k_count_nonzero(const int* __restrict__ a, int n, int* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool nz = i < n && a[i] > 0;
+  const unsigned m = __ballot_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
+}
+
+// sigmaSort keys: ascending particle count inside windows of `sigma` elements (stable)
+__global__ void k_sort_keys(const int* __restrict__ ppe, int ne, int sigma, uint64_t* keys, int* vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  const uint64_t win = (uint64_t)(i / sigma);
+  keys[i] = (win << 32) | (uint32_t)ppe[i];
+  vals[i] = i;
+}
+
+__global__ void k_rows(const int* __restrict__ sorted_elem, const int* __restrict__ ppe, int ne,
+                       int nrows, int* row2elem, int* elem2row, int* row_ppe) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  if (i < ne) {
+    const int e = sorted_elem ? sorted_elem[i] : i;
+    row2elem[i] = e;
+    elem2row[e] = i;
+    row_ppe[i] = ppe[e];
+  } else {               // padding rows up to a multiple of C (SCS_buildFns.h:39-44)
+    row2elem[i] = i;
+    elem2row[i] = i;
+    row_ppe[i] = 0;
+  }
+}
+
+// chunk width = widest row; cw[0]=sum, cw[1]=count of non-empty chunks; inv = sum of 1/width
+__global__ void k_chunk_widths(const int* __restrict__ row_ppe, int nchunks, int C, int* width,
+                               int* cw, double* inv) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  int w = 0;
+  for (int r = 0; r < C; ++r) w = max(w, row_ppe[(long)c * C + r]);
+  width[c] = w;
+  if (w > 0) {
+    atomicAdd(cw, w);
+    atomicAdd(cw + 1, 1);
+    atomicAdd(inv, 1.0 / w);
+  }
+}
+
+// SCS_buildFns.h:62-97
+__global__ void k_pad_widths(int* width, int nchunks, const int* __restrict__ cw,
+                             const double* __restrict__ inv, double pad, int strat) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const int cw_sum = cw[0], cw_cnt = cw[1];
+  if (cw_sum <= 0) return;
+  const int w = width[c];
+  if (strat == PP_PAD_EVENLY) {
+    const int avg_pad = (int)(cw_sum * pad / cw_cnt);
+    if (w > 0) width[c] = w + avg_pad;
+  } else if (strat == PP_PAD_PROPORTIONALLY) {
+    width[c] = (int)(w + w * pad);
+  } else {
+    const double cw_sum2 = cw_sum / inv[0] * pad;
+    if (w != 0) width[c] = (int)(w + cw_sum2 / w);
+  }
+}
+
+__global__ void k_slices_per_chunk(const int* __restrict__ width, int nchunks, int V, int* spc) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nchunks) return;
+  spc[c] = c < nchunks ? width[c] / V + (width[c] % V != 0) : 0;
+}
+
+__global__ void k_fill_slices(const int* __restrict__ width, const int* __restrict__ slice_off,
+                              int nchunks, int V, int C, int* s2c, int* slice_size) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const int b = slice_off[c], e = slice_off[c + 1];
+  for (int j = b; j < e; ++j) {
+    s2c[j] = c;
+    const int rem = width[c] % V;
+    const int last = rem + (rem == 0) * V;
+    slice_size[j] = (j == e - 1) ? last * C : V * C;
+  }
+}
+
+__global__ void k_chunk_start(const int* __restrict__ slice_off, const int* __restrict__ offsets,
+                              int nchunks, int capacity, int* chunk_start) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  chunk_start[c] = slice_off[c] < slice_off[c + 1] ? offsets[slice_off[c]] : capacity;
+}
+
+__global__ void k_tile_slice(const int* __restrict__ offsets, int nslices, int ntiles, int* tile_slice) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int slot = t * 32;
+  int lo = 0, hi = nslices;   // last S with offsets[S] <= slot
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (offsets[mid] <= slot) lo = mid; else hi = mid;
+  }
+  tile_slice[t] = lo;
+}
+
+// setupParticleMask (SCS_buildFns.h:155-199): slot (row, col) holds a particle iff col < ppe(row)
+__global__ void k_scs_mask(PsView v, const int* __restrict__ row_ppe, int ne, uint32_t* mask, long nwords) {
+  const long s = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  bool bit = false;
+  if (s < v.capacity) {
+    int S = v.tile_slice[s >> 5];
+    while (s >= v.offsets[S + 1]) ++S;
+    const int rel = (int)(s - v.offsets[S]);
+    const int r = rel % v.C;
+    // column inside the chunk = columns of earlier slices of the same chunk + column in slice
+    const int chunk = v.slice_to_chunk[S];
+    int S0 = S;
+    while (S0 > 0 && v.slice_to_chunk[S0 - 1] == chunk) --S0;
+    const int col = (int)((s - v.offsets[S0]) / v.C);
+    const int row = chunk * v.C + r;
+    bit = v.row_to_element[row] < ne && col < row_ppe[row];
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, bit);
+  if ((threadIdx.x & 31) == 0 && (s >> 5) < nwords) mask[s >> 5] = m;
+}
+
+__global__ void k_assign_slots(const int* __restrict__ elems, int n, const int* __restrict__ elem2row,
+                               const int* __restrict__ chunk_start, int C, int* row_fill, int* slots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int row = elem2row[elems[i]];
+  const int col = atomicAdd(row_fill + row, 1);
+  slots[i] = chunk_start[row / C] + row % C + col * C;
+}
+
+// ---- rebuild kernels
+__global__ void k_hist_kept(PsView v, const int* __restrict__ new_elem, int* count) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = -1;
+  if (s < v.capacity) {
+    const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+    if (m) e = new_elem[s];
+  }
+  // warp-aggregated histogram: lanes with the same destination share one atomic
+  const unsigned act = __match_any_sync(0xffffffffu, e);
+  if (e >= 0 && (threadIdx.x & 31) == (__ffs(act) - 1)) atomicAdd(count + e, __popc(act));
+}
+__global__ void k_hist_new(const int* __restrict__ elems, int n, int* count, int* bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = elems[i];
+  if (e < 0) { *bad = 1; return; }
+  atomicAdd(count + e, 1);
+}
+
+struct MemberTable {
+  int n;
+  char* src[16];
+  char* dst[16];
+  int bytes[16];   // scalar bytes
+  int ncomp[16];
+};
+
+// one kernel moves every member of every kept particle (CopyPSToPS psMemberType.h:74-115 moves
+// one member per kernel launch)
+__global__ void k_move_kept(PsView v, const int* __restrict__ new_elem,
+                            const int* __restrict__ elem2row, const int* __restrict__ chunk_start,
+                            int C, int dense, const int* __restrict__ dense_off, int* row_fill,
+                            MemberTable mt, long src_stride, long dst_stride, uint32_t* new_mask_unused,
+                            int* new_slot_of) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.capacity) return;
+  const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  int ns = -1;
+  if (m) {
+    const int e = new_elem[s];
+    if (e >= 0) {
+      if (dense) {
+        ns = dense_off[e] + atomicAdd(row_fill + e, 1);
+      } else {
+        const int row = elem2row[e];
+        const int col = atomicAdd(row_fill + row, 1);
+        ns = chunk_start[row / C] + row % C + col * C;
+      }
+      for (int k = 0; k < mt.n; ++k) {
+        const int sb = mt.bytes[k];
+        for (int c = 0; c < mt.ncomp[k]; ++c) {
+          const char* a = mt.src[k] + ((long)c * src_stride + s) * sb;
+          char* b = mt.dst[k] + ((long)c * dst_stride + ns) * sb;
+          if (sb == 8) *(double*)b = *(const double*)a;
+          else if (sb == 4) *(int*)b = *(const int*)a;
+          else for (int q = 0; q < sb; ++q) b[q] = a[q];
+        }
+      }
+    }
+  }
+  if (new_slot_of) new_slot_of[s] = ns;
+}
+
+__global__ void k_place_new(const int* __restrict__ slots, int n, MemberTable mt, long dst_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ns = slots[i];
+  for (int k = 0; k < mt.n; ++k) {
+    const int sb = mt.bytes[k];
+    for (int c = 0; c < mt.ncomp[k]; ++c) {
+      const char* a = mt.src[k] + ((long)c * n + i) * sb;   // new particle arrays are [ncomp][n]
+      char* b = mt.dst[k] + ((long)c * dst_stride + ns) * sb;
+      if (sb == 8) *(double*)b = *(const double*)a;
+      else if (sb == 4) *(int*)b = *(const int*)a;
+      else for (int q = 0; q < sb; ++q) b[q] = a[q];
+    }
+  }
+}
+
+__global__ void k_assign_dense(const int* __restrict__ elems, int n, const int* __restrict__ off,
+                               int* fill, int* slots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = elems[i];
+  slots[i] = off[e] + atomicAdd(fill + e, 1);
+}
+
+__global__ void k_mask_first_n2(uint32_t* mask, long nwords, int n) {
+  long w = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (w >= nwords) return;
+  long lo = w * 32;
+  uint32_t v = 0;
+  if (lo + 32 <= n) v = 0xffffffffu;
+  else if (lo < n) v = (1u << (n - lo)) - 1u;
+  mask[w] = v;
+}
+
+__global__ void k_expand_offsets2(const int* __restrict__ off, int ne, int n, int cap, int* slot_elem) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cap) return;
+  if (s >= n) { slot_elem[s] = 0; return; }
+  int lo = 0, hi = ne;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= s) lo = mid; else hi = mid;
+  }
+  slot_elem[s] = lo;
+}
+
+// DPS rebuild: particles stay where they are; deleted slots become holes that new particles fill
+__global__ void k_dps_update(PsView v, const int* __restrict__ new_elem, int* slot_elem,
+                             uint32_t* mask, int* nkept) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (s < v.capacity) {
+    const bool m = (mask[s >> 5] >> (s & 31)) & 1u;
+    if (m) {
+      const int e = new_elem[s];
+      if (e >= 0) { keep = true; slot_elem[s] = e; }
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, keep);
+  if ((threadIdx.x & 31) == 0) {
+    if ((s >> 5) < (v.capacity + 31) / 32) mask[s >> 5] = b;
+    if (b) atomicAdd(nkept, __popc(b));
+  }
+}
+// rank the free slots: hole h (0-based among unset mask bits in slot order) receives new particle h
+__global__ void k_dps_hole_count(const uint32_t* __restrict__ mask, long nwords, int cap, int* cnt) {
+  long w = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (w > nwords) return;
+  if (w == nwords) { cnt[w] = 0; return; }
+  uint32_t free_bits = ~mask[w];
+  const long lo = w * 32;
+  if (lo + 32 > cap) free_bits &= (cap > lo) ? ((1u << (cap - lo)) - 1u) : 0u;
+  cnt[w] = __popc(free_bits);
+}
+__global__ void k_dps_fill_holes(uint32_t* mask, long nwords, int cap, const int* __restrict__ hole_off,
+                                 const int* __restrict__ new_elems, int n_new, int* slot_elem, int* slots) {
+  long w = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (w >= nwords) return;
+  uint32_t free_bits = ~mask[w];
+  const long lo = w * 32;
+  if (lo + 32 > cap) free_bits &= (cap > lo) ? ((1u << (cap - lo)) - 1u) : 0u;
+  int h = hole_off[w];
+  uint32_t set = 0;
+  while (free_bits && h < n_new) {
+    const int b = __ffs(free_bits) - 1;
+    free_bits &= free_bits - 1;
+    const int s = (int)(lo + b);
+    slots[h] = s;
+    slot_elem[s] = new_elems[h];
+    set |= 1u << b;
+    ++h;
+  }
+  if (set) mask[w] |= set;
+}
+
+pp_status scan_exclusive(const int* in, int* out, int n, cudaStream_t s) {
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s);
+  char* tmp;
+  PP_TRY(pp_dev_alloc(&tmp, tb, s));
+  PP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, s));
+  pp_dev_free(tmp, s);
+  return PP_OK;
+}
+
+void free_layout(ScsLayout& L, cudaStream_t s) {
+  pp_dev_free(L.offsets, s); pp_dev_free(L.slice_to_chunk, s); pp_dev_free(L.row_to_element, s);
+  pp_dev_free(L.element_to_row, s); pp_dev_free(L.chunk_start, s); pp_dev_free(L.tile_slice, s);
+  pp_dev_free(L.row_ppe, s); pp_dev_free(L.mask, s);
+  L = ScsLayout();
+}
+
+// Everything SellCSigma::construct derives from particles-per-element (SellCSigma.h:230-283)
+pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, cudaStream_t s,
+                     ScsLayout& L) {
+  int* scal;
+  double* inv;
+  PP_TRY(pp_dev_alloc(&scal, 4, s));
+  PP_TRY(pp_dev_alloc(&inv, 1, s));
+  PP_CUDA(cudaMemsetAsync(scal, 0, 4 * sizeof(int), s));
+  PP_CUDA(cudaMemsetAsync(inv, 0, sizeof(double), s));
+  // chooseChunkHeight (SCS_buildFns.h:4-16)
+  k_count_nonzero<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(ppe_dev, ne, scal + 2);
+  int nnz = 0;
+  PP_CUDA(cudaMemcpyAsync(&nnz, scal + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  const int Cmax = cfg.team_size > 0 ? cfg.team_size : 1;
+  L.C = nnz == 0 ? 1 : (nnz < Cmax ? nnz : Cmax);
+  const int C = L.C;
+  L.nchunks = ne / C + (ne % C != 0);
+  L.nrows = L.nchunks * C;
+  // sigmaSort (SCS_sort.h:4-49, CUDA branch)
+  int* sorted_elem = nullptr;
+  if (cfg.sigma > 1) {
+    const int sigma = cfg.sigma < ne ? cfg.sigma : ne;
+    uint64_t *k_in, *k_out;
+    int *v_in;
+    PP_TRY(pp_dev_alloc(&k_in, ne, s));
+    PP_TRY(pp_dev_alloc(&k_out, ne, s));
+    PP_TRY(pp_dev_alloc(&v_in, ne, s));
+    PP_TRY(pp_dev_alloc(&sorted_elem, ne, s));
+    k_sort_keys<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(ppe_dev, ne, sigma > 0 ? sigma : 1, k_in, v_in);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, 64, s);
+    char* tmp;
+    PP_TRY(pp_dev_alloc(&tmp, tb, s));
+    PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, 64, s));
+    pp_dev_free(tmp, s); pp_dev_free(k_in, s); pp_dev_free(k_out, s); pp_dev_free(v_in, s);
+  }
+  PP_TRY(pp_dev_alloc(&L.row_to_element, L.nrows, s));
+  PP_TRY(pp_dev_alloc(&L.element_to_row, L.nrows, s));
+  PP_TRY(pp_dev_alloc(&L.row_ppe, L.nrows, s));
+  k_rows<<<pp_div_up(L.nrows, kBlock), kBlock, 0, s>>>(sorted_elem, ppe_dev, ne, L.nrows,
+                                                      L.row_to_element, L.element_to_row, L.row_ppe);
+  pp_dev_free(sorted_elem, s);
+  // constructChunks (SCS_buildFns.h:19-98)
+  int *width, *spc, *slice_off;
+  PP_TRY(pp_dev_alloc(&width, L.nchunks, s));
+  PP_TRY(pp_dev_alloc(&spc, L.nchunks + 1, s));
+  PP_TRY(pp_dev_alloc(&slice_off, L.nchunks + 1, s));
+  k_chunk_widths<<<pp_div_up(L.nchunks, kBlock), kBlock, 0, s>>>(L.row_ppe, L.nchunks, C, width, scal, inv);
+  if (cfg.shuffle_padding > 0)
+    k_pad_widths<<<pp_div_up(L.nchunks, kBlock), kBlock, 0, s>>>(width, L.nchunks, scal, inv,
+                                                                 cfg.shuffle_padding, cfg.padding_strat);
+  // constructOffsets (SCS_buildFns.h:115-153)
+  const int V = cfg.V > 0 ? cfg.V : 1;
+  k_slices_per_chunk<<<pp_div_up(L.nchunks + 1, kBlock), kBlock, 0, s>>>(width, L.nchunks, V, spc);
+  PP_TRY(scan_exclusive(spc, slice_off, L.nchunks + 1, s));
+  PP_CUDA(cudaMemcpyAsync(&L.nslices, slice_off + L.nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  int* slice_size;
+  PP_TRY(pp_dev_alloc(&slice_size, L.nslices + 1, s));
+  PP_TRY(pp_dev_alloc(&L.slice_to_chunk, L.nslices + 1, s));
+  PP_TRY(pp_dev_alloc(&L.offsets, L.nslices + 2, s));
+  PP_CUDA(cudaMemsetAsync(slice_size, 0, sizeof(int) * (L.nslices + 1), s));
+  k_fill_slices<<<pp_div_up(L.nchunks, kBlock), kBlock, 0, s>>>(width, slice_off, L.nchunks, V, C,
+                                                               L.slice_to_chunk, slice_size);
+  PP_TRY(scan_exclusive(slice_size, L.offsets, L.nslices + 1, s));
+  PP_CUDA(cudaMemcpyAsync(&L.capacity, L.offsets + L.nslices, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  PP_TRY(pp_dev_alloc(&L.chunk_start, L.nchunks, s));
+  k_chunk_start<<<pp_div_up(L.nchunks, kBlock), kBlock, 0, s>>>(slice_off, L.offsets, L.nchunks,
+                                                               L.capacity, L.chunk_start);
+  const int ntiles = (L.capacity + 31) / 32;
+  PP_TRY(pp_dev_alloc(&L.tile_slice, ntiles + 1, s));
+  if (ntiles > 0)
+    k_tile_slice<<<pp_div_up(ntiles, kBlock), kBlock, 0, s>>>(L.offsets, L.nslices, ntiles, L.tile_slice);
+  L.mask_words = ntiles + 1;
+  PP_TRY(pp_dev_alloc(&L.mask, L.mask_words, s));
+  PP_CUDA(cudaMemsetAsync(L.mask, 0, sizeof(uint32_t) * L.mask_words, s));
+  PP_KERNEL_CHECK();
+  pp_dev_free(width, s); pp_dev_free(spc, s); pp_dev_free(slice_off, s); pp_dev_free(slice_size, s);
+  pp_dev_free(scal, s); pp_dev_free(inv, s);
+  return PP_OK;
+}
+
+PsView layout_view(const ScsLayout& L, int ne) {
+  PsView v;
+  v.kind = PP_PS_SCS; v.capacity = L.capacity; v.mask_bits = L.mask; v.slot_elem = nullptr;
+  v.offsets = L.offsets; v.slice_to_chunk = L.slice_to_chunk; v.row_to_element = L.row_to_element;
+  v.tile_slice = L.tile_slice; v.C = L.C; v.nslices = L.nslices;
+  (void)ne;
+  return v;
+}
+
+void adopt_layout(pp_ps* ps, ScsLayout& L, cudaStream_t s) {
+  pp_dev_free(ps->offsets, s); pp_dev_free(ps->slice_to_chunk, s); pp_dev_free(ps->row_to_element, s);
+  pp_dev_free(ps->element_to_row, s); pp_dev_free(ps->tile_slice, s); pp_dev_free(ps->mask_bits, s);
+  pp_dev_free(ps->chunk_start, s); pp_dev_free(ps->row_ppe, s);
+  ps->C = L.C; ps->nchunks = L.nchunks; ps->nrows = L.nrows; ps->nslices = L.nslices;
+  ps->capacity = L.capacity;
+  ps->offsets = L.offsets; ps->slice_to_chunk = L.slice_to_chunk;
+  ps->row_to_element = L.row_to_element; ps->element_to_row = L.element_to_row;
+  ps->tile_slice = L.tile_slice; ps->mask_bits = L.mask; ps->mask_words_alloc = L.mask_words;
+  ps->chunk_start = L.chunk_start; ps->row_ppe = L.row_ppe;
+  L = ScsLayout();
+  if (ps->slot_elem) { pp_dev_free(ps->slot_elem, s); ps->slot_elem = nullptr; }
+  ps->slot_elem_valid = false;
+  ps->slot_elem_materialized = false;
+}
+
+pp_status member_table(const pp_ps* ps, const std::vector<void*>& src, const std::vector<void*>& dst,
+                       MemberTable& mt) {
+  PP_REQUIRE(ps->nmembers <= 16, "at most 16 particle members are supported");
+  mt.n = ps->nmembers;
+  for (int i = 0; i < ps->nmembers; ++i) {
+    mt.src[i] = (char*)(src.empty() ? nullptr : src[i]);
+    mt.dst[i] = (char*)dst[i];
+    mt.bytes[i] = ps->members[i].scalar_bytes;
+    mt.ncomp[i] = ps->members[i].ncomp;
+  }
+  return PP_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// SellCSigma::construct (SellCSigma.h:230-283)
+// ------------------------------------------------------------------------------------------
+pp_status pp_scs_build(pp_ps* ps, const int* ppe_dev, const int* pelems_dev,
+                       const void* const* pinfo, int memspace, cudaStream_t s) {
+  ScsLayout L;
+  PP_TRY(scs_layout(ps->cfg, ps->nelems, ppe_dev, s, L));
+  const int ne = ps->nelems, np = ps->nptcls;
+  if (L.capacity > 0 && np > 0) {
+    PsView v = layout_view(L, ne);
+    k_scs_mask<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(v, L.row_ppe, ne, L.mask, L.mask_words);
+  }
+  adopt_layout(ps, L, s);
+  ps->V = ps->cfg.V;
+  // allocate the data and its swap copy with extra padding (SellCSigma.h:264-272)
+  long cap = ps->capacity;
+  if (ps->cfg.extra_padding > 0) cap = (long)(cap * (1 + ps->cfg.extra_padding));
+  if (cap < 1) cap = 1;
+  ps->stride = cap;
+  PP_TRY(pp_ps_alloc_members(ps, ps->data, ps->stride, s));
+  if (!ps->cfg.always_realloc) {
+    PP_TRY(pp_ps_alloc_members(ps, ps->swap, ps->stride, s));
+    ps->swap_stride = ps->stride;
+  }
+  // initSCSData (SCS_buildFns.h:202-225)
+  if (np > 0 && pelems_dev && pinfo) {
+    int *row_fill, *slots;
+    PP_TRY(pp_dev_alloc(&row_fill, ps->nrows, s));
+    PP_TRY(pp_dev_alloc(&slots, np, s));
+    PP_CUDA(cudaMemsetAsync(row_fill, 0, sizeof(int) * ps->nrows, s));
+    k_assign_slots<<<pp_div_up(np, kBlock), kBlock, 0, s>>>(pelems_dev, np, ps->element_to_row,
+                                                            ps->chunk_start, ps->C, row_fill, slots);
+    MemberTable mt;
+    std::vector<void*> srcs(ps->nmembers, nullptr);
+    std::vector<char*> staged(ps->nmembers, nullptr);
+    for (int i = 0; i < ps->nmembers; ++i) {
+      const size_t bytes = (size_t)ps->members[i].scalar_bytes * ps->members[i].ncomp * np;
+      PP_TRY(pp_dev_import(&staged[i], (const char*)pinfo[i], bytes, memspace, s));
+      srcs[i] = staged[i];
+    }
+    PP_TRY(member_table(ps, srcs, ps->data, mt));
+    k_place_new<<<pp_div_up(np, kBlock), kBlock, 0, s>>>(slots, np, mt, ps->stride);
+    for (char* p : staged) pp_dev_free(p, s);
+    pp_dev_free(row_fill, s); pp_dev_free(slots, s);
+  }
+  PP_KERNEL_CHECK();
+  return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// rebuild (SCS_rebuild.h:123-314; CSR_rebuild.hpp:18-118; dps_rebuild.hpp)
+// ------------------------------------------------------------------------------------------
+extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
+                                   const int32_t* new_particle_elements,
+                                   const void* const* new_particle_info, pp_stream stream_) {
+  PP_REQUIRE(ps && (new_element || ps->capacity == 0), "null argument");
+  PP_REQUIRE(n_new >= 0, "negative number of new particles");
+  PP_REQUIRE(n_new == 0 || (new_particle_elements && new_particle_info),
+             "new particles need their elements and member data");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int ne = ps->nelems;
+  const int kind = ps->cfg.kind;
+  int* scal;
+  PP_TRY(pp_dev_alloc(&scal, 4, s));
+  PP_CUDA(cudaMemsetAsync(scal, 0, 4 * sizeof(int), s));
+  MemberTable mt_new;
+  {
+    std::vector<void*> srcs(ps->nmembers, nullptr);
+    for (int i = 0; i < ps->nmembers && n_new > 0; ++i) srcs[i] = (void*)new_particle_info[i];
+    PP_TRY(member_table(ps, srcs, ps->data, mt_new));
+  }
+
+  if (kind == PP_PS_DPS) {
+    // in place: kept particles only change their parent element; holes are refilled
+    if (ps->capacity > 0)
+      k_dps_update<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_element,
+                                                                      ps->slot_elem, ps->mask_bits, scal);
+    int nkept = 0;
+    PP_CUDA(cudaMemcpyAsync(&nkept, scal, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+    const long need = (long)nkept + n_new;
+    if (need > ps->capacity) {
+      // grow: capacity rule of dps.hpp:129-132 applied to the new particle count
+      const int new_cap = (int)ceil(ceil(double(need) / 32) * (1 + ps->cfg.extra_padding)) * 32;
+      std::vector<void*> nd;
+      PP_TRY(pp_ps_alloc_members(ps, nd, new_cap, s));
+      for (int i = 0; i < ps->nmembers; ++i) {
+        const int sb = ps->members[i].scalar_bytes;
+        for (int c = 0; c < ps->members[i].ncomp; ++c)
+          PP_CUDA(cudaMemcpyAsync((char*)nd[i] + (size_t)c * new_cap * sb,
+                                  (char*)ps->data[i] + (size_t)c * ps->stride * sb,
+                                  (size_t)ps->capacity * sb, cudaMemcpyDeviceToDevice, s));
+        pp_dev_free((char*)ps->data[i], s);
+      }
+      ps->data = nd;
+      int* nse;
+      uint32_t* nm;
+      const long nw = (new_cap + 31) / 32 + 1;
+      PP_TRY(pp_dev_alloc(&nse, new_cap + 1, s));
+      PP_TRY(pp_dev_alloc(&nm, nw, s));
+      PP_CUDA(cudaMemsetAsync(nse, 0, sizeof(int) * (new_cap + 1), s));
+      PP_CUDA(cudaMemsetAsync(nm, 0, sizeof(uint32_t) * nw, s));
+      PP_CUDA(cudaMemcpyAsync(nse, ps->slot_elem, sizeof(int) * ps->capacity, cudaMemcpyDeviceToDevice, s));
+      PP_CUDA(cudaMemcpyAsync(nm, ps->mask_bits, sizeof(uint32_t) * ((ps->capacity + 31) / 32),
+                              cudaMemcpyDeviceToDevice, s));
+      pp_dev_free(ps->slot_elem, s); pp_dev_free(ps->mask_bits, s);
+      ps->slot_elem = nse; ps->mask_bits = nm; ps->mask_words_alloc = nw;
+      ps->capacity = new_cap; ps->stride = new_cap;
+    }
+    if (n_new > 0) {
+      const long nwords = (ps->capacity + 31) / 32;
+      int *cnt, *off, *slots;
+      PP_TRY(pp_dev_alloc(&cnt, nwords + 1, s));
+      PP_TRY(pp_dev_alloc(&off, nwords + 1, s));
+      PP_TRY(pp_dev_alloc(&slots, n_new, s));
+      k_dps_hole_count<<<pp_div_up(nwords + 1, kBlock), kBlock, 0, s>>>(ps->mask_bits, nwords, ps->capacity, cnt);
+      PP_TRY(scan_exclusive(cnt, off, (int)nwords + 1, s));
+      k_dps_fill_holes<<<pp_div_up(nwords, kBlock), kBlock, 0, s>>>(ps->mask_bits, nwords, ps->capacity, off,
+                                                                    new_particle_elements, n_new,
+                                                                    ps->slot_elem, slots);
+      for (int i = 0; i < ps->nmembers; ++i) mt_new.dst[i] = (char*)ps->data[i];
+      k_place_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, mt_new, ps->stride);
+      pp_dev_free(cnt, s); pp_dev_free(off, s); pp_dev_free(slots, s);
+    }
+    ps->nptcls = (int)need;
+    PP_KERNEL_CHECK();
+    pp_dev_free(scal, s);
+    return PP_OK;
+  }
+
+  // ---- element-sorted kinds: histogram of destinations (countNewParticles / rebuild_count)
+  int* count;
+  PP_TRY(pp_dev_alloc(&count, ne + 1, s));
+  PP_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ne + 1), s));
+  if (ps->capacity > 0)
+    k_hist_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count);
+  if (n_new > 0)
+    k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, scal + 1);
+  int* tot_dev;
+  PP_TRY(pp_dev_alloc(&tot_dev, ne + 2, s));
+  PP_TRY(scan_exclusive(count, tot_dev, ne + 1, s));   // tot_dev[ne] = active particles
+  int active = 0, bad = 0;
+  PP_CUDA(cudaMemcpyAsync(&active, tot_dev + ne, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaMemcpyAsync(&bad, scal + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  if (bad) {   // SCS_rebuild.h:147-151 (the reference exits the process)
+    pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s);
+    pp_set_error("there are new particles being added that are marked as inactive (element id -1)");
+    return PP_ERR_INVALID;
+  }
+
+  if (kind == PP_PS_CSR) {
+    // CSR: dense element-major array, capacity = 1.05 * particles (CSR_buildFns.hpp:55-93)
+    int new_cap = (int)(active * 1.05);
+    if (new_cap < active) new_cap = active;
+    const long new_stride = new_cap > 0 ? new_cap : 1;
+    std::vector<void*> nd;
+    PP_TRY(pp_ps_alloc_members(ps, nd, new_stride, s));
+    int* fill;
+    PP_TRY(pp_dev_alloc(&fill, ne + 1, s));
+    PP_CUDA(cudaMemsetAsync(fill, 0, sizeof(int) * (ne + 1), s));
+    MemberTable mt;
+    PP_TRY(member_table(ps, ps->data, nd, mt));
+    if (ps->capacity > 0)
+      k_move_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
+          ps->view(), new_element, nullptr, nullptr, 1, 1, tot_dev, fill, mt, ps->stride, new_stride,
+          nullptr, nullptr);
+    if (n_new > 0) {
+      int* slots;
+      PP_TRY(pp_dev_alloc(&slots, n_new, s));
+      k_assign_dense<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, tot_dev, fill, slots);
+      for (int i = 0; i < ps->nmembers; ++i) mt_new.dst[i] = (char*)nd[i];
+      k_place_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, mt_new, new_stride);
+      pp_dev_free(slots, s);
+    }
+    for (void* p : ps->data) pp_dev_free((char*)p, s);
+    ps->data = nd;
+    ps->stride = new_stride;
+    pp_dev_free(ps->mask_bits, s); pp_dev_free(ps->slot_elem, s); pp_dev_free(ps->offsets, s);
+    const long nwords = (new_cap + 31) / 32 + 1;
+    PP_TRY(pp_dev_alloc(&ps->mask_bits, nwords, s));
+    ps->mask_words_alloc = nwords;
+    k_mask_first_n2<<<pp_div_up(nwords, kBlock), kBlock, 0, s>>>(ps->mask_bits, nwords, active);
+    PP_TRY(pp_dev_alloc(&ps->slot_elem, new_cap + 1, s));
+    if (new_cap > 0)
+      k_expand_offsets2<<<pp_div_up(new_cap, kBlock), kBlock, 0, s>>>(tot_dev, ne, active, new_cap, ps->slot_elem);
+    ps->offsets = tot_dev;
+    ps->slot_elem_valid = true;
+    ps->capacity = new_cap;
+    ps->nptcls = active;
+    PP_KERNEL_CHECK();
+    pp_dev_free(fill, s); pp_dev_free(count, s); pp_dev_free(scal, s);
+    return PP_OK;
+  }
+
+  // ---- SCS / CabM
+  if (active == 0) {   // SCS_rebuild.h:169-181: structure keeps its shape, mask cleared
+    PP_CUDA(cudaMemsetAsync(ps->mask_bits, 0, sizeof(uint32_t) * ps->mask_words_alloc, s));
+    ps->nptcls = 0;
+    pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s);
+    return PP_OK;
+  }
+  ScsLayout L;
+  PP_TRY(scs_layout(ps->cfg, ne, count, s, L));
+  // (re)allocate the swap buffer: SCS_rebuild.h:223-229 (condition reproduced as written)
+  if (ps->cfg.always_realloc || ps->swap.empty() || ps->swap_stride < L.capacity ||
+      ps->swap_stride * ps->cfg.minimize_size < L.capacity) {
+    for (void* p : ps->swap) pp_dev_free((char*)p, s);
+    long nstride = (long)(L.capacity * (1 + ps->cfg.extra_padding));
+    if (nstride < L.capacity) nstride = L.capacity;
+    if (nstride < 1) nstride = 1;
+    PP_TRY(pp_ps_alloc_members(ps, ps->swap, nstride, s));
+    ps->swap_stride = nstride;
+  }
+  int* row_fill;
+  PP_TRY(pp_dev_alloc(&row_fill, L.nrows + 1, s));
+  PP_CUDA(cudaMemsetAsync(row_fill, 0, sizeof(int) * (L.nrows + 1), s));
+  MemberTable mt;
+  PP_TRY(member_table(ps, ps->data, ps->swap, mt));
+  if (ps->capacity > 0)
+    k_move_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
+        ps->view(), new_element, L.element_to_row, L.chunk_start, L.C, 0, nullptr, row_fill, mt,
+        ps->stride, ps->swap_stride, nullptr, nullptr);
+  if (n_new > 0) {
+    int* slots;
+    PP_TRY(pp_dev_alloc(&slots, n_new, s));
+    k_assign_slots<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new,
+                                                               L.element_to_row, L.chunk_start, L.C,
+                                                               row_fill, slots);
+    for (int i = 0; i < ps->nmembers; ++i) mt_new.dst[i] = (char*)ps->swap[i];
+    k_place_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, mt_new, ps->swap_stride);
+    pp_dev_free(slots, s);
+  }
+  // mask of the new structure: the first count(row) columns of every row are occupied
+  {
+    PsView v = layout_view(L, ne);
+    k_scs_mask<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(v, L.row_ppe, ne, L.mask, L.mask_words);
+  }
+  PP_KERNEL_CHECK();
+  adopt_layout(ps, L, s);
+  std::swap(ps->data, ps->swap);
+  std::swap(ps->stride, ps->swap_stride);
+  if (ps->cfg.always_realloc) {
+    for (void* p : ps->swap) pp_dev_free((char*)p, s);
+    ps->swap.clear();
+    ps->swap_stride = 0;
+  }
+  ps->nptcls = active;
+  pp_dev_free(row_fill, s); pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s);
+  return PP_OK;
 }

@@ -61,7 +61,8 @@ def init3d_internal(mesh, slot_elem, mask, seed=PARTICLE_SEED):
     x[h] = xx[h]
     theta = ang * 2 * np.pi
     zdir = rr * 2 - 1
-    V = mesh.coords[mesh.elem2verts[slot_elem]]        # [cap,4,3]
+    se = np.where(mask.astype(bool), slot_elem, 0)     # padding rows carry element ids >= nelems
+    V = mesh.coords[mesh.elem2verts[se]]               # [cap,4,3]
     a = 1 - x - y - z
     pos = (a[:, None] * V[:, 0] + x[:, None] * V[:, 1]) + y[:, None] * V[:, 2]
     pos = pos + z[:, None] * V[:, 3]
@@ -82,7 +83,8 @@ def init2d_internal(mesh, slot_elem, mask, seed=PARTICLE_SEED):
     x, y, ang = r[:, 0].copy(), r[:, 1].copy(), r[:, 2] * 2 * np.pi
     f = x + y > 1
     x[f], y[f] = 1 - x[f], 1 - y[f]
-    V = mesh.coords[mesh.elem2verts[slot_elem]]        # [cap,3,2]
+    se = np.where(mask.astype(bool), slot_elem, 0)
+    V = mesh.coords[mesh.elem2verts[se]]               # [cap,3,2]
     pos = (V[:, 0] + x[:, None] * (V[:, 1] - V[:, 0])) + y[:, None] * (V[:, 2] - V[:, 0])
     X = np.zeros((3, cap))
     D = np.zeros((3, cap))

@@ -1,0 +1,279 @@
+"""GPU tests of the particle structures, following particle_structs/test/{buildSCSTest.cpp,
+test_structure.cpp,test_rebuild.cpp}: invariants keyed by particle id (slot numbering and row
+order are backend-dependent in the reference)."""
+import numpy as np
+import pytest
+
+from gpu_common import dev, pp, torch
+
+pytestmark = pytest.mark.gpu
+
+TYPES = [(np.int32, 1), (np.float64, 3), (np.int32, 1)]      # test particle: id, vec3, int
+
+
+def _kinds():
+    P = pp()
+    return {
+        "scs_c32": dict(kind=P.capi.PP_PS_SCS, team_size=32, sigma=0x7fffffff, V=1024),
+        "scs_s1_v10": dict(kind=P.capi.PP_PS_SCS, team_size=32, sigma=1, V=10),
+        "scs_c4_v2": dict(kind=P.capi.PP_PS_SCS, team_size=4, sigma=0x7fffffff, V=2),
+        "scs_s7": dict(kind=P.capi.PP_PS_SCS, team_size=8, sigma=7, V=3),
+        "scs_padprop": dict(kind=P.capi.PP_PS_SCS, team_size=32, config={"padding_strat": 1}),
+        "scs_padinv": dict(kind=P.capi.PP_PS_SCS, team_size=32, config={"padding_strat": 2}),
+        "csr": dict(kind=P.capi.PP_PS_CSR),
+        "cabm": dict(kind=P.capi.PP_PS_CABM),
+        "dps": dict(kind=P.capi.PP_PS_DPS),
+    }
+
+
+KINDS = ["scs_c32", "scs_s1_v10", "scs_c4_v2", "scs_s7", "scs_padprop", "scs_padinv", "csr", "cabm", "dps"]
+SIZES = [(5, 25), (50, 1000), (2500, 100000), (1, 40), (300, 0)]
+
+
+def _ppe(ne, np_, seed=3):
+    rng = np.random.default_rng(seed)
+    if np_ == 0:
+        return np.zeros(ne, np.int32)
+    w = rng.random(ne) ** 3          # skewed, with empty elements
+    w[rng.random(ne) < 0.2] = 0
+    if w.sum() == 0:
+        w[0] = 1
+    ppe = np.floor(w / w.sum() * np_).astype(np.int32)
+    ppe[np.argmax(w)] += np_ - ppe.sum()
+    return ppe
+
+
+def _make(kindname, ne, np_, with_data=False, seed=3):
+    P = pp()
+    ppe = _ppe(ne, np_, seed)
+    kw = dict(_kinds()[kindname])
+    kind = kw.pop("kind")
+    pel = info = None
+    if with_data:
+        pel = np.repeat(np.arange(ne, dtype=np.int32), ppe)
+        rng = np.random.default_rng(seed + 1)
+        rng.shuffle(pel)
+        ids = np.arange(np_, dtype=np.int32)
+        info = [ids.reshape(1, -1), rng.random((3, np_)), (ids * 7).reshape(1, -1)]
+    ps = P.ParticleStructure(kind, TYPES, ppe, particle_elements=pel, particle_info=info, **kw)
+    return ps, ppe, pel, info
+
+
+@pytest.mark.parametrize("kindname", KINDS)
+@pytest.mark.parametrize("ne,np_", SIZES)
+def test_build_counts_and_layout(kindname, ne, np_):
+    """buildSCSTest.cpp:47-129 / test_structure.cpp:43-113: sizes, per-element counts, mask."""
+    ps, ppe, _, _ = _make(kindname, ne, np_)
+    assert ps.nelems == ne and ps.nptcls == np_
+    assert ps.capacity >= np_
+    slot_elem, mask = ps.slot_elem_and_mask()
+    assert mask.sum() == np_
+    m = mask.astype(bool)
+    assert np.array_equal(np.bincount(slot_elem[m], minlength=ne)[:ne], ppe)
+    lay = ps.layout()
+    if lay.kind in (0, 2) and np_ > 0:           # Sell-C-sigma geometry (SellCSigma.h:541-551)
+        t = torch()
+        from importlib import import_module
+        api = import_module("pumi-pic_b200").api
+        off = api._tensor_from_ptr(lay.offsets, (lay.nslices + 1,), t.int32, ps).cpu().numpy()
+        s2c = api._tensor_from_ptr(lay.slice_to_chunk, (lay.nslices,), t.int32, ps).cpu().numpy()
+        r2e = api._tensor_from_ptr(lay.row_to_element, (lay.nrows,), t.int32, ps).cpu().numpy()
+        e2r = api._tensor_from_ptr(lay.element_to_row, (lay.nrows,), t.int32, ps).cpu().numpy()
+        assert off[0] == 0 and off[-1] == ps.capacity and ps.numrows == lay.nchunks * lay.C
+        assert np.all(np.diff(off) % lay.C == 0) and np.all(np.diff(off) // lay.C <= lay.V)
+        assert np.all(np.diff(s2c) >= 0)
+        assert np.array_equal(r2e[e2r[:ne]], np.arange(ne)) and np.array_equal(np.sort(r2e), np.arange(lay.nrows))
+        # slot -> element through the slice geometry must equal the library's own map
+        want = np.empty(ps.capacity, np.int32)
+        for S in range(lay.nslices):
+            n = off[S + 1] - off[S]
+            rows = s2c[S] * lay.C + (np.arange(n) % lay.C)
+            want[off[S]:off[S + 1]] = r2e[rows]
+        assert np.array_equal(want, slot_elem)
+        # sigma sort: ascending particle count inside each window (SCS_sort.h CUDA branch)
+        sigma = min(_kinds()[kindname].get("sigma", 0x7fffffff), ne)
+        counts = ppe[r2e[:ne]]
+        if sigma > 1:
+            for w0 in range(0, ne, sigma):
+                assert np.all(np.diff(counts[w0:w0 + sigma]) >= 0)
+                assert set(r2e[:ne][w0:w0 + sigma]) == set(range(w0, min(w0 + sigma, ne)))
+        else:
+            assert np.array_equal(r2e[:ne], np.arange(ne))
+
+
+@pytest.mark.parametrize("kindname", ["scs_c32", "scs_c4_v2", "dps"])
+def test_build_with_particle_data(kindname):
+    """initSCSData / fillAoSoA: every given particle lands in its element with its data intact."""
+    ne, np_ = 300, 20000
+    ps, ppe, pel, info = _make(kindname, ne, np_, with_data=True)
+    slot_elem, mask = ps.slot_elem_and_mask()
+    m = mask.astype(bool)
+    ids = ps.get(0).cpu().numpy()[0, :ps.capacity][m]
+    assert np.array_equal(np.sort(ids), np.arange(np_))
+    assert np.array_equal(slot_elem[m], pel[ids])
+    assert np.array_equal(ps.get(1).cpu().numpy()[:, :ps.capacity][:, m], info[1][:, ids])
+    assert np.array_equal(ps.get(2).cpu().numpy()[0, :ps.capacity][m], ids * 7)
+
+
+def _state(ps):
+    slot_elem, mask = ps.slot_elem_and_mask()
+    return slot_elem, mask.astype(bool)
+
+
+def _set_ids(ps):
+    """pID(p) = p for every slot (the reference tests do this inside the lambda)."""
+    t = torch()
+    ids = ps.get(0)
+    ids[0, :] = t.arange(ids.shape[1], dtype=t.int32, device="cuda")
+    v = ps.get(1)
+    v[:] = (t.arange(v.shape[1], dtype=t.float64, device="cuda") * 0.5)[None, :]
+
+
+def _check(ps, new_element, cap0, removed=None, new_elems=None, np_expected=None):
+    slot_elem, m = _state(ps)
+    ids = ps.get(0).cpu().numpy()[0, :ps.capacity][m]
+    vec = ps.get(1).cpu().numpy()[:, :ps.capacity][:, m]
+    assert ps.nptcls == np_expected == m.sum()
+    old = ids < cap0
+    assert np.array_equal(slot_elem[m][old], new_element[ids[old]])      # destination check
+    assert np.all(vec[:, old] == ids[old] * 0.5)                          # payload moved with it
+    if removed is not None:
+        assert not np.any(removed[ids[old]])
+    if new_elems is not None:
+        newi = ids[~old] - cap0
+        assert np.array_equal(np.sort(newi), np.arange(len(new_elems)))
+        assert np.array_equal(slot_elem[m][~old], new_elems[newi])
+    assert len(np.unique(ids)) == len(ids)
+
+
+@pytest.mark.parametrize("kindname", KINDS)
+@pytest.mark.parametrize("ne,np_", [(5, 25), (50, 1000), (2500, 100000)])
+def test_rebuild_scenarios(kindname, ne, np_):
+    """test_rebuild.cpp: no change, new elements, added, deleted, added+deleted."""
+    t = torch()
+    ps, ppe, _, _ = _make(kindname, ne, np_)
+
+    def setup():
+        _set_ids(ps)
+        slot_elem, m = _state(ps)
+        cap = ps.capacity
+        slots = np.arange(cap)
+        return slot_elem, m, cap, slots
+
+    # 1. rebuildNoChanges (:5-67): id sums per element are conserved
+    slot_elem, m, cap, slots = setup()
+    new_element = np.where(m, slot_elem, -1).astype(np.int32)
+    sums = np.bincount(slot_elem[m], weights=slots[m], minlength=ne)
+    ps.rebuild(dev(new_element))
+    _check(ps, new_element, cap, np_expected=np_)
+    se2, m2 = _state(ps)
+    ids2 = ps.get(0).cpu().numpy()[0, :ps.capacity][m2]
+    assert np.array_equal(np.bincount(se2[m2], weights=ids2, minlength=ne), sums)
+
+    # 2. rebuildNewElems (:70-129): (3e + p) % ne
+    slot_elem, m, cap, slots = setup()
+    new_element = np.where(m, (slot_elem * 3 + slots) % ne, -1).astype(np.int32)
+    ps.rebuild(dev(new_element))
+    _check(ps, new_element, cap, np_expected=np_)
+
+    # 3. rebuildNewPtcls (:132-205): cap/2 new particles
+    slot_elem, m, cap, slots = setup()
+    new_element = np.where(m, (slot_elem * 3 + slots + 2) % ne, -1).astype(np.int32)
+    nnp = cap // 2
+    new_elems = (np.arange(nnp) % ne).astype(np.int32)
+    info = [dev((np.arange(nnp) + cap).astype(np.int32).reshape(1, -1)),
+            t.zeros((3, nnp), dtype=t.float64, device="cuda"),
+            t.zeros((1, nnp), dtype=t.int32, device="cuda")]
+    ps.rebuild(dev(new_element), dev(new_elems), info)
+    _check(ps, new_element, cap, new_elems=new_elems, np_expected=np_ + nnp)
+    np_now = np_ + nnp
+
+    # 4. rebuildPtclsDestroyed (:208-262): every 7th slot removed
+    slot_elem, m, cap, slots = setup()
+    removed = m & (slots % 7 == 0)
+    new_element = np.where(m & ~removed, slot_elem, -1).astype(np.int32)
+    ps.rebuild(dev(new_element))
+    np_now -= int(removed.sum())
+    _check(ps, new_element, cap, removed=removed, np_expected=np_now)
+
+    # 5. rebuildNewAndDestroyed (:265-341)
+    slot_elem, m, cap, slots = setup()
+    removed = m & (slots % 7 == 0)
+    new_element = np.where(m & ~removed, (3 * slot_elem + 7) % ne, -1).astype(np.int32)
+    nnp = cap // 2
+    new_elems = (np.arange(nnp) % ne).astype(np.int32)
+    info = [dev((np.arange(nnp) + cap).astype(np.int32).reshape(1, -1)),
+            t.zeros((3, nnp), dtype=t.float64, device="cuda"),
+            t.zeros((1, nnp), dtype=t.int32, device="cuda")]
+    ps.rebuild(dev(new_element), dev(new_elems), info)
+    np_now += nnp - int(removed.sum())
+    _check(ps, new_element, cap, removed=removed, new_elems=new_elems, np_expected=np_now)
+
+
+@pytest.mark.parametrize("kindname", ["scs_c32", "csr", "dps"])
+def test_rebuild_to_empty_and_refill(kindname):
+    """SCS_rebuild.h:169-181: deleting everything keeps the structure usable."""
+    t = torch()
+    ne, np_ = 40, 900
+    ps, ppe, _, _ = _make(kindname, ne, np_)
+    ps.rebuild(dev(np.full(ps.capacity, -1, np.int32)))
+    assert ps.nptcls == 0
+    _, mask = ps.slot_elem_and_mask()
+    assert mask.sum() == 0
+    n = 333
+    new_elems = (np.arange(n) * 5 % ne).astype(np.int32)
+    info = [dev(np.arange(n, dtype=np.int32).reshape(1, -1)),
+            t.ones((3, n), dtype=t.float64, device="cuda"), t.zeros((1, n), dtype=t.int32, device="cuda")]
+    ps.rebuild(dev(np.full(max(ps.capacity, 1), -1, np.int32)), dev(new_elems), info)
+    assert ps.nptcls == n
+    slot_elem, mask = ps.slot_elem_and_mask()
+    m = mask.astype(bool)
+    ids = ps.get(0).cpu().numpy()[0, :ps.capacity][m]
+    assert np.array_equal(slot_elem[m], new_elems[ids])
+
+
+def test_rebuild_rejects_inactive_new_particles():
+    t = torch()
+    ps, _, _, _ = _make("scs_c32", 10, 100)
+    slot_elem, mask = ps.slot_elem_and_mask()
+    info = [t.zeros((1, 2), dtype=t.int32, device="cuda"), t.zeros((3, 2), dtype=t.float64, device="cuda"),
+            t.zeros((1, 2), dtype=t.int32, device="cuda")]
+    with pytest.raises(pp().PumipicError):
+        ps.rebuild(dev(np.where(mask, slot_elem, -1).astype(np.int32)),
+                   dev(np.array([3, -1], np.int32)), info)
+
+
+@pytest.mark.parametrize("kindname", ["scs_c32", "scs_c4_v2", "csr"])
+def test_search_runs_on_every_structure_kind(kindname):
+    """The fused search walks SCS / CSR slot geometry exactly like the flat structure."""
+    import oracle_api as orc
+    import ptcl_init as pi
+    from gpu_common import PARTICLE, make_gpu_mesh
+    from meshes import kuhn_cube
+    mesh = kuhn_cube(6)
+    P = pp()
+    kw = dict(_kinds()[kindname]); kind = kw.pop("kind")
+    ps = P.ParticleStructure(kind, PARTICLE, pi.even_ppe(mesh.nelems, 30000), **kw)
+    slot_elem, mask = ps.slot_elem_and_mask()
+    X, D = pi.init3d_internal(mesh, slot_elem, mask)
+    stride = ps.get(0).shape[1]
+    Xp = np.zeros((3, stride)); Xp[:, :ps.capacity] = X
+    Dp = np.zeros((3, stride)); Dp[:, :ps.capacity] = D
+    gm = make_gpu_mesh(mesh)
+    t = torch()
+    x = dev(Xp); d = dev(Dp); tg = t.zeros_like(x)
+    ids = t.zeros(ps.capacity, dtype=t.int32, device="cuda")
+    dist = pi.push_distance(mesh)
+    r = P.push_direction_search(gm, ps, d, dist, x, tg, ids, elem_ids_empty=True, from_orig=True)
+    T = np.zeros_like(X); m = mask.astype(bool)
+    T[:, m] = X[:, m] + dist * D[:, m]
+    found, ids_o, _, _, st = orc.OracleMesh(mesh).search_mesh(slot_elem, mask, X, T)
+    assert np.array_equal(ids.cpu().numpy(), ids_o)
+    assert (r.found, r.loops) == (int(found), st.loops)
+    # and the structure follows the particles: rebuild with the new elements
+    ps.get(2)[0, :ps.capacity] = t.arange(ps.capacity, dtype=t.int32, device="cuda")
+    ps.rebuild(ids)
+    se2, m2 = ps.slot_elem_and_mask()
+    m2 = m2.astype(bool)
+    pid = ps.get(2).cpu().numpy()[0, :ps.capacity][m2]
+    assert np.array_equal(se2[m2], ids_o[pid]) and m2.sum() == (ids_o[m] >= 0).sum()
