@@ -217,6 +217,19 @@ pp_status pp_push_direction(pp_ps* ps, double* tgt, const double* dir, int64_t s
 pp_status pp_update_positions(pp_ps* ps, double* x, double* xtgt, int64_t stride,
                               pp_stream stream);
 
+/* test/ellipticalPush.hpp:10-34 setup: phi = atan2(d(z-k), w-h), b = (z-k)/sin(phi), stored as
+ * float like the reference's particle members; :36-70 push: the particle advances `deg` degrees
+ * (scaled by 1/class_id of its row element, 0.01x for class 1) along its ellipse. */
+pp_status pp_push_elliptical_setup(pp_ps* ps, const double* x, int64_t stride, float* b,
+                                   float* phi, double h, double k, double d, pp_stream stream);
+pp_status pp_push_elliptical(pp_mesh* mesh, pp_ps* ps, double* xtgt, int64_t stride,
+                             const float* b, float* phi, double h, double k, double d, double deg,
+                             pp_stream stream);
+/* src/pumipic_ptcl_ops.hpp:33-53 setUnsafeProcs: new_elems = elems, new_procs = owner of the
+ * element when it is not safe on this PICpart (tags from pp_mesh_set_picpart), else this rank. */
+pp_status pp_set_unsafe_procs(pp_mesh* mesh, pp_ps* ps, const int32_t* elems, int32_t* new_elems,
+                              int32_t* new_procs, pp_stream stream);
+
 /* ============================== search =================================================== */
 
 typedef enum pp_search_variant {
@@ -273,6 +286,23 @@ pp_status pp_push_direction_search(pp_mesh* mesh, pp_ps* ps, const double* dir, 
 /* Unfused PIC-form push: xtgt = x + distance*dir for masked slots. */
 pp_status pp_push_from(pp_ps* ps, const double* x, double* xtgt, const double* dir,
                        int64_t stride, double distance, pp_stream stream);
+
+/* ============================== gyro scatter (2D) ======================================== */
+
+/* test/gyroScatter.hpp:96-166 createGyroRingMappings (+ :25-90 searchAndBuildMap): for every
+ * vertex x ring x point the 3 vertices of the triangle containing the ring point, or -1.
+ * map_out: device int32[3*nverts*nrings*points_per_ring].  Forward and backward maps are
+ * identical in the reference (:126-131), build one and use it twice. */
+pp_status pp_gyro_ring_map(pp_mesh* mesh, double rmax, int32_t nrings, int32_t points_per_ring,
+                           double theta_deg, int32_t* map_out, pp_search_stats* stats_host,
+                           pp_stream stream);
+/* test/gyroScatter.hpp:168-229 gyroScatter: scatter_w[nverts] (device) is zeroed and filled. */
+pp_status pp_gyro_scatter(pp_mesh* mesh, pp_ps* ps, const int32_t* v2v, double rmax,
+                          int32_t nrings, int32_t points_per_ring, double* scatter_w,
+                          pp_stream stream);
+/* test/gyroScatter.hpp:244-248 setSyncArray: sync[2v] = fwd[v], sync[2v+1] = bkwd[v] */
+pp_status pp_gyro_interleave(const double* fwd, const double* bkwd, int32_t nverts,
+                             double* sync_array, pp_stream stream);
 
 #ifdef __cplusplus
 }

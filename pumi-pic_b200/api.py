@@ -286,3 +286,44 @@ def update_positions(ps, x, xtgt):
 def push_from(ps, x, xtgt, direction, distance):
     check(lib().pp_push_from(ps.h, _ptr(x), _ptr(xtgt), _ptr(direction), x.shape[1], distance,
                              _stream()))
+
+
+def elliptical_setup(ps, x, b, phi, h, k, d):
+    check(lib().pp_push_elliptical_setup(ps.h, _ptr(x), x.shape[1], _ptr(b), _ptr(phi), h, k, d,
+                                         _stream()))
+
+
+def elliptical_push(mesh, ps, xtgt, b, phi, h, k, d, deg):
+    check(lib().pp_push_elliptical(mesh.h, ps.h, _ptr(xtgt), xtgt.shape[1], _ptr(b), _ptr(phi),
+                                   h, k, d, deg, _stream()))
+
+
+def set_unsafe_procs(mesh, ps, elems):
+    torch = _torch()
+    ne = torch.empty(ps.capacity, dtype=torch.int32, device="cuda")
+    npr = torch.empty(ps.capacity, dtype=torch.int32, device="cuda")
+    check(lib().pp_set_unsafe_procs(mesh.h, ps.h, _ptr(elems), _ptr(ne), _ptr(npr), _stream()))
+    return ne, npr
+
+
+def gyro_ring_map(mesh, rmax, nrings, ppr, theta_deg):
+    torch = _torch()
+    out = torch.empty(3 * mesh.nverts * nrings * ppr, dtype=torch.int32, device="cuda")
+    st = capi.SearchStats()
+    check(lib().pp_gyro_ring_map(mesh.h, rmax, nrings, ppr, theta_deg, _ptr(out), C.byref(st),
+                                 _stream()))
+    return out, SearchResult(st)
+
+
+def gyro_scatter(mesh, ps, v2v, rmax, nrings, ppr):
+    torch = _torch()
+    out = torch.empty(mesh.nverts, dtype=torch.float64, device="cuda")
+    check(lib().pp_gyro_scatter(mesh.h, ps.h, _ptr(v2v), rmax, nrings, ppr, _ptr(out), _stream()))
+    return out
+
+
+def gyro_interleave(fwd, bkwd):
+    torch = _torch()
+    out = torch.empty(2 * fwd.shape[0], dtype=torch.float64, device="cuda")
+    check(lib().pp_gyro_interleave(_ptr(fwd), _ptr(bkwd), fwd.shape[0], _ptr(out), _stream()))
+    return out

@@ -109,6 +109,18 @@ PROTOTYPES = {
     "pp_push_direction": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                     C.c_void_p]),
     "pp_update_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pp_push_elliptical_setup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_double, C.c_double, C.c_double, C.c_void_p]),
+    "pp_push_elliptical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     C.c_void_p]),
+    "pp_set_unsafe_procs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+    "pp_gyro_ring_map": (C.c_int, [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_double,
+                                   C.c_void_p, C.POINTER(SearchStats), C.c_void_p]),
+    "pp_gyro_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
+                                  C.c_int32, C.c_void_p, C.c_void_p]),
+    "pp_gyro_interleave": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "pp_search_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs),
                                  C.POINTER(SearchStats), C.c_void_p]),
     "pp_search_set_staged": (None, [C.c_int32]),

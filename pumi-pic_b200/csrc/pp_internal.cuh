@@ -127,6 +127,7 @@ struct pp_mesh {
   void* walk;       // PPTetRec[nelems] or PPTriRec[nelems]
   PPBccRec3* walk_bcc;  // [nelems] (3D only)
   int* aux;         // [nelems] owner rank if the element is not safe here, else -1
+  int* vert_first_elem;  // [nverts] lowest-numbered element adjacent to each vertex (ask_up(0,dim) first entry)
   // search scratch
   int* stats_dev;   // device counters (see SearchCounters)
 };

@@ -29,6 +29,11 @@ __global__ void k_side_minmax(const int* __restrict__ elem2sides, int nent, int*
   atomicMax(hi + s, e);
 }
 
+__global__ void k_vert_first(const int* __restrict__ ev, int nent, int nv, int* first) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nent) atomicMin(first + ev[i], i / nv);
+}
+
 __global__ void k_side_finalize(const int* __restrict__ lo, const int* __restrict__ hi,
                                 int nsides, int* side2elem, int8_t* exposed, int* n_exposed) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,6 +255,9 @@ extern "C" pp_status pp_mesh_create(const pp_mesh_desc* d, pp_stream stream_, pp
   PP_TRY(pp_dev_alloc(&m->dual, (size_t)ndual + 1, s));
   const size_t rec = dim == 3 ? sizeof(PPTetRec) : sizeof(PPTriRec);
   PP_CUDA(cudaMallocAsync(&m->walk, rec * (size_t)ne, s));
+  PP_TRY(pp_dev_alloc(&m->vert_first_elem, d->nverts, s));
+  k_fill_int<<<pp_div_up(d->nverts, kBlock), kBlock, 0, s>>>(m->vert_first_elem, d->nverts, 0x7fffffff);
+  k_vert_first<<<pp_div_up((long)ne * nv, kBlock), kBlock, 0, s>>>(m->elem2verts, ne * nv, nv, m->vert_first_elem);
   PP_TRY(pp_dev_alloc(&m->aux, ne, s));
   k_fill_int<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(m->aux, ne, -1);
   if (dim == 3) {
@@ -277,7 +285,7 @@ extern "C" pp_status pp_mesh_destroy(pp_mesh* m) {
   cudaFree(m->coords); cudaFree(m->elem2verts); cudaFree(m->elem2sides); cudaFree(m->side2verts);
   cudaFree(m->elem_class); cudaFree(m->measure); cudaFree(m->exposed); cudaFree(m->side2elem);
   cudaFree(m->dual_off); cudaFree(m->dual); cudaFree(m->safe); cudaFree(m->owner);
-  cudaFree(m->walk); cudaFree(m->walk_bcc); cudaFree(m->aux); cudaFree(m->stats_dev);
+  cudaFree(m->walk); cudaFree(m->walk_bcc); cudaFree(m->aux); cudaFree(m->vert_first_elem); cudaFree(m->stats_dev);
   delete m;
   return PP_OK;
 }

@@ -819,15 +819,17 @@ pp_status read_stats(pp_mesh* mesh, int variant, int looplimit, pp_search_stats*
   return PP_OK;
 }
 
-pp_status do_search(pp_mesh* mesh, pp_ps* ps, const pp_search_args* a, const double* dir,
-                    double distance, bool push, int push_from_orig, pp_search_stats* stats_host,
-                    cudaStream_t s) {
-  PP_REQUIRE(mesh && ps && a, "null argument");
+pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_search_args* a,
+                    const double* dir, double distance, bool push, int push_from_orig,
+                    pp_search_stats* stats_host, cudaStream_t s) {
+  PP_REQUIRE(mesh && a, "null argument");
   PP_REQUIRE(a->x_tgt && a->elem_ids, "x_tgt and elem_ids are required");
-  PP_REQUIRE(a->stride >= ps->capacity, "stride smaller than capacity");
-  PP_REQUIRE(ps->nelems == mesh->nelems, "particle structure and mesh disagree on nelems");
+  PP_REQUIRE(a->stride >= view.capacity, "stride smaller than capacity");
+  PP_REQUIRE(ps_nelems == mesh->nelems, "particle structure and mesh disagree on nelems");
+  struct { int capacity; } ps_{view.capacity};
+  auto* ps = &ps_;
   SearchParams p;
-  p.ps = ps->view();
+  p.ps = view;
   p.walk = mesh->walk;
   p.walk_bcc = mesh->walk_bcc;
   p.staged = g_staged_walk;
@@ -882,9 +884,17 @@ pp_status do_search(pp_mesh* mesh, pp_ps* ps, const pp_search_args* a, const dou
 
 }  // namespace
 
+// internal entry for searches over a flat list of points (gyro ring map)
+pp_status pp_search_view(pp_mesh* mesh, const PsView& view, const pp_search_args* args,
+                         pp_search_stats* stats_host, cudaStream_t s) {
+  return do_search(mesh, view, mesh->nelems, args, nullptr, 0.0, false, 0, stats_host, s);
+}
+
 extern "C" pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
                                     pp_search_stats* stats_host, pp_stream stream) {
-  return do_search(mesh, ps, args, nullptr, 0.0, false, 0, stats_host, (cudaStream_t)stream);
+  PP_REQUIRE(ps, "null particle structure");
+  return do_search(mesh, ps->view(), ps->nelems, args, nullptr, 0.0, false, 0, stats_host,
+                   (cudaStream_t)stream);
 }
 
 extern "C" void pp_search_set_staged(int32_t on) { g_staged_walk = on ? 1 : 0; }
@@ -902,6 +912,7 @@ extern "C" pp_status pp_push_direction_search(pp_mesh* mesh, pp_ps* ps, const do
   PP_REQUIRE(dir, "null direction array");
   PP_REQUIRE(args && args->variant == PP_SEARCH_NEW, "fused push needs PP_SEARCH_NEW");
   PP_REQUIRE(args->x_orig, "x_orig is required");
-  return do_search(mesh, ps, args, dir, distance, true, push_from_orig ? 1 : 0, stats_host,
-                   (cudaStream_t)stream);
+  PP_REQUIRE(ps, "null particle structure");
+  return do_search(mesh, ps->view(), ps->nelems, args, dir, distance, true, push_from_orig ? 1 : 0,
+                   stats_host, (cudaStream_t)stream);
 }
