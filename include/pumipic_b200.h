@@ -33,6 +33,7 @@ extern "C" {
 
 typedef struct pp_mesh pp_mesh;
 typedef struct pp_ps pp_ps;
+typedef struct pp_comm pp_comm;
 typedef void* pp_stream; /* cudaStream_t */
 
 typedef enum pp_status {
@@ -45,6 +46,9 @@ typedef enum pp_status {
 } pp_status;
 
 typedef enum pp_memspace { PP_HOST = 0, PP_DEVICE = 1 } pp_memspace;
+typedef enum pp_dtype { PP_INT32 = 0, PP_INT64 = 1, PP_FLOAT32 = 2, PP_FLOAT64 = 3 } pp_dtype;
+/* Mesh::Op (pumipic_mesh.hpp:57-62) */
+typedef enum pp_op { PP_SUM = 0, PP_MAX = 1, PP_MIN = 2, PP_BCAST = 3 } pp_op;
 
 const char* pp_last_error(void);
 /* library version "major.minor.patch" and the GPU architecture it was built for ("sm_100a") */
@@ -124,6 +128,20 @@ pp_status pp_host_kuhn_cube(int32_t n, double length, int32_t* nverts_out, doubl
 pp_status pp_host_plate(int32_t n, double length, int32_t* nverts_out, double** coords_out,
                         int32_t* nelems_out, int32_t** elem2verts_out);
 void pp_host_free(void* p);
+/* PICpart tags of rank `rank` for an element->owner partition (pumipic::Input semantics,
+ * src/pumipic_part_construct.cpp:73-114,409-468; methods: 0 FULL, 1 BFS, 2 MINIMUM, 3 NONE as
+ * pumipic_input.hpp:33-39; defaults buffer_layers 3, safe_layers 1, vertex-bridged BFS).
+ * safe_out[nelems] = Mesh::safeTag(), has_part_out[nranks] = which cores are buffered here. */
+pp_status pp_host_picpart_tags(int32_t dim, int32_t nverts, int32_t nelems,
+                               const int32_t* elem2verts, const int32_t* owner, int32_t nranks,
+                               int32_t rank, int32_t buffer_method, int32_t safe_method,
+                               int32_t buffer_layers, int32_t safe_layers, int32_t* safe_out,
+                               int32_t* has_part_out);
+/* Owner of lower-dimensional entities = minimum owner of the adjacent elements
+ * (defineOwners, part_construct.cpp:304-323).  elem2ents: [nelems*ents_per_elem]. */
+pp_status pp_host_entity_owners(int32_t nents, int32_t nelems, int32_t ents_per_elem,
+                                const int32_t* elem2ents, const int32_t* elem_owner,
+                                int32_t nranks, int32_t* ent_owner_out);
 
 /* ============================== particle structure ====================================== */
 
@@ -303,6 +321,52 @@ pp_status pp_gyro_scatter(pp_mesh* mesh, pp_ps* ps, const int32_t* v2v, double r
 /* test/gyroScatter.hpp:244-248 setSyncArray: sync[2v] = fwd[v], sync[2v+1] = bkwd[v] */
 pp_status pp_gyro_interleave(const double* fwd, const double* bkwd, int32_t nverts,
                              double* sync_array, pp_stream stream);
+
+/* ============================== communication (NCCL over NVLink) ========================= */
+
+/* One process per GPU.  Rank 0 calls pp_comm_unique_id and distributes the 128 bytes by any
+ * means (torch.distributed, MPI, a file); every rank then calls pp_comm_create.  nranks == 1
+ * needs no id and never loads NCCL.  Replaces the MPI_Comm of support/ViewComm.h. */
+pp_status pp_comm_unique_id(uint8_t id_out[128]);
+pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t id[128], pp_comm** out);
+pp_status pp_comm_destroy(pp_comm* comm);
+int32_t pp_comm_size(const pp_comm* comm);
+int32_t pp_comm_rank(const pp_comm* comm);
+
+/* PS_Comm_Allreduce / PS_Comm_Alltoall / PS_Comm_Send / PS_Comm_Recv (support/ViewComm.h:51-291)
+ * on device buffers; dtype is a pp_dtype, op a pp_op (SUM/MAX/MIN).  Sends and receives that
+ * must progress together go between pp_comm_group_start/end (as PS_Comm_Isend/Irecv + Waitall). */
+pp_status pp_comm_allreduce(pp_comm* comm, const void* send, void* recv, int64_t count,
+                            int32_t dtype, int32_t op, pp_stream stream);
+pp_status pp_comm_alltoall(pp_comm* comm, const void* send, void* recv, int64_t count_per_peer,
+                           int32_t dtype, pp_stream stream);
+pp_status pp_comm_send(pp_comm* comm, const void* buf, int64_t count, int32_t dtype, int32_t peer,
+                       pp_stream stream);
+pp_status pp_comm_recv(pp_comm* comm, void* buf, int64_t count, int32_t dtype, int32_t peer,
+                       pp_stream stream);
+pp_status pp_comm_group_start(void);
+pp_status pp_comm_group_end(void);
+
+/* Mesh::reduceCommArray (src/pumipic_comm.cpp:223-440) for full-mesh PICparts: every rank holds
+ * a copy of all nents entities; after the call every copy holds the SUM/MAX/MIN over ranks, or
+ * for PP_BCAST the owner's value (ent_owner = Mesh::entOwners(edim), device int32[nents]).
+ * comm_array: device [nents*nvals], entity-major (createCommArray, pumipic_comm.cpp:187-192). */
+pp_status pp_comm_array_reduce(pp_comm* comm, void* comm_array, int64_t nents, int32_t nvals,
+                               int32_t dtype, int32_t op, const int32_t* ent_owner,
+                               pp_stream stream);
+
+/* migrate (particle_structure.hpp:101-104; SCS_migrate.h:5-221): particles whose new_process is
+ * another rank are packed (element sent as global id), exchanged all-to-all-v, mapped back to
+ * local element ids and inserted by the rebuild that ends the call.  new_element is modified in
+ * place exactly like the reference (sent particles become -1).  World distributor only. */
+typedef struct pp_migrate_stats {
+  int64_t sent, received;
+} pp_migrate_stats;
+pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_element,
+                        const int32_t* new_process, int32_t n_new,
+                        const int32_t* new_particle_elements,
+                        const void* const* new_particle_info, pp_migrate_stats* stats_host,
+                        pp_stream stream);
 
 #ifdef __cplusplus
 }

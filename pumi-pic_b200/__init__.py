@@ -10,4 +10,5 @@ from .capi import PumipicError, lib                  # noqa: F401
 from .api import (Mesh, ParticleStructure, SearchResult, search_mesh, push_constant,  # noqa: F401
                   push_direction, update_positions, push_direction_search, host_kuhn_cube,
                   host_plate, host_derive_sides, push_from, elliptical_setup, elliptical_push,
-                  set_unsafe_procs, gyro_ring_map, gyro_scatter, gyro_interleave)
+                  set_unsafe_procs, gyro_ring_map, gyro_scatter, gyro_interleave, Comm, migrate, host_picpart_tags,
+                  host_entity_owners)

@@ -60,6 +60,32 @@ def host_plate(n, length=1.0):
     return _host_gen(lib().pp_host_plate, n, length, 2)
 
 
+FULL, BFS, MINIMUM, NONE = 0, 1, 2, 3
+
+
+def host_picpart_tags(dim, nverts, elem2verts, owner, nranks, rank, buffer_method=FULL,
+                      safe_method=BFS, buffer_layers=3, safe_layers=1):
+    ev = np.ascontiguousarray(elem2verts, np.int32)
+    ow = np.ascontiguousarray(owner, np.int32)
+    safe = np.empty(ev.shape[0], np.int32)
+    part = np.empty(nranks, np.int32)
+    check(lib().pp_host_picpart_tags(dim, nverts, ev.shape[0], ev.ctypes.data_as(capi.c_i32p),
+                                     ow.ctypes.data_as(capi.c_i32p), nranks, rank, buffer_method,
+                                     safe_method, buffer_layers, safe_layers,
+                                     safe.ctypes.data_as(capi.c_i32p), part.ctypes.data_as(capi.c_i32p)))
+    return safe, part
+
+
+def host_entity_owners(nents, elem2ents, elem_owner, nranks):
+    ee = np.ascontiguousarray(elem2ents, np.int32)
+    ow = np.ascontiguousarray(elem_owner, np.int32)
+    out = np.empty(nents, np.int32)
+    check(lib().pp_host_entity_owners(nents, ee.shape[0], ee.shape[1], ee.ctypes.data_as(capi.c_i32p),
+                                      ow.ctypes.data_as(capi.c_i32p), nranks,
+                                      out.ctypes.data_as(capi.c_i32p)))
+    return out
+
+
 # ------------------------------------------------------------------ mesh
 class Mesh:
     """pumipic::Mesh / o::Mesh stand-in: owns a pp_mesh built from host numpy arrays."""
@@ -327,3 +353,65 @@ def gyro_interleave(fwd, bkwd):
     out = torch.empty(2 * fwd.shape[0], dtype=torch.float64, device="cuda")
     check(lib().pp_gyro_interleave(_ptr(fwd), _ptr(bkwd), fwd.shape[0], _ptr(out), _stream()))
     return out
+
+
+# ------------------------------------------------------------------ communication
+class Comm:
+    """NCCL communicator of the C ABI.  The unique id travels over torch.distributed (plumbing)."""
+
+    _DT = None
+
+    def __init__(self, nranks=None, rank=None):
+        torch = _torch()
+        import torch.distributed as dist
+        if nranks is None:
+            nranks = dist.get_world_size() if dist.is_initialized() else 1
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        self.nranks, self.rank = nranks, rank
+        uid = None
+        if nranks > 1:
+            buf = (C.c_uint8 * 128)()
+            if rank == 0:
+                check(lib().pp_comm_unique_id(buf))
+            obj = [bytes(buf)]
+            dist.broadcast_object_list(obj, src=0)
+            uid = (C.c_uint8 * 128).from_buffer_copy(obj[0])
+        self.h = C.c_void_p()
+        check(lib().pp_comm_create(nranks, rank, uid, C.byref(self.h)))
+
+    @staticmethod
+    def _dtype(t):
+        torch = _torch()
+        return {torch.int32: capi.PP_INT32, torch.int64: capi.PP_INT64,
+                torch.float32: capi.PP_FLOAT32, torch.float64: capi.PP_FLOAT64}[t.dtype]
+
+    def allreduce(self, t, op=capi.PP_SUM):
+        check(lib().pp_comm_allreduce(self.h, _ptr(t), _ptr(t), t.numel(), self._dtype(t), op, _stream()))
+        return t
+
+    def alltoall(self, send, recv):
+        check(lib().pp_comm_alltoall(self.h, _ptr(send), _ptr(recv), send.numel() // self.nranks,
+                                     self._dtype(send), _stream()))
+        return recv
+
+    def array_reduce(self, arr, nents, nvals, op, ent_owner=None):
+        check(lib().pp_comm_array_reduce(self.h, _ptr(arr), nents, nvals, self._dtype(arr), op,
+                                         _ptr(ent_owner), _stream()))
+        return arr
+
+    def __del__(self):
+        try:
+            lib().pp_comm_destroy(self.h)
+        except Exception:
+            pass
+
+
+def migrate(ps, comm, new_element, new_process, new_particle_elements=None, new_particle_info=None):
+    n_new = 0 if new_particle_elements is None else int(new_particle_elements.shape[0])
+    info = None
+    if n_new:
+        info = (C.c_void_p * len(ps.members))(*[t.data_ptr() for t in new_particle_info])
+    st = capi.MigrateStats()
+    check(lib().pp_ps_migrate(ps.h, comm.h, _ptr(new_element), _ptr(new_process), n_new,
+                              _ptr(new_particle_elements), info, C.byref(st), _stream()))
+    return st.sent, st.received

@@ -71,6 +71,13 @@ class SearchStats(C.Structure):
                 ("hops", C.c_int64)]
 
 
+class MigrateStats(C.Structure):
+    _fields_ = [("sent", C.c_int64), ("received", C.c_int64)]
+
+
+PP_INT32, PP_INT64, PP_FLOAT32, PP_FLOAT64 = 0, 1, 2, 3
+PP_SUM, PP_MAX, PP_MIN, PP_BCAST = 0, 1, 2, 3
+
 # every symbol include/pumipic_b200.h declares: name -> (restype, argtypes)
 PROTOTYPES = {
     "pp_last_error": (C.c_char_p, []),
@@ -89,6 +96,11 @@ PROTOTYPES = {
     "pp_host_plate": (C.c_int, [C.c_int32, C.c_double, c_i32p, C.POINTER(c_dp), c_i32p,
                                 C.POINTER(c_i32p)]),
     "pp_host_free": (None, [C.c_void_p]),
+    "pp_host_picpart_tags": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       c_i32p, c_i32p]),
+    "pp_host_entity_owners": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32,
+                                        c_i32p]),
     "pp_ps_config_default": (None, [C.POINTER(PsConfig), C.c_int32]),
     "pp_ps_create": (C.c_int, [C.POINTER(PsConfig), C.c_int32, C.POINTER(MemberDesc), C.c_int32,
                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -123,6 +135,24 @@ PROTOTYPES = {
     "pp_gyro_interleave": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "pp_search_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs),
                                  C.POINTER(SearchStats), C.c_void_p]),
+    "pp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "pp_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pp_comm_size": (C.c_int32, [C.c_void_p]),
+    "pp_comm_rank": (C.c_int32, [C.c_void_p]),
+    "pp_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_void_p]),
+    "pp_comm_alltoall": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                   C.c_void_p]),
+    "pp_comm_send": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "pp_comm_recv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "pp_comm_group_start": (C.c_int, []),
+    "pp_comm_group_end": (C.c_int, []),
+    "pp_comm_array_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p, C.c_void_p]),
+    "pp_ps_migrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(MigrateStats),
+                                C.c_void_p]),
     "pp_search_set_staged": (None, [C.c_int32]),
     "pp_search_last_stats": (C.c_int, [C.c_void_p, C.POINTER(SearchStats), C.c_void_p]),
     "pp_push_direction_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

@@ -1,0 +1,478 @@
+// pp_comm.cu -- NCCL transport, particle migration and the ghost-entity field reduction.
+//
+// Replaces support/ViewComm*.h(pp) (PS_Comm_* MPI wrappers, host-staged unless GPU-aware MPI),
+// particle_structs/src/scs/SCS_migrate.h:5-221 (one Isend/Irecv per member type per peer, each
+// preceded by a pack kernel + fence) and the full-mesh branch of Mesh::reduceCommArray
+// (src/pumipic_comm.cpp:223-247, a host-staged MPI_Allreduce).  Here everything stays in HBM:
+// counts travel in one ncclAllGather, every peer gets ONE packed byte buffer inside a
+// ncclGroupStart/End (= all-to-all-v over NVLink), and the reduction is an in-place ncclAllReduce.
+//
+// NCCL is resolved at run time (dlopen "libnccl.so.2"): in a torch process that is the NCCL torch
+// already loaded, otherwise the system library.  Single-GPU use never touches it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cub/cub.cuh>
+
+#include "pp_internal.cuh"
+
+namespace {
+constexpr int kBlock = 256;
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+pp_status load_nccl() {
+  if (g_nccl.handle) return PP_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    pp_set_error("cannot load NCCL: %s", dlerror());
+    return PP_ERR_NCCL;
+  }
+#define PP_SYM(field, name)                                        \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                       \
+  if (!g_nccl.field) { pp_set_error("NCCL symbol %s missing", name); return PP_ERR_NCCL; }
+  PP_SYM(GetUniqueId, "ncclGetUniqueId");
+  PP_SYM(CommInitRank, "ncclCommInitRank");
+  PP_SYM(CommDestroy, "ncclCommDestroy");
+  PP_SYM(AllReduce, "ncclAllReduce");
+  PP_SYM(AllGather, "ncclAllGather");
+  PP_SYM(Send, "ncclSend");
+  PP_SYM(Recv, "ncclRecv");
+  PP_SYM(GroupStart, "ncclGroupStart");
+  PP_SYM(GroupEnd, "ncclGroupEnd");
+  PP_SYM(GetErrorString, "ncclGetErrorString");
+#undef PP_SYM
+  g_nccl.handle = h;
+  return PP_OK;
+}
+
+#define PP_NCCL(call)                                                                  \
+  do {                                                                                 \
+    ncclResult_t r__ = (call);                                                         \
+    if (r__ != ncclSuccess) {                                                          \
+      pp_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                  \
+                   g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?");          \
+      return PP_ERR_NCCL;                                                              \
+    }                                                                                  \
+  } while (0)
+}  // namespace
+
+struct pp_comm {
+  ncclComm_t comm;
+  int nranks, rank;
+};
+
+extern "C" pp_status pp_comm_unique_id(uint8_t id_out[128]) {
+  PP_REQUIRE(id_out, "null argument");
+  PP_TRY(load_nccl());
+  ncclUniqueId id;
+  PP_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id_out, id.internal, 128);
+  return PP_OK;
+}
+
+extern "C" pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t id[128], pp_comm** out) {
+  PP_REQUIRE(out && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
+  pp_comm* c = new pp_comm();
+  c->comm = nullptr; c->nranks = nranks; c->rank = rank;
+  if (nranks > 1) {
+    PP_REQUIRE(id, "a unique id is required for more than one rank");
+    PP_TRY(load_nccl());
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    PP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
+  }
+  *out = c;
+  return PP_OK;
+}
+
+extern "C" pp_status pp_comm_destroy(pp_comm* c) {
+  if (!c) return PP_OK;
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  delete c;
+  return PP_OK;
+}
+extern "C" int32_t pp_comm_size(const pp_comm* c) { return c ? c->nranks : -1; }
+extern "C" int32_t pp_comm_rank(const pp_comm* c) { return c ? c->rank : -1; }
+
+static pp_status nccl_type(int32_t dtype, ncclDataType_t* t, size_t* bytes) {
+  switch (dtype) {
+    case PP_INT32: *t = ncclInt32; *bytes = 4; return PP_OK;
+    case PP_INT64: *t = ncclInt64; *bytes = 8; return PP_OK;
+    case PP_FLOAT32: *t = ncclFloat32; *bytes = 4; return PP_OK;
+    case PP_FLOAT64: *t = ncclFloat64; *bytes = 8; return PP_OK;
+    default: pp_set_error("unknown pp_dtype %d", dtype); return PP_ERR_INVALID;
+  }
+}
+
+// PS_Comm_Allreduce (support/ViewComm_gpu.hpp:184-210) on device memory, in place allowed
+extern "C" pp_status pp_comm_allreduce(pp_comm* c, const void* send, void* recv, int64_t count,
+                                       int32_t dtype, int32_t op, pp_stream stream) {
+  PP_REQUIRE(c && send && recv && count >= 0, "bad argument");
+  ncclDataType_t t; size_t b;
+  PP_TRY(nccl_type(dtype, &t, &b));
+  if (c->nranks == 1) {
+    if (send != recv) PP_CUDA(cudaMemcpyAsync(recv, send, b * count, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PP_OK;
+  }
+  PP_REQUIRE(op == PP_SUM || op == PP_MAX || op == PP_MIN, "unsupported reduction");
+  const ncclRedOp_t o = op == PP_SUM ? ncclSum : op == PP_MAX ? ncclMax : ncclMin;
+  PP_NCCL(g_nccl.AllReduce(send, recv, (size_t)count, t, o, c->comm, (cudaStream_t)stream));
+  return PP_OK;
+}
+
+// PS_Comm_Alltoall (support/ViewComm_gpu.hpp:130-160): `count` elements per peer
+extern "C" pp_status pp_comm_alltoall(pp_comm* c, const void* send, void* recv, int64_t count,
+                                      int32_t dtype, pp_stream stream) {
+  PP_REQUIRE(c && send && recv && count >= 0, "bad argument");
+  ncclDataType_t t; size_t b;
+  PP_TRY(nccl_type(dtype, &t, &b));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->nranks == 1) {
+    if (send != recv) PP_CUDA(cudaMemcpyAsync(recv, send, b * count, cudaMemcpyDeviceToDevice, s));
+    return PP_OK;
+  }
+  PP_NCCL(g_nccl.GroupStart());
+  for (int p = 0; p < c->nranks; ++p) {
+    PP_NCCL(g_nccl.Send((const char*)send + (size_t)p * count * b, (size_t)count, t, p, c->comm, s));
+    PP_NCCL(g_nccl.Recv((char*)recv + (size_t)p * count * b, (size_t)count, t, p, c->comm, s));
+  }
+  PP_NCCL(g_nccl.GroupEnd());
+  return PP_OK;
+}
+
+// PS_Comm_Send / PS_Comm_Recv (support/ViewComm_gpu.hpp:13-60): blocking pair semantics are the
+// caller's responsibility (NCCL matches a send with the peer's recv on the same communicator)
+extern "C" pp_status pp_comm_send(pp_comm* c, const void* buf, int64_t count, int32_t dtype,
+                                  int32_t peer, pp_stream stream) {
+  PP_REQUIRE(c && c->nranks > 1 && buf && peer >= 0 && peer < c->nranks, "bad argument");
+  ncclDataType_t t; size_t b;
+  PP_TRY(nccl_type(dtype, &t, &b));
+  PP_NCCL(g_nccl.Send(buf, (size_t)count, t, peer, c->comm, (cudaStream_t)stream));
+  return PP_OK;
+}
+extern "C" pp_status pp_comm_recv(pp_comm* c, void* buf, int64_t count, int32_t dtype,
+                                  int32_t peer, pp_stream stream) {
+  PP_REQUIRE(c && c->nranks > 1 && buf && peer >= 0 && peer < c->nranks, "bad argument");
+  ncclDataType_t t; size_t b;
+  PP_TRY(nccl_type(dtype, &t, &b));
+  PP_NCCL(g_nccl.Recv(buf, (size_t)count, t, peer, c->comm, (cudaStream_t)stream));
+  return PP_OK;
+}
+extern "C" pp_status pp_comm_group_start(void) { PP_TRY(load_nccl()); PP_NCCL(g_nccl.GroupStart()); return PP_OK; }
+extern "C" pp_status pp_comm_group_end(void) { PP_TRY(load_nccl()); PP_NCCL(g_nccl.GroupEnd()); return PP_OK; }
+
+// ------------------------------------------------------------------------------------------
+// Mesh::reduceCommArray for full-mesh PICparts (pumipic_comm.cpp:223-247) + BCAST_OP
+// ------------------------------------------------------------------------------------------
+namespace {
+template <class T>
+__global__ void k_mask_not_owned(T* a, const int* __restrict__ owner, int self, long nents, int nvals) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= nents * nvals) return;
+  if (owner[i / nvals] != self) a[i] = T(0);
+}
+}  // namespace
+
+extern "C" pp_status pp_comm_array_reduce(pp_comm* c, void* comm_array, int64_t nents, int32_t nvals,
+                                          int32_t dtype, int32_t op, const int32_t* ent_owner,
+                                          pp_stream stream) {
+  PP_REQUIRE(c && comm_array && nents >= 0 && nvals >= 1, "bad argument");
+  if (c->nranks == 1) return PP_OK;          // pumipic_comm.cpp:232-233
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t nccl_op = op;
+  if (op == PP_BCAST) {
+    // owner's value wins: zero every copy that is not the owner's, then sum (adds exact zeros)
+    PP_REQUIRE(ent_owner, "BCAST needs the entity owners");
+    const long n = nents * nvals;
+    const int g = pp_div_up(n, kBlock);
+    if (n > 0) {
+      if (dtype == PP_FLOAT64) k_mask_not_owned<<<g, kBlock, 0, s>>>((double*)comm_array, ent_owner, c->rank, nents, nvals);
+      else if (dtype == PP_FLOAT32) k_mask_not_owned<<<g, kBlock, 0, s>>>((float*)comm_array, ent_owner, c->rank, nents, nvals);
+      else if (dtype == PP_INT32) k_mask_not_owned<<<g, kBlock, 0, s>>>((int*)comm_array, ent_owner, c->rank, nents, nvals);
+      else k_mask_not_owned<<<g, kBlock, 0, s>>>((long long*)comm_array, ent_owner, c->rank, nents, nvals);
+      PP_KERNEL_CHECK();
+    }
+    nccl_op = PP_SUM;
+  }
+  return pp_comm_allreduce(c, comm_array, comm_array, nents * nvals, dtype, nccl_op, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// migrate (SCS_migrate.h:5-221, identical algorithm in CSR_migrate.hpp / dps / cabm)
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_count_dest(PsView v, const int* __restrict__ new_proc, int self, int nranks, int* cnt) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  int dest = -1;
+  if (s < v.capacity && ((__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u)) {
+    const int p = new_proc[s];
+    if (p != self && p >= 0 && p < nranks) dest = p;
+  }
+  const unsigned grp = __match_any_sync(0xffffffffu, dest);
+  if (dest >= 0 && (threadIdx.x & 31) == (__ffs(grp) - 1)) atomicAdd(cnt + dest, __popc(grp));
+}
+
+struct PackTable {
+  int n;
+  const char* src[16];
+  int bytes[16];
+  int ncomp[16];
+};
+
+// wire format of one peer block holding n particles (all sections 8-byte aligned):
+//   int64 gid[n] | member0: [ncomp0][n] scalars | member1 ... (LayoutLeft per member, as the
+//   reference's per-member messages, MemberTypeLibraries.h:272-279)
+__host__ __device__ inline size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
+__host__ __device__ inline size_t block_bytes(const PackTable& t, size_t n) {
+  size_t b = 8 * n;
+  for (int k = 0; k < t.n; ++k) b += align8((size_t)t.bytes[k] * t.ncomp[k] * n);
+  return b;
+}
+
+__global__ void k_pack(PsView v, const int* __restrict__ new_proc, int* new_elem,
+                       const long long* __restrict__ elem_gids, int self, int nranks,
+                       const int* __restrict__ send_cnt, const size_t* __restrict__ peer_byte_off,
+                       int* cursor, PackTable t, long stride, char* sendbuf) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.capacity) return;
+  if (!((__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u)) return;
+  const int p = new_proc[s];
+  if (p == self || p < 0 || p >= nranks) return;
+  const int e = new_elem[s];
+  const int i = atomicAdd(cursor + p, 1);
+  const size_t n = (size_t)send_cnt[p];
+  char* blk = sendbuf + peer_byte_off[p];
+  ((long long*)blk)[i] = e < 0 ? -1 : (elem_gids ? elem_gids[e] : (long long)e);
+  size_t off = 8 * n;
+  for (int k = 0; k < t.n; ++k) {
+    const int sb = t.bytes[k];
+    for (int c = 0; c < t.ncomp[k]; ++c) {
+      const char* a = t.src[k] + ((size_t)c * stride + s) * sb;
+      char* b = blk + off + ((size_t)c * n + i) * sb;
+      if (sb == 8) *(double*)b = *(const double*)a;
+      else if (sb == 4) *(int*)b = *(const int*)a;
+      else for (int q = 0; q < sb; ++q) b[q] = a[q];
+    }
+    off += align8((size_t)sb * t.ncomp[k] * n);
+  }
+  new_elem[s] = -1;   // removeSentParticles (SCS_migrate.h:190-196)
+}
+
+// received peer blocks -> [ncomp][n_total] member arrays + local element ids
+__global__ void k_unpack(const char* __restrict__ recvbuf, const size_t* __restrict__ peer_byte_off,
+                         const int* __restrict__ recv_cnt, const int* __restrict__ recv_off, int nranks,
+                         int n_total, int row_len, PackTable t, char* const* dst,
+                         const long long* __restrict__ sorted_gid,
+                         const int* __restrict__ sorted_lid, int ne, int* elems_out, int* bad) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_total) return;
+  int p = 0;
+  while (p + 1 < nranks && recv_off[p + 1] <= j) ++p;
+  const int i = j - recv_off[p];
+  const size_t n = (size_t)recv_cnt[p];
+  const char* blk = recvbuf + peer_byte_off[p];
+  const long long gid = ((const long long*)blk)[i];
+  int lid = -1;
+  if (sorted_gid) {                    // gid -> lid (replaces Kokkos::UnorderedMap, SCS_migrate.h:181-187)
+    int lo = 0, hi = ne - 1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      const long long g = sorted_gid[mid];
+      if (g == gid) { lid = sorted_lid[mid]; break; }
+      if (g < gid) lo = mid + 1; else hi = mid - 1;
+    }
+  } else if (gid >= 0 && gid < ne) {
+    lid = (int)gid;
+  }
+  if (lid < 0) *bad = 1;
+  elems_out[j] = lid;
+  size_t off = 8 * n;
+  for (int k = 0; k < t.n; ++k) {
+    const int sb = t.bytes[k];
+    for (int c = 0; c < t.ncomp[k]; ++c) {
+      const char* a = blk + off + ((size_t)c * n + i) * sb;
+      char* b = dst[k] + ((size_t)c * row_len + j) * sb;
+      if (sb == 8) *(double*)b = *(const double*)a;
+      else if (sb == 4) *(int*)b = *(const int*)a;
+      else for (int q = 0; q < sb; ++q) b[q] = a[q];
+    }
+    off += align8((size_t)sb * t.ncomp[k] * n);
+  }
+}
+
+__global__ void k_iota(int* a, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+}  // namespace
+
+extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
+                                   const int32_t* new_particle_elements,
+                                   const void* const* new_particle_info, pp_stream stream_);
+
+extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_element,
+                                   const int32_t* new_process, int32_t n_new,
+                                   const int32_t* new_particle_elements,
+                                   const void* const* new_particle_info,
+                                   pp_migrate_stats* stats_host, pp_stream stream_) {
+  PP_REQUIRE(ps && comm && (new_element || ps->capacity == 0), "null argument");
+  cudaStream_t s = (cudaStream_t)stream_;
+  if (stats_host) { stats_host->sent = 0; stats_host->received = 0; }
+  // serial: SCS_migrate.h:20-25
+  if (comm->nranks == 1)
+    return pp_ps_rebuild(ps, new_element, n_new, new_particle_elements, new_particle_info, stream_);
+  PP_REQUIRE(new_process, "new_process is required");
+  PP_REQUIRE(ps->nmembers <= 16, "at most 16 particle members are supported");
+  const int R = comm->nranks, me = comm->rank;
+  PackTable pt;
+  pt.n = ps->nmembers;
+  for (int k = 0; k < pt.n; ++k) {
+    pt.src[k] = (const char*)ps->data[k];
+    pt.bytes[k] = ps->members[k].scalar_bytes;
+    pt.ncomp[k] = ps->members[k].ncomp;
+  }
+  // 1. particles per destination, 2. counts to everybody (PS_Comm_Ialltoall, :48)
+  int *send_cnt, *all_cnt;
+  PP_TRY(pp_dev_alloc(&send_cnt, R, s));
+  PP_TRY(pp_dev_alloc(&all_cnt, (size_t)R * R, s));
+  PP_CUDA(cudaMemsetAsync(send_cnt, 0, sizeof(int) * R, s));
+  if (ps->capacity > 0)
+    k_count_dest<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_process, me, R, send_cnt);
+  PP_KERNEL_CHECK();
+  PP_NCCL(g_nccl.AllGather(send_cnt, all_cnt, (size_t)R, ncclInt32, comm->comm, s));
+  std::vector<int> h_all((size_t)R * R);
+  PP_CUDA(cudaMemcpyAsync(h_all.data(), all_cnt, sizeof(int) * R * R, cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  std::vector<int> h_send(R), h_recv(R), h_recv_off(R + 1, 0);
+  std::vector<size_t> h_sbo(R + 1, 0), h_rbo(R + 1, 0);
+  long tot_send = 0, tot_recv = 0;
+  for (int p = 0; p < R; ++p) {
+    h_send[p] = h_all[(size_t)me * R + p];
+    h_recv[p] = h_all[(size_t)p * R + me];
+    h_sbo[p + 1] = h_sbo[p] + block_bytes(pt, (size_t)h_send[p]);
+    h_rbo[p + 1] = h_rbo[p] + block_bytes(pt, (size_t)h_recv[p]);
+    h_recv_off[p + 1] = h_recv_off[p] + h_recv[p];
+    tot_send += h_send[p]; tot_recv += h_recv[p];
+  }
+  if (stats_host) { stats_host->sent = tot_send; stats_host->received = tot_recv; }
+  // 3. pack: one buffer per peer holding gids + every member (gatherParticlesToSend +
+  //    CopyParticlesToSend, :83-98), sent particles are marked deleted in new_element
+  char *sendbuf, *recvbuf;
+  size_t *d_sbo, *d_rbo;
+  int *cursor, *d_recv_cnt, *d_recv_off;
+  PP_TRY(pp_dev_alloc(&sendbuf, h_sbo[R] + 8, s));
+  PP_TRY(pp_dev_alloc(&recvbuf, h_rbo[R] + 8, s));
+  PP_TRY(pp_dev_alloc(&d_sbo, R + 1, s));
+  PP_TRY(pp_dev_alloc(&d_rbo, R + 1, s));
+  PP_TRY(pp_dev_alloc(&cursor, R, s));
+  PP_TRY(pp_dev_alloc(&d_recv_cnt, R, s));
+  PP_TRY(pp_dev_alloc(&d_recv_off, R + 1, s));
+  PP_CUDA(cudaMemcpyAsync(d_sbo, h_sbo.data(), sizeof(size_t) * (R + 1), cudaMemcpyHostToDevice, s));
+  PP_CUDA(cudaMemcpyAsync(d_rbo, h_rbo.data(), sizeof(size_t) * (R + 1), cudaMemcpyHostToDevice, s));
+  PP_CUDA(cudaMemcpyAsync(d_recv_cnt, h_recv.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s));
+  PP_CUDA(cudaMemcpyAsync(d_recv_off, h_recv_off.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice, s));
+  PP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * R, s));
+  if (ps->capacity > 0)
+    k_pack<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
+        ps->view(), new_process, new_element, (const long long*)ps->elem_gids, me, R, send_cnt, d_sbo,
+        cursor, pt, ps->stride, sendbuf);
+  PP_KERNEL_CHECK();
+  // 4. all-to-all-v: grouped send/recv, one message per peer (:148-175 uses 1+num_types per peer)
+  PP_NCCL(g_nccl.GroupStart());
+  for (int p = 0; p < R; ++p) {
+    if (p == me) continue;
+    if (h_send[p] > 0)
+      PP_NCCL(g_nccl.Send(sendbuf + h_sbo[p], h_sbo[p + 1] - h_sbo[p], ncclUint8, p, comm->comm, s));
+    if (h_recv[p] > 0)
+      PP_NCCL(g_nccl.Recv(recvbuf + h_rbo[p], h_rbo[p + 1] - h_rbo[p], ncclUint8, p, comm->comm, s));
+  }
+  PP_NCCL(g_nccl.GroupEnd());
+  // 5. unpack into contiguous new-particle arrays, gid -> lid, append the caller's new particles
+  const int n_in = (int)tot_recv + n_new;
+  std::vector<char*> in_data(ps->nmembers, nullptr);
+  int* in_elems = nullptr;
+  int* bad;
+  PP_TRY(pp_dev_alloc(&bad, 1, s));
+  PP_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
+  pp_status st = PP_OK;
+  if (n_in > 0) {
+    PP_TRY(pp_dev_alloc(&in_elems, n_in, s));
+    for (int k = 0; k < ps->nmembers; ++k)
+      PP_TRY(pp_dev_alloc(&in_data[k], (size_t)pt.bytes[k] * pt.ncomp[k] * n_in, s));
+    // [ncomp][n_in] with received particles first; the caller's new particles follow
+    if (tot_recv > 0) {
+      // received particles are written with row length n_in so both groups share one array
+      char** d_dst;
+      PP_TRY(pp_dev_alloc(&d_dst, ps->nmembers, s));
+      PP_CUDA(cudaMemcpyAsync(d_dst, in_data.data(), sizeof(char*) * ps->nmembers, cudaMemcpyHostToDevice, s));
+      if (ps->elem_gids && !ps->sorted_gid) {
+        // lazily build the sorted gid table (createGlobalMapping, SCS_buildFns.h:101-112)
+        long long* keys_in = (long long*)ps->elem_gids;
+        int* vals_in;
+        PP_TRY(pp_dev_alloc(&vals_in, ps->nelems, s));
+        PP_TRY(pp_dev_alloc(&ps->sorted_gid, ps->nelems, s));
+        PP_TRY(pp_dev_alloc(&ps->sorted_lid, ps->nelems, s));
+        k_iota<<<pp_div_up(ps->nelems, kBlock), kBlock, 0, s>>>(vals_in, ps->nelems);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in, (long long*)ps->sorted_gid, vals_in,
+                                        ps->sorted_lid, ps->nelems, 0, 64, s);
+        char* tmp;
+        PP_TRY(pp_dev_alloc(&tmp, tb, s));
+        PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys_in, (long long*)ps->sorted_gid, vals_in,
+                                                ps->sorted_lid, ps->nelems, 0, 64, s));
+        pp_dev_free(tmp, s); pp_dev_free(vals_in, s);
+      }
+      // rows are n_in long so that the caller's new particles can follow the received ones
+      k_unpack<<<pp_div_up(tot_recv, kBlock), kBlock, 0, s>>>(
+          recvbuf, d_rbo, d_recv_cnt, d_recv_off, R, (int)tot_recv, n_in, pt, d_dst,
+          (const long long*)ps->sorted_gid, ps->sorted_lid, ps->nelems, in_elems, bad);
+      pp_dev_free(d_dst, s);
+    }
+    if (n_new > 0) {
+      PP_CUDA(cudaMemcpyAsync(in_elems + tot_recv, new_particle_elements, sizeof(int) * n_new,
+                              cudaMemcpyDeviceToDevice, s));
+      for (int k = 0; k < ps->nmembers; ++k) {
+        const size_t sb = pt.bytes[k];
+        for (int c = 0; c < pt.ncomp[k]; ++c)
+          PP_CUDA(cudaMemcpyAsync(in_data[k] + ((size_t)c * n_in + tot_recv) * sb,
+                                  (const char*)new_particle_info[k] + (size_t)c * n_new * sb,
+                                  (size_t)n_new * sb, cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    PP_KERNEL_CHECK();
+    int h_bad = 0;
+    PP_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+    if (h_bad) {
+      pp_set_error("migrate: a received particle names an element gid that is not on this rank");
+      st = PP_ERR_INVALID;
+    }
+  }
+  // 6. rebuild with the received particles as new particles (:209)
+  if (st == PP_OK) {
+    std::vector<const void*> info(ps->nmembers, nullptr);
+    for (int k = 0; k < ps->nmembers; ++k) info[k] = in_data[k];
+    st = pp_ps_rebuild(ps, new_element, n_in, in_elems, n_in > 0 ? info.data() : nullptr, stream_);
+  }
+  for (char* p : in_data) pp_dev_free(p, s);
+  pp_dev_free(in_elems, s); pp_dev_free(bad, s);
+  pp_dev_free(send_cnt, s); pp_dev_free(all_cnt, s); pp_dev_free(sendbuf, s); pp_dev_free(recvbuf, s);
+  pp_dev_free(d_sbo, s); pp_dev_free(d_rbo, s); pp_dev_free(cursor, s);
+  pp_dev_free(d_recv_cnt, s); pp_dev_free(d_recv_off, s);
+  return st;
+}

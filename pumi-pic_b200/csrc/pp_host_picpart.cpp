@@ -1,0 +1,112 @@
+// pp_host_picpart.cpp -- host-side PICpart tags: which elements are safe on this rank, which
+// other parts are buffered, and entity ownership.  Follows src/pumipic_part_construct.cpp:
+// Mesh::Mesh(Input&) :73-114, bfsBufferLayers :409-441, bfsSafeInward :443-468 (BFS through
+// vertex-bridged adjacency, bridge_dim = 0) and defineOwners :304-323.  Setup-time code that the
+// reference also runs on the host side of Omega_h; sub-mesh extraction for non-full PICparts is a
+// "next" row.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pumipic_b200.h"
+
+void pp_set_error(const char* fmt, ...);
+
+namespace {
+struct Up {  // ask_up(0, dim): vertex -> elements
+  std::vector<int> off, val;
+};
+Up build_up(int nverts, int nelems, int nv, const int32_t* ev) {
+  Up u;
+  u.off.assign((size_t)nverts + 1, 0);
+  for (int64_t i = 0; i < (int64_t)nelems * nv; ++i) u.off[ev[i] + 1]++;
+  for (int v = 0; v < nverts; ++v) u.off[v + 1] += u.off[v];
+  u.val.resize(u.off[nverts]);
+  std::vector<int> fill(nverts, 0);
+  for (int e = 0; e < nelems; ++e)
+    for (int k = 0; k < nv; ++k) {
+      const int v = ev[(int64_t)e * nv + k];
+      u.val[u.off[v] + fill[v]++] = e;
+    }
+  return u;
+}
+// one BFS layer (part_construct.cpp:387-405): every element around a bridge that touches a
+// visited element becomes visited
+void bfs_layer(const Up& u, int nverts, const std::vector<int>& visited, std::vector<int>& next) {
+  for (int b = 0; b < nverts; ++b) {
+    bool here = false;
+    for (int j = u.off[b]; j < u.off[b + 1]; ++j)
+      if (visited[u.val[j]]) here = true;
+    if (here)
+      for (int j = u.off[b]; j < u.off[b + 1]; ++j) next[u.val[j]] = 1;
+  }
+}
+}  // namespace
+
+extern "C" pp_status pp_host_picpart_tags(int32_t dim, int32_t nverts, int32_t nelems,
+                                          const int32_t* elem2verts, const int32_t* owner,
+                                          int32_t nranks, int32_t rank, int32_t buffer_method,
+                                          int32_t safe_method, int32_t buffer_layers,
+                                          int32_t safe_layers, int32_t* safe_out,
+                                          int32_t* has_part_out) {
+  if (!(dim == 2 || dim == 3) || !elem2verts || !owner || !safe_out || !has_part_out ||
+      nranks < 1 || rank < 0 || rank >= nranks) {
+    pp_set_error("pp_host_picpart_tags: bad argument");
+    return PP_ERR_INVALID;
+  }
+  enum { FULL = 0, BFS = 1, MINIMUM = 2, NONE = 3 };
+  if (buffer_method == NONE) buffer_method = MINIMUM;        // pumipic_input.cpp:96-100
+  if (buffer_method == MINIMUM) buffer_layers = 0;
+  if (safe_method == MINIMUM) safe_layers = 0;
+  const int nv = dim + 1;
+  std::vector<int> is_safe(nelems, safe_method == FULL), has_part(nranks, 1);
+  Up u;
+  const bool need_bfs = (safe_method != NONE && safe_method != FULL) || buffer_method != FULL;
+  if (need_bfs || (buffer_method == BFS && safe_method == FULL)) u = build_up(nverts, nelems, nv, elem2verts);
+  if (need_bfs) {
+    // bfsBufferLayers
+    std::vector<int> safe(nelems, 0), part(nranks, 0), visited(nelems), next(nelems);
+    for (int e = 0; e < nelems; ++e) visited[e] = next[e] = safe[e] = (owner[e] == rank);
+    part[rank] = 1;
+    for (int i = 0; i < buffer_layers || i < safe_layers; ++i) {
+      bfs_layer(u, nverts, visited, next);
+      for (int e = 0; e < nelems; ++e) {
+        visited[e] = next[e];
+        if (i == safe_layers - 1) safe[e] = next[e];
+        if (i < buffer_layers && visited[e]) part[owner[e]] = 1;
+      }
+    }
+    if (safe_method == BFS || safe_method == MINIMUM) is_safe = safe;
+    if (buffer_method == BFS || buffer_method == MINIMUM) has_part = part;
+  }
+  if (buffer_method == BFS && safe_method == FULL) {
+    // bfsSafeInward: everything is safe except safe_layers layers next to unbuffered parts
+    std::vector<int> visited(nelems), next(nelems);
+    for (int e = 0; e < nelems; ++e) visited[e] = next[e] = !has_part[owner[e]];
+    for (int i = 0; i < safe_layers; ++i) {
+      bfs_layer(u, nverts, visited, next);
+      visited = next;
+    }
+    for (int e = 0; e < nelems; ++e) is_safe[e] = !visited[e] || owner[e] == rank;
+  }
+  memcpy(safe_out, is_safe.data(), sizeof(int32_t) * nelems);
+  memcpy(has_part_out, has_part.data(), sizeof(int32_t) * nranks);
+  return PP_OK;
+}
+
+extern "C" pp_status pp_host_entity_owners(int32_t nents, int32_t nelems, int32_t ents_per_elem,
+                                           const int32_t* elem2ents, const int32_t* elem_owner,
+                                           int32_t nranks, int32_t* ent_owner_out) {
+  if (!elem2ents || !elem_owner || !ent_owner_out || nents < 0) {
+    pp_set_error("pp_host_entity_owners: bad argument");
+    return PP_ERR_INVALID;
+  }
+  for (int i = 0; i < nents; ++i) ent_owner_out[i] = nranks;   // defineOwners: min over adjacent elements
+  for (int e = 0; e < nelems; ++e)
+    for (int k = 0; k < ents_per_elem; ++k) {
+      const int x = elem2ents[(int64_t)e * ents_per_elem + k];
+      if (elem_owner[e] < ent_owner_out[x]) ent_owner_out[x] = elem_owner[e];
+    }
+  return PP_OK;
+}

@@ -184,6 +184,8 @@ struct pp_ps {
   int* chunk_start;         // [nchunks] first slot of each chunk
   int* row_ppe;             // [nrows] particles per row at the last (re)build
   int64_t* elem_gids;       // [nelems] or null
+  int64_t* sorted_gid;      // [nelems] gids ascending (built lazily for migrate)
+  int* sorted_lid;          // [nelems] local id of sorted_gid[i]
   PsView view() const;
 };
 

@@ -179,7 +179,7 @@ extern "C" pp_status pp_ps_create(const pp_ps_config* cfg, int32_t nmembers,
   ps->chunk_start = nullptr; ps->row_ppe = nullptr;
   ps->C = 1; ps->V = cfg->V; ps->nchunks = 0; ps->nslices = 0;
   ps->offsets = ps->slice_to_chunk = ps->row_to_element = ps->element_to_row = ps->tile_slice = nullptr;
-  ps->elem_gids = nullptr;
+  ps->elem_gids = nullptr; ps->sorted_gid = nullptr; ps->sorted_lid = nullptr;
   int* ppe_dev;
   PP_TRY(pp_dev_import(&ppe_dev, ppe, (size_t)ne, memspace, s));
   int* pel_dev = nullptr;
@@ -204,7 +204,7 @@ extern "C" pp_status pp_ps_destroy(pp_ps* ps) {
   for (void* p : ps->swap) cudaFree(p);
   cudaFree(ps->mask_bits); cudaFree(ps->slot_elem); cudaFree(ps->offsets);
   cudaFree(ps->slice_to_chunk); cudaFree(ps->row_to_element); cudaFree(ps->element_to_row);
-  cudaFree(ps->tile_slice); cudaFree(ps->elem_gids); cudaFree(ps->chunk_start); cudaFree(ps->row_ppe);
+  cudaFree(ps->tile_slice); cudaFree(ps->elem_gids); cudaFree(ps->chunk_start); cudaFree(ps->row_ppe); cudaFree(ps->sorted_gid); cudaFree(ps->sorted_lid);
   delete ps;
   return PP_OK;
 }

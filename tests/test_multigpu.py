@@ -1,0 +1,37 @@
+"""Launches tests/mgpu_worker.py: one rank on a single-GPU box (serial paths of migrate /
+reduceCommArray), and 2 (or 4) NCCL ranks when the box has that many GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _run(n):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", str(29511 + n),
+           os.path.join(HERE, "mgpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_single_rank_paths():
+    _run(1)
+
+
+def test_two_ranks_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    _run(2)
+
+
+def test_four_ranks_nccl():
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run(4)
