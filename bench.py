@@ -175,7 +175,12 @@ def main():
     ap.add_argument("--ps", default="scs", choices=["dps", "scs", "csr"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-staged", action="store_true", help="use the simple thread-per-slot kernel")
+    ap.add_argument("--walk-kernel", type=int, default=2, choices=[0, 1, 2],
+                    help="0 thread-per-slot, 1 block-staged, 2 Sell-C-sigma chunk walk (default)")
+    ap.add_argument("--loop", default="seeded", choices=["seeded", "pingpong"],
+                    help="seeded: every step pushes from the rebuilt positions with elem_ids seeded "
+                         "from the structure rows (what every reference call site does); "
+                         "pingpong: buffers swap and elem_ids carry over, no rebuild in between")
     a = ap.parse_args()
     if a.cpu_sample <= 0:
         a.cpu_sample = a.particles
@@ -190,7 +195,7 @@ def main():
               "particles_per_gpu": a.particles, "tets_per_gpu": 6 * a.cube_n ** 3,
               "push": "xtgt = x + d*dir, d = L/(3*nelems^(1/3)), sign alternates per step",
               "l2": "inputs (>=0.8 GB of particle columns per step) are larger than the 126 MB L2",
-              "particle_structure": a.ps, "parallelism": "independent shard per GPU (no exchange in push+search)"}
+              "particle_structure": a.ps, "loop": a.loop, "parallelism": "independent shard per GPU (no exchange in push+search)"}
 
     if a.impl == "reference":
         # CPU arm: rank 0 only; the reference's own CPU algorithm via the oracle port (the real
@@ -224,8 +229,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pp = importlib.import_module("pumi-pic_b200")
     P = pp
-    if a.no_staged:
-        P.lib().pp_search_set_staged(0)
+    P.lib().pp_search_set_staged(a.walk_kernel)
     m, ppe = build_workload(pp, wl, a.cube_n, a.particles)
     gm = pp.Mesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
     kind = {"dps": P.capi.PP_PS_DPS, "scs": P.capi.PP_PS_SCS, "csr": P.capi.PP_PS_CSR}[a.ps]
@@ -239,7 +243,12 @@ def main():
     dr = torch.as_tensor(D).cuda()
     ids = torch.zeros(cap, dtype=torch.int32, device="cuda")
 
+    seeded = a.loop == "seeded"
+
     def step(it, a_, b_, sync=False):
+        if seeded:   # x stays in xa (the rebuilt state); +d / -d alternate so no step repeats its predecessor
+            return P.push_direction_search(gm, ps, dr, d if it % 2 == 0 else -d, xa, xb, ids,
+                                           elem_ids_empty=True, from_orig=True, sync=sync)
         return P.push_direction_search(gm, ps, dr, d if it % 2 == 0 else -d, a_, b_, ids,
                                        elem_ids_empty=False, from_orig=True, sync=sync)
 
@@ -273,9 +282,11 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
     # stationary population: count live particles once (the oscillation keeps it constant)
-    live = int((ids >= 0).sum().item())
     st = P.capi.SearchStats()
     P.capi.check(P.lib().pp_search_last_stats(gm.h, st, None))
+    # particles pushed + searched per step: every masked particle in the seeded loop; in the
+    # ping-pong loop the ones still inside the domain (the oscillation keeps that set constant)
+    live = int(st.active) if seeded else int((ids >= 0).sum().item())
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     n = torch.tensor([float(live)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -299,12 +310,14 @@ def main():
 
         def e2e_step(k):
             dx.copy_(hx, non_blocking=True); dd.copy_(hd, non_blocking=True)
-            di.copy_(hi, non_blocking=True)
+            if not seeded:
+                di.copy_(hi, non_blocking=True)
             P.push_direction_search(gm, ps, dd, d if (it + k) % 2 == 0 else -d, dx, dt_, di,
-                                    from_orig=True, sync=False)
+                                    elem_ids_empty=seeded, from_orig=True, sync=False)
             ht.copy_(dt_, non_blocking=True); hi.copy_(di, non_blocking=True)
             torch.cuda.synchronize()
-            hx.copy_(ht)   # the caller's next step starts from the pushed positions
+            if not seeded:
+                hx.copy_(ht)   # the caller's next step starts from the pushed positions
         e2e_step(0)
         if world > 1:
             dist.barrier()
@@ -316,11 +329,12 @@ def main():
         et = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        live2 = torch.tensor([float((hi >= 0).sum().item())], dtype=torch.float64, device="cuda")
+        live2 = torch.tensor([float(live if seeded else (hi >= 0).sum().item())], dtype=torch.float64,
+                             device="cuda")
         if world > 1:
             dist.all_reduce(live2, op=dist.ReduceOp.SUM)
         e2e = {"value": float(live2.item()) * e2e_steps / float(et.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(hx.numel() * 8 + hd.numel() * 8 + hi.numel() * 4),
+               "h2d_bytes_per_step": int(hx.numel() * 8 + hd.numel() * 8 + (0 if seeded else hi.numel() * 4)),
                "d2h_bytes_per_step": int(ht.numel() * 8 + hi.numel() * 4),
                "steps": e2e_steps,
                "note": "pinned host buffers, cudaMemcpyAsync H2D -> fused kernel -> D2H per step"}
@@ -357,7 +371,8 @@ def main():
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_search<3,BCC,PUSH> (fused push + walk)",
+                         "kernel": ["k_search<3,BCC,PUSH>", "k_walk_bcc<3,PUSH>", "k_walk_scs<3,PUSH>"][a.walk_kernel]
+                                   + " (fused push + walk)",
                          "algorithmic_bytes_per_particle_step": ALGO_BYTES_PER_PARTICLE_STEP,
                          "kernel_ms": kavg_ms, "peak_source": peak_src},
             "cpu_baseline": cpu,

@@ -139,7 +139,7 @@ struct SearchCounters {
   int not_found;
   int aborted;
   int active;
-  int pad;
+  int next_chunk;   // dynamic chunk scheduler of the chunk walk (k_walk_scs)
   unsigned long long hops;
 };
 
@@ -158,6 +158,11 @@ struct PsView {  // what kernels need to map slot -> (row element, mask)
   const int* tile_slice;  // slice holding the first slot of each 32-slot tile
   int C;
   int nslices;
+  // chunk geometry (SCS): slots of chunk c are [chunk_start[c], chunk_start[c+1]), column-major
+  // over its C rows: slot = chunk_start[c] + col*C + row
+  const int* chunk_start = nullptr;   // [nchunks+1]
+  int nchunks = 0;
+  int nelems = 0;
 };
 
 struct pp_ps {
@@ -181,7 +186,7 @@ struct pp_ps {
   int* row_to_element;
   int* element_to_row;
   int* tile_slice;
-  int* chunk_start;         // [nchunks] first slot of each chunk
+  int* chunk_start;         // [nchunks+1] first slot of each chunk, chunk_start[nchunks] = capacity
   int* row_ppe;             // [nrows] particles per row at the last (re)build
   int64_t* elem_gids;       // [nelems] or null
   int64_t* sorted_gid;      // [nelems] gids ascending (built lazily for migrate)

@@ -69,6 +69,9 @@ PsView pp_ps::view() const {
   v.tile_slice = tile_slice;
   v.C = C;
   v.nslices = nslices;
+  v.chunk_start = chunk_start;
+  v.nchunks = (cfg.kind == PP_PS_SCS || cfg.kind == PP_PS_CABM) ? nchunks : 0;
+  v.nelems = nelems;
   return v;
 }
 

@@ -120,8 +120,9 @@ __global__ void k_fill_slices(const int* __restrict__ width, const int* __restri
 __global__ void k_chunk_start(const int* __restrict__ slice_off, const int* __restrict__ offsets,
                               int nchunks, int capacity, int* chunk_start) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nchunks) return;
-  chunk_start[c] = slice_off[c] < slice_off[c + 1] ? offsets[slice_off[c]] : capacity;
+  if (c > nchunks) return;
+  // an empty chunk owns no slice: its (empty) slot range sits where the next chunk begins
+  chunk_start[c] = c < nchunks ? offsets[slice_off[c]] : capacity;
 }
 
 __global__ void k_tile_slice(const int* __restrict__ offsets, int nslices, int ntiles, int* tile_slice) {
@@ -410,8 +411,8 @@ pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, cudaSt
   PP_TRY(scan_exclusive(slice_size, L.offsets, L.nslices + 1, s));
   PP_CUDA(cudaMemcpyAsync(&L.capacity, L.offsets + L.nslices, sizeof(int), cudaMemcpyDeviceToHost, s));
   PP_CUDA(cudaStreamSynchronize(s));
-  PP_TRY(pp_dev_alloc(&L.chunk_start, L.nchunks, s));
-  k_chunk_start<<<pp_div_up(L.nchunks, kBlock), kBlock, 0, s>>>(slice_off, L.offsets, L.nchunks,
+  PP_TRY(pp_dev_alloc(&L.chunk_start, L.nchunks + 1, s));
+  k_chunk_start<<<pp_div_up(L.nchunks + 1, kBlock), kBlock, 0, s>>>(slice_off, L.offsets, L.nchunks,
                                                                L.capacity, L.chunk_start);
   const int ntiles = (L.capacity + 31) / 32;
   PP_TRY(pp_dev_alloc(&L.tile_slice, ntiles + 1, s));
@@ -431,7 +432,7 @@ PsView layout_view(const ScsLayout& L, int ne) {
   v.kind = PP_PS_SCS; v.capacity = L.capacity; v.mask_bits = L.mask; v.slot_elem = nullptr;
   v.offsets = L.offsets; v.slice_to_chunk = L.slice_to_chunk; v.row_to_element = L.row_to_element;
   v.tile_slice = L.tile_slice; v.C = L.C; v.nslices = L.nslices;
-  (void)ne;
+  v.chunk_start = L.chunk_start; v.nchunks = L.nchunks; v.nelems = ne;
   return v;
 }
 

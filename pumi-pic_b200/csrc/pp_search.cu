@@ -775,6 +775,262 @@ __global__ void __launch_bounds__(BLOCK, (DIM == 3 ? 3 : 4)) k_walk_bcc(SearchPa
   }
 }
 
+// ---------------------------------------------------------------- chunk walk (Sell-C-sigma, C = 32)
+// The barycentric search_mesh for a Sell-C-sigma structure whose elem_ids are seeded from the
+// rows (every reference call site: the particles were rebuilt into the row of their element).
+//
+//   * warp per chunk: lane r owns row r of the chunk, so the walk record of the row's element is
+//     gathered ONCE per chunk into registers and reused for every column of the row; the
+//     particle columns themselves (x, dir, xtgt, elem_ids) are fully coalesced 256 B accesses;
+//   * origin check (check_initial_parents) and the first exit test use that register record;
+//   * particles that must hop are pushed, with a warp-aggregated claim, into a per-warp
+//     shared-memory queue; whenever the queue holds a full warp of work it is drained: the 32
+//     neighbour records are fetched COOPERATIVELY with 16-byte cp.async pieces (consecutive lanes
+//     read consecutive pieces, so a record costs 1.5 L1 wavefronts instead of 12) into a
+//     bank-conflict-free stage, each lane evaluates one queued particle and re-queues it if it
+//     must hop again.  Lanes therefore stay full although walk lengths differ (49 % stop at
+//     once, 2 % need four hops or more);
+//   * chunks are handed out by an atomic counter, there is no block-level synchronisation.
+constexpr int kQCap = 128;   // queue entries per warp (drained down below 32 before refilling)
+
+template <int DIM>
+struct WarpSmem {
+  static constexpr int STAGE = 32 * StageCfg<DIM>::STRIDE;
+  static constexpr int BYTES = STAGE + kQCap * (3 * 8 + 3 * 4);
+};
+
+template <int DIM>
+__device__ __forceinline__ void warp_stage_fetch(const typename StageCfg<DIM>::Raw* table,
+                                                 const int* q_E, int n, unsigned char* stage,
+                                                 int lane) {
+  using Cfg = StageCfg<DIM>;
+  const int total = n * Cfg::PIECES;
+#pragma unroll
+  for (int k = 0; k < Cfg::PIECES; ++k) {
+    const int idx = lane + k * 32;
+    if (idx < total) {
+      const int item = idx / Cfg::PIECES;
+      const int piece = idx - item * Cfg::PIECES;
+      const int e = q_E[item];
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + item * Cfg::STRIDE + piece * 16);
+      const void* src = reinterpret_cast<const int4*>(table + e) + piece;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncwarp();
+}
+
+__device__ __forceinline__ void load_row_rec(const void* bcc_table, const void*, int E, Bcc3& r) {
+  const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const PPBccRec3*>(bcc_table) + E);
+  const double2 p0 = __ldg(q + 0), p1 = __ldg(q + 1), p2 = __ldg(q + 2), p3 = __ldg(q + 3);
+  const double2 p4 = __ldg(q + 4), p5 = __ldg(q + 5), p6 = __ldg(q + 6), p7 = __ldg(q + 7);
+  const double2 p8 = __ldg(q + 8), p9 = __ldg(q + 9), p10 = __ldg(q + 10);
+  const int4 p11 = __ldg(reinterpret_cast<const int4*>(q + 11));
+  r.a0 = {p0.x, p0.y, p1.x};
+  r.a1 = {p1.y, p2.x, p2.y};
+  r.a2 = {p3.x, p3.y, p4.x};
+  r.n0 = {p4.y, p5.x, p5.y};
+  r.n1 = {p6.x, p6.y, p7.x};
+  r.n2 = {p7.y, p8.x, p8.y};
+  r.n3 = {p9.x, p9.y, p10.x};
+  r.inv_vol = p10.y;
+  r.adj[0] = p11.x; r.adj[1] = p11.y; r.adj[2] = p11.z; r.adj[3] = p11.w;
+}
+__device__ __forceinline__ void load_row_rec(const void*, const void* walk, int E, Tri& r) {
+  load_rec(walk, E, r);
+}
+__device__ __forceinline__ void zero_rec(Bcc3& r) {
+  r.a0 = r.a1 = r.a2 = r.n0 = r.n1 = r.n2 = r.n3 = d3{0, 0, 0};
+  r.inv_vol = -1.0;
+  r.adj[0] = r.adj[1] = r.adj[2] = r.adj[3] = -1;
+}
+__device__ __forceinline__ void zero_rec(Tri& r) {
+  r.M[0] = r.M[1] = r.M[2] = d2{0, 0};
+  r.area = 1.0;
+  r.adj[0] = r.adj[1] = r.adj[2] = -1;
+  r.codes = 0; r.cls = 0; r.aux = -1;
+}
+
+template <int DIM, bool PUSH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(SearchParams p) {
+  using Cfg = StageCfg<DIM>;
+  using Rec = typename std::conditional<DIM == 3, Bcc3, Tri>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  unsigned char* wbase = smem + (threadIdx.x >> 5) * WarpSmem<DIM>::BYTES;
+  unsigned char* stage = wbase;
+  double* q_tx = reinterpret_cast<double*>(wbase + WarpSmem<DIM>::STAGE);
+  double* q_ty = q_tx + kQCap;
+  double* q_tz = q_ty + kQCap;
+  int* q_E = reinterpret_cast<int*>(q_tz + kQCap);
+  int* q_slot = q_E + kQCap;
+  int* q_it = q_slot + kQCap;
+  const auto* table = reinterpret_cast<const typename Cfg::Raw*>(DIM == 3 ? p.walk_bcc : p.walk);
+  const unsigned full = 0xffffffffu;
+  const unsigned lt = (1u << lane) - 1u;
+  ThreadStats st;
+  int qn = 0;   // queue fill, warp-uniform
+
+  // one walk iteration of a particle whose record is `rec`: find_exit_face (BCC) +
+  // check_model_intersection + set_new_element.  Returns true if the particle must hop to `next`.
+  auto advance = [&](const Rec& rec, int& e, int it, d3 t, int& next) -> bool {
+    bool done;
+    int f;
+    if constexpr (DIM == 3) {
+      double b[4];
+      bcc_tet(rec, t, b);
+      done = all_positive<4>(b, kEps);
+      f = min_index4(b);
+    } else {
+      double b[3];
+      bcc_tri(rec, d2{t.x, t.y}, b);
+      done = all_positive<3>(b, kEps);
+      f = min3(b);
+    }
+    st.iters = it > st.iters ? it : st.iters;
+    if (done) return false;
+    const int a = adj_of(rec, f);
+    if (a < 0) { e = -1; return false; }          // exposed side: the particle leaves the domain
+    ++st.hops;
+    if (p.looplimit && it >= p.looplimit) { st.not_found += 1; e = -1; return false; }  // tpp:584-606
+    next = a;
+    return true;
+  };
+  auto enqueue = [&](bool push, int slot, int next, int it, d3 t) {
+    const unsigned m = __ballot_sync(full, push);
+    if (push) {
+      const int pos = qn + __popc(m & lt);
+      q_E[pos] = next; q_slot[pos] = slot; q_it[pos] = it;
+      q_tx[pos] = t.x; q_ty[pos] = t.y; q_tz[pos] = t.z;
+    }
+    qn += __popc(m);
+    __syncwarp();
+  };
+  auto drain = [&](int n) {       // n <= 32 entries from the top of the queue
+    const int base = qn - n;
+    const bool has = lane < n;
+    int E = -1, slot = 0, it = 0;
+    d3 t = {0, 0, 0};
+    if (has) {
+      E = q_E[base + lane]; slot = q_slot[base + lane]; it = q_it[base + lane];
+      t = {q_tx[base + lane], q_ty[base + lane], q_tz[base + lane]};
+    }
+    warp_stage_fetch<DIM>(table, q_E + base, n, stage, lane);
+    qn = base;
+    bool push = false;
+    int next = -1;
+    if (has) {
+      Rec rec;
+      read_stage(stage + lane * Cfg::STRIDE, rec);
+      push = advance(rec, E, it + 1, t, next);
+      if (!push) p.elem_ids[slot] = E;
+    }
+    __syncwarp();                 // every lane has read its stage row / queue entry
+    enqueue(push, slot, next, it + 1, t);
+  };
+
+  const int nchunks = p.ps.nchunks;
+  const int* __restrict__ cstart = p.ps.chunk_start;
+  const bool from_orig = PUSH && p.push_from_orig;
+  while (true) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(&p.counters->next_chunk, 1);
+    c = __shfl_sync(full, c, 0);
+    if (c >= nchunks) break;
+    const int s0 = __ldg(cstart + c), s1 = __ldg(cstart + c + 1);
+    if (s1 <= s0) continue;
+    const int rowE = __ldg(p.ps.row_to_element + c * 32 + lane);
+    const bool row_ok = rowE < p.nelems;          // padding rows of the last chunk hold no particle
+    int sb = s0;                                  // next column to process
+    while (sb < s1) {
+      Rec rec;
+      if (row_ok) load_row_rec(p.walk_bcc, p.walk, rowE, rec); else zero_rec(rec);
+      for (; sb < s1 && qn <= kQCap - 32; sb += 32) {
+        const int s = sb + lane;
+        const uint32_t w = __ldg(p.ps.mask_bits + (sb >> 5));
+        const bool mask = (w >> lane) & 1u;
+        int E = -1;
+        bool push = false;
+        int next = -1;
+        d3 tgt = {0, 0, 0};
+        if (mask) {
+          E = rowE;                               // setInitial (tpp:504-515)
+          const d3 org = {p.xo[s], p.xo[p.stride + s], p.xo[2 * p.stride + s]};
+          if (PUSH) {
+            const d3 base = from_orig ? org : d3{p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+            const d3 dr = {p.dir[s], p.dir[p.stride + s], p.dir[2 * p.stride + s]};
+            tgt = {base.x + p.distance * dr.x, base.y + p.distance * dr.y, base.z + p.distance * dr.z};
+            p.xt_rw[s] = tgt.x; p.xt_rw[p.stride + s] = tgt.y; p.xt_rw[2 * p.stride + s] = tgt.z;
+          } else {
+            tgt = {p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+          }
+          if (!(norm3(tgt - org) < p.tol)) {      // finishUnmoved (tpp:525-533)
+            st.active += 1;
+            bool inside;                          // check_initial_parents (tpp:73-145)
+            if constexpr (DIM == 3) {
+              double b[4];
+              bcc_tet(rec, org, b);
+              inside = all_positive<4>(b, p.tol);
+            } else {
+              double b[3];
+              bcc_tri(rec, d2{org.x, org.y}, b);
+              inside = all_positive<3>(b, p.tol);
+            }
+            if (!inside) { st.not_in += 1; E = -1; }
+            else push = advance(rec, E, 1, tgt, next);
+          }
+        }
+        if (!push) p.elem_ids[s] = E;             // unmasked slots get -1 (elem_ids is seeded here)
+        enqueue(push, s, next, 1, tgt);
+      }
+      while (qn >= 32) drain(32);
+    }
+  }
+  while (qn > 0) drain(qn < 32 ? qn : 32);
+
+  // ---- warp-aggregated counters
+  const int iters = __reduce_max_sync(full, st.iters);
+  const int nin = __reduce_add_sync(full, st.not_in);
+  const int nnf = __reduce_add_sync(full, st.not_found);
+  const int nac = __reduce_add_sync(full, st.active);
+  const int nh = __reduce_add_sync(full, st.hops);
+  if (lane == 0) {
+    if (iters) atomicMax(&p.counters->max_iters, iters);
+    if (nin) atomicAdd(&p.counters->not_in_elem, nin);
+    if (nnf) atomicAdd(&p.counters->not_found, nnf);
+    if (nac) atomicAdd(&p.counters->active, nac);
+    if (nh) atomicAdd(&p.counters->hops, (unsigned long long)nh);
+  }
+}
+
+int g_sm_count = 0;
+
+template <int DIM>
+pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
+  constexpr int WARPS = 4;
+  constexpr size_t smem = (size_t)WARPS * WarpSmem<DIM>::BYTES;
+  if (!g_sm_count) {
+    int dev = 0;
+    PP_CUDA(cudaGetDevice(&dev));
+    PP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int want = pp_div_up(p.ps.nchunks, WARPS);
+  const int persistent = g_sm_count * (512 / (WARPS * 32));
+  const int grid = want < persistent ? want : persistent;
+  if (push) {
+    auto k = k_walk_scs<DIM, true, WARPS>;
+    PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, WARPS * 32, smem, s>>>(p);
+  } else {
+    auto k = k_walk_scs<DIM, false, WARPS>;
+    PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, WARPS * 32, smem, s>>>(p);
+  }
+  return PP_OK;
+}
+
 template <int DIM, bool LEG2D>
 pp_status launch_walk_bcc(const SearchParams& p, bool push, cudaStream_t s) {
   constexpr int BLOCK = 256;
@@ -800,7 +1056,7 @@ void launch(const SearchParams& p, bool push, cudaStream_t s) {
   else k_search<DIM, MODE, false><<<grid, block, 0, s>>>(p);
 }
 
-int g_staged_walk = 1;
+int g_staged_walk = 2;
 
 pp_status read_stats(pp_mesh* mesh, int variant, int looplimit, pp_search_stats* out, cudaStream_t s) {
   SearchCounters h;
@@ -849,6 +1105,10 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
         if (a->require_intersection) {
           PP_REQUIRE(a->inter_faces && a->inter_points, "intersection outputs are required");
           if (mesh->dim == 3) launch<3, M_RAY>(p, push, s); else launch<2, M_RAY>(p, push, s);
+        } else if (p.staged >= 2 && a->elem_ids_empty && view.nchunks > 0 && view.C == 32 &&
+                   view.chunk_start) {
+          if (mesh->dim == 3) PP_TRY(launch_walk_scs<3>(p, push, s));
+          else PP_TRY(launch_walk_scs<2>(p, push, s));
         } else if (p.staged) {
           if (mesh->dim == 3) PP_TRY((launch_walk_bcc<3, false>(p, push, s)));
           else PP_TRY((launch_walk_bcc<2, false>(p, push, s)));
@@ -897,7 +1157,7 @@ extern "C" pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_ar
                    (cudaStream_t)stream);
 }
 
-extern "C" void pp_search_set_staged(int32_t on) { g_staged_walk = on ? 1 : 0; }
+extern "C" void pp_search_set_staged(int32_t on) { g_staged_walk = on < 0 ? 0 : (on > 2 ? 2 : on); }
 
 extern "C" pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host,
                                           pp_stream stream) {
