@@ -791,12 +791,12 @@ __global__ void __launch_bounds__(BLOCK, (DIM == 3 ? 3 : 4)) k_walk_bcc(SearchPa
 //     must hop again.  Lanes therefore stay full although walk lengths differ (49 % stop at
 //     once, 2 % need four hops or more);
 //   * chunks are handed out by an atomic counter, there is no block-level synchronisation.
-constexpr int kQCap = 128;   // queue entries per warp (drained down below 32 before refilling)
+constexpr int kQCap = 192;   // queue entries per warp (drained down below 32 before refilling)
 
 template <int DIM>
 struct WarpSmem {
   static constexpr int STAGE = 32 * StageCfg<DIM>::STRIDE;
-  static constexpr int BYTES = STAGE + kQCap * (3 * 8 + 3 * 4);
+  static constexpr int BYTES = STAGE + kQCap * (3 * 8 + 3 * 4) + 32 * 4;
 };
 
 template <int DIM>
@@ -822,37 +822,6 @@ __device__ __forceinline__ void warp_stage_fetch(const typename StageCfg<DIM>::R
   __syncwarp();
 }
 
-__device__ __forceinline__ void load_row_rec(const void* bcc_table, const void*, int E, Bcc3& r) {
-  const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const PPBccRec3*>(bcc_table) + E);
-  const double2 p0 = __ldg(q + 0), p1 = __ldg(q + 1), p2 = __ldg(q + 2), p3 = __ldg(q + 3);
-  const double2 p4 = __ldg(q + 4), p5 = __ldg(q + 5), p6 = __ldg(q + 6), p7 = __ldg(q + 7);
-  const double2 p8 = __ldg(q + 8), p9 = __ldg(q + 9), p10 = __ldg(q + 10);
-  const int4 p11 = __ldg(reinterpret_cast<const int4*>(q + 11));
-  r.a0 = {p0.x, p0.y, p1.x};
-  r.a1 = {p1.y, p2.x, p2.y};
-  r.a2 = {p3.x, p3.y, p4.x};
-  r.n0 = {p4.y, p5.x, p5.y};
-  r.n1 = {p6.x, p6.y, p7.x};
-  r.n2 = {p7.y, p8.x, p8.y};
-  r.n3 = {p9.x, p9.y, p10.x};
-  r.inv_vol = p10.y;
-  r.adj[0] = p11.x; r.adj[1] = p11.y; r.adj[2] = p11.z; r.adj[3] = p11.w;
-}
-__device__ __forceinline__ void load_row_rec(const void*, const void* walk, int E, Tri& r) {
-  load_rec(walk, E, r);
-}
-__device__ __forceinline__ void zero_rec(Bcc3& r) {
-  r.a0 = r.a1 = r.a2 = r.n0 = r.n1 = r.n2 = r.n3 = d3{0, 0, 0};
-  r.inv_vol = -1.0;
-  r.adj[0] = r.adj[1] = r.adj[2] = r.adj[3] = -1;
-}
-__device__ __forceinline__ void zero_rec(Tri& r) {
-  r.M[0] = r.M[1] = r.M[2] = d2{0, 0};
-  r.area = 1.0;
-  r.adj[0] = r.adj[1] = r.adj[2] = -1;
-  r.codes = 0; r.cls = 0; r.aux = -1;
-}
-
 template <int DIM, bool PUSH, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(SearchParams p) {
   using Cfg = StageCfg<DIM>;
@@ -867,6 +836,7 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
   int* q_E = reinterpret_cast<int*>(q_tz + kQCap);
   int* q_slot = q_E + kQCap;
   int* q_it = q_slot + kQCap;
+  int* q_rowE = q_it + kQCap;
   const auto* table = reinterpret_cast<const typename Cfg::Raw*>(DIM == 3 ? p.walk_bcc : p.walk);
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
@@ -931,9 +901,26 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
     enqueue(push, slot, next, it + 1, t);
   };
 
+  // row records of a chunk: cooperative fetch through the stage, then one register copy per lane
+  auto fetch_rows = [&](int e, Rec& rec) {
+    q_rowE[lane] = e;
+    __syncwarp();
+    warp_stage_fetch<DIM>(table, q_rowE, 32, stage, lane);
+    read_stage(stage + lane * Cfg::STRIDE, rec);
+    __syncwarp();
+  };
+  const bool from_orig = PUSH && p.push_from_orig;
+  // column loads: origin and (direction | target); issued one column ahead of their use
+  auto load_col = [&](int s, uint32_t w, d3& o, d3& a) {
+    if ((w >> lane) & 1u) {
+      o = {p.xo[s], p.xo[p.stride + s], p.xo[2 * p.stride + s]};
+      if (PUSH) a = {p.dir[s], p.dir[p.stride + s], p.dir[2 * p.stride + s]};
+      else a = {p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+    }
+  };
+
   const int nchunks = p.ps.nchunks;
   const int* __restrict__ cstart = p.ps.chunk_start;
-  const bool from_orig = PUSH && p.push_from_orig;
   while (true) {
     int c = 0;
     if (lane == 0) c = atomicAdd(&p.counters->next_chunk, 1);
@@ -941,15 +928,29 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
     if (c >= nchunks) break;
     const int s0 = __ldg(cstart + c), s1 = __ldg(cstart + c + 1);
     if (s1 <= s0) continue;
+    const int ncols = (s1 - s0) >> 5;
     const int rowE = __ldg(p.ps.row_to_element + c * 32 + lane);
-    const bool row_ok = rowE < p.nelems;          // padding rows of the last chunk hold no particle
-    int sb = s0;                                  // next column to process
-    while (sb < s1) {
-      Rec rec;
-      if (row_ok) load_row_rec(p.walk_bcc, p.walk, rowE, rec); else zero_rec(rec);
-      for (; sb < s1 && qn <= kQCap - 32; sb += 32) {
-        const int s = sb + lane;
-        const uint32_t w = __ldg(p.ps.mask_bits + (sb >> 5));
+    const int rowF = rowE < p.nelems ? rowE : 0;  // padding rows of the last chunk hold no particle
+    Rec rec;
+    fetch_rows(rowF, rec);
+    for (int cb = 0; cb < ncols; cb += 32) {      // batches of 32 columns: one mask word per lane
+      const int nb = ncols - cb < 32 ? ncols - cb : 32;
+      const uint32_t mw = lane < nb ? __ldg(p.ps.mask_bits + (s0 >> 5) + cb + lane) : 0u;
+      const unsigned nz = __ballot_sync(full, mw != 0u);
+      const int nlive = 32 - __clz(nz);           // rows fill from column 0: empty columns trail
+      for (int j = nlive; j < nb; ++j) p.elem_ids[s0 + (cb + j) * 32 + lane] = -1;
+      if (nlive == 0) continue;
+      uint32_t w = __shfl_sync(full, mw, 0);
+      d3 org = {0, 0, 0}, aux = {0, 0, 0};
+      load_col(s0 + cb * 32 + lane, w, org, aux);
+      for (int j = 0; j < nlive; ++j) {
+        const int s = s0 + (cb + j) * 32 + lane;
+        uint32_t wn = 0;
+        d3 org_n = {0, 0, 0}, aux_n = {0, 0, 0};
+        if (j + 1 < nlive) {
+          wn = __shfl_sync(full, mw, j + 1);
+          load_col(s + 32, wn, org_n, aux_n);
+        }
         const bool mask = (w >> lane) & 1u;
         int E = -1;
         bool push = false;
@@ -957,14 +958,12 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
         d3 tgt = {0, 0, 0};
         if (mask) {
           E = rowE;                               // setInitial (tpp:504-515)
-          const d3 org = {p.xo[s], p.xo[p.stride + s], p.xo[2 * p.stride + s]};
           if (PUSH) {
             const d3 base = from_orig ? org : d3{p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
-            const d3 dr = {p.dir[s], p.dir[p.stride + s], p.dir[2 * p.stride + s]};
-            tgt = {base.x + p.distance * dr.x, base.y + p.distance * dr.y, base.z + p.distance * dr.z};
+            tgt = {base.x + p.distance * aux.x, base.y + p.distance * aux.y, base.z + p.distance * aux.z};
             p.xt_rw[s] = tgt.x; p.xt_rw[p.stride + s] = tgt.y; p.xt_rw[2 * p.stride + s] = tgt.z;
           } else {
-            tgt = {p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+            tgt = aux;
           }
           if (!(norm3(tgt - org) < p.tol)) {      // finishUnmoved (tpp:525-533)
             st.active += 1;
@@ -984,9 +983,14 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
         }
         if (!push) p.elem_ids[s] = E;             // unmasked slots get -1 (elem_ids is seeded here)
         enqueue(push, s, next, 1, tgt);
+        org = org_n; aux = aux_n; w = wn;
+        if (qn > kQCap - 32) {                    // queue cannot take another column: drain it
+          while (qn >= 32) drain(32);
+          fetch_rows(rowF, rec);
+        }
       }
-      while (qn >= 32) drain(32);
     }
+    while (qn >= 32) drain(32);
   }
   while (qn > 0) drain(qn < 32 ? qn : 32);
 
