@@ -32,6 +32,7 @@ struct SearchParams {
   double* inter_points;
   int looplimit;
   double tol;
+  double unmoved_sq;    // see unmoved_threshold()
   int nelems;
   SearchCounters* counters;
   // fused direction push (test_adj.cpp:550-562): xt += distance*dir before the walk
@@ -188,9 +189,10 @@ __device__ __forceinline__ int max_index4(const double* a) {
 }
 // pumipic_utils.hpp:88-92 min3
 __device__ __forceinline__ int min3(const double* a) {
-  int idx = (a[0] < a[1]) ? 0 : 1;
-  idx = (a[idx] < a[2]) ? idx : 2;
-  return idx;
+  const bool first = a[0] < a[1];      // no dynamic indexing: a[] stays in registers
+  const int idx = first ? 0 : 1;
+  const double m = first ? a[0] : a[1];
+  return (m < a[2]) ? idx : 2;
 }
 
 // ---------------------------------------------------------------- intersections
@@ -791,13 +793,28 @@ __global__ void __launch_bounds__(BLOCK, (DIM == 3 ? 3 : 4)) k_walk_bcc(SearchPa
 //     must hop again.  Lanes therefore stay full although walk lengths differ (49 % stop at
 //     once, 2 % need four hops or more);
 //   * chunks are handed out by an atomic counter, there is no block-level synchronisation.
-constexpr int kQCap = 192;   // queue entries per warp (drained down below 32 before refilling)
+constexpr int kQCap = 64;    // queue entries per warp; a full warp of work is drained at once
+constexpr int kRing = 3;     // particle columns in flight per warp (cp.async ring)
 
 template <int DIM>
 struct WarpSmem {
   static constexpr int STAGE = 32 * StageCfg<DIM>::STRIDE;
-  static constexpr int BYTES = STAGE + kQCap * (3 * 8 + 3 * 4) + 32 * 4;
+  static constexpr int QUEUE = kQCap * (3 * 8 + 3 * 4);
+  static constexpr int RING = kRing * 6 * 32 * 8;
+  static constexpr int BYTES = STAGE + QUEUE + RING + 32 * 4 * 4;   // + row adjacency (4 ints per lane)
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 template <int DIM>
 __device__ __forceinline__ void warp_stage_fetch(const typename StageCfg<DIM>::Raw* table,
@@ -812,13 +829,11 @@ __device__ __forceinline__ void warp_stage_fetch(const typename StageCfg<DIM>::R
       const int item = idx / Cfg::PIECES;
       const int piece = idx - item * Cfg::PIECES;
       const int e = q_E[item];
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + item * Cfg::STRIDE + piece * 16);
-      const void* src = reinterpret_cast<const int4*>(table + e) + piece;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+      cp_async16(stage + item * Cfg::STRIDE + piece * 16, reinterpret_cast<const int4*>(table + e) + piece);
     }
   }
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncwarp();
 }
 
@@ -836,16 +851,21 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
   int* q_E = reinterpret_cast<int*>(q_tz + kQCap);
   int* q_slot = q_E + kQCap;
   int* q_it = q_slot + kQCap;
-  int* q_rowE = q_it + kQCap;
+  double* ring = reinterpret_cast<double*>(wbase + WarpSmem<DIM>::STAGE + WarpSmem<DIM>::QUEUE) + lane;
+  int* q_rowE = reinterpret_cast<int*>(wbase + WarpSmem<DIM>::STAGE + WarpSmem<DIM>::QUEUE + WarpSmem<DIM>::RING);
   const auto* table = reinterpret_cast<const typename Cfg::Raw*>(DIM == 3 ? p.walk_bcc : p.walk);
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
-  ThreadStats st;
+  constexpr int kAdjOff = DIM == 3 ? 176 : 56;   // byte offset of adj[] inside a staged record
+  int* row_adj = q_rowE + lane * 4;              // adjacency of this lane's row (aliases q_rowE)
+  int st_iters = 0, st_active = 0;               // per-lane counters; the rest are warp-uniform
+  int n_push = 0, n_lost = 0, n_notin = 0;
   int qn = 0;   // queue fill, warp-uniform
 
-  // one walk iteration of a particle whose record is `rec`: find_exit_face (BCC) +
-  // check_model_intersection + set_new_element.  Returns true if the particle must hop to `next`.
-  auto advance = [&](const Rec& rec, int& e, int it, d3 t, int& next) -> bool {
+  // one walk iteration of a particle whose record is `rec` (adjacency read from shared memory at
+  // `adj`): find_exit_face (BCC) + check_model_intersection + set_new_element.  Returns true if
+  // the particle must hop to `next`.
+  auto advance = [&](const Rec& rec, const int* adj, int& e, int it, d3 t, int& next, bool& lost) -> bool {
     bool done;
     int f;
     if constexpr (DIM == 3) {
@@ -859,17 +879,19 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
       done = all_positive<3>(b, kEps);
       f = min3(b);
     }
-    st.iters = it > st.iters ? it : st.iters;
+    st_iters = it > st_iters ? it : st_iters;
     if (done) return false;
-    const int a = adj_of(rec, f);
+    const int a = adj[f];
     if (a < 0) { e = -1; return false; }          // exposed side: the particle leaves the domain
-    ++st.hops;
-    if (p.looplimit && it >= p.looplimit) { st.not_found += 1; e = -1; return false; }  // tpp:584-606
+    if (p.looplimit && it >= p.looplimit) { lost = true; e = -1; return false; }  // tpp:584-606
     next = a;
     return true;
   };
-  auto enqueue = [&](bool push, int slot, int next, int it, d3 t) {
+  // hops = particles that moved to a neighbour (queued) + those stopped there by the loop limit
+  auto enqueue = [&](bool push, bool lost, int slot, int next, int it, d3 t) {
     const unsigned m = __ballot_sync(full, push);
+    if (p.looplimit) n_lost += __popc(__ballot_sync(full, lost));
+    n_push += __popc(m);
     if (push) {
       const int pos = qn + __popc(m & lt);
       q_E[pos] = next; q_slot[pos] = slot; q_it[pos] = it;
@@ -889,16 +911,17 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
     }
     warp_stage_fetch<DIM>(table, q_E + base, n, stage, lane);
     qn = base;
-    bool push = false;
+    bool push = false, lost = false;
     int next = -1;
     if (has) {
       Rec rec;
       read_stage(stage + lane * Cfg::STRIDE, rec);
-      push = advance(rec, E, it + 1, t, next);
+      push = advance(rec, reinterpret_cast<const int*>(stage + lane * Cfg::STRIDE + kAdjOff), E, it + 1,
+                     t, next, lost);
       if (!push) p.elem_ids[slot] = E;
     }
     __syncwarp();                 // every lane has read its stage row / queue entry
-    enqueue(push, slot, next, it + 1, t);
+    enqueue(push, lost, slot, next, it + 1, t);
   };
 
   // row records of a chunk: cooperative fetch through the stage, then one register copy per lane
@@ -907,16 +930,26 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
     __syncwarp();
     warp_stage_fetch<DIM>(table, q_rowE, 32, stage, lane);
     read_stage(stage + lane * Cfg::STRIDE, rec);
+    const int* sa = reinterpret_cast<const int*>(stage + lane * Cfg::STRIDE + kAdjOff);
+    row_adj[0] = sa[0]; row_adj[1] = sa[1]; row_adj[2] = sa[2];
+    if (DIM == 3) row_adj[3] = sa[3];
     __syncwarp();
   };
   const bool from_orig = PUSH && p.push_from_orig;
-  // column loads: origin and (direction | target); issued one column ahead of their use
-  auto load_col = [&](int s, uint32_t w, d3& o, d3& a) {
-    if ((w >> lane) & 1u) {
-      o = {p.xo[s], p.xo[p.stride + s], p.xo[2 * p.stride + s]};
-      if (PUSH) a = {p.dir[s], p.dir[p.stride + s], p.dir[2 * p.stride + s]};
-      else a = {p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+  const double* __restrict__ colA = p.xo;                 // origin
+  const double* __restrict__ colB = PUSH ? p.dir : p.xt;  // direction | target
+  // column prefetch: each lane copies its own six doubles into its private ring entries, so the
+  // only synchronisation is its own cp.async.wait_group
+  auto issue_col = [&](int s, bool m, int r) {
+    if (m) {
+      double* d = ring + r * (6 * 32);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        cp_async8(d + k * 32, colA + k * p.stride + s);
+        cp_async8(d + (3 + k) * 32, colB + k * p.stride + s);
+      }
     }
+    cp_async_commit();
   };
 
   const int nchunks = p.ps.nchunks;
@@ -931,29 +964,35 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
     const int ncols = (s1 - s0) >> 5;
     const int rowE = __ldg(p.ps.row_to_element + c * 32 + lane);
     const int rowF = rowE < p.nelems ? rowE : 0;  // padding rows of the last chunk hold no particle
-    Rec rec;
-    fetch_rows(rowF, rec);
     for (int cb = 0; cb < ncols; cb += 32) {      // batches of 32 columns: one mask word per lane
       const int nb = ncols - cb < 32 ? ncols - cb : 32;
       const uint32_t mw = lane < nb ? __ldg(p.ps.mask_bits + (s0 >> 5) + cb + lane) : 0u;
       const unsigned nz = __ballot_sync(full, mw != 0u);
       const int nlive = 32 - __clz(nz);           // rows fill from column 0: empty columns trail
-      for (int j = nlive; j < nb; ++j) p.elem_ids[s0 + (cb + j) * 32 + lane] = -1;
-      if (nlive == 0) continue;
-      uint32_t w = __shfl_sync(full, mw, 0);
-      d3 org = {0, 0, 0}, aux = {0, 0, 0};
-      load_col(s0 + cb * 32 + lane, w, org, aux);
+      // my_cols: bit j set iff this lane's slot in column j holds a particle
+      uint32_t my_cols = 0;
+      for (int j = 0; j < nlive; ++j) my_cols |= ((__shfl_sync(full, mw, j) >> lane) & 1u) << j;
+      const int sbase = s0 + cb * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < kRing; ++k) issue_col(sbase + k * 32, (my_cols >> k) & 1u, k);
+      for (int j = nlive; j < nb; ++j) p.elem_ids[sbase + j * 32] = -1;
+      Rec rec;
+      fetch_rows(rowF, rec);                      // also waits for the first columns
+      int r = 0;
       for (int j = 0; j < nlive; ++j) {
-        const int s = s0 + (cb + j) * 32 + lane;
-        uint32_t wn = 0;
-        d3 org_n = {0, 0, 0}, aux_n = {0, 0, 0};
-        if (j + 1 < nlive) {
-          wn = __shfl_sync(full, mw, j + 1);
-          load_col(s + 32, wn, org_n, aux_n);
+        const int s = sbase + j * 32;
+        cp_async_wait<kRing - 1>();
+        const bool mask = (my_cols >> j) & 1u;
+        const double* d = ring + r * (6 * 32);
+        d3 org = {0, 0, 0}, aux = {0, 0, 0};
+        if (mask) {
+          org = {d[0], d[32], d[64]};
+          aux = {d[96], d[128], d[160]};
         }
-        const bool mask = (w >> lane) & 1u;
+        issue_col(s + kRing * 32, j + kRing < nlive && ((my_cols >> ((j + kRing) & 31)) & 1u), r);
+        r = r + 1 == kRing ? 0 : r + 1;
         int E = -1;
-        bool push = false;
+        bool push = false, lost = false, notin = false;
         int next = -1;
         d3 tgt = {0, 0, 0};
         if (mask) {
@@ -965,8 +1004,9 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
           } else {
             tgt = aux;
           }
-          if (!(norm3(tgt - org) < p.tol)) {      // finishUnmoved (tpp:525-533)
-            st.active += 1;
+          const d3 mv = tgt - org;
+          if (!(dot3(mv, mv) < p.unmoved_sq)) {   // finishUnmoved (tpp:525-533), see unmoved_threshold()
+            st_active += 1;
             bool inside;                          // check_initial_parents (tpp:73-145)
             if constexpr (DIM == 3) {
               double b[4];
@@ -977,36 +1017,40 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(Sea
               bcc_tri(rec, d2{org.x, org.y}, b);
               inside = all_positive<3>(b, p.tol);
             }
-            if (!inside) { st.not_in += 1; E = -1; }
-            else push = advance(rec, E, 1, tgt, next);
+            if (!inside) { notin = true; E = -1; }
+            else push = advance(rec, row_adj, E, 1, tgt, next, lost);
           }
         }
         if (!push) p.elem_ids[s] = E;             // unmasked slots get -1 (elem_ids is seeded here)
-        enqueue(push, s, next, 1, tgt);
-        org = org_n; aux = aux_n; w = wn;
-        if (qn > kQCap - 32) {                    // queue cannot take another column: drain it
-          while (qn >= 32) drain(32);
-          fetch_rows(rowF, rec);
-        }
+        if (__any_sync(full, notin)) n_notin += __popc(__ballot_sync(full, notin));
+        enqueue(push, lost, s, next, 1, tgt);
+        while (qn >= 32) drain(32);
       }
     }
-    while (qn >= 32) drain(32);
   }
   while (qn > 0) drain(qn < 32 ? qn : 32);
 
   // ---- warp-aggregated counters
-  const int iters = __reduce_max_sync(full, st.iters);
-  const int nin = __reduce_add_sync(full, st.not_in);
-  const int nnf = __reduce_add_sync(full, st.not_found);
-  const int nac = __reduce_add_sync(full, st.active);
-  const int nh = __reduce_add_sync(full, st.hops);
+  const int iters = __reduce_max_sync(full, st_iters);
+  const int nac = __reduce_add_sync(full, st_active);
   if (lane == 0) {
     if (iters) atomicMax(&p.counters->max_iters, iters);
-    if (nin) atomicAdd(&p.counters->not_in_elem, nin);
-    if (nnf) atomicAdd(&p.counters->not_found, nnf);
+    if (n_notin) atomicAdd(&p.counters->not_in_elem, n_notin);
+    if (n_lost) atomicAdd(&p.counters->not_found, n_lost);
     if (nac) atomicAdd(&p.counters->active, nac);
-    if (nh) atomicAdd(&p.counters->hops, (unsigned long long)nh);
+    if (n_push + n_lost) atomicAdd(&p.counters->hops, (unsigned long long)(n_push + n_lost));
   }
+}
+
+// finishUnmoved tests sqrt(d) < tol with d = |tgt - org|^2.  sqrt is correctly rounded and
+// monotone, so the test equals d < T with T the smallest double whose square root is >= tol;
+// T is found here on the host and the kernel skips the square root (bit-identical decisions).
+double unmoved_threshold(double tol) {
+  if (!(tol > 0)) return 0.0;             // sqrt(d) < tol is never true
+  double T = tol * tol;
+  while (sqrt(T) >= tol && T > 0) T = nextafter(T, 0.0);
+  while (sqrt(T) < tol) T = nextafter(T, INFINITY);
+  return T;
 }
 
 int g_sm_count = 0;
@@ -1097,6 +1141,7 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
   p.elem_ids = a->elem_ids; p.ids_empty = a->elem_ids_empty;
   p.inter_faces = a->inter_faces; p.inter_points = a->inter_points;
   p.looplimit = a->looplimit; p.tol = mesh->tol; p.nelems = mesh->nelems;
+  p.unmoved_sq = unmoved_threshold(mesh->tol);
   p.counters = (SearchCounters*)mesh->stats_dev;
   p.dir = dir; p.distance = distance; p.xt_rw = const_cast<double*>(a->x_tgt);
   p.push_from_orig = push_from_orig;
