@@ -577,10 +577,9 @@ __device__ __forceinline__ void bcc_tet(const Bcc3& t, d3 p, double bcc[4]) {
   v[1] = dot3(p0, t.n1);
   v[2] = dot3(p - t.a1, t.n2);
   v[3] = dot3(p - t.a2, t.n3);
-  if (t.inv_vol > 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) bcc[i] = t.inv_vol * v[i];
-  } else {
+  for (int i = 0; i < 4; ++i) bcc[i] = t.inv_vol * v[i];
+  if (__builtin_expect(!(t.inv_vol > 0), 0)) {    // barycentric_tet fails on a degenerate tet
 #pragma unroll
     for (int i = 0; i < 4; ++i) bcc[i] = -1;
   }
@@ -793,8 +792,14 @@ __global__ void __launch_bounds__(BLOCK, (DIM == 3 ? 3 : 4)) k_walk_bcc(SearchPa
 //     must hop again.  Lanes therefore stay full although walk lengths differ (49 % stop at
 //     once, 2 % need four hops or more);
 //   * chunks are handed out by an atomic counter, there is no block-level synchronisation.
+#ifndef PP_SCS_MINB
+#define PP_SCS_MINB 4        // resident 128-thread blocks per SM the chunk walk is compiled for
+#endif
+#ifndef PP_SCS_RING
+#define PP_SCS_RING 3
+#endif
 constexpr int kQCap = 64;    // queue entries per warp; a full warp of work is drained at once
-constexpr int kRing = 3;     // particle columns in flight per warp (cp.async ring)
+constexpr int kRing = PP_SCS_RING;   // particle columns in flight per warp (cp.async ring)
 
 template <int DIM>
 struct WarpSmem {
@@ -821,15 +826,33 @@ __device__ __forceinline__ void warp_stage_fetch(const typename StageCfg<DIM>::R
                                                  const int* q_E, int n, unsigned char* stage,
                                                  int lane) {
   using Cfg = StageCfg<DIM>;
-  const int total = n * Cfg::PIECES;
+  if constexpr (Cfg::PIECES == 12) {
+    // piece index lane + 32k: 32k mod 12 has period 3 in k, so (item, piece) of k = 3m + r is
+    // (item_r + 8m, piece_r): three divisions per call instead of twelve
 #pragma unroll
-  for (int k = 0; k < Cfg::PIECES; ++k) {
-    const int idx = lane + k * 32;
-    if (idx < total) {
-      const int item = idx / Cfg::PIECES;
-      const int piece = idx - item * Cfg::PIECES;
-      const int e = q_E[item];
-      cp_async16(stage + item * Cfg::STRIDE + piece * 16, reinterpret_cast<const int4*>(table + e) + piece);
+    for (int r = 0; r < 3; ++r) {
+      const int idx = lane + 32 * r;
+      const int item_r = idx / 12;
+      const int piece_r = idx - item_r * 12;
+      const unsigned char* src_r = reinterpret_cast<const unsigned char*>(table) + piece_r * 16;
+      unsigned char* dst_r = stage + item_r * Cfg::STRIDE + piece_r * 16;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int item = item_r + 8 * m;
+        if (item < n) cp_async16(dst_r + m * 8 * Cfg::STRIDE, src_r + (long)q_E[item] * (long)sizeof(typename Cfg::Raw));
+      }
+    }
+  } else {
+    const int total = n * Cfg::PIECES;
+#pragma unroll
+    for (int k = 0; k < Cfg::PIECES; ++k) {
+      const int idx = lane + k * 32;
+      if (idx < total) {
+        const int item = idx / Cfg::PIECES;
+        const int piece = idx - item * Cfg::PIECES;
+        const int e = q_E[item];
+        cp_async16(stage + item * Cfg::STRIDE + piece * 16, reinterpret_cast<const int4*>(table + e) + piece);
+      }
     }
   }
   cp_async_commit();
@@ -838,7 +861,7 @@ __device__ __forceinline__ void warp_stage_fetch(const typename StageCfg<DIM>::R
 }
 
 template <int DIM, bool PUSH, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_walk_scs(SearchParams p) {
+__global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchParams p) {
   using Cfg = StageCfg<DIM>;
   using Rec = typename std::conditional<DIM == 3, Bcc3, Tri>::type;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1065,7 +1088,7 @@ pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
     PP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   const int want = pp_div_up(p.ps.nchunks, WARPS);
-  const int persistent = g_sm_count * (512 / (WARPS * 32));
+  const int persistent = g_sm_count * PP_SCS_MINB;
   const int grid = want < persistent ? want : persistent;
   if (push) {
     auto k = k_walk_scs<DIM, true, WARPS>;
