@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--ps", default="scs", choices=["dps", "scs", "csr"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-parts", type=int, default=8, help="pieces of the pipelined host-buffer step")
     ap.add_argument("--walk-kernel", type=int, default=2, choices=[0, 1, 2],
                     help="0 thread-per-slot, 1 block-staged, 2 Sell-C-sigma chunk walk (default)")
     ap.add_argument("--loop", default="seeded", choices=["seeded", "pingpong"],
@@ -309,15 +310,19 @@ def main():
         e2e_steps = max(3, min(a.steps, 5))
 
         def e2e_step(k):
+            if seeded:
+                # the reference-facing call with HOST buffers: copies and kernel pipelined inside
+                P.push_direction_search_host(gm, ps, hx, hd, ht, hi, d if (it + k) % 2 == 0 else -d,
+                                             nparts=a.e2e_parts, sync=False)
+                torch.cuda.synchronize()
+                return
             dx.copy_(hx, non_blocking=True); dd.copy_(hd, non_blocking=True)
-            if not seeded:
-                di.copy_(hi, non_blocking=True)
+            di.copy_(hi, non_blocking=True)
             P.push_direction_search(gm, ps, dd, d if (it + k) % 2 == 0 else -d, dx, dt_, di,
-                                    elem_ids_empty=seeded, from_orig=True, sync=False)
+                                    elem_ids_empty=False, from_orig=True, sync=False)
             ht.copy_(dt_, non_blocking=True); hi.copy_(di, non_blocking=True)
             torch.cuda.synchronize()
-            if not seeded:
-                hx.copy_(ht)   # the caller's next step starts from the pushed positions
+            hx.copy_(ht)   # the caller's next step starts from the pushed positions
         e2e_step(0)
         if world > 1:
             dist.barrier()
@@ -337,7 +342,9 @@ def main():
                "h2d_bytes_per_step": int(hx.numel() * 8 + hd.numel() * 8 + (0 if seeded else hi.numel() * 4)),
                "d2h_bytes_per_step": int(ht.numel() * 8 + hi.numel() * 4),
                "steps": e2e_steps,
-               "note": "pinned host buffers, cudaMemcpyAsync H2D -> fused kernel -> D2H per step"}
+               "note": ("pp_push_direction_search_host: pinned host buffers, %d pieces, H2D / kernel / D2H "
+                        "overlapped on three streams" % a.e2e_parts) if seeded else
+                       "pinned host buffers, cudaMemcpyAsync H2D -> fused kernel -> D2H per step"}
 
     if rank != 0:
         if world > 1:

@@ -285,9 +285,9 @@ typedef struct pp_search_stats {
  * counters copied out. */
 pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
                          pp_search_stats* stats_host, pp_stream stream);
-/* Kernel selection for the barycentric walks: 1 (default) = block-staged kernel (cooperative
- * record fetch + shared-memory compaction), 0 = the simple thread-per-slot kernel.  Both give
- * identical results; the switch exists for A/B measurements. */
+/* Kernel selection for the barycentric walks: 2 (default) = Sell-C-sigma chunk walk where it
+ * applies (C = 32, elem_ids seeded from the rows), 1 = block-staged kernel, 0 = the simple
+ * thread-per-slot kernel.  All give identical results; the switch exists for A/B measurements. */
 void pp_search_set_staged(int32_t on);
 /* Counters of the most recent search on this mesh handle (synchronises the stream). */
 pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host, pp_stream stream);
@@ -301,6 +301,19 @@ pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host, pp_st
 pp_status pp_push_direction_search(pp_mesh* mesh, pp_ps* ps, const double* dir, double distance,
                                    int32_t push_from_orig, const pp_search_args* args,
                                    pp_search_stats* stats_host, pp_stream stream);
+/* The same fused step for callers whose particle columns live in HOST memory (pinned memory
+ * recommended): xtgt = x + distance*dir, then search_mesh seeded from the structure rows
+ * (elem_ids passed empty, adjacency.tpp:504-515), results written back to host arrays.
+ *   h_x_orig, h_dir  host [3][stride] in;  h_x_tgt host [3][stride] out;  h_elem_ids host [capacity] out
+ * The slot range is cut into `nparts` pieces at chunk boundaries (Sell-C-sigma, C = 32; other
+ * structures run as one piece); host->device copies, the kernel and device->host copies of
+ * successive pieces overlap on internal streams.  nparts <= 0 picks a default.  All work is
+ * ordered after prior work on `stream`, and `stream` waits for the last copy. */
+pp_status pp_push_direction_search_host(pp_mesh* mesh, pp_ps* ps, const double* h_x_orig,
+                                        const double* h_dir, double* h_x_tgt, int32_t* h_elem_ids,
+                                        int64_t stride, double distance, int32_t looplimit,
+                                        int32_t nparts, pp_search_stats* stats_host,
+                                        pp_stream stream);
 /* Unfused PIC-form push: xtgt = x + distance*dir for masked slots. */
 pp_status pp_push_from(pp_ps* ps, const double* x, double* xtgt, const double* dir,
                        int64_t stride, double distance, pp_stream stream);

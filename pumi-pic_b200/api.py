@@ -295,6 +295,16 @@ def push_direction_search(mesh, ps, direction, distance, x_orig, x_tgt, elem_ids
     return SearchResult(st) if sync else None
 
 
+def push_direction_search_host(mesh, ps, h_x, h_dir, h_xtgt, h_ids, distance, looplimit=0, nparts=0,
+                               sync=True):
+    """Host-buffer step: h_* are CPU tensors (pinned for overlap) of shape [3, stride] / [capacity]."""
+    st = capi.SearchStats()
+    check(lib().pp_push_direction_search_host(mesh.h, ps.h, _ptr(h_x), _ptr(h_dir), _ptr(h_xtgt),
+                                              _ptr(h_ids), h_x.shape[1], distance, looplimit, nparts,
+                                              C.byref(st) if sync else None, _stream()))
+    return SearchResult(st) if sync else None
+
+
 def push_constant(ps, x, xtgt, distance, d):
     check(lib().pp_push_constant(ps.h, _ptr(x), _ptr(xtgt), x.shape[1], distance, d[0], d[1], d[2],
                                  _stream()))

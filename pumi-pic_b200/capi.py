@@ -158,6 +158,10 @@ PROTOTYPES = {
     "pp_push_direction_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                            C.c_int32, C.POINTER(SearchArgs),
                                            C.POINTER(SearchStats), C.c_void_p]),
+    "pp_push_direction_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                                C.c_int32, C.c_int32, C.POINTER(SearchStats),
+                                                C.c_void_p]),
     "pp_push_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_double, C.c_void_p]),
 }

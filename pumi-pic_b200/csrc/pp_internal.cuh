@@ -130,6 +130,7 @@ struct pp_mesh {
   int* vert_first_elem;  // [nverts] lowest-numbered element adjacent to each vertex (ask_up(0,dim) first entry)
   // search scratch
   int* stats_dev;   // device counters (see SearchCounters)
+  void* hostpipe;   // staging buffers / streams of pp_push_direction_search_host (lazy)
 };
 
 // device-side counters of one search

@@ -6,6 +6,8 @@
 
 #include "pp_internal.cuh"
 
+void pp_hostpipe_destroy(pp_mesh* mesh);   // pp_search.cu
+
 namespace {
 
 constexpr int kBlock = 256;
@@ -286,6 +288,7 @@ extern "C" pp_status pp_mesh_destroy(pp_mesh* m) {
   cudaFree(m->elem_class); cudaFree(m->measure); cudaFree(m->exposed); cudaFree(m->side2elem);
   cudaFree(m->dual_off); cudaFree(m->dual); cudaFree(m->safe); cudaFree(m->owner);
   cudaFree(m->walk); cudaFree(m->walk_bcc); cudaFree(m->aux); cudaFree(m->vert_first_elem); cudaFree(m->stats_dev);
+  pp_hostpipe_destroy(m);
   delete m;
   return PP_OK;
 }

@@ -33,6 +33,8 @@ struct SearchParams {
   int looplimit;
   double tol;
   double unmoved_sq;    // see unmoved_threshold()
+  int chunk_begin, chunk_end;   // chunk walk: chunks [begin, end) of the structure
+  int* sched;           // chunk walk: dynamic scheduler counter of this launch
   int nelems;
   SearchCounters* counters;
   // fused direction push (test_adj.cpp:550-562): xt += distance*dir before the walk
@@ -975,13 +977,12 @@ __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchPara
     cp_async_commit();
   };
 
-  const int nchunks = p.ps.nchunks;
   const int* __restrict__ cstart = p.ps.chunk_start;
   while (true) {
     int c = 0;
-    if (lane == 0) c = atomicAdd(&p.counters->next_chunk, 1);
+    if (lane == 0) c = p.chunk_begin + atomicAdd(p.sched, 1);
     c = __shfl_sync(full, c, 0);
-    if (c >= nchunks) break;
+    if (c >= p.chunk_end) break;
     const int s0 = __ldg(cstart + c), s1 = __ldg(cstart + c + 1);
     if (s1 <= s0) continue;
     const int ncols = (s1 - s0) >> 5;
@@ -1087,7 +1088,7 @@ pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
     PP_CUDA(cudaGetDevice(&dev));
     PP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int want = pp_div_up(p.ps.nchunks, WARPS);
+  const int want = pp_div_up(p.chunk_end - p.chunk_begin, WARPS);
   const int persistent = g_sm_count * PP_SCS_MINB;
   const int grid = want < persistent ? want : persistent;
   if (push) {
@@ -1146,9 +1147,13 @@ pp_status read_stats(pp_mesh* mesh, int variant, int looplimit, pp_search_stats*
   return PP_OK;
 }
 
+// part: optional piece of a chunk-walk launch (pp_push_direction_search_host); the caller then
+// zeroes the counters once and gives every piece its own scheduler counter
+struct ChunkPart { int begin, end; int* sched; };
+
 pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_search_args* a,
                     const double* dir, double distance, bool push, int push_from_orig,
-                    pp_search_stats* stats_host, cudaStream_t s) {
+                    pp_search_stats* stats_host, cudaStream_t s, const ChunkPart* part = nullptr) {
   PP_REQUIRE(mesh && a, "null argument");
   PP_REQUIRE(a->x_tgt && a->elem_ids, "x_tgt and elem_ids are required");
   PP_REQUIRE(a->stride >= view.capacity, "stride smaller than capacity");
@@ -1169,7 +1174,10 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
   p.dir = dir; p.distance = distance; p.xt_rw = const_cast<double*>(a->x_tgt);
   p.push_from_orig = push_from_orig;
   p.elem2sides = mesh->elem2sides; p.dual = mesh->dual; p.ndual = 0;
-  PP_CUDA(cudaMemsetAsync(mesh->stats_dev, 0, sizeof(SearchCounters), s));
+  p.chunk_begin = part ? part->begin : 0;
+  p.chunk_end = part ? part->end : view.nchunks;
+  p.sched = part ? part->sched : &p.counters->next_chunk;
+  if (!part) PP_CUDA(cudaMemsetAsync(mesh->stats_dev, 0, sizeof(SearchCounters), s));
   if (ps->capacity > 0) {
     switch (a->variant) {
       case PP_SEARCH_NEW:
@@ -1177,8 +1185,8 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
         if (a->require_intersection) {
           PP_REQUIRE(a->inter_faces && a->inter_points, "intersection outputs are required");
           if (mesh->dim == 3) launch<3, M_RAY>(p, push, s); else launch<2, M_RAY>(p, push, s);
-        } else if (p.staged >= 2 && a->elem_ids_empty && view.nchunks > 0 && view.C == 32 &&
-                   view.chunk_start) {
+        } else if (part || (p.staged >= 2 && a->elem_ids_empty && view.nchunks > 0 && view.C == 32 &&
+                            view.chunk_start)) {
           if (mesh->dim == 3) PP_TRY(launch_walk_scs<3>(p, push, s));
           else PP_TRY(launch_walk_scs<2>(p, push, s));
         } else if (p.staged) {
@@ -1247,4 +1255,144 @@ extern "C" pp_status pp_push_direction_search(pp_mesh* mesh, pp_ps* ps, const do
   PP_REQUIRE(ps, "null particle structure");
   return do_search(mesh, ps->view(), ps->nelems, args, dir, distance, true, push_from_orig ? 1 : 0,
                    stats_host, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-buffer variant: particle columns live in (pinned) host memory.  The slot range is cut into
+// pieces at chunk boundaries; H2D copies, the chunk-walk kernel and D2H copies of successive
+// pieces run on three streams, so the PCIe transfers in both directions overlap the kernel.
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int kMaxParts = 64;
+struct HostPipe {
+  double *x = nullptr, *dir = nullptr, *xt = nullptr;
+  int* ids = nullptr;
+  int* sched = nullptr;            // [kMaxParts]
+  long stride = 0;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t e_begin = nullptr, e_end = nullptr, e_in[kMaxParts], e_k[kMaxParts];
+  std::vector<int> chunk_start;
+};
+
+pp_status hostpipe_get(pp_mesh* mesh, long stride, HostPipe** out) {
+  HostPipe* hp = (HostPipe*)mesh->hostpipe;
+  if (!hp) {
+    hp = new HostPipe();
+    PP_CUDA(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
+    PP_CUDA(cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+    PP_CUDA(cudaEventCreateWithFlags(&hp->e_begin, cudaEventDisableTiming));
+    PP_CUDA(cudaEventCreateWithFlags(&hp->e_end, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxParts; ++i) {
+      PP_CUDA(cudaEventCreateWithFlags(&hp->e_in[i], cudaEventDisableTiming));
+      PP_CUDA(cudaEventCreateWithFlags(&hp->e_k[i], cudaEventDisableTiming));
+    }
+    PP_CUDA(cudaMalloc((void**)&hp->sched, kMaxParts * sizeof(int)));
+    mesh->hostpipe = hp;
+  }
+  if (hp->stride < stride) {
+    cudaFree(hp->x); cudaFree(hp->dir); cudaFree(hp->xt); cudaFree(hp->ids);
+    hp->x = hp->dir = hp->xt = nullptr; hp->ids = nullptr; hp->stride = 0;
+    PP_CUDA(cudaMalloc((void**)&hp->x, 3 * stride * sizeof(double)));
+    PP_CUDA(cudaMalloc((void**)&hp->dir, 3 * stride * sizeof(double)));
+    PP_CUDA(cudaMalloc((void**)&hp->xt, 3 * stride * sizeof(double)));
+    PP_CUDA(cudaMalloc((void**)&hp->ids, stride * sizeof(int)));
+    hp->stride = stride;
+  }
+  *out = hp;
+  return PP_OK;
+}
+}  // namespace
+
+void pp_hostpipe_destroy(pp_mesh* mesh) {
+  HostPipe* hp = (HostPipe*)mesh->hostpipe;
+  if (!hp) return;
+  cudaFree(hp->x); cudaFree(hp->dir); cudaFree(hp->xt); cudaFree(hp->ids); cudaFree(hp->sched);
+  cudaStreamDestroy(hp->s_in); cudaStreamDestroy(hp->s_out);
+  cudaEventDestroy(hp->e_begin); cudaEventDestroy(hp->e_end);
+  for (int i = 0; i < kMaxParts; ++i) { cudaEventDestroy(hp->e_in[i]); cudaEventDestroy(hp->e_k[i]); }
+  delete hp;
+  mesh->hostpipe = nullptr;
+}
+
+extern "C" pp_status pp_push_direction_search_host(pp_mesh* mesh, pp_ps* ps, const double* h_x_orig,
+                                                   const double* h_dir, double* h_x_tgt,
+                                                   int32_t* h_elem_ids, int64_t stride,
+                                                   double distance, int32_t looplimit,
+                                                   int32_t nparts, pp_search_stats* stats_host,
+                                                   pp_stream stream) {
+  PP_REQUIRE(mesh && ps && h_x_orig && h_dir && h_x_tgt && h_elem_ids, "null argument");
+  PP_REQUIRE(stride >= ps->capacity, "stride smaller than capacity");
+  PP_REQUIRE(ps->nelems == mesh->nelems, "particle structure and mesh disagree on nelems");
+  cudaStream_t s = (cudaStream_t)stream;
+  const PsView view = ps->view();
+  const bool chunked = view.nchunks > 0 && view.C == 32 && view.chunk_start;
+  if (nparts < 1) nparts = 8;
+  if (nparts > kMaxParts) nparts = kMaxParts;
+  if (!chunked || nparts > view.nchunks) nparts = 1;
+  HostPipe* hp;
+  PP_TRY(hostpipe_get(mesh, stride, &hp));
+  const long dstride = hp->stride;
+  const int cap = ps->capacity;
+  pp_search_args a;
+  a.variant = PP_SEARCH_NEW;
+  a.x_orig = hp->x; a.x_tgt = hp->xt; a.stride = dstride;
+  a.elem_ids = hp->ids; a.elem_ids_empty = 1; a.require_intersection = 0;
+  a.inter_faces = nullptr; a.inter_points = nullptr; a.looplimit = looplimit;
+  // piece boundaries in slots
+  std::vector<int> cbeg(nparts + 1, 0), sbeg(nparts + 1, 0);
+  if (chunked) {
+    hp->chunk_start.resize(view.nchunks + 1);
+    PP_CUDA(cudaMemcpyAsync(hp->chunk_start.data(), view.chunk_start, sizeof(int) * (view.nchunks + 1),
+                            cudaMemcpyDeviceToHost, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+    // equal slot counts per piece (chunk widths differ)
+    int c = 0;
+    for (int i = 1; i < nparts; ++i) {
+      const long target = (long)cap * i / nparts;
+      while (c < view.nchunks && hp->chunk_start[c] < target) ++c;
+      cbeg[i] = c; sbeg[i] = hp->chunk_start[c];
+    }
+    cbeg[nparts] = view.nchunks;
+  }
+  sbeg[nparts] = cap;
+  PP_CUDA(cudaMemsetAsync(mesh->stats_dev, 0, sizeof(SearchCounters), s));
+  PP_CUDA(cudaMemsetAsync(hp->sched, 0, kMaxParts * sizeof(int), s));
+  PP_CUDA(cudaEventRecord(hp->e_begin, s));
+  PP_CUDA(cudaStreamWaitEvent(hp->s_in, hp->e_begin, 0));
+  PP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->e_begin, 0));
+  for (int i = 0; i < nparts; ++i) {
+    const long lo = sbeg[i], n = sbeg[i + 1] - sbeg[i];
+    if (n > 0)
+      for (int k = 0; k < 3; ++k) {
+        PP_CUDA(cudaMemcpyAsync(hp->x + k * dstride + lo, h_x_orig + k * stride + lo, n * sizeof(double),
+                                cudaMemcpyHostToDevice, hp->s_in));
+        PP_CUDA(cudaMemcpyAsync(hp->dir + k * dstride + lo, h_dir + k * stride + lo, n * sizeof(double),
+                                cudaMemcpyHostToDevice, hp->s_in));
+      }
+    PP_CUDA(cudaEventRecord(hp->e_in[i], hp->s_in));
+  }
+  for (int i = 0; i < nparts; ++i) {
+    PP_CUDA(cudaStreamWaitEvent(s, hp->e_in[i], 0));
+    if (chunked) {
+      ChunkPart part{cbeg[i], cbeg[i + 1], hp->sched + i};
+      if (part.end > part.begin)
+        PP_TRY(do_search(mesh, view, ps->nelems, &a, hp->dir, distance, true, 1, nullptr, s, &part));
+    } else {
+      PP_TRY(do_search(mesh, view, ps->nelems, &a, hp->dir, distance, true, 1, nullptr, s));
+    }
+    PP_CUDA(cudaEventRecord(hp->e_k[i], s));
+    PP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->e_k[i], 0));
+    const long lo = sbeg[i], n = sbeg[i + 1] - sbeg[i];
+    if (n > 0) {
+      for (int k = 0; k < 3; ++k)
+        PP_CUDA(cudaMemcpyAsync(h_x_tgt + k * stride + lo, hp->xt + k * dstride + lo, n * sizeof(double),
+                                cudaMemcpyDeviceToHost, hp->s_out));
+      PP_CUDA(cudaMemcpyAsync(h_elem_ids + lo, hp->ids + lo, n * sizeof(int), cudaMemcpyDeviceToHost,
+                              hp->s_out));
+    }
+  }
+  PP_CUDA(cudaEventRecord(hp->e_end, hp->s_out));
+  PP_CUDA(cudaStreamWaitEvent(s, hp->e_end, 0));
+  if (stats_host) PP_TRY(read_stats(mesh, PP_SEARCH_NEW, looplimit, stats_host, s));
+  return PP_OK;
 }

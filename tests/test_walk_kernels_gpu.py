@@ -168,3 +168,31 @@ def test_chunk_walk_after_rebuild_full_loop():
                 o_pos[k] = To[:, j]
                 o_elem[k] = int(ids_o[j])
         assert ps.nptcls == len(o_pos)
+
+
+@pytest.mark.parametrize("kind,nparts", [("scs", 5), ("scs", 1), ("scs", 64), ("csr", 4), ("dps", 3)])
+def test_host_buffer_pipeline_matches_oracle(kind, nparts):
+    """pp_push_direction_search_host: pinned host columns in, host results out, pieces overlapped."""
+    mesh = load_fixture("cube7k")
+    P = pp()
+    om = orc.OracleMesh(mesh)
+    gm = make_gpu_mesh(mesh)
+    ps = make_ps(_kind(kind), _uneven_ppe(mesh.nelems, 50000))
+    slot_elem, mask = ps.slot_elem_and_mask()
+    X, D = pi.init3d_internal(mesh, slot_elem, mask)
+    m = mask.astype(bool)
+    t = torch()
+    dist = 2.5 * pi.push_distance(mesh)
+    hx = t.as_tensor(X).pin_memory(); hd = t.as_tensor(D).pin_memory()
+    ht = t.zeros_like(hx).pin_memory()
+    hi = t.full((ps.capacity,), -9, dtype=t.int32).pin_memory()
+    for rep in range(2):                           # second call reuses the staging buffers
+        r = P.push_direction_search_host(gm, ps, hx, hd, ht, hi, dist, nparts=nparts)
+        t.cuda.synchronize()
+        T = np.zeros_like(X)
+        T[:, m] = X[:, m] + dist * D[:, m]
+        found, ids_o, _, _, st = om.search_mesh(slot_elem, mask, X, T)
+        assert np.array_equal(hi.numpy(), ids_o)
+        assert np.array_equal(ht.numpy()[:, m], T[:, m])
+        assert (r.found, r.loops, r.not_in_elem) == (int(found), st.loops, st.not_in_elem)
+        assert r.active == int(m.sum())
