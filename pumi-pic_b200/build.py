@@ -62,5 +62,22 @@ def build(verbose=False, force=False, extra_flags=(), lib=None, obj=None):
     return LIB
 
 
+def build_cpp_tests():
+    """nvcc-compiled driver that exercises the C++ API mirror (tests/cpp); the binary travels to
+    the GPU box with the snapshot."""
+    src = os.path.join(ROOT, "tests", "cpp", "pseudo_push_and_search.cu")
+    out_dir = os.path.join(ROOT, "tests", "cpp", "_bin")
+    out = os.path.join(out_dir, "pseudo_push_and_search")
+    os.makedirs(out_dir, exist_ok=True)
+    hdr = os.path.join(HERE, "cpp", "pumipic_b200.hpp")
+    if _newer(src, out, [hdr, LIB, os.path.join(ROOT, "include", "pumipic_b200.h")]):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2",
+                               "-std=c++17", "--extended-lambda", "-fmad=false",
+                               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "cpp"),
+                               src, "-o", out, "-L", HERE, "-lpumipic_b200",
+                               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../../pumi-pic_b200"])
+    return out
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

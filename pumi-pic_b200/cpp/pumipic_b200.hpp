@@ -1,0 +1,517 @@
+// pumipic_b200.hpp -- header-only C++ mirror of the PUMI-PIC API surface of the particle hot path,
+// implemented over the C ABI of libpumipic_b200.so (include/pumipic_b200.h).
+//
+// Same names, argument meaning and error behaviour as the reference so that a driver written
+// against SCOREC/pumi-pic (test/pseudoPushAndSearch.cpp, test/test_adj.cpp, test/pseudoXGCm.cpp)
+// reads the same here.  What it mirrors (paths relative to the reference):
+//   pumipic::MemberTypes / BaseType          particle_structs/src/support/MemberTypes.h:21-60,
+//                                            support/ppTypes.h:13-30
+//   pumipic::Segment                         particle_structs/src/support/Segment.h:31-101
+//   pumipic::ParticleStructure<DataTypes>    particle_structs/src/particle_structure.hpp:19-144
+//   pumipic::SellCSigma / SCS_Input          scs/SellCSigma.h:66-72, scs/scs_input.hpp:4-36
+//   pumipic::CSR / DPS / CabM                csr/CSR.hpp:37-44, dps/dps.hpp:41-48, cabm/cabm.hpp:41-48
+//   pumipic::parallel_for                    particle_structs/src/ps_for.hpp:5-31
+//   pumipic::Mesh                            src/pumipic_mesh.hpp:12-76 (hot-path subset)
+//   pumipic::search_mesh / search_mesh_2d    src/pumipic_adjacency.hpp:37-45,559-562,1013-1020
+//   pumipic::migrate_ptcls / setUnsafeProcs  src/pumipic_ptcl_ops.hpp:12-85
+//   pumipic::Distributor                     particle_structs/src/support/psDistributor.hpp:10-28
+//
+// Differences forced by the missing third-party stack (no Kokkos, no Omega_h here): device arrays
+// are pumipic::View<T> (a ref-counted cudaMalloc buffer with data()/size(), the role of
+// Kokkos::View<T*> and Omega_h::Write<T>), and pumipic::Mesh is built from the mesh arrays an
+// Omega_h mesh would hand over.  Errors: like the reference (printError + exit / throw 1), a failed
+// C-ABI call prints pp_last_error() and throws std::runtime_error.
+//
+// User lambdas cannot cross a C ABI: ps::parallel_for is a template that needs nvcc
+// (__CUDACC__); host-only translation units get everything else, including the named built-in
+// kernels (push, search, rebuild, migrate, scatter).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "pumipic_b200.h"
+
+#ifdef __CUDACC__
+#define PP_INLINE __host__ __device__ inline
+#define PP_DEV_INLINE __device__ inline
+#define PS_LAMBDA [=] __device__
+#else
+#define PP_INLINE inline
+#define PP_DEV_INLINE inline
+#endif
+
+namespace pumipic {
+
+typedef int lid_t;       // support/ppTypes.h:6-8
+typedef long int gid_t;
+typedef double fp_t;     // src/pumipic_kktypes.hpp:10-16 (FP64 build)
+
+inline void pp_check(pp_status st, const char* what) {
+  if (st != PP_OK) {
+    std::fprintf(stderr, "[ERROR] %s: %s\n", what, pp_last_error());
+    throw std::runtime_error(std::string(what) + ": " + pp_last_error());
+  }
+}
+inline void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    std::fprintf(stderr, "[ERROR] %s: %s\n", what, cudaGetErrorString(e));
+    throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+  }
+}
+
+// ---------------------------------------------------------------- device array
+template <class T>
+class View {
+ public:
+  View() : n_(0) {}
+  explicit View(size_t n, const std::string& name = "") : n_(n), name_(name) { alloc(); }
+  View(const std::string& name, size_t n) : n_(n), name_(name) { alloc(); }   // Kokkos argument order
+  View(size_t n, T fill, const std::string& name = "") : n_(n), name_(name) {  // Omega_h::Write(n, v)
+    alloc();
+    std::vector<T> h(n, fill);
+    if (n) cuda_check(cudaMemcpy(p_.get(), h.data(), n * sizeof(T), cudaMemcpyHostToDevice), "View fill");
+  }
+  explicit View(const std::vector<T>& host) : n_(host.size()) {
+    alloc();
+    if (n_) cuda_check(cudaMemcpy(p_.get(), host.data(), n_ * sizeof(T), cudaMemcpyHostToDevice), "View h2d");
+  }
+  T* data() const { return p_.get(); }
+  size_t size() const { return n_; }
+  bool exists() const { return n_ != 0; }
+  PP_DEV_INLINE T& operator()(size_t i) const { return raw_[i]; }
+  PP_DEV_INLINE T& operator[](size_t i) const { return raw_[i]; }
+  std::vector<T> toHost() const {
+    std::vector<T> h(n_);
+    if (n_) cuda_check(cudaMemcpy(h.data(), p_.get(), n_ * sizeof(T), cudaMemcpyDeviceToHost), "View d2h");
+    return h;
+  }
+
+ private:
+  void alloc() {
+    T* q = nullptr;
+    if (n_) cuda_check(cudaMalloc((void**)&q, n_ * sizeof(T)), "View alloc");
+    p_ = std::shared_ptr<T>(q, [](T* x) { if (x) cudaFree(x); });
+    raw_ = q;
+  }
+  std::shared_ptr<T> p_;
+  T* raw_ = nullptr;
+  size_t n_;
+  std::string name_;
+};
+
+// ---------------------------------------------------------------- member types
+template <class T> struct BaseType { typedef T type; static constexpr int size = 1; };
+template <class T, int N> struct BaseType<T[N]> {
+  typedef typename BaseType<T>::type type;
+  static constexpr int size = N * BaseType<T>::size;
+};
+
+template <typename... Types> struct MemberTypes;
+template <> struct MemberTypes<> {
+  static constexpr std::size_t size = 0;
+  static constexpr std::size_t memsize = 0;
+  static void describe(pp_member_desc*) {}
+};
+template <typename H, typename... T> struct MemberTypes<H, T...> {
+  static constexpr std::size_t size = 1 + MemberTypes<T...>::size;
+  static constexpr std::size_t memsize = sizeof(H) + MemberTypes<T...>::memsize;
+  static void describe(pp_member_desc* d) {
+    d->scalar_bytes = (int32_t)sizeof(typename BaseType<H>::type);
+    d->ncomp = BaseType<H>::size;
+    MemberTypes<T...>::describe(d + 1);
+  }
+};
+template <std::size_t N, typename... Types> struct MemberTypeAtIndex;
+template <typename H, typename... T> struct MemberTypeAtIndex<0, MemberTypes<H, T...>> { typedef H type; };
+template <std::size_t N, typename H, typename... T> struct MemberTypeAtIndex<N, MemberTypes<H, T...>> {
+  typedef typename MemberTypeAtIndex<N - 1, MemberTypes<T...>>::type type;
+};
+
+// MemberTypeViews (MemberTypeLibraries.h:17): one device array per member, [ncomp][n]
+typedef void** MemberTypeViews;
+template <class DataTypes> MemberTypeViews createMemberViews(int n) {
+  pp_member_desc d[DataTypes::size ? DataTypes::size : 1];
+  DataTypes::describe(d);
+  void** v = new void*[DataTypes::size];
+  for (std::size_t i = 0; i < DataTypes::size; ++i)
+    cuda_check(cudaMalloc(&v[i], (size_t)d[i].scalar_bytes * d[i].ncomp * (n > 0 ? n : 1)), "createMemberViews");
+  return v;
+}
+template <class DataTypes> void destroyViews(MemberTypeViews v) {
+  if (!v) return;
+  for (std::size_t i = 0; i < DataTypes::size; ++i) cudaFree(v[i]);
+  delete[] v;
+}
+
+// ---------------------------------------------------------------- Segment: by-value accessor
+// value(slot, i) lives at base[i * stride + slot] (LayoutLeft, support/ppView.h:7)
+template <class Type>
+class Segment {
+ public:
+  typedef typename BaseType<Type>::type Base;
+  Segment() : base_(nullptr), stride_(0) {}
+  Segment(Base* b, long stride) : base_(b), stride_(stride) {}
+  PP_DEV_INLINE Base& operator()(const int& particle_index) const { return base_[particle_index]; }
+  PP_DEV_INLINE Base& operator()(const int& particle_index, const int& i) const {
+    return base_[(long)i * stride_ + particle_index];
+  }
+  Base* data() const { return base_; }
+  long stride() const { return stride_; }
+
+ private:
+  Base* base_;
+  long stride_;
+};
+
+// ---------------------------------------------------------------- Distributor (world only)
+class Distributor {
+ public:
+  Distributor() : comm_(nullptr) {}
+  explicit Distributor(pp_comm* c) : comm_(c) {}
+  bool isWorld() const { return true; }
+  int num_ranks() const { return comm_ ? pp_comm_size(comm_) : 1; }
+  pp_comm* comm() const { return comm_; }
+
+ private:
+  pp_comm* comm_;
+};
+
+// Kokkos::TeamPolicy stand-in: only team_size() matters to the structures (C = team_size)
+struct TeamPolicy {
+  TeamPolicy(int league = 1, int team = 32) : league_(league), team_(team) {}
+  int team_size() const { return team_; }
+  int league_, team_;
+};
+
+enum PaddingStrategy { PAD_EVENLY, PAD_PROPORTIONALLY, PAD_INVERSELY };
+
+// ---------------------------------------------------------------- ParticleStructure
+template <class DataTypes>
+class ParticleStructure {
+ public:
+  typedef DataTypes Types;
+  typedef View<lid_t> kkLidView;
+  typedef View<gid_t> kkGidView;
+  typedef MemberTypeViews MTVs;
+  template <std::size_t N> using DataType = typename MemberTypeAtIndex<N, DataTypes>::type;
+  template <std::size_t N> using Slice = Segment<DataType<N>>;
+
+  virtual ~ParticleStructure() { if (h_) pp_ps_destroy(h_); }
+  const std::string& getName() const { return name; }
+  lid_t nElems() const { return pp_ps_nelems(h_); }
+  lid_t nPtcls() const { return pp_ps_nptcls(h_); }
+  lid_t capacity() const { return pp_ps_capacity(h_); }
+  lid_t numRows() const { return pp_ps_numrows(h_); }
+
+  // invalidated by rebuild / migrate, like the reference's Segments
+  template <std::size_t N> Slice<N> get() {
+    void* base = nullptr;
+    int64_t stride = 0;
+    pp_check(pp_ps_member(h_, (int32_t)N, &base, &stride), "ParticleStructure::get");
+    return Slice<N>(static_cast<typename BaseType<DataType<N>>::type*>(base), (long)stride);
+  }
+
+  virtual void rebuild(kkLidView new_element, kkLidView new_particle_elements = kkLidView(),
+                       MTVs new_particle_info = NULL) {
+    pp_check(pp_ps_rebuild(h_, new_element.data(), (int32_t)new_particle_elements.size(),
+                           new_particle_elements.data(), new_particle_info, stream_),
+             "ParticleStructure::rebuild");
+  }
+  virtual void migrate(kkLidView new_element, kkLidView new_process, Distributor dist = Distributor(),
+                       kkLidView new_particle_elements = kkLidView(), MTVs new_particle_info = NULL) {
+    if (!dist.comm() || dist.num_ranks() == 1) {   // SCS_migrate.h:20-25
+      rebuild(new_element, new_particle_elements, new_particle_info);
+      return;
+    }
+    pp_migrate_stats st;
+    pp_check(pp_ps_migrate(h_, dist.comm(), new_element.data(), new_process.data(),
+                           (int32_t)new_particle_elements.size(), new_particle_elements.data(),
+                           new_particle_info, &st, stream_),
+             "ParticleStructure::migrate");
+  }
+  virtual void printMetrics() const {
+    std::printf("%s: elements %d rows %d particles %d capacity %d\n", name.c_str(), nElems(), numRows(),
+                nPtcls(), capacity());
+  }
+  virtual void printFormat(const char* prefix = "") const { std::printf("%s%s\n", prefix, name.c_str()); }
+
+  pp_ps* handle() const { return h_; }
+  cudaStream_t stream() const { return (cudaStream_t)stream_; }
+  void setStream(cudaStream_t s) { stream_ = (pp_stream)s; }
+
+ protected:
+  ParticleStructure(const std::string& n) : name(n), h_(nullptr), stream_(nullptr) {}
+  void create(pp_ps_config cfg, lid_t ne, lid_t np, kkLidView ppe, kkGidView gids,
+              kkLidView particle_elements, MTVs particle_info) {
+    pp_member_desc d[DataTypes::size ? DataTypes::size : 1];
+    DataTypes::describe(d);
+    pp_check(pp_ps_create(&cfg, (int32_t)DataTypes::size, d, ne, np, ppe.data(),
+                          gids.size() ? (const int64_t*)gids.data() : nullptr,
+                          particle_elements.size() ? particle_elements.data() : nullptr,
+                          particle_info, PP_DEVICE, stream_, &h_),
+             name.c_str());
+  }
+  std::string name;
+  pp_ps* h_;
+  pp_stream stream_;
+};
+
+template <class DataTypes> class SellCSigma;
+
+template <class DataTypes>
+class SCS_Input {
+ public:
+  typedef View<lid_t> kkLidView;
+  typedef View<gid_t> kkGidView;
+  typedef MemberTypeViews MTVs;
+  typedef TeamPolicy PolicyType;
+  SCS_Input(PolicyType& p, lid_t sigma_, lid_t vertical_chunk_size, lid_t num_elements, lid_t num_particles,
+            kkLidView particles_per_elements, kkGidView element_gids,
+            kkLidView particle_elements_ = kkLidView(), MTVs particle_info = NULL)
+      : policy(p), sig(sigma_), V(vertical_chunk_size), ne(num_elements), np(num_particles),
+        ppe(particles_per_elements), e_gids(element_gids), particle_elms(particle_elements_), p_info(particle_info) {}
+  bool always_realloc = false;
+  double minimize_size = .8;
+  double shuffle_padding = 0.1;
+  double extra_padding = 0.05;
+  PaddingStrategy padding_strat = PAD_EVENLY;
+  std::string name = "ptcls";
+
+ protected:
+  PolicyType policy;
+  lid_t sig, V, ne, np;
+  kkLidView ppe;
+  kkGidView e_gids;
+  kkLidView particle_elms;
+  MTVs p_info;
+  friend class SellCSigma<DataTypes>;
+};
+
+template <class DataTypes>
+class SellCSigma : public ParticleStructure<DataTypes> {
+ public:
+  typedef ParticleStructure<DataTypes> Base;
+  using typename Base::kkGidView;
+  using typename Base::kkLidView;
+  using typename Base::MTVs;
+  typedef TeamPolicy PolicyType;
+  SellCSigma(PolicyType& p, lid_t sigma, lid_t vertical_chunk_size, lid_t num_elements, lid_t num_particles,
+             kkLidView particles_per_element, kkGidView element_gids, kkLidView particle_elements = kkLidView(),
+             MTVs particle_info = NULL)
+      : Base("ptcls") {
+    pp_ps_config cfg;
+    pp_ps_config_default(&cfg, PP_PS_SCS);
+    cfg.team_size = p.team_size(); cfg.sigma = sigma; cfg.V = vertical_chunk_size;
+    this->create(cfg, num_elements, num_particles, particles_per_element, element_gids, particle_elements,
+                 particle_info);
+  }
+  explicit SellCSigma(SCS_Input<DataTypes>& in) : Base(in.name) {
+    pp_ps_config cfg;
+    pp_ps_config_default(&cfg, PP_PS_SCS);
+    cfg.team_size = in.policy.team_size(); cfg.sigma = in.sig; cfg.V = in.V;
+    cfg.shuffle_padding = in.shuffle_padding; cfg.extra_padding = in.extra_padding;
+    cfg.minimize_size = in.minimize_size; cfg.padding_strat = (int32_t)in.padding_strat;
+    cfg.always_realloc = in.always_realloc;
+    this->create(cfg, in.ne, in.np, in.ppe, in.e_gids, in.particle_elms, in.p_info);
+  }
+  lid_t C() const { return layout().C; }
+  lid_t V() const { return layout().V; }
+  pp_ps_layout layout() const {
+    pp_ps_layout l;
+    pp_check(pp_ps_get_layout(this->h_, this->stream_, &l), "SellCSigma::layout");
+    return l;
+  }
+};
+
+#define PP_B200_FLAT_STRUCTURE(NAME, KIND, LABEL)                                                     \
+  template <class DataTypes>                                                                          \
+  class NAME : public ParticleStructure<DataTypes> {                                                  \
+   public:                                                                                            \
+    typedef ParticleStructure<DataTypes> Base;                                                        \
+    using typename Base::kkGidView;                                                                   \
+    using typename Base::kkLidView;                                                                   \
+    using typename Base::MTVs;                                                                        \
+    typedef TeamPolicy PolicyType;                                                                    \
+    NAME(PolicyType& p, lid_t num_elements, lid_t num_particles, kkLidView particles_per_element,     \
+         kkGidView element_gids, kkLidView particle_elements = kkLidView(), MTVs particle_info = NULL) \
+        : Base(LABEL) {                                                                               \
+      pp_ps_config cfg;                                                                               \
+      pp_ps_config_default(&cfg, KIND);                                                               \
+      cfg.team_size = p.team_size();                                                                  \
+      this->create(cfg, num_elements, num_particles, particles_per_element, element_gids,             \
+                   particle_elements, particle_info);                                                 \
+    }                                                                                                 \
+  };
+PP_B200_FLAT_STRUCTURE(CSR, PP_PS_CSR, "ptcls")     // csr/CSR.hpp:37-44
+PP_B200_FLAT_STRUCTURE(DPS, PP_PS_DPS, "ptcls")     // dps/dps.hpp:41-48
+PP_B200_FLAT_STRUCTURE(CabM, PP_PS_CABM, "ptcls")   // cabm/cabm.hpp:41-48
+#undef PP_B200_FLAT_STRUCTURE
+
+// ---------------------------------------------------------------- parallel_for (nvcc only)
+#ifdef __CUDACC__
+namespace detail {
+template <class Fn>
+__global__ void k_parallel_for(Fn fn, int capacity, const uint32_t* __restrict__ mask_bits,
+                               const int* __restrict__ slot_elem) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= capacity) return;
+  const bool mask = (mask_bits[slot >> 5] >> (slot & 31)) & 1u;
+  fn(slot_elem[slot], slot, mask);
+}
+}  // namespace detail
+
+// ps_for.hpp:5-31: fn(const int elem, const int slot, const bool mask) for every slot of the
+// structure including padding.  Consecutive threads take consecutive slots, which in a
+// Sell-C-sigma chunk are consecutive rows (coalesced member access), as in SellCSigma.h:528-558.
+template <typename FunctionType, typename DataTypes>
+void parallel_for(ParticleStructure<DataTypes>* ps, FunctionType& fn, std::string name = "") {
+  (void)name;
+  pp_ps_layout l;
+  pp_check(pp_ps_get_layout(ps->handle(), (pp_stream)ps->stream(), &l), "parallel_for");
+  if (l.capacity == 0) return;
+  const int block = 256;
+  detail::k_parallel_for<<<(l.capacity + block - 1) / block, block, 0, ps->stream()>>>(
+      fn, l.capacity, l.mask_bits, l.slot_elem);
+  cuda_check(cudaGetLastError(), "parallel_for launch");
+}
+#endif
+
+// ---------------------------------------------------------------- Mesh (PICpart handle)
+class Mesh {
+ public:
+  enum Op { SUM_OP, MAX_OP, MIN_OP, BCAST_OP };   // pumipic_mesh.hpp:57-62
+  // host arrays with Omega_h's entity numbering (coords, ask_elem_verts, ask_down(dim,dim-1),
+  // ask_verts_of(dim-1), class_id); derived search data is built once on the device
+  Mesh(int dim, const std::vector<double>& coords, const std::vector<int>& elem2verts,
+       const std::vector<int>& elem2sides, const std::vector<int>& side2verts,
+       const std::vector<int>& elem_class = std::vector<int>())
+      : dim_(dim), comm_(nullptr) {
+    pp_mesh_desc d;
+    d.dim = dim;
+    d.nverts = (int32_t)(coords.size() / dim);
+    d.nelems = (int32_t)(elem2verts.size() / (dim + 1));
+    d.nsides = (int32_t)(side2verts.size() / dim);
+    d.coords = coords.data(); d.elem2verts = elem2verts.data(); d.elem2sides = elem2sides.data();
+    d.side2verts = side2verts.data(); d.elem_class = elem_class.empty() ? nullptr : elem_class.data();
+    d.memspace = PP_HOST;
+    pp_check(pp_mesh_create(&d, nullptr, &h_), "Mesh");
+    nents_[0] = d.nverts; nents_[dim - 1] = d.nsides; nents_[dim] = d.nelems;
+  }
+  ~Mesh() { if (h_) pp_mesh_destroy(h_); }
+  Mesh(const Mesh&) = delete;
+  Mesh& operator=(const Mesh&) = delete;
+  int dim() const { return dim_; }
+  lid_t nelems() const { return nents_[dim_]; }
+  lid_t nents(int d) const { return nents_[d]; }
+  pp_mesh* handle() const { return h_; }
+  pp_mesh* operator->() const { return h_; }
+  bool isFullMesh() const { return true; }
+  // PICpart tags (Mesh::safeTag(), Mesh::entOwners(dim)) and the communicator
+  void setPICpart(const std::vector<int>& safe, const std::vector<int>& owners, int self_rank, pp_comm* comm) {
+    pp_check(pp_mesh_set_picpart(h_, safe.data(), owners.data(), self_rank, PP_HOST, nullptr), "setPICpart");
+    comm_ = comm;
+  }
+  pp_comm* comm() const { return comm_; }
+  template <class T> View<T> createCommArray(int edim, int nvals, T init) {   // pumipic_comm.cpp:187-192
+    return View<T>((size_t)nents_[edim] * nvals, init);
+  }
+  // full-mesh PICparts: SUM/MAX/MIN over all copies, or the owner's value (pumipic_comm.cpp:223-247)
+  void reduceCommArray(int edim, Op op, View<double> array, const int* ent_owner_dev = nullptr) {
+    if (!comm_) return;
+    const int nvals = (int)(array.size() / nents_[edim]);
+    pp_check(pp_comm_array_reduce(comm_, array.data(), nents_[edim], nvals, PP_FLOAT64, (int32_t)op,
+                                  ent_owner_dev, nullptr), "reduceCommArray");
+  }
+
+ private:
+  int dim_;
+  lid_t nents_[4] = {0, 0, 0, 0};
+  pp_mesh* h_ = nullptr;
+  pp_comm* comm_;
+};
+
+// ---------------------------------------------------------------- search
+namespace detail {
+template <class PS, class Seg3>
+inline bool run_search(Mesh& mesh, PS* ptcls, int variant, Seg3 x_orig, Seg3 x_tgt, View<lid_t>& elem_ids,
+                       bool requireIntersection, View<lid_t>* inter_faces, View<fp_t>* inter_points,
+                       int inter_dim, int looplimit) {
+  const size_t cap = (size_t)ptcls->capacity();
+  pp_search_args a;
+  a.variant = variant;
+  a.x_orig = x_orig.data(); a.x_tgt = x_tgt.data(); a.stride = x_tgt.stride();
+  a.elem_ids_empty = elem_ids.size() == 0;
+  if (elem_ids.size() == 0) elem_ids = View<lid_t>(cap, "elem_ids");           // tpp:504-509
+  a.elem_ids = elem_ids.data();
+  a.require_intersection = requireIntersection;
+  if (inter_faces && (requireIntersection || variant == PP_SEARCH_3D_LEGACY)) {
+    if (inter_faces->size() < cap) *inter_faces = View<lid_t>(cap, (lid_t)-1, "inter_faces");   // tpp:538-539
+    if (inter_points->size() < cap * inter_dim) *inter_points = View<fp_t>(cap * inter_dim, 0.0, "inter_points");
+  }
+  a.inter_faces = inter_faces ? inter_faces->data() : nullptr;
+  a.inter_points = inter_points ? inter_points->data() : nullptr;
+  a.looplimit = looplimit;
+  pp_search_stats st;
+  pp_check(pp_search_mesh(mesh.handle(), ptcls->handle(), &a, &st, (pp_stream)ptcls->stream()), "search_mesh");
+  return st.found != 0;
+}
+}  // namespace detail
+
+// adjacency.hpp:37-45 / adjacency.tpp:642
+template <class ParticleType, typename Segment3d, typename SegmentInt>
+bool search_mesh(Mesh& mesh, ParticleStructure<ParticleType>* ptcls, Segment3d x_ps_orig, Segment3d x_ps_tgt,
+                 SegmentInt /*pids*/, View<lid_t>& elem_ids, bool requireIntersection, View<lid_t>& inter_faces,
+                 View<fp_t>& inter_points, int looplimit = 0, int /*debug*/ = 0) {
+  return detail::run_search(mesh, ptcls, PP_SEARCH_NEW, x_ps_orig, x_ps_tgt, elem_ids, requireIntersection,
+                            &inter_faces, &inter_points, mesh.dim(), looplimit);
+}
+// adjacency.hpp:559-562 (legacy 3D: line-triangle + dual graph)
+template <class ParticleType, typename Segment3d, typename SegmentInt>
+bool search_mesh(Mesh& mesh, ParticleStructure<ParticleType>* ptcls, Segment3d x_ps_d, Segment3d xtgt_ps_d,
+                 SegmentInt /*pid_d*/, View<lid_t>& elem_ids, View<fp_t>& xpoints_d, View<lid_t>& xface_id,
+                 int looplimit = 0, int /*debug*/ = 0) {
+  return detail::run_search(mesh, ptcls, PP_SEARCH_3D_LEGACY, x_ps_d, xtgt_ps_d, elem_ids, false, &xface_id,
+                            &xpoints_d, 3, looplimit);
+}
+// adjacency.hpp:1013-1020 (elem_ids by value, -1 = start in the row element)
+template <class ParticleType, typename Segment3d, typename SegmentInt>
+bool search_mesh_2d(Mesh& mesh, ParticleStructure<ParticleType>* ptcls, Segment3d x_ps_d, Segment3d xtgt_ps_d,
+                    SegmentInt /*pid_d*/, View<lid_t> elem_ids, int looplimit = 0, bool /*debug*/ = false) {
+  return detail::run_search(mesh, ptcls, PP_SEARCH_2D_LEGACY, x_ps_d, xtgt_ps_d, elem_ids, false, nullptr,
+                            nullptr, 2, looplimit);
+}
+
+// ---------------------------------------------------------------- migration ops (ptcl_ops.hpp)
+template <class PS>
+void setUnsafeProcs(Mesh& mesh, PS* ptcls, View<lid_t> elems, View<lid_t>& new_elems, View<lid_t>& new_procs) {
+  const size_t cap = (size_t)ptcls->capacity();
+  if (new_elems.size() < cap) new_elems = View<lid_t>(cap);
+  if (new_procs.size() < cap) new_procs = View<lid_t>(cap);
+  pp_check(pp_set_unsafe_procs(mesh.handle(), ptcls->handle(), elems.data(), new_elems.data(), new_procs.data(),
+                               (pp_stream)ptcls->stream()), "setUnsafeProcs");
+}
+template <class PS>
+void migrate_ptcls(Mesh& mesh, PS* ptcls, View<lid_t> new_elems) {
+  View<lid_t> ptcl_elems, ptcl_procs;
+  setUnsafeProcs(mesh, ptcls, new_elems, ptcl_elems, ptcl_procs);
+  ptcls->migrate(ptcl_elems, ptcl_procs, Distributor(mesh.comm()));
+}
+// the EnGPar balancer is out of scope; without it migrate_lb_ptcls is migrate_ptcls,
+// which is also what the reference does on one rank (pumipic_lb.hpp:357-358)
+template <class PS>
+void migrate_lb_ptcls(Mesh& mesh, PS* ptcls, View<lid_t> new_elems, float /*tol*/, float /*step_factor*/ = 0.5) {
+  migrate_ptcls(mesh, ptcls, new_elems);
+}
+
+}  // namespace pumipic
+
+namespace ps = pumipic;

@@ -41,6 +41,14 @@ __global__ void k_copy_ints(const int* __restrict__ src, int n, int cap, int* ds
   dst[s] = s < n ? src[s] : fill;
 }
 
+__global__ void k_csr_slots(const int* __restrict__ elems, int n, const int* __restrict__ off, int* fill,
+                            int* slots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = elems[i];
+  slots[i] = off[e] + atomicAdd(fill + e, 1);
+}
+
 // copy member data [ncomp][np] -> [ncomp][stride] at slots given by `slots` (or identity)
 __global__ void k_place_member(const char* __restrict__ src, long np, int ncomp, int sb,
                                const int* __restrict__ slots, char* dst, long stride) {
@@ -145,18 +153,28 @@ static pp_status build_flat(pp_ps* ps, const int* ppe_dev, const int* pelems_dev
                                                                            ps->slot_elem);
   }
   ps->slot_elem_valid = true;
-  if (csr) ps->offsets = off; else pp_dev_free(off, s);
   if (pinfo && np > 0) {
-    PP_REQUIRE(!csr, "CSR initial particle data: use PP_PS_SCS/DPS or rebuild with new particles");
+    int* slots = nullptr;
+    if (csr) {   // CSR_buildFns.hpp:95-141 initCsrData: particle i -> next free slot of its element
+      PP_REQUIRE(pelems_dev, "CSR initial particle data needs particle_elements");
+      int* fill;
+      PP_TRY(pp_dev_alloc(&fill, ne + 1, s));
+      PP_TRY(pp_dev_alloc(&slots, np, s));
+      PP_CUDA(cudaMemsetAsync(fill, 0, sizeof(int) * (ne + 1), s));
+      k_csr_slots<<<pp_div_up(np, kBlock), kBlock, 0, s>>>(pelems_dev, np, off, fill, slots);
+      pp_dev_free(fill, s);
+    }
     for (int i = 0; i < ps->nmembers; ++i) {
       const int sb = ps->members[i].scalar_bytes, nc = ps->members[i].ncomp;
       char* src;
       PP_TRY(pp_dev_import(&src, (const char*)pinfo[i], (size_t)sb * nc * np, memspace, s));
-      k_place_member<<<pp_div_up((long)np * nc, kBlock), kBlock, 0, s>>>(src, np, nc, sb, nullptr,
+      k_place_member<<<pp_div_up((long)np * nc, kBlock), kBlock, 0, s>>>(src, np, nc, sb, slots,
                                                                          (char*)ps->data[i], ps->stride);
       pp_dev_free(src, s);
     }
+    pp_dev_free(slots, s);
   }
+  if (csr) ps->offsets = off; else pp_dev_free(off, s);
   PP_KERNEL_CHECK();
   return PP_OK;
 }
