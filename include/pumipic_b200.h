@@ -223,6 +223,13 @@ pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
                         const int32_t* new_particle_elements,
                         const void* const* new_particle_info, pp_stream stream);
 
+/* Record move of a full re-layout: 1 (default) = through an array-of-records stage (every DRAM
+ * access a full sector), 0 = direct scatter.  Same results as sets of particles; for A/B timing. */
+void pp_ps_set_staged_rebuild(int32_t on);
+/* Average particles per element from which a rebuild derives counts and in-row ranks from a sort
+ * of the particles by destination element instead of per-element atomics (default 128). */
+void pp_ps_set_rank_sort_threshold(int32_t particles_per_element);
+
 /* ============================== push ===================================================== */
 
 /* test/pseudoPushAndSearch.cpp:87-118: xtgt = x + distance*(dx,dy,dz) for masked slots */
@@ -243,6 +250,11 @@ pp_status pp_push_elliptical_setup(pp_ps* ps, const double* x, int64_t stride, f
 pp_status pp_push_elliptical(pp_mesh* mesh, pp_ps* ps, double* xtgt, int64_t stride,
                              const float* b, float* phi, double h, double k, double d, double deg,
                              pp_stream stream);
+/* src/pumipic_push.hpp:17-74 pushBoris on flat component-major arrays [3][stride] of n particles:
+ * v- = v - q'E, v' = v- + q'(v- x B), v = v- + c (v' x B) + q'E, x = x_prev + v dt, x_prev = x
+ * (charge 1, amu 10 as in the reference). */
+pp_status pp_push_boris(int64_t n, int64_t stride, double* pos, double* pos_prev, double* vel,
+                        const double* efield, const double* bfield, double dt, pp_stream stream);
 /* src/pumipic_ptcl_ops.hpp:33-53 setUnsafeProcs: new_elems = elems, new_procs = owner of the
  * element when it is not safe on this PICpart (tags from pp_mesh_set_picpart), else this rank. */
 pp_status pp_set_unsafe_procs(pp_mesh* mesh, pp_ps* ps, const int32_t* elems, int32_t* new_elems,

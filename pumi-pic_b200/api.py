@@ -305,6 +305,11 @@ def push_direction_search_host(mesh, ps, h_x, h_dir, h_xtgt, h_ids, distance, lo
     return SearchResult(st) if sync else None
 
 
+def push_boris(pos, pos_prev, vel, efield, bfield, dt):
+    check(lib().pp_push_boris(pos.shape[1], pos.shape[1], _ptr(pos), _ptr(pos_prev), _ptr(vel),
+                              _ptr(efield), _ptr(bfield), dt, _stream()))
+
+
 def push_constant(ps, x, xtgt, distance, d):
     check(lib().pp_push_constant(ps.h, _ptr(x), _ptr(xtgt), x.shape[1], distance, d[0], d[1], d[2],
                                  _stream()))

@@ -116,6 +116,8 @@ PROTOTYPES = {
     "pp_ps_get_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PsLayout)]),
     "pp_ps_rebuild": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                 C.POINTER(C.c_void_p), C.c_void_p]),
+    "pp_ps_set_staged_rebuild": (None, [C.c_int32]),
+    "pp_ps_set_rank_sort_threshold": (None, [C.c_int32]),
     "pp_push_constant": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                    C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "pp_push_direction": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
@@ -162,6 +164,8 @@ PROTOTYPES = {
                                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                                 C.c_int32, C.c_int32, C.POINTER(SearchStats),
                                                 C.c_void_p]),
+    "pp_push_boris": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_double, C.c_void_p]),
     "pp_push_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_double, C.c_void_p]),
 }

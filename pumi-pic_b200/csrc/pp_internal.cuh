@@ -14,6 +14,7 @@
 // error plumbing
 // ------------------------------------------------------------------------------------------
 void pp_set_error(const char* fmt, ...);
+void pp_runtime_init();   // once per device: keep the async allocation pool cached
 
 #define PP_CUDA(call)                                                                     \
   do {                                                                                    \
@@ -192,6 +193,8 @@ struct pp_ps {
   int64_t* elem_gids;       // [nelems] or null
   int64_t* sorted_gid;      // [nelems] gids ascending (built lazily for migrate)
   int* sorted_lid;          // [nelems] local id of sorted_gid[i]
+  char* stage;              // record stage of the rebuild (grow-only scratch)
+  size_t stage_bytes;
   PsView view() const;
 };
 

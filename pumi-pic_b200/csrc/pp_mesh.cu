@@ -200,6 +200,7 @@ extern "C" pp_status pp_mesh_create(const pp_mesh_desc* d, pp_stream stream_, pp
   PP_REQUIRE(d->dim == 2 || d->dim == 3, "dim must be 2 or 3");
   PP_REQUIRE(d->nverts > 0 && d->nelems > 0 && d->nsides > 0, "empty mesh");
   PP_REQUIRE(d->coords && d->elem2verts && d->elem2sides && d->side2verts, "null mesh array");
+  pp_runtime_init();
   cudaStream_t s = (cudaStream_t)stream_;
   const int dim = d->dim, nv = dim + 1, ne = d->nelems, ns = d->nsides;
   pp_mesh* m = new pp_mesh();

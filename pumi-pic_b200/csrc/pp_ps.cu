@@ -189,6 +189,7 @@ extern "C" pp_status pp_ps_create(const pp_ps_config* cfg, int32_t nmembers,
   PP_REQUIRE(nmembers > 0 && ne > 0 && np >= 0, "bad sizes");
   for (int i = 0; i < nmembers; ++i)
     PP_REQUIRE(members[i].scalar_bytes > 0 && members[i].ncomp > 0, "bad member descriptor");
+  pp_runtime_init();
   cudaStream_t s = (cudaStream_t)stream_;
   pp_ps* ps = new pp_ps();
   ps->cfg = *cfg;
@@ -201,6 +202,7 @@ extern "C" pp_status pp_ps_create(const pp_ps_config* cfg, int32_t nmembers,
   ps->C = 1; ps->V = cfg->V; ps->nchunks = 0; ps->nslices = 0;
   ps->offsets = ps->slice_to_chunk = ps->row_to_element = ps->element_to_row = ps->tile_slice = nullptr;
   ps->elem_gids = nullptr; ps->sorted_gid = nullptr; ps->sorted_lid = nullptr;
+  ps->stage = nullptr; ps->stage_bytes = 0;
   int* ppe_dev;
   PP_TRY(pp_dev_import(&ppe_dev, ppe, (size_t)ne, memspace, s));
   int* pel_dev = nullptr;
@@ -225,7 +227,7 @@ extern "C" pp_status pp_ps_destroy(pp_ps* ps) {
   for (void* p : ps->swap) cudaFree(p);
   cudaFree(ps->mask_bits); cudaFree(ps->slot_elem); cudaFree(ps->offsets);
   cudaFree(ps->slice_to_chunk); cudaFree(ps->row_to_element); cudaFree(ps->element_to_row);
-  cudaFree(ps->tile_slice); cudaFree(ps->elem_gids); cudaFree(ps->chunk_start); cudaFree(ps->row_ppe); cudaFree(ps->sorted_gid); cudaFree(ps->sorted_lid);
+  cudaFree(ps->tile_slice); cudaFree(ps->elem_gids); cudaFree(ps->chunk_start); cudaFree(ps->row_ppe); cudaFree(ps->sorted_gid); cudaFree(ps->sorted_lid); cudaFree(ps->stage);
   delete ps;
   return PP_OK;
 }

@@ -48,7 +48,47 @@ __global__ void k_update_positions(int cap, double* __restrict__ x, double* __re
     xt[i * stride + s] = 0;
   }
 }
+
+// src/pumipic_push.hpp:26-71 pushBoris, one thread per particle (the reference launches it with
+// parallel_for(1, ...), :74, i.e. as a formula; here it runs over all n particles).
+__global__ void k_push_boris(long n, long stride, double* __restrict__ pos, double* __restrict__ prev,
+                             double* __restrict__ vel, const double* __restrict__ ef,
+                             const double* __restrict__ bf, double qPrime, double dt) {
+  const long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const d3 v = {vel[p], vel[stride + p], vel[2 * stride + p]};
+  const d3 E = {ef[p], ef[stride + p], ef[2 * stride + p]};
+  const d3 B = {bf[p], bf[stride + p], bf[2 * stride + p]};
+  const double bmag = norm3(B);
+  const double coeff = 2.0 * qPrime / (1.0 + (qPrime * bmag) * (qPrime * bmag));
+  const d3 qpE = {E.x * qPrime, E.y * qPrime, E.z * qPrime};
+  const d3 vMinus = v - qpE;                                   // v_minus = v - q'E
+  const d3 c1 = cross3(vMinus, B);
+  const d3 vPrime = {vMinus.x + c1.x * qPrime, vMinus.y + c1.y * qPrime, vMinus.z + c1.z * qPrime};
+  const d3 c2 = cross3(vPrime, B);
+  d3 w = {vMinus.x + c2.x * coeff, vMinus.y + c2.y * coeff, vMinus.z + c2.z * coeff};
+  w = {w.x + qpE.x, w.y + qpE.y, w.z + qpE.z};
+  const d3 pre = {prev[p], prev[stride + p], prev[2 * stride + p]};
+  prev[p] = pos[p]; prev[stride + p] = pos[stride + p]; prev[2 * stride + p] = pos[2 * stride + p];
+  pos[p] = pre.x + w.x * dt; pos[stride + p] = pre.y + w.y * dt; pos[2 * stride + p] = pre.z + w.z * dt;
+  vel[p] = w.x; vel[stride + p] = w.y; vel[2 * stride + p] = w.z;
+}
 }  // namespace
+
+extern "C" pp_status pp_push_boris(int64_t n, int64_t stride, double* pos, double* pos_prev, double* vel,
+                                   const double* efield, const double* bfield, double dt,
+                                   pp_stream stream) {
+  PP_REQUIRE(pos && pos_prev && vel && efield && bfield, "null argument");
+  PP_REQUIRE(n >= 0 && stride >= n, "stride smaller than n");
+  PP_REQUIRE(dt > 0, "dt must be positive (OMEGA_H_CHECK in pumipic_push.hpp:35)");
+  if (n == 0) return PP_OK;
+  const double charge = 1, amu = 10;   // pumipic_push.hpp:32-33
+  const double qPrime = charge * 1.60217662e-19 / (amu * 1.6737236e-27) * dt * 0.5;
+  k_push_boris<<<pp_div_up(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(n, stride, pos, pos_prev, vel,
+                                                                           efield, bfield, qPrime, dt);
+  PP_KERNEL_CHECK();
+  return PP_OK;
+}
 
 extern "C" pp_status pp_push_constant(pp_ps* ps, const double* x, double* xtgt, int64_t stride,
                                       double distance, double dx, double dy, double dz,

@@ -326,6 +326,270 @@ __global__ void k_dps_fill_holes(uint32_t* mask, long nwords, int cap, const int
   if (set) mask[w] |= set;
 }
 
+// ------------------------------------------------------------------------------------------
+// Staged record move (the full re-layout of an element-sorted structure).
+//
+// With rows re-sorted by particle count, the destination slot of a particle is unrelated to its
+// source slot, and in the component-major SoA layout every 8-byte component of a particle sits
+// in a different 32-byte sector: a direct scatter turns each component store into a partial
+// sector write at a random address.  The move therefore goes through an array-of-records stage:
+//   pack   : read the old structure in slot order (coalesced), claim the destination slot, write
+//            the whole record (padded to full sectors) at stage[dest];
+//   unpack : read the stage in destination order and write the new SoA columns coalesced; the
+//            particle mask of the new structure is produced by the same pass.
+// Every DRAM access is a full sector; traffic is 2 x record (SoA) + 2 x padded record (stage).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxUnits = 40;          // 8-byte units of a particle record (<= 320 B)
+struct UnitTable {
+  int nunits;                          // units in use
+  int rec_bytes;                       // record stride in the stage (multiple of 32)
+  unsigned char kind[kMaxUnits];       // 0: one 8-byte scalar, 1: two 4-byte scalars (b may be null)
+  const char* sa[kMaxUnits];           // source component bases (slot 0)
+  const char* sb[kMaxUnits];
+  char* da[kMaxUnits];                 // destination component bases (slot 0)
+  char* db[kMaxUnits];
+};
+
+__device__ __forceinline__ unsigned long long unit_load(const UnitTable& t, int u, long s) {
+  if (t.kind[u] == 0) return *reinterpret_cast<const unsigned long long*>(t.sa[u] + 8 * s);
+  const unsigned lo = *reinterpret_cast<const unsigned*>(t.sa[u] + 4 * s);
+  const unsigned hi = t.sb[u] ? *reinterpret_cast<const unsigned*>(t.sb[u] + 4 * s) : 0u;
+  return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+__device__ __forceinline__ void unit_store(const UnitTable& t, int u, long s, unsigned long long v) {
+  if (t.kind[u] == 0) { *reinterpret_cast<unsigned long long*>(t.da[u] + 8 * s) = v; return; }
+  *reinterpret_cast<unsigned*>(t.da[u] + 4 * s) = (unsigned)v;
+  if (t.db[u]) *reinterpret_cast<unsigned*>(t.db[u] + 4 * s) = (unsigned)(v >> 32);
+}
+
+constexpr int kGroup = 4;   // quads (16 B) moved per batch: 8 independent loads in flight per thread
+
+__device__ __forceinline__ void load_group(const UnitTable& t, int q0, long s, uint4 (&r)[kGroup]) {
+#pragma unroll
+  for (int k = 0; k < kGroup; ++k) {
+    const int u = 2 * (q0 + k);
+    const unsigned long long a = u < t.nunits ? unit_load(t, u, s) : 0ull;
+    const unsigned long long b = u + 1 < t.nunits ? unit_load(t, u + 1, s) : 0ull;
+    r[k] = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+  }
+}
+__device__ __forceinline__ void pack_record(const UnitTable& t, long s, uint4* rec, const uint4 (&first)[kGroup]) {
+  const int nq = t.rec_bytes >> 4;
+#pragma unroll
+  for (int k = 0; k < kGroup; ++k)
+    if (k < nq) rec[k] = first[k];
+  for (int q0 = kGroup; q0 < nq; q0 += kGroup) {
+    uint4 r[kGroup];
+    load_group(t, q0, s, r);
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k)
+      if (q0 + k < nq) rec[q0 + k] = r[k];
+  }
+}
+
+// pack kept particles: dense != 0 -> CSR destination (dense_off[e] + fill), else Sell-C-sigma.
+//   * the first batch of record loads is issued before the destination chain (new element -> row
+//     -> slot claim), so the two latencies overlap;
+//   * records are written cooperatively: every lane parks its record in shared memory, then
+//     Q = rec_bytes/16 consecutive lanes store one record as one contiguous run.  A per-lane
+//     store of 16 bytes to 32 random records costs 32 memory transactions per instruction and the
+//     kernel becomes transaction-bound (measured: lg_throttle, 18 % of DRAM peak at 160 B records).
+__global__ void __launch_bounds__(256) k_stage_pack(PsView v, const int* __restrict__ new_elem,
+                                                    const int* __restrict__ elem2row,
+                                                    const int* __restrict__ chunk_start, int C, int dense,
+                                                    const int* __restrict__ dense_off, int* row_fill,
+                                                    const int* __restrict__ rank,
+                                                    const __grid_constant__ UnitTable t, char* stage) {
+  extern __shared__ __align__(16) unsigned char pack_smem[];
+  const int lane = threadIdx.x & 31;
+  const int stride = t.rec_bytes + 16;                       // bank-conflict-free row stride
+  unsigned char* wsm = pack_smem + (threadIdx.x >> 5) * 32 * stride;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  bool m = false;
+  if (s < v.capacity) m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  if (__ballot_sync(0xffffffffu, m) == 0u) return;           // warp-uniform
+  const int nq = t.rec_bytes >> 4;
+  int ns = -1;
+  if (m) {
+    const int e = __ldg(new_elem + s);
+    uint4 r[kGroup];
+    load_group(t, 0, s, r);
+    if (e >= 0) {
+      if (dense) {
+        ns = __ldg(dense_off + e) + (rank ? __ldg(rank + s) : atomicAdd(row_fill + e, 1));
+      } else {
+        const int row = __ldg(elem2row + e);
+        const int cs = __ldg(chunk_start + row / C);
+        const int col = rank ? __ldg(rank + s) : atomicAdd(row_fill + row, 1);
+        ns = cs + row % C + col * C;
+      }
+      uint4* mine = reinterpret_cast<uint4*>(wsm + lane * stride);
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k)
+        if (k < nq) mine[k] = r[k];
+      for (int q0 = kGroup; q0 < nq; q0 += kGroup) {
+        load_group(t, q0, s, r);
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k)
+          if (q0 + k < nq) mine[q0 + k] = r[k];
+      }
+    }
+  }
+  __syncwarp();
+  const int rpi = 32 / nq;                                   // records per store instruction
+  const int myrec = lane / nq, piece = lane - myrec * nq;
+  const bool act = myrec < rpi;
+  for (int base = 0; base < 32; base += rpi) {
+    const int rec = base + myrec;
+    const int nsr = __shfl_sync(0xffffffffu, ns, rec & 31);
+    if (act && rec < 32 && nsr >= 0)
+      *reinterpret_cast<uint4*>(stage + (long)nsr * t.rec_bytes + piece * 16) =
+          *reinterpret_cast<const uint4*>(wsm + rec * stride + piece * 16);
+  }
+}
+// pack new particles: member arrays are [ncomp][n], destination slots precomputed
+__global__ void __launch_bounds__(256) k_stage_pack_new(const int* __restrict__ slots, int n,
+                                                        const __grid_constant__ UnitTable t, char* stage) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint4 first[kGroup];
+  load_group(t, 0, i, first);
+  pack_record(t, i, reinterpret_cast<uint4*>(stage + (long)slots[i] * t.rec_bytes), first);
+}
+__device__ __forceinline__ void unpack_record(const UnitTable& t, const char* stage, long slot) {
+  const uint4* rec = reinterpret_cast<const uint4*>(stage + slot * t.rec_bytes);
+  const int nq = (t.nunits + 1) >> 1;
+  for (int q0 = 0; q0 < nq; q0 += kGroup) {
+    uint4 r[kGroup];
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k)
+      if (q0 + k < nq) r[k] = __ldg(rec + q0 + k);     // cached: neighbouring quads share sectors
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {
+      const int u = 2 * (q0 + k);
+      if (u < t.nunits) unit_store(t, u, slot, (unsigned long long)r[k].x | ((unsigned long long)r[k].y << 32));
+      if (u + 1 < t.nunits) unit_store(t, u + 1, slot, (unsigned long long)r[k].z | ((unsigned long long)r[k].w << 32));
+    }
+  }
+}
+// unpack into a Sell-C-sigma layout with C = 32: one warp per 32-slot tile (= one column of a
+// chunk, lane = row); also writes the particle mask (slot (row, col) holds a particle iff
+// col < ppe(row), SCS_buildFns.h:155-199)
+__global__ void __launch_bounds__(256) k_stage_unpack_scs(PsView v, const int* __restrict__ row_ppe,
+                                                          const __grid_constant__ UnitTable t,
+                                                          const char* __restrict__ stage, uint32_t* mask) {
+  const int lane = threadIdx.x & 31;
+  const long tile = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long sb = tile * 32;
+  if (sb >= v.capacity) return;
+  int S = __ldg(v.tile_slice + tile);
+  while (sb >= __ldg(v.offsets + S + 1)) ++S;
+  const int chunk = __ldg(v.slice_to_chunk + S);
+  const int col = (int)((sb - __ldg(v.chunk_start + chunk)) >> 5);
+  const bool valid = col < __ldg(row_ppe + chunk * 32 + lane);
+  const unsigned w = __ballot_sync(0xffffffffu, valid);
+  if (lane == 0) mask[tile] = w;
+  if (valid) unpack_record(t, stage, sb + lane);
+}
+// unpack into a dense (CSR) layout: the first `n` slots hold particles
+__global__ void __launch_bounds__(256) k_stage_unpack_dense(int n, const __grid_constant__ UnitTable t,
+                                                            const char* __restrict__ stage) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) unpack_record(t, stage, s);
+}
+
+pp_status launch_stage_pack(const PsView& v, const int* new_elem, const int* elem2row, const int* chunk_start,
+                            int C, int dense, const int* dense_off, int* row_fill, const int* rank,
+                            const UnitTable& t, char* stage, cudaStream_t s) {
+  const size_t smem = (size_t)(kBlock / 32) * 32 * (t.rec_bytes + 16);
+  PP_CUDA(cudaFuncSetAttribute(k_stage_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_stage_pack<<<pp_div_up(v.capacity, kBlock), kBlock, smem, s>>>(v, new_elem, elem2row, chunk_start, C, dense,
+                                                                   dense_off, row_fill, rank, t, stage);
+  return PP_OK;
+}
+
+// Build the unit table of a structure; false if a member cannot be expressed in 4/8-byte units.
+bool unit_table(const pp_ps* ps, const void* const* src, long src_stride, const std::vector<void*>* dst,
+                long dst_stride, UnitTable& t) {
+  t.nunits = 0;
+  int n4 = 0;
+  // 8-byte scalars first, then pairs of 4-byte scalars: natural alignment inside the record
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < ps->nmembers; ++i) {
+      const int sb = ps->members[i].scalar_bytes;
+      if (sb != 4 && sb != 8) return false;
+      if ((pass == 0) != (sb == 8)) continue;
+      for (int c = 0; c < ps->members[i].ncomp; ++c) {
+        const char* sp = src ? (const char*)src[i] + (size_t)c * src_stride * sb : nullptr;
+        char* dp = dst ? (char*)(*dst)[i] + (size_t)c * dst_stride * sb : nullptr;
+        if (sb == 8) {
+          if (t.nunits >= kMaxUnits) return false;
+          t.kind[t.nunits] = 0; t.sa[t.nunits] = sp; t.sb[t.nunits] = nullptr;
+          t.da[t.nunits] = dp; t.db[t.nunits] = nullptr; ++t.nunits;
+        } else if (n4 % 2 == 0) {
+          if (t.nunits >= kMaxUnits) return false;
+          t.kind[t.nunits] = 1; t.sa[t.nunits] = sp; t.sb[t.nunits] = nullptr;
+          t.da[t.nunits] = dp; t.db[t.nunits] = nullptr; ++t.nunits; ++n4;
+        } else {
+          t.sb[t.nunits - 1] = sp; t.db[t.nunits - 1] = dp; ++n4;
+        }
+      }
+    }
+  t.rec_bytes = ((t.nunits * 8 + 31) / 32) * 32;
+  return t.nunits > 0;
+}
+
+// ---- contention-free ranks for crowded elements.  With thousands of particles per element the
+// per-element atomics of the histogram and of the slot claim serialise; instead the kept
+// particles are sorted by destination element (stable radix sort on log2(ne) bits) and the rank
+// of a particle inside its element, the per-element counts and the slot order all follow from
+// the sorted sequence.  Side effect: the slot order inside a row is deterministic.
+__global__ void k_rank_keys(PsView v, const int* __restrict__ new_elem, int ne, unsigned* keys, int* vals) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.capacity) return;
+  const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  const int e = m ? new_elem[s] : -1;
+  keys[s] = e >= 0 ? (unsigned)e : (unsigned)ne;   // deleted / empty slots sort to the end
+  vals[s] = s;
+}
+__global__ void k_rank_bounds(const unsigned* __restrict__ keys, int n, int ne, int* first, int* count) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned e = keys[j];
+  if (e >= (unsigned)ne) return;
+  if (j == 0 || keys[j - 1] != e) first[e] = j;
+  if (j == n - 1 || keys[j + 1] != e) count[e] = j + 1;   // end for now; turned into a count below
+}
+__global__ void k_rank_counts(const int* __restrict__ first, int* count, int ne) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < ne && count[e] > 0) count[e] -= first[e];
+}
+__global__ void k_rank_scatter(const unsigned* __restrict__ keys, const int* __restrict__ vals, int n, int ne,
+                               const int* __restrict__ first, int* rank) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned e = keys[j];
+  if (e < (unsigned)ne) rank[vals[j]] = j - first[e];
+}
+// row_fill[row(e)] = kept particles of e, so that new particles are appended behind them
+__global__ void k_fill_from_kept(const int* __restrict__ kept, int ne, const int* __restrict__ elem2row, int* row_fill) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < ne) row_fill[elem2row ? elem2row[e] : e] = kept[e];
+}
+
+int g_rank_sort_ppe = 128;   // particles per element from which ranks come from a sort
+int g_staged_rebuild = 1;   // 0: direct scatter (k_move_kept), kept for A/B measurements
+
+pp_status stage_ensure(pp_ps* ps, size_t bytes, cudaStream_t s) {
+  if (ps->stage_bytes >= bytes) return PP_OK;
+  if (ps->stage) PP_CUDA(cudaFreeAsync(ps->stage, s));
+  ps->stage = nullptr; ps->stage_bytes = 0;
+  bytes += bytes / 8;                  // head room: capacity drifts by a few percent per rebuild
+  PP_CUDA(cudaMallocAsync((void**)&ps->stage, bytes, s));
+  ps->stage_bytes = bytes;
+  return PP_OK;
+}
+
 pp_status scan_exclusive(const int* in, int* out, int n, cudaStream_t s) {
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s);
@@ -600,8 +864,39 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
   int* count;
   PP_TRY(pp_dev_alloc(&count, ne + 1, s));
   PP_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ne + 1), s));
-  if (ps->capacity > 0)
+  // crowded elements: ranks and counts from a sort instead of per-element atomics (see k_rank_keys)
+  int* rank = nullptr;
+  int* kept = nullptr;     // kept particles per element (only with ranks and new particles)
+  const bool crowded = g_staged_rebuild && kind != PP_PS_DPS && ps->capacity > 0 &&
+                       (long)ps->nptcls >= (long)g_rank_sort_ppe * ne;
+  if (crowded) {
+    const int cap = ps->capacity;
+    unsigned *k_in, *k_out;
+    int *v_in, *v_out, *first;
+    PP_TRY(pp_dev_alloc(&k_in, cap, s)); PP_TRY(pp_dev_alloc(&k_out, cap, s));
+    PP_TRY(pp_dev_alloc(&v_in, cap, s)); PP_TRY(pp_dev_alloc(&v_out, cap, s));
+    PP_TRY(pp_dev_alloc(&first, ne + 1, s));
+    PP_TRY(pp_dev_alloc(&rank, cap, s));
+    k_rank_keys<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, ne, k_in, v_in);
+    int bits = 1;
+    while ((1u << bits) <= (unsigned)ne && bits < 32) ++bits;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, cap, 0, bits, s);
+    char* tmp;
+    PP_TRY(pp_dev_alloc(&tmp, tb, s));
+    PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, v_out, cap, 0, bits, s));
+    k_rank_bounds<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(k_out, cap, ne, first, count);
+    k_rank_counts<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(first, count, ne);
+    k_rank_scatter<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(k_out, v_out, cap, ne, first, rank);
+    if (n_new > 0) {
+      PP_TRY(pp_dev_alloc(&kept, ne + 1, s));
+      PP_CUDA(cudaMemcpyAsync(kept, count, sizeof(int) * ne, cudaMemcpyDeviceToDevice, s));
+    }
+    pp_dev_free(tmp, s); pp_dev_free(k_in, s); pp_dev_free(k_out, s); pp_dev_free(v_in, s);
+    pp_dev_free(v_out, s); pp_dev_free(first, s);
+  } else if (ps->capacity > 0) {
     k_hist_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count);
+  }
   if (n_new > 0)
     k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, scal + 1);
   int* tot_dev;
@@ -612,7 +907,7 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
   PP_CUDA(cudaMemcpyAsync(&bad, scal + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
   PP_CUDA(cudaStreamSynchronize(s));
   if (bad) {   // SCS_rebuild.h:147-151 (the reference exits the process)
-    pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s);
+    pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s); pp_dev_free(rank, s); pp_dev_free(kept, s);
     pp_set_error("there are new particles being added that are marked as inactive (element id -1)");
     return PP_ERR_INVALID;
   }
@@ -627,19 +922,45 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
     int* fill;
     PP_TRY(pp_dev_alloc(&fill, ne + 1, s));
     PP_CUDA(cudaMemsetAsync(fill, 0, sizeof(int) * (ne + 1), s));
-    MemberTable mt;
-    PP_TRY(member_table(ps, ps->data, nd, mt));
-    if (ps->capacity > 0)
-      k_move_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
-          ps->view(), new_element, nullptr, nullptr, 1, 1, tot_dev, fill, mt, ps->stride, new_stride,
-          nullptr, nullptr);
-    if (n_new > 0) {
-      int* slots;
-      PP_TRY(pp_dev_alloc(&slots, n_new, s));
-      k_assign_dense<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, tot_dev, fill, slots);
-      for (int i = 0; i < ps->nmembers; ++i) mt_new.dst[i] = (char*)nd[i];
-      k_place_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, mt_new, new_stride);
-      pp_dev_free(slots, s);
+    std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
+    UnitTable ut;
+    const bool staged = g_staged_rebuild && active > 0 &&
+                        unit_table(ps, old_src.data(), ps->stride, &nd, new_stride, ut);
+    if (rank && !staged) {   // ranks feed the staged pack only: fall back to atomics
+      pp_dev_free(rank, s); rank = nullptr;
+      if (kept) { pp_dev_free(kept, s); kept = nullptr; }
+    }
+    if (kept) k_fill_from_kept<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(kept, ne, nullptr, fill);
+    if (staged) {
+      PP_TRY(stage_ensure(ps, (size_t)new_cap * ut.rec_bytes, s));
+      if (ps->capacity > 0)
+        PP_TRY(launch_stage_pack(ps->view(), new_element, nullptr, nullptr, 1, 1, tot_dev, fill, rank, ut,
+                                 ps->stage, s));
+      if (n_new > 0) {
+        int* slots;
+        PP_TRY(pp_dev_alloc(&slots, n_new, s));
+        k_assign_dense<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, tot_dev, fill, slots);
+        UnitTable un;
+        unit_table(ps, new_particle_info, n_new, nullptr, 0, un);
+        k_stage_pack_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, un, ps->stage);
+        pp_dev_free(slots, s);
+      }
+      k_stage_unpack_dense<<<pp_div_up(active, kBlock), kBlock, 0, s>>>(active, ut, ps->stage);
+    } else {
+      MemberTable mt;
+      PP_TRY(member_table(ps, ps->data, nd, mt));
+      if (ps->capacity > 0)
+        k_move_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
+            ps->view(), new_element, nullptr, nullptr, 1, 1, tot_dev, fill, mt, ps->stride, new_stride,
+            nullptr, nullptr);
+      if (n_new > 0) {
+        int* slots;
+        PP_TRY(pp_dev_alloc(&slots, n_new, s));
+        k_assign_dense<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, tot_dev, fill, slots);
+        for (int i = 0; i < ps->nmembers; ++i) mt_new.dst[i] = (char*)nd[i];
+        k_place_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, mt_new, new_stride);
+        pp_dev_free(slots, s);
+      }
     }
     for (void* p : ps->data) pp_dev_free((char*)p, s);
     ps->data = nd;
@@ -657,7 +978,7 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
     ps->capacity = new_cap;
     ps->nptcls = active;
     PP_KERNEL_CHECK();
-    pp_dev_free(fill, s); pp_dev_free(count, s); pp_dev_free(scal, s);
+    pp_dev_free(fill, s); pp_dev_free(count, s); pp_dev_free(scal, s); pp_dev_free(rank, s); pp_dev_free(kept, s);
     return PP_OK;
   }
 
@@ -665,7 +986,7 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
   if (active == 0) {   // SCS_rebuild.h:169-181: structure keeps its shape, mask cleared
     PP_CUDA(cudaMemsetAsync(ps->mask_bits, 0, sizeof(uint32_t) * ps->mask_words_alloc, s));
     ps->nptcls = 0;
-    pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s);
+    pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s); pp_dev_free(rank, s); pp_dev_free(kept, s);
     return PP_OK;
   }
   ScsLayout L;
@@ -683,24 +1004,52 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
   int* row_fill;
   PP_TRY(pp_dev_alloc(&row_fill, L.nrows + 1, s));
   PP_CUDA(cudaMemsetAsync(row_fill, 0, sizeof(int) * (L.nrows + 1), s));
-  MemberTable mt;
-  PP_TRY(member_table(ps, ps->data, ps->swap, mt));
-  if (ps->capacity > 0)
-    k_move_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
-        ps->view(), new_element, L.element_to_row, L.chunk_start, L.C, 0, nullptr, row_fill, mt,
-        ps->stride, ps->swap_stride, nullptr, nullptr);
-  if (n_new > 0) {
-    int* slots;
-    PP_TRY(pp_dev_alloc(&slots, n_new, s));
-    k_assign_slots<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new,
-                                                               L.element_to_row, L.chunk_start, L.C,
-                                                               row_fill, slots);
-    for (int i = 0; i < ps->nmembers; ++i) mt_new.dst[i] = (char*)ps->swap[i];
-    k_place_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, mt_new, ps->swap_stride);
-    pp_dev_free(slots, s);
+  std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
+  UnitTable ut;
+  const bool staged = g_staged_rebuild && L.C == 32 &&
+                      unit_table(ps, old_src.data(), ps->stride, &ps->swap, ps->swap_stride, ut);
+  if (rank && !staged) {   // ranks feed the staged pack only: fall back to atomics
+    pp_dev_free(rank, s); rank = nullptr;
+    if (kept) { pp_dev_free(kept, s); kept = nullptr; }
   }
-  // mask of the new structure: the first count(row) columns of every row are occupied
-  {
+  if (kept) k_fill_from_kept<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(kept, ne, L.element_to_row, row_fill);
+  if (staged) {
+    PP_TRY(stage_ensure(ps, (size_t)L.capacity * ut.rec_bytes, s));
+    if (ps->capacity > 0)
+      PP_TRY(launch_stage_pack(ps->view(), new_element, L.element_to_row, L.chunk_start, L.C, 0, nullptr,
+                               row_fill, rank, ut, ps->stage, s));
+    if (n_new > 0) {
+      int* slots;
+      PP_TRY(pp_dev_alloc(&slots, n_new, s));
+      k_assign_slots<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new,
+                                                                 L.element_to_row, L.chunk_start, L.C,
+                                                                 row_fill, slots);
+      UnitTable un;
+      unit_table(ps, new_particle_info, n_new, nullptr, 0, un);
+      k_stage_pack_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, un, ps->stage);
+      pp_dev_free(slots, s);
+    }
+    // unpack in destination order; the same pass writes the mask of the new structure
+    k_stage_unpack_scs<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(layout_view(L, ne), L.row_ppe, ut,
+                                                                        ps->stage, L.mask);
+  } else {
+    MemberTable mt;
+    PP_TRY(member_table(ps, ps->data, ps->swap, mt));
+    if (ps->capacity > 0)
+      k_move_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
+          ps->view(), new_element, L.element_to_row, L.chunk_start, L.C, 0, nullptr, row_fill, mt,
+          ps->stride, ps->swap_stride, nullptr, nullptr);
+    if (n_new > 0) {
+      int* slots;
+      PP_TRY(pp_dev_alloc(&slots, n_new, s));
+      k_assign_slots<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new,
+                                                                 L.element_to_row, L.chunk_start, L.C,
+                                                                 row_fill, slots);
+      for (int i = 0; i < ps->nmembers; ++i) mt_new.dst[i] = (char*)ps->swap[i];
+      k_place_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, mt_new, ps->swap_stride);
+      pp_dev_free(slots, s);
+    }
+    // mask of the new structure: the first count(row) columns of every row are occupied
     PsView v = layout_view(L, ne);
     k_scs_mask<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(v, L.row_ppe, ne, L.mask, L.mask_words);
   }
@@ -715,5 +1064,12 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
   }
   ps->nptcls = active;
   pp_dev_free(row_fill, s); pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s);
+  pp_dev_free(rank, s); pp_dev_free(kept, s);
   return PP_OK;
+}
+
+extern "C" void pp_ps_set_staged_rebuild(int32_t on) { g_staged_rebuild = on ? 1 : 0; }
+
+extern "C" void pp_ps_set_rank_sort_threshold(int32_t particles_per_element) {
+  g_rank_sort_ppe = particles_per_element > 0 ? particles_per_element : 1;
 }

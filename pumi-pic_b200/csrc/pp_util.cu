@@ -16,3 +16,18 @@ void pp_set_error(const char* fmt, ...) {
 extern "C" const char* pp_last_error(void) { return g_err; }
 extern "C" const char* pp_version(void) { return "0.1.0"; }
 extern "C" const char* pp_build_arch(void) { return "sm_100a"; }
+
+// The library allocates its scratch with cudaMallocAsync.  The default pool returns freed memory
+// to the driver at every synchronisation (release threshold 0), which turns the scratch arrays
+// of each rebuild into fresh cudaMalloc calls; keep freed blocks cached instead.
+void pp_runtime_init() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_for = dev;
+}

@@ -220,6 +220,13 @@ def push_direction(mask, tgt, direction, distance):
                              C.c_double(distance))
 
 
+def push_boris(pos, pos_prev, vel, efield, bfield, dt):
+    """in place on [3][n] float64 arrays (src/pumipic_push.hpp:17-74)"""
+    n = pos.shape[1]
+    lib().orc_push_boris(C.c_int(n), _dp(pos), _dp(pos_prev), _dp(vel), _dp(_f64(efield)),
+                         _dp(_f64(bfield)), C.c_double(dt))
+
+
 def update_positions(x, xtgt):
     lib().orc_update_positions(C.c_int(x.shape[1]), _dp(x), _dp(xtgt), C.c_long(x.shape[1]))
 

@@ -1,0 +1,188 @@
+#!/usr/bin/env python
+"""Phase breakdown of the full PIC step on one B200 (CUDA events per phase, median over steps).
+
+  c2 : Kuhn cube N=55 (998 250 tets), 10 M particles, Sell-C-sigma: fused push+search,
+       updatePtclPositions, rebuild  (BASELINE configs[1] as a real time-step loop)
+  c3 : ps_combo160-like rebuild sweep: 160-byte particles, 50 % of the particles re-drawn per step
+  c4 : 2D plate (2 M triangles), 50 M particles: push + search_mesh_2d + rebuild + 2 x gyroScatter
+
+Prints one JSON object per configuration; results are copied into profiles/ by hand.
+"""
+import argparse
+import importlib
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def load_module(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class HostMesh:
+    pass
+
+
+def host_mesh(pp, dim, n):
+    coords, ev = (pp.host_kuhn_cube(n, 1.0) if dim == 3 else pp.host_plate(n, 1.0))
+    e2s, s2v = pp.host_derive_sides(dim, ev)
+    m = HostMesh()
+    m.dim, m.coords, m.elem2verts, m.elem2sides, m.side2verts = dim, coords, ev, e2s, s2v
+    m.nelems, m.nverts = ev.shape[0], coords.shape[0]
+    m.class_id = np.ones(m.nelems, np.int32)
+    return m
+
+
+class Timer:
+    def __init__(self, torch):
+        self.torch = torch
+        self.t = {}
+
+    def run(self, name, fn):
+        a = self.torch.cuda.Event(enable_timing=True)
+        b = self.torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        self.t.setdefault(name, []).append((a, b))
+        return r
+
+    def summary(self, skip=1):
+        self.torch.cuda.synchronize()
+        out = {}
+        for k, evs in self.t.items():
+            ms = [a.elapsed_time(b) for a, b in evs]
+            ms = ms[skip:] if len(ms) > skip else ms
+            out[k] = {"median_ms": float(np.median(ms)), "min_ms": float(np.min(ms)), "n": len(ms)}
+        return out
+
+
+def c2(pp, wl, torch, steps, nptcls, cube_n, kind):
+    P = pp
+    m = host_mesh(pp, 3, cube_n)
+    gm = pp.Mesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
+    members = [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float64, 3)]
+    ps = pp.ParticleStructure(kind, members, wl.even_ppe(m.nelems, nptcls))
+    slot_elem, mask = ps.slot_elem_and_mask()
+    X, D = wl.init3d_internal(m, slot_elem, mask)
+    cap = ps.capacity
+    ps.get(0)[:, :cap] = torch.as_tensor(X).cuda()
+    ps.get(3)[:, :cap] = torch.as_tensor(D).cuda()
+    ps.get(2)[0, :cap] = torch.arange(cap, dtype=torch.int32, device="cuda")
+    d = wl.push_distance(m)
+    T = Timer(torch)
+    counts = []
+    for it in range(steps + 1):
+        x, tg, dr = ps.get(0), ps.get(1), ps.get(3)
+        ids = torch.empty(ps.capacity, dtype=torch.int32, device="cuda")
+        T.run("push+search (fused)", lambda: P.push_direction_search(gm, ps, dr, d, x, tg, ids,
+                                                                     elem_ids_empty=True, from_orig=True,
+                                                                     sync=False))
+        T.run("updatePtclPositions", lambda: P.update_positions(ps, x, tg))
+        T.run("rebuild", lambda: ps.rebuild(ids))
+        counts.append(ps.nptcls)
+    s = T.summary()
+    tot = sum(v["median_ms"] for v in s.values())
+    return {"config": "c2", "particles": nptcls, "tets": m.nelems, "phases": s,
+            "full_step_ms": tot, "full_steps_per_s": nptcls / (tot * 1e-3),
+            "particles_after": counts[-1], "capacity": ps.capacity}
+
+
+def c3(pp, wl, torch, steps, ne, np_, kind):
+    """ps_combo160.cpp:207-232: every step half of the particles get a new random element."""
+    members = [(np.float64, 17), (np.int32, 4), (np.int64, 1)]       # perfTypes.hpp:7-9, 160 B
+    rng = np.random.default_rng(1024 * 1024)
+    ppe = np.bincount(rng.integers(0, ne, np_), minlength=ne).astype(np.int32)
+    ps = pp.ParticleStructure(kind, members, ppe, sigma=ne, V=1024)
+    T = Timer(torch)
+    for it in range(steps + 1):
+        cap = ps.capacity
+        lay_se, _ = None, None
+        lay = ps.layout()
+        se = pp.api._tensor_from_ptr(lay.slot_elem, (cap,), torch.int32, ps)
+        move = torch.rand(cap, device="cuda") < 0.5
+        new = torch.where(move, torch.randint(0, ne, (cap,), device="cuda", dtype=torch.int32), se)
+        T.run("rebuild", lambda: ps.rebuild(new))
+    s = T.summary()
+    return {"config": "c3", "elements": ne, "particles": np_, "record_bytes": 160, "phases": s,
+            "rebuild_particles_per_s": np_ / (s["rebuild"]["median_ms"] * 1e-3),
+            "rebuild_GBps_at_326B": 326.0 * np_ / (s["rebuild"]["median_ms"] * 1e-3) / 1e9}
+
+
+def c4(pp, wl, torch, steps, nptcls, plate_n, kind):
+    P = pp
+    m = host_mesh(pp, 2, plate_n)
+    gm = pp.Mesh(2, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
+    members = [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float64, 3)]
+    ps = pp.ParticleStructure(kind, members, wl.even_ppe(m.nelems, nptcls))
+    cap = ps.capacity
+    lay = ps.layout()
+    se = pp.api._tensor_from_ptr(lay.slot_elem, (cap,), torch.int32, ps).long().clamp(0, m.nelems - 1)
+    # positions: element centroid + small in-element jitter, directions uniform on the circle (device side)
+    ev = torch.as_tensor(m.elem2verts).cuda().long()
+    co = torch.as_tensor(m.coords).cuda()
+    w = torch.rand(cap, 3, device="cuda", dtype=torch.float64) + 0.05
+    w = w / w.sum(dim=1, keepdim=True)
+    pos = (co[ev[se]] * w[:, :, None]).sum(dim=1)                  # [cap, 2]
+    ps.get(0)[0, :cap] = pos[:, 0]; ps.get(0)[1, :cap] = pos[:, 1]; ps.get(0)[2, :cap] = 0
+    ang = torch.rand(cap, device="cuda", dtype=torch.float64) * 2 * np.pi
+    ps.get(3)[0, :cap] = torch.cos(ang); ps.get(3)[1, :cap] = torch.sin(ang); ps.get(3)[2, :cap] = 0
+    del ev, co, w, pos, ang, se
+    d = wl.push_distance(m)
+    rings, ppr, rmax = 3, 8, 0.038 * (1.0 / plate_n) / 0.01       # a few element widths
+    T = Timer(torch)
+    fmap, st = T.run("gyro ring map (setup)", lambda: P.gyro_ring_map(gm, rmax, rings, ppr, 0.0))
+    for it in range(steps + 1):
+        x, tg, dr = ps.get(0), ps.get(1), ps.get(3)
+        ids = torch.full((ps.capacity,), -1, dtype=torch.int32, device="cuda")
+        T.run("push", lambda: P.push_from(ps, x, tg, dr, d))
+        T.run("search_mesh_2d", lambda: P.search_mesh(gm, ps, x, tg, ids, variant=P.capi.PP_SEARCH_2D_LEGACY,
+                                                       looplimit=200, sync=False))
+        T.run("updatePtclPositions", lambda: P.update_positions(ps, x, tg))
+        T.run("rebuild", lambda: ps.rebuild(ids))
+        T.run("gyroScatter x2", lambda: (P.gyro_scatter(gm, ps, fmap, rmax, rings, ppr),
+                                         P.gyro_scatter(gm, ps, fmap, rmax, rings, ppr)))
+    s = T.summary()
+    tot = sum(v["median_ms"] for k, v in s.items() if "setup" not in k)
+    return {"config": "c4", "particles": nptcls, "triangles": m.nelems, "verts": m.nverts, "phases": s,
+            "full_step_ms": tot, "full_steps_per_s": nptcls / (tot * 1e-3), "particles_after": ps.nptcls}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c2,c3,c4")
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--ps", default="scs")
+    ap.add_argument("--c2-particles", type=int, default=10_000_000)
+    ap.add_argument("--c4-particles", type=int, default=50_000_000)
+    a = ap.parse_args()
+    import torch
+    pp = importlib.import_module("pumi-pic_b200")
+    wl = load_module("pp_workloads", os.path.join(ROOT, "pumi-pic_b200", "workloads.py"))
+    kind = {"scs": pp.capi.PP_PS_SCS, "csr": pp.capi.PP_PS_CSR, "dps": pp.capi.PP_PS_DPS}[a.ps]
+    for c in a.configs.split(","):
+        if c == "c2":
+            r = c2(pp, wl, torch, a.steps, a.c2_particles, 55, kind)
+        elif c == "c3":
+            r = c3(pp, wl, torch, a.steps, 5500, 55_000_000 // 2, kind)
+        elif c == "c4":
+            r = c4(pp, wl, torch, a.steps, a.c4_particles, 1000, kind)
+        else:
+            continue
+        r["particle_structure"] = a.ps
+        print(json.dumps(r))
+        sys.stdout.flush()
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

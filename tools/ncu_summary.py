@@ -37,7 +37,7 @@ for i, r in enumerate(rows):
         h = i; break
 if h is not None:
     hdr = rows[h]; ix = {n: i for i, n in enumerate(hdr)}
-    data = [r for r in rows[h + 1:] if len(r) == len(hdr)]
+    data = [r for r in rows[h + 1:] if len(r) == len(hdr) and r[0] != "Address"]
     tot = sum(int(r[ix["# Samples"]]) for r in data)
     print("== top stalled instructions (of %d samples)" % tot)
     order = sorted(range(len(data)), key=lambda i: -int(data[i][ix["# Samples"]]))[:ntop]
