@@ -40,11 +40,11 @@ __global__ void k_count_nonzero(const int* __restrict__ a, int n, int* out) {
 }
 
 // sigmaSort keys: ascending particle count inside windows of `sigma` elements (stable)
-__global__ void k_sort_keys(const int* __restrict__ ppe, int ne, int sigma, uint64_t* keys, int* vals) {
+__global__ void k_sort_keys(const int* __restrict__ ppe, int ne, int sigma, int cbits, uint64_t* keys, int* vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ne) return;
   const uint64_t win = (uint64_t)(i / sigma);
-  keys[i] = (win << 32) | (uint32_t)ppe[i];
+  keys[i] = (win << cbits) | (uint32_t)ppe[i];
   vals[i] = i;
 }
 
@@ -64,18 +64,23 @@ __global__ void k_rows(const int* __restrict__ sorted_elem, const int* __restric
   }
 }
 
-// chunk width = widest row; cw[0]=sum, cw[1]=count of non-empty chunks; inv = sum of 1/width
+// chunk width = widest row; cw[0]=sum, cw[1]=count of non-empty chunks; inv = sum of 1/width.
+// One warp per chunk (lanes stride over the C rows).
 __global__ void k_chunk_widths(const int* __restrict__ row_ppe, int nchunks, int C, int* width,
                                int* cw, double* inv) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= nchunks) return;
   int w = 0;
-  for (int r = 0; r < C; ++r) w = max(w, row_ppe[(long)c * C + r]);
-  width[c] = w;
-  if (w > 0) {
-    atomicAdd(cw, w);
-    atomicAdd(cw + 1, 1);
-    atomicAdd(inv, 1.0 / w);
+  for (int r = lane; r < C; r += 32) w = max(w, row_ppe[(long)c * C + r]);
+  w = __reduce_max_sync(0xffffffffu, w);
+  if (lane == 0) {
+    width[c] = w;
+    if (w > 0) {
+      atomicAdd(cw, w);
+      atomicAdd(cw + 1, 1);
+      atomicAdd(inv, 1.0 / w);
+    }
   }
 }
 
@@ -175,9 +180,8 @@ __global__ void k_hist_kept(PsView v, const int* __restrict__ new_elem, int* cou
     const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
     if (m) e = new_elem[s];
   }
-  // warp-aggregated histogram: lanes with the same destination share one atomic
-  const unsigned act = __match_any_sync(0xffffffffu, e);
-  if (e >= 0 && (threadIdx.x & 31) == (__ffs(act) - 1)) atomicAdd(count + e, __popc(act));
+  // consecutive slots are different rows, so lanes rarely share a destination: plain reductions
+  if (e >= 0) atomicAdd(count + e, 1);
 }
 __global__ void k_hist_new(const int* __restrict__ elems, int n, int* count, int* bad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -608,7 +612,7 @@ void free_layout(ScsLayout& L, cudaStream_t s) {
 }
 
 // Everything SellCSigma::construct derives from particles-per-element (SellCSigma.h:230-283)
-pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, cudaStream_t s,
+pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, long np_bound, cudaStream_t s,
                      ScsLayout& L) {
   int* scal;
   double* inv;
@@ -626,22 +630,29 @@ pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, cudaSt
   const int C = L.C;
   L.nchunks = ne / C + (ne % C != 0);
   L.nrows = L.nchunks * C;
-  // sigmaSort (SCS_sort.h:4-49, CUDA branch)
+  // sigmaSort (SCS_sort.h:4-49, CUDA branch): ascending particle count inside windows of sigma
+  // elements, stable.  Key = (window, count) packed into the fewest bits: counts are bounded by
+  // the particle total, so a full sort of 1 M elements takes 3 radix passes instead of 8.
   int* sorted_elem = nullptr;
   if (cfg.sigma > 1) {
     const int sigma = cfg.sigma < ne ? cfg.sigma : ne;
+    int cbits = 1;
+    while (cbits < 31 && (1ll << cbits) <= (long long)np_bound) ++cbits;
+    const int nwin = (ne + sigma - 1) / sigma;
+    int wbits = 0;
+    while ((1 << wbits) < nwin) ++wbits;
     uint64_t *k_in, *k_out;
     int *v_in;
     PP_TRY(pp_dev_alloc(&k_in, ne, s));
     PP_TRY(pp_dev_alloc(&k_out, ne, s));
     PP_TRY(pp_dev_alloc(&v_in, ne, s));
     PP_TRY(pp_dev_alloc(&sorted_elem, ne, s));
-    k_sort_keys<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(ppe_dev, ne, sigma > 0 ? sigma : 1, k_in, v_in);
+    k_sort_keys<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(ppe_dev, ne, sigma > 0 ? sigma : 1, cbits, k_in, v_in);
     size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, 64, s);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s);
     char* tmp;
     PP_TRY(pp_dev_alloc(&tmp, tb, s));
-    PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, 64, s));
+    PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s));
     pp_dev_free(tmp, s); pp_dev_free(k_in, s); pp_dev_free(k_out, s); pp_dev_free(v_in, s);
   }
   PP_TRY(pp_dev_alloc(&L.row_to_element, L.nrows, s));
@@ -655,7 +666,7 @@ pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, cudaSt
   PP_TRY(pp_dev_alloc(&width, L.nchunks, s));
   PP_TRY(pp_dev_alloc(&spc, L.nchunks + 1, s));
   PP_TRY(pp_dev_alloc(&slice_off, L.nchunks + 1, s));
-  k_chunk_widths<<<pp_div_up(L.nchunks, kBlock), kBlock, 0, s>>>(L.row_ppe, L.nchunks, C, width, scal, inv);
+  k_chunk_widths<<<pp_div_up((long)L.nchunks * 32, kBlock), kBlock, 0, s>>>(L.row_ppe, L.nchunks, C, width, scal, inv);
   if (cfg.shuffle_padding > 0)
     k_pad_widths<<<pp_div_up(L.nchunks, kBlock), kBlock, 0, s>>>(width, L.nchunks, scal, inv,
                                                                  cfg.shuffle_padding, cfg.padding_strat);
@@ -736,7 +747,7 @@ pp_status member_table(const pp_ps* ps, const std::vector<void*>& src, const std
 pp_status pp_scs_build(pp_ps* ps, const int* ppe_dev, const int* pelems_dev,
                        const void* const* pinfo, int memspace, cudaStream_t s) {
   ScsLayout L;
-  PP_TRY(scs_layout(ps->cfg, ps->nelems, ppe_dev, s, L));
+  PP_TRY(scs_layout(ps->cfg, ps->nelems, ppe_dev, 0x7fffffffL, s, L));   // caller-provided counts: no tighter bound
   const int ne = ps->nelems, np = ps->nptcls;
   if (L.capacity > 0 && np > 0) {
     PsView v = layout_view(L, ne);
@@ -990,7 +1001,7 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
     return PP_OK;
   }
   ScsLayout L;
-  PP_TRY(scs_layout(ps->cfg, ne, count, s, L));
+  PP_TRY(scs_layout(ps->cfg, ne, count, active, s, L));
   // (re)allocate the swap buffer: SCS_rebuild.h:223-229 (condition reproduced as written)
   if (ps->cfg.always_realloc || ps->swap.empty() || ps->swap_stride < L.capacity ||
       ps->swap_stride * ps->cfg.minimize_size < L.capacity) {
