@@ -862,7 +862,7 @@ __device__ __forceinline__ void warp_stage_fetch(const typename StageCfg<DIM>::R
   __syncwarp();
 }
 
-template <int DIM, bool PUSH, int WARPS>
+template <int DIM, bool PUSH, bool LEG, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchParams p) {
   using Cfg = StageCfg<DIM>;
   using Rec = typename std::conditional<DIM == 3, Bcc3, Tri>::type;
@@ -969,8 +969,8 @@ __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchPara
     if (m) {
       double* d = ring + r * (6 * 32);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        cp_async8(d + k * 32, colA + k * p.stride + s);
+      for (int k = 0; k < (LEG ? DIM : 3); ++k) {   // search_mesh_2d reads the target only
+        if (!LEG) cp_async8(d + k * 32, colA + k * p.stride + s);
         cp_async8(d + (3 + k) * 32, colB + k * p.stride + s);
       }
     }
@@ -1010,8 +1010,8 @@ __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchPara
         const double* d = ring + r * (6 * 32);
         d3 org = {0, 0, 0}, aux = {0, 0, 0};
         if (mask) {
-          org = {d[0], d[32], d[64]};
-          aux = {d[96], d[128], d[160]};
+          if (!LEG) org = {d[0], d[32], d[64]};
+          aux = {d[96], d[128], (LEG && DIM == 2) ? 0.0 : d[160]};
         }
         issue_col(s + kRing * 32, j + kRing < nlive && ((my_cols >> ((j + kRing) & 31)) & 1u), r);
         r = r + 1 == kRing ? 0 : r + 1;
@@ -1029,7 +1029,10 @@ __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchPara
             tgt = aux;
           }
           const d3 mv = tgt - org;
-          if (!(dot3(mv, mv) < p.unmoved_sq)) {   // finishUnmoved (tpp:525-533), see unmoved_threshold()
+          if (LEG) {                              // search_mesh_2d (adjacency.hpp:1045-1117): no origin test
+            st_active += 1;
+            push = advance(rec, row_adj, E, 1, tgt, next, lost);
+          } else if (!(dot3(mv, mv) < p.unmoved_sq)) {   // finishUnmoved (tpp:525-533), see unmoved_threshold()
             st_active += 1;
             bool inside;                          // check_initial_parents (tpp:73-145)
             if constexpr (DIM == 3) {
@@ -1079,7 +1082,7 @@ double unmoved_threshold(double tol) {
 
 int g_sm_count = 0;
 
-template <int DIM>
+template <int DIM, bool LEG>
 pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
   constexpr int WARPS = 4;
   constexpr size_t smem = (size_t)WARPS * WarpSmem<DIM>::BYTES;
@@ -1091,12 +1094,12 @@ pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
   const int want = pp_div_up(p.chunk_end - p.chunk_begin, WARPS);
   const int persistent = g_sm_count * PP_SCS_MINB;
   const int grid = want < persistent ? want : persistent;
-  if (push) {
-    auto k = k_walk_scs<DIM, true, WARPS>;
+  if (push && !LEG) {
+    auto k = k_walk_scs<DIM, true, false, WARPS>;
     PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, WARPS * 32, smem, s>>>(p);
   } else {
-    auto k = k_walk_scs<DIM, false, WARPS>;
+    auto k = k_walk_scs<DIM, false, LEG, WARPS>;
     PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, WARPS * 32, smem, s>>>(p);
   }
@@ -1187,8 +1190,8 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
           if (mesh->dim == 3) launch<3, M_RAY>(p, push, s); else launch<2, M_RAY>(p, push, s);
         } else if (part || (p.staged >= 2 && a->elem_ids_empty && view.nchunks > 0 && view.C == 32 &&
                             view.chunk_start)) {
-          if (mesh->dim == 3) PP_TRY(launch_walk_scs<3>(p, push, s));
-          else PP_TRY(launch_walk_scs<2>(p, push, s));
+          if (mesh->dim == 3) PP_TRY((launch_walk_scs<3, false>(p, push, s)));
+          else PP_TRY((launch_walk_scs<2, false>(p, push, s)));
         } else if (p.staged) {
           if (mesh->dim == 3) PP_TRY((launch_walk_bcc<3, false>(p, push, s)));
           else PP_TRY((launch_walk_bcc<2, false>(p, push, s)));
@@ -1199,7 +1202,11 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
       case PP_SEARCH_2D_LEGACY:
         PP_REQUIRE(mesh->dim == 2, "search_mesh_2d needs a 2D mesh");
         PP_REQUIRE(!push, "fused push is only available for the new search API");
-        if (p.staged) PP_TRY((launch_walk_bcc<2, true>(p, false, s)));
+        // elem_ids_empty: the caller passes a fresh array of -1 (test/pseudoXGCm.cpp:147-153), so every
+        // particle starts in its row element and the chunk walk applies
+        if (p.staged >= 2 && a->elem_ids_empty && view.nchunks > 0 && view.C == 32 && view.chunk_start)
+          PP_TRY((launch_walk_scs<2, true>(p, false, s)));
+        else if (p.staged) PP_TRY((launch_walk_bcc<2, true>(p, false, s)));
         else launch<2, M_LEG2D>(p, false, s);
         break;
       case PP_SEARCH_3D_LEGACY: {

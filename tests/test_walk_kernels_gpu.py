@@ -196,3 +196,30 @@ def test_host_buffer_pipeline_matches_oracle(kind, nparts):
         assert np.array_equal(ht.numpy()[:, m], T[:, m])
         assert (r.found, r.loops, r.not_in_elem) == (int(found), st.loops, st.not_in_elem)
         assert r.active == int(m.sum())
+
+
+@pytest.mark.parametrize("variant", [2, 1, 0])
+@pytest.mark.parametrize("kind", ["scs", "csr"])
+@pytest.mark.parametrize("meshname,nptcls", [("xgc24k", 120000), ("plate20", 7000)])
+def test_search_mesh_2d_fresh_ids_all_kernels(meshname, nptcls, kind, variant):
+    """adjacency.hpp:1013 search_mesh_2d as test/pseudoXGCm.cpp:147-153 calls it: elem_ids is a fresh
+    array of -1 (elem_ids_empty promises that), so particles start in their row element."""
+    mesh = _mesh(meshname)
+    P = pp()
+    P.lib().pp_search_set_staged(variant)
+    om = orc.OracleMesh(mesh)
+    gm = make_gpu_mesh(mesh)
+    ps = make_ps(_kind(kind), _uneven_ppe(mesh.nelems, nptcls, seed=3))
+    slot_elem, mask = ps.slot_elem_and_mask()
+    X, D = pi.init2d_internal(mesh, slot_elem, mask)
+    t = torch()
+    for mult, limit in ((1.0, 200), (7.0, 200), (7.0, 2)):
+        T = X.copy()
+        orc.push_direction(mask, T, D, mult * pi.push_distance(mesh))
+        start = np.full(ps.capacity, -1, np.int32)
+        ids = dev(start)
+        r = P.search_mesh(gm, ps, dev(X), dev(T), ids, elem_ids_empty=True,
+                          variant=P.capi.PP_SEARCH_2D_LEGACY, looplimit=limit)
+        found, ids_o, st = om.search_mesh_2d(slot_elem, mask, T, start, looplimit=limit)
+        assert np.array_equal(ids.cpu().numpy(), ids_o)
+        assert (r.found, r.loops, r.not_found) == (int(found), st.loops, st.not_found)

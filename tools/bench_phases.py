@@ -146,7 +146,7 @@ def c4(pp, wl, torch, steps, nptcls, plate_n, kind):
         ids = torch.full((ps.capacity,), -1, dtype=torch.int32, device="cuda")
         T.run("push", lambda: P.push_from(ps, x, tg, dr, d))
         T.run("search_mesh_2d", lambda: P.search_mesh(gm, ps, x, tg, ids, variant=P.capi.PP_SEARCH_2D_LEGACY,
-                                                       looplimit=200, sync=False))
+                                                       elem_ids_empty=True, looplimit=200, sync=False))
         T.run("updatePtclPositions", lambda: P.update_positions(ps, x, tg))
         T.run("rebuild", lambda: ps.rebuild(ids))
         T.run("gyroScatter x2", lambda: (P.gyro_scatter(gm, ps, fmap, rmax, rings, ppr),
