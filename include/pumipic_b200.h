@@ -226,6 +226,9 @@ pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
 /* Record move of a full re-layout: 1 (default) = through an array-of-records stage (every DRAM
  * access a full sector), 0 = direct scatter.  Same results as sets of particles; for A/B timing. */
 void pp_ps_set_staged_rebuild(int32_t on);
+/* SellCSigma::setShuffling (scs/SellCSigma.h:92): try the in-place reshuffle (SCS_rebuild.h:4-120)
+ * before a full re-layout.  Default on. */
+void pp_ps_set_shuffling(int32_t on);
 /* Average particles per element from which a rebuild derives counts and in-row ranks from a sort
  * of the particles by destination element instead of per-element atomics (default 128). */
 void pp_ps_set_rank_sort_threshold(int32_t particles_per_element);

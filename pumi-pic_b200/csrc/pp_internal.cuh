@@ -194,6 +194,8 @@ struct pp_ps {
   int64_t* sorted_gid;      // [nelems] gids ascending (built lazily for migrate)
   int* sorted_lid;          // [nelems] local id of sorted_gid[i]
   char* stage;              // record stage of the rebuild (grow-only scratch)
+  int shuffle_skip = 0;     // rebuilds to wait before the next reshuffle attempt
+  int shuffle_streak = 0;   // consecutive failed reshuffle attempts
   size_t stage_bytes;
   PsView view() const;
 };

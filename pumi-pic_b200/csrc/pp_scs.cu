@@ -173,15 +173,20 @@ __global__ void k_assign_slots(const int* __restrict__ elems, int n, const int* 
 }
 
 // ---- rebuild kernels
-__global__ void k_hist_kept(PsView v, const int* __restrict__ new_elem, int* count) {
+// countNewParticles (SCS_rebuild.h:133-138).  The value the atomic returns is the particle's rank
+// inside its destination element, which is all the slot claim of the record move needs: with
+// `rank` the move runs without a second round of atomics.
+__global__ void k_hist_kept(PsView v, const int* __restrict__ new_elem, int* count, int* rank) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   int e = -1;
   if (s < v.capacity) {
     const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
     if (m) e = new_elem[s];
   }
-  // consecutive slots are different rows, so lanes rarely share a destination: plain reductions
-  if (e >= 0) atomicAdd(count + e, 1);
+  if (e >= 0) {
+    if (rank) rank[s] = atomicAdd(count + e, 1);
+    else atomicAdd(count + e, 1);
+  }
 }
 __global__ void k_hist_new(const int* __restrict__ elems, int n, int* count, int* bad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -581,6 +586,105 @@ __global__ void k_fill_from_kept(const int* __restrict__ kept, int ne, const int
   if (e < ne) row_fill[elem2row ? elem2row[e] : e] = kept[e];
 }
 
+// ------------------------------------------------------------------------------------------
+// reshuffle (SCS_rebuild.h:4-120): when every row has at least as many holes as particles moving
+// into it, only the movers travel (each into a hole of its destination row) and nothing else of
+// the structure changes.  Same rules as the reference: a hole is a slot that holds no particle
+// after the deletions (a mover's own slot is NOT a hole for this round).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int slot_row(const PsView& v, int slot) {
+  int S = __ldg(v.tile_slice + (slot >> 5));
+  while (slot >= __ldg(v.offsets + S + 1)) ++S;
+  const int r = (slot - __ldg(v.offsets + S)) % v.C;
+  return __ldg(v.slice_to_chunk + S) * v.C + r;
+}
+// incoming particles and holes per row; new_mask = particle after deletions
+__global__ void k_shuffle_count(PsView v, const int* __restrict__ new_elem, const int* __restrict__ elem2row,
+                                int* incoming, int* holes, int* outgoing, uint32_t* new_mask) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  bool is_particle = false;
+  if (s < v.capacity) {
+    const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+    const int row = slot_row(v, s);
+    const int e = m ? new_elem[s] : -1;
+    is_particle = m && e != -1;
+    if (is_particle) {
+      const int nrow = elem2row[e];
+      if (nrow != row) { atomicAdd(incoming + nrow, 1); atomicAdd(outgoing + row, 1); }
+    } else {
+      atomicAdd(holes + row, 1);
+      if (m) atomicAdd(outgoing + row, 1);      // deleted
+    }
+  }
+  const unsigned w = __ballot_sync(0xffffffffu, is_particle);
+  if ((threadIdx.x & 31) == 0 && s < v.capacity) new_mask[s >> 5] = w;
+}
+__global__ void k_shuffle_count_new(const int* __restrict__ elems, int n, const int* __restrict__ elem2row,
+                                    int* incoming) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(incoming + elem2row[elems[i]], 1);
+}
+__global__ void k_shuffle_row_counts(int* row_ppe, const int* __restrict__ incoming,
+                                     const int* __restrict__ outgoing, int nrows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrows) row_ppe[r] += incoming[r] - outgoing[r];
+}
+__global__ void k_shuffle_fits(const int* __restrict__ incoming, const int* __restrict__ holes, int nrows,
+                               int* fail) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrows && incoming[r] > holes[r]) *fail = 1;
+}
+// movers, grouped by destination row: src >= 0 is a slot of the structure, src < 0 is new particle -src-1
+__global__ void k_shuffle_gather(PsView v, const int* __restrict__ new_elem, const int* __restrict__ elem2row,
+                                 int* cursor, int* src) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.capacity) return;
+  const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  if (!m) return;
+  const int e = new_elem[s];
+  if (e == -1) return;
+  const int nrow = elem2row[e];
+  if (nrow != slot_row(v, s)) src[atomicAdd(cursor + nrow, 1)] = s;
+}
+__global__ void k_shuffle_gather_new(const int* __restrict__ elems, int n, const int* __restrict__ elem2row,
+                                     int* cursor, int* src) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) src[atomicAdd(cursor + elem2row[elems[i]], 1)] = -i - 1;
+}
+// every hole of row r takes the next mover bound for r, while there is one
+__global__ void k_shuffle_holes(PsView v, const uint32_t* __restrict__ new_mask, int* next,
+                                const int* __restrict__ end, int* hole) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.capacity) return;
+  if ((new_mask[s >> 5] >> (s & 31)) & 1u) return;
+  const int row = slot_row(v, s);
+  if (next[row] >= end[row]) return;              // cheap pre-test, the claim below decides
+  const int idx = atomicAdd(next + row, 1);
+  if (idx < end[row]) hole[idx] = s;
+}
+__global__ void k_shuffle_move(const int* __restrict__ src, const int* __restrict__ hole, int nmove,
+                               MemberTable mt, MemberTable mt_new, long stride, int n_new, uint32_t* mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nmove) return;
+  const int from = src[i], to = hole[i];
+  const bool fresh = from < 0;
+  const long fi = fresh ? -from - 1 : from;
+  const MemberTable& t = fresh ? mt_new : mt;
+  const long fstride = fresh ? n_new : stride;
+  for (int k = 0; k < t.n; ++k) {
+    const int sb = t.bytes[k];
+    for (int c = 0; c < t.ncomp[k]; ++c) {
+      const char* a = t.src[k] + ((long)c * fstride + fi) * sb;
+      char* b = mt.dst[k] + ((long)c * stride + to) * sb;
+      if (sb == 8) *(double*)b = *(const double*)a;
+      else if (sb == 4) *(int*)b = *(const int*)a;
+      else for (int q = 0; q < sb; ++q) b[q] = a[q];
+    }
+  }
+  if (!fresh) atomicAnd(mask + (from >> 5), ~(1u << (from & 31)));
+  atomicOr(mask + (to >> 5), 1u << (to & 31));
+}
+
 int g_rank_sort_ppe = 128;   // particles per element from which ranks come from a sort
 int g_staged_rebuild = 1;   // 0: direct scatter (k_move_kept), kept for A/B measurements
 
@@ -740,6 +844,72 @@ pp_status member_table(const pp_ps* ps, const std::vector<void*>& src, const std
   return PP_OK;
 }
 }  // namespace
+
+int g_try_shuffling = 1;
+
+// SCS_rebuild.h:4-120.  done = true iff the particles fitted and the structure was updated in place.
+pp_status try_reshuffle(pp_ps* ps, const int* new_element, int n_new, const int* new_particle_elements,
+                        const void* const* new_particle_info, const MemberTable& mt_new_in, cudaStream_t s,
+                        bool& done) {
+  done = false;
+  const int cap = ps->capacity, nrows = ps->nrows;
+  const PsView v = ps->view();
+  int *incoming, *holes, *outgoing, *fail;
+  uint32_t* new_mask;
+  const long nwords = (cap + 31) / 32;
+  PP_TRY(pp_dev_alloc(&incoming, nrows + 1, s));
+  PP_TRY(pp_dev_alloc(&holes, nrows + 1, s));
+  PP_TRY(pp_dev_alloc(&outgoing, nrows + 1, s));
+  PP_TRY(pp_dev_alloc(&fail, 2, s));
+  PP_TRY(pp_dev_alloc(&new_mask, nwords + 1, s));
+  PP_CUDA(cudaMemsetAsync(incoming, 0, sizeof(int) * (nrows + 1), s));
+  PP_CUDA(cudaMemsetAsync(holes, 0, sizeof(int) * (nrows + 1), s));
+  PP_CUDA(cudaMemsetAsync(outgoing, 0, sizeof(int) * (nrows + 1), s));
+  PP_CUDA(cudaMemsetAsync(fail, 0, 2 * sizeof(int), s));
+  k_shuffle_count<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(v, new_element, ps->element_to_row, incoming, holes,
+                                                           outgoing, new_mask);
+  if (n_new > 0)
+    k_shuffle_count_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new,
+                                                                    ps->element_to_row, incoming);
+  k_shuffle_fits<<<pp_div_up(nrows, kBlock), kBlock, 0, s>>>(incoming, holes, nrows, fail);
+  int* begin;
+  PP_TRY(pp_dev_alloc(&begin, nrows + 2, s));
+  PP_TRY(scan_exclusive(incoming, begin, nrows + 1, s));    // begin[nrows] = number of movers
+  int h_fail = 0, nmove = 0;
+  PP_CUDA(cudaMemcpyAsync(&h_fail, fail, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaMemcpyAsync(&nmove, begin + nrows, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  if (!h_fail) {
+    // the deletions take effect; movers keep their bit until they have been copied
+    PP_CUDA(cudaMemcpyAsync(ps->mask_bits, new_mask, sizeof(uint32_t) * nwords, cudaMemcpyDeviceToDevice, s));
+    if (nmove > 0) {
+      int *cursor, *src, *hole;
+      PP_TRY(pp_dev_alloc(&cursor, nrows + 1, s));
+      PP_TRY(pp_dev_alloc(&src, nmove, s));
+      PP_TRY(pp_dev_alloc(&hole, nmove, s));
+      PP_CUDA(cudaMemcpyAsync(cursor, begin, sizeof(int) * (nrows + 1), cudaMemcpyDeviceToDevice, s));
+      k_shuffle_gather<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(v, new_element, ps->element_to_row, cursor, src);
+      if (n_new > 0)
+        k_shuffle_gather_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new,
+                                                                         ps->element_to_row, cursor, src);
+      // cursor[r] is now the end of row r's movers; begin[r] counts up as holes claim them
+      k_shuffle_holes<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(v, new_mask, begin, cursor, hole);
+      MemberTable mt, mtn = mt_new_in;
+      PP_TRY(member_table(ps, ps->data, ps->data, mt));
+      (void)new_particle_info;
+      k_shuffle_move<<<pp_div_up(nmove, kBlock), kBlock, 0, s>>>(src, hole, nmove, mt, mtn, ps->stride, n_new,
+                                                                 ps->mask_bits);
+      pp_dev_free(cursor, s); pp_dev_free(src, s); pp_dev_free(hole, s);
+    }
+    k_shuffle_row_counts<<<pp_div_up(nrows, kBlock), kBlock, 0, s>>>(ps->row_ppe, incoming, outgoing, nrows);
+    PP_KERNEL_CHECK();
+    done = true;
+  }
+  pp_dev_free(outgoing, s);
+  pp_dev_free(incoming, s); pp_dev_free(holes, s); pp_dev_free(fail, s); pp_dev_free(new_mask, s);
+  pp_dev_free(begin, s);
+  return PP_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // SellCSigma::construct (SellCSigma.h:230-283)
@@ -906,7 +1076,12 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
     pp_dev_free(tmp, s); pp_dev_free(k_in, s); pp_dev_free(k_out, s); pp_dev_free(v_in, s);
     pp_dev_free(v_out, s); pp_dev_free(first, s);
   } else if (ps->capacity > 0) {
-    k_hist_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count);
+    if (g_staged_rebuild) {
+      PP_TRY(pp_dev_alloc(&rank, ps->capacity, s));
+      if (n_new > 0) PP_TRY(pp_dev_alloc(&kept, ne + 1, s));
+    }
+    k_hist_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count, rank);
+    if (kept) PP_CUDA(cudaMemcpyAsync(kept, count, sizeof(int) * ne, cudaMemcpyDeviceToDevice, s));
   }
   if (n_new > 0)
     k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, scal + 1);
@@ -1000,6 +1175,25 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
     pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s); pp_dev_free(rank, s); pp_dev_free(kept, s);
     return PP_OK;
   }
+  // tryShuffling (SCS_rebuild.h:183-189).  An attempt costs a pass over the slots; after a failure
+  // the next attempts are spaced out (1, 2, 4, ... 64 rebuilds), after a success every rebuild tries.
+  if (g_try_shuffling && ps->capacity > 0 && ps->tile_slice) {
+    if (ps->shuffle_skip > 0) {
+      --ps->shuffle_skip;
+    } else {
+      bool done = false;
+      PP_TRY(try_reshuffle(ps, new_element, n_new, new_particle_elements, new_particle_info, mt_new, s, done));
+      if (done) {
+        ps->shuffle_streak = 0;
+        ps->nptcls = active;
+        pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s); pp_dev_free(rank, s);
+        pp_dev_free(kept, s);
+        return PP_OK;
+      }
+      ps->shuffle_streak = ps->shuffle_streak < 6 ? ps->shuffle_streak + 1 : 6;
+      ps->shuffle_skip = (1 << ps->shuffle_streak) - 1;
+    }
+  }
   ScsLayout L;
   PP_TRY(scs_layout(ps->cfg, ne, count, active, s, L));
   // (re)allocate the swap buffer: SCS_rebuild.h:223-229 (condition reproduced as written)
@@ -1084,3 +1278,5 @@ extern "C" void pp_ps_set_staged_rebuild(int32_t on) { g_staged_rebuild = on ? 1
 extern "C" void pp_ps_set_rank_sort_threshold(int32_t particles_per_element) {
   g_rank_sort_ppe = particles_per_element > 0 ? particles_per_element : 1;
 }
+
+extern "C" void pp_ps_set_shuffling(int32_t on) { g_try_shuffling = on ? 1 : 0; }

@@ -151,6 +151,7 @@ def _default_rebuild_modes():
     yield
     pp().lib().pp_ps_set_staged_rebuild(1)
     pp().lib().pp_ps_set_rank_sort_threshold(128)
+    pp().lib().pp_ps_set_shuffling(1)
 
 
 # move = how records travel in a re-layout: staged records + atomics (default for sparse rows),
@@ -289,3 +290,66 @@ def test_search_runs_on_every_structure_kind(kindname):
     m2 = m2.astype(bool)
     pid = ps.get(2).cpu().numpy()[0, :ps.capacity][m2]
     assert np.array_equal(se2[m2], ids_o[pid]) and m2.sum() == (ids_o[m] >= 0).sum()
+
+
+@pytest.mark.parametrize("kindname", ["scs_c32", "scs_s7", "scs_padprop", "cabm"])
+def test_reshuffle_keeps_the_layout_when_movers_fit(kindname, _default_rebuild_modes):
+    """SCS_rebuild.h:4-120: few movers, a few deletions and a few new particles fit into the row
+    padding -> capacity, slot->element map and every non-moving particle's slot stay as they are;
+    when the movers do not fit the full re-layout runs and gives the same particle sets."""
+    t = torch()
+    ne, np_ = 900, 60000
+    ps, ppe, _, _ = _make(kindname, ne, np_)
+    rng = np.random.default_rng(4)
+    for rnd in range(3):
+        _set_ids(ps)
+        slot_elem, m = _state(ps)
+        cap = ps.capacity
+        slots = np.arange(cap)
+        stay = slot_elem.copy()
+        movers = m & (rng.random(cap) < 0.01)
+        dels = m & ~movers & (rng.random(cap) < 0.01)
+        new_element = np.where(m, stay, -1).astype(np.int32)
+        # movers go to elements that certainly have room: the ones losing a particle this round
+        targets = slot_elem[dels]
+        if len(targets) == 0:
+            targets = slot_elem[m][:1]
+        new_element[movers] = rng.choice(targets, movers.sum())
+        new_element[dels] = -1
+        # each deletion frees one slot, but several movers may pick the same target: cap them
+        room = np.bincount(slot_elem[dels], minlength=ne)
+        take = np.zeros(ne, np.int64)
+        for sidx in np.flatnonzero(movers):
+            e = new_element[sidx]
+            if take[e] < room[e] and e != slot_elem[sidx]:
+                take[e] += 1
+            else:
+                new_element[sidx] = slot_elem[sidx]
+        n_move = int((m & (new_element != slot_elem) & (new_element >= 0)).sum())
+        lay0 = ps.layout()
+        sig0 = (lay0.capacity, lay0.nchunks, lay0.nslices)
+        ps.rebuild(dev(new_element))
+        lay1 = ps.layout()
+        assert (lay1.capacity, lay1.nchunks, lay1.nslices) == sig0        # in place
+        _check(ps, new_element, cap, removed=dels, np_expected=int(m.sum() - dels.sum()))
+        se2, m2 = _state(ps)
+        assert np.array_equal(se2, slot_elem)                              # rows did not move
+        ids = ps.get(0).cpu().numpy()[0, :cap]
+        stayed = m & (new_element == slot_elem)
+        assert np.array_equal(ids[stayed], slots[stayed]) and m2[stayed].all()   # stayers kept their slots
+        assert n_move > 0
+    # now far too many movers for the padding: falls back to the re-layout
+    _set_ids(ps)
+    slot_elem, m = _state(ps)
+    cap = ps.capacity
+    new_element = np.where(m, (slot_elem * 7 + np.arange(cap)) % ne, -1).astype(np.int32)
+    ps.rebuild(dev(new_element))
+    _check(ps, new_element, cap, np_expected=int(m.sum()))
+    # shuffling switched off: same sets
+    pp().lib().pp_ps_set_shuffling(0)
+    _set_ids(ps)
+    slot_elem, m = _state(ps)
+    cap = ps.capacity
+    new_element = np.where(m, slot_elem, -1).astype(np.int32)
+    ps.rebuild(dev(new_element))
+    _check(ps, new_element, cap, np_expected=int(m.sum()))
