@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--ps", default="scs", choices=["dps", "scs", "csr"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch the timed steps eagerly (one event per step) instead of one CUDA graph")
     ap.add_argument("--e2e-parts", type=int, default=8, help="pieces of the pipelined host-buffer step")
     ap.add_argument("--walk-kernel", type=int, default=2, choices=[0, 1, 2],
                     help="0 thread-per-slot, 1 block-staged, 2 Sell-C-sigma chunk walk (default)")
@@ -196,7 +198,9 @@ def main():
               "particles_per_gpu": a.particles, "tets_per_gpu": 6 * a.cube_n ** 3,
               "push": "xtgt = x + d*dir, d = L/(3*nelems^(1/3)), sign alternates per step",
               "l2": "inputs (>=0.8 GB of particle columns per step) are larger than the 126 MB L2",
-              "particle_structure": a.ps, "loop": a.loop, "parallelism": "independent shard per GPU (no exchange in push+search)"}
+              "particle_structure": a.ps, "loop": a.loop,
+              "launch": "eager, one CUDA event per step" if a.no_graph else "the K timed steps replayed as one CUDA graph",
+              "parallelism": "independent shard per GPU (no exchange in push+search)"}
 
     if a.impl == "reference":
         # CPU arm: rank 0 only; the reference's own CPU algorithm via the oracle port (the real
@@ -264,24 +268,51 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
-    active_steps = 0
+    # The K timed steps are captured once in a CUDA graph (K fused-kernel launches with their
+    # alternating push sign) and replayed by ONE launch: the step is 0.29 ms of GPU work, and with
+    # N ranks sharing the host the Python/ctypes launch path otherwise shows up as gaps between
+    # kernels.  --no-graph times the same K launches eagerly with an event after every step.
     stream = torch.cuda.current_stream()
+    graph = None
+    if not a.no_graph:
+        cs = torch.cuda.Stream()
+        cs.wait_stream(stream)
+        graph = torch.cuda.CUDAGraph()
+        it0, A0, B0 = it, A, B
+        with torch.cuda.graph(graph, stream=cs):
+            for k in range(a.steps):
+                step(it, A, B); A, B = B, A; it += 1
+        graph.replay()            # untimed: uploads the graph, extra warm-up of the same K steps
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    active_steps = 0
     if sampler:
         sampler.begin()
-    ev[0].record(stream)
-    for k in range(a.steps):
-        step(it, A, B); A, B = B, A; it += 1
-        ev[k + 1].record(stream)
-    torch.cuda.synchronize()
+    if graph is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        graph.replay()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        total_ms = e0.elapsed_time(e1)
+        kernel_ms = [total_ms / a.steps] * a.steps
+    else:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+        ev[0].record(stream)
+        for k in range(a.steps):
+            step(it, A, B); A, B = B, A; it += 1
+            ev[k + 1].record(stream)
+        torch.cuda.synchronize()
+        total_ms = ev[0].elapsed_time(ev[-1])
+        kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
     if sampler:
         sampler.end()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
     # stationary population: count live particles once (the oscillation keeps it constant)
     st = P.capi.SearchStats()
     P.capi.check(P.lib().pp_search_last_stats(gm.h, st, None))

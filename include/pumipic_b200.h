@@ -268,7 +268,9 @@ pp_status pp_set_unsafe_procs(pp_mesh* mesh, pp_ps* ps, const int32_t* elems, in
 typedef enum pp_search_variant {
   PP_SEARCH_NEW = 0,       /* adjacency.tpp:642 search_mesh (BCC or ray intersection, 2D/3D) */
   PP_SEARCH_2D_LEGACY = 1, /* adjacency.hpp:1013 search_mesh_2d */
-  PP_SEARCH_3D_LEGACY = 2  /* adjacency.hpp:559 search_mesh (line-triangle + dual graph) */
+  PP_SEARCH_3D_LEGACY = 2, /* adjacency.hpp:559 search_mesh (line-triangle + dual graph) */
+  PP_SEARCH_3D = 3         /* adjacency.hpp:316 search_mesh_3d (barycentric_coords_tet, tol 1e-20,
+                            * checkCurrentElm / findIntersection / processUndetected) */
 } pp_search_variant;
 
 typedef struct pp_search_args {
@@ -280,8 +282,8 @@ typedef struct pp_search_args {
   int32_t elem_ids_empty;        /* !=0: behave as if elem_ids.size()==0 (seed from the row element);
                                   * PP_SEARCH_2D_LEGACY: !=0 promises elem_ids is a fresh array of -1 */
   int32_t require_intersection;  /* PP_SEARCH_NEW only */
-  int32_t* inter_faces;          /* [capacity] or NULL (required when require_intersection / legacy 3D xface) */
-  double* inter_points;          /* [dim*capacity] AoS or NULL (legacy 3D: xpoints [3*capacity]) */
+  int32_t* inter_faces;          /* [capacity] or NULL (required when require_intersection / legacy 3D and search_mesh_3d xface) */
+  double* inter_points;          /* [dim*capacity] AoS or NULL (legacy 3D, search_mesh_3d: xpoints [3*capacity]) */
   int32_t looplimit;             /* 0 = unlimited */
 } pp_search_args;
 
@@ -290,7 +292,7 @@ typedef struct pp_search_stats {
   int32_t loops;        /* walk iterations the reference would have executed */
   int32_t not_in_elem;  /* deleted by check_initial_parents (adjacency.tpp:73-145) */
   int32_t not_found;    /* deleted by the loop limit */
-  int32_t aborted;      /* legacy 3D: particles whose origin is outside their element (reference aborts) */
+  int32_t aborted;      /* legacy 3D, search_mesh_3d: particles whose origin is outside their element (reference aborts) */
   int32_t active;       /* particles that entered the walk */
   int64_t hops;         /* total element hops */
 } pp_search_stats;

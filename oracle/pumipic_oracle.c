@@ -858,6 +858,176 @@ int orc_search_mesh_legacy3d(const orc_mesh* m, int cap, const int* slot_elem,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * adjacency.hpp:316-555 search_mesh_3d (three kernels per iteration: checkCurrentElm,
+ * findIntersection, processUndetected), with barycentric_coords_tet :136-158 and
+ * isPointWithinElemTet :300-313, tol 1e-20.
+ * ---------------------------------------------------------------------------------------- */
+/* adjacency.hpp:136-158: vals = 1/6 (p-a).cross(c-a, b-a), vol = tet_volume_from_basis; when
+ * vol < tol the function returns with bcc zeroed (the caller ignores the return value). */
+int orc_barycentric_coords_tet(const double M[12], const double p[3], double bcc[4], double tol) {
+  double vals[4];
+  for (int f = 0; f < 4; ++f) {
+    const double* a = M + 3 * TET_FACE[f][0];
+    const double* b = M + 3 * TET_FACE[f][1];
+    const double* c = M + 3 * TET_FACE[f][2];
+    double vab[3], vac[3], vap[3], cr[3];
+    v3_sub(b, a, vab);
+    v3_sub(c, a, vac);
+    v3_sub(p, a, vap);
+    v3_cross(vac, vab, cr);
+    vals[f] = 1.0 / 6.0 * v3_dot(vap, cr);
+    bcc[f] = 0;
+  }
+  double b0[3], b1[3], b2[3], c[3];
+  v3_sub(M + 3, M, b0);
+  v3_sub(M + 6, M, b1);
+  v3_sub(M + 9, M, b2);
+  v3_cross(b0, b1, c);
+  const double vol = v3_dot(c, b2) / 6.0;
+  if (vol < tol) return 0;
+  const double inv = 1.0 / vol;
+  for (int i = 0; i < 4; ++i) bcc[i] = inv * vals[i];
+  return 1;
+}
+
+static int point_within_tet(const orc_mesh* m, int e, const double p[3], double tol) {
+  int tv[4]; double M[12], bcc[4];
+  gather_tet(m, e, tv, M);
+  orc_barycentric_coords_tet(M, p, bcc, tol);
+  return orc_all_positive(bcc, 4, tol);
+}
+
+int orc_search_mesh_3d(const orc_mesh* m, int cap, const int* slot_elem,
+                       const unsigned char* mask, const double* x_orig, const double* x_tgt,
+                       long stride, int* elem_ids, int elem_ids_empty, double* xpoints_d,
+                       int* xface_d, int looplimit, orc_search_stats* stats) {
+  const double tol = 1.0e-20;
+  int* done = (int*)malloc(sizeof(int) * ((size_t)cap + 1));
+  int* next = (int*)malloc(sizeof(int) * ((size_t)cap + 1));
+  const int ndual = m->dual_off[m->nelems];
+  int aborted = 0;
+#pragma omp parallel for
+  for (int s = 0; s < cap; ++s) {            /* :356-366 fill */
+    next[s] = -1;
+    if (mask[s] > 0) {
+      if (elem_ids_empty) elem_ids[s] = slot_elem[s];
+      done[s] = (elem_ids[s] == -1) * 2;
+    } else {
+      elem_ids[s] = -1; done[s] = 2;
+    }
+  }
+#pragma omp parallel for reduction(+ : aborted)
+  for (int s = 0; s < cap; ++s) {            /* :368-379 checkParent: tests the ROW element */
+    if (!(mask[s] > 0 && done[s] != 2)) continue;
+    double orig[3];
+    load3(x_orig, stride, s, orig);
+    if (!point_within_tet(m, slot_elem[s], orig, tol)) aborted += 1;   /* OMEGA_H_CHECK(false) */
+  }
+  int found = 0, loops = 0;
+  while (!found) {
+#pragma omp parallel for
+    for (int s = 0; s < cap; ++s) {          /* :395-410 checkCurrentElm */
+      if (!(mask[s] > 0 && !done[s])) continue;
+      double dest[3];
+      load3(x_tgt, stride, s, dest);
+      done[s] = point_within_tet(m, elem_ids[s], dest, tol) ? 2 : 0;
+      next[s] = elem_ids[s];
+    }
+#pragma omp parallel for
+    for (int s = 0; s < cap; ++s) {          /* :412-469 findIntersection */
+      if (!(mask[s] > 0 && done[s] < 2)) continue;
+      const int E = elem_ids[s];
+      int tv[4]; double M[12], dest[3], orig[3];
+      gather_tet(m, E, tv, M);
+      load3(x_tgt, stride, s, dest);
+      load3(x_orig, stride, s, orig);
+      int dual_id = m->dual_off[E];
+      int adj_id = -1, ind_exp = -1;
+      double projd[4] = {0, 0, 0, 0};
+      double xpts[3] = {0, 0, 0};
+      for (int fi = 0; fi < 4; ++fi) {
+        const int F = m->elem2sides[4 * (long)E + fi];
+        int fv[3]; double fc[9], xp[3];
+        for (int k = 0; k < 3; ++k) {
+          fv[k] = m->side2verts[3 * (long)F + k];
+          for (int i = 0; i < 3; ++i) fc[3 * k + i] = m->coords[3 * (long)fv[k] + i];
+        }
+        const int flip = orc_is_face_flipped_3d(fi, fv, tv);
+        const int det = orc_line_triangle_intx_simple(fc, orig, dest, xp, &projd[fi], flip, tol);
+        const int ex = m->exposed[F];
+        if (det && ex) {
+          ind_exp = fi;
+          for (int i = 0; i < 3; ++i) xpts[i] = xp[i];
+        }
+        if (det && !ex) adj_id = dual_id;
+        if (!ex) ++dual_id;
+      }
+      if (ind_exp >= 0) {                    /* wall collision */
+        for (int i = 0; i < 3; ++i) xpoints_d[3 * (long)s + i] = xpts[i];
+        xface_d[s] = m->elem2sides[4 * (long)E + ind_exp];
+        next[s] = -1;
+        done[s] = 2;
+      }
+      if (adj_id >= 0) {                     /* interior; also overrides a wall hit (:460-468) */
+        next[s] = m->dual[adj_id];
+        done[s] = 1;
+      }
+    }
+#pragma omp parallel for
+    for (int s = 0; s < cap; ++s) {          /* :471-516 processUndetected */
+      const int d = done[s];
+      done[s] = (d < 2) ? 0 : 2;
+      if (!(mask[s] > 0 && d < 1)) continue;
+      const int E = elem_ids[s];
+      int tv[4]; double M[12], dest[3], orig[3];
+      gather_tet(m, E, tv, M);
+      load3(x_tgt, stride, s, dest);
+      load3(x_orig, stride, s, orig);
+      double projd[4] = {-1, -1, -1, -1};
+      double xpoints[12];
+      for (int fi = 0; fi < 4; ++fi) {
+        const int F = m->elem2sides[4 * (long)E + fi];
+        int fv[3]; double fc[9], xp[3];
+        for (int k = 0; k < 3; ++k) {
+          fv[k] = m->side2verts[3 * (long)F + k];
+          for (int i = 0; i < 3; ++i) fc[3 * k + i] = m->coords[3 * (long)fv[k] + i];
+        }
+        const int flip = orc_is_face_flipped_3d(fi, fv, tv);
+        orc_line_triangle_intx_simple(fc, orig, dest, xp, &projd[fi], flip, tol);
+        for (int i = 0; i < 3; ++i) xpoints[fi * 3 + i] = xp[i];
+      }
+      const int mi = orc_max_index(projd, 4);
+      const int fid = m->elem2sides[4 * (long)E + mi];
+      if (m->exposed[fid]) {
+        next[s] = -1;
+        for (int i = 0; i < 3; ++i) xpoints_d[3 * (long)s + i] = xpoints[mi * 3 + i];
+        xface_d[s] = fid;
+        done[s] = 2;
+      } else {
+        /* dual graph indexed by FACE id (:510), as in the legacy search; an out-of-range read
+         * is undefined in the reference, the oracle drops the particle */
+        if (fid < ndual) next[s] = m->dual[fid];
+        else { next[s] = -1; done[s] = 2; }
+      }
+    }
+#pragma omp parallel for
+    for (int s = 0; s < cap; ++s) elem_ids[s] = next[s];  /* :518-522 */
+    found = 1;
+    if (min_done(done, cap) == 0) found = 0;
+    ++loops;
+    if (looplimit && loops >= looplimit) break;           /* :528 */
+  }
+  if (stats) {
+    int nf = 0;
+    for (int s = 0; s < cap; ++s) nf += (mask[s] > 0 && !done[s]);
+    stats->loops = loops; stats->not_in_elem = 0; stats->not_found = nf;
+    stats->aborted = aborted;
+  }
+  free(done); free(next);
+  return found;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Pushes
  * ---------------------------------------------------------------------------------------- */
 void orc_push_constant(int cap, const unsigned char* mask, const double* x, double* xtgt,

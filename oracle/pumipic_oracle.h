@@ -109,6 +109,13 @@ int orc_search_mesh_legacy3d(const orc_mesh* m, int cap, const int* slot_elem,
                              int elem_ids_empty, double* xpoints, int* xface, int looplimit,
                              orc_search_stats* stats);
 
+/* src/pumipic_adjacency.hpp:316 search_mesh_3d (3 kernels per iteration, tol 1e-20) */
+int orc_barycentric_coords_tet(const double M[12], const double p[3], double bcc[4], double tol);
+int orc_search_mesh_3d(const orc_mesh* m, int cap, const int* slot_elem,
+                       const unsigned char* mask, const double* x_orig, const double* x_tgt,
+                       long stride, int* elem_ids, int elem_ids_empty, double* xpoints,
+                       int* xface, int looplimit, orc_search_stats* stats);
+
 /* --- pushes --- */
 /* test/pseudoPushAndSearch.cpp:87-118 */
 void orc_push_constant(int cap, const unsigned char* mask, const double* x, double* xtgt,

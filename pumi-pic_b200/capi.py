@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PUMIPIC_B200_LIB", os.path.join(HERE, "libpumipic_b20
 PP_OK = 0
 PP_HOST, PP_DEVICE = 0, 1
 PP_PS_SCS, PP_PS_CSR, PP_PS_CABM, PP_PS_DPS = 0, 1, 2, 3
-PP_SEARCH_NEW, PP_SEARCH_2D_LEGACY, PP_SEARCH_3D_LEGACY = 0, 1, 2
+PP_SEARCH_NEW, PP_SEARCH_2D_LEGACY, PP_SEARCH_3D_LEGACY, PP_SEARCH_3D = 0, 1, 2, 3
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)

@@ -453,7 +453,7 @@ inline bool run_search(Mesh& mesh, PS* ptcls, int variant, Seg3 x_orig, Seg3 x_t
   if (elem_ids.size() == 0) elem_ids = View<lid_t>(cap, "elem_ids");           // tpp:504-509
   a.elem_ids = elem_ids.data();
   a.require_intersection = requireIntersection;
-  if (inter_faces && (requireIntersection || variant == PP_SEARCH_3D_LEGACY)) {
+  if (inter_faces && (requireIntersection || variant == PP_SEARCH_3D_LEGACY || variant == PP_SEARCH_3D)) {
     if (inter_faces->size() < cap) *inter_faces = View<lid_t>(cap, (lid_t)-1, "inter_faces");   // tpp:538-539
     if (inter_points->size() < cap * inter_dim) *inter_points = View<fp_t>(cap * inter_dim, 0.0, "inter_points");
   }
@@ -480,6 +480,14 @@ bool search_mesh(Mesh& mesh, ParticleStructure<ParticleType>* ptcls, Segment3d x
                  SegmentInt /*pid_d*/, View<lid_t>& elem_ids, View<fp_t>& xpoints_d, View<lid_t>& xface_id,
                  int looplimit = 0, int /*debug*/ = 0) {
   return detail::run_search(mesh, ptcls, PP_SEARCH_3D_LEGACY, x_ps_d, xtgt_ps_d, elem_ids, false, &xface_id,
+                            &xpoints_d, 3, looplimit);
+}
+// adjacency.hpp:316-324 search_mesh_3d (GITRm's search: barycentric_coords_tet with tol 1e-20)
+template <class ParticleStruct, typename CurrentCoordView, typename TargetCoordView, typename SegmentInt>
+bool search_mesh_3d(Mesh& mesh, ParticleStruct* ptcls, CurrentCoordView x_ps_d, TargetCoordView xtgt_ps_d,
+                    SegmentInt /*pid_d*/, View<lid_t>& elem_ids, View<fp_t>& xpoints_d, View<lid_t>& xface_d,
+                    int looplimit = 0, int /*debug*/ = 0) {
+  return detail::run_search(mesh, ptcls, PP_SEARCH_3D, x_ps_d, xtgt_ps_d, elem_ids, false, &xface_d,
                             &xpoints_d, 3, looplimit);
 }
 // adjacency.hpp:1013-1020 (elem_ids by value, -1 = start in the row element)

@@ -95,6 +95,23 @@ extern "C" pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t 
     ncclUniqueId uid;
     memcpy(uid.internal, id, 128);
     PP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
+    // NCCL connects point-to-point and collective channels lazily, on the first call that uses
+    // them (tens of milliseconds per new peer): a migration that reaches a diagonal neighbour for
+    // the first time in step 40 would stall that step.  Touch every peer and both collectives now.
+    char* w = nullptr;
+    PP_CUDA(cudaMalloc(&w, (size_t)(2 * nranks + 2) * 8));
+    PP_CUDA(cudaMemset(w, 0, (size_t)(2 * nranks + 2) * 8));
+    PP_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < nranks; ++p) {
+      if (p == rank) continue;
+      PP_NCCL(g_nccl.Send(w + 8 * p, 8, ncclUint8, p, c->comm, 0));
+      PP_NCCL(g_nccl.Recv(w + 8 * (nranks + p), 8, ncclUint8, p, c->comm, 0));
+    }
+    PP_NCCL(g_nccl.GroupEnd());
+    PP_NCCL(g_nccl.AllReduce(w, w, 1, ncclInt64, ncclSum, c->comm, 0));
+    PP_NCCL(g_nccl.AllGather(w + 8 * 2 * nranks, w, 2, ncclInt32, c->comm, 0));
+    PP_CUDA(cudaStreamSynchronize(0));
+    PP_CUDA(cudaFree(w));
   }
   *out = c;
   return PP_OK;

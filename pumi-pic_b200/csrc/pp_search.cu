@@ -16,7 +16,7 @@
 
 namespace {
 
-enum Mode { M_BCC = 0, M_RAY = 1, M_LEG2D = 2, M_LEG3D = 3 };
+enum Mode { M_BCC = 0, M_RAY = 1, M_LEG2D = 2, M_LEG3D = 3, M_S3D = 4 };
 
 struct SearchParams {
   PsView ps;
@@ -157,6 +157,27 @@ __device__ __forceinline__ bool bcc_tet_legacy(const Tet& t, d3 p, double bcc[4]
 #pragma unroll
   for (int i = 0; i < 4; ++i) bcc[i] = inv * v[i];
   return true;
+}
+// adjacency.hpp:136-158 barycentric_coords_tet (search_mesh_3d): vals scaled by 1/6, true volume
+// (== measure_elements_real: both are tet_volume_from_basis(simplex_basis)); bcc stays 0 when
+// vol < tol and the caller ignores the status
+__device__ __forceinline__ void bcc_tet_s3d(const Tet& t, d3 p, double bcc[4], double tol) {
+  const d3 n0 = cross3(t.M[1] - t.M[0], t.M[2] - t.M[0]);
+  const d3 n1 = cross3(t.M[3] - t.M[0], t.M[1] - t.M[0]);
+  const d3 n2 = cross3(t.M[3] - t.M[1], t.M[2] - t.M[1]);
+  const d3 n3 = cross3(t.M[3] - t.M[2], t.M[0] - t.M[2]);
+  const d3 p0 = p - t.M[0];
+  double v[4];
+  v[0] = 1.0 / 6.0 * dot3(p0, n0);
+  v[1] = 1.0 / 6.0 * dot3(p0, n1);
+  v[2] = 1.0 / 6.0 * dot3(p - t.M[1], n2);
+  v[3] = 1.0 / 6.0 * dot3(p - t.M[2], n3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) bcc[i] = 0;
+  if (t.vol < tol) return;
+  const double inv = 1.0 / t.vol;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) bcc[i] = inv * v[i];
 }
 // adjacency.tpp:23-39 barycentric_tri: edges (0,1),(1,2),(2,0)
 __device__ __forceinline__ void bcc_tri(const Tri& t, d2 p, double bcc[3]) {
@@ -470,6 +491,55 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
               E = -1; done = true; break;           // "leaked"
             }
           }
+        } else if constexpr (MODE == M_S3D) {
+          // adjacency.hpp:395-516: checkCurrentElm, findIntersection, processUndetected
+          constexpr double tol3 = 1.0e-20;
+          double b[4];
+          if (it == 1) {                                   // checkParent :368-379 (row element)
+            if (erow == E) {
+              bcc_tet_s3d(rec, org, b, tol3);
+            } else {
+              Rec rrow;
+              load_rec(p.walk, erow, rrow);
+              bcc_tet_s3d(rrow, org, b, tol3);
+            }
+            if (!all_positive<4>(b, tol3)) st.aborted = 1;
+          }
+          bcc_tet_s3d(rec, tgt, b, tol3);
+          if (all_positive<4>(b, tol3)) { done = true; break; }
+          double dproj[4] = {-1, -1, -1, -1};
+          d3 xpts[4];
+          int ind_exp = -1, adj_f = -1;
+#pragma unroll
+          for (int fi = 0; fi < 4; ++fi) {
+            const unsigned code = (rec.codes >> (8 * fi)) & 0xffu;
+            const d3 V0 = vert_of(rec, code & 3), V1 = vert_of(rec, (code >> 2) & 3),
+                     V2 = vert_of(rec, (code >> 4) & 3);
+            const bool det = line_tri_simple(V0, V1, V2, org, tgt, xpts[fi], dproj[fi], (code >> 6) & 1, tol3);
+            if (det && rec.adj[fi] < 0) ind_exp = fi;
+            if (det && rec.adj[fi] >= 0) adj_f = fi;
+          }
+          if (ind_exp >= 0) {                              // wall collision :441-453
+            xp_out = ind_exp == 0 ? xpts[0] : ind_exp == 1 ? xpts[1] : ind_exp == 2 ? xpts[2] : xpts[3];
+            xface = -adj_of(rec, ind_exp) - 1; write_x = true;
+            next = -1; done = true;
+          }
+          if (adj_f >= 0) {                                // interior; overrides a wall hit :456-468
+            next = adj_of(rec, adj_f); done = false;
+          }
+          if (ind_exp < 0 && adj_f < 0) {                  // processUndetected :471-516
+            const int mi = max_index4(dproj);
+            const int a = adj_of(rec, mi);
+            if (a < 0) {
+              xp_out = mi == 0 ? xpts[0] : mi == 1 ? xpts[1] : mi == 2 ? xpts[2] : xpts[3];
+              xface = -a - 1; write_x = true; next = -1; done = true;
+            } else {
+              const int fid = p.elem2sides[4 * (long)E + mi];   // dual indexed by face id (:510)
+              if (fid < p.ndual) next = p.dual[fid];
+              else { next = -1; done = true; }
+            }
+          }
+          if (done) { E = next; break; }
         }
         // set_new_element + loop limit
         prevE = E;
@@ -477,6 +547,8 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
         ++st.hops;
         if (MODE == M_LEG3D) {
           if (p.looplimit && it > p.looplimit) { st.not_found = 1; break; }     // :756
+        } else if (MODE == M_S3D) {
+          if (p.looplimit && it >= p.looplimit) { st.not_found = 1; break; }    // :528 (id kept)
         } else {
           if (p.looplimit && it >= p.looplimit) { st.not_found = 1; E = -1; break; }  // tpp:584-606
         }
@@ -485,14 +557,14 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
       st.iters = it;
     }
     // ---- outputs
-    if (mask || p.ids_empty || MODE == M_LEG2D || MODE == M_LEG3D) p.elem_ids[s] = mask ? E : -1;
+    if (mask || p.ids_empty || MODE == M_LEG2D || MODE == M_LEG3D || MODE == M_S3D) p.elem_ids[s] = mask ? E : -1;
     if (MODE == M_RAY) {
       // initializeIntersection resets every slot (tpp:535-549); hits overwrite
       p.inter_faces[s] = xface;
 #pragma unroll
       for (int i = 0; i < DIM; ++i)
         p.inter_points[(long)DIM * s + i] = write_x ? (i == 0 ? xp_out.x : i == 1 ? xp_out.y : xp_out.z) : 0.0;
-    } else if (MODE == M_LEG3D && xface >= 0) {
+    } else if ((MODE == M_LEG3D || MODE == M_S3D) && xface >= 0) {
       p.inter_faces[s] = xface;
       p.inter_points[3 * (long)s] = xp_out.x;
       p.inter_points[3 * (long)s + 1] = xp_out.y;
@@ -1218,6 +1290,17 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
         PP_CUDA(cudaStreamSynchronize(s));
         p.ndual = nd;
         launch<3, M_LEG3D>(p, false, s);
+        break;
+      }
+      case PP_SEARCH_3D: {
+        PP_REQUIRE(mesh->dim == 3, "search_mesh_3d needs a 3D mesh");
+        PP_REQUIRE(!push, "fused push is only available for the new search API");
+        PP_REQUIRE(a->x_orig && a->inter_faces && a->inter_points, "xpoints / xface are required");
+        int nd = 0;
+        PP_CUDA(cudaMemcpyAsync(&nd, mesh->dual_off + mesh->nelems, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PP_CUDA(cudaStreamSynchronize(s));
+        p.ndual = nd;
+        launch<3, M_S3D>(p, false, s);
         break;
       }
       default:

@@ -157,6 +157,20 @@ class OracleMesh:
             _ip(ids), C.c_int(empty), _dp(xpts), _ip(xface), C.c_int(looplimit), C.byref(st))
         return bool(found), ids, xpts.reshape(cap, 3), xface, st
 
+    def search_mesh_3d(self, slot_elem, mask, x, xtgt, elem_ids=None, looplimit=0):
+        cap = mask.shape[0]
+        empty = elem_ids is None
+        ids = np.full(cap, -1, np.int32) if empty else np.ascontiguousarray(elem_ids, np.int32).copy()
+        xpts = np.zeros(3 * cap, np.float64)
+        xface = np.full(cap, -1, np.int32)
+        st = SearchStats()
+        x = _f64(x); xtgt = _f64(xtgt)
+        found = lib().orc_search_mesh_3d(
+            self.h, C.c_int(cap), _ip(np.ascontiguousarray(slot_elem, np.int32)),
+            _u8(np.ascontiguousarray(mask, np.uint8)), _dp(x), _dp(xtgt), C.c_long(x.shape[1]),
+            _ip(ids), C.c_int(empty), _dp(xpts), _ip(xface), C.c_int(looplimit), C.byref(st))
+        return bool(found), ids, xpts.reshape(cap, 3), xface, st
+
     def gyro_scatter(self, slot_elem, mask, v2v, rmax, nrings, ppr):
         out = np.zeros(self.mesh.nverts, np.float64)
         lib().orc_gyro_scatter(self.h, C.c_int(mask.shape[0]),

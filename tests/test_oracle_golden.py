@@ -144,3 +144,52 @@ def test_gyro_scatter_known_answer():
     for v in range(mesh.nverts):
         want = {3: 2.0, 2: 12.0, 8: 0.0}.get(v, 2.0 / 3.0)
         assert abs(w[v] - want) <= 1e-10 * max(1.0, abs(want)), (v, w[v], want)
+
+
+def test_search_mesh_3d_oracle_consistent_with_the_other_3d_walks():
+    """adjacency.hpp:316 search_mesh_3d has no test in the reference: its oracle is
+    pinned on geometry -- every particle it keeps ends in a tet that contains the target by the
+    reference's own barycentric test, every particle it drops crossed an exposed face whose plane
+    contains the reported point -- and against the two pinned 3D walks on the same inputs."""
+    import ptcl_init as pi
+    mesh = load_fixture("cube7k")
+    om = orc.OracleMesh(mesh)
+    n = 20000
+    slot_elem = (np.arange(n, dtype=np.int64) * mesh.nelems // n).astype(np.int32)
+    mask = np.ones(n, np.uint8)
+    X, D = pi.init3d_internal(mesh, slot_elem, mask)
+    ext = (mesh.coords.max(axis=0) - mesh.coords.min(axis=0)).max()
+    T = np.zeros_like(X)
+    orc.push_constant(mask, X, T, ext / 20, (0.0, 0.0, 1.0))
+    found, ids, xp, xf, st = om.search_mesh_3d(slot_elem, mask, X, T, looplimit=200)
+    assert found and st.aborted == 0 and st.loops > 1
+    f9, ids9, xp9, xf9, st9 = om.search_mesh_legacy3d(slot_elem, mask, X, T, looplimit=200)
+    fb, idsb, _, _, stb = om.search_mesh(slot_elem, mask, X, T)
+    assert fb
+    # same destinations as the new BCC walk, except for particles that graze a face or an edge
+    assert (ids != idsb).mean() < 2e-3
+    # the legacy walk (a9) does not converge for every random interior start (its fallback indexes
+    # the dual graph by face id, adjacency.hpp:726); where it does finish the two must agree
+    ok9 = ids9 == idsb
+    assert ok9.mean() > 0.5 and (ids[ok9] != ids9[ok9]).mean() < 2e-3
+    same = (xf >= 0) & (xf == xf9)
+    assert same.sum() > 100 and np.array_equal(xp[same], xp9[same])
+    inside = ids >= 0
+    assert inside.sum() > 1000 and (~inside).sum() > 100
+    vol = om.vol()
+    for s in np.nonzero(inside)[0][::37]:
+        e = ids[s]
+        M = mesh.coords[mesh.elem2verts[e]]
+        ok, b = orc.barycentric_tet(vol[e], M, np.ascontiguousarray(T[:, s]))
+        assert ok and b.min() >= -1e-8
+    # wall hits: the point lies on the exposed face's plane, between origin and target in z
+    exposed = om.exposed()
+    for s in np.nonzero(xf >= 0)[0][::11]:
+        assert exposed[xf[s]] == 1 and ids[s] == -1
+        fv = mesh.coords[mesh.side2verts[xf[s]]]
+        nrm = np.cross(fv[1] - fv[0], fv[2] - fv[0])
+        assert abs(np.dot(nrm, xp[s] - fv[0])) <= 1e-9 * np.abs(nrm).max() * ext
+        assert X[2, s] - 1e-12 <= xp[s, 2] <= T[2, s] + 1e-12
+    # loop limit: stops after `looplimit` iterations, unfinished particles keep their next element
+    f2, ids2, _, _, st2 = om.search_mesh_3d(slot_elem, mask, X, T, looplimit=2)
+    assert not f2 and st2.loops == 2 and st2.not_found > 0

@@ -179,6 +179,55 @@ def test_legacy_3d_search_matches_oracle():
     assert (xf_o >= 0).sum() > 0 and (ids_o >= 0).sum() > 0
 
 
+@pytest.mark.parametrize("meshname,push", [("cube7k", "constant"), ("cube7k", "direction"),
+                                           ("kuhn8", "direction")])
+def test_search_mesh_3d_matches_oracle(meshname, push):
+    """adjacency.hpp:316 search_mesh_3d (PP_SEARCH_3D): element ids, wall faces, wall points and
+    counters bit-exact against the oracle, two consecutive steps, with and without a loop limit."""
+    mesh = kuhn_cube(8) if meshname == "kuhn8" else load_fixture(meshname)
+    om = orc.OracleMesh(mesh)
+    gm, ps, slot_elem, mask, X, D = _setup(mesh, 30000)
+    ext = (mesh.coords.max(axis=0) - mesh.coords.min(axis=0)).max()
+    t = torch()
+    P = pp()
+    cap = ps.capacity
+    T = np.zeros_like(X)
+    if push == "constant":
+        orc.push_constant(mask, X, T, ext / 20, (0.0, 0.0, 1.0))
+    else:
+        T = X.copy()
+        orc.push_direction(mask, T, D, 6 * pi.push_distance(mesh))
+    for limit in (0, 3):
+        ids = t.zeros(cap, dtype=t.int32, device="cuda")
+        xface = t.full((cap,), -1, dtype=t.int32, device="cuda")
+        xpts = t.zeros(3 * cap, dtype=t.float64, device="cuda")
+        r = P.search_mesh(gm, ps, dev(X), dev(T), ids, elem_ids_empty=True, variant=P.capi.PP_SEARCH_3D,
+                          inter_faces=xface, inter_points=xpts, looplimit=limit)
+        found, ids_o, xp_o, xf_o, st = om.search_mesh_3d(slot_elem, mask, X, T, looplimit=limit)
+        assert np.array_equal(ids.cpu().numpy(), ids_o)
+        assert np.array_equal(xface.cpu().numpy(), xf_o)
+        assert np.array_equal(xpts.cpu().numpy().reshape(cap, 3), xp_o)
+        assert (r.found, r.loops, r.aborted, r.not_found) == (int(found), st.loops, st.aborted, st.not_found)
+        if limit == 0:
+            assert found and (xf_o >= 0).sum() > 0 and (ids_o >= 0).sum() > 0
+        else:
+            assert not found and st.not_found > 0
+    # second step from the found elements (elem_ids passed in), origin = previous target
+    keep = ids_o.copy()
+    T2 = T.copy()
+    orc.push_direction(mask, T2, D, 2 * pi.push_distance(mesh))
+    ids = dev(keep)
+    xface = t.full((cap,), -1, dtype=t.int32, device="cuda")
+    xpts = t.zeros(3 * cap, dtype=t.float64, device="cuda")
+    r = P.search_mesh(gm, ps, dev(T), dev(T2), ids, elem_ids_empty=False, variant=P.capi.PP_SEARCH_3D,
+                      inter_faces=xface, inter_points=xpts, looplimit=100)
+    found, ids_o2, xp_o2, xf_o2, st2 = om.search_mesh_3d(slot_elem, mask, T, T2, elem_ids=keep, looplimit=100)
+    assert np.array_equal(ids.cpu().numpy(), ids_o2)
+    assert np.array_equal(xface.cpu().numpy(), xf_o2)
+    assert np.array_equal(xpts.cpu().numpy().reshape(cap, 3), xp_o2)
+    assert (r.found, r.loops, r.aborted) == (int(found), st2.loops, st2.aborted)
+
+
 def test_fused_push_search_equals_push_then_search():
     mesh = kuhn_cube(8)
     gm, ps, slot_elem, mask, X, D = _setup(mesh, 25000)
