@@ -336,6 +336,40 @@ pp_status pp_push_direction_search_host(pp_mesh* mesh, pp_ps* ps, const double* 
 pp_status pp_push_from(pp_ps* ps, const double* x, double* xtgt, const double* dir,
                        int64_t stride, double distance, pp_stream stream);
 
+/* ============================== gather (field -> particle) =============================== */
+/* The interpolation helpers an application's push calls per particle (GITRm's Boris push feeds
+ * pp_push_boris with them).  All outputs are component-major [ncomp][stride] like the particle
+ * members; only masked slots are written.
+ *
+ * src/pumipic_adjacency.hpp:801-809 findBCCoordsInTet + :772-799 interpolateTetVtx /
+ * interpolate3dFieldTet: barycentric coordinates of x in tet elem_ids[slot] (find_barycentric_tet,
+ * :97-133), then out[c] = sum_f bcc[f] * field[vertex_opposite(f)*dof + c].  Slots with
+ * elem_ids < 0 are skipped.  n_outside_host (may be NULL; non-NULL synchronises the stream)
+ * receives the number of particles the reference's OMEGA_H_CHECKs would abort on (point outside
+ * its element by more than 1e-10); their outputs are left untouched.
+ *   field: device double[nverts*dof], vertex-major (an Omega_h vertex tag with dof components) */
+pp_status pp_gather_tet_field(pp_mesh* mesh, pp_ps* ps, const double* x, int64_t stride,
+                              const int32_t* elem_ids, const double* field, int32_t dof, double* out,
+                              int32_t* n_outside_host, pp_stream stream);
+/* src/pumipic_utils.hpp:298-321 interpolate2d_field: bilinear interpolation of component `comp` of
+ * an ncomp-component table data[(i + j*nx)*ncomp + comp] on the uniform grid
+ * (gridx0 + i*dx, gridz0 + j*dz) at (x or sqrt(x^2+y^2) when cyl_symm, z).  out: [stride]. */
+pp_status pp_gather_grid2d(pp_ps* ps, const double* x, int64_t stride, const double* data,
+                           double gridx0, double gridz0, double dx, double dz, int32_t nx, int32_t nz,
+                           int32_t cyl_symm, int32_t ncomp, int32_t comp, double* out,
+                           pp_stream stream);
+/* src/pumipic_utils.hpp:439-456 interp2dVector: the three components of a 3-component table, the
+ * first two rotated by atan2(y, x) when cyl_symm.  out: [3][stride]. */
+pp_status pp_gather_grid2d_vector(pp_ps* ps, const double* x, int64_t stride, const double* data3,
+                                  double gridx0, double gridz0, double dx, double dz, int32_t nx,
+                                  int32_t nz, int32_t cyl_symm, double* out, pp_stream stream);
+/* src/pumipic_utils.hpp:377-420 interpolate3d_field: trilinear interpolation of
+ * data[i + j*nx + k*nx*ny] on the grid lines gridx[nx], gridy[ny], gridz[nz] (device arrays;
+ * ny or nz may be 1).  out: [stride]. */
+pp_status pp_gather_grid3d(pp_ps* ps, const double* x, int64_t stride, const double* data,
+                           const double* gridx, const double* gridy, const double* gridz, int32_t nx,
+                           int32_t ny, int32_t nz, double* out, pp_stream stream);
+
 /* ============================== gyro scatter (2D) ======================================== */
 
 /* test/gyroScatter.hpp:96-166 createGyroRingMappings (+ :25-90 searchAndBuildMap): for every

@@ -1028,6 +1028,160 @@ int orc_search_mesh_3d(const orc_mesh* m, int cap, const int* slot_elem,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Gather (mesh / grid -> particle field interpolation): adjacency.hpp:770-809 and
+ * pumipic_utils.hpp:186-456.  Device helpers of the reference that GITRm's Boris push calls.
+ * ---------------------------------------------------------------------------------------- */
+/* adjacency.hpp:772-790 interpolateTetVtx.  The reference indexes its 4-entry gather with
+ * d*dof+comp, which is only in bounds for dof == 1; the restatement reads field[vert*dof+comp]
+ * (the documented intent: "Field has dof components ... stored in order 0,1,2,3 at tet's
+ * vertices"), identical to the reference for dof == 1. */
+double orc_interpolate_tet_vtx(const orc_mesh* m, const double* field, int elem,
+                               const double bcc[4], int dof, int comp) {
+  static const int OPP[4] = {3, 2, 0, 1};   /* simplex_opposite_template(3, 2, fi) */
+  const int* tv = m->elem2verts + 4 * (long)elem;
+  double val = 0;
+  for (int fi = 0; fi < 4; ++fi) val = val + bcc[fi] * field[(long)tv[OPP[fi]] * dof + comp];
+  return val;
+}
+/* adjacency.hpp:801-809 findBCCoordsInTet + :793-799 interpolate3dFieldTet for every masked
+ * particle: out[c*stride+s].  Returns the number of particles the reference would abort on
+ * (find_barycentric_tet failed or a coordinate below -EPSILON); their output is left untouched. */
+int orc_gather_tet_field(const orc_mesh* m, int cap, const unsigned char* mask, const double* x,
+                         long stride, const int* elem_ids, const double* field, int dof,
+                         double* out) {
+  int bad = 0;
+#pragma omp parallel for reduction(+ : bad)
+  for (int s = 0; s < cap; ++s) {
+    if (!mask[s]) continue;
+    const int e = elem_ids[s];
+    if (e < 0) continue;
+    int tv[4]; double M[12], p[3], bcc[4];
+    gather_tet(m, e, tv, M);
+    load3(x, stride, s, p);
+    const int res = orc_find_barycentric_tet(M, p, bcc);
+    if (!res || !orc_all_positive(bcc, 4, 1e-10)) { bad += 1; continue; }
+    for (int c = 0; c < dof; ++c) out[c * stride + s] = orc_interpolate_tet_vtx(m, field, e, bcc, dof, c);
+  }
+  return bad;
+}
+
+/* pumipic_utils.hpp:245-248 */
+static inline double interp2d_base(double d1, double d2, double grid1, double grid2, double v,
+                                   double dv) {
+  return (d1 * (grid2 - v) + d2 * (v - grid1)) / dv;
+}
+/* pumipic_utils.hpp:260-296 interpolate2d */
+static double interpolate2d(const double* data, double gridXi, double gridXip1, double gridZj,
+                            double gridZjp1, double x0, double z, int nx, int nz, int i, int j,
+                            double dx, double dz, double y, int cyl, int nComp, int comp) {
+  if (nx <= 1 && nz <= 1) return data[comp];
+  double x = x0;
+  if (cyl) x = sqrt(x * x + y * y);
+  double fxz = 0;
+  if (i >= nx - 1 && j >= nz - 1) {
+    fxz = data[(nx - 1 + (long)(nz - 1) * nx) * nComp + comp];
+  } else if (i >= nx - 1) {
+    fxz = interp2d_base(data[(nx - 1 + (long)j * nx) * nComp + comp],
+                        data[(nx - 1 + (long)(j + 1) * nx) * nComp + comp], z - gridZj, gridZjp1 - z,
+                        z, dz);
+  } else if (j >= nz - 1) {
+    fxz = interp2d_base(data[(i + (long)(nz - 1) * nx) * nComp + comp],
+                        data[(i + (long)(nz - 1) * nx) * nComp + comp], x - gridXi, gridXip1 - x, x,
+                        dx);
+  } else {
+    const double f1 = interp2d_base(data[(i + (long)j * nx) * nComp + comp],
+                                    data[(i + 1 + (long)j * nx) * nComp + comp], gridXi, gridXip1, x, dx);
+    const double f2 = interp2d_base(data[(i + (long)(j + 1) * nx) * nComp + comp],
+                                    data[(i + 1 + (long)(j + 1) * nx) * nComp + comp], gridXi, gridXip1,
+                                    x, dx);
+    fxz = interp2d_base(f1, f2, gridZj, gridZjp1, z, dz);
+  }
+  return fxz;
+}
+/* pumipic_utils.hpp:298-321 interpolate2d_field (uniform grid given by origin and spacing) */
+double orc_interpolate2d_field(const double* data, double gridx0, double gridz0, double dx,
+                               double dz, int nx, int nz, const double pos[3], int cyl, int nComp,
+                               int comp) {
+  if (nx <= 1 && nz <= 1) return data[comp];
+  double x = pos[0];
+  const double z = pos[2];
+  if (cyl) x = sqrt(x * x + pos[1] * pos[1]);
+  int i = (int)floor((x - gridx0) / dx);
+  int j = (int)floor((z - gridz0) / dz);
+  if (i < 0) i = 0;
+  if (j < 0) j = 0;
+  const double gridXi = gridx0 + i * dx, gridXip1 = gridx0 + (i + 1) * dx;
+  const double gridZj = gridz0 + j * dz, gridZjp1 = gridz0 + (j + 1) * dz;
+  return interpolate2d(data, gridXi, gridXip1, gridZj, gridZjp1, x, z, nx, nz, i, j, dx, dz, 0, 0,
+                       nComp, comp);
+}
+/* pumipic_utils.hpp:439-456 interp2dVector: three components, rotated by atan2(y, x) when the
+ * data are cylindrically symmetric */
+void orc_interp2d_vector(const double* data3, double gridx0, double gridz0, double dx, double dz,
+                         int nx, int nz, const double pos[3], double field[3], int cyl) {
+  for (int i = 0; i < 3; ++i)
+    field[i] = orc_interpolate2d_field(data3, gridx0, gridz0, dx, dz, nx, nz, pos, cyl, 3, i);
+  if (cyl) {
+    const double theta = atan2(pos[1], pos[0]);
+    const double f0 = field[0], f1 = field[1];
+    field[0] = cos(theta) * f0 - sin(theta) * f1;
+    field[1] = sin(theta) * f0 + cos(theta) * f1;
+  }
+}
+/* pumipic_utils.hpp:377-420 interpolate3d_field (grid coordinates given as arrays) */
+double orc_interpolate3d_field(double x, double y, double z, int nx, int ny, int nz,
+                               const double* gridx, const double* gridy, const double* gridz,
+                               const double* data) {
+  /* The reference evaluates all four rows and the y / z spacings unconditionally and discards
+   * them when ny <= 1 or nz <= 1 (:415-416); those reads lie outside the tables, so the
+   * restatement skips what is discarded. */
+  const double dx = gridx[1] - gridx[0];
+  const double dy = ny > 1 ? gridy[1] - gridy[0] : 1.0;
+  const double dz = nz > 1 ? gridz[1] - gridz[0] : 1.0;
+  int i = (int)floor((x - gridx[0]) / dx);
+  int j = (int)floor((y - gridy[0]) / dy);
+  int k = (int)floor((z - gridz[0]) / dz);
+  i = (i < 0) ? 0 : ((i >= nx - 1) ? (nx - 2) : i);
+  j = (j < 0 || ny <= 1) ? 0 : ((j >= ny - 1) ? (ny - 2) : j);
+  k = (k < 0 || nz <= 1) ? 0 : ((k >= nz - 1) ? (nz - 2) : k);
+#define D_(I) data[(I)], data[(I) + 1]
+  const long nxy = (long)nx * ny;
+  const double fx_z0 = interp2d_base(D_(i + (long)j * nx + k * nxy), gridx[i], gridx[i + 1], x, dx);
+  if (nz <= 1) return fx_z0;
+  const double fx_z1 = interp2d_base(D_(i + (long)j * nx + (k + 1) * nxy), gridx[i], gridx[i + 1], x, dx);
+  const double fxz0 = interp2d_base(fx_z0, fx_z1, gridz[k], gridz[k + 1], z, dz);
+  if (ny <= 1) return fxz0;
+  const double fxy_z0 = interp2d_base(D_(i + (long)(j + 1) * nx + k * nxy), gridx[i], gridx[i + 1], x, dx);
+  const double fxy_z1 = interp2d_base(D_(i + (long)(j + 1) * nx + (k + 1) * nxy), gridx[i], gridx[i + 1], x, dx);
+#undef D_
+  const double fxz1 = interp2d_base(fxy_z0, fxy_z1, gridz[k], gridz[k + 1], z, dz);
+  return interp2d_base(fxz0, fxz1, gridy[j], gridy[j + 1], y, dy);
+}
+/* per-particle drivers over a particle structure (masked slots) */
+void orc_gather_grid2d_vector(int cap, const unsigned char* mask, const double* x, long stride,
+                              const double* data3, double gridx0, double gridz0, double dx,
+                              double dz, int nx, int nz, int cyl, double* out) {
+#pragma omp parallel for
+  for (int s = 0; s < cap; ++s) {
+    if (!mask[s]) continue;
+    double p[3], f[3];
+    load3(x, stride, s, p);
+    orc_interp2d_vector(data3, gridx0, gridz0, dx, dz, nx, nz, p, f, cyl);
+    for (int c = 0; c < 3; ++c) out[c * stride + s] = f[c];
+  }
+}
+void orc_gather_grid3d(int cap, const unsigned char* mask, const double* x, long stride,
+                       const double* data, const double* gridx, const double* gridy,
+                       const double* gridz, int nx, int ny, int nz, double* out) {
+#pragma omp parallel for
+  for (int s = 0; s < cap; ++s) {
+    if (!mask[s]) continue;
+    out[s] = orc_interpolate3d_field(x[s], x[stride + s], x[2 * stride + s], nx, ny, nz, gridx,
+                                     gridy, gridz, data);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Pushes
  * ---------------------------------------------------------------------------------------- */
 void orc_push_constant(int cap, const unsigned char* mask, const double* x, double* xtgt,

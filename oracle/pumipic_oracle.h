@@ -116,6 +116,27 @@ int orc_search_mesh_3d(const orc_mesh* m, int cap, const int* slot_elem,
                        long stride, int* elem_ids, int elem_ids_empty, double* xpoints,
                        int* xface, int looplimit, orc_search_stats* stats);
 
+/* --- gather: src/pumipic_adjacency.hpp:770-809, src/pumipic_utils.hpp:186-456 --- */
+double orc_interpolate_tet_vtx(const orc_mesh* m, const double* field, int elem,
+                               const double bcc[4], int dof, int comp);
+int orc_gather_tet_field(const orc_mesh* m, int cap, const unsigned char* mask, const double* x,
+                         long stride, const int* elem_ids, const double* field, int dof,
+                         double* out);
+double orc_interpolate2d_field(const double* data, double gridx0, double gridz0, double dx,
+                               double dz, int nx, int nz, const double pos[3], int cyl, int nComp,
+                               int comp);
+void orc_interp2d_vector(const double* data3, double gridx0, double gridz0, double dx, double dz,
+                         int nx, int nz, const double pos[3], double field[3], int cyl);
+double orc_interpolate3d_field(double x, double y, double z, int nx, int ny, int nz,
+                               const double* gridx, const double* gridy, const double* gridz,
+                               const double* data);
+void orc_gather_grid2d_vector(int cap, const unsigned char* mask, const double* x, long stride,
+                              const double* data3, double gridx0, double gridz0, double dx,
+                              double dz, int nx, int nz, int cyl, double* out);
+void orc_gather_grid3d(int cap, const unsigned char* mask, const double* x, long stride,
+                       const double* data, const double* gridx, const double* gridy,
+                       const double* gridz, int nx, int ny, int nz, double* out);
+
 /* --- pushes --- */
 /* test/pseudoPushAndSearch.cpp:87-118 */
 void orc_push_constant(int cap, const unsigned char* mask, const double* x, double* xtgt,

@@ -347,6 +347,41 @@ def set_unsafe_procs(mesh, ps, elems):
     return ne, npr
 
 
+def gather_tet_field(mesh, ps, x, elem_ids, field, dof):
+    """interpolate3dFieldTet for every masked particle; returns (out [dof, stride], n_outside)."""
+    torch = _torch()
+    out = torch.zeros(dof, x.shape[1], dtype=torch.float64, device="cuda")
+    bad = C.c_int32(0)
+    check(lib().pp_gather_tet_field(mesh.h, ps.h, _ptr(x), x.shape[1], _ptr(elem_ids), _ptr(field), dof,
+                                    _ptr(out), C.byref(bad), _stream()))
+    return out, bad.value
+
+
+def gather_grid2d(ps, x, data, gridx0, gridz0, dx, dz, nx, nz, cyl, ncomp=1, comp=0):
+    torch = _torch()
+    out = torch.zeros(x.shape[1], dtype=torch.float64, device="cuda")
+    check(lib().pp_gather_grid2d(ps.h, _ptr(x), x.shape[1], _ptr(data), gridx0, gridz0, dx, dz, nx, nz,
+                                 int(bool(cyl)), ncomp, comp, _ptr(out), _stream()))
+    return out
+
+
+def gather_grid2d_vector(ps, x, data3, gridx0, gridz0, dx, dz, nx, nz, cyl):
+    torch = _torch()
+    out = torch.zeros(3, x.shape[1], dtype=torch.float64, device="cuda")
+    check(lib().pp_gather_grid2d_vector(ps.h, _ptr(x), x.shape[1], _ptr(data3), gridx0, gridz0, dx, dz,
+                                        nx, nz, int(bool(cyl)), _ptr(out), _stream()))
+    return out
+
+
+def gather_grid3d(ps, x, data, gridx, gridy, gridz):
+    torch = _torch()
+    out = torch.zeros(x.shape[1], dtype=torch.float64, device="cuda")
+    check(lib().pp_gather_grid3d(ps.h, _ptr(x), x.shape[1], _ptr(data), _ptr(gridx), _ptr(gridy),
+                                 _ptr(gridz), gridx.numel(), gridy.numel(), gridz.numel(), _ptr(out),
+                                 _stream()))
+    return out
+
+
 def gyro_ring_map(mesh, rmax, nrings, ppr, theta_deg):
     torch = _torch()
     out = torch.empty(3 * mesh.nverts * nrings * ppr, dtype=torch.int32, device="cuda")

@@ -167,6 +167,18 @@ PROTOTYPES = {
                                                 C.c_void_p]),
     "pp_push_boris": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_double, C.c_void_p]),
+    "pp_gather_tet_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
+                                      C.c_void_p]),
+    "pp_gather_grid2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_double,
+                                   C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pp_gather_grid2d_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_double,
+                                          C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_void_p, C.c_void_p]),
+    "pp_gather_grid3d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_void_p]),
     "pp_push_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_double, C.c_void_p]),
 }

@@ -520,6 +520,48 @@ void migrate_lb_ptcls(Mesh& mesh, PS* ptcls, View<lid_t> new_elems, float /*tol*
   migrate_ptcls(mesh, ptcls, new_elems);
 }
 
+// ---------------------------------------------------------------- gather (field -> particle)
+// Whole-structure forms of the interpolation helpers GITRm's push calls per particle
+// (src/pumipic_adjacency.hpp:772-809, src/pumipic_utils.hpp:298-321,377-420,439-456): one kernel
+// over all masked particles, output component-major like a particle member.
+// interpolate3dFieldTet after findBCCoordsInTet; returns the number of particles outside their element
+template <class PS, class Seg3>
+int interpolate3dFieldTet(Mesh& mesh, PS* ptcls, Seg3 x, View<lid_t> elem_ids, View<fp_t> field, int dof,
+                          View<fp_t>& out) {
+  const size_t need = (size_t)dof * x.stride();
+  if (out.size() < need) out = View<fp_t>(need, 0.0, "gathered field");
+  int32_t bad = 0;
+  pp_check(pp_gather_tet_field(mesh.handle(), ptcls->handle(), x.data(), x.stride(), elem_ids.data(), field.data(),
+                               dof, out.data(), &bad, (pp_stream)ptcls->stream()), "interpolate3dFieldTet");
+  return bad;
+}
+// interp2dVector on a uniform (r|x, z) grid; out is [3][stride]
+template <class PS, class Seg3>
+void interp2dVector(PS* ptcls, Seg3 x, View<fp_t> data3, fp_t gridx0, fp_t gridz0, fp_t dx, fp_t dz, lid_t nx,
+                    lid_t nz, View<fp_t>& out, bool cylSymm = false) {
+  const size_t need = (size_t)3 * x.stride();
+  if (out.size() < need) out = View<fp_t>(need, 0.0, "gathered field");
+  pp_check(pp_gather_grid2d_vector(ptcls->handle(), x.data(), x.stride(), data3.data(), gridx0, gridz0, dx, dz, nx,
+                                   nz, cylSymm, out.data(), (pp_stream)ptcls->stream()), "interp2dVector");
+}
+// interpolate2d_field: one component of an nComp-component table; out is [stride]
+template <class PS, class Seg3>
+void interpolate2d_field(PS* ptcls, Seg3 x, View<fp_t> data, fp_t gridx0, fp_t gridz0, fp_t dx, fp_t dz, lid_t nx,
+                         lid_t nz, View<fp_t>& out, bool cylSymm = true, lid_t nComp = 1, lid_t comp = 0) {
+  if (out.size() < (size_t)x.stride()) out = View<fp_t>((size_t)x.stride(), 0.0, "gathered field");
+  pp_check(pp_gather_grid2d(ptcls->handle(), x.data(), x.stride(), data.data(), gridx0, gridz0, dx, dz, nx, nz,
+                            cylSymm, nComp, comp, out.data(), (pp_stream)ptcls->stream()), "interpolate2d_field");
+}
+// interpolate3d_field on grid lines gridx / gridy / gridz; out is [stride]
+template <class PS, class Seg3>
+void interpolate3d_field(PS* ptcls, Seg3 x, View<fp_t> gridx, View<fp_t> gridy, View<fp_t> gridz, View<fp_t> data,
+                         View<fp_t>& out) {
+  if (out.size() < (size_t)x.stride()) out = View<fp_t>((size_t)x.stride(), 0.0, "gathered field");
+  pp_check(pp_gather_grid3d(ptcls->handle(), x.data(), x.stride(), data.data(), gridx.data(), gridy.data(),
+                            gridz.data(), (int32_t)gridx.size(), (int32_t)gridy.size(), (int32_t)gridz.size(),
+                            out.data(), (pp_stream)ptcls->stream()), "interpolate3d_field");
+}
+
 }  // namespace pumipic
 
 namespace ps = pumipic;

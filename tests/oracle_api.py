@@ -269,3 +269,47 @@ def set_unsafe_procs(mask, elems, safe, owner, self_rank):
                                _ip(np.ascontiguousarray(owner, np.int32)), C.c_int(self_rank),
                                _ip(ne), _ip(npr))
     return ne, npr
+
+
+# ---- gather (field interpolation) ----
+def gather_tet_field(om, mask, x, elem_ids, field, dof):
+    x = _f64(x); field = _f64(field)
+    out = np.zeros((dof, x.shape[1]), np.float64)
+    bad = lib().orc_gather_tet_field(om.h, C.c_int(mask.shape[0]), _u8(np.ascontiguousarray(mask, np.uint8)),
+                                     _dp(x), C.c_long(x.shape[1]), _ip(np.ascontiguousarray(elem_ids, np.int32)),
+                                     _dp(field), C.c_int(dof), _dp(out))
+    return out, int(bad)
+
+
+def interpolate2d_field(data, gridx0, gridz0, dx, dz, nx, nz, pos, cyl, ncomp=1, comp=0):
+    f = lib().orc_interpolate2d_field
+    f.restype = C.c_double
+    return f(_dp(_f64(data)), C.c_double(gridx0), C.c_double(gridz0), C.c_double(dx), C.c_double(dz),
+             C.c_int(nx), C.c_int(nz), _dp(_f64(pos)), C.c_int(int(cyl)), C.c_int(ncomp), C.c_int(comp))
+
+
+def gather_grid2d_vector(mask, x, data3, gridx0, gridz0, dx, dz, nx, nz, cyl):
+    x = _f64(x)
+    out = np.zeros((3, x.shape[1]), np.float64)
+    lib().orc_gather_grid2d_vector(C.c_int(mask.shape[0]), _u8(np.ascontiguousarray(mask, np.uint8)), _dp(x),
+                                   C.c_long(x.shape[1]), _dp(_f64(data3)), C.c_double(gridx0),
+                                   C.c_double(gridz0), C.c_double(dx), C.c_double(dz), C.c_int(nx),
+                                   C.c_int(nz), C.c_int(int(cyl)), _dp(out))
+    return out
+
+
+def interpolate3d_field(x, y, z, gridx, gridy, gridz, data):
+    f = lib().orc_interpolate3d_field
+    f.restype = C.c_double
+    return f(C.c_double(x), C.c_double(y), C.c_double(z), C.c_int(len(gridx)), C.c_int(len(gridy)),
+             C.c_int(len(gridz)), _dp(_f64(gridx)), _dp(_f64(gridy)), _dp(_f64(gridz)), _dp(_f64(data)))
+
+
+def gather_grid3d(mask, x, data, gridx, gridy, gridz):
+    x = _f64(x)
+    out = np.zeros(x.shape[1], np.float64)
+    lib().orc_gather_grid3d(C.c_int(mask.shape[0]), _u8(np.ascontiguousarray(mask, np.uint8)), _dp(x),
+                            C.c_long(x.shape[1]), _dp(_f64(data)), _dp(_f64(gridx)), _dp(_f64(gridy)),
+                            _dp(_f64(gridz)), C.c_int(len(gridx)), C.c_int(len(gridy)), C.c_int(len(gridz)),
+                            _dp(out))
+    return out
