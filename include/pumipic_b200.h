@@ -137,6 +137,20 @@ pp_status pp_host_picpart_tags(int32_t dim, int32_t nverts, int32_t nelems,
                                int32_t rank, int32_t buffer_method, int32_t safe_method,
                                int32_t buffer_layers, int32_t safe_layers, int32_t* safe_out,
                                int32_t* has_part_out);
+/* The sub-mesh of a partially buffered PICpart (constructPICPart, part_construct.cpp:116-262):
+ * elements whose owner's core is buffered here (has_part[owner] != 0, from pp_host_picpart_tags)
+ * and their vertices, both keeping their relative order in the full mesh (:182-195).
+ *   elem_l2g[nelems_l], vert_l2g[nverts_l]  full-mesh index of every local element / vertex
+ *   elem2verts_l[nelems_l*(dim+1)]          connectivity in local vertex numbers
+ *   coords_l[nverts_l*dim]
+ * Outputs are malloc'd; free with pp_host_free.  Tags (owner, safe, class) follow by indexing
+ * the full-mesh arrays with elem_l2g / vert_l2g (convertTag, :597-617). */
+pp_status pp_host_picpart_extract(int32_t dim, int32_t nverts, int32_t nelems, const double* coords,
+                                  const int32_t* elem2verts, const int32_t* owner, int32_t nranks,
+                                  const int32_t* has_part, int32_t* nelems_out,
+                                  int32_t** elem_l2g_out, int32_t* nverts_out,
+                                  int32_t** vert_l2g_out, int32_t** elem2verts_out,
+                                  double** coords_out);
 /* Owner of lower-dimensional entities = minimum owner of the adjacent elements
  * (defineOwners, part_construct.cpp:304-323).  elem2ents: [nelems*ents_per_elem]. */
 pp_status pp_host_entity_owners(int32_t nents, int32_t nelems, int32_t ents_per_elem,
@@ -419,6 +433,26 @@ pp_status pp_comm_group_end(void);
 pp_status pp_comm_array_reduce(pp_comm* comm, void* comm_array, int64_t nents, int32_t nvals,
                                int32_t dtype, int32_t op, const int32_t* ent_owner,
                                pp_stream stream);
+
+/* Mesh::reduceCommArray for partially buffered PICparts (src/pumipic_comm.cpp:249-439) with the
+ * set-up of Mesh::setupComm (:12-184).  A plan is built once per entity dimension from
+ *   ent_gids[nents]   global id of every entity of this PICpart (Mesh::globalIds(edim))
+ *   ent_owner[nents]  owning rank (Mesh::entOwners(edim))
+ * (memspace says where the two arrays live; collective: every rank calls it).  The owner of an
+ * entity must hold a copy of it.  pp_comm_plan_reduce then leaves, in every copy of every entity,
+ * the SUM / MAX / MIN over all copies, or for PP_BCAST the owner's value: copies are sent to the
+ * owner (fan in), merged there in ascending rank order (deterministic, unlike the reference's
+ * atomics) and sent back (fan out), all on device buffers over NCCL.
+ * comm_array: device [nents*nvals], entity-major (createCommArray, pumipic_comm.cpp:187-192). */
+typedef struct pp_comm_plan pp_comm_plan;
+pp_status pp_comm_plan_create(pp_comm* comm, int64_t nents, const int64_t* ent_gids,
+                              const int32_t* ent_owner, int32_t memspace, pp_stream stream,
+                              pp_comm_plan** out);
+pp_status pp_comm_plan_destroy(pp_comm_plan* plan);
+/* entities this rank sends to owners / receives as an owner per reduction */
+pp_status pp_comm_plan_counts(const pp_comm_plan* plan, int64_t* n_send, int64_t* n_recv);
+pp_status pp_comm_plan_reduce(pp_comm_plan* plan, void* comm_array, int32_t nvals, int32_t dtype,
+                              int32_t op, pp_stream stream);
 
 /* migrate (particle_structure.hpp:101-104; SCS_migrate.h:5-221): particles whose new_process is
  * another rank are packed (element sent as global id), exchanged all-to-all-v, mapped back to

@@ -86,6 +86,28 @@ def host_entity_owners(nents, elem2ents, elem_owner, nranks):
     return out
 
 
+def host_picpart_extract(dim, coords, elem2verts, owner, nranks, has_part):
+    """(elem_l2g, vert_l2g, elem2verts_local, coords_local) of the PICpart that buffers `has_part`."""
+    co = np.ascontiguousarray(coords, np.float64)
+    ev = np.ascontiguousarray(elem2verts, np.int32)
+    ow = np.ascontiguousarray(owner, np.int32)
+    hp = np.ascontiguousarray(has_part, np.int32)
+    ne, nv = C.c_int32(), C.c_int32()
+    el2g, vl2g, evl = capi.c_i32p(), capi.c_i32p(), capi.c_i32p()
+    col = capi.c_dp()
+    check(lib().pp_host_picpart_extract(dim, co.shape[0], ev.shape[0], co.ctypes.data_as(capi.c_dp),
+                                        ev.ctypes.data_as(capi.c_i32p), ow.ctypes.data_as(capi.c_i32p),
+                                        nranks, hp.ctypes.data_as(capi.c_i32p), C.byref(ne), C.byref(el2g),
+                                        C.byref(nv), C.byref(vl2g), C.byref(evl), C.byref(col)))
+    out = (np.ctypeslib.as_array(el2g, shape=(max(ne.value, 1),))[:ne.value].copy(),
+           np.ctypeslib.as_array(vl2g, shape=(max(nv.value, 1),))[:nv.value].copy(),
+           np.ctypeslib.as_array(evl, shape=(max(ne.value, 1), dim + 1))[:ne.value].copy(),
+           np.ctypeslib.as_array(col, shape=(max(nv.value, 1), dim))[:nv.value].copy())
+    for p in (el2g, vl2g, evl, col):
+        lib().pp_host_free(p)
+    return out
+
+
 # ------------------------------------------------------------------ mesh
 class Mesh:
     """pumipic::Mesh / o::Mesh stand-in: owns a pp_mesh built from host numpy arrays."""
@@ -449,6 +471,10 @@ class Comm:
                                          _ptr(ent_owner), _stream()))
         return arr
 
+    def plan(self, ent_gids, ent_owner):
+        """Owner fan-in / fan-out plan for comm arrays of a partially buffered PICpart."""
+        return CommPlan(self, ent_gids, ent_owner)
+
     def __del__(self):
         try:
             lib().pp_comm_destroy(self.h)
@@ -465,3 +491,31 @@ def migrate(ps, comm, new_element, new_process, new_particle_elements=None, new_
     check(lib().pp_ps_migrate(ps.h, comm.h, _ptr(new_element), _ptr(new_process), n_new,
                               _ptr(new_particle_elements), info, C.byref(st), _stream()))
     return st.sent, st.received
+
+
+class CommPlan:
+    """Mesh::setupComm + reduceCommArray for one entity dimension (pp_comm_plan_*)."""
+
+    def __init__(self, comm, ent_gids, ent_owner):
+        g = np.ascontiguousarray(ent_gids, np.int64)
+        o = np.ascontiguousarray(ent_owner, np.int32)
+        self.comm = comm
+        self.nents = g.shape[0]
+        self.h = C.c_void_p()
+        check(lib().pp_comm_plan_create(comm.h, g.shape[0], _np_ptr(g), _np_ptr(o), capi.PP_HOST, _stream(),
+                                        C.byref(self.h)))
+
+    def counts(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().pp_comm_plan_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def reduce(self, arr, nvals, op):
+        check(lib().pp_comm_plan_reduce(self.h, _ptr(arr), nvals, Comm._dtype(arr), op, _stream()))
+        return arr
+
+    def __del__(self):
+        try:
+            lib().pp_comm_plan_destroy(self.h)
+        except Exception:
+            pass

@@ -153,6 +153,16 @@ PROTOTYPES = {
     "pp_comm_group_end": (C.c_int, []),
     "pp_comm_array_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p]),
+    "pp_comm_plan_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pp_comm_plan_destroy": (C.c_int, [C.c_void_p]),
+    "pp_comm_plan_counts": (C.c_int, [C.c_void_p, c_i64p, c_i64p]),
+    "pp_comm_plan_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p]),
+    "pp_host_picpart_extract": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_dp, c_i32p, c_i32p,
+                                          C.c_int32, c_i32p, C.POINTER(C.c_int32),
+                                          C.POINTER(c_i32p), C.POINTER(C.c_int32), C.POINTER(c_i32p),
+                                          C.POINTER(c_i32p), C.POINTER(c_dp)]),
     "pp_ps_migrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(MigrateStats),
                                 C.c_void_p]),

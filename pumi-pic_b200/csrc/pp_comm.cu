@@ -10,6 +10,8 @@
 // NCCL is resolved at run time (dlopen "libnccl.so.2"): in a torch process that is the NCCL torch
 // already loaded, otherwise the system library.  Single-GPU use never touches it.
 #include <dlfcn.h>
+
+#include <algorithm>
 #include <nccl.h>
 
 #include <cub/cub.cuh>
@@ -492,4 +494,211 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
   pp_dev_free(d_sbo, s); pp_dev_free(d_rbo, s); pp_dev_free(cursor, s);
   pp_dev_free(d_recv_cnt, s); pp_dev_free(d_recv_off, s);
   return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// Mesh::reduceCommArray for partially buffered PICparts (pumipic_comm.cpp:249-439) and the
+// set-up half of Mesh::setupComm (:12-184).
+//
+// The reference renumbers every entity into a "bulk communication ordering" (whole cores first,
+// boundary entities by an atomic counter), stages the array through the host and exchanges one
+// MPI message per buffered core plus one per bounding part, merging with device atomics.  Here
+// the plan is a plain owner fan-in / fan-out over explicit index lists: for every peer p the
+// entities this rank holds that p owns (send list) and the entities this rank owns that p holds
+// (receive list), matched once by global id at set-up.  A reduction is pack -> grouped
+// ncclSend/ncclRecv over NVLink -> merge in ascending rank order (deterministic, no atomics) ->
+// pack -> send back -> unpack; nothing touches the host.
+// ------------------------------------------------------------------------------------------
+struct pp_comm_plan {
+  pp_comm* comm;
+  int64_t nents;
+  std::vector<int64_t> send_off, recv_off;   // [R+1], entity offsets per peer
+  int* d_send_idx;                           // local index of every entity to send, grouped by owner
+  int* d_recv_idx;                           // local index of every entity received, grouped by holder
+};
+
+namespace {
+template <class T>
+__global__ void k_plan_pack(const T* __restrict__ arr, const int* __restrict__ idx, long n, int nvals,
+                            T* __restrict__ buf) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n * nvals) return;
+  buf[i] = arr[(long)idx[i / nvals] * nvals + i % nvals];
+}
+template <class T>
+__global__ void k_plan_unpack(T* __restrict__ arr, const int* __restrict__ idx, long n, int nvals,
+                              const T* __restrict__ buf) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n * nvals) return;
+  arr[(long)idx[i / nvals] * nvals + i % nvals] = buf[i];
+}
+template <class T>
+__global__ void k_plan_merge(T* __restrict__ arr, const int* __restrict__ idx, long n, int nvals,
+                             const T* __restrict__ buf, int op) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n * nvals) return;
+  T* a = arr + (long)idx[i / nvals] * nvals + i % nvals;
+  const T x = *a, y = buf[i];
+  *a = op == PP_SUM ? x + y : op == PP_MAX ? (x < y ? y : x) : (y < x ? y : x);
+}
+
+template <class T>
+pp_status plan_reduce_t(pp_comm_plan* pl, T* arr, int nvals, int op, ncclDataType_t nt, cudaStream_t s) {
+  pp_comm* c = pl->comm;
+  const int R = c->nranks, me = c->rank;
+  const int64_t ns = pl->send_off[R], nr = pl->recv_off[R];
+  T *sbuf, *rbuf;
+  PP_TRY(pp_dev_alloc(&sbuf, (size_t)ns * nvals, s));
+  PP_TRY(pp_dev_alloc(&rbuf, (size_t)nr * nvals, s));
+  auto blocks = [&](int64_t n) { return pp_div_up(n * nvals, kBlock); };
+  if (op != PP_BCAST) {
+    // fan in: every copy goes to the owner of its entity
+    if (ns) k_plan_pack<<<blocks(ns), kBlock, 0, s>>>(arr, pl->d_send_idx, ns, nvals, sbuf);
+    PP_KERNEL_CHECK();
+    PP_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < R; ++p) {
+      if (p == me) continue;
+      const int64_t a = pl->send_off[p], b = pl->send_off[p + 1];
+      if (b > a) PP_NCCL(g_nccl.Send(sbuf + a * nvals, (size_t)(b - a) * nvals, nt, p, c->comm, s));
+      const int64_t ra = pl->recv_off[p], rb = pl->recv_off[p + 1];
+      if (rb > ra) PP_NCCL(g_nccl.Recv(rbuf + ra * nvals, (size_t)(rb - ra) * nvals, nt, p, c->comm, s));
+    }
+    PP_NCCL(g_nccl.GroupEnd());
+    for (int p = 0; p < R; ++p) {          // ascending rank order: bit-reproducible sums
+      const int64_t ra = pl->recv_off[p], rb = pl->recv_off[p + 1];
+      if (rb > ra)
+        k_plan_merge<<<blocks(rb - ra), kBlock, 0, s>>>(arr, pl->d_recv_idx + ra, rb - ra, nvals,
+                                                        rbuf + ra * nvals, op);
+    }
+    PP_KERNEL_CHECK();
+  }
+  // fan out: the owner's value (the total) goes back to every copy
+  if (nr) k_plan_pack<<<blocks(nr), kBlock, 0, s>>>(arr, pl->d_recv_idx, nr, nvals, rbuf);
+  PP_KERNEL_CHECK();
+  PP_NCCL(g_nccl.GroupStart());
+  for (int p = 0; p < R; ++p) {
+    if (p == me) continue;
+    const int64_t ra = pl->recv_off[p], rb = pl->recv_off[p + 1];
+    if (rb > ra) PP_NCCL(g_nccl.Send(rbuf + ra * nvals, (size_t)(rb - ra) * nvals, nt, p, c->comm, s));
+    const int64_t a = pl->send_off[p], b = pl->send_off[p + 1];
+    if (b > a) PP_NCCL(g_nccl.Recv(sbuf + a * nvals, (size_t)(b - a) * nvals, nt, p, c->comm, s));
+  }
+  PP_NCCL(g_nccl.GroupEnd());
+  if (ns) k_plan_unpack<<<blocks(ns), kBlock, 0, s>>>(arr, pl->d_send_idx, ns, nvals, sbuf);
+  PP_KERNEL_CHECK();
+  pp_dev_free(sbuf, s); pp_dev_free(rbuf, s);
+  return PP_OK;
+}
+}  // namespace
+
+extern "C" pp_status pp_comm_plan_create(pp_comm* c, int64_t nents, const int64_t* ent_gids,
+                                         const int32_t* ent_owner, int32_t memspace, pp_stream stream,
+                                         pp_comm_plan** out) {
+  PP_REQUIRE(c && out && nents >= 0 && (nents == 0 || (ent_gids && ent_owner)), "bad argument");
+  PP_REQUIRE(nents < (int64_t)1 << 31, "too many entities");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int R = c->nranks, me = c->rank;
+  pp_comm_plan* pl = new pp_comm_plan();
+  pl->comm = c; pl->nents = nents; pl->d_send_idx = nullptr; pl->d_recv_idx = nullptr;
+  pl->send_off.assign(R + 1, 0); pl->recv_off.assign(R + 1, 0);
+  *out = pl;
+  if (R == 1) return PP_OK;
+  std::vector<int64_t> gid((size_t)nents);
+  std::vector<int32_t> own((size_t)nents);
+  if (nents) {
+    const cudaMemcpyKind k = memspace == PP_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost;
+    PP_CUDA(cudaMemcpyAsync(gid.data(), ent_gids, sizeof(int64_t) * nents, k, s));
+    PP_CUDA(cudaMemcpyAsync(own.data(), ent_owner, sizeof(int32_t) * nents, k, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+  }
+  // send lists: my copies of entities owned elsewhere, grouped by owner, ascending gid
+  std::vector<std::vector<std::pair<int64_t, int>>> bucket(R);
+  std::vector<std::pair<int64_t, int>> mine;
+  for (int64_t i = 0; i < nents; ++i) {
+    PP_REQUIRE(own[i] >= 0 && own[i] < R, "entity owner out of range");
+    (own[i] == me ? mine : bucket[own[i]]).push_back({gid[i], (int)i});
+  }
+  std::sort(mine.begin(), mine.end());
+  std::vector<int> send_idx, h_cnt(R, 0);
+  std::vector<int64_t> send_gid;
+  for (int p = 0; p < R; ++p) {
+    std::sort(bucket[p].begin(), bucket[p].end());
+    h_cnt[p] = (int)bucket[p].size();
+    pl->send_off[p + 1] = pl->send_off[p] + h_cnt[p];
+    for (auto& e : bucket[p]) { send_gid.push_back(e.first); send_idx.push_back(e.second); }
+  }
+  // counts to everybody
+  int *d_cnt, *d_all;
+  PP_TRY(pp_dev_alloc(&d_cnt, R, s));
+  PP_TRY(pp_dev_alloc(&d_all, (size_t)R * R, s));
+  PP_CUDA(cudaMemcpyAsync(d_cnt, h_cnt.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s));
+  PP_NCCL(g_nccl.AllGather(d_cnt, d_all, (size_t)R, ncclInt32, c->comm, s));
+  std::vector<int> h_all((size_t)R * R);
+  PP_CUDA(cudaMemcpyAsync(h_all.data(), d_all, sizeof(int) * R * R, cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  for (int p = 0; p < R; ++p) pl->recv_off[p + 1] = pl->recv_off[p] + h_all[(size_t)p * R + me];
+  const int64_t ns = pl->send_off[R], nr = pl->recv_off[R];
+  // global ids of what every holder will send me
+  long long *d_sg, *d_rg;
+  PP_TRY(pp_dev_alloc(&d_sg, (size_t)ns, s));
+  PP_TRY(pp_dev_alloc(&d_rg, (size_t)nr, s));
+  if (ns) PP_CUDA(cudaMemcpyAsync(d_sg, send_gid.data(), sizeof(int64_t) * ns, cudaMemcpyHostToDevice, s));
+  PP_NCCL(g_nccl.GroupStart());
+  for (int p = 0; p < R; ++p) {
+    if (p == me) continue;
+    const int64_t a = pl->send_off[p], b = pl->send_off[p + 1];
+    if (b > a) PP_NCCL(g_nccl.Send(d_sg + a, (size_t)(b - a), ncclInt64, p, c->comm, s));
+    const int64_t ra = pl->recv_off[p], rb = pl->recv_off[p + 1];
+    if (rb > ra) PP_NCCL(g_nccl.Recv(d_rg + ra, (size_t)(rb - ra), ncclInt64, p, c->comm, s));
+  }
+  PP_NCCL(g_nccl.GroupEnd());
+  std::vector<int64_t> recv_gid((size_t)nr);
+  if (nr) PP_CUDA(cudaMemcpyAsync(recv_gid.data(), d_rg, sizeof(int64_t) * nr, cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  pp_dev_free(d_cnt, s); pp_dev_free(d_all, s); pp_dev_free(d_sg, s); pp_dev_free(d_rg, s);
+  std::vector<int> recv_idx((size_t)nr);
+  for (int64_t k = 0; k < nr; ++k) {
+    auto it = std::lower_bound(mine.begin(), mine.end(), std::make_pair(recv_gid[k], -1));
+    if (it == mine.end() || it->first != recv_gid[k]) {
+      pp_set_error("pp_comm_plan_create: rank %d received entity gid %lld that it does not own", me,
+                   (long long)recv_gid[k]);
+      return PP_ERR_INVALID;
+    }
+    recv_idx[k] = it->second;
+  }
+  PP_CUDA(cudaMalloc(&pl->d_send_idx, sizeof(int) * (size_t)(ns ? ns : 1)));
+  PP_CUDA(cudaMalloc(&pl->d_recv_idx, sizeof(int) * (size_t)(nr ? nr : 1)));
+  if (ns) PP_CUDA(cudaMemcpy(pl->d_send_idx, send_idx.data(), sizeof(int) * ns, cudaMemcpyHostToDevice));
+  if (nr) PP_CUDA(cudaMemcpy(pl->d_recv_idx, recv_idx.data(), sizeof(int) * nr, cudaMemcpyHostToDevice));
+  return PP_OK;
+}
+
+extern "C" pp_status pp_comm_plan_destroy(pp_comm_plan* pl) {
+  if (!pl) return PP_OK;
+  if (pl->d_send_idx) cudaFree(pl->d_send_idx);
+  if (pl->d_recv_idx) cudaFree(pl->d_recv_idx);
+  delete pl;
+  return PP_OK;
+}
+
+extern "C" pp_status pp_comm_plan_counts(const pp_comm_plan* pl, int64_t* n_send, int64_t* n_recv) {
+  PP_REQUIRE(pl, "null plan");
+  if (n_send) *n_send = pl->send_off.back();
+  if (n_recv) *n_recv = pl->recv_off.back();
+  return PP_OK;
+}
+
+extern "C" pp_status pp_comm_plan_reduce(pp_comm_plan* pl, void* comm_array, int32_t nvals, int32_t dtype,
+                                         int32_t op, pp_stream stream) {
+  PP_REQUIRE(pl && (comm_array || pl->nents == 0) && nvals >= 1, "bad argument");
+  PP_REQUIRE(op == PP_SUM || op == PP_MAX || op == PP_MIN || op == PP_BCAST, "unknown reduction");
+  if (pl->comm->nranks == 1) return PP_OK;     // pumipic_comm.cpp:232-233
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case PP_INT32: return plan_reduce_t(pl, (int*)comm_array, nvals, op, ncclInt32, s);
+    case PP_INT64: return plan_reduce_t(pl, (long long*)comm_array, nvals, op, ncclInt64, s);
+    case PP_FLOAT32: return plan_reduce_t(pl, (float*)comm_array, nvals, op, ncclFloat32, s);
+    case PP_FLOAT64: return plan_reduce_t(pl, (double*)comm_array, nvals, op, ncclFloat64, s);
+    default: pp_set_error("unknown pp_dtype %d", dtype); return PP_ERR_INVALID;
+  }
 }

@@ -5,6 +5,7 @@
 // reference also runs on the host side of Omega_h; sub-mesh extraction for non-full PICparts is a
 // "next" row.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -108,5 +109,64 @@ extern "C" pp_status pp_host_entity_owners(int32_t nents, int32_t nelems, int32_
       const int x = elem2ents[(int64_t)e * ents_per_elem + k];
       if (elem_owner[e] < ent_owner_out[x]) ent_owner_out[x] = elem_owner[e];
     }
+  return PP_OK;
+}
+
+// Sub-mesh extraction for a partially buffered PICpart (constructPICPart,
+// part_construct.cpp:116-262): the elements whose owner's core is buffered here stay
+// (setSafeEnts :467-489), entities keep their relative order (offset_scan of the keep flags,
+// :182-195), vertices are the vertices of the kept elements, coordinates are gathered
+// (gatherCoords :499-511).  Output arrays are malloc'd; free with pp_host_free.
+extern "C" pp_status pp_host_picpart_extract(int32_t dim, int32_t nverts, int32_t nelems,
+                                             const double* coords, const int32_t* elem2verts,
+                                             const int32_t* owner, int32_t nranks,
+                                             const int32_t* has_part, int32_t* nelems_out,
+                                             int32_t** elem_l2g_out, int32_t* nverts_out,
+                                             int32_t** vert_l2g_out, int32_t** elem2verts_out,
+                                             double** coords_out) {
+  if (!(dim == 2 || dim == 3) || !coords || !elem2verts || !owner || !has_part || !nelems_out ||
+      !elem_l2g_out || !nverts_out || !vert_l2g_out || !elem2verts_out || !coords_out || nranks < 1) {
+    pp_set_error("pp_host_picpart_extract: bad argument");
+    return PP_ERR_INVALID;
+  }
+  const int nv = dim + 1;
+  std::vector<int> vkeep(nverts, 0);
+  int ne_l = 0;
+  for (int e = 0; e < nelems; ++e) {
+    if (owner[e] < 0 || owner[e] >= nranks) {
+      pp_set_error("pp_host_picpart_extract: element %d has owner %d outside [0,%d)", e, owner[e], nranks);
+      return PP_ERR_INVALID;
+    }
+    if (!has_part[owner[e]]) continue;
+    ++ne_l;
+    for (int k = 0; k < nv; ++k) vkeep[elem2verts[(int64_t)e * nv + k]] = 1;
+  }
+  std::vector<int> vnum(nverts, -1);
+  int nv_l = 0;
+  for (int v = 0; v < nverts; ++v)
+    if (vkeep[v]) vnum[v] = nv_l++;
+  int32_t* el2g = (int32_t*)malloc(sizeof(int32_t) * (size_t)(ne_l > 0 ? ne_l : 1));
+  int32_t* vl2g = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nv_l > 0 ? nv_l : 1));
+  int32_t* ev = (int32_t*)malloc(sizeof(int32_t) * (size_t)(ne_l > 0 ? ne_l : 1) * nv);
+  double* co = (double*)malloc(sizeof(double) * (size_t)(nv_l > 0 ? nv_l : 1) * dim);
+  if (!el2g || !vl2g || !ev || !co) {
+    free(el2g); free(vl2g); free(ev); free(co);
+    pp_set_error("pp_host_picpart_extract: out of memory");
+    return PP_ERR_NOMEM;
+  }
+  int j = 0;
+  for (int e = 0; e < nelems; ++e) {
+    if (!has_part[owner[e]]) continue;
+    el2g[j] = e;
+    for (int k = 0; k < nv; ++k) ev[(int64_t)j * nv + k] = vnum[elem2verts[(int64_t)e * nv + k]];
+    ++j;
+  }
+  for (int v = 0; v < nverts; ++v)
+    if (vkeep[v]) {
+      vl2g[vnum[v]] = v;
+      for (int d = 0; d < dim; ++d) co[(int64_t)vnum[v] * dim + d] = coords[(int64_t)v * dim + d];
+    }
+  *nelems_out = ne_l; *elem_l2g_out = el2g; *nverts_out = nv_l; *vert_l2g_out = vl2g;
+  *elem2verts_out = ev; *coords_out = co;
   return PP_OK;
 }

@@ -6,6 +6,7 @@ Checks, following particle_structs/test/test_migrate.cpp and test/test_comm_arra
   2. comm-array reductions: SUM of ones == nranks, MIN of owners, BCAST owner's value
   3. a full PIC loop (fused push+search -> setUnsafeProcs -> migrate) on a block-partitioned
      Kuhn cube: the union over ranks of (particle id -> element) must equal the serial CPU oracle
+  4. the same loop and the comm-array reductions on partially buffered PICparts (sub-meshes)
 """
 import importlib
 import os
@@ -216,6 +217,124 @@ def test_pic_loop(P, comm, rank, R, steps=6):
               % (R, len(alive), nptcl))
 
 
+def test_partial_picparts(P, comm, rank, R, steps=6):
+    """Partially buffered PICparts (Input BFS buffer / BFS safe, part_construct.cpp:116-262): every
+    rank holds only its core and the cores within 3 BFS layers, as a renumbered sub-mesh.  Checks
+    (a) Mesh::reduceCommArray's owner fan-in / fan-out (pumipic_comm.cpp:249-439) through
+    pp_comm_plan_* against numpy on the gathered copies, (b) the PIC loop with migration by global
+    element id against the serial oracle on the full mesh, by particle id, bit-exact."""
+    n = 16
+    mesh = kuhn_cube(n)
+    ne = mesh.nelems
+    cen = mesh.coords[mesh.elem2verts].mean(axis=1)
+    owner = np.minimum((cen[:, 0] * R).astype(np.int32), R - 1)          # slabs along x
+    safe_g, part = P.host_picpart_tags(3, mesh.nverts, mesh.elem2verts, owner, R, rank,
+                                       P.api.BFS, P.api.BFS, 3, 1)
+    if R >= 4:
+        assert part.sum() < R, "slabs 4 cells wide: 3 BFS layers must not reach the second neighbour"
+    el2g, vl2g, evl, col = P.host_picpart_extract(3, mesh.coords, mesh.elem2verts, owner, R, part)
+    e2s, s2v = P.host_derive_sides(3, evl)
+    gm = P.Mesh(3, col, evl, e2s, s2v, np.ones(len(el2g), np.int32))
+    gm.set_picpart(safe_g[el2g], owner[el2g], rank)
+    # ---- (a) vertex comm array over the plan
+    vo_g = P.host_entity_owners(mesh.nverts, mesh.elem2verts, owner, R)
+    plan = comm.plan(vl2g.astype(np.int64) * 5 + 3, vo_g[vl2g])           # non-trivial global ids
+    nv = 2
+    holders = gather_np(vl2g)
+    nh = np.zeros(mesh.nverts)
+    for h in holders:
+        nh[h] += 1
+    ns, nr = plan.counts()
+    assert ns == int((vo_g[vl2g] != rank).sum())
+    assert nr == int((nh[vl2g][vo_g[vl2g] == rank] - 1).sum())
+    base = (np.arange(len(vl2g) * nv) % 7) * 0.125
+    for dt in (torch.float64, torch.int32):
+        mine_v = (np.repeat(vl2g, nv) % 13 + 10.0 * rank + (base if dt == torch.float64 else 0))
+        vals = gather_np(mine_v)
+        for op, red in ((P.capi.PP_SUM, np.add), (P.capi.PP_MAX, np.maximum), (P.capi.PP_MIN, np.minimum)):
+            want = np.full(mesh.nverts * nv, np.nan)
+            for h, v in zip(holders, vals):        # ascending rank order, like the plan's merge
+                idx = (np.repeat(h, nv) * nv + np.tile(np.arange(nv), len(h)))
+                cur = want[idx]
+                want[idx] = np.where(np.isnan(cur), v, red(cur, v))
+            arr = torch.as_tensor(mine_v).to(dt).cuda()
+            plan.reduce(arr, nv, op)
+            idx = (np.repeat(vl2g, nv) * nv + np.tile(np.arange(nv), len(vl2g)))
+            got = arr.cpu().numpy().astype(np.float64)
+            if op == P.capi.PP_SUM and dt == torch.float64 and R > 2:
+                # the owner adds its own value first, then the others in rank order
+                assert np.allclose(got, want[idx], rtol=1e-14, atol=0)
+            else:
+                assert np.array_equal(got, want[idx]), (op, dt)
+        arr = torch.as_tensor(mine_v).to(dt).cuda()
+        plan.reduce(arr, nv, P.capi.PP_BCAST)
+        own_val = np.repeat(vl2g, nv) % 13 + 10.0 * np.repeat(vo_g[vl2g], nv)
+        got = arr.cpu().numpy().astype(np.float64)
+        if dt == torch.float64:
+            # the owner's `base` term is indexed by the owner's local numbering: fetch it from there
+            want = np.full(mesh.nverts * nv, np.nan)
+            for r_, (h, v) in enumerate(zip(holders, vals)):
+                sel = np.repeat(vo_g[h] == r_, nv)
+                idx_h = (np.repeat(h, nv) * nv + np.tile(np.arange(nv), len(h)))
+                want[idx_h[sel]] = v[sel]
+            assert np.array_equal(got, want[idx])
+        else:
+            assert np.array_equal(got, own_val)
+    # ---- (b) PIC loop on the sub-mesh, particles migrate by global element id
+    nptcl = 60000
+    ppe_g = pi.even_ppe(ne, nptcl)
+    slot_elem_g = np.repeat(np.arange(ne, dtype=np.int32), ppe_g)
+    mask_g = np.ones(nptcl, np.uint8)
+    X, D = pi.init3d_internal(mesh, slot_elem_g, mask_g)
+    dist_push = pi.push_distance(mesh) * 2.5
+    g2l = np.full(ne, -1, np.int32)
+    g2l[el2g] = np.arange(len(el2g), dtype=np.int32)
+    mine = owner[slot_elem_g] == rank
+    pel = g2l[slot_elem_g[mine]]
+    assert (pel >= 0).all()
+    info = [X[:, mine], np.zeros((3, mine.sum())), np.nonzero(mine)[0].astype(np.int32).reshape(1, -1),
+            D[:, mine]]
+    ppe = np.bincount(pel, minlength=len(el2g)).astype(np.int32)
+    ps = P.ParticleStructure(P.capi.PP_PS_SCS, PIC, ppe, elem_gids=el2g.astype(np.int64),
+                             particle_elements=pel, particle_info=info)
+    om = orc.OracleMesh(mesh)
+    Xo = X.copy(); ids_o = None
+    migrated = 0
+    safe_l, owner_l = safe_g[el2g], owner[el2g]
+    for it in range(steps):
+        cap = ps.capacity
+        x, tg, dr = ps.get(0), ps.get(1), ps.get(3)
+        ids = torch.zeros(max(cap, 1), dtype=torch.int32, device="cuda")
+        P.push_direction_search(gm, ps, dr, dist_push, x, tg, ids, elem_ids_empty=True, from_orig=True)
+        P.update_positions(ps, x, tg)
+        ne_d, np_d = P.set_unsafe_procs(gm, ps, ids)
+        sent, recv = P.migrate(ps, comm, ne_d, np_d)
+        migrated += sent
+        To = Xo + dist_push * D
+        found, ids_o, _, _, st = om.search_mesh(slot_elem_g if ids_o is None else np.maximum(ids_o, 0),
+                                                (mask_g if ids_o is None else (ids_o >= 0).astype(np.uint8)),
+                                                Xo, To)
+        Xo = To
+        se, m = ps.slot_elem_and_mask(); m = m.astype(bool)
+        pids = ps.get(2).cpu().numpy()[0, :ps.capacity][m]
+        xs = ps.get(0).cpu().numpy()[:, :ps.capacity][:, m]
+        got = {}
+        for d in gather_np((pids, el2g[se[m]], xs)):
+            for i, e, xx in zip(d[0].tolist(), d[1].tolist(), d[2].T):
+                assert i not in got, "particle %d lives on two ranks" % i
+                got[i] = (e, xx)
+        alive = np.nonzero(ids_o >= 0)[0]
+        assert sorted(got) == alive.tolist(), "particle set differs from the serial oracle"
+        for i in alive[:: max(1, len(alive) // 3000)]:
+            assert got[i][0] == ids_o[i] and np.array_equal(got[i][1], Xo[:, i])
+        assert np.all((safe_l[se[m]] == 1) | (owner_l[se[m]] == rank))
+    tot = sum(gather_np(migrated))
+    assert R == 1 or tot > 0
+    if rank == 0:
+        print("partial PICparts ok on %d ranks: %d local of %d elements, %d particles migrated"
+              % (R, len(el2g), ne, tot))
+
+
 def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -227,6 +346,7 @@ def main():
     test_comm_array(P, comm, rank, R)
     test_migrate(P, comm, rank, R)
     test_pic_loop(P, comm, rank, R)
+    test_partial_picparts(P, comm, rank, R)
     dist.barrier()
     if rank == 0:
         print("MGPU_OK")

@@ -166,3 +166,29 @@ def test_two_rank_protocol_on_gloo():
     for p in procs:
         p.join(timeout=30)
     assert all(r[1] == "ok" for r in res), res
+
+
+def test_picpart_extract_matches_numpy_twin():
+    """constructPICPart's sub-mesh (part_construct.cpp:116-262): kept elements and their vertices in
+    full-mesh order, local connectivity, gathered coordinates; slabs so that far cores are dropped."""
+    pp = importlib.import_module("pumi-pic_b200")
+    for mesh in (kuhn_cube(8), plate(32)):
+        cen = mesh.coords[mesh.elem2verts].mean(axis=1)
+        nranks = 4
+        owner = np.minimum((cen[:, 0] * nranks).astype(np.int32), nranks - 1)
+        for rank in range(nranks):
+            safe, part = pp.host_picpart_tags(mesh.dim, mesh.nverts, mesh.elem2verts, owner, nranks, rank,
+                                              pp.api.BFS, pp.api.BFS, 1, 1)
+            assert part[rank] == 1 and part.sum() < nranks          # partially buffered
+            el2g, vl2g, evl, col = pp.host_picpart_extract(mesh.dim, mesh.coords, mesh.elem2verts, owner,
+                                                           nranks, part)
+            keep = part[owner].astype(bool)
+            assert np.array_equal(el2g, np.nonzero(keep)[0])
+            assert np.array_equal(vl2g, np.unique(mesh.elem2verts[keep]))
+            assert np.array_equal(vl2g[evl], mesh.elem2verts[keep])
+            assert np.array_equal(col, mesh.coords[vl2g])
+            # the local mesh is a valid simplicial mesh for the search: sides can be derived
+            e2s, s2v = pp.host_derive_sides(mesh.dim, evl)
+            assert e2s.shape == evl.shape and s2v.max() < len(vl2g)
+            # every safe element is kept, and the kept set is core + whole neighbouring cores
+            assert keep[safe.astype(bool)].all()
