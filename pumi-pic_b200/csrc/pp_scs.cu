@@ -10,6 +10,8 @@
 // particle in one kernel (the reference launches one gather/scatter kernel per member type);
 // (3) the per-32-slot `tile_slice` table lets any kernel map slot -> row without the
 // slice-per-team launch shape of SellCSigma::parallel_for.
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "pp_internal.cuh"
@@ -32,11 +34,20 @@ struct ScsLayout {
   long mask_words = 0;
 };
 
+// grid-stride, one atomic per block: per-warp atomics on one address serialise (25 us for 1 M elements)
 __global__ void k_count_nonzero(const int* __restrict__ a, int n, int* out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool nz = i < n && a[i] > 0;
-  const unsigned m = __ballot_sync(0xffffffffu, nz);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
+  __shared__ int part[kBlock / 32];
+  int cnt = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    cnt += a[i] > 0;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kBlock / 32; ++w) t += part[w];
+    if (t) atomicAdd(out, t);
+  }
 }
 
 // sigmaSort keys: ascending particle count inside windows of `sigma` elements (stable)
@@ -65,21 +76,33 @@ __global__ void k_rows(const int* __restrict__ sorted_elem, const int* __restric
 }
 
 // chunk width = widest row; cw[0]=sum, cw[1]=count of non-empty chunks; inv = sum of 1/width.
-// One warp per chunk (lanes stride over the C rows).
+// One warp per chunk (lanes stride over the C rows), warps stride over the chunks and keep their
+// partial sums in registers: three atomics per block instead of three per chunk.
 __global__ void k_chunk_widths(const int* __restrict__ row_ppe, int nchunks, int C, int* width,
                                int* cw, double* inv) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ int p_sum[kBlock / 32], p_cnt[kBlock / 32];
+  __shared__ double p_inv[kBlock / 32];
   const int lane = threadIdx.x & 31;
-  if (c >= nchunks) return;
-  int w = 0;
-  for (int r = lane; r < C; r += 32) w = max(w, row_ppe[(long)c * C + r]);
-  w = __reduce_max_sync(0xffffffffu, w);
-  if (lane == 0) {
-    width[c] = w;
-    if (w > 0) {
-      atomicAdd(cw, w);
-      atomicAdd(cw + 1, 1);
-      atomicAdd(inv, 1.0 / w);
+  const int wid = threadIdx.x >> 5;
+  int sum = 0, cnt = 0;
+  double isum = 0.0;
+  for (long c = blockIdx.x * (long)(kBlock / 32) + wid; c < nchunks; c += (long)gridDim.x * (kBlock / 32)) {
+    int w = 0;
+    for (int r = lane; r < C; r += 32) w = max(w, row_ppe[c * C + r]);
+    w = __reduce_max_sync(0xffffffffu, w);
+    if (lane == 0) {
+      width[c] = w;
+      if (w > 0) { sum += w; cnt += 1; isum += 1.0 / w; }
+    }
+  }
+  if (lane == 0) { p_sum[wid] = sum; p_cnt[wid] = cnt; p_inv[wid] = isum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kBlock / 32; ++w) { sum += p_sum[w]; cnt += p_cnt[w]; isum += p_inv[w]; }
+    if (cnt) {
+      atomicAdd(cw, sum);
+      atomicAdd(cw + 1, cnt);
+      atomicAdd(inv, isum);
     }
   }
 }
@@ -725,7 +748,7 @@ pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, long n
   PP_CUDA(cudaMemsetAsync(scal, 0, 4 * sizeof(int), s));
   PP_CUDA(cudaMemsetAsync(inv, 0, sizeof(double), s));
   // chooseChunkHeight (SCS_buildFns.h:4-16)
-  k_count_nonzero<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(ppe_dev, ne, scal + 2);
+  k_count_nonzero<<<std::min(pp_div_up(ne, kBlock), 1184), kBlock, 0, s>>>(ppe_dev, ne, scal + 2);
   int nnz = 0;
   PP_CUDA(cudaMemcpyAsync(&nnz, scal + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
   PP_CUDA(cudaStreamSynchronize(s));
@@ -770,7 +793,7 @@ pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, long n
   PP_TRY(pp_dev_alloc(&width, L.nchunks, s));
   PP_TRY(pp_dev_alloc(&spc, L.nchunks + 1, s));
   PP_TRY(pp_dev_alloc(&slice_off, L.nchunks + 1, s));
-  k_chunk_widths<<<pp_div_up((long)L.nchunks * 32, kBlock), kBlock, 0, s>>>(L.row_ppe, L.nchunks, C, width, scal, inv);
+  k_chunk_widths<<<std::min(pp_div_up((long)L.nchunks * 32, kBlock), 1184), kBlock, 0, s>>>(L.row_ppe, L.nchunks, C, width, scal, inv);
   if (cfg.shuffle_padding > 0)
     k_pad_widths<<<pp_div_up(L.nchunks, kBlock), kBlock, 0, s>>>(width, L.nchunks, scal, inv,
                                                                  cfg.shuffle_padding, cfg.padding_strat);
