@@ -157,6 +157,102 @@ pp_status pp_host_entity_owners(int32_t nents, int32_t nelems, int32_t ents_per_
                                 const int32_t* elem2ents, const int32_t* elem_owner,
                                 int32_t nranks, int32_t* ent_owner_out);
 
+/* ---- host mesh with every entity dimension, and the Omega_h `.osh` format ----
+ * What the reference holds in an Omega_h::Mesh on the set-up side: vertices, edges, faces,
+ * elements, the d -> d-1 adjacency with alignment codes, and named tags per dimension.
+ * Entities are numbered exactly as in the file (Omega_h's numbering). */
+typedef struct pp_host_mesh pp_host_mesh;
+typedef enum pp_host_tag_type { PP_TAG_I8 = 0, PP_TAG_I32 = 2, PP_TAG_I64 = 3, PP_TAG_F64 = 5 } pp_host_tag_type;
+typedef struct pp_host_tag {
+  const char* name;   /* owned by the mesh */
+  int32_t ncomps;
+  int32_t type;       /* pp_host_tag_type (Omega_h's type codes) */
+  int64_t nvalues;    /* nents * ncomps */
+  const void* data;   /* owned by the mesh */
+} pp_host_tag;
+/* Omega_h::binary::read(path, comm) of a serial `.osh` directory (test/test_file.cpp:24,
+ * src/pumipic_file.cpp:135). */
+pp_status pp_host_mesh_read_osh(const char* path, pp_host_mesh** out);
+/* Omega_h::binary::write(path, mesh) (src/pumipic_file.cpp:69). */
+pp_status pp_host_mesh_write_osh(const pp_host_mesh* mesh, const char* path);
+/* Omega_h::build_from_elems2verts: faces / edges derived from the elements (numbered by sorted
+ * vertex tuple, vertex order of the last use), "global" and "coordinates" tags added. */
+pp_status pp_host_mesh_from_elems(int32_t dim, int32_t nverts, const double* coords,
+                                  int32_t nelems, const int32_t* elem2verts, pp_host_mesh** out);
+void pp_host_mesh_destroy(pp_host_mesh* mesh);
+int32_t pp_host_mesh_dim(const pp_host_mesh* mesh);
+int32_t pp_host_mesh_nents(const pp_host_mesh* mesh, int32_t d);          /* Mesh::nents(d) */
+const int32_t* pp_host_mesh_down(const pp_host_mesh* mesh, int32_t d);    /* ask_down(d,d-1).ab2b */
+const int8_t* pp_host_mesh_codes(const pp_host_mesh* mesh, int32_t d);    /* ask_down(d,d-1).codes */
+const int32_t* pp_host_mesh_ent2verts(const pp_host_mesh* mesh, int32_t d); /* ask_verts_of(d) */
+const double* pp_host_mesh_coords(const pp_host_mesh* mesh);              /* Mesh::coords() */
+int32_t pp_host_mesh_ntags(const pp_host_mesh* mesh, int32_t d);
+pp_status pp_host_mesh_tag_at(const pp_host_mesh* mesh, int32_t d, int32_t i, pp_host_tag* out);
+pp_status pp_host_mesh_find_tag(const pp_host_mesh* mesh, int32_t d, const char* name,
+                                pp_host_tag* out);
+/* Mesh::add_tag / set_tag; data holds nents(d) * ncomps values and is copied. */
+pp_status pp_host_mesh_set_tag(pp_host_mesh* mesh, int32_t d, const char* name, int32_t ncomps,
+                               int32_t type, const void* data);
+/* Partition files of pumipic::Input (src/pumipic_input.cpp:44-89): `.ptn` (owner per element)
+ * or `.cpn` (owner per class id; elem_class = the elements' class_id tag, else NULL). */
+pp_status pp_host_read_partition(const char* path, int32_t nelems, const int32_t* elem_class,
+                                 int32_t* owner_out);
+
+/* ---- PICpart construction and `.ppm` files --------------------------------
+ * pumipic::Mesh(Input&) (src/pumipic_part_construct.cpp:73-262) + Mesh::setupComm
+ * (src/pumipic_comm.cpp:12-184) + the safe-zone overlap regions of ParticleBalancer
+ * (src/pumipic_lb.cpp:23-82) for rank `rank` of `nranks`.  Like the reference, every rank starts
+ * from the full mesh loaded in serial; unlike it, nothing is exchanged: what the peers would
+ * send (boundary entity lists, safe flags, sbar tables) is a function of the same full mesh and
+ * partition and is evaluated locally.  Entities owned by a part of which only a boundary is
+ * held get their rank-local ids in ascending entity order (the reference takes them from
+ * atomics, any order being valid, pumipic_comm.cpp:66-75).
+ * Methods: 0 FULL, 1 BFS, 2 MINIMUM, 3 NONE (pumipic_input.hpp:33-39); layers < 0 = the defaults
+ * (buffer 3, safe 1, pumipic_input.cpp:103-110). */
+typedef struct pp_host_picpart pp_host_picpart;
+pp_status pp_host_picpart_build(const pp_host_mesh* full, const int32_t* elem_owner,
+                                int32_t nranks, int32_t rank, int32_t buffer_method,
+                                int32_t safe_method, int32_t buffer_layers, int32_t safe_layers,
+                                pp_host_picpart** out);
+void pp_host_picpart_destroy(pp_host_picpart* pp);
+/* The PICpart's own mesh (Mesh::mesh()), with the tags the reference puts on it: "ownership"
+ * (entOwners), "gids" (globalIds), "rank_lids" (rankLocalIndex), "global" (index in the full
+ * mesh) on every dimension, "safe" (safeTag) and "sbar_id" (ParticleBalancer::getSbarIDs) on
+ * elements.  Owned by the PICpart. */
+const pp_host_mesh* pp_host_picpart_mesh(const pp_host_picpart* pp);
+typedef struct pp_host_picpart_dim {
+  int64_t num_entities;                 /* Mesh::nents of the full mesh                      */
+  int32_t nents;                        /* entities of this dimension in the PICpart         */
+  int32_t num_cores;                    /* numBuffers(d) - 1                                 */
+  const int32_t* buffered_parts;        /* bufferedRanks(d) [num_cores]                      */
+  const int32_t* offset_ents_per_rank;  /* nentsOffsets(d) [nranks+1]                        */
+  const int32_t* ent_to_comm_arr_index; /* commArrayIndex(d) [nents]                         */
+  const int32_t* is_complete_part;      /* [nranks]: 0 absent, 1 boundary only, 2 complete   */
+  int32_t num_bounds, num_boundaries;
+  const int32_t* boundary_parts;        /* [num_boundaries]                                  */
+  const int32_t* offset_bounded;        /* [nranks+1] or empty (element dimension)           */
+  int32_t n_offset_bounded;
+  const int32_t* bounded_ent_ids;       /* [n_bounded_ent_ids]                               */
+  int32_t n_bounded_ent_ids;
+  const int32_t* ent_l2g;               /* full-mesh index per local entity, NULL after a read */
+} pp_host_picpart_dim;
+pp_status pp_host_picpart_get(const pp_host_picpart* pp, int32_t d, pp_host_picpart_dim* out);
+int32_t pp_host_picpart_is_full_mesh(const pp_host_picpart* pp);   /* Mesh::isFullMesh() */
+int32_t pp_host_picpart_nranks(const pp_host_picpart* pp);
+int32_t pp_host_picpart_rank(const pp_host_picpart* pp);
+/* pumipic::write(picparts, prefix) (src/pumipic_file.cpp:45-116): <prefix>_<nranks>.ppm/
+ * <name>_<rank>.osh + <name>_<rank>.ppm (format version 2). */
+pp_status pp_host_picpart_write(const pp_host_picpart* pp, const char* prefix);
+/* pumipic::read(lib, comm, prefix, &mesh) (src/pumipic_file.cpp:118-205), versions 1 and 2. */
+pp_status pp_host_picpart_read(const char* prefix, int32_t nranks, int32_t rank,
+                               pp_host_picpart** out);
+/* The safe-zone overlap regions ("sbars") this part belongs to (ParticleBalancer,
+ * src/pumipic_lb.hpp:97-101): global sbar id and the sorted parts sharing it.  parts of sbar i
+ * are parts[off[i] .. off[i+1]).  Pointers are owned by the PICpart. */
+pp_status pp_host_picpart_sbars(const pp_host_picpart* pp, int32_t* nsbars,
+                                const int32_t** sbar_ids, const int32_t** parts_off,
+                                const int32_t** parts, int32_t* max_sbar);
+
 /* ============================== particle structure ====================================== */
 
 typedef enum pp_ps_kind {

@@ -108,6 +108,195 @@ def host_picpart_extract(dim, coords, elem2verts, owner, nranks, has_part):
     return out
 
 
+_TAG_DTYPES = {capi.PP_TAG_I8: np.int8, capi.PP_TAG_I32: np.int32, capi.PP_TAG_I64: np.int64,
+               capi.PP_TAG_F64: np.float64}
+_TAG_CODES = {np.dtype(v): k for k, v in _TAG_DTYPES.items()}
+
+
+def _as_np(ptr, n, dtype):
+    """Copy of n values behind a ctypes pointer (empty when n == 0 or the pointer is NULL)."""
+    if n <= 0 or not ptr:
+        return np.empty(0, dtype)
+    addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+    return np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr),
+                         dtype=dtype).copy()
+
+
+class HostMesh:
+    """Host-side mesh with every entity dimension and its tags (what the reference keeps in an
+    Omega_h::Mesh on the set-up side); reads and writes Omega_h `.osh` directories."""
+
+    def __init__(self, handle, owned=True, keepalive=None):
+        self.h = C.c_void_p(handle) if isinstance(handle, int) else handle
+        self._owned = owned
+        self._keepalive = keepalive
+
+    @classmethod
+    def read_osh(cls, path):
+        h = C.c_void_p()
+        check(lib().pp_host_mesh_read_osh(str(path).encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_elems(cls, dim, coords, elem2verts):
+        co = np.ascontiguousarray(coords, np.float64)
+        ev = np.ascontiguousarray(elem2verts, np.int32)
+        h = C.c_void_p()
+        check(lib().pp_host_mesh_from_elems(dim, co.shape[0], co.ctypes.data_as(capi.c_dp),
+                                            ev.shape[0], ev.ctypes.data_as(capi.c_i32p), C.byref(h)))
+        return cls(h)
+
+    def write_osh(self, path):
+        check(lib().pp_host_mesh_write_osh(self.h, str(path).encode()))
+
+    @property
+    def dim(self):
+        return lib().pp_host_mesh_dim(self.h)
+
+    def nents(self, d):
+        return lib().pp_host_mesh_nents(self.h, d)
+
+    def down(self, d):
+        return _as_np(lib().pp_host_mesh_down(self.h, d), self.nents(d) * (d + 1), np.int32).reshape(-1, d + 1)
+
+    def codes(self, d):
+        return _as_np(lib().pp_host_mesh_codes(self.h, d), self.nents(d) * (d + 1), np.int8).reshape(-1, d + 1)
+
+    def ent2verts(self, d):
+        return _as_np(lib().pp_host_mesh_ent2verts(self.h, d), self.nents(d) * (d + 1), np.int32).reshape(-1, d + 1)
+
+    def coords(self):
+        return _as_np(lib().pp_host_mesh_coords(self.h), self.nents(0) * self.dim, np.float64).reshape(-1, self.dim)
+
+    def tag_names(self, d):
+        out = []
+        t = capi.HostTag()
+        for i in range(lib().pp_host_mesh_ntags(self.h, d)):
+            check(lib().pp_host_mesh_tag_at(self.h, d, i, C.byref(t)))
+            out.append(t.name.decode())
+        return out
+
+    def has_tag(self, d, name):
+        return name in self.tag_names(d)
+
+    def tag(self, d, name):
+        t = capi.HostTag()
+        check(lib().pp_host_mesh_find_tag(self.h, d, name.encode(), C.byref(t)))
+        a = _as_np(t.data, t.nvalues, _TAG_DTYPES[t.type])
+        return a.reshape(-1, t.ncomps) if t.ncomps > 1 else a
+
+    def set_tag(self, d, name, values):
+        a = np.ascontiguousarray(values)
+        ncomps = 1 if a.ndim == 1 else a.shape[1]
+        assert a.shape[0] == self.nents(d), "one row per entity"
+        check(lib().pp_host_mesh_set_tag(self.h, d, name.encode(), ncomps, _TAG_CODES[a.dtype],
+                                         _np_ptr(a)))
+
+    def sides(self):
+        """(elem2verts, elem2sides, side2verts) as pp_mesh_create wants them."""
+        d = self.dim
+        return self.ent2verts(d), self.down(d), self.ent2verts(d - 1) if d > 1 else None
+
+    def __del__(self):
+        try:
+            if self._owned and self.h:
+                lib().pp_host_mesh_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def host_read_partition(path, nelems, elem_class=None):
+    """Owner per element from a `.ptn` / `.cpn` file (pumipic::Input, pumipic_input.cpp:44-89)."""
+    out = np.empty(nelems, np.int32)
+    cls = None if elem_class is None else np.ascontiguousarray(elem_class, np.int32)
+    check(lib().pp_host_read_partition(str(path).encode(), nelems,
+                                       None if cls is None else cls.ctypes.data_as(capi.c_i32p),
+                                       out.ctypes.data_as(capi.c_i32p)))
+    return out
+
+
+class Picpart:
+    """pumipic::Mesh on the host: the PICpart's mesh, tags and communication record."""
+
+    _FIELDS = ("buffered_parts", "offset_ents_per_rank", "ent_to_comm_arr_index", "is_complete_part",
+               "boundary_parts", "offset_bounded", "bounded_ent_ids", "ent_l2g")
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def build(cls, full, elem_owner, nranks, rank, buffer_method=BFS, safe_method=BFS,
+              buffer_layers=-1, safe_layers=-1):
+        ow = np.ascontiguousarray(elem_owner, np.int32)
+        assert ow.shape[0] == full.nents(full.dim)
+        h = C.c_void_p()
+        check(lib().pp_host_picpart_build(full.h, ow.ctypes.data_as(capi.c_i32p), nranks, rank,
+                                          buffer_method, safe_method, buffer_layers, safe_layers,
+                                          C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def read(cls, prefix, nranks, rank):
+        h = C.c_void_p()
+        check(lib().pp_host_picpart_read(str(prefix).encode(), nranks, rank, C.byref(h)))
+        return cls(h)
+
+    def write(self, prefix):
+        check(lib().pp_host_picpart_write(self.h, str(prefix).encode()))
+
+    @property
+    def nranks(self):
+        return lib().pp_host_picpart_nranks(self.h)
+
+    @property
+    def rank(self):
+        return lib().pp_host_picpart_rank(self.h)
+
+    @property
+    def is_full_mesh(self):
+        return bool(lib().pp_host_picpart_is_full_mesh(self.h))
+
+    def mesh(self):
+        return HostMesh(lib().pp_host_picpart_mesh(self.h), owned=False, keepalive=self)
+
+    def dim_info(self, d):
+        """dict of the per-dimension members pumipic::Mesh keeps (pumipic_mesh.hpp:118-143)."""
+        s = capi.PicpartDim()
+        check(lib().pp_host_picpart_get(self.h, d, C.byref(s)))
+        nr = self.nranks
+        has = s.nents > 0 or s.num_entities > 0
+        sizes = {"buffered_parts": max(s.num_cores, 0), "offset_ents_per_rank": nr + 1 if has else 0,
+                 "ent_to_comm_arr_index": s.nents, "is_complete_part": nr if has else 0,
+                 "boundary_parts": s.num_boundaries, "offset_bounded": s.n_offset_bounded,
+                 "bounded_ent_ids": s.n_bounded_ent_ids, "ent_l2g": s.nents}
+        out = {"num_entities": s.num_entities, "nents": s.nents, "num_cores": s.num_cores,
+               "num_bounds": s.num_bounds, "num_boundaries": s.num_boundaries}
+        for f in self._FIELDS:
+            out[f] = _as_np(getattr(s, f), sizes[f], np.int32)
+        return out
+
+    def sbars(self):
+        """{global sbar id: tuple of parts} for the safe-zone overlaps this part belongs to, and max_sbar."""
+        n, mx = C.c_int32(), C.c_int32()
+        ids, off, parts = capi.c_i32p(), capi.c_i32p(), capi.c_i32p()
+        check(lib().pp_host_picpart_sbars(self.h, C.byref(n), C.byref(ids), C.byref(off), C.byref(parts),
+                                          C.byref(mx)))
+        ids_a = _as_np(ids, n.value, np.int32)
+        off_a = _as_np(off, n.value + 1, np.int32)
+        parts_a = _as_np(parts, int(off_a[-1]) if n.value else 0, np.int32)
+        return {int(ids_a[i]): tuple(int(x) for x in parts_a[off_a[i]:off_a[i + 1]])
+                for i in range(n.value)}, mx.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().pp_host_picpart_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------ mesh
 class Mesh:
     """pumipic::Mesh / o::Mesh stand-in: owns a pp_mesh built from host numpy arrays."""

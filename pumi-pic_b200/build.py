@@ -36,7 +36,8 @@ def build(verbose=False, force=False, extra_flags=(), lib=None, obj=None):
         OBJ = obj
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
-    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+    hdrs = (glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.hpp"))
+            + glob.glob(os.path.join(ROOT, "include", "*.h")))
     objs, procs = [], []
     for s in srcs:
         o = os.path.join(OBJ, os.path.basename(s) + ".o")
@@ -57,7 +58,7 @@ def build(verbose=False, force=False, extra_flags=(), lib=None, obj=None):
         raise RuntimeError("libpumipic_b200.so: compilation failed")
     if force or procs or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-o", LIB] + objs + ["-ldl"]
+               "-o", LIB] + objs + ["-ldl", "-lz"]
         subprocess.check_call(cmd)
     return LIB
 

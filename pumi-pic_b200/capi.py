@@ -71,11 +71,27 @@ class SearchStats(C.Structure):
                 ("hops", C.c_int64)]
 
 
+class HostTag(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("ncomps", C.c_int32), ("type", C.c_int32),
+                ("nvalues", C.c_int64), ("data", C.c_void_p)]
+
+
+class PicpartDim(C.Structure):
+    _fields_ = [("num_entities", C.c_int64), ("nents", C.c_int32), ("num_cores", C.c_int32),
+                ("buffered_parts", c_i32p), ("offset_ents_per_rank", c_i32p),
+                ("ent_to_comm_arr_index", c_i32p), ("is_complete_part", c_i32p),
+                ("num_bounds", C.c_int32), ("num_boundaries", C.c_int32),
+                ("boundary_parts", c_i32p), ("offset_bounded", c_i32p),
+                ("n_offset_bounded", C.c_int32), ("bounded_ent_ids", c_i32p),
+                ("n_bounded_ent_ids", C.c_int32), ("ent_l2g", c_i32p)]
+
+
 class MigrateStats(C.Structure):
     _fields_ = [("sent", C.c_int64), ("received", C.c_int64)]
 
 
 PP_INT32, PP_INT64, PP_FLOAT32, PP_FLOAT64 = 0, 1, 2, 3
+PP_TAG_I8, PP_TAG_I32, PP_TAG_I64, PP_TAG_F64 = 0, 2, 3, 5
 PP_SUM, PP_MAX, PP_MIN, PP_BCAST = 0, 1, 2, 3
 
 # every symbol include/pumipic_b200.h declares: name -> (restype, argtypes)
@@ -189,6 +205,35 @@ PROTOTYPES = {
     "pp_gather_grid3d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p]),
+    "pp_host_mesh_read_osh": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "pp_host_mesh_write_osh": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "pp_host_mesh_from_elems": (C.c_int, [C.c_int32, C.c_int32, c_dp, C.c_int32, c_i32p,
+                                          C.POINTER(C.c_void_p)]),
+    "pp_host_mesh_destroy": (None, [C.c_void_p]),
+    "pp_host_mesh_dim": (C.c_int32, [C.c_void_p]),
+    "pp_host_mesh_nents": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pp_host_mesh_down": (c_i32p, [C.c_void_p, C.c_int32]),
+    "pp_host_mesh_codes": (C.POINTER(C.c_int8), [C.c_void_p, C.c_int32]),
+    "pp_host_mesh_ent2verts": (c_i32p, [C.c_void_p, C.c_int32]),
+    "pp_host_mesh_coords": (c_dp, [C.c_void_p]),
+    "pp_host_mesh_ntags": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pp_host_mesh_tag_at": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(HostTag)]),
+    "pp_host_mesh_find_tag": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.POINTER(HostTag)]),
+    "pp_host_mesh_set_tag": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32,
+                                       C.c_void_p]),
+    "pp_host_read_partition": (C.c_int, [C.c_char_p, C.c_int32, c_i32p, c_i32p]),
+    "pp_host_picpart_build": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pp_host_picpart_destroy": (None, [C.c_void_p]),
+    "pp_host_picpart_mesh": (C.c_void_p, [C.c_void_p]),
+    "pp_host_picpart_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(PicpartDim)]),
+    "pp_host_picpart_is_full_mesh": (C.c_int32, [C.c_void_p]),
+    "pp_host_picpart_nranks": (C.c_int32, [C.c_void_p]),
+    "pp_host_picpart_rank": (C.c_int32, [C.c_void_p]),
+    "pp_host_picpart_write": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "pp_host_picpart_read": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pp_host_picpart_sbars": (C.c_int, [C.c_void_p, c_i32p, C.POINTER(c_i32p), C.POINTER(c_i32p),
+                                        C.POINTER(c_i32p), c_i32p]),
     "pp_push_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_double, C.c_void_p]),
 }

@@ -10,14 +10,12 @@
 
 #include <vector>
 
+#include "pp_host_internal.hpp"
 #include "pumipic_b200.h"
 
 void pp_set_error(const char* fmt, ...);
 
-namespace {
-struct Up {  // ask_up(0, dim): vertex -> elements
-  std::vector<int> off, val;
-};
+namespace pph {
 Up build_up(int nverts, int nelems, int nv, const int32_t* ev) {
   Up u;
   u.off.assign((size_t)nverts + 1, 0);
@@ -32,6 +30,7 @@ Up build_up(int nverts, int nelems, int nv, const int32_t* ev) {
     }
   return u;
 }
+namespace {
 // one BFS layer (part_construct.cpp:387-405): every element around a bridge that touches a
 // visited element becomes visited
 void bfs_layer(const Up& u, int nverts, const std::vector<int>& visited, std::vector<int>& next) {
@@ -45,26 +44,17 @@ void bfs_layer(const Up& u, int nverts, const std::vector<int>& visited, std::ve
 }
 }  // namespace
 
-extern "C" pp_status pp_host_picpart_tags(int32_t dim, int32_t nverts, int32_t nelems,
-                                          const int32_t* elem2verts, const int32_t* owner,
-                                          int32_t nranks, int32_t rank, int32_t buffer_method,
-                                          int32_t safe_method, int32_t buffer_layers,
-                                          int32_t safe_layers, int32_t* safe_out,
-                                          int32_t* has_part_out) {
-  if (!(dim == 2 || dim == 3) || !elem2verts || !owner || !safe_out || !has_part_out ||
-      nranks < 1 || rank < 0 || rank >= nranks) {
-    pp_set_error("pp_host_picpart_tags: bad argument");
-    return PP_ERR_INVALID;
-  }
+// Mesh::Mesh(Input&), part_construct.cpp:73-114: safe tag and buffered parts of one rank.
+void picpart_tags(const Up& u, int nverts, int nelems, const int32_t* owner, int nranks, int rank,
+                  int buffer_method, int safe_method, int buffer_layers, int safe_layers,
+                  std::vector<int>& is_safe, std::vector<int>& has_part) {
   enum { FULL = 0, BFS = 1, MINIMUM = 2, NONE = 3 };
   if (buffer_method == NONE) buffer_method = MINIMUM;        // pumipic_input.cpp:96-100
   if (buffer_method == MINIMUM) buffer_layers = 0;
   if (safe_method == MINIMUM) safe_layers = 0;
-  const int nv = dim + 1;
-  std::vector<int> is_safe(nelems, safe_method == FULL), has_part(nranks, 1);
-  Up u;
+  is_safe.assign((size_t)nelems, safe_method == FULL);
+  has_part.assign((size_t)nranks, 1);
   const bool need_bfs = (safe_method != NONE && safe_method != FULL) || buffer_method != FULL;
-  if (need_bfs || (buffer_method == BFS && safe_method == FULL)) u = build_up(nverts, nelems, nv, elem2verts);
   if (need_bfs) {
     // bfsBufferLayers
     std::vector<int> safe(nelems, 0), part(nranks, 0), visited(nelems), next(nelems);
@@ -91,6 +81,24 @@ extern "C" pp_status pp_host_picpart_tags(int32_t dim, int32_t nverts, int32_t n
     }
     for (int e = 0; e < nelems; ++e) is_safe[e] = !visited[e] || owner[e] == rank;
   }
+}
+}  // namespace pph
+
+extern "C" pp_status pp_host_picpart_tags(int32_t dim, int32_t nverts, int32_t nelems,
+                                          const int32_t* elem2verts, const int32_t* owner,
+                                          int32_t nranks, int32_t rank, int32_t buffer_method,
+                                          int32_t safe_method, int32_t buffer_layers,
+                                          int32_t safe_layers, int32_t* safe_out,
+                                          int32_t* has_part_out) {
+  if (!(dim == 2 || dim == 3) || !elem2verts || !owner || !safe_out || !has_part_out ||
+      nranks < 1 || rank < 0 || rank >= nranks) {
+    pp_set_error("pp_host_picpart_tags: bad argument");
+    return PP_ERR_INVALID;
+  }
+  const pph::Up u = pph::build_up(nverts, nelems, dim + 1, elem2verts);
+  std::vector<int> is_safe, has_part;
+  pph::picpart_tags(u, nverts, nelems, owner, nranks, rank, buffer_method, safe_method,
+                    buffer_layers, safe_layers, is_safe, has_part);
   memcpy(safe_out, is_safe.data(), sizeof(int32_t) * nelems);
   memcpy(has_part_out, has_part.data(), sizeof(int32_t) * nranks);
   return PP_OK;

@@ -126,3 +126,55 @@ def read_osh(path):
         if (d, "class_dim") in tags:
             out["class_dim_%d" % d] = tags[(d, "class_dim")][1].astype(np.int8)
     return out
+
+
+def read_osh_tags(path):
+    """Like read_osh, plus every tag: dict dim, nents[d], down[d], codes[d], verts[d], tags[(d, name)]."""
+    with open(path + "/0.osh", "rb") as f:
+        s = _Stream(f.read())
+    assert s.take("B") == 0xA1 and s.take("B") == 0x1A, "bad magic"
+    compressed = s.take("b")
+    s.take("b")
+    dim = s.take("b")
+    s.take("i"); s.take("i"); s.take("b"); s.take("i")
+    assert s.take("b") == 0
+    nents = [s.take("i"), 0, 0, 0]
+    down, codes = {}, {}
+    for d in range(1, dim + 1):
+        down[d] = s.array(np.int32, compressed)
+        nents[d] = len(down[d]) // (d + 1)
+        if d > 1:
+            codes[d] = s.array(np.int8, compressed)
+    tags = {}
+    for d in range(dim + 1):
+        for _ in range(s.take("i")):
+            nl = s.take("i")
+            name = s.raw(nl).decode()
+            s.take("b")
+            typ = s.take("b")
+            tags[(d, name)] = s.array(_TYPES[typ], compressed)
+    geo = read_osh(path)
+    verts = {1: geo["edge2verts"].ravel(), 2: geo["face2verts"].ravel()}
+    if dim == 3:
+        verts[3] = geo["elem2verts"].ravel()
+    return {"dim": dim, "nents": nents, "down": down, "codes": codes, "verts": verts, "tags": tags}
+
+
+def read_ppm(path):
+    """pumipic::write's per-rank record (src/pumipic_file.cpp:82-115), format versions 1 and 2."""
+    with open(path, "rb") as f:
+        s = _Stream(f.read())
+    version = s.take("b")
+    out = {"version": version, "full": s.take("b"), "dims": []}
+    for _ in range(4):
+        o = {"num_entites": s.take("q") if version >= 2 else 0, "num_cores": s.take("i")}
+        for k in ("buffered_parts", "offset_ents_per_rank", "ent_to_comm_arr_index",
+                  "is_complete_part"):
+            o[k] = s.array(np.int32, True)
+        o["num_bounds"] = s.take("i")
+        o["num_boundaries"] = s.take("i")
+        for k in ("boundary_parts", "offset_bounded", "bounded_ent_ids"):
+            o[k] = s.array(np.int32, True)
+        out["dims"].append(o)
+    assert s.p == len(s.b), "trailing bytes in .ppm"
+    return out
