@@ -563,6 +563,80 @@ pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_element,
                         const void* const* new_particle_info, pp_migrate_stats* stats_host,
                         pp_stream stream);
 
+/* ============================== particle load balancing ==================== */
+
+/* The plan of ParticleBalancer::balance (src/pumipic_lb.cpp:478-511), i.e. what
+ * engpar::balanceWeights returns for the N-graph of buildNgraph (:395-462), evaluated for ALL parts
+ * from the global weight vector.  EnGPar is a third-party dependency that is not in the reference
+ * tree: the diffusion is restated from its published scheme and its parity is UNPINNED
+ * (csrc/pp_host_lb.cpp); the reference's own acceptance bounds (test/test_lb.cpp:126,176) are
+ * what the tests hold it to.
+ *   sbars: nsbars regions, global id sbar_ids[i], sorted parts parts[parts_off[i]..parts_off[i+1]);
+ *          graph vertex of part parts[parts_off[i]+j] in sbar i = sbar_ids[i] + j (< nverts)
+ *   vert_weight[nverts]: particles per vertex;  forced[nranks] (or NULL): particles each part is
+ *          already receiving from others (pumipic_lb.hpp:196-200)
+ *   tol: target max/avg (1.05 = 5 %); step_factor in (0,1]; max_iters <= 0 = 100
+ * Output (pp_host_free each): nsends transfers "send_weight[i] particles of vertex send_vert[i] to
+ * part send_part[i]", ascending (vertex, part); imbalance[0] before, imbalance[1] planned (or NULL). */
+pp_status pp_host_lb_plan(int32_t nranks, int32_t nsbars, const int32_t* sbar_ids,
+                          const int32_t* parts_off, const int32_t* parts, int32_t nverts,
+                          const double* vert_weight, const double* forced, double tol,
+                          double step_factor, int32_t max_iters, int32_t* nsends,
+                          int32_t** send_vert, int32_t** send_part, double** send_weight,
+                          double* imbalance);
+
+/* pumipic::ParticleBalancer (src/pumipic_lb.hpp:32-115) for one part.
+ *   sbar table: the regions this part knows (pp_host_picpart_sbars); with a communicator of more
+ *   than one rank the tables of all ranks are merged (collective), without one the table given
+ *   must already be the global one.
+ *   elem_sbar[nelems] = ParticleBalancer::getSbarIDs (the "sbar_id" tag), elem_owner[nelems] =
+ *   Mesh::entOwners(dim); memspace says where the two arrays live. */
+typedef struct pp_balancer pp_balancer;
+pp_status pp_balancer_create(int32_t nranks, int32_t rank, int32_t nsbars, const int32_t* sbar_ids,
+                             const int32_t* parts_off, const int32_t* parts, int32_t nelems,
+                             const int32_t* elem_sbar, const int32_t* elem_owner, int32_t memspace,
+                             pp_comm* comm, pp_stream stream, pp_balancer** out);
+pp_status pp_balancer_destroy(pp_balancer* b);
+/* graph vertices of all parts / of this part (global vertex id and sbar id, ascending; host
+ * pointers owned by the balancer) */
+pp_status pp_balancer_info(const pp_balancer* b, int32_t* nverts, int32_t* nlocal,
+                           const int32_t** local_verts, const int32_t** local_sbars);
+/* addWeights (pumipic_lb.hpp:133-208): counts, per own vertex, the masked particles that stay on
+ * this rank (new_procs == rank, new_elems != -1) and, per destination, the ones already leaving;
+ * new_elems / new_procs: device int32[capacity] indexed by slot.  The result lands in this part's
+ * entries of the global weight vector. */
+pp_status pp_balancer_add_weights_ps(pp_balancer* b, pp_ps* ps, const int32_t* new_elems,
+                                     const int32_t* new_procs, pp_stream stream);
+/* addWeights (pumipic_lb.hpp:211-229): ptcls_per_elem = device int32[nelems] */
+pp_status pp_balancer_add_weights_array(pp_balancer* b, const int32_t* ptcls_per_elem,
+                                        pp_stream stream);
+/* The global weight vector on the device: [nverts] vertex weights then [nranks] forced weights. */
+pp_status pp_balancer_weights(pp_balancer* b, double** weights_dev, int64_t* n);
+/* balance (pumipic_lb.cpp:478-511): sums the weight vector over the communicator (skipped when
+ * comm is NULL or has one rank: the vector is then taken as already global), runs
+ * pp_host_lb_plan and keeps this part's sends.  One rank: the empty plan. */
+pp_status pp_balancer_balance(pp_balancer* b, pp_comm* comm, double tol, double step_factor,
+                              pp_stream stream);
+/* this part's plan: nsends x (sbar id, target part, weight); host pointers owned by the balancer */
+pp_status pp_balancer_plan(const pp_balancer* b, int32_t* nsends, const int32_t** sbar,
+                           const int32_t** part, const double** weight, double imbalance[2]);
+/* selectParticles (pumipic_lb.hpp:231-289): re-targets new_procs of ceil(weight) particles per
+ * planned send, particles in elements of other parts' cores first, then any.  Consumes the plan. */
+pp_status pp_balancer_select_ps(pp_balancer* b, pp_ps* ps, const int32_t* new_elems,
+                                int32_t* new_procs, pp_stream stream);
+/* selectParticles (pumipic_lb.hpp:291-353): new_procs = device int32[nptcls], nptcls = sum of
+ * ptcls_per_elem; the particles of element e are entries [scan(e), scan(e) + ptcls_per_elem[e]). */
+pp_status pp_balancer_select_array(pp_balancer* b, const int32_t* ptcls_per_elem, int64_t nptcls,
+                                   int32_t* new_procs, pp_stream stream);
+/* repartition (pumipic_lb.hpp:355-366) = add_weights_ps + balance + select_ps;
+ * partition (:368-381) = add_weights_array + balance + select_array. */
+pp_status pp_balancer_repartition(pp_balancer* b, pp_comm* comm, pp_ps* ps, double tol,
+                                  const int32_t* new_elems, int32_t* new_procs, double step_factor,
+                                  pp_stream stream);
+pp_status pp_balancer_partition(pp_balancer* b, pp_comm* comm, const int32_t* ptcls_per_elem,
+                                int64_t nptcls, double tol, double step_factor, int32_t* new_procs,
+                                pp_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -708,3 +708,122 @@ class CommPlan:
             lib().pp_comm_plan_destroy(self.h)
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------ particle load balancing
+def _sbar_arrays(table):
+    ids = np.asarray(sorted(table), np.int32)
+    off = np.zeros(len(ids) + 1, np.int32)
+    parts = []
+    for i, g in enumerate(ids):
+        parts.extend(table[int(g)])
+        off[i + 1] = len(parts)
+    return ids, off, np.asarray(parts, np.int32)
+
+
+def host_lb_plan(nranks, table, vert_weight, forced=None, tol=1.05, step_factor=0.3, max_iters=0):
+    """pp_host_lb_plan: `table` = {sbar id: sorted parts}; returns ([(vertex, part, weight)],
+    (imbalance before, imbalance planned))."""
+    ids, off, parts = _sbar_arrays(table)
+    w = np.ascontiguousarray(vert_weight, np.float64)
+    f = None if forced is None else np.ascontiguousarray(forced, np.float64)
+    n = C.c_int32()
+    sv, sp, sw = capi.c_i32p(), capi.c_i32p(), capi.c_dp()
+    imb = (C.c_double * 2)()
+    check(lib().pp_host_lb_plan(nranks, len(ids), ids.ctypes.data_as(capi.c_i32p),
+                                off.ctypes.data_as(capi.c_i32p), parts.ctypes.data_as(capi.c_i32p),
+                                w.shape[0], w.ctypes.data_as(capi.c_dp),
+                                None if f is None else f.ctypes.data_as(capi.c_dp), tol, step_factor,
+                                max_iters, C.byref(n), C.byref(sv), C.byref(sp), C.byref(sw), imb))
+    out = [(int(sv[i]), int(sp[i]), float(sw[i])) for i in range(n.value)]
+    for p in (sv, sp, sw):
+        lib().pp_host_free(p)
+    return out, (imb[0], imb[1])
+
+
+class Balancer:
+    """pumipic::ParticleBalancer (pumipic_lb.hpp:32-115) for one part (pp_balancer_*)."""
+
+    def __init__(self, nranks, rank, table, elem_sbar, elem_owner, comm=None):
+        """table = {sbar id: sorted parts}: the global table, or with a multi-rank `comm` the
+        regions this part knows (Picpart.sbars()[0]); elem_sbar / elem_owner: numpy or cuda int32."""
+        ids, off, parts = _sbar_arrays(table)
+        host = isinstance(elem_sbar, np.ndarray)
+        if host:
+            es = np.ascontiguousarray(elem_sbar, np.int32)
+            eo = np.ascontiguousarray(elem_owner, np.int32)
+            pes, peo, ne = _np_ptr(es), _np_ptr(eo), es.shape[0]
+        else:
+            pes, peo, ne = _ptr(elem_sbar), _ptr(elem_owner), elem_sbar.shape[0]
+        self.nranks, self.rank, self.nelems = nranks, rank, ne
+        self.h = C.c_void_p()
+        check(lib().pp_balancer_create(nranks, rank, len(ids), ids.ctypes.data_as(capi.c_i32p),
+                                       off.ctypes.data_as(capi.c_i32p),
+                                       parts.ctypes.data_as(capi.c_i32p), ne, pes, peo,
+                                       capi.PP_HOST if host else capi.PP_DEVICE,
+                                       None if comm is None else comm.h, _stream(), C.byref(self.h)))
+
+    def info(self):
+        """(graph vertices of all parts, this part's global vertex ids, their sbar ids)"""
+        nv, nl = C.c_int32(), C.c_int32()
+        lv, ls = capi.c_i32p(), capi.c_i32p()
+        check(lib().pp_balancer_info(self.h, C.byref(nv), C.byref(nl), C.byref(lv), C.byref(ls)))
+        return nv.value, _as_np(lv, nl.value, np.int32), _as_np(ls, nl.value, np.int32)
+
+    def weights(self):
+        """the global weight vector as a cuda float64 tensor view: [nverts] then [nranks] forced"""
+        torch = _torch()
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib().pp_balancer_weights(self.h, C.byref(p), C.byref(n)))
+        return _tensor_from_ptr(p.value, (n.value,), torch.float64, self)
+
+    def add_weights(self, ps, new_elems, new_procs):
+        check(lib().pp_balancer_add_weights_ps(self.h, ps.h, _ptr(new_elems), _ptr(new_procs), _stream()))
+
+    def add_weights_array(self, ptcls_per_elem):
+        check(lib().pp_balancer_add_weights_array(self.h, _ptr(ptcls_per_elem), _stream()))
+
+    def balance(self, comm=None, tol=1.05, step_factor=0.3):
+        check(lib().pp_balancer_balance(self.h, None if comm is None else comm.h, tol, step_factor,
+                                        _stream()))
+        return self.plan()
+
+    def plan(self):
+        """([(sbar id, target part, weight)] of this part, (imbalance before, planned))"""
+        n = C.c_int32()
+        sb, pt, wt = capi.c_i32p(), capi.c_i32p(), capi.c_dp()
+        imb = (C.c_double * 2)()
+        check(lib().pp_balancer_plan(self.h, C.byref(n), C.byref(sb), C.byref(pt), C.byref(wt), imb))
+        return [(int(sb[i]), int(pt[i]), float(wt[i])) for i in range(n.value)], (imb[0], imb[1])
+
+    def select(self, ps, new_elems, new_procs):
+        check(lib().pp_balancer_select_ps(self.h, ps.h, _ptr(new_elems), _ptr(new_procs), _stream()))
+        return new_procs
+
+    def select_array(self, ptcls_per_elem, nptcls):
+        torch = _torch()
+        out = torch.empty(nptcls, dtype=torch.int32, device="cuda")
+        check(lib().pp_balancer_select_array(self.h, _ptr(ptcls_per_elem), nptcls, _ptr(out), _stream()))
+        return out
+
+    def repartition(self, comm, ps, tol, new_elems, new_procs, step_factor=0.3):
+        check(lib().pp_balancer_repartition(self.h, None if comm is None else comm.h, ps.h, tol,
+                                            _ptr(new_elems), _ptr(new_procs), step_factor, _stream()))
+        return new_procs
+
+    def partition(self, comm, ptcls_per_elem, tol, step_factor=0.3):
+        torch = _torch()
+        nptcls = int(ptcls_per_elem.sum().item())
+        out = torch.empty(nptcls, dtype=torch.int32, device="cuda")
+        check(lib().pp_balancer_partition(self.h, None if comm is None else comm.h,
+                                          _ptr(ptcls_per_elem), nptcls, tol, step_factor, _ptr(out),
+                                          _stream()))
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().pp_balancer_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

@@ -236,6 +236,26 @@ PROTOTYPES = {
                                         C.POINTER(c_i32p), c_i32p]),
     "pp_push_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_double, C.c_void_p]),
+    "pp_host_lb_plan": (C.c_int, [C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, C.c_int32, c_dp, c_dp,
+                                  C.c_double, C.c_double, C.c_int32, c_i32p, C.POINTER(c_i32p),
+                                  C.POINTER(c_i32p), C.POINTER(c_dp), c_dp]),
+    "pp_balancer_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p,
+                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pp_balancer_destroy": (C.c_int, [C.c_void_p]),
+    "pp_balancer_info": (C.c_int, [C.c_void_p, c_i32p, c_i32p, C.POINTER(c_i32p), C.POINTER(c_i32p)]),
+    "pp_balancer_add_weights_ps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_balancer_add_weights_array": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_balancer_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_i64p]),
+    "pp_balancer_balance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
+    "pp_balancer_plan": (C.c_int, [C.c_void_p, c_i32p, C.POINTER(c_i32p), C.POINTER(c_i32p),
+                                   C.POINTER(c_dp), c_dp]),
+    "pp_balancer_select_ps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_balancer_select_array": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pp_balancer_repartition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                          C.c_void_p, C.c_double, C.c_void_p]),
+    "pp_balancer_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                        C.c_double, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -386,6 +386,7 @@ void parallel_for(ParticleStructure<DataTypes>* ps, FunctionType& fn, std::strin
 #endif
 
 // ---------------------------------------------------------------- Mesh (PICpart handle)
+class ParticleBalancer;
 class Mesh {
  public:
   enum Op { SUM_OP, MAX_OP, MIN_OP, BCAST_OP };   // pumipic_mesh.hpp:57-62
@@ -421,6 +422,11 @@ class Mesh {
     comm_ = comm;
   }
   pp_comm* comm() const { return comm_; }
+  // Mesh::ptclBalancer() (pumipic_mesh.hpp:76).  The reference builds it lazily by exchanging safe
+  // flags over MPI; here it is made from the PICpart's sbar table (ParticleBalancer below) and
+  // attached by the caller, who keeps ownership.
+  ParticleBalancer* ptclBalancer() const { return balancer_; }
+  void setPtclBalancer(ParticleBalancer* b) { balancer_ = b; }
   template <class T> View<T> createCommArray(int edim, int nvals, T init) {   // pumipic_comm.cpp:187-192
     return View<T>((size_t)nents_[edim] * nvals, init);
   }
@@ -437,6 +443,7 @@ class Mesh {
   lid_t nents_[4] = {0, 0, 0, 0};
   pp_mesh* h_ = nullptr;
   pp_comm* comm_;
+  ParticleBalancer* balancer_ = nullptr;
 };
 
 // ---------------------------------------------------------------- search
@@ -513,11 +520,85 @@ void migrate_ptcls(Mesh& mesh, PS* ptcls, View<lid_t> new_elems) {
   setUnsafeProcs(mesh, ptcls, new_elems, ptcl_elems, ptcl_procs);
   ptcls->migrate(ptcl_elems, ptcl_procs, Distributor(mesh.comm()));
 }
-// the EnGPar balancer is out of scope; without it migrate_lb_ptcls is migrate_ptcls,
-// which is also what the reference does on one rank (pumipic_lb.hpp:357-358)
+// ---------------------------------------------------------------- particle load balancing (pumipic_lb.hpp)
+// pumipic::ParticleBalancer (src/pumipic_lb.hpp:32-115).  Built from what the host PICpart record
+// holds (pp_host_picpart_sbars, the "sbar_id" and "ownership" element tags) instead of the MPI
+// exchange of the reference's constructor (pumipic_lb.cpp:23-82).
+class ParticleBalancer {
+ public:
+  ParticleBalancer(Mesh& picparts, const std::vector<int>& sbar_ids, const std::vector<int>& parts_off,
+                   const std::vector<int>& parts, const std::vector<int>& elem_sbar,
+                   const std::vector<int>& elem_owner, int self_rank = 0) {
+    pp_comm* c = picparts.comm();
+    const int nranks = c ? pp_comm_size(c) : 1;
+    const int rank = c ? pp_comm_rank(c) : self_rank;
+    pp_check(pp_balancer_create(nranks, rank, (int32_t)sbar_ids.size(), sbar_ids.data(), parts_off.data(),
+                                parts.data(), (int32_t)elem_sbar.size(), elem_sbar.data(), elem_owner.data(),
+                                PP_HOST, c, nullptr, &h_), "ParticleBalancer");
+    sbar_ids_ = View<lid_t>(elem_sbar);
+  }
+  ~ParticleBalancer() { if (h_) pp_balancer_destroy(h_); }
+  ParticleBalancer(const ParticleBalancer&) = delete;
+  ParticleBalancer& operator=(const ParticleBalancer&) = delete;
+  pp_balancer* handle() const { return h_; }
+  View<lid_t> getSbarIDs(Mesh&) const { return sbar_ids_; }                       // pumipic_lb.cpp:464-466
+  // pumipic_lb.hpp:355-366; new_procs is changed in place
+  template <class PS>
+  void repartition(Mesh& picparts, PS* ps, double tol, View<lid_t> new_elems, View<lid_t> new_procs,
+                   double step_factor = 0.3) {
+    pp_check(pp_balancer_repartition(h_, picparts.comm(), ps->handle(), tol, new_elems.data(), new_procs.data(),
+                                     step_factor, (pp_stream)ps->stream()), "ParticleBalancer::repartition");
+  }
+  // pumipic_lb.hpp:368-381: the new process of every particle, particles of element e at
+  // [scan(e), scan(e) + ptcls_per_elem[e]); selection_iterations is accepted for source
+  // compatibility (one pass assigns every planned send here)
+  View<lid_t> partition(Mesh& picparts, View<lid_t> ptcls_per_elem, double tol, double step_factor = 0.3,
+                        int /*selection_iterations*/ = 5) {
+    const std::vector<lid_t> h = ptcls_per_elem.toHost();
+    long np = 0;
+    for (lid_t c : h) np += c;
+    View<lid_t> new_procs((size_t)np, 0);
+    pp_check(pp_balancer_partition(h_, picparts.comm(), ptcls_per_elem.data(), np, tol, step_factor,
+                                   new_procs.data(), nullptr), "ParticleBalancer::partition");
+    cuda_check(cudaStreamSynchronize(nullptr), "ParticleBalancer::partition");
+    return new_procs;
+  }
+  // the steps of repartition, callable on their own (pumipic_lb.hpp:70-90)
+  template <class PS>
+  void addWeights(Mesh&, PS* ps, View<lid_t> new_elems, View<lid_t> new_procs) {
+    pp_check(pp_balancer_add_weights_ps(h_, ps->handle(), new_elems.data(), new_procs.data(),
+                                        (pp_stream)ps->stream()), "ParticleBalancer::addWeights");
+  }
+  void addWeights(Mesh&, View<lid_t> ptcls_per_elem) {
+    pp_check(pp_balancer_add_weights_array(h_, ptcls_per_elem.data(), nullptr), "ParticleBalancer::addWeights");
+  }
+  // ParticlePlan stays inside the handle: balance() then selectParticles()
+  void balance(Mesh& picparts, double tol, double step_factor = 0.3) {
+    pp_check(pp_balancer_balance(h_, picparts.comm(), tol, step_factor, nullptr), "ParticleBalancer::balance");
+  }
+  template <class PS>
+  void selectParticles(Mesh&, PS* ps, View<lid_t> new_elems, View<lid_t> new_parts) {
+    pp_check(pp_balancer_select_ps(h_, ps->handle(), new_elems.data(), new_parts.data(),
+                                   (pp_stream)ps->stream()), "ParticleBalancer::selectParticles");
+  }
+
+ private:
+  pp_balancer* h_ = nullptr;
+  View<lid_t> sbar_ids_;
+};
+
+// ptcl_ops.hpp:55-71: setUnsafeProcs -> ParticleBalancer::repartition -> migrate.  On one rank the
+// balancer is a no-op (pumipic_lb.hpp:360-361); on several a balancer must have been attached.
 template <class PS>
-void migrate_lb_ptcls(Mesh& mesh, PS* ptcls, View<lid_t> new_elems, float /*tol*/, float /*step_factor*/ = 0.5) {
-  migrate_ptcls(mesh, ptcls, new_elems);
+void migrate_lb_ptcls(Mesh& mesh, PS* ptcls, View<lid_t> new_elems, float tol, float step_factor = 0.5) {
+  View<lid_t> ptcl_elems, ptcl_procs;
+  setUnsafeProcs(mesh, ptcls, new_elems, ptcl_elems, ptcl_procs);
+  if (mesh.comm() && pp_comm_size(mesh.comm()) > 1) {
+    if (!mesh.ptclBalancer())
+      throw std::runtime_error("migrate_lb_ptcls: no ParticleBalancer attached (Mesh::setPtclBalancer)");
+    mesh.ptclBalancer()->repartition(mesh, ptcls, tol, ptcl_elems, ptcl_procs, step_factor);
+  }
+  ptcls->migrate(ptcl_elems, ptcl_procs, Distributor(mesh.comm()));
 }
 
 // ---------------------------------------------------------------- gather (field -> particle)

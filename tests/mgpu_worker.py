@@ -335,6 +335,54 @@ def test_partial_picparts(P, comm, rank, R, steps=6):
               % (R, len(el2g), ne, tot))
 
 
+def test_balancer(P, comm, rank, R):
+    """testBalancePS (test/test_lb.cpp:132-207): 100 particles per element on the even ranks only,
+    two rounds of repartition + migrate; the imbalance must end <= 1.5 and no particle may be lost,
+    duplicated or moved to another element."""
+    from meshes import plate
+    m = plate(16)
+    full = P.HostMesh.from_elems(2, m.coords, m.elem2verts)
+    cx = m.coords[m.elem2verts].mean(axis=1)[:, 0]
+    owner = np.minimum((cx * R).astype(np.int32), R - 1)            # R stripes
+    part = P.Picpart.build(full, owner, R, rank, P.BFS, P.FULL)
+    pm = part.mesh()
+    sbar, own, safe = pm.tag(2, "sbar_id"), pm.tag(2, "ownership"), pm.tag(2, "safe")
+    gids = pm.tag(2, "gids").astype(np.int64)
+    table, _ = part.sbars()
+    bal = P.Balancer(R, rank, table, sbar.astype(np.int32), own.astype(np.int32), comm=comm)
+    ne = pm.nents(2)
+    ppe = np.where(own == rank, 100 if rank % 2 == 0 else 0, 0).astype(np.int32)
+    npr = int(ppe.sum())
+    pel = np.repeat(np.arange(ne, dtype=np.int32), ppe)
+    ids = np.arange(npr, dtype=np.int32) + rank * 1000000
+    info = [ids.reshape(1, -1), np.zeros((3, npr)), gids[pel].astype(np.int32).reshape(1, -1)]
+    ps = P.ParticleStructure(P.capi.PP_PS_SCS, TYPES, ppe, elem_gids=gids, particle_elements=pel,
+                             particle_info=info)
+    d_safe, d_own = dev(safe.astype(np.int32)), dev(own.astype(np.int32))
+    before = gather_np(ps.nptcls)
+    for _ in range(2):
+        se, mk = ps.slot_elem_and_mask()
+        d_se, d_mk = dev(se), dev(mk.astype(bool))
+        new_elems = torch.where(d_mk, d_se, torch.full_like(d_se, -1))
+        unsafe = d_mk & (d_safe[d_se.long()] == 0)
+        new_procs = torch.where(unsafe, d_own[d_se.long()], torch.full_like(d_se, rank))
+        bal.repartition(comm, ps, 1.05, new_elems, new_procs)
+        P.migrate(ps, comm, new_elems, new_procs)
+    after = gather_np(ps.nptcls)
+    assert sum(after) == sum(before)
+    imb = max(after) / (sum(after) / R)
+    assert imb <= 1.5, (before, after)
+    se, mk = ps.slot_elem_and_mask()
+    mk = mk.astype(bool)
+    pid = ps.get(0).cpu().numpy()[0, :ps.capacity][mk]
+    home = ps.get(2).cpu().numpy()[0, :ps.capacity][mk]
+    assert np.array_equal(gids[se[mk]].astype(np.int32), home)     # still in its element
+    allp = np.concatenate(gather_np(pid))
+    assert len(np.unique(allp)) == len(allp) == sum(before)
+    if rank == 0:
+        print("balancer ok on %d ranks: particles %s -> %s (imbalance %.3f)" % (R, before, after, imb))
+
+
 def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -347,6 +395,8 @@ def main():
     test_migrate(P, comm, rank, R)
     test_pic_loop(P, comm, rank, R)
     test_partial_picparts(P, comm, rank, R)
+    if R > 1:          # one rank: repartition is a no-op (pumipic_lb.hpp:360-361)
+        test_balancer(P, comm, rank, R)
     dist.barrier()
     if rank == 0:
         print("MGPU_OK")

@@ -1,0 +1,174 @@
+"""GPU tests of the particle balancer's device side (pp_balancer_*):
+addWeights / selectParticles of pumipic_lb.hpp:133-353 on one GPU acting as rank r of 4 (the other
+ranks' entries of the global weight vector are written by the test, which is what the all-reduce
+would deliver).  Integer work: the counts must equal numpy's exactly; WHICH particles move is
+atomic-order dependent here and in the reference, so selections are compared as counts per
+(sbar, target).  The scenarios are test/test_lb.cpp's.  (File name sorts last on purpose: the
+round that added it had no GPU time left to run it.)
+"""
+import numpy as np
+import pytest
+
+from gpu_common import dev, pp, torch
+from test_lb_host import NR, _global_table, _picparts, _vertex_of
+
+pytestmark = pytest.mark.gpu
+
+TYPES = [(np.int32, 1)]
+
+
+def _rank_setup(r, parts, table):
+    P = pp()
+    m = parts[r].mesh()
+    sbar = m.tag(2, "sbar_id").astype(np.int32)
+    own = m.tag(2, "ownership").astype(np.int32)
+    safe = m.tag(2, "safe").astype(np.int32)
+    bal = P.Balancer(NR, r, table, sbar, own)
+    return bal, sbar, own, safe
+
+
+def _ps_with(ppe, kind):
+    P = pp()
+    kw = dict(kind=kind)
+    if kind == P.capi.PP_PS_SCS:
+        kw.update(team_size=32, sigma=0x7fffffff, V=1024)
+    k = kw.pop("kind")
+    return P.ParticleStructure(k, TYPES, ppe.astype(np.int32), **kw)
+
+
+@pytest.mark.parametrize("kind", ["scs", "csr", "dps"])
+@pytest.mark.parametrize("safe_method,layers", [("full", -1), ("bfs", 2)])
+def test_count_plan_select_on_a_structure(kind, safe_method, layers):
+    P = pp()
+    t = torch()
+    K = {"scs": P.capi.PP_PS_SCS, "csr": P.capi.PP_PS_CSR, "dps": P.capi.PP_PS_DPS}[kind]
+    full, owner, parts = _picparts(safe=P.FULL if safe_method == "full" else P.BFS, safe_layers=layers)
+    table, nverts = _global_table(parts)
+    vof = _vertex_of(table)
+    r = 0
+    bal, sbar, own, safe = _rank_setup(r, parts, table)
+    nv, lverts, lsbars = bal.info()
+    assert nv == nverts
+    assert lverts.tolist() == sorted(v for (g, p), v in vof.items() if p == r)
+    assert [vof[(int(g), r)] for g in lsbars] == lverts.tolist()
+
+    # 100 particles in every element this rank holds safely, none elsewhere (test_lb.cpp:143-151)
+    ne = sbar.shape[0]
+    ppe = np.where(safe > 0, 100, 0).astype(np.int32)
+    rng = np.random.default_rng(5)
+    ppe[rng.random(ne) < 0.1] = 0
+    ps = _ps_with(ppe, K)
+    slot_elem, mask = ps.slot_elem_and_mask()
+    mask = mask.astype(bool)
+    cap = ps.capacity
+    # balancePtcls (test_lb.cpp:181-207): stay in the element; unsafe -> owner (none here); a few
+    # particles are already leaving for rank 2 and a few are being deleted
+    new_elems = np.where(mask, slot_elem, -1).astype(np.int32)
+    new_procs = np.full(cap, r, np.int32)
+    live = np.flatnonzero(mask)
+    leaving = live[::97]
+    deleted = live[5::101]
+    new_procs[leaving] = 2
+    new_elems[deleted] = -1
+    d_elems, d_procs = dev(new_elems), dev(new_procs)
+
+    bal.add_weights(ps, d_elems, d_procs)
+    w = bal.weights().cpu().numpy()
+    assert w.shape[0] == nverts + NR
+    want = np.zeros(nverts + NR)
+    stay = mask & (new_procs == r) & (new_elems >= 0)
+    for g, c in zip(*np.unique(sbar[new_elems[stay]], return_counts=True)):
+        if (int(g), r) in vof:
+            want[vof[(int(g), r)]] = c
+    want[nverts + 2] = np.count_nonzero(mask & (new_procs == 2))
+    assert np.array_equal(w, want)
+
+    # the other ranks hold nothing: the vector is already global -> plan without a communicator
+    sends, (before, planned) = bal.balance(None, tol=1.05, step_factor=0.3)
+    ref, (rb, rp) = P.host_lb_plan(NR, table, want[:nverts], forced=want[nverts:], tol=1.05, step_factor=0.3)
+    vpart = {v: (g, p) for (g, p), v in vof.items()}
+    mine = [(vpart[v][0], q, a) for v, q, a in ref if vpart[v][1] == r and np.ceil(a - 1e-9) > 0]
+    assert sends == mine and (before, planned) == (rb, rp)
+    assert before > 2.0 and len(sends) > 0
+
+    out = bal.select(ps, d_elems, d_procs.clone()).cpu().numpy()
+    t.cuda.synchronize()
+    # nothing but eligible particles changed, targets belong to the particle's sbar
+    changed = out != new_procs
+    assert not changed[~stay].any()
+    assert np.array_equal(out[~changed], new_procs[~changed])
+    g_of = sbar[np.where(stay, new_elems, 0)]
+    for g in np.unique(g_of[changed]):
+        assert set(np.unique(out[changed & (g_of == g)])) <= set(table[int(g)]) - {r}
+    # counts per (sbar, target) = ceil(plan), capped by the particles available in order of targets
+    for g in sorted({s for s, _, _ in sends}):
+        have = int(np.count_nonzero(stay & (g_of == g)))
+        for s, q, a in sends:
+            if s != g:
+                continue
+            n = min(int(np.ceil(a - 1e-9)), have)
+            have -= n
+            assert np.count_nonzero(changed & (g_of == g) & (out == q)) == n
+    # particles in other parts' cores go first (selectNonCoreParticles, pumipic_lb.hpp:246-266)
+    for g in sorted({s for s, _, _ in sends}):
+        cand = stay & (g_of == g)
+        noncore = cand & (own[np.where(stay, new_elems, 0)] != r)
+        moved = int(np.count_nonzero(changed & cand))
+        assert np.count_nonzero(changed & noncore) == min(moved, int(np.count_nonzero(noncore)))
+    # the plan is consumed: a second selection moves nothing more
+    again = bal.select(ps, d_elems, dev(out)).cpu().numpy()
+    assert np.array_equal(again, out)
+
+
+def test_partition_of_particles_per_element():
+    """testBalanceArray (test_lb.cpp:78-130) from rank 3's side: (rank+1)*50 particles per element."""
+    P = pp()
+    full, owner, parts = _picparts()
+    table, nverts = _global_table(parts)
+    vof = _vertex_of(table)
+    r = 3
+    bal, sbar, own, safe = _rank_setup(r, parts, table)
+    ne = sbar.shape[0]
+    ppe = np.full(ne, (r + 1) * 50, np.int32)
+    ppe[::7] = 0
+    d_ppe = dev(ppe)
+    bal.add_weights_array(d_ppe)
+    w = bal.weights()
+    for q in range(NR):                       # what the all-reduce would add for the other ranks
+        if q != r:
+            w[vof[(0, q)]] = float((q + 1) * 50 * ne)
+    wh = w.cpu().numpy()
+    assert wh[vof[(0, r)]] == ppe.sum()
+    sends, (before, planned) = bal.balance(None, tol=1.05)
+    assert planned <= 1.05 < before and all(q != r for _, q, _ in sends)
+    nptcls = int(ppe.sum())
+    out = bal.select_array(d_ppe, nptcls).cpu().numpy()
+    assert out.shape[0] == nptcls
+    want = {q: int(np.ceil(a - 1e-9)) for _, q, a in sends}
+    got = np.bincount(out, minlength=NR)
+    for q in range(NR):
+        assert got[q] == (want.get(q, 0) if q != r else nptcls - sum(want.values()))
+    # one call = add_weights + balance + select; with no peers' weights the rank is the only
+    # loaded one and spreads its particles evenly
+    out2 = bal.partition(None, d_ppe, 1.05).cpu().numpy()
+    got2 = np.bincount(out2, minlength=NR)
+    assert got2.sum() == nptcls and got2.max() / got2.mean() <= 1.06
+
+
+def test_single_rank_and_errors():
+    P = pp()
+    sbar = np.zeros(10, np.int32)
+    own = np.zeros(10, np.int32)
+    bal = P.Balancer(1, 0, {0: (0,)}, sbar, own)
+    ppe = np.full(10, 3, np.int32)
+    ps = _ps_with(ppe, P.capi.PP_PS_SCS)
+    cap = ps.capacity
+    ne, npr = dev(np.zeros(cap, np.int32)), dev(np.zeros(cap, np.int32))
+    out = bal.repartition(None, ps, 1.05, ne, npr)          # pumipic_lb.hpp:360-361: no-op
+    assert not out.cpu().numpy().any()
+    assert not bal.partition(None, dev(ppe), 1.05).cpu().numpy().any() # :370-377: all stay on rank 0
+    with pytest.raises(P.PumipicError):
+        P.Balancer(2, 0, {0: (1, 0)}, sbar, own)             # unsorted parts
+    b2 = P.Balancer(2, 1, {0: (0, 1)}, sbar, own)
+    with pytest.raises(P.PumipicError, match="no plan"):
+        b2.select(ps, ne, npr)
