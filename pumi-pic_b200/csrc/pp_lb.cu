@@ -356,7 +356,8 @@ static pp_status lb_publish_counts(pp_balancer* b, cudaStream_t s) {
 
 extern "C" pp_status pp_balancer_add_weights_ps(pp_balancer* b, pp_ps* ps, const int32_t* new_elems,
                                                 const int32_t* new_procs, pp_stream stream_) {
-  PP_REQUIRE(b && ps && new_elems && new_procs, "null argument");
+  // an empty structure (capacity 0) has no slot arrays: a rank without particles still takes part
+  PP_REQUIRE(b && ps && ((new_elems && new_procs) || ps->capacity == 0), "null argument");
   cudaStream_t s = (cudaStream_t)stream_;
   const int nbins = b->nlocal + b->nranks;
   PP_CUDA(cudaMemsetAsync(b->counts, 0, sizeof(int) * (size_t)nbins, s));
@@ -460,7 +461,7 @@ extern "C" pp_status pp_balancer_plan(const pp_balancer* b, int32_t* nsends, con
 
 extern "C" pp_status pp_balancer_select_ps(pp_balancer* b, pp_ps* ps, const int32_t* new_elems,
                                            int32_t* new_procs, pp_stream stream_) {
-  PP_REQUIRE(b && ps && new_elems && new_procs, "null argument");
+  PP_REQUIRE(b && ps && ((new_elems && new_procs) || ps->capacity == 0), "null argument");
   PP_REQUIRE(b->has_plan, "no plan: call pp_balancer_balance first");
   if (b->nranks == 1 || b->plan_sbar.empty() || ps->capacity <= 0) return PP_OK;
   cudaStream_t s = (cudaStream_t)stream_;

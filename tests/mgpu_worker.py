@@ -391,11 +391,16 @@ def main():
     dist.init_process_group("nccl" if R > 1 else "gloo", device_id=torch.device("cuda", local) if R > 1 else None)
     P = importlib.import_module("pumi-pic_b200")
     comm = P.Comm()
-    test_comm_array(P, comm, rank, R)
-    test_migrate(P, comm, rank, R)
-    test_pic_loop(P, comm, rank, R)
-    test_partial_picparts(P, comm, rank, R)
-    if R > 1:          # one rank: repartition is a no-op (pumipic_lb.hpp:360-361)
+    only = os.environ.get("MGPU_ONLY", "")       # e.g. MGPU_ONLY=balancer for one scenario
+    if only in ("", "comm_array"):
+        test_comm_array(P, comm, rank, R)
+    if only in ("", "migrate"):
+        test_migrate(P, comm, rank, R)
+    if only in ("", "pic_loop"):
+        test_pic_loop(P, comm, rank, R)
+    if only in ("", "partial"):
+        test_partial_picparts(P, comm, rank, R)
+    if R > 1 and only in ("", "balancer"):   # one rank: repartition is a no-op (pumipic_lb.hpp:360-361)
         test_balancer(P, comm, rank, R)
     dist.barrier()
     if rank == 0:
@@ -404,4 +409,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        # a rank that fails must not sit in NCCL teardown while its peers wait in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)

@@ -172,3 +172,11 @@ def test_single_rank_and_errors():
     b2 = P.Balancer(2, 1, {0: (0, 1)}, sbar, own)
     with pytest.raises(P.PumipicError, match="no plan"):
         b2.select(ps, ne, npr)
+    # a rank without particles (capacity 0, no slot arrays) still takes part in every step
+    empty = _ps_with(np.zeros(10, np.int32), P.capi.PP_PS_SCS)
+    z = dev(np.zeros(empty.capacity, np.int32))
+    b2.add_weights(empty, z, z)
+    assert not b2.weights().cpu().numpy().any()
+    assert b2.balance(None)[0] == []
+    b2.select(empty, z, z)
+    b2.repartition(None, empty, 1.05, z, z)
