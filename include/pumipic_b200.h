@@ -322,6 +322,10 @@ typedef struct pp_ps_layout {
   const int32_t* slot_elem;      /* [capacity] */
 } pp_ps_layout;
 pp_status pp_ps_get_layout(pp_ps* ps, pp_stream stream, pp_ps_layout* out);
+/* ParticleStructure::getPIDs (particle_structs/src/ps_for.hpp:57-88): pids[nptcls] = the slots of
+ * the masked particles grouped by element (ascending slot inside a group), offsets[nelems+1] = the
+ * start of each element's group; both device int32. */
+pp_status pp_ps_get_pids(pp_ps* ps, int32_t* pids, int32_t* offsets, pp_stream stream);
 
 /* rebuild (particle_structure.hpp:99-100; SCS_rebuild.h:123, CSR_rebuild.hpp:18, dps_rebuild.hpp):
  *   new_element[capacity]       new parent element per slot, -1 deletes the particle

@@ -428,6 +428,14 @@ class ParticleStructure:
         check(lib().pp_ps_get_layout(self.h, _stream(), C.byref(lay)))
         return lay
 
+    def get_pids(self):
+        """ParticleStructure::getPIDs: (pids[nptcls], offsets[nelems+1]) as cuda int32 tensors."""
+        torch = _torch()
+        pids = torch.empty(self.nptcls, dtype=torch.int32, device="cuda")
+        offsets = torch.empty(self.nelems + 1, dtype=torch.int32, device="cuda")
+        check(lib().pp_ps_get_pids(self.h, _ptr(pids), _ptr(offsets), _stream()))
+        return pids, offsets
+
     def slot_elem_and_mask(self):
         """(slot_elem[cap] int32, mask[cap] uint8) on the host (test helper)."""
         torch = _torch()

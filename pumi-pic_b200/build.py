@@ -63,21 +63,27 @@ def build(verbose=False, force=False, extra_flags=(), lib=None, obj=None):
     return LIB
 
 
+CPP_DRIVERS = ("pseudo_push_and_search", "mirror_api")
+
+
 def build_cpp_tests():
-    """nvcc-compiled driver that exercises the C++ API mirror (tests/cpp); the binary travels to
-    the GPU box with the snapshot."""
-    src = os.path.join(ROOT, "tests", "cpp", "pseudo_push_and_search.cu")
+    """nvcc-compiled drivers that exercise the C++ API mirror (tests/cpp); the binaries travel to
+    the GPU box with the snapshot.  Returns the path of the first one (the PIC-loop driver)."""
     out_dir = os.path.join(ROOT, "tests", "cpp", "_bin")
-    out = os.path.join(out_dir, "pseudo_push_and_search")
     os.makedirs(out_dir, exist_ok=True)
     hdr = os.path.join(HERE, "cpp", "pumipic_b200.hpp")
-    if _newer(src, out, [hdr, LIB, os.path.join(ROOT, "include", "pumipic_b200.h")]):
-        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2",
-                               "-std=c++17", "--extended-lambda", "-fmad=false",
-                               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "cpp"),
-                               src, "-o", out, "-L", HERE, "-lpumipic_b200",
-                               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../../pumi-pic_b200"])
-    return out
+    outs = []
+    for name in CPP_DRIVERS:
+        src = os.path.join(ROOT, "tests", "cpp", name + ".cu")
+        out = os.path.join(out_dir, name)
+        outs.append(out)
+        if _newer(src, out, [hdr, LIB, os.path.join(ROOT, "include", "pumipic_b200.h")]):
+            subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2",
+                                   "-std=c++17", "--extended-lambda", "-fmad=false",
+                                   "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "cpp"),
+                                   src, "-o", out, "-L", HERE, "-lpumipic_b200",
+                                   "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../../pumi-pic_b200"])
+    return outs[0]
 
 
 if __name__ == "__main__":

@@ -130,6 +130,7 @@ PROTOTYPES = {
     "pp_ps_kind_of": (C.c_int32, [C.c_void_p]),
     "pp_ps_member": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), c_i64p]),
     "pp_ps_get_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PsLayout)]),
+    "pp_ps_get_pids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pp_ps_rebuild": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                 C.POINTER(C.c_void_p), C.c_void_p]),
     "pp_ps_set_staged_rebuild": (None, [C.c_int32]),

@@ -15,6 +15,9 @@
 //   pumipic::search_mesh / search_mesh_2d    src/pumipic_adjacency.hpp:37-45,559-562,1013-1020
 //   pumipic::migrate_ptcls / setUnsafeProcs  src/pumipic_ptcl_ops.hpp:12-85
 //   pumipic::Distributor                     particle_structs/src/support/psDistributor.hpp:10-28
+//   pumipic::ParticleBalancer / migrate_lb_ptcls   src/pumipic_lb.hpp:32-115, pumipic_ptcl_ops.hpp:55-71
+//   PS_Comm_* (ViewComm)                     support/ViewComm.h:51-291
+//   getPIDs / getMemberView                  particle_structs/src/ps_for.hpp:57-88, MemberTypeLibraries.h:90-105
 //
 // Differences forced by the missing third-party stack (no Kokkos, no Omega_h here): device arrays
 // are pumipic::View<T> (a ref-counted cudaMalloc buffer with data()/size(), the role of
@@ -136,20 +139,55 @@ template <std::size_t N, typename H, typename... T> struct MemberTypeAtIndex<N, 
   typedef typename MemberTypeAtIndex<N - 1, MemberTypes<T...>>::type type;
 };
 
-// MemberTypeViews (MemberTypeLibraries.h:17): one device array per member, [ncomp][n]
+// MemberTypeViews (MemberTypeLibraries.h:17): one device array per member, [ncomp][n]; the entry
+// after the last member keeps n so that getMemberView can index component-major
 typedef void** MemberTypeViews;
 template <class DataTypes> MemberTypeViews createMemberViews(int n) {
   pp_member_desc d[DataTypes::size ? DataTypes::size : 1];
   DataTypes::describe(d);
-  void** v = new void*[DataTypes::size];
+  void** v = new void*[DataTypes::size + 1];
   for (std::size_t i = 0; i < DataTypes::size; ++i)
     cuda_check(cudaMalloc(&v[i], (size_t)d[i].scalar_bytes * d[i].ncomp * (n > 0 ? n : 1)), "createMemberViews");
+  v[DataTypes::size] = reinterpret_cast<void*>(static_cast<std::intptr_t>(n > 0 ? n : 0));
   return v;
 }
 template <class DataTypes> void destroyViews(MemberTypeViews v) {
   if (!v) return;
   for (std::size_t i = 0; i < DataTypes::size; ++i) cudaFree(v[i]);
   delete[] v;
+}
+// getMemberView<DataTypes, N>(mtv) (MemberTypeLibraries.h:90-105): typed access to the N-th array
+// of a MemberTypeViews; view(i) / view(i, c) = particle i, component c (device code), plus
+// host <-> device copies of the whole array in the same [ncomp][n] order.
+template <class Type>
+class MemberView {
+ public:
+  typedef typename BaseType<Type>::type Base;
+  static constexpr int ncomp = BaseType<Type>::size;
+  MemberView() : p_(nullptr), n_(0) {}
+  MemberView(Base* p, long n) : p_(p), n_(n) {}
+  PP_DEV_INLINE Base& operator()(const int& i) const { return p_[i]; }
+  PP_DEV_INLINE Base& operator()(const int& i, const int& c) const { return p_[(long)c * n_ + i]; }
+  Base* data() const { return p_; }
+  long size() const { return n_; }
+  void fromHost(const std::vector<Base>& h) const {      // h[c * n + i]
+    if (n_) cuda_check(cudaMemcpy(p_, h.data(), sizeof(Base) * ncomp * n_, cudaMemcpyHostToDevice), "MemberView h2d");
+  }
+  std::vector<Base> toHost() const {
+    std::vector<Base> h((size_t)ncomp * n_);
+    if (n_) cuda_check(cudaMemcpy(h.data(), p_, sizeof(Base) * ncomp * n_, cudaMemcpyDeviceToHost), "MemberView d2h");
+    return h;
+  }
+
+ private:
+  Base* p_;
+  long n_;
+};
+template <class DataTypes, std::size_t N>
+MemberView<typename MemberTypeAtIndex<N, DataTypes>::type> getMemberView(MemberTypeViews v) {
+  typedef typename MemberTypeAtIndex<N, DataTypes>::type T;
+  const long n = (long)reinterpret_cast<std::intptr_t>(v[DataTypes::size]);
+  return MemberView<T>(static_cast<typename BaseType<T>::type*>(v[N]), n);
 }
 
 // ---------------------------------------------------------------- Segment: by-value accessor
@@ -237,6 +275,14 @@ class ParticleStructure {
                            (int32_t)new_particle_elements.size(), new_particle_elements.data(),
                            new_particle_info, &st, stream_),
              "ParticleStructure::migrate");
+  }
+  // ps_for.hpp:57-88: slots of the masked particles grouped by element + each group's start
+  template <typename ViewT>
+  void getPIDs(ViewT& pids, ViewT& offsets) {
+    offsets = ViewT((size_t)nElems() + 1);
+    pids = ViewT((size_t)nPtcls());
+    pp_check(pp_ps_get_pids(h_, pids.data(), offsets.data(), stream_), "ParticleStructure::getPIDs");
+    cuda_check(cudaStreamSynchronize((cudaStream_t)stream_), "ParticleStructure::getPIDs");
   }
   virtual void printMetrics() const {
     std::printf("%s: elements %d rows %d particles %d capacity %d\n", name.c_str(), nElems(), numRows(),
@@ -407,7 +453,31 @@ class Mesh {
     pp_check(pp_mesh_create(&d, nullptr, &h_), "Mesh");
     nents_[0] = d.nverts; nents_[dim - 1] = d.nsides; nents_[dim] = d.nelems;
   }
-  ~Mesh() { if (h_) pp_mesh_destroy(h_); }
+  // pumipic::Mesh(Input&) (pumipic_mesh.cpp / pumipic_part_construct.cpp:116-262): the PICpart of
+  // this rank as pp_host_picpart_build / pp_host_picpart_read made it.  The record stays owned by
+  // the caller and must outlive the Mesh.  With a communicator of more than one rank the comm-array
+  // plans of setupComm (pumipic_comm.cpp:12-184) are built per entity dimension on first use.
+  Mesh(const pp_host_picpart* record, pp_comm* comm) : dim_(0), comm_(comm), record_(record) {
+    const pp_host_mesh* m = pp_host_picpart_mesh(record);
+    if (!m) throw std::runtime_error("Mesh: the PICpart record has no mesh");
+    dim_ = pp_host_mesh_dim(m);
+    for (int d = 0; d <= dim_; ++d) nents_[d] = pp_host_mesh_nents(m, d);
+    pp_mesh_desc d;
+    d.dim = dim_; d.nverts = nents_[0]; d.nelems = nents_[dim_]; d.nsides = nents_[dim_ - 1];
+    d.coords = pp_host_mesh_coords(m);
+    d.elem2verts = pp_host_mesh_ent2verts(m, dim_);
+    d.elem2sides = pp_host_mesh_down(m, dim_);
+    d.side2verts = pp_host_mesh_ent2verts(m, dim_ - 1);
+    d.elem_class = hostTag<int32_t>(dim_, "class_id", false);
+    d.memspace = PP_HOST;
+    pp_check(pp_mesh_create(&d, nullptr, &h_), "Mesh");
+    pp_check(pp_mesh_set_picpart(h_, hostTag<int32_t>(dim_, "safe"), hostTag<int32_t>(dim_, "ownership"),
+                                 pp_host_picpart_rank(record), PP_HOST, nullptr), "Mesh: PICpart tags");
+  }
+  ~Mesh() {
+    for (int d = 0; d < 4; ++d) if (plan_[d]) pp_comm_plan_destroy(plan_[d]);
+    if (h_) pp_mesh_destroy(h_);
+  }
   Mesh(const Mesh&) = delete;
   Mesh& operator=(const Mesh&) = delete;
   int dim() const { return dim_; }
@@ -415,7 +485,30 @@ class Mesh {
   lid_t nents(int d) const { return nents_[d]; }
   pp_mesh* handle() const { return h_; }
   pp_mesh* operator->() const { return h_; }
-  bool isFullMesh() const { return true; }
+  bool isFullMesh() const { return record_ ? pp_host_picpart_is_full_mesh(record_) != 0 : true; }
+  // ---- the PICpart record (pumipic_mesh.hpp:33-52); only for a Mesh made from one
+  const pp_host_picpart* record() const { return record_; }
+  int numBuffers(int edim) const { return dimInfo(edim).num_cores + 1; }
+  std::vector<lid_t> bufferedRanks(int edim) const {
+    const pp_host_picpart_dim i = dimInfo(edim);
+    return std::vector<lid_t>(i.buffered_parts, i.buffered_parts + (i.num_cores > 0 ? i.num_cores : 0));
+  }
+  View<gid_t> globalIds(int edim) const {
+    const int64_t* g = hostTag<int64_t>(edim, "gids");
+    return View<gid_t>(std::vector<gid_t>(g, g + nents_[edim]));
+  }
+  View<lid_t> safeTag() const { return tagView(dim_, "safe"); }
+  View<lid_t> entOwners(int edim) const { return tagView(edim, "ownership"); }
+  View<lid_t> rankLocalIndex(int edim) const { return tagView(edim, "rank_lids"); }
+  View<lid_t> nentsOffsets(int edim) const {
+    const pp_host_picpart_dim i = dimInfo(edim);
+    return View<lid_t>(std::vector<lid_t>(i.offset_ents_per_rank,
+                                          i.offset_ents_per_rank + pp_host_picpart_nranks(record_) + 1));
+  }
+  View<lid_t> commArrayIndex(int edim) const {
+    const pp_host_picpart_dim i = dimInfo(edim);
+    return View<lid_t>(std::vector<lid_t>(i.ent_to_comm_arr_index, i.ent_to_comm_arr_index + i.nents));
+  }
   // PICpart tags (Mesh::safeTag(), Mesh::entOwners(dim)) and the communicator
   void setPICpart(const std::vector<int>& safe, const std::vector<int>& owners, int self_rank, pp_comm* comm) {
     pp_check(pp_mesh_set_picpart(h_, safe.data(), owners.data(), self_rank, PP_HOST, nullptr), "setPICpart");
@@ -430,19 +523,58 @@ class Mesh {
   template <class T> View<T> createCommArray(int edim, int nvals, T init) {   // pumipic_comm.cpp:187-192
     return View<T>((size_t)nents_[edim] * nvals, init);
   }
-  // full-mesh PICparts: SUM/MAX/MIN over all copies, or the owner's value (pumipic_comm.cpp:223-247)
-  void reduceCommArray(int edim, Op op, View<double> array, const int* ent_owner_dev = nullptr) {
-    if (!comm_) return;
+  // Mesh::reduceCommArray (pumipic_comm.cpp:223-440).  Arrays are indexed by the PICpart's own entity
+  // numbering (the reference permutes them into its "comm array" order for the MPI staging,
+  // commArrayIndex; that order is internal to it).  Full-mesh PICparts: one all-reduce, or the
+  // owner's value; partially buffered ones: owner fan-in / fan-out over the plan of this dimension.
+  template <class T>
+  void reduceCommArray(int edim, Op op, View<T> array, const int* ent_owner_dev = nullptr) {
+    if (!comm_ || pp_comm_size(comm_) == 1) return;
     const int nvals = (int)(array.size() / nents_[edim]);
-    pp_check(pp_comm_array_reduce(comm_, array.data(), nents_[edim], nvals, PP_FLOAT64, (int32_t)op,
-                                  ent_owner_dev, nullptr), "reduceCommArray");
+    const int32_t dt = std::is_same<T, double>::value ? PP_FLOAT64 : std::is_same<T, float>::value ? PP_FLOAT32
+                     : sizeof(T) == 8 ? PP_INT64 : PP_INT32;
+    if (!record_ || isFullMesh()) {
+      View<lid_t> owners;
+      if (op == BCAST_OP && !ent_owner_dev && record_) { owners = entOwners(edim); ent_owner_dev = owners.data(); }
+      pp_check(pp_comm_array_reduce(comm_, array.data(), nents_[edim], nvals, dt, (int32_t)op,
+                                    ent_owner_dev, nullptr), "reduceCommArray");
+      cuda_check(cudaStreamSynchronize(nullptr), "reduceCommArray");
+      return;
+    }
+    if (!plan_[edim])
+      pp_check(pp_comm_plan_create(comm_, nents_[edim], hostTag<int64_t>(edim, "gids"),
+                                   hostTag<int32_t>(edim, "ownership"), PP_HOST, nullptr, &plan_[edim]),
+               "reduceCommArray: setupComm");
+    pp_check(pp_comm_plan_reduce(plan_[edim], array.data(), nvals, dt, (int32_t)op, nullptr), "reduceCommArray");
   }
 
  private:
+  template <class T>
+  const T* hostTag(int edim, const char* name, bool required = true) const {
+    if (!record_) throw std::runtime_error("Mesh: not built from a PICpart record");
+    pp_host_tag t;
+    if (pp_host_mesh_find_tag(pp_host_picpart_mesh(record_), edim, name, &t) != PP_OK) {
+      if (!required) return nullptr;
+      throw std::runtime_error(std::string("Mesh: the PICpart record has no tag ") + name);
+    }
+    return static_cast<const T*>(t.data);
+  }
+  View<lid_t> tagView(int edim, const char* name) const {
+    const int32_t* p = hostTag<int32_t>(edim, name);
+    return View<lid_t>(std::vector<lid_t>(p, p + nents_[edim]));
+  }
+  pp_host_picpart_dim dimInfo(int edim) const {
+    if (!record_) throw std::runtime_error("Mesh: not built from a PICpart record");
+    pp_host_picpart_dim i;
+    pp_check(pp_host_picpart_get(record_, edim, &i), "Mesh: PICpart record");
+    return i;
+  }
   int dim_;
   lid_t nents_[4] = {0, 0, 0, 0};
   pp_mesh* h_ = nullptr;
   pp_comm* comm_;
+  const pp_host_picpart* record_ = nullptr;
+  pp_comm_plan* plan_[4] = {nullptr, nullptr, nullptr, nullptr};
   ParticleBalancer* balancer_ = nullptr;
 };
 
@@ -537,6 +669,24 @@ class ParticleBalancer {
                                 PP_HOST, c, nullptr, &h_), "ParticleBalancer");
     sbar_ids_ = View<lid_t>(elem_sbar);
   }
+  // ParticleBalancer(Mesh& picparts) (pumipic_lb.cpp:23): everything comes from the Mesh's record
+  explicit ParticleBalancer(Mesh& picparts) {
+    const pp_host_picpart* rec = picparts.record();
+    if (!rec) throw std::runtime_error("ParticleBalancer: the Mesh was not built from a PICpart record");
+    int32_t n = 0, mx = 0;
+    const int32_t *ids = nullptr, *off = nullptr, *parts = nullptr;
+    pp_check(pp_host_picpart_sbars(rec, &n, &ids, &off, &parts, &mx), "ParticleBalancer: sbars");
+    pp_host_tag sb, ow;
+    const pp_host_mesh* m = pp_host_picpart_mesh(rec);
+    pp_check(pp_host_mesh_find_tag(m, picparts.dim(), "sbar_id", &sb), "ParticleBalancer: sbar_id tag");
+    pp_check(pp_host_mesh_find_tag(m, picparts.dim(), "ownership", &ow), "ParticleBalancer: ownership tag");
+    pp_check(pp_balancer_create(pp_host_picpart_nranks(rec), pp_host_picpart_rank(rec), n, ids, off, parts,
+                                picparts.nelems(), static_cast<const int32_t*>(sb.data),
+                                static_cast<const int32_t*>(ow.data), PP_HOST, picparts.comm(), nullptr, &h_),
+             "ParticleBalancer");
+    const int32_t* p = static_cast<const int32_t*>(sb.data);
+    sbar_ids_ = View<lid_t>(std::vector<lid_t>(p, p + picparts.nelems()));
+  }
   ~ParticleBalancer() { if (h_) pp_balancer_destroy(h_); }
   ParticleBalancer(const ParticleBalancer&) = delete;
   ParticleBalancer& operator=(const ParticleBalancer&) = delete;
@@ -599,6 +749,118 @@ void migrate_lb_ptcls(Mesh& mesh, PS* ptcls, View<lid_t> new_elems, float tol, f
     mesh.ptclBalancer()->repartition(mesh, ptcls, tol, ptcl_elems, ptcl_procs, step_factor);
   }
   ptcls->migrate(ptcl_elems, ptcl_procs, Distributor(mesh.comm()));
+}
+
+// ---------------------------------------------------------------- ViewComm (support/ViewComm.h:51-291)
+// PS_Comm_* on device views over the NCCL communicator of the C ABI; `PS_Comm` stands where MPI_Comm
+// stood, PS_Request where MPI_Request stood.  NCCL has no tags: messages between a pair of ranks
+// match in posting order (the reference's call sites post one message per tag and peer, in the
+// same order on both sides).  Non-blocking sends / receives are deferred and issued together --
+// inside one ncclGroup -- by the first PS_Comm_Wait / PS_Comm_Waitall that needs one of them, which
+// is also where the reference finishes its deferred unpacks (ViewComm.h:153-154).
+typedef pp_comm* PS_Comm;
+enum PS_Op { PS_SUM = PP_SUM, PS_MAX = PP_MAX, PS_MIN = PP_MIN };
+struct PS_Request {
+  int kind = 0;            // 0 done / empty, 1 send, 2 recv
+  void* buf = nullptr;
+  int64_t count = 0;
+  int32_t dtype = 0;
+  int peer = -1;
+  pp_comm* comm = nullptr;
+};
+namespace detail {
+template <class T> struct comm_dtype;
+template <> struct comm_dtype<int> { static constexpr int32_t value = PP_INT32; };
+template <> struct comm_dtype<long> { static constexpr int32_t value = PP_INT64; };
+template <> struct comm_dtype<long long> { static constexpr int32_t value = PP_INT64; };
+template <> struct comm_dtype<float> { static constexpr int32_t value = PP_FLOAT32; };
+template <> struct comm_dtype<double> { static constexpr int32_t value = PP_FLOAT64; };
+inline std::vector<PS_Request*>& pending_requests() {
+  static std::vector<PS_Request*> p;
+  return p;
+}
+// issue every deferred message of `comm` in one group, then wait for the stream
+inline int flush_requests(pp_comm* comm) {
+  std::vector<PS_Request*>& all = pending_requests();
+  std::vector<PS_Request*> mine, rest;
+  for (PS_Request* r : all) (r->comm == comm ? mine : rest).push_back(r);
+  all.swap(rest);
+  if (mine.empty()) return 0;
+  pp_status st = pp_comm_group_start();
+  for (PS_Request* r : mine) {
+    if (st == PP_OK)
+      st = r->kind == 1 ? pp_comm_send(comm, r->buf, r->count, r->dtype, r->peer, nullptr)
+                        : pp_comm_recv(comm, r->buf, r->count, r->dtype, r->peer, nullptr);
+    r->kind = 0;
+  }
+  const pp_status en = pp_comm_group_end();
+  if (st == PP_OK) st = en;
+  if (st == PP_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = PP_ERR_CUDA;
+  return (int)st;
+}
+}  // namespace detail
+
+template <class T>
+int PS_Comm_Send(View<T> view, int offset, int size, int dest, int /*tag*/, PS_Comm comm) {
+  pp_status st = pp_comm_send(comm, view.data() + offset, size, detail::comm_dtype<T>::value, dest, nullptr);
+  if (st == PP_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = PP_ERR_CUDA;
+  return (int)st;
+}
+template <class T>
+int PS_Comm_Recv(View<T> view, int offset, int size, int source, int /*tag*/, PS_Comm comm) {
+  pp_status st = pp_comm_recv(comm, view.data() + offset, size, detail::comm_dtype<T>::value, source, nullptr);
+  if (st == PP_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = PP_ERR_CUDA;
+  return (int)st;
+}
+template <class T>
+int PS_Comm_Isend(View<T> view, int offset, int size, int dest, int /*tag*/, PS_Comm comm, PS_Request* req) {
+  req->kind = 1; req->buf = view.data() + offset; req->count = size;
+  req->dtype = detail::comm_dtype<T>::value; req->peer = dest; req->comm = comm;
+  detail::pending_requests().push_back(req);
+  return 0;
+}
+template <class T>
+int PS_Comm_Irecv(View<T> view, int offset, int size, int source, int /*tag*/, PS_Comm comm, PS_Request* req) {
+  req->kind = 2; req->buf = view.data() + offset; req->count = size;
+  req->dtype = detail::comm_dtype<T>::value; req->peer = source; req->comm = comm;
+  detail::pending_requests().push_back(req);
+  return 0;
+}
+inline int PS_Comm_Wait(PS_Request* req, void* /*status*/ = nullptr) {
+  return req->kind ? detail::flush_requests(req->comm) : 0;
+}
+inline int PS_Comm_Waitall(int num_requests, PS_Request* requests, void* /*statuses*/ = nullptr) {
+  int rc = 0;
+  for (int i = 0; i < num_requests; ++i)
+    if (requests[i].kind) { const int r = detail::flush_requests(requests[i].comm); if (r) rc = r; }
+  return rc;
+}
+template <class T>
+int PS_Comm_Alltoall(View<T> send_view, int send_size, View<T> recv_view, int /*recv_size*/, PS_Comm comm) {
+  pp_status st = pp_comm_alltoall(comm, send_view.data(), recv_view.data(), send_size,
+                                  detail::comm_dtype<T>::value, nullptr);
+  if (st == PP_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = PP_ERR_CUDA;
+  return (int)st;
+}
+template <class T>
+int PS_Comm_Ialltoall(View<T> send_view, int send_size, View<T> recv_view, int recv_size, PS_Comm comm,
+                      PS_Request* req) {
+  req->kind = 0;   // completed at once: the collective is already stream-ordered
+  return PS_Comm_Alltoall(send_view, send_size, recv_view, recv_size, comm);
+}
+template <class T>
+int PS_Comm_Allreduce(View<T> send_view, View<T> recv_view, int count, PS_Op op, PS_Comm comm) {
+  pp_status st = pp_comm_allreduce(comm, send_view.data(), recv_view.data(), count,
+                                   detail::comm_dtype<T>::value, (int32_t)op, nullptr);
+  if (st == PP_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = PP_ERR_CUDA;
+  return (int)st;
+}
+// the result is defined on `root` only, as with MPI_Reduce; the other ranks reduce into scratch
+template <class T>
+int PS_Comm_Reduce(View<T> send_view, View<T> recv_view, int count, PS_Op op, int root, PS_Comm comm) {
+  if (pp_comm_rank(comm) == root) return PS_Comm_Allreduce(send_view, recv_view, count, op, comm);
+  View<T> scratch((size_t)count);
+  return PS_Comm_Allreduce(send_view, scratch, count, op, comm);
 }
 
 // ---------------------------------------------------------------- gather (field -> particle)

@@ -178,7 +178,7 @@ extern "C" pp_status pp_comm_alltoall(pp_comm* c, const void* send, void* recv, 
 // caller's responsibility (NCCL matches a send with the peer's recv on the same communicator)
 extern "C" pp_status pp_comm_send(pp_comm* c, const void* buf, int64_t count, int32_t dtype,
                                   int32_t peer, pp_stream stream) {
-  PP_REQUIRE(c && c->nranks > 1 && buf && peer >= 0 && peer < c->nranks, "bad argument");
+  PP_REQUIRE(c && c->nranks > 1 && (buf || count == 0) && peer >= 0 && peer < c->nranks, "bad argument");
   ncclDataType_t t; size_t b;
   PP_TRY(nccl_type(dtype, &t, &b));
   PP_NCCL(g_nccl.Send(buf, (size_t)count, t, peer, c->comm, (cudaStream_t)stream));
@@ -186,7 +186,7 @@ extern "C" pp_status pp_comm_send(pp_comm* c, const void* buf, int64_t count, in
 }
 extern "C" pp_status pp_comm_recv(pp_comm* c, void* buf, int64_t count, int32_t dtype,
                                   int32_t peer, pp_stream stream) {
-  PP_REQUIRE(c && c->nranks > 1 && buf && peer >= 0 && peer < c->nranks, "bad argument");
+  PP_REQUIRE(c && c->nranks > 1 && (buf || count == 0) && peer >= 0 && peer < c->nranks, "bad argument");
   ncclDataType_t t; size_t b;
   PP_TRY(nccl_type(dtype, &t, &b));
   PP_NCCL(g_nccl.Recv(buf, (size_t)count, t, peer, c->comm, (cudaStream_t)stream));
@@ -355,7 +355,7 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
   // serial: SCS_migrate.h:20-25
   if (comm->nranks == 1)
     return pp_ps_rebuild(ps, new_element, n_new, new_particle_elements, new_particle_info, stream_);
-  PP_REQUIRE(new_process, "new_process is required");
+  PP_REQUIRE(new_process || ps->capacity == 0, "new_process is required");
   PP_REQUIRE(ps->nmembers <= 16, "at most 16 particle members are supported");
   const int R = comm->nranks, me = comm->rank;
   PackTable pt;

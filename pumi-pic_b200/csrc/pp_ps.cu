@@ -274,3 +274,62 @@ extern "C" pp_status pp_ps_get_layout(pp_ps* ps, pp_stream stream_, pp_ps_layout
   o->mask_bits = ps->mask_bits; o->slot_elem = ps->slot_elem;
   return PP_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// getPIDs (particle_structs/src/ps_for.hpp:57-88): slots of the masked particles grouped by
+// element + the start of each element's group.  The reference orders a group by atomic arrival;
+// here a stable radix sort of (element, slot) makes it ascending in slot, which is one of the
+// orders the reference can produce.
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_pid_keys(PsView v, int nelems, int* __restrict__ keys, int* __restrict__ slots) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.capacity) return;
+  int e;
+  const bool m = pp_slot_lookup(v, s, e);
+  keys[s] = m ? e : nelems;   // unmasked slots sort behind every element
+  slots[s] = s;
+}
+// offsets[e] = first position of a key >= e in the sorted keys, e = 0..nelems
+__global__ void k_pid_offsets(const int* __restrict__ sorted_keys, int n, int nelems,
+                              int* __restrict__ offsets) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > nelems) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sorted_keys[mid] < e) lo = mid + 1; else hi = mid;
+  }
+  offsets[e] = lo;
+}
+}  // namespace
+
+extern "C" pp_status pp_ps_get_pids(pp_ps* ps, int32_t* pids, int32_t* offsets, pp_stream stream_) {
+  PP_REQUIRE(ps && offsets && (pids || ps->nptcls == 0), "null argument");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int cap = ps->capacity, ne = ps->nelems;
+  if (cap == 0) {
+    PP_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int) * ((size_t)ne + 1), s));
+    return PP_OK;
+  }
+  int *keys, *slots, *keys_out, *slots_out;
+  PP_TRY(pp_dev_alloc(&keys, (size_t)cap, s));
+  PP_TRY(pp_dev_alloc(&slots, (size_t)cap, s));
+  PP_TRY(pp_dev_alloc(&keys_out, (size_t)cap, s));
+  PP_TRY(pp_dev_alloc(&slots_out, (size_t)cap, s));
+  k_pid_keys<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), ne, keys, slots);
+  int bits = 1;
+  while (bits < 31 && (1 << bits) <= ne) ++bits;   // keys are 0..ne
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys_out, slots, slots_out, cap, 0, bits, s);
+  char* tmp;
+  PP_TRY(pp_dev_alloc(&tmp, tb, s));
+  PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys_out, slots, slots_out, cap, 0, bits, s));
+  k_pid_offsets<<<pp_div_up(ne + 1, kBlock), kBlock, 0, s>>>(keys_out, cap, ne, offsets);
+  if (ps->nptcls > 0)
+    PP_CUDA(cudaMemcpyAsync(pids, slots_out, sizeof(int) * (size_t)ps->nptcls, cudaMemcpyDeviceToDevice, s));
+  pp_dev_free(tmp, s);
+  pp_dev_free(keys, s); pp_dev_free(slots, s); pp_dev_free(keys_out, s); pp_dev_free(slots_out, s);
+  PP_KERNEL_CHECK();
+  return PP_OK;
+}

@@ -173,7 +173,7 @@ extern "C" pp_status pp_push_elliptical(pp_mesh* mesh, pp_ps* ps, double* xtgt, 
 
 extern "C" pp_status pp_set_unsafe_procs(pp_mesh* mesh, pp_ps* ps, const int32_t* elems,
                                          int32_t* new_elems, int32_t* new_procs, pp_stream stream) {
-  PP_REQUIRE(mesh && ps && elems && new_elems && new_procs, "null argument");
+  PP_REQUIRE(mesh && ps && ((elems && new_elems && new_procs) || ps->capacity == 0), "null argument");
   if (ps->capacity == 0) return PP_OK;
   k_set_unsafe<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
       ps->view(), elems, mesh->aux, mesh->self_rank, new_elems, new_procs);
