@@ -216,6 +216,10 @@ class Distributor {
   Distributor() : comm_(nullptr) {}
   explicit Distributor(pp_comm* c) : comm_(c) {}
   bool isWorld() const { return true; }
+  // psDistributor.hpp:24-28: position of a rank in the distributor and back; the world
+  // distributor is the identity (usable in device code)
+  PP_INLINE int index(int rank) const { return rank; }
+  PP_INLINE int rank(int i) const { return i; }
   int num_ranks() const { return comm_ ? pp_comm_size(comm_) : 1; }
   pp_comm* comm() const { return comm_; }
 
