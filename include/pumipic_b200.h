@@ -572,22 +572,23 @@ pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_element,
 /* The plan of ParticleBalancer::balance (src/pumipic_lb.cpp:478-511), i.e. what
  * engpar::balanceWeights returns for the N-graph of buildNgraph (:395-462), evaluated for ALL parts
  * from the global weight vector.  EnGPar is a third-party dependency that is not in the reference
- * tree: the diffusion is restated from its published scheme and its parity is UNPINNED
- * (csrc/pp_host_lb.cpp); the reference's own acceptance bounds (test/test_lb.cpp:126,176) are
- * what the tests hold it to.
+ * tree and its parity is UNPINNED: instead of its neighbour-to-neighbour diffusion the plan is
+ * solved directly as a transportation problem (csrc/pp_host_lb.cpp) -- surplus of the overloaded
+ * parts -> the regions they share with underloaded parts -> their deficits, a maximum flow.  The
+ * reference's own acceptance bounds (test/test_lb.cpp:126,176) are what the tests hold it to.
  *   sbars: nsbars regions, global id sbar_ids[i], sorted parts parts[parts_off[i]..parts_off[i+1]);
  *          graph vertex of part parts[parts_off[i]+j] in sbar i = sbar_ids[i] + j (< nverts)
  *   vert_weight[nverts]: particles per vertex;  forced[nranks] (or NULL): particles each part is
  *          already receiving from others (pumipic_lb.hpp:196-200)
- *   tol: target max/avg (1.05 = 5 %); step_factor in (0,1]; max_iters <= 0 = 100
+ *   tol: target max/avg (1.05 = 5 %): at or below it nothing is planned;  step_factor in (0,1]:
+ *          EnGPar's diffusion rate, validated but without effect on a direct solve
  * Output (pp_host_free each): nsends transfers "send_weight[i] particles of vertex send_vert[i] to
  * part send_part[i]", ascending (vertex, part); imbalance[0] before, imbalance[1] planned (or NULL). */
 pp_status pp_host_lb_plan(int32_t nranks, int32_t nsbars, const int32_t* sbar_ids,
                           const int32_t* parts_off, const int32_t* parts, int32_t nverts,
                           const double* vert_weight, const double* forced, double tol,
-                          double step_factor, int32_t max_iters, int32_t* nsends,
-                          int32_t** send_vert, int32_t** send_part, double** send_weight,
-                          double* imbalance);
+                          double step_factor, int32_t* nsends, int32_t** send_vert,
+                          int32_t** send_part, double** send_weight, double* imbalance);
 
 /* pumipic::ParticleBalancer (src/pumipic_lb.hpp:32-115) for one part.
  *   sbar table: the regions this part knows (pp_host_picpart_sbars); with a communicator of more

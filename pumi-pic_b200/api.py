@@ -729,7 +729,7 @@ def _sbar_arrays(table):
     return ids, off, np.asarray(parts, np.int32)
 
 
-def host_lb_plan(nranks, table, vert_weight, forced=None, tol=1.05, step_factor=0.3, max_iters=0):
+def host_lb_plan(nranks, table, vert_weight, forced=None, tol=1.05, step_factor=0.3):
     """pp_host_lb_plan: `table` = {sbar id: sorted parts}; returns ([(vertex, part, weight)],
     (imbalance before, imbalance planned))."""
     ids, off, parts = _sbar_arrays(table)
@@ -742,7 +742,7 @@ def host_lb_plan(nranks, table, vert_weight, forced=None, tol=1.05, step_factor=
                                 off.ctypes.data_as(capi.c_i32p), parts.ctypes.data_as(capi.c_i32p),
                                 w.shape[0], w.ctypes.data_as(capi.c_dp),
                                 None if f is None else f.ctypes.data_as(capi.c_dp), tol, step_factor,
-                                max_iters, C.byref(n), C.byref(sv), C.byref(sp), C.byref(sw), imb))
+                                C.byref(n), C.byref(sv), C.byref(sp), C.byref(sw), imb))
     out = [(int(sv[i]), int(sp[i]), float(sw[i])) for i in range(n.value)]
     for p in (sv, sp, sw):
         lib().pp_host_free(p)

@@ -238,7 +238,7 @@ PROTOTYPES = {
     "pp_push_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                C.c_double, C.c_void_p]),
     "pp_host_lb_plan": (C.c_int, [C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, C.c_int32, c_dp, c_dp,
-                                  C.c_double, C.c_double, C.c_int32, c_i32p, C.POINTER(c_i32p),
+                                  C.c_double, C.c_double, c_i32p, C.POINTER(c_i32p),
                                   C.POINTER(c_i32p), C.POINTER(c_dp), c_dp]),
     "pp_balancer_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p,
                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

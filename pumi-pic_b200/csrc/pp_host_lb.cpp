@@ -8,18 +8,18 @@
 //   engpar::balanceWeights (EnGPar >= 1.1.0, third party, NOT in the reference tree; CMakeLists.txt:61)
 //   and the WeightPartitionMap it returns (:484-507).
 // EnGPar's sources are absent and no reference test fixes its output (test/test_lb.cpp only bounds
-// the resulting imbalance): PARITY UNPINNED.  What is restated is the published scheme -- diffusive
-// transfer of weight from heavier to lighter parts through the hyperedges they share, a fraction
-// step_factor of the difference per iteration split over a part's neighbours by the number of
-// shared hyperedges ("sides"), until the imbalance max/avg drops below the tolerance.
-// Differences that are deliberate:
-//   * every rank evaluates the same deterministic iteration on the global weight vector (one
-//     all-reduce of <= max_sbar + nranks doubles) instead of exchanging weights with its neighbours
-//     every iteration -- the graph has tens of vertices, the latency of one NVLink collective is
-//     the whole cost;
-//   * a vertex never plans to send more than the particles it holds when the plan is made
-//     (the reference forwards weight it has only been promised and then selects what it can);
-//   * opposite flows through one sbar are netted.
+// the resulting imbalance): PARITY UNPINNED.  EnGPar diffuses weight between neighbouring parts over
+// many iterations, each exchanging weights with its neighbours.  Here every rank holds the global
+// weight vector after ONE all-reduce of <= max_sbar + nranks doubles, so the plan is computed
+// directly, and identically on every rank, as the transportation problem that diffusion
+// approximates: overloaded parts give up their surplus over the average, through the regions
+// (sbars) they share with underloaded parts, up to what each region holds -- a maximum flow on a
+// graph of tens of nodes.  Consequences:
+//   * the plan is the best any one-hop selection can reach (particles can only be handed to a part
+//     that holds their element safely, i.e. a part of the same sbar);
+//   * a vertex never plans to send more than the particles it holds when the plan is made (the
+//     reference forwards weight it has only been promised and then selects what it can);
+//   * step_factor (EnGPar's diffusion rate) has nothing to control and is only validated.
 // No CUDA.
 #include <math.h>
 #include <stdint.h>
@@ -35,11 +35,6 @@
 void pp_set_error(const char* fmt, ...);
 
 namespace {
-
-struct Flow {
-  int32_t vert, part;
-  double w;
-};
 
 template <class T>
 T* dup_out(const std::vector<T>& v) {
@@ -59,7 +54,7 @@ double imbalance_of(const std::vector<double>& W) {
 extern "C" pp_status pp_host_lb_plan(int32_t nranks, int32_t nsbars, const int32_t* sbar_ids,
                                      const int32_t* parts_off, const int32_t* parts, int32_t nverts,
                                      const double* vert_weight, const double* forced, double tol,
-                                     double step_factor, int32_t max_iters, int32_t* nsends,
+                                     double step_factor, int32_t* nsends,
                                      int32_t** send_vert, int32_t** send_part, double** send_weight,
                                      double* imbalance) {
   if (nranks < 1 || nsbars < 0 || nverts < 0 || !nsends || !send_vert || !send_part || !send_weight ||
@@ -71,7 +66,6 @@ extern "C" pp_status pp_host_lb_plan(int32_t nranks, int32_t nsbars, const int32
     pp_set_error("pp_host_lb_plan: step_factor must be in (0, 1]");
     return PP_ERR_INVALID;
   }
-  if (max_iters <= 0) max_iters = 100;
   // sbars in ascending id order: the plan must not depend on the order the caller lists them in
   std::vector<int> order((size_t)nsbars);
   for (int i = 0; i < nsbars; ++i) order[(size_t)i] = i;
@@ -102,62 +96,77 @@ extern "C" pp_status pp_host_lb_plan(int32_t nranks, int32_t nsbars, const int32
       W[(size_t)parts[j]] += w;
     }
   }
-  // sides[p][q]: hyperedges shared by p and q
-  std::vector<int> sides((size_t)nranks * nranks, 0), side_total((size_t)nranks, 0);
-  for (int s = 0; s < nsbars; ++s)
-    for (int a = parts_off[s]; a < parts_off[s + 1]; ++a)
-      for (int b = parts_off[s]; b < parts_off[s + 1]; ++b)
-        if (a != b) sides[(size_t)parts[a] * nranks + parts[b]] += 1;
-  for (int p = 0; p < nranks; ++p)
-    for (int q = 0; q < nranks; ++q) side_total[(size_t)p] += sides[(size_t)p * nranks + q];
   if (imbalance) imbalance[0] = imbalance_of(W);
+  double avg = 0;
+  for (double x : W) avg += x;
+  avg /= (double)nranks;
 
+  // Transportation problem: source -> overloaded part p (capacity: its surplus W[p] - avg)
+  //   -> p's vertex in sbar s (capacity: the particles it holds) -> every underloaded part q of s
+  //   -> sink (capacity: q's deficit avg - W[q]); solved by shortest augmenting paths.
   std::map<std::pair<int, int>, double> flow;   // (vertex, target part) -> weight
-  for (int it = 0; it < max_iters; ++it) {
-    if (imbalance_of(W) <= tol) break;
-    const std::vector<double> snap(W);
-    double moved = 0;
-    for (int p = 0; p < nranks; ++p) {
-      if (!side_total[(size_t)p]) continue;
-      for (int q = 0; q < nranks; ++q) {
-        const int sd = sides[(size_t)p * nranks + q];
-        if (!sd || !(snap[(size_t)q] < snap[(size_t)p])) continue;
-        double want = (snap[(size_t)p] - snap[(size_t)q]) * step_factor * (double)sd /
-                      (double)side_total[(size_t)p];
-        for (int i = 0; i < nsbars && want > 0; ++i) {
-          const int s = order[(size_t)i];
-          int ip = -1, iq = -1;
-          for (int j = parts_off[s]; j < parts_off[s + 1]; ++j) {
-            if (parts[j] == p) ip = j - parts_off[s];
-            if (parts[j] == q) iq = j - parts_off[s];
-          }
-          if (ip < 0 || iq < 0) continue;
-          const int v = sbar_ids[s] + ip;
-          const double take = std::min(avail[(size_t)v], want);
-          if (!(take > 0)) continue;
-          flow[std::make_pair(v, q)] += take;
-          avail[(size_t)v] -= take;
-          W[(size_t)p] -= take;
-          W[(size_t)q] += take;
-          want -= take;
-          moved += take;
+  if (avg > 0 && imbalance_of(W) > tol) {
+    // node numbering: 0 source, 1 sink, 2 + p parts as senders, 2 + R + q parts as receivers,
+    // 2 + 2R + v vertices
+    const int R = nranks, NN = 2 + 2 * R + nverts;
+    struct Edge { int to; double cap; };
+    std::vector<Edge> edges;
+    std::vector<std::vector<int>> adj((size_t)NN);
+    auto add_edge = [&](int u, int v, double c) {
+      adj[(size_t)u].push_back((int)edges.size()); edges.push_back({v, c});
+      adj[(size_t)v].push_back((int)edges.size()); edges.push_back({u, 0.0});
+    };
+    for (int p = 0; p < R; ++p) {
+      if (W[(size_t)p] > avg) add_edge(0, 2 + p, W[(size_t)p] - avg);
+      if (W[(size_t)p] < avg) add_edge(2 + R + p, 1, avg - W[(size_t)p]);
+    }
+    std::vector<std::pair<int, std::pair<int, int>>> send_edges;   // edge index -> (vertex, target)
+    for (int i = 0; i < nsbars; ++i) {
+      const int s = order[(size_t)i];
+      for (int a = parts_off[s]; a < parts_off[s + 1]; ++a) {
+        const int p = parts[a], v = sbar_ids[s] + (a - parts_off[s]);
+        if (!(W[(size_t)p] > avg) || !(avail[(size_t)v] > 0)) continue;
+        add_edge(2 + p, 2 + 2 * R + v, avail[(size_t)v]);
+        for (int b = parts_off[s]; b < parts_off[s + 1]; ++b) {
+          const int q = parts[b];
+          if (q == p || !(W[(size_t)q] < avg)) continue;
+          send_edges.push_back(std::make_pair((int)edges.size(), std::make_pair(v, q)));
+          add_edge(2 + 2 * R + v, 2 + R + q, avail[(size_t)v]);
         }
       }
     }
-    if (moved < 0.5) break;   // less than one particle would move: stalled
-  }
-  // net opposite flows through the same sbar: (vertex of p in s -> q) against (vertex of q in s -> p)
-  for (int i = 0; i < nsbars; ++i) {
-    const int s = order[(size_t)i], k = parts_off[s + 1] - parts_off[s];
-    for (int a = 0; a < k; ++a)
-      for (int b = a + 1; b < k; ++b) {
-        auto fa = flow.find(std::make_pair(sbar_ids[s] + a, parts[parts_off[s] + b]));
-        auto fb = flow.find(std::make_pair(sbar_ids[s] + b, parts[parts_off[s] + a]));
-        if (fa == flow.end() || fb == flow.end()) continue;
-        const double m = std::min(fa->second, fb->second);
-        fa->second -= m;
-        fb->second -= m;
+    const double eps = 1e-9;
+    std::vector<int> prev_edge((size_t)NN), queue;
+    for (long guard = 0; guard < 4L * NN * (long)edges.size() + 64; ++guard) {
+      std::fill(prev_edge.begin(), prev_edge.end(), -1);
+      queue.assign(1, 0);
+      prev_edge[0] = -2;
+      for (size_t h = 0; h < queue.size() && prev_edge[1] == -1; ++h)
+        for (int e : adj[(size_t)queue[h]])
+          if (edges[(size_t)e].cap > eps && prev_edge[(size_t)edges[(size_t)e].to] == -1) {
+            prev_edge[(size_t)edges[(size_t)e].to] = e;
+            queue.push_back(edges[(size_t)e].to);
+          }
+      if (prev_edge[1] == -1) break;
+      double f = 1e300;
+      for (int v = 1; v != 0; v = edges[(size_t)(prev_edge[(size_t)v] ^ 1)].to)
+        f = std::min(f, edges[(size_t)prev_edge[(size_t)v]].cap);
+      for (int v = 1; v != 0; v = edges[(size_t)(prev_edge[(size_t)v] ^ 1)].to) {
+        edges[(size_t)prev_edge[(size_t)v]].cap -= f;
+        edges[(size_t)(prev_edge[(size_t)v] ^ 1)].cap += f;
       }
+    }
+    for (const auto& se : send_edges) {
+      const double f = edges[(size_t)(se.first ^ 1)].cap;   // flow = residual of the reverse edge
+      if (!(f > 0)) continue;
+      flow[se.second] += f;
+      const int v = se.second.first, q = se.second.second;
+      int p = -1;
+      for (int i = 0; i < nsbars && p < 0; ++i)
+        if (v >= sbar_ids[i] && v < sbar_ids[i] + (parts_off[i + 1] - parts_off[i])) p = parts[parts_off[i] + v - sbar_ids[i]];
+      W[(size_t)p] -= f;
+      W[(size_t)q] += f;
+    }
   }
   std::vector<int32_t> ov, op;
   std::vector<double> ow;

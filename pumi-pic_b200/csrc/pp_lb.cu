@@ -404,7 +404,7 @@ extern "C" pp_status pp_balancer_balance(pp_balancer* b, pp_comm* comm, double t
     double* sw = nullptr;
     PP_TRY(pp_host_lb_plan(b->nranks, (int32_t)b->sbar_ids.size(), b->sbar_ids.data(),
                            b->parts_off.data(), b->parts.data(), b->nverts, w.data(),
-                           w.data() + b->nverts, tol, step_factor, 0, &ns, &sv, &sp, &sw, b->imbalance));
+                           w.data() + b->nverts, tol, step_factor, &ns, &sv, &sp, &sw, b->imbalance));
     // keep this part's sends, grouped by local vertex in ascending (vertex, target) order
     for (int l = 0; l < b->nlocal; ++l) {
       int acc = 0;

@@ -1,4 +1,4 @@
-"""CPU-only: the weight-diffusion plan of the particle balancer.
+"""CPU-only: the plan of the particle balancer.
 
 engpar::balanceWeights is third-party code outside the reference tree and no reference test pins
 its output (PARITY UNPINNED, csrc/pp_host_lb.cpp): the bar is the reference's own acceptance test,
@@ -88,7 +88,7 @@ def test_balance_array_scenario_of_test_lb():
     assert before == pytest.approx(_imb(tot0))
     after = _imb(_apply(table, w, sends))
     assert after <= 1.3                                   # test_lb.cpp:126
-    assert after <= 1.06 and planned <= 1.05              # what the diffusion actually reaches
+    assert after <= 1.06 and planned <= 1.05              # what the plan actually reaches
     assert _apply(table, w, sends).sum() == tot0.sum()
 
 

@@ -1,7 +1,8 @@
 # multi-GPU checks on an N-GPU box: parity worker at 1/2/4 ranks, full PIC step and headline bench scaling
 N=$(nvidia-smi -L | wc -l)
 tag=${1:-r1h}
-python -m pytest tests/test_multigpu.py -x -q 2>&1 | tail -15
+mkdir -p gpurun_out
+python -m pytest tests/test_multigpu.py -x -q > gpurun_out/${tag}_multigpu.log 2>&1; tail -15 gpurun_out/${tag}_multigpu.log
 for n in 1 2 4 8; do
  [ $n -le $N ] || continue
  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n tools/bench_picstep.py --steps 10 2>gpurun_out/${tag}_picstep_$n.err | tail -1 | tee -a gpurun_out/${tag}_picstep.jsonl
