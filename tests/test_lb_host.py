@@ -179,3 +179,49 @@ def test_plan_edge_cases():
             pp.host_lb_plan(2, bad, np.zeros(4))
     with pytest.raises(pp.PumipicError):
         pp.host_lb_plan(2, table, np.zeros(2), step_factor=0.0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_plan_moves_the_maximum_possible_weight(seed):
+    """The plan is a maximum flow: surplus over the average -> shared regions -> deficits.  Its
+    total equals the optimum of the same transportation problem stated as a linear program."""
+    from scipy.optimize import linprog
+    rng = np.random.default_rng(seed)
+    R, nsb = 6, 9
+    table, gid = {}, 0
+    for _ in range(nsb):
+        k = int(rng.integers(1, R))
+        parts = tuple(sorted(rng.choice(R, size=k, replace=False).tolist()))
+        table[gid] = parts
+        gid += len(parts)
+    w = np.floor(rng.random(gid) ** 2 * 1000)
+    vpart = {g + j: (g, p) for g, ps in table.items() for j, p in enumerate(ps)}
+    W = np.zeros(R)
+    for v, (g, p) in vpart.items():
+        W[p] += w[v]
+    avg = W.mean()
+    sends, (before, planned) = pp.host_lb_plan(R, table, w, tol=1.0)
+    # LP: variables x[v, q] for v on an overloaded part, q an underloaded part of v's sbar
+    var = [(v, q) for v, (g, p) in vpart.items() if W[p] > avg for q in table[g] if q != p and W[q] < avg]
+    total = sum(a for _, _, a in sends)
+    if not var:
+        assert sends == []
+        return
+    A, b = [], []
+    for v in {v for v, _ in var}:                          # a vertex gives at most what it holds
+        A.append([1.0 if vv == v else 0.0 for vv, _ in var]); b.append(w[v])
+    for p in range(R):
+        if W[p] > avg:                                     # a part gives at most its surplus
+            A.append([1.0 if vpart[vv][1] == p else 0.0 for vv, _ in var]); b.append(W[p] - avg)
+        if W[p] < avg:                                     # and takes at most its deficit
+            A.append([1.0 if q == p else 0.0 for _, q in var]); b.append(avg - W[p])
+    res = linprog(-np.ones(len(var)), A_ub=np.asarray(A), b_ub=np.asarray(b), bounds=(0, None), method="highs")
+    assert res.status == 0
+    assert total == pytest.approx(-res.fun, rel=1e-9, abs=1e-6)
+    assert {(v, q) for v, q, _ in sends} <= set(var)
+    after = W.copy()
+    for v, q, a in sends:
+        after[vpart[v][1]] -= a
+        after[q] += a
+    assert planned == pytest.approx(after.max() / avg) and planned <= before + 1e-12
+    assert np.all(after <= np.maximum(W, avg) + 1e-6)      # nobody ends above max(own start, average)
