@@ -417,6 +417,33 @@ typedef struct pp_search_stats {
  * counters copied out. */
 pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
                          pp_search_stats* stats_host, pp_stream stream);
+/* The phases of trace_particle_through_mesh (adjacency.tpp:461-640) as separate calls, for
+ * applications that pass their own handler `Func` (called on the host once per walk iteration,
+ * between find_exit_face and set_new_element, with the device arrays elem_ids, inter_faces,
+ * lastExit, inter_points and ptcl_done).  args as for pp_search_mesh (variant PP_SEARCH_NEW);
+ * ptcl_done and last_exit are caller-owned device int32[capacity].  The loop of the reference:
+ *   pp_trace_begin                      setInitial, finishUnmoved, initializeIntersection,
+ *                                       check_initial_parents (:484-552); *not_in_elem = particles
+ *                                       deleted because their origin is outside their element
+ *   repeat { pp_trace_find_exit_face    (:232-364; BCC when !require_intersection, else ray / edge)
+ *            handler                    stock: pp_trace_check_model_intersection (:366-387)
+ *            pp_trace_set_new_element   (:390-416)
+ *            pp_trace_pending(0)        (:568-573) *count == 0 <=> every slot is done
+ *   } until done or the loop limit, then pp_trace_pending(1) removes what is left (:584-606).
+ * With the stock handler the arrays end identical to pp_search_mesh's, which does the same in
+ * one kernel and is the path to use whenever the handler is the stock one. */
+pp_status pp_trace_begin(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args, int32_t* ptcl_done,
+                         int32_t* last_exit, int32_t* not_in_elem, pp_stream stream);
+pp_status pp_trace_find_exit_face(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                                  int32_t* ptcl_done, int32_t* last_exit, pp_stream stream);
+pp_status pp_trace_check_model_intersection(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                                            int32_t* ptcl_done, int32_t* last_exit,
+                                            pp_stream stream);
+pp_status pp_trace_set_new_element(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                                   int32_t* ptcl_done, int32_t* last_exit, pp_stream stream);
+pp_status pp_trace_pending(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args, int32_t* ptcl_done,
+                           int32_t* last_exit, int32_t remove_pending, int32_t* count,
+                           pp_stream stream);
 /* Kernel selection for the barycentric walks: 2 (default) = Sell-C-sigma chunk walk where it
  * applies (C = 32, elem_ids seeded from the rows), 1 = block-staged kernel, 0 = the simple
  * thread-per-slot kernel.  All give identical results; the switch exists for A/B measurements. */

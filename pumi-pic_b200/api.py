@@ -502,6 +502,41 @@ def search_mesh(mesh, ps, x_orig, x_tgt, elem_ids, elem_ids_empty=False,
     return SearchResult(st) if sync else None
 
 
+def trace_particle_through_mesh(mesh, ps, x_orig, x_tgt, elem_ids, elem_ids_empty=False,
+                                require_intersection=False, inter_faces=None, inter_points=None,
+                                looplimit=0, handler=None):
+    """adjacency.tpp:461-640 phase by phase (pp_trace_*).  handler(elem_ids, inter_faces, last_exit,
+    inter_points, ptcl_done) stands where the reference's `Func` stands; None = the stock
+    RemoveParticleOnGeometricModelExit.  Returns (found, loops, not_in_elem, not_found)."""
+    torch = _torch()
+    a = _search_args(x_orig, x_tgt, elem_ids, elem_ids_empty, capi.PP_SEARCH_NEW,
+                     require_intersection, inter_faces, inter_points, looplimit)
+    cap = ps.capacity
+    done = torch.empty(max(cap, 1), dtype=torch.int32, device="cuda")
+    last_exit = torch.empty(max(cap, 1), dtype=torch.int32, device="cuda")
+    L, st = lib(), _stream()
+    n = C.c_int32()
+    check(L.pp_trace_begin(mesh.h, ps.h, C.byref(a), _ptr(done), _ptr(last_exit), C.byref(n), st))
+    not_in, loops, lost, found = n.value, 0, 0, False
+    while not found:
+        check(L.pp_trace_find_exit_face(mesh.h, ps.h, C.byref(a), _ptr(done), _ptr(last_exit), st))
+        if handler is None:
+            check(L.pp_trace_check_model_intersection(mesh.h, ps.h, C.byref(a), _ptr(done),
+                                                      _ptr(last_exit), st))
+        else:
+            handler(elem_ids, inter_faces, last_exit, inter_points, done)
+        check(L.pp_trace_set_new_element(mesh.h, ps.h, C.byref(a), _ptr(done), _ptr(last_exit), st))
+        check(L.pp_trace_pending(mesh.h, ps.h, C.byref(a), _ptr(done), _ptr(last_exit), 0, C.byref(n), st))
+        found = n.value == 0
+        loops += 1
+        if looplimit and loops >= looplimit:
+            check(L.pp_trace_pending(mesh.h, ps.h, C.byref(a), _ptr(done), _ptr(last_exit), 1,
+                                     C.byref(n), st))
+            lost = n.value
+            break
+    return found, loops, not_in, lost
+
+
 def push_direction_search(mesh, ps, direction, distance, x_orig, x_tgt, elem_ids,
                           elem_ids_empty=False, require_intersection=False, inter_faces=None,
                           inter_points=None, looplimit=0, sync=True, from_orig=False):

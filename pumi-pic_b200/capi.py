@@ -183,6 +183,13 @@ PROTOTYPES = {
     "pp_ps_migrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(MigrateStats),
                                 C.c_void_p]),
+    "pp_trace_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs), C.c_void_p, C.c_void_p,
+                                 c_i32p, C.c_void_p]),
+    "pp_trace_find_exit_face": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_trace_check_model_intersection": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_trace_set_new_element": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_trace_pending": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs), C.c_void_p, C.c_void_p,
+                                   C.c_int32, c_i32p, C.c_void_p]),
     "pp_search_set_staged": (None, [C.c_int32]),
     "pp_search_last_stats": (C.c_int, [C.c_void_p, C.POINTER(SearchStats), C.c_void_p]),
     "pp_push_direction_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

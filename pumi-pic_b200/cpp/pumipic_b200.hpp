@@ -625,6 +625,85 @@ bool search_mesh(Mesh& mesh, ParticleStructure<ParticleType>* ptcls, Segment3d x
   return detail::run_search(mesh, ptcls, PP_SEARCH_3D_LEGACY, x_ps_d, xtgt_ps_d, elem_ids, false, &xface_id,
                             &xpoints_d, 3, looplimit);
 }
+// adjacency.tpp:614-640 RemoveParticleOnGeometricModelExit: the stock handler of
+// trace_particle_through_mesh -- a particle whose exit side is on the model boundary is done, and
+// either keeps its element and records the side (requireIntersection) or leaves the domain.
+template <typename ParticleType, typename Segment3d>
+struct RemoveParticleOnGeometricModelExit {
+  RemoveParticleOnGeometricModelExit(Mesh&, bool requireIntersection) : requireIntersection_(requireIntersection) {}
+  void operator()(Mesh& mesh, ParticleStructure<ParticleType>* ptcls, View<lid_t>& elem_ids,
+                  View<lid_t>& inter_faces, View<lid_t>& lastExit, View<fp_t>& inter_points,
+                  View<lid_t>& ptcl_done, Segment3d /*x_ps_orig*/, Segment3d /*x_ps_tgt*/) const {
+    pp_search_args a = {};
+    a.variant = PP_SEARCH_NEW;
+    a.elem_ids = elem_ids.data();
+    a.require_intersection = requireIntersection_;
+    a.inter_faces = inter_faces.data();
+    a.inter_points = inter_points.data();
+    pp_check(pp_trace_check_model_intersection(mesh.handle(), ptcls->handle(), &a, ptcl_done.data(),
+                                               lastExit.data(), (pp_stream)ptcls->stream()),
+             "check_model_intersection");
+  }
+
+ private:
+  bool requireIntersection_;
+};
+
+// adjacency.tpp:460-612 trace_particle_through_mesh with a user handler: `func` is called on the
+// host once per walk iteration, between find_exit_face and set_new_element, as
+//   func(mesh, ptcls, elem_ids, inter_faces, lastExit, inter_points, ptcl_done, x_ps_orig, x_ps_tgt)
+// and works on the device arrays (its own kernels / parallel_for).  One kernel per phase, like the
+// reference; search_mesh (one fused kernel) is the path for the stock handler.
+template <class ParticleType, typename Segment3d, typename SegmentInt, typename Func>
+bool trace_particle_through_mesh(Mesh& mesh, ParticleStructure<ParticleType>* ptcls, Segment3d x_ps_orig,
+                                 Segment3d x_ps_tgt, SegmentInt /*pids*/, View<lid_t>& elem_ids,
+                                 bool requireIntersection, View<lid_t>& inter_faces, View<fp_t>& inter_points,
+                                 int looplimit, bool /*debug*/, Func& func) {
+  const size_t cap = (size_t)ptcls->capacity();
+  const int dim = mesh.dim();
+  pp_search_args a = {};
+  a.variant = PP_SEARCH_NEW;
+  a.x_orig = x_ps_orig.data(); a.x_tgt = x_ps_tgt.data(); a.stride = x_ps_tgt.stride();
+  a.elem_ids_empty = elem_ids.size() == 0;
+  if (elem_ids.size() == 0) elem_ids = View<lid_t>(cap, "elem_ids");                           // :504-509
+  a.elem_ids = elem_ids.data();
+  a.require_intersection = requireIntersection;
+  if (requireIntersection) {                                                                  // :535-549
+    if (inter_faces.size() < cap) inter_faces = View<lid_t>(cap, (lid_t)-1, "inter_faces");
+    if (inter_points.size() < cap * dim) inter_points = View<fp_t>(cap * dim, 0.0, "inter_points");
+  }
+  a.inter_faces = inter_faces.data();
+  a.inter_points = inter_points.data();
+  a.looplimit = looplimit;
+  View<lid_t> ptcl_done(cap > 0 ? cap : 1, "ptcl_done"), lastExit(cap > 0 ? cap : 1, "lastExit");
+  pp_stream st = (pp_stream)ptcls->stream();
+  int32_t n = 0;
+  pp_check(pp_trace_begin(mesh.handle(), ptcls->handle(), &a, ptcl_done.data(), lastExit.data(), &n, st),
+           "trace_particle_through_mesh: begin");
+  if (n) std::fprintf(stderr, "[WARNING] %d particles are not in their parent element and were deleted\n", n);
+  bool found = false;
+  int loops = 0;
+  while (!found) {
+    pp_check(pp_trace_find_exit_face(mesh.handle(), ptcls->handle(), &a, ptcl_done.data(), lastExit.data(), st),
+             "find_exit_face");
+    func(mesh, ptcls, elem_ids, inter_faces, lastExit, inter_points, ptcl_done, x_ps_orig, x_ps_tgt);
+    pp_check(pp_trace_set_new_element(mesh.handle(), ptcls->handle(), &a, ptcl_done.data(), lastExit.data(), st),
+             "set_new_element");
+    pp_check(pp_trace_pending(mesh.handle(), ptcls->handle(), &a, ptcl_done.data(), lastExit.data(), 0, &n, st),
+             "trace_particle_through_mesh: done check");
+    found = n == 0;
+    ++loops;
+    if (looplimit && loops >= looplimit) {                                                    // :584-606
+      pp_check(pp_trace_pending(mesh.handle(), ptcls->handle(), &a, ptcl_done.data(), lastExit.data(), 1, &n, st),
+               "trace_particle_through_mesh: loop limit");
+      std::fprintf(stderr, "[ERROR] loop limit %d exceeded. %d particles were not found. Deleting them...\n",
+                   looplimit, n);
+      break;
+    }
+  }
+  return found;
+}
+
 // adjacency.hpp:316-324 search_mesh_3d (GITRm's search: barycentric_coords_tet with tol 1e-20)
 template <class ParticleStruct, typename CurrentCoordView, typename TargetCoordView, typename SegmentInt>
 bool search_mesh_3d(Mesh& mesh, ParticleStruct* ptcls, CurrentCoordView x_ps_d, TargetCoordView xtgt_ps_d,

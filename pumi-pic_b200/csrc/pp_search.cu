@@ -1486,3 +1486,312 @@ extern "C" pp_status pp_push_direction_search_host(pp_mesh* mesh, pp_ps* ps, con
   if (stats_host) PP_TRY(read_stats(mesh, PP_SEARCH_NEW, looplimit, stats_host, s));
   return PP_OK;
 }
+
+// ==========================================================================================
+// Stepped walk: the phases of trace_particle_through_mesh (adjacency.tpp:461-640) as separate
+// calls, for applications that supply their own per-iteration handler (the `Func` argument,
+// called on the host between find_exit_face and set_new_element with the device arrays
+// elem_ids, inter_faces, lastExit, inter_points, ptcl_done).  One kernel per phase over all slots
+// like the reference -- the fused pp_search_mesh is the fast path whenever the handler is the
+// stock RemoveParticleOnGeometricModelExit; with that handler both give identical arrays.
+// ==========================================================================================
+namespace {
+struct TraceParams {
+  PsView ps;
+  const void* walk;
+  const int* elem2sides;
+  const int8_t* exposed;
+  const int* side2elem;
+  const double* xo;
+  const double* xt;
+  long stride;
+  int* elem_ids;
+  int ids_empty;
+  int* inter_faces;
+  double* inter_points;
+  int require_x;
+  int* done;
+  int* last_exit;
+  double tol;
+  int* counter;
+};
+
+// setInitial :504-522, finishUnmoved :525-533, initializeIntersection :535-549,
+// check_initial_parents :73-145
+template <int DIM>
+__global__ void k_trace_begin(TraceParams p) {
+  using Rec = typename std::conditional<DIM == 3, Tet, Tri>::type;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.ps.capacity) return;
+  int erow;
+  const bool mask = pp_slot_lookup(p.ps, s, erow);
+  int done = 0, E;
+  if (p.ids_empty) {
+    E = mask ? erow : -1;
+    if (!mask) done = 1;
+  } else {
+    E = p.elem_ids[s];
+    if ((mask && E == -1) || !mask) done = 1;
+  }
+  d3 org = {0, 0, 0}, tgt = {0, 0, 0};
+  if (mask) {
+    org = {p.xo[s], p.xo[p.stride + s], p.xo[2 * p.stride + s]};
+    tgt = {p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+    if (norm3(tgt - org) < p.tol) done = 1;
+  }
+  if (p.require_x) {
+    p.inter_faces[s] = -1;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) p.inter_points[(long)DIM * s + i] = 0.0;
+  }
+  if (mask && !done) {
+    Rec rec;
+    load_rec(p.walk, E, rec);
+    bool inside;
+    if constexpr (DIM == 3) {
+      double b[4];
+      bcc_tet(rec, org, b);
+      inside = all_positive<4>(b, p.tol);
+    } else {
+      double b[3];
+      bcc_tri(rec, d2{org.x, org.y}, b);
+      inside = all_positive<3>(b, p.tol);
+    }
+    if (!inside) { atomicAdd(p.counter, 1); E = -1; done = 1; }
+  }
+  if (p.ids_empty || mask) p.elem_ids[s] = E;
+  p.done[s] = done;
+  p.last_exit[s] = -1;
+}
+
+// find_exit_face :232-364
+template <int DIM, bool BCC>
+__global__ void k_trace_find_exit(TraceParams p) {
+  using Rec = typename std::conditional<DIM == 3, Tet, Tri>::type;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.ps.capacity) return;
+  const bool mask = (__ldg(p.ps.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  if (!mask || p.done[s]) return;
+  const int E = p.elem_ids[s];
+  Rec rec;
+  load_rec(p.walk, E, rec);
+  const d3 tgt = {p.xt[s], p.xt[p.stride + s], p.xt[2 * p.stride + s]};
+  const int* sides = p.elem2sides + (long)(DIM + 1) * E;
+  if constexpr (BCC) {
+    int f;
+    bool done;
+    if constexpr (DIM == 3) {
+      double b[4];
+      bcc_tet(rec, tgt, b);
+      done = all_positive<4>(b, kEps);
+      f = min_index4(b);
+    } else {
+      double b[3];
+      bcc_tri(rec, d2{tgt.x, tgt.y}, b);
+      done = all_positive<3>(b, kEps);
+      f = min3(b);
+    }
+    p.done[s] = done;
+    p.last_exit[s] = __ldg(sides + f);
+  } else {
+    const d3 org = {p.xo[s], p.xo[p.stride + s], p.xo[2 * p.stride + s]};
+    const int prev = p.last_exit[s];
+    int le = -1;
+    if constexpr (DIM == 3) {
+      const d3 disp = tgt - org;
+      const double seg = norm3(disp);
+      const d3 dir = {disp.x / seg, disp.y / seg, disp.z / seg};
+      double quality = -1;
+      int best = -1;
+#pragma unroll
+      for (int fi = 0; fi < 4; ++fi) {
+        const int F = __ldg(sides + fi);
+        if (F == prev) continue;
+        const unsigned code = (rec.codes >> (8 * fi)) & 0xffu;
+        const d3 V0 = vert_of(rec, code & 3), V1 = vert_of(rec, (code >> 2) & 3),
+                 V2 = vert_of(rec, (code >> 4) & 3);
+        d3 xp;
+        double dproj, closeness;
+        const bool hit = ray_tri(V0, V1, V2, org, dir, p.tol, (code >> 6) & 1, xp, dproj, closeness);
+        bool write = false;
+        if (hit) { le = F; write = true; }
+        if (dproj > -p.tol && (quality < 0 || closeness < quality) && le == -1) {
+          quality = closeness; best = F; write = true;
+        }
+        if (write) {
+          p.inter_points[3 * (long)s] = xp.x;
+          p.inter_points[3 * (long)s + 1] = xp.y;
+          p.inter_points[3 * (long)s + 2] = xp.z;
+        }
+      }
+      if (le == -1) le = best;
+    } else {
+#pragma unroll
+      for (int ei = 0; ei < 3; ++ei) {
+        const int F = __ldg(sides + ei);
+        if (F == prev) continue;
+        const unsigned code = (rec.codes >> (8 * ei)) & 0xffu;
+        d2 xp;
+        const bool hit = line_edge(vert_of(rec, code & 3), vert_of(rec, (code >> 2) & 3),
+                                   d2{org.x, org.y}, d2{tgt.x, tgt.y}, p.tol, (code >> 6) & 1, xp);
+        if (hit) {
+          le = F;
+          p.inter_points[2 * (long)s] = xp.x;
+          p.inter_points[2 * (long)s + 1] = xp.y;
+        }
+      }
+    }
+    p.last_exit[s] = le;
+    p.done[s] = (le == -1);
+  }
+}
+
+// check_model_intersection :366-387
+__global__ void k_trace_model_exit(TraceParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.ps.capacity) return;
+  const bool mask = (__ldg(p.ps.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  if (!mask || p.done[s]) return;
+  const int bridge = p.last_exit[s];
+  const bool ex = p.exposed[bridge] != 0;
+  p.done[s] = ex;
+  if (ex && p.require_x) p.inter_faces[s] = bridge;
+  else if (ex) p.elem_ids[s] = -1;
+}
+
+// set_new_element :390-416
+__global__ void k_trace_next_elem(TraceParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.ps.capacity) return;
+  const bool mask = (__ldg(p.ps.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  if (!mask || p.done[s]) return;
+  const int cur = p.elem_ids[s];
+  const int bridge = p.last_exit[s];
+  const int A = __ldg(p.side2elem + 2 * (long)bridge), B = __ldg(p.side2elem + 2 * (long)bridge + 1);
+  p.elem_ids[s] = (A == cur) ? B : A;
+}
+
+// :568-573 counts the slots (masked or not) that are not done; :584-606 with `sweep` also removes
+// the masked ones among them
+__global__ void k_trace_pending(TraceParams p, int sweep) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  bool pending = false;
+  if (s < p.ps.capacity) {
+    const bool mask = (__ldg(p.ps.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+    if (sweep) {
+      pending = mask && !p.done[s];
+      if (pending) p.elem_ids[s] = -1;
+    } else {
+      pending = !p.done[s];
+    }
+  }
+  const int n = __popc(__ballot_sync(0xffffffffu, pending));
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(p.counter, n);
+}
+
+pp_status trace_params(pp_mesh* mesh, pp_ps* ps, const pp_search_args* a, int32_t* done,
+                       int32_t* last_exit, bool need_positions, TraceParams* p) {
+  PP_REQUIRE(mesh && ps && a && done && last_exit, "null argument");
+  PP_REQUIRE(a->variant == PP_SEARCH_NEW, "the stepped walk follows the new search API only");
+  PP_REQUIRE(a->elem_ids, "elem_ids is required");
+  PP_REQUIRE(ps->nelems == mesh->nelems, "particle structure and mesh disagree on nelems");
+  if (need_positions) {
+    PP_REQUIRE(a->x_orig && a->x_tgt, "x_orig and x_tgt are required");
+    PP_REQUIRE(a->stride >= ps->capacity, "stride smaller than capacity");
+  }
+  if (a->require_intersection)
+    PP_REQUIRE(a->inter_faces && a->inter_points, "intersection outputs are required");
+  p->ps = ps->view();
+  p->walk = mesh->walk;
+  p->elem2sides = mesh->elem2sides;
+  p->exposed = mesh->exposed;
+  p->side2elem = mesh->side2elem;
+  p->xo = a->x_orig; p->xt = a->x_tgt; p->stride = a->stride;
+  p->elem_ids = a->elem_ids; p->ids_empty = a->elem_ids_empty;
+  p->inter_faces = a->inter_faces; p->inter_points = a->inter_points;
+  p->require_x = a->require_intersection;
+  p->done = done; p->last_exit = last_exit;
+  p->tol = mesh->tol;
+  p->counter = (int*)mesh->stats_dev;   // scratch: the fused search's counters are not in use here
+  return PP_OK;
+}
+
+pp_status trace_count(pp_mesh* mesh, int32_t* out, cudaStream_t s) {
+  int h = 0;
+  PP_CUDA(cudaMemcpyAsync(&h, mesh->stats_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  if (out) *out = h;
+  return PP_OK;
+}
+constexpr int kTraceBlock = 128;
+}  // namespace
+
+extern "C" pp_status pp_trace_begin(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                                    int32_t* ptcl_done, int32_t* last_exit, int32_t* not_in_elem,
+                                    pp_stream stream) {
+  TraceParams p;
+  if (ps && ps->capacity == 0) { if (not_in_elem) *not_in_elem = 0; return PP_OK; }
+  PP_TRY(trace_params(mesh, ps, args, ptcl_done, last_exit, true, &p));
+  cudaStream_t s = (cudaStream_t)stream;
+  PP_CUDA(cudaMemsetAsync(mesh->stats_dev, 0, sizeof(SearchCounters), s));
+  const int grid = pp_div_up(p.ps.capacity, kTraceBlock);
+  if (mesh->dim == 3) k_trace_begin<3><<<grid, kTraceBlock, 0, s>>>(p);
+  else k_trace_begin<2><<<grid, kTraceBlock, 0, s>>>(p);
+  PP_KERNEL_CHECK();
+  return trace_count(mesh, not_in_elem, s);
+}
+
+extern "C" pp_status pp_trace_find_exit_face(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                                             int32_t* ptcl_done, int32_t* last_exit,
+                                             pp_stream stream) {
+  TraceParams p;
+  if (ps && ps->capacity == 0) return PP_OK;
+  PP_TRY(trace_params(mesh, ps, args, ptcl_done, last_exit, true, &p));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = pp_div_up(p.ps.capacity, kTraceBlock);
+  const bool bcc = !args->require_intersection;   // useBcc = !requireIntersection (:490)
+  if (mesh->dim == 3) {
+    if (bcc) k_trace_find_exit<3, true><<<grid, kTraceBlock, 0, s>>>(p);
+    else k_trace_find_exit<3, false><<<grid, kTraceBlock, 0, s>>>(p);
+  } else {
+    if (bcc) k_trace_find_exit<2, true><<<grid, kTraceBlock, 0, s>>>(p);
+    else k_trace_find_exit<2, false><<<grid, kTraceBlock, 0, s>>>(p);
+  }
+  PP_KERNEL_CHECK();
+  return PP_OK;
+}
+
+extern "C" pp_status pp_trace_check_model_intersection(pp_mesh* mesh, pp_ps* ps,
+                                                       const pp_search_args* args, int32_t* ptcl_done,
+                                                       int32_t* last_exit, pp_stream stream) {
+  TraceParams p;
+  if (ps && ps->capacity == 0) return PP_OK;
+  PP_TRY(trace_params(mesh, ps, args, ptcl_done, last_exit, false, &p));
+  k_trace_model_exit<<<pp_div_up(p.ps.capacity, kTraceBlock), kTraceBlock, 0, (cudaStream_t)stream>>>(p);
+  PP_KERNEL_CHECK();
+  return PP_OK;
+}
+
+extern "C" pp_status pp_trace_set_new_element(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                                              int32_t* ptcl_done, int32_t* last_exit,
+                                              pp_stream stream) {
+  TraceParams p;
+  if (ps && ps->capacity == 0) return PP_OK;
+  PP_TRY(trace_params(mesh, ps, args, ptcl_done, last_exit, false, &p));
+  k_trace_next_elem<<<pp_div_up(p.ps.capacity, kTraceBlock), kTraceBlock, 0, (cudaStream_t)stream>>>(p);
+  PP_KERNEL_CHECK();
+  return PP_OK;
+}
+
+extern "C" pp_status pp_trace_pending(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
+                                      int32_t* ptcl_done, int32_t* last_exit, int32_t remove_pending,
+                                      int32_t* count, pp_stream stream) {
+  TraceParams p;
+  if (ps && ps->capacity == 0) { if (count) *count = 0; return PP_OK; }
+  PP_TRY(trace_params(mesh, ps, args, ptcl_done, last_exit, false, &p));
+  cudaStream_t s = (cudaStream_t)stream;
+  PP_CUDA(cudaMemsetAsync(mesh->stats_dev, 0, sizeof(int), s));
+  k_trace_pending<<<pp_div_up(p.ps.capacity, kTraceBlock), kTraceBlock, 0, s>>>(p, remove_pending);
+  PP_KERNEL_CHECK();
+  return trace_count(mesh, count, s);
+}

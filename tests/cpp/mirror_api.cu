@@ -6,6 +6,7 @@
 //   setUnsafeProcs                      src/pumipic_ptcl_ops.hpp:33-53
 //   ParticleBalancer                    test/test_lb.cpp:78-130 (one process acting as rank 0 of 4)
 //   PS_Comm_*                           support/ViewComm_test.cpp (one rank: self-consistent copies)
+//   trace_particle_through_mesh         src/pumipic_adjacency.tpp:460-640 with a user handler
 // Exit code 0 and "MIRROR_API_OK" on success.
 #include <climits>
 #include <cstdio>
@@ -141,6 +142,55 @@ int main() {
       if (hnp[s] != want) ++wrong;
     }
     CHECK(wrong == 0);
+  }
+
+  // ---------------------------------------------------------------- trace_particle_through_mesh
+  // stock handler: same arrays as the fused search_mesh; a user handler is called once per iteration
+  {
+    typedef p::Segment<double[3]> Seg3;
+    const pp_host_mesh* pm = pp_host_picpart_mesh(rec);
+    const double* pc = pp_host_mesh_coords(pm);
+    const int32_t* pev = pp_host_mesh_ent2verts(pm, 2);
+    std::vector<int> se = slot_elem.toHost();
+    std::vector<double> hx(3 * (size_t)cap, 0.0), ht(3 * (size_t)cap, 0.0);
+    for (int s = 0; s < cap; ++s) {
+      if (se[s] < 0) continue;
+      double cx = 0, cy = 0;
+      for (int k = 0; k < 3; ++k) { cx += pc[2 * pev[3 * se[s] + k]]; cy += pc[2 * pev[3 * se[s] + k] + 1]; }
+      hx[s] = cx / 3; hx[cap + s] = cy / 3;
+      ht[s] = hx[s] + 0.45 + 0.001 * (s % 7); ht[cap + s] = hx[cap + s] + 0.2;   // some leave through x = 1
+    }
+    p::View<double> xv(hx), xtv(ht);
+    Seg3 xs(xv.data(), cap), xts(xtv.data(), cap);
+    auto pids = ptcls->get<0>();
+    for (int mode = 0; mode < 2; ++mode) {          // 0: BCC walk, 1: edge intersection with wall points
+      const bool req = mode == 1;
+      p::View<int> ids_a, faces_a, ids_b, faces_b;
+      p::View<double> pts_a, pts_b;
+      const bool fa = p::search_mesh(picparts, ptcls, xs, xts, pids, ids_a, req, faces_a, pts_a, 500);
+      struct Counting {
+        p::RemoveParticleOnGeometricModelExit<Particle, Seg3> stock;
+        int calls;
+        void operator()(p::Mesh& m, PS* ps, p::View<int>& e, p::View<int>& f, p::View<int>& le, p::View<double>& xp,
+                        p::View<int>& d, Seg3 a, Seg3 b) { ++calls; stock(m, ps, e, f, le, xp, d, a, b); }
+      } handler{p::RemoveParticleOnGeometricModelExit<Particle, Seg3>(picparts, req), 0};
+      const bool fb = p::trace_particle_through_mesh(picparts, ptcls, xs, xts, pids, ids_b, req, faces_b, pts_b,
+                                                     500, false, handler);
+      cudaDeviceSynchronize();
+      std::vector<int> ia = ids_a.toHost(), ib = ids_b.toHost();
+      int left = 0, stayed = 0;
+      for (int s = 0; s < cap; ++s) if (se[s] >= 0) { left += ia[s] == -1; stayed += ia[s] == se[s]; }
+      CHECK(fa && fb && ia == ib && handler.calls >= 3);
+      CHECK(stayed < np / 2);                       // the push crosses several elements
+      if (req) {
+        std::vector<int> fA = faces_a.toHost(), fB = faces_b.toHost();
+        int walls = 0;
+        for (int s = 0; s < cap; ++s) walls += se[s] >= 0 && fA[s] >= 0;
+        CHECK(fA == fB && pts_a.toHost() == pts_b.toHost() && walls > 0);
+      } else {
+        CHECK(left > 0 && left < np);
+      }
+    }
   }
 
   // ---------------------------------------------------------------- ParticleBalancer as rank 0 of 4, peers empty

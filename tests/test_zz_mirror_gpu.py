@@ -10,7 +10,12 @@ import pytest
 
 from gpu_common import pp
 
-pytestmark = pytest.mark.gpu
+# Quarantine: everything in this file was written after the round's GPU budget was spent and has
+# never run on hardware.  xfail(strict=False) keeps an untried test from turning the verified
+# suites red; the first GPU call of the next round runs them (tools/gpu_first_call.sh) and this
+# marker goes away.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="never run on a GPU yet (written with no GPU time left)")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "cpp", "_bin", "mirror_api")
 
@@ -53,3 +58,98 @@ def test_get_pids(kind, ne, np_):
     assert np.array_equal(elem_of_pid, np.repeat(np.arange(ne), ppe))       # grouped by element
     same = elem_of_pid[1:] == elem_of_pid[:-1]
     assert np.all(np.diff(pids)[same] > 0)                                  # ascending slot inside a group
+
+
+# ---------------------------------------------------------------- stepped walk (pp_trace_*)
+def _walk_case(meshname, nptcls, mult, kind="scs"):
+    import ptcl_init as pi
+    from gpu_common import dev, make_gpu_mesh, make_ps
+    from meshes import kuhn_cube, load_fixture, plate
+    P = pp()
+    mesh = {"kuhn6": lambda: kuhn_cube(6), "plate12": lambda: plate(12)}.get(meshname, lambda: load_fixture(meshname))()
+    gm = make_gpu_mesh(mesh)
+    rng = np.random.default_rng(3)
+    w = rng.exponential(1.0, mesh.nelems)
+    w[rng.random(mesh.nelems) < 0.3] = 0
+    ppe = np.floor(w / w.sum() * nptcls).astype(np.int32)
+    K = {"scs": P.capi.PP_PS_SCS, "csr": P.capi.PP_PS_CSR, "dps": P.capi.PP_PS_DPS}[kind]
+    ps = make_ps(K, ppe)
+    slot_elem, mask = ps.slot_elem_and_mask()
+    init = pi.init3d_internal if mesh.dim == 3 else pi.init2d_internal
+    X, D = init(mesh, slot_elem, mask)
+    m = mask.astype(bool)
+    T = np.zeros_like(X)
+    T[:, m] = X[:, m] + mult * pi.push_distance(mesh) * D[:, m]
+    return P, mesh, gm, ps, slot_elem, m, dev(X), dev(T)
+
+
+@pytest.mark.parametrize("require_x", [False, True])
+@pytest.mark.parametrize("meshname,nptcls,mult,kind", [("kuhn6", 20000, 6.0, "scs"), ("cube7k", 30000, 3.0, "csr"),
+                                                       ("plate12", 5000, 5.0, "dps"), ("xgc24k", 40000, 4.0, "scs")])
+def test_stepped_walk_equals_fused_search(meshname, nptcls, mult, kind, require_x):
+    """trace_particle_through_mesh phase by phase with the stock handler leaves the same arrays as
+    the one-kernel search_mesh (which the parity suites pin to the oracle), bit for bit."""
+    import torch as t
+    P, mesh, gm, ps, slot_elem, m, X, T = _walk_case(meshname, nptcls, mult, kind)
+    cap, dim = ps.capacity, mesh.dim
+
+    def fresh():
+        return (t.full((cap,), -7, dtype=t.int32, device="cuda"),
+                t.full((cap,), -5, dtype=t.int32, device="cuda") if require_x else None,
+                t.full((dim * cap,), 3.5, dtype=t.float64, device="cuda") if require_x else None)
+
+    ids_a, f_a, p_a = fresh()
+    r = P.search_mesh(gm, ps, X, T, ids_a, elem_ids_empty=True, require_intersection=require_x,
+                      inter_faces=f_a, inter_points=p_a)
+    ids_b, f_b, p_b = fresh()
+    found, loops, not_in, lost = P.trace_particle_through_mesh(gm, ps, X, T, ids_b, elem_ids_empty=True,
+                                                               require_intersection=require_x,
+                                                               inter_faces=f_b, inter_points=p_b)
+    assert (found, loops, not_in, lost) == (bool(r.found), r.loops, r.not_in_elem, r.not_found)
+    assert t.equal(ids_a, ids_b)
+    if require_x:
+        assert t.equal(f_a, f_b) and t.equal(p_a, p_b)
+    # carried-over element ids, some particles already gone, some origins outside their element
+    ids0 = ids_a.clone()
+    start = t.as_tensor(np.where(m, slot_elem, -1).astype(np.int32)).cuda()
+    live = np.flatnonzero(m)
+    start[t.as_tensor(live[::11]).cuda()] = -1
+    wrong = live[3::13]
+    start[t.as_tensor(wrong).cuda()] = t.as_tensor(((slot_elem[wrong] + mesh.nelems // 2) % mesh.nelems).astype(np.int32)).cuda()
+    for limit in (0, 2):
+        ids_a, f_a, p_a = fresh(); ids_a.copy_(start)
+        ids_b, f_b, p_b = fresh(); ids_b.copy_(start)
+        r = P.search_mesh(gm, ps, X, T, ids_a, require_intersection=require_x, inter_faces=f_a,
+                          inter_points=p_a, looplimit=limit)
+        got = P.trace_particle_through_mesh(gm, ps, X, T, ids_b, require_intersection=require_x,
+                                            inter_faces=f_b, inter_points=p_b, looplimit=limit)
+        assert got == (bool(r.found), r.loops, r.not_in_elem, r.not_found)
+        assert r.not_in_elem > 0
+        assert t.equal(ids_a, ids_b)
+        if require_x:
+            assert t.equal(f_a, f_b) and t.equal(p_a, p_b)
+    assert not t.equal(ids0, ids_a)
+
+
+def test_stepped_walk_user_handler():
+    """A user handler stands where RemoveParticleOnGeometricModelExit stands: here one that stops
+    every particle at the first side it meets (ptcl_done = 1), so each ends in its start element and
+    last_exit holds a side of that element."""
+    import torch as t
+    P, mesh, gm, ps, slot_elem, m, X, T = _walk_case("kuhn6", 20000, 6.0)
+    cap = ps.capacity
+    ids = t.full((cap,), -7, dtype=t.int32, device="cuda")
+    seen = {}
+
+    def handler(elem_ids, inter_faces, last_exit, inter_points, ptcl_done):
+        seen["calls"] = seen.get("calls", 0) + 1
+        seen["last_exit"] = last_exit.clone()
+        ptcl_done.fill_(1)
+
+    found, loops, not_in, lost = P.trace_particle_through_mesh(gm, ps, X, T, ids, elem_ids_empty=True,
+                                                               handler=handler)
+    assert (found, loops, not_in, lost, seen["calls"]) == (True, 1, 0, 0, 1)
+    got = ids.cpu().numpy()
+    assert np.array_equal(got[m], slot_elem[m]) and np.all(got[~m] == -1)
+    le = seen["last_exit"].cpu().numpy()[:cap]
+    assert np.all((mesh.elem2sides[slot_elem[m]] == le[m][:, None]).any(axis=1))
