@@ -529,6 +529,8 @@ def trace_particle_through_mesh(mesh, ps, x_orig, x_tgt, elem_ids, elem_ids_empt
         check(L.pp_trace_pending(mesh.h, ps.h, C.byref(a), _ptr(done), _ptr(last_exit), 0, C.byref(n), st))
         found = n.value == 0
         loops += 1
+        if loops > 1000000:      # a handler that never finishes its particles must not hang the caller
+            raise capi.PumipicError("trace_particle_through_mesh: no progress after %d iterations" % loops)
         if looplimit and loops >= looplimit:
             check(L.pp_trace_pending(mesh.h, ps.h, C.byref(a), _ptr(done), _ptr(last_exit), 1,
                                      C.byref(n), st))

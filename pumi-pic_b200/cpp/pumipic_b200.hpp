@@ -693,6 +693,8 @@ bool trace_particle_through_mesh(Mesh& mesh, ParticleStructure<ParticleType>* pt
              "trace_particle_through_mesh: done check");
     found = n == 0;
     ++loops;
+    if (loops > 1000000)   // a handler that never finishes its particles must not hang the caller
+      throw std::runtime_error("trace_particle_through_mesh: no progress after 1000000 iterations");
     if (looplimit && loops >= looplimit) {                                                    // :584-606
       pp_check(pp_trace_pending(mesh.handle(), ptcls->handle(), &a, ptcl_done.data(), lastExit.data(), 1, &n, st),
                "trace_particle_through_mesh: loop limit");
