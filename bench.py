@@ -391,7 +391,7 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("k_search_dram_bytes_per_launch")
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_api as orc
         from meshes import Mesh as TMesh
