@@ -244,6 +244,12 @@ __device__ __forceinline__ double cross2(d2 a, d2 b) { return a.x * b.y - a.y * 
 // are_close(a,0,tol,tol): |a| <= tol, else |0-a|/max(|a|,0) = |a|/|a| <= tol, which is 1 <= tol for
 // finite a and NaN (false) for infinite a -- evaluated without the division.
 __device__ __forceinline__ bool pp_gtez(double a, double tol) {
+#ifndef PP_AB_GTEZ_V1
+  // for 0 <= tol < 1 (every tolerance of the path: 1e-20, 1e-10, max(1e-15/min_area, 1e-8)) the
+  // test below is (|a| <= tol) || (a > 0), i.e. exactly a >= -tol for every a including NaN and
+  // the infinities: one compare instead of three
+  if (tol >= 0.0 && tol < 1.0) return a >= -tol;
+#endif
   const double am = fabs(a);
 #ifdef PP_AB_OLD_GTEZ
   bool close;
