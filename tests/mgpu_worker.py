@@ -400,7 +400,10 @@ def main():
         test_pic_loop(P, comm, rank, R)
     if only in ("", "partial"):
         test_partial_picparts(P, comm, rank, R)
-    if R > 1 and only in ("", "balancer"):   # one rank: repartition is a no-op (pumipic_lb.hpp:360-361)
+    # One rank: repartition is a no-op (pumipic_lb.hpp:360-361).  Quarantined until its first
+    # successful multi-GPU run (its one attempt hit the call's time limit): only
+    # with MGPU_ONLY=balancer or MGPU_UNVERIFIED=1 (tools/gpu_mg.sh sets the latter).
+    if R > 1 and (only == "balancer" or (only == "" and os.environ.get("MGPU_UNVERIFIED") == "1")):
         test_balancer(P, comm, rank, R)
     dist.barrier()
     if rank == 0:
