@@ -934,7 +934,8 @@ __device__ __forceinline__ void warp_stage_fetch(const typename StageCfg<DIM>::R
   __syncwarp();
 }
 
-template <int DIM, bool PUSH, bool LEG, int WARPS>
+// PUSH: 0 no push, 1 xt += d*dir (test_adj form), 2 xt = xo + d*dir (PIC form; the bench's path)
+template <int DIM, int PUSH, bool LEG, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchParams p) {
   using Cfg = StageCfg<DIM>;
   using Rec = typename std::conditional<DIM == 3, Bcc3, Tri>::type;
@@ -1032,7 +1033,7 @@ __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchPara
     if (DIM == 3) row_adj[3] = sa[3];
     __syncwarp();
   };
-  const bool from_orig = PUSH && p.push_from_orig;
+  constexpr bool from_orig = PUSH == 2;
   const double* __restrict__ colA = p.xo;                 // origin
   const double* __restrict__ colB = PUSH ? p.dir : p.xt;  // direction | target
   // column prefetch: each lane copies its own six doubles into its private ring entries, so the
@@ -1166,12 +1167,16 @@ pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
   const int want = pp_div_up(p.chunk_end - p.chunk_begin, WARPS);
   const int persistent = g_sm_count * PP_SCS_MINB;
   const int grid = want < persistent ? want : persistent;
-  if (push && !LEG) {
-    auto k = k_walk_scs<DIM, true, false, WARPS>;
+  if (push && !LEG && p.push_from_orig) {
+    auto k = k_walk_scs<DIM, 2, false, WARPS>;
+    PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, WARPS * 32, smem, s>>>(p);
+  } else if (push && !LEG) {
+    auto k = k_walk_scs<DIM, 1, false, WARPS>;
     PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, WARPS * 32, smem, s>>>(p);
   } else {
-    auto k = k_walk_scs<DIM, false, LEG, WARPS>;
+    auto k = k_walk_scs<DIM, 0, LEG, WARPS>;
     PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, WARPS * 32, smem, s>>>(p);
   }
