@@ -7,3 +7,4 @@ python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; tai
 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; cut -c1-300 gpurun_out/${tag}_bench.json
 python tools/bench_lb.py > gpurun_out/${tag}_lb.json 2> gpurun_out/${tag}_lb.err; cat gpurun_out/${tag}_lb.json
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>/dev/null; cut -c1-200 gpurun_out/${tag}_bench_reference.json
+python tools/bench_c3_sweep.py --quick --iters 10 > gpurun_out/${tag}_c3_sweep.jsonl 2> gpurun_out/${tag}_c3_sweep.err; cut -c1-260 gpurun_out/${tag}_c3_sweep.jsonl
