@@ -17,6 +17,10 @@
 //     counter is read before it is bumped, so once an sbar's quota is filled the rest of the
 //     particles only read.  Counts per (sbar, target) are exactly the plan's (capped by the
 //     particles available); WHICH particles go is decided by atomic order, as in the reference.
+// Not reproduced from the reference's selection (pumipic_lb.hpp:256-263): it advances to an sbar's
+// next target only when a particle reads a remaining weight of exactly 0.0, which never happens for
+// a fractional weight -- the first target then gets ceil(w) particles and the later ones none.  Here
+// every target gets its ceil(w) in turn.
 // The neighbour exchanges of the reference (forced weights :176-200, EnGPar's own) collapse into one
 // in-place all-reduce of the global weight vector over NCCL.
 #include <cub/cub.cuh>
