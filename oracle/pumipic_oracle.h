@@ -8,11 +8,18 @@
  * cpu_baseline / --impl reference legs may load it.  The product (libpumipic_b200.so) never
  * links, loads or calls anything in this directory.
  *
- * PARITY PINNING: the real reference cannot be compiled here (needs Kokkos, Omega_h, EnGPar,
- * MPI -- none present, no network).  The oracle is pinned against the
- * reference's own golden vectors instead: test/search2d.cpp (15 element-id cases),
- * test/moller_trumbore_line_tri_test.cpp, src/unit_tests.hpp barycentric values and
- * test/pseudoXGCm_scatter.cpp vertex values (tests/test_oracle_golden.py).
+ * PARITY PINNING: the real reference cannot be compiled as a whole here (needs Kokkos, Omega_h,
+ * EnGPar, MPI -- none present, no network).  The oracle is pinned
+ *   (1) against the reference's own golden vectors: test/search2d.cpp (15 element-id cases),
+ *       test/moller_trumbore_line_tri_test.cpp, src/unit_tests.hpp barycentric values and
+ *       test/pseudoXGCm_scatter.cpp vertex values (tests/test_oracle_golden.py);
+ *   (2) primitive by primitive against the reference's own source, compiled unmodified from
+ *       /root/reference against a stand-in for Omega_h's vector types (oracle/_ref/, built by
+ *       oracle/build_ref_primitives.py): bit-identical outputs on random and degenerate inputs
+ *       (tests/test_oracle_vs_reference_primitives.py);
+ *   (3) on geometry, with test/test_adj.cpp's property checks at a strict tolerance
+ *       (tests/test_oracle_properties.py).
+ * Not pinned (no reference test or source fixes them): see DESIGN.md section 2 "Unpinned".
  *
  * Omega_h small-vector arithmetic (cross, inner_product, norm, ...) lives in a third-party
  * dependency that is not vendored in the reference tree (SCOREC/omega_h, scorec-v10.8.4 in the

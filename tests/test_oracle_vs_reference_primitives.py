@@ -1,0 +1,177 @@
+"""CPU-only: the oracle's geometric primitives against THE REFERENCE'S OWN CODE, bit for bit.
+
+oracle/build_ref_primitives.py compiles the reference's barycentric_tet / barycentric_tri /
+ray_intersects_triangle / line_segment_intersects_triangle / line_edge_2d / find_exit_face_bcc_3d
+(src/pumipic_adjacency.tpp:23-228), find_barycentric_tet / find_barycentric_tri_simple /
+line_triangle_intx_simple (src/pumipic_adjacency.hpp:97-273) and all_positive / min3 / min_index /
+max_index / isFaceFlipped (src/pumipic_utils.hpp:78-149,489-507) unmodified, straight from
+/root/reference, against a stand-in for Omega_h's small-vector types (oracle/ref_shim/).  Every
+restatement in oracle/pumipic_oracle.c must return exactly the same doubles and decisions on
+random, near-degenerate and degenerate inputs.  What this does NOT pin is Omega_h's own arithmetic
+(cross, inner_product, norm ...): the shim restates it from its published definitions, as the
+oracle does.  Skipped where the library was never built (no /root/reference and no prebuilt copy).
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_api as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libpumipic_ref_primitives.so")
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "oracle", "build_ref_primitives.py")],
+                          stdout=subprocess.DEVNULL)
+    if not os.path.exists(LIB):
+        pytest.skip("reference primitives not built (needs /root/reference once)")
+    return C.CDLL(LIB)
+
+
+def _d(a):
+    return np.ascontiguousarray(a, np.float64).ctypes.data_as(dp)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, np.int32).ctypes.data_as(ip)
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def _tets(rng, n):
+    """random tets, some flat or inverted, and points inside / on faces / on vertices / far away"""
+    M = rng.random((n, 4, 3))
+    M[::7, 3] = M[::7, 0] + 1e-14 * rng.random((len(M[::7]), 3))       # nearly degenerate
+    M[::11, 3] = M[::11, 0]                                              # degenerate
+    w = rng.random((n, 4)); w /= w.sum(axis=1, keepdims=True)
+    p = np.einsum("nk,nkd->nd", w, M)
+    p[::3] += rng.normal(0, 0.5, p[::3].shape)                           # outside
+    p[1::5] = M[1::5, 1]                                                 # on a vertex
+    p[2::5] = 0.5 * (M[2::5, 0] + M[2::5, 2])                            # on an edge
+    return M, p
+
+
+def test_barycentric_and_exit_face(ref):
+    L = orc.lib()
+    rng = np.random.default_rng(1)
+    M, P = _tets(rng, 4000)
+    for m, p in zip(M, P):
+        e1, e2, e3 = m[1] - m[0], m[2] - m[0], m[3] - m[0]
+        vol = float(np.dot(np.cross(e1, e2), e3) / 6.0)
+        for v in (vol, -vol, 0.0):
+            a, b = np.zeros(4), np.zeros(4)
+            ra = L.orc_barycentric_tet(C.c_double(v), _d(m), _d(p), _d(a))
+            rb = ref.ref_barycentric_tet(C.c_double(v), _d(m), _d(p), _d(b))
+            assert ra == rb and _same(a, b)
+        a, b = np.zeros(4), np.zeros(4)
+        assert L.orc_find_barycentric_tet(_d(m), _d(p), _d(a)) == ref.ref_find_barycentric_tet(_d(m), _d(p), _d(b))
+        assert _same(a, b)
+        # find_exit_face_bcc_3d = barycentric_tet + all_positive(EPSILON) + min_index
+        done = C.c_int()
+        f = ref.ref_find_exit_face_bcc_3d(C.c_double(vol), _d(m), _d(p), C.byref(done))
+        L.orc_barycentric_tet(C.c_double(vol), _d(m), _d(p), _d(a))
+        assert f == L.orc_min_index(_d(a), 4) and done.value == L.orc_all_positive(_d(a), 4, C.c_double(1e-10))
+    # triangles
+    T = rng.random((3000, 3, 2))
+    Q = rng.random((3000, 2)) * 1.5 - 0.25
+    Q[::4] = T[::4, 1]
+    for t, q in zip(T, Q):
+        area = 0.5 * float((t[1, 0] - t[0, 0]) * (t[2, 1] - t[0, 1]) - (t[1, 1] - t[0, 1]) * (t[2, 0] - t[0, 0]))
+        a, b = np.zeros(3), np.zeros(3)
+        L.orc_barycentric_tri(C.c_double(area), _d(t), _d(q), _d(a))
+        ref.ref_barycentric_tri(C.c_double(area), _d(t), _d(q), _d(b))
+        assert _same(a, b)
+        assert L.orc_min3(_d(a)) == ref.ref_min3(_d(b))
+
+
+def test_all_positive_min_max_index(ref):
+    L = orc.lib()
+    rng = np.random.default_rng(2)
+    special = [0.0, -0.0, 1e-10, -1e-10, np.nextafter(-1e-10, -1), np.nextafter(-1e-10, 0), 1e-8, -1e-8,
+               np.inf, -np.inf, np.nan, 1.0, -1.0, 5e-11, -5e-11]
+    for k in range(6000):
+        n = 3 if k % 2 else 4
+        v = rng.normal(0, 1e-9 if k % 3 else 1.0, n)
+        if k % 5 == 0:
+            v[rng.integers(0, n)] = special[k // 5 % len(special)]
+        if k % 7 == 0:
+            v[1] = v[0]                                               # ties
+        for tol in (1e-10, 1e-8, 1e-20, 0.0, 1.0, 2.5):
+            assert L.orc_all_positive(_d(v), n, C.c_double(tol)) == ref.ref_all_positive(_d(v), n, C.c_double(tol)), (v, tol)
+        if not np.isnan(v).any():
+            assert L.orc_min_index(_d(v), n) == ref.ref_min_index(_d(v), n)
+            assert L.orc_max_index(_d(v), n) == ref.ref_max_index(_d(v), n)
+            if n == 3:
+                assert L.orc_min3(_d(v)) == ref.ref_min3(_d(v))
+
+
+def test_face_flips(ref):
+    L = orc.lib()
+    import itertools
+    tv = np.array([11, 5, 7, 3], np.int32)
+    faces = [(0, 2, 1), (0, 1, 3), (1, 2, 3), (2, 0, 3)]
+    for fi, f in enumerate(faces):
+        for perm in itertools.permutations(f):
+            fv = tv[list(perm)]
+            assert L.orc_is_face_flipped_3d(fi, _i(fv), _i(tv)) == ref.ref_is_face_flipped_3d(fi, _i(fv), _i(tv))
+    t3 = np.array([4, 9, 2], np.int32)
+    for ei, e in enumerate([(0, 1), (1, 2), (2, 0)]):
+        for perm in itertools.permutations(e):
+            ev = t3[list(perm)]
+            assert L.orc_is_face_flipped_2d(_i(ev), _i(t3)) == ref.ref_is_face_flipped_2d(ei, _i(ev), _i(t3))
+
+
+def test_ray_segment_edge_and_legacy_intersections(ref):
+    L = orc.lib()
+    rng = np.random.default_rng(3)
+    for k in range(5000):
+        face = rng.random((3, 3))
+        o = rng.random(3) * 2 - 0.5
+        d = rng.random(3) * 2 - 0.5
+        if k % 6 == 0:                                                # ray in the face's plane
+            d = o + (face[1] - face[0])
+        if k % 9 == 0:                                                # through a vertex
+            d = o + 2 * (face[2] - o)
+        if k % 50 == 0:
+            d = o.copy()                                              # zero-length path: 0/0
+        for flip in (0, 1):
+            for tol in (1e-8, 0.0):
+                out = []
+                for fn_ray, fn_seg in ((L.orc_ray_intersects_triangle, L.orc_line_segment_intersects_triangle),
+                                       (ref.ref_ray_intersects_triangle, ref.ref_line_segment_intersects_triangle)):
+                    xp, xs = np.zeros(3), np.zeros(3)
+                    a, b, c = C.c_double(), C.c_double(), C.c_double()
+                    a2, b2, c2 = C.c_double(), C.c_double(), C.c_double()
+                    r1 = fn_ray(_d(face), _d(o), _d(d), _d(xp), C.c_double(tol), flip, C.byref(a), C.byref(b), C.byref(c))
+                    r2 = fn_seg(_d(face), _d(o), _d(d), _d(xs), C.c_double(tol), flip, C.byref(a2), C.byref(b2), C.byref(c2))
+                    out.append((r1, r2, xp, xs, [a.value, b.value, c.value, a2.value, b2.value, c2.value]))
+                assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+                assert _same(out[0][2], out[1][2]) and _same(out[0][3], out[1][3]) and _same(out[0][4], out[1][4])
+        for reverse in (0, 1):
+            res = []
+            for fn in (L.orc_line_triangle_intx_simple, ref.ref_line_triangle_intx_simple):
+                xp = np.zeros(3)
+                dpj = C.c_double(-7.0)
+                r = fn(_d(face), _d(o), _d(d), _d(xp), C.byref(dpj), reverse, C.c_double(1e-10))
+                res.append((r, xp, dpj.value))
+            assert res[0][0] == res[1][0] and _same(res[0][1], res[1][1]) and _same(res[0][2], res[1][2])
+        # 2D segment against an edge
+        e = rng.random(4)
+        o2, d2 = rng.random(2) * 2 - 0.5, rng.random(2) * 2 - 0.5
+        if k % 8 == 0:
+            d2 = o2 + (e[2:] - e[:2])                                 # parallel to the edge
+        for flip in (0, 1):
+            xa, xb = np.zeros(2), np.zeros(2)
+            ra = L.orc_line_edge_2d(_d(e), _d(o2), _d(d2), _d(xa), C.c_double(1e-8), flip)
+            rb = ref.ref_line_edge_2d(_d(e), _d(o2), _d(d2), _d(xb), C.c_double(1e-8), flip)
+            assert ra == rb and _same(xa, xb)
