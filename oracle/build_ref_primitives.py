@@ -46,6 +46,17 @@ FUNCTIONS = [
     ("src/pumipic_adjacency.tpp", r"bool line_segment_intersects_triangle\(", 0),
     ("src/pumipic_adjacency.tpp", r"bool line_edge_2d\(", 0),
     ("src/pumipic_adjacency.tpp", r"o::LO find_exit_face_bcc_3d\(", 0),
+    # the search loops (compiled against ref_shim/omega_h_mesh_shim.hpp)
+    ("src/pumipic_adjacency.hpp", r"o::Vector<3> makeVector3\(int pid", 0),
+    ("src/pumipic_adjacency.hpp", r"o::Vector<2> makeVector2\(int pid", 0),
+    ("src/pumipic_adjacency.tpp", r"o::LO check_initial_parents\(", 0),
+    ("src/pumipic_adjacency.tpp", r"void find_exit_face\(", 0),
+    ("src/pumipic_adjacency.tpp", r"void check_model_intersection\(", 0),
+    ("src/pumipic_adjacency.tpp", r"void set_new_element\(", 0),
+    ("src/pumipic_adjacency.tpp", r"o::Real compute_tolerance_from_area\(", 0),
+    ("src/pumipic_adjacency.tpp", r"bool trace_particle_through_mesh\(", 0),
+    ("src/pumipic_adjacency.tpp", r"struct RemoveParticleOnGeometricModelExit", 0),
+    ("src/pumipic_adjacency.tpp", r"bool search_mesh\(o::Mesh& mesh", 0),
 ]
 
 
@@ -70,6 +81,8 @@ def extract(text, pattern, which):
             if depth == 0:
                 break
         i += 1
+    if text[i + 1:i + 40].lstrip().startswith(";"):      # struct / class definitions
+        i = text.index(";", i)
     line0 = text.count("\n", 0, start) + 1
     line1 = text.count("\n", 0, i) + 1
     return text[start:i + 1], line0, line1
@@ -81,6 +94,7 @@ def main():
         return 0
     srcs = [os.path.join(REF, f) for f in sorted({f for f, _, _ in FUNCTIONS})]
     srcs += [os.path.join(REF, "src/pumipic_constants.hpp"), os.path.join(HERE, "ref_shim", "omega_h_shim.hpp"),
+             os.path.join(HERE, "ref_shim", "omega_h_mesh_shim.hpp"),
              os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.abspath(__file__)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0

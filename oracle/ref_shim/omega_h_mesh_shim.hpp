@@ -1,0 +1,155 @@
+// omega_h_mesh_shim.hpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Serial, host-only stand-ins for what the reference's search LOOPS touch besides the small-vector
+// types of omega_h_shim.hpp, so that check_initial_parents / find_exit_face /
+// check_model_intersection / set_new_element / compute_tolerance_from_area /
+// trace_particle_through_mesh / RemoveParticleOnGeometricModelExit / search_mesh
+// (src/pumipic_adjacency.tpp:72-660) compile UNMODIFIED (oracle/build_ref_primitives.py):
+//   Omega_h::Write / Read / HostWrite   ref-counted arrays (a const copy still writes, like a view)
+//   Omega_h::Mesh                       hands out the arrays it was given: ask_elem_verts, coords,
+//                                       ask_down(dim,dim-1), ask_up(dim-1,dim), ask_verts_of(dim-1);
+//                                       measure_elements_real and mark_exposed_sides return arrays
+//                                       supplied by the caller (the same derived arrays the oracle
+//                                       uses -- what is under test here is the reference's loop logic)
+//   gather_verts / gather_vectors / gather_down / get_min
+//   pumipic::ParticleStructure + parallel_for   a loop over all slots: fn(row element, slot, mask)
+//   Kokkos::parallel_reduce(Min), atomic_add, Timer, Profiling; MPI_Comm_rank; RecordTime ...
+// Every kernel of the reference is data-parallel over slots with no cross-slot dependence other than
+// counters, so a serial loop executes exactly what the Kokkos backends execute.
+#pragma once
+#include <cfloat>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "omega_h_shim.hpp"
+
+#define PS_LAMBDA [=]
+#define OMEGA_H_LAMBDA [=]
+#define printError(...) ((void)0)
+
+typedef int MPI_Comm;
+static inline int MPI_Comm_rank(MPI_Comm, int* rank) { *rank = 0; return 0; }
+
+namespace Kokkos {
+template <class T>
+struct Min {
+  T& ref;
+  explicit Min(T& r) : ref(r) {}
+};
+template <class F, class T>
+void parallel_reduce(int n, F f, Min<T> out) {
+  T v = DBL_MAX;   // identity of the Min reducer
+  for (int i = 0; i < n; ++i) f(i, v);
+  out.ref = v;
+}
+template <class T, class U> void atomic_add(T* p, U v) { *p += v; }
+struct Timer { double seconds() const { return 0.0; } };
+namespace Profiling {
+static inline void pushRegion(const char*) {}
+static inline void popRegion() {}
+}  // namespace Profiling
+}  // namespace Kokkos
+
+namespace Omega_h {
+typedef signed char I8;
+template <class T>
+class Write {
+  std::shared_ptr<std::vector<T>> d_;
+
+ public:
+  Write() : d_(std::make_shared<std::vector<T>>()) {}
+  Write(int n, T v, const std::string& = "") : d_(std::make_shared<std::vector<T>>((size_t)n, v)) {}
+  explicit Write(int n, const std::string& = "") : d_(std::make_shared<std::vector<T>>((size_t)n)) {}
+  int size() const { return (int)d_->size(); }
+  T& operator[](int i) const { return (*d_)[(size_t)i]; }
+  T* data() const { return d_->data(); }
+};
+template <class T>
+class Read {
+  Write<T> w_;
+
+ public:
+  Read() {}
+  Read(Write<T> w) : w_(w) {}
+  int size() const { return w_.size(); }
+  const T& operator[](int i) const { return w_[i]; }
+};
+template <class T>
+class HostWrite {
+  Write<T> w_;
+
+ public:
+  explicit HostWrite(Write<T> w) : w_(w) {}
+  T& operator[](int i) const { return w_[i]; }
+};
+typedef Read<LO> LOs;
+typedef Read<Real> Reals;
+typedef Read<I8> Bytes;
+template <class T> T get_min(Read<T> a) {
+  T m = a[0];
+  for (int i = 1; i < a.size(); ++i) if (a[i] < m) m = a[i];
+  return m;
+}
+
+struct Adj {
+  LOs a2ab, ab2b;
+};
+struct CommStub {
+  MPI_Comm get_impl() const { return 0; }
+};
+class Mesh {
+ public:
+  int dim_ = 0;
+  LOs elem_verts, down, side_verts, up_off, up_vals;
+  Reals coords_, measure;
+  Bytes exposed;
+  CommStub comm_;
+  int dim() const { return dim_; }
+  LOs ask_elem_verts() const { return elem_verts; }
+  Reals coords() const { return coords_; }
+  Adj ask_down(int, int) const { Adj a; a.ab2b = down; return a; }
+  Adj ask_up(int, int) const { Adj a; a.a2ab = up_off; a.ab2b = up_vals; return a; }
+  LOs ask_verts_of(int) const { return side_verts; }
+  const CommStub* comm() const { return &comm_; }
+};
+static inline Reals measure_elements_real(Mesh* m) { return m->measure; }
+static inline Bytes mark_exposed_sides(Mesh* m) { return m->exposed; }
+
+template <int n> Few<LO, n> gather_verts(LOs const& a, LO e) {
+  Few<LO, n> v;
+  for (int i = 0; i < n; ++i) v[i] = a[e * n + i];
+  return v;
+}
+template <int n> Few<LO, n> gather_down(LOs const& a, LO e) { return gather_verts<n>(a, e); }
+template <int neev, int dim> Matrix<dim, neev> gather_vectors(Reals const& a, Few<LO, neev> v) {
+  Matrix<dim, neev> x;
+  for (int i = 0; i < neev; ++i)
+    for (int j = 0; j < dim; ++j) x[i][j] = a[v[i] * dim + j];
+  return x;
+}
+}  // namespace Omega_h
+
+static inline double pumipic_prebarrier(MPI_Comm) { return 0.0; }
+static inline void RecordTime(const std::string&, double, double = 0.0) {}
+static inline void PrintAdditionalTimeInfo(const char*, int) {}
+
+namespace pumipic {
+typedef int lid_t;   // particle_structs/src/support/ppTypes.h
+// what ps::parallel_for needs from a structure: capacity, row element and mask per slot
+template <class DataTypes>
+class ParticleStructure {
+ public:
+  int cap = 0;
+  const int* slot_elem = nullptr;
+  const unsigned char* mask = nullptr;
+  int capacity() const { return cap; }
+};
+template <class DataTypes, class F>
+void parallel_for(ParticleStructure<DataTypes>* ps, F& fn, std::string = "") {
+  for (int s = 0; s < ps->cap; ++s) fn(ps->slot_elem[s], s, ps->mask[s] != 0);
+}
+}  // namespace pumipic
+namespace particle_structs = pumipic;

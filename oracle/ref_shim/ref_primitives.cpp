@@ -2,9 +2,10 @@
 // signatures as the oracle's primitives (oracle/pumipic_oracle.h:60-83), around the reference's own
 // functions: their text is pulled in from oracle/_ref/ref_primitives.inc, which
 // oracle/build_ref_primitives.py extracts from /root/reference at build time.
-#include "omega_h_shim.hpp"
+#include "omega_h_mesh_shim.hpp"
 
 namespace o = Omega_h;
+namespace ps = particle_structs;
 #define TriVerts 3   /* src/pumipic_adjacency.hpp:68-69 */
 #define TriDim 2
 
@@ -100,4 +101,57 @@ int ref_find_exit_face_bcc_3d(double vol, const double M[12], const double p[3],
   *done = d;
   return f;
 }
+}  // extern "C"
+
+// ---- the reference's search_mesh (adjacency.tpp:642 -> trace_particle_through_mesh :461) on a mesh
+// given by its arrays; derived arrays (ask_up, exposed sides, element measures) come from the caller
+struct Seg3 {
+  const double* p; long stride;
+  double operator()(int pid, int i) const { return p[(long)i * stride + pid]; }
+};
+struct SegI {
+  const int* p;
+  int operator()(int pid) const { return p[pid]; }
+};
+template <class T> static o::Write<T> to_write(const T* a, long n) {
+  o::Write<T> w((int)n, T());
+  for (long i = 0; i < n; ++i) w[(int)i] = a[i];
+  return w;
+}
+struct RefParticle {};
+
+extern "C" int ref_search_mesh(int dim, int nverts, const double* coords, int nelems, const int* elem2verts,
+                    int nsides, const int* elem2sides, const int* side2verts, const int* side2elem_off,
+                    const int* side2elem, const signed char* exposed, const double* measure, int cap,
+                    const int* slot_elem, const unsigned char* mask, const double* x, const double* xtgt,
+                    long stride, int* elem_ids, int elem_ids_empty, int require_intersection,
+                    int* inter_faces, double* inter_points, int inter_given, int looplimit) {
+  o::Mesh mesh;
+  mesh.dim_ = dim;
+  mesh.coords_ = o::Reals(to_write(coords, (long)nverts * dim));
+  mesh.elem_verts = o::LOs(to_write(elem2verts, (long)nelems * (dim + 1)));
+  mesh.down = o::LOs(to_write(elem2sides, (long)nelems * (dim + 1)));
+  mesh.side_verts = o::LOs(to_write(side2verts, (long)nsides * dim));
+  mesh.up_off = o::LOs(to_write(side2elem_off, (long)nsides + 1));
+  mesh.up_vals = o::LOs(to_write(side2elem, (long)side2elem_off[nsides]));
+  mesh.exposed = o::Bytes(to_write(exposed, (long)nsides));
+  mesh.measure = o::Reals(to_write(measure, (long)nelems));
+  pumipic::ParticleStructure<RefParticle> ptcls;
+  ptcls.cap = cap; ptcls.slot_elem = slot_elem; ptcls.mask = mask;
+  std::vector<int> pid((size_t)cap);
+  for (int i = 0; i < cap; ++i) pid[(size_t)i] = i;
+  Seg3 xo{x, stride}, xt{xtgt, stride};
+  SegI pids{pid.data()};
+  o::Write<o::LO> ids, faces;
+  o::Write<o::Real> pts;
+  if (!elem_ids_empty) ids = to_write(elem_ids, cap);
+  if (inter_given) { faces = to_write(inter_faces, cap); pts = to_write(inter_points, (long)dim * cap); }
+  const bool found = pumipic::search_mesh(mesh, &ptcls, xo, xt, pids, ids, require_intersection != 0, faces, pts,
+                                          looplimit, 0);
+  for (int i = 0; i < cap; ++i) elem_ids[i] = ids[i];
+  if (require_intersection) {
+    for (int i = 0; i < cap; ++i) inter_faces[i] = faces[i];
+    for (long i = 0; i < (long)dim * cap; ++i) inter_points[i] = pts[(int)i];
+  }
+  return found;
 }

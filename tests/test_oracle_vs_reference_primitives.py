@@ -175,3 +175,65 @@ def test_ray_segment_edge_and_legacy_intersections(ref):
             ra = L.orc_line_edge_2d(_d(e), _d(o2), _d(d2), _d(xa), C.c_double(1e-8), flip)
             rb = ref.ref_line_edge_2d(_d(e), _d(o2), _d(d2), _d(xb), C.c_double(1e-8), flip)
             assert ra == rb and _same(xa, xb)
+
+
+# ---------------------------------------------------------------- the search loops themselves
+def _ref_search(ref, om, mesh, slot_elem, mask, X, T, elem_ids=None, require_intersection=False,
+                looplimit=0, inter_given=False):
+    cap = mask.shape[0]
+    dim = mesh.dim
+    ids = np.full(cap, -1, np.int32) if elem_ids is None else np.ascontiguousarray(elem_ids, np.int32).copy()
+    faces = np.full(cap, 7, np.int32) if inter_given else np.full(cap, -1, np.int32)
+    pts = np.full(dim * cap, 2.5) if inter_given else np.zeros(dim * cap)
+    off, val = om.side2elem_off(), om.side2elem()
+    X, T = np.ascontiguousarray(X, np.float64), np.ascontiguousarray(T, np.float64)
+    found = ref.ref_search_mesh(
+        dim, mesh.nverts, _d(mesh.coords), mesh.nelems, _i(mesh.elem2verts), mesh.nsides,
+        _i(mesh.elem2sides), _i(mesh.side2verts), _i(off), _i(val),
+        np.ascontiguousarray(om.exposed(), np.int8).ctypes.data_as(C.POINTER(C.c_byte)), _d(om.vol()), cap,
+        _i(slot_elem), np.ascontiguousarray(mask, np.uint8).ctypes.data_as(C.POINTER(C.c_ubyte)),
+        _d(X), _d(T), C.c_long(X.shape[1]), ids.ctypes.data_as(ip), int(elem_ids is None),
+        int(require_intersection), faces.ctypes.data_as(ip), pts.ctypes.data_as(dp), int(inter_given), looplimit)
+    return bool(found), ids, faces, pts.reshape(cap, dim)
+
+
+@pytest.mark.parametrize("meshname,n,mult", [("kuhn5", 5000, 5.0), ("cube7k", 12000, 3.0), ("plate15", 3000, 5.0),
+                                             ("xgc24k", 8000, 6.0), ("tri8", 300, 2.0)])
+def test_search_mesh_equals_the_reference_loops(ref, meshname, n, mult):
+    """The oracle's search_mesh against the reference's own search_mesh -> trace_particle_through_mesh
+    (adjacency.tpp:461-660, with its find_exit_face, check_model_intersection, set_new_element,
+    check_initial_parents and compute_tolerance_from_area) compiled unmodified and run serially over
+    the same mesh arrays: element ids, wall sides and wall points must be identical, in both modes,
+    with fresh and carried-over element ids, deleted particles, wrong parents and a loop limit."""
+    import ptcl_init as pi
+    from meshes import kuhn_cube, load_fixture, plate
+    mesh = {"kuhn5": lambda: kuhn_cube(5), "plate15": lambda: plate(15)}.get(meshname, lambda: load_fixture(meshname))()
+    om = orc.OracleMesh(mesh)
+    slot_elem = ((np.arange(n, dtype=np.int64) * 7919) % mesh.nelems).astype(np.int32)
+    mask = np.ones(n, np.uint8)
+    mask[::13] = 0
+    init = pi.init3d_internal if mesh.dim == 3 else pi.init2d_internal
+    X, D = init(mesh, slot_elem, mask)
+    m = mask.astype(bool)
+    T = X.copy()
+    T[:, m] = X[:, m] + mult * pi.push_distance(mesh) * D[:, m]
+    T[:, 5::41] = X[:, 5::41]                                   # particles that do not move
+    for req in (False, True):
+        f0, i0, x0, p0, st = om.search_mesh(slot_elem, mask, X, T, require_intersection=req)
+        f1, i1, x1, p1 = _ref_search(ref, om, mesh, slot_elem, mask, X, T, require_intersection=req)
+        assert f0 == f1 and np.array_equal(i0, i1)
+        if req:
+            assert np.array_equal(x0, x1) and _same(p0, p1) and (x0 >= 0).any()
+        # carried-over ids with deletions and wrong parents, arrays handed in dirty, and a loop limit
+        start = np.where(m, slot_elem, -1).astype(np.int32)
+        live = np.flatnonzero(m)
+        start[live[::11]] = -1
+        start[live[3::17]] = (slot_elem[live[3::17]] + mesh.nelems // 2) % mesh.nelems
+        for limit in (0, 2):
+            f0, i0, x0, p0, st = om.search_mesh(slot_elem, mask, X, T, elem_ids=start, require_intersection=req,
+                                                looplimit=limit)
+            f1, i1, x1, p1 = _ref_search(ref, om, mesh, slot_elem, mask, X, T, elem_ids=start,
+                                         require_intersection=req, looplimit=limit, inter_given=req)
+            assert f0 == f1 and np.array_equal(i0, i1) and st.not_in_elem > 0
+            if req:
+                assert np.array_equal(x0, x1) and _same(p0, p1)
