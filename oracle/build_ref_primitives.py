@@ -57,6 +57,9 @@ FUNCTIONS = [
     ("src/pumipic_adjacency.tpp", r"bool trace_particle_through_mesh\(", 0),
     ("src/pumipic_adjacency.tpp", r"struct RemoveParticleOnGeometricModelExit", 0),
     ("src/pumipic_adjacency.tpp", r"bool search_mesh\(o::Mesh& mesh", 0),
+    # search_mesh_2d (legacy 2D walk) with the 5-argument barycentric_tri it calls
+    ("src/pumipic_adjacency.hpp", r"OMEGA_H_DEVICE void barycentric_tri\(", 0),
+    ("src/pumipic_adjacency.hpp", r"bool search_mesh_2d\(o::Mesh& mesh", 0),
 ]
 
 
@@ -66,10 +69,17 @@ def extract(text, pattern, which):
         raise SystemExit("build_ref_primitives: %r not found in the reference" % pattern)
     pos = hits[which].start()
     start = text.rfind("\n", 0, pos) + 1
-    # include a preceding `template <...>` / `template <...> OMEGA_H_DEVICE` line
-    prev_start = text.rfind("\n", 0, start - 1) + 1
-    if text[prev_start:start].lstrip().startswith("template"):
-        start = prev_start
+    # include a preceding `template <...>` header (one line, or a few lines ending in '>')
+    probe = start
+    for _ in range(4):
+        prev_start = text.rfind("\n", 0, probe - 1) + 1
+        line = text[prev_start:probe].strip()
+        if line.startswith("template"):
+            start = prev_start
+            break
+        if not line.endswith(">") and not line.endswith(","):
+            break
+        probe = prev_start
     brace = text.index("{", pos)
     depth, i = 0, brace
     while True:

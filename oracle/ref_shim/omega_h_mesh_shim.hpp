@@ -32,6 +32,7 @@
 
 typedef int MPI_Comm;
 static inline int MPI_Comm_rank(MPI_Comm, int* rank) { *rank = 0; return 0; }
+static inline int MPI_Comm_size(MPI_Comm, int* size) { *size = 1; return 0; }
 
 namespace Kokkos {
 template <class T>
@@ -108,6 +109,7 @@ class Mesh {
   Bytes exposed;
   CommStub comm_;
   int dim() const { return dim_; }
+  int nelems() const { return measure.size(); }
   LOs ask_elem_verts() const { return elem_verts; }
   Reals coords() const { return coords_; }
   Adj ask_down(int, int) const { Adj a; a.ab2b = down; return a; }

@@ -155,3 +155,38 @@ extern "C" int ref_search_mesh(int dim, int nverts, const double* coords, int ne
   }
   return found;
 }
+
+static void fill_mesh(o::Mesh& mesh, int dim, int nverts, const double* coords, int nelems, const int* elem2verts,
+                      int nsides, const int* elem2sides, const int* side2verts, const int* side2elem_off,
+                      const int* side2elem, const signed char* exposed, const double* measure) {
+  mesh.dim_ = dim;
+  mesh.coords_ = o::Reals(to_write(coords, (long)nverts * dim));
+  mesh.elem_verts = o::LOs(to_write(elem2verts, (long)nelems * (dim + 1)));
+  mesh.down = o::LOs(to_write(elem2sides, (long)nelems * (dim + 1)));
+  mesh.side_verts = o::LOs(to_write(side2verts, (long)nsides * dim));
+  mesh.up_off = o::LOs(to_write(side2elem_off, (long)nsides + 1));
+  mesh.up_vals = o::LOs(to_write(side2elem, (long)side2elem_off[nsides]));
+  mesh.exposed = o::Bytes(to_write(exposed, (long)nsides));
+  mesh.measure = o::Reals(to_write(measure, (long)nelems));
+}
+
+// the reference's search_mesh_2d (adjacency.hpp:1013-1158): elem_ids in/out (-1 = use the row element)
+extern "C" int ref_search_mesh_2d(int nverts, const double* coords, int nelems, const int* elem2verts, int nsides,
+                                  const int* elem2sides, const int* side2verts, const int* side2elem_off,
+                                  const int* side2elem, const signed char* exposed, const double* measure,
+                                  int cap, const int* slot_elem, const unsigned char* mask, const double* x,
+                                  const double* xtgt, long stride, int* elem_ids, int looplimit) {
+  o::Mesh mesh;
+  fill_mesh(mesh, 2, nverts, coords, nelems, elem2verts, nsides, elem2sides, side2verts, side2elem_off, side2elem,
+            exposed, measure);
+  pumipic::ParticleStructure<RefParticle> ptcls;
+  ptcls.cap = cap; ptcls.slot_elem = slot_elem; ptcls.mask = mask;
+  std::vector<int> pid((size_t)cap);
+  for (int i = 0; i < cap; ++i) pid[(size_t)i] = i;
+  Seg3 xo{x, stride}, xt{xtgt, stride};
+  SegI pids{pid.data()};
+  o::Write<o::LO> ids = to_write(elem_ids, cap);
+  const bool found = pumipic::search_mesh_2d(mesh, &ptcls, xo, xt, pids, ids, looplimit, false);
+  for (int i = 0; i < cap; ++i) elem_ids[i] = ids[i];
+  return found;
+}

@@ -237,3 +237,38 @@ def test_search_mesh_equals_the_reference_loops(ref, meshname, n, mult):
             assert f0 == f1 and np.array_equal(i0, i1) and st.not_in_elem > 0
             if req:
                 assert np.array_equal(x0, x1) and _same(p0, p1)
+
+
+@pytest.mark.parametrize("meshname,n,mult", [("plate15", 3000, 5.0), ("xgc24k", 8000, 6.0), ("tri8", 300, 2.0),
+                                             ("tri8_parDiag", 300, 3.0)])
+def test_search_mesh_2d_equals_the_reference_loop(ref, meshname, n, mult):
+    """The oracle's search_mesh_2d against the reference's own (adjacency.hpp:1013-1158, with the
+    5-argument barycentric_tri of :75-94) compiled unmodified: identical element ids, including the
+    `-nelems` sentinel, carried-over ids and the loop limit."""
+    import ptcl_init as pi
+    from meshes import load_fixture, plate
+    mesh = {"plate15": lambda: plate(15)}.get(meshname, lambda: load_fixture(meshname))()
+    om = orc.OracleMesh(mesh)
+    slot_elem = ((np.arange(n, dtype=np.int64) * 7919) % mesh.nelems).astype(np.int32)
+    mask = np.ones(n, np.uint8)
+    mask[::13] = 0
+    X, D = pi.init2d_internal(mesh, slot_elem, mask)
+    m = mask.astype(bool)
+    T = X.copy()
+    T[:, m] = X[:, m] + mult * pi.push_distance(mesh) * D[:, m]
+    off, val = om.side2elem_off(), om.side2elem()
+    start = np.full(n, -1, np.int32)
+    live = np.flatnonzero(m)
+    start[live[::7]] = slot_elem[live[::7]]                      # some given, some -1 (row element)
+    start[live[2::19]] = -mesh.nelems                            # "already outside" sentinel (:1053-1056)
+    for limit in (0, 2):
+        f0, i0, st = om.search_mesh_2d(slot_elem, mask, T, start, looplimit=limit)
+        ids = start.copy()
+        f1 = ref.ref_search_mesh_2d(
+            mesh.nverts, _d(mesh.coords), mesh.nelems, _i(mesh.elem2verts), mesh.nsides, _i(mesh.elem2sides),
+            _i(mesh.side2verts), _i(off), _i(val),
+            np.ascontiguousarray(om.exposed(), np.int8).ctypes.data_as(C.POINTER(C.c_byte)), _d(om.vol()), n,
+            _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _d(X), _d(T), C.c_long(X.shape[1]),
+            ids.ctypes.data_as(ip), limit)
+        assert f0 == bool(f1) and np.array_equal(i0, ids)
+        assert (ids >= 0).any() and (ids[m] == -1).any()
