@@ -1,19 +1,20 @@
 #!/usr/bin/env python
-"""Builds oracle/_ref/libpumipic_ref_primitives.so: the REFERENCE'S OWN geometric primitives,
-compiled unmodified from the sources where they lie under /root/reference.  TEST INFRASTRUCTURE.
+"""Builds oracle/_ref/libpumipic_ref_primitives.so: the REFERENCE'S OWN search code -- geometric
+primitives and the search loops -- compiled unmodified from the sources where they lie under
+/root/reference.  TEST INFRASTRUCTURE.
 
 The reference as a whole is unbuildable here (Kokkos, Omega_h, EnGPar, MPI are absent; DESIGN.md
-section 2), but the per-particle geometry of the search is a handful of free functions that only
-use Omega_h's small-vector vocabulary.  This script
-  1. locates each function in the reference tree by its signature and copies its text, brace
-     matched, into oracle/_ref/ref_primitives.inc (git-ignored: no reference source enters the
-     repository),
-  2. compiles it with g++ against oracle/ref_shim/omega_h_shim.hpp (our stand-in for the
-     Omega_h / Kokkos types and small-vector arithmetic, restated from their published definitions)
-     and oracle/ref_shim/ref_primitives.cpp (extern "C" wrappers with the oracle's signatures),
-     with -ffp-contract=off like the oracle.
-tests/test_oracle_vs_reference_primitives.py then requires the oracle's restatement of every one of
-these functions to agree with the reference's own code bit for bit on random and degenerate inputs.
+section 2), but its search is free functions and templates over a small vocabulary.  This script
+  1. locates each function in the reference tree by its signature and copies its text (brace
+     matching that skips comments and literals) into oracle/_ref/ref_primitives.inc (git-ignored:
+     no reference source enters the repository),
+  2. compiles it with g++, -ffp-contract=off like the oracle, against oracle/ref_shim/: our
+     stand-ins for Omega_h's small-vector types and arithmetic (omega_h_shim.hpp), for
+     Omega_h::Mesh / Write / Read, ps::parallel_for and the Kokkos / MPI calls the loops make
+     (omega_h_mesh_shim.hpp: serial, the kernels being data-parallel over slots), and extern "C"
+     wrappers with the oracle's signatures (ref_primitives.cpp).
+tests/test_oracle_vs_reference_primitives.py then requires the oracle's restatements -- every
+primitive and all four searches -- to agree with the reference's own code bit for bit.
 The script is a no-op (exit 0) where /root/reference does not exist (the GPU box: the prebuilt
 library travels with the snapshot).
 """
@@ -60,6 +61,14 @@ FUNCTIONS = [
     # search_mesh_2d (legacy 2D walk) with the 5-argument barycentric_tri it calls
     ("src/pumipic_adjacency.hpp", r"OMEGA_H_DEVICE void barycentric_tri\(", 0),
     ("src/pumipic_adjacency.hpp", r"bool search_mesh_2d\(o::Mesh& mesh", 0),
+    # legacy 3D search_mesh and search_mesh_3d with their helpers
+    ("src/pumipic_adjacency.hpp", r"o::Matrix<3, 3> gatherVectors3x3\(", 0),
+    ("src/pumipic_adjacency.hpp", r"o::Matrix<3, 4> gatherVectors4x3\(", 0),
+    ("src/pumipic_adjacency.hpp", r"bool barycentric_coords_tet\(", 0),
+    ("src/pumipic_adjacency.hpp", r"OMEGA_H_DEVICE bool isPointWithinElemTet\(", 0),
+    ("src/pumipic_adjacency.hpp", r"OMEGA_H_DEVICE bool isPointWithinElemTet\(", 1),
+    ("src/pumipic_adjacency.hpp", r"bool search_mesh_3d\(o::Mesh& mesh", 0),
+    ("src/pumipic_adjacency.hpp", r"bool search_mesh\(o::Mesh& mesh, ParticleStructure< ParticleType >\* ptcls", 0),
 ]
 
 
@@ -82,8 +91,20 @@ def extract(text, pattern, which):
         probe = prev_start
     brace = text.index("{", pos)
     depth, i = 0, brace
-    while True:
+    while True:                                       # brace matching that skips comments and literals
         c = text[i]
+        if text.startswith("//", i):
+            i = text.index("\n", i)
+            continue
+        if text.startswith("/*", i):
+            i = text.index("*/", i) + 2
+            continue
+        if c == '"' or c == "'":
+            j = i + 1
+            while text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            i = j + 1
+            continue
         if c == "{":
             depth += 1
         elif c == "}":

@@ -13,10 +13,12 @@
  *   (1) against the reference's own golden vectors: test/search2d.cpp (15 element-id cases),
  *       test/moller_trumbore_line_tri_test.cpp, src/unit_tests.hpp barycentric values and
  *       test/pseudoXGCm_scatter.cpp vertex values (tests/test_oracle_golden.py);
- *   (2) primitive by primitive against the reference's own source, compiled unmodified from
- *       /root/reference against a stand-in for Omega_h's vector types (oracle/_ref/, built by
- *       oracle/build_ref_primitives.py): bit-identical outputs on random and degenerate inputs
- *       (tests/test_oracle_vs_reference_primitives.py);
+ *   (2) against the reference's own source, compiled unmodified from /root/reference over
+ *       stand-ins for the Omega_h / Kokkos types (oracle/_ref/, built by
+ *       oracle/build_ref_primitives.py): every geometric primitive, and the four searches
+ *       themselves (search_mesh -> trace_particle_through_mesh, search_mesh_2d, legacy 3D
+ *       search_mesh, search_mesh_3d), give bit-identical results to the functions below on
+ *       random and degenerate inputs (tests/test_oracle_vs_reference_primitives.py);
  *   (3) on geometry, with test/test_adj.cpp's property checks at a strict tolerance
  *       (tests/test_oracle_properties.py).
  * Not pinned (no reference test or source fixes them): see DESIGN.md section 2 "Unpinned".

@@ -89,6 +89,7 @@ class HostWrite {
 typedef Read<LO> LOs;
 typedef Read<Real> Reals;
 typedef Read<I8> Bytes;
+template <class F> void parallel_for(int n, F f, const std::string& = "") { for (int i = 0; i < n; ++i) f(i); }
 template <class T> T get_min(Read<T> a) {
   T m = a[0];
   for (int i = 1; i < a.size(); ++i) if (a[i] < m) m = a[i];
@@ -104,7 +105,7 @@ struct CommStub {
 class Mesh {
  public:
   int dim_ = 0;
-  LOs elem_verts, down, side_verts, up_off, up_vals;
+  LOs elem_verts, down, side_verts, up_off, up_vals, dual_off, dual_vals;
   Reals coords_, measure;
   Bytes exposed;
   CommStub comm_;
@@ -115,6 +116,7 @@ class Mesh {
   Adj ask_down(int, int) const { Adj a; a.ab2b = down; return a; }
   Adj ask_up(int, int) const { Adj a; a.a2ab = up_off; a.ab2b = up_vals; return a; }
   LOs ask_verts_of(int) const { return side_verts; }
+  Adj ask_dual() const { Adj a; a.a2ab = dual_off; a.ab2b = dual_vals; return a; }
   const CommStub* comm() const { return &comm_; }
 };
 static inline Reals measure_elements_real(Mesh* m) { return m->measure; }
@@ -139,6 +141,7 @@ static inline void RecordTime(const std::string&, double, double = 0.0) {}
 static inline void PrintAdditionalTimeInfo(const char*, int) {}
 
 namespace pumipic {
+using ::RecordTime;
 typedef int lid_t;   // particle_structs/src/support/ppTypes.h
 // what ps::parallel_for needs from a structure: capacity, row element and mask per slot
 template <class DataTypes>

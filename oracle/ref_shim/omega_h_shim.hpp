@@ -19,7 +19,9 @@
 
 #define OMEGA_H_DEVICE static inline
 #define OMEGA_H_INLINE static inline
-#define OMEGA_H_CHECK(cond) assert(cond)
+// OMEGA_H_CHECK aborts the reference; here it throws so that a wrapper can report "would have aborted"
+struct RefCheckFailed {};
+#define OMEGA_H_CHECK(cond) do { if (!(cond)) throw RefCheckFailed(); } while (0)
 #define printInfo(...) ((void)0)
 
 namespace Kokkos {
@@ -83,6 +85,13 @@ static inline Vector<3> cross(Vector<3> a, Vector<3> b) {
 static inline Real cross(Vector<2> a, Vector<2> b) { return a[0] * b[1] - a[1] * b[0]; }
 static inline Vector<2> perp(Vector<2> v) { Vector<2> r; r[0] = -v[1]; r[1] = v[0]; return r; }
 static inline Real triangle_area_from_basis(Few<Vector<2>, 2> b) { return cross(b[0], b[1]) / 2.0; }
+// simplex_basis<3,3>: edge vectors p[i+1] - p[0];  tet_volume_from_basis(b) = (cross(b0,b1) . b2) / 6
+template <int sdim, int edim> Few<Vector<sdim>, edim> simplex_basis(Few<Vector<sdim>, edim + 1> p) {
+  Few<Vector<sdim>, edim> b;
+  for (int i = 0; i < edim; ++i) b[i] = p[i + 1] - p[0];
+  return b;
+}
+static inline Real tet_volume_from_basis(Few<Vector<3>, 3> b) { return inner_product(cross(b[0], b[1]), b[2]) / 6.0; }
 
 static inline Real rel_diff_with_floor(Real a, Real b, Real floor) {
   Real am = std::fabs(a), bm = std::fabs(b);

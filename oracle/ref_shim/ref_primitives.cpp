@@ -190,3 +190,40 @@ extern "C" int ref_search_mesh_2d(int nverts, const double* coords, int nelems, 
   for (int i = 0; i < cap; ++i) elem_ids[i] = ids[i];
   return found;
 }
+
+// the reference's legacy 3D search_mesh (adjacency.hpp:559-768; variant 0) and search_mesh_3d
+// (:316-555; variant 1).  Returns found (0/1), or -2 when an OMEGA_H_CHECK of the reference fired
+// (it would have aborted the process: a particle's origin is not in its start element).
+extern "C" int ref_search_mesh_3d_variants(int variant, int nverts, const double* coords, int nelems,
+                                           const int* elem2verts, int nsides, const int* elem2sides,
+                                           const int* side2verts, const int* side2elem_off, const int* side2elem,
+                                           const signed char* exposed, const double* measure, const int* dual_off,
+                                           const int* dual, int cap, const int* slot_elem, const unsigned char* mask,
+                                           const double* x, const double* xtgt, long stride, int* elem_ids,
+                                           int elem_ids_empty, double* xpoints, int* xface, int looplimit) {
+  o::Mesh mesh;
+  fill_mesh(mesh, 3, nverts, coords, nelems, elem2verts, nsides, elem2sides, side2verts, side2elem_off, side2elem,
+            exposed, measure);
+  mesh.dual_off = o::LOs(to_write(dual_off, (long)nelems + 1));
+  mesh.dual_vals = o::LOs(to_write(dual, (long)dual_off[nelems]));
+  pumipic::ParticleStructure<RefParticle> ptcls;
+  ptcls.cap = cap; ptcls.slot_elem = slot_elem; ptcls.mask = mask;
+  std::vector<int> pid((size_t)cap);
+  for (int i = 0; i < cap; ++i) pid[(size_t)i] = i;
+  Seg3 xo{x, stride}, xt{xtgt, stride};
+  SegI pids{pid.data()};
+  o::Write<o::LO> ids;
+  if (!elem_ids_empty) ids = to_write(elem_ids, cap);
+  o::Write<o::Real> xp = to_write(xpoints, 3L * cap);
+  o::Write<o::LO> xf = to_write(xface, cap);
+  int found;
+  try {
+    if (variant == 0) found = pumipic::search_mesh(mesh, &ptcls, xo, xt, pids, ids, xp, xf, looplimit, 0);
+    else found = pumipic::search_mesh_3d(mesh, &ptcls, xo, xt, pids, ids, xp, xf, looplimit, 0);
+  } catch (const RefCheckFailed&) {
+    return -2;
+  }
+  for (int i = 0; i < cap; ++i) { elem_ids[i] = ids[i]; xface[i] = xf[i]; }
+  for (long i = 0; i < 3L * cap; ++i) xpoints[i] = xp[(int)i];
+  return found;
+}

@@ -1,15 +1,19 @@
-"""CPU-only: the oracle's geometric primitives against THE REFERENCE'S OWN CODE, bit for bit.
+"""CPU-only: the oracle against THE REFERENCE'S OWN CODE, bit for bit.
 
-oracle/build_ref_primitives.py compiles the reference's barycentric_tet / barycentric_tri /
-ray_intersects_triangle / line_segment_intersects_triangle / line_edge_2d / find_exit_face_bcc_3d
-(src/pumipic_adjacency.tpp:23-228), find_barycentric_tet / find_barycentric_tri_simple /
-line_triangle_intx_simple (src/pumipic_adjacency.hpp:97-273) and all_positive / min3 / min_index /
-max_index / isFaceFlipped (src/pumipic_utils.hpp:78-149,489-507) unmodified, straight from
-/root/reference, against a stand-in for Omega_h's small-vector types (oracle/ref_shim/).  Every
-restatement in oracle/pumipic_oracle.c must return exactly the same doubles and decisions on
-random, near-degenerate and degenerate inputs.  What this does NOT pin is Omega_h's own arithmetic
-(cross, inner_product, norm ...): the shim restates it from its published definitions, as the
-oracle does.  Skipped where the library was never built (no /root/reference and no prebuilt copy).
+oracle/build_ref_primitives.py compiles, unmodified and straight from /root/reference,
+  * the geometric primitives: barycentric_tet / barycentric_tri / ray_intersects_triangle /
+    line_segment_intersects_triangle / line_edge_2d / find_exit_face_bcc_3d
+    (src/pumipic_adjacency.tpp:23-228), find_barycentric_tet / find_barycentric_tri_simple /
+    line_triangle_intx_simple (src/pumipic_adjacency.hpp:97-273), all_positive / min3 / min_index /
+    max_index / isFaceFlipped (src/pumipic_utils.hpp:78-149,489-507);
+  * the search loops: search_mesh -> trace_particle_through_mesh and its kernels
+    (adjacency.tpp:72-660), search_mesh_2d (adjacency.hpp:1013-1158), the legacy 3D search_mesh
+    (:559-768) and search_mesh_3d (:316-555)
+against stand-ins for the Omega_h / Kokkos vocabulary (oracle/ref_shim/).  Every restatement in
+oracle/pumipic_oracle.c must return exactly the same doubles, ids and decisions.  What this does
+NOT pin is Omega_h's own arithmetic and mesh derivations (cross, inner_product, ask_up ...): the
+shims restate them from the published definitions, as the oracle does.  Skipped where the library
+was never built (no /root/reference and no prebuilt copy).
 """
 import ctypes as C
 import os
@@ -272,3 +276,60 @@ def test_search_mesh_2d_equals_the_reference_loop(ref, meshname, n, mult):
             ids.ctypes.data_as(ip), limit)
         assert f0 == bool(f1) and np.array_equal(i0, ids)
         assert (ids >= 0).any() and (ids[m] == -1).any()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("meshname,n,mult", [("kuhn5", 4000, 4.0), ("cube7k", 10000, 3.0)])
+def test_legacy_3d_searches_equal_the_reference_loops(ref, meshname, n, mult, variant):
+    """variant 0: the legacy 3D search_mesh (adjacency.hpp:559-768); variant 1: search_mesh_3d
+    (:316-555, which no reference test exercises).  Both compiled unmodified -- including the
+    dual-graph-indexed-by-face-id fallbacks (:726, :510) -- and compared with the oracle's
+    restatements: element ids, wall points and wall faces, with fresh and carried-over ids and loop
+    limits; where the reference would abort (origin outside the start element) the oracle must
+    report it."""
+    import ptcl_init as pi
+    from meshes import kuhn_cube, load_fixture
+    mesh = kuhn_cube(5) if meshname == "kuhn5" else load_fixture(meshname)
+    om = orc.OracleMesh(mesh)
+    slot_elem = ((np.arange(n, dtype=np.int64) * 7919) % mesh.nelems).astype(np.int32)
+    mask = np.ones(n, np.uint8)
+    mask[::13] = 0
+    X, D = pi.init3d_internal(mesh, slot_elem, mask)
+    m = mask.astype(bool)
+    T = X.copy()
+    T[:, m] = X[:, m] + mult * pi.push_distance(mesh) * D[:, m]
+    off, val, doff, dval = om.side2elem_off(), om.side2elem(), om.dual_off(), om.dual()
+    oracle_fn = om.search_mesh_legacy3d if variant == 0 else om.search_mesh_3d
+
+    def run_ref(elem_ids, limit):
+        ids = np.full(n, -1, np.int32) if elem_ids is None else elem_ids.copy()
+        xp, xf = np.zeros(3 * n), np.full(n, -1, np.int32)
+        r = ref.ref_search_mesh_3d_variants(
+            variant, mesh.nverts, _d(mesh.coords), mesh.nelems, _i(mesh.elem2verts), mesh.nsides,
+            _i(mesh.elem2sides), _i(mesh.side2verts), _i(off), _i(val),
+            np.ascontiguousarray(om.exposed(), np.int8).ctypes.data_as(C.POINTER(C.c_byte)), _d(om.vol()),
+            _i(doff), _i(dval), n, _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _d(X), _d(T),
+            C.c_long(X.shape[1]), ids.ctypes.data_as(ip), int(elem_ids is None), xp.ctypes.data_as(dp),
+            xf.ctypes.data_as(ip), limit)
+        return r, ids, xp.reshape(n, 3), xf
+
+    carried = np.where(m, slot_elem, -1).astype(np.int32)
+    carried[np.flatnonzero(m)[::9]] = -1
+    for start in (None, carried):
+        for limit in (40, 3):
+            f0, i0, p0, x0, st = oracle_fn(slot_elem, mask, X, T, elem_ids=start, looplimit=limit)
+            r, i1, p1, x1 = run_ref(start, limit)
+            assert st.aborted == 0 and r == int(f0)
+            assert np.array_equal(i0, i1) and np.array_equal(x0, x1) and _same(p0, p1)
+            assert (x0 >= 0).any() and (i0 >= 0).any()
+    # a particle whose origin is not in its start element: the reference aborts, the oracle says so
+    bad = carried.copy()
+    k = np.flatnonzero(m & (carried >= 0))[5]
+    bad[k] = (slot_elem[k] + mesh.nelems // 2) % mesh.nelems
+    if variant == 0:                                   # legacy: checks the element it starts the walk in (:619-627)
+        f0, i0, p0, x0, st = oracle_fn(slot_elem, mask, X, T, elem_ids=bad, looplimit=40)
+        assert st.aborted >= 1 and run_ref(bad, 40)[0] == -2
+    else:                                              # search_mesh_3d: checks the ROW element (:368-379)
+        f0, i0, p0, x0, st = oracle_fn(slot_elem, mask, X, T, elem_ids=bad, looplimit=40)
+        r, i1, p1, x1 = run_ref(bad, 40)
+        assert st.aborted == 0 and r == int(f0) and np.array_equal(i0, i1)
