@@ -72,6 +72,18 @@ FUNCTIONS = [
 ]
 
 
+# test/gyroScatter.hpp (global namespace; compiled in ref_shim/ref_xgcm.cpp against xgcm_shim.hpp)
+XGCM_FUNCTIONS = [
+    ("test/gyroScatter.hpp", r"namespace \{\n  o::Real gyro_rmax", 0),
+    ("test/gyroScatter.hpp", r"void setGyroConfig\(", 0),
+    ("test/gyroScatter.hpp", r"o::LOs searchAndBuildMap\(", 0),
+    ("test/gyroScatter.hpp", r"void createGyroRingMappings\(", 0),
+    ("test/gyroScatter.hpp", r"void gyroScatter\(", 0),
+]
+XGCM_TYPEDEFS = [r"typedef MemberTypes<[^;]*> Point;", r"typedef ps::ParticleStructure<Point> PSpt;",
+                 r"typedef MemberTypes<[^;]*> Particle;", r"typedef ps::ParticleStructure<Particle> PS;"]
+
+
 def extract(text, pattern, which):
     hits = [m for m in re.finditer(pattern, text)]
     if len(hits) <= which:
@@ -126,7 +138,9 @@ def main():
     srcs = [os.path.join(REF, f) for f in sorted({f for f, _, _ in FUNCTIONS})]
     srcs += [os.path.join(REF, "src/pumipic_constants.hpp"), os.path.join(HERE, "ref_shim", "omega_h_shim.hpp"),
              os.path.join(HERE, "ref_shim", "omega_h_mesh_shim.hpp"),
-             os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.abspath(__file__)]
+             os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "xgcm_shim.hpp"),
+             os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"), os.path.join(REF, "test/gyroScatter.hpp"),
+             os.path.abspath(__file__)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0
     os.makedirs(OUT, exist_ok=True)
@@ -145,9 +159,23 @@ def main():
         parts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(OUT, "ref_primitives.inc"), "w") as fh:
         fh.write("\n".join(parts))
+    xparts = [parts[0]]
+    types = open(os.path.join(REF, "test/pseudoXGCmTypes.hpp")).read()
+    for pat in XGCM_TYPEDEFS:
+        m = re.search(pat, types)
+        if not m:
+            raise SystemExit("build_ref_primitives: %r not found in pseudoXGCmTypes.hpp" % pat)
+        xparts.append("// test/pseudoXGCmTypes.hpp\n" + m.group(0) + "\n")
+    for f, pat, which in XGCM_FUNCTIONS:
+        text = cache.setdefault(f, open(os.path.join(REF, f)).read())
+        body, l0, l1 = extract(text, pat, which)
+        xparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
+    with open(os.path.join(OUT, "ref_xgcm.inc"), "w") as fh:
+        fh.write("\n".join(xparts))
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
            "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", OUT,
-           os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), "-o", LIB]
+           os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
+           "-o", LIB]
     subprocess.check_call(cmd)
     print(LIB)
     return 0

@@ -18,8 +18,12 @@
 // counters, so a serial loop executes exactly what the Kokkos backends execute.
 #pragma once
 #include <cfloat>
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
+#include <map>
 #include <memory>
+#include <tuple>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -105,7 +109,9 @@ struct CommStub {
 class Mesh {
  public:
   int dim_ = 0;
-  LOs elem_verts, down, side_verts, up_off, up_vals, dual_off, dual_vals;
+  LOs elem_verts, down, side_verts, up_off, up_vals, dual_off, dual_vals, v2e_off, v2e_vals;
+  int nverts_ = 0;
+  std::shared_ptr<std::map<std::string, Reals>> tags = std::make_shared<std::map<std::string, Reals>>();
   Reals coords_, measure;
   Bytes exposed;
   CommStub comm_;
@@ -113,8 +119,15 @@ class Mesh {
   int nelems() const { return measure.size(); }
   LOs ask_elem_verts() const { return elem_verts; }
   Reals coords() const { return coords_; }
-  Adj ask_down(int, int) const { Adj a; a.ab2b = down; return a; }
-  Adj ask_up(int, int) const { Adj a; a.a2ab = up_off; a.ab2b = up_vals; return a; }
+  int nverts() const { return nverts_; }
+  Adj ask_down(int, int low) const { Adj a; a.ab2b = low == 0 ? elem_verts : down; return a; }
+  Adj get_adj(int from, int to) const { return ask_down(from, to); }
+  Adj ask_up(int low, int) const {
+    Adj a;
+    if (low == 0) { a.a2ab = v2e_off; a.ab2b = v2e_vals; } else { a.a2ab = up_off; a.ab2b = up_vals; }
+    return a;
+  }
+  void set_tag(int, const std::string& name, Reals v) { (*tags)[name] = v; }
   LOs ask_verts_of(int) const { return side_verts; }
   Adj ask_dual() const { Adj a; a.a2ab = dual_off; a.ab2b = dual_vals; return a; }
   const CommStub* comm() const { return &comm_; }
@@ -142,7 +155,62 @@ static inline void PrintAdditionalTimeInfo(const char*, int) {}
 
 namespace pumipic {
 using ::RecordTime;
-typedef int lid_t;   // particle_structs/src/support/ppTypes.h
+typedef int lid_t;
+typedef double fp_t;
+typedef fp_t Vector3d[3];
+
+template <class T> struct MemberBase { typedef T type; static constexpr int ncomp = 1; };
+template <class T, int N> struct MemberBase<T[N]> { typedef T type; static constexpr int ncomp = N; };
+template <class... Ts> struct MemberTypes {
+  static constexpr std::size_t size = sizeof...(Ts);
+  template <std::size_t N> using type = typename std::tuple_element<N, std::tuple<Ts...>>::type;
+};
+// value(particle, component) at base[component * stride + particle]; a const copy still writes
+template <class T> struct MemberAccessor {
+  typedef typename MemberBase<T>::type Base;
+  Base* p = nullptr;
+  long stride = 0;
+  Base& operator()(int i) const { return p[i]; }
+  Base& operator()(int i, int c) const { return p[(long)c * stride + i]; }
+};
+struct MemberViews {
+  std::vector<void*> arrays;
+  long n = 0;
+};
+typedef MemberViews* MemberTypeViews;
+template <class DT, std::size_t... I> void alloc_members(MemberViews* v, long n, std::index_sequence<I...>) {
+  (void)std::initializer_list<int>{(v->arrays.push_back(std::calloc(
+      (size_t)(n > 0 ? n : 1) * MemberBase<typename DT::template type<I>>::ncomp,
+      sizeof(typename MemberBase<typename DT::template type<I>>::type))), 0)...};
+}
+template <class DT> MemberTypeViews createMemberViews(int n) {
+  MemberViews* v = new MemberViews();
+  v->n = n;
+  alloc_members<DT>(v, n, std::make_index_sequence<DT::size>());
+  return v;
+}
+template <class DT, std::size_t N> MemberAccessor<typename DT::template type<N>> getMemberView(MemberTypeViews v) {
+  MemberAccessor<typename DT::template type<N>> a;
+  a.p = static_cast<typename MemberBase<typename DT::template type<N>>::type*>(v->arrays[N]);
+  a.stride = v->n;
+  return a;
+}
+template <class DT> void destroyViews(MemberTypeViews v) {
+  for (void* p : v->arrays) std::free(p);
+  delete v;
+}
+
+template <class T> class KView {   // Kokkos::View<T*>: ("name", n), (i) indexing, shared storage
+  std::shared_ptr<std::vector<T>> d_;
+
+ public:
+  KView() : d_(std::make_shared<std::vector<T>>()) {}
+  KView(const std::string&, int n) : d_(std::make_shared<std::vector<T>>((size_t)n, T())) {}
+  T& operator()(int i) const { return (*d_)[(size_t)i]; }
+  int size() const { return (int)d_->size(); }
+};
+
+   // particle_structs/src/support/ppTypes.h
 // what ps::parallel_for needs from a structure: capacity, row element and mask per slot
 template <class DataTypes>
 class ParticleStructure {
@@ -150,7 +218,14 @@ class ParticleStructure {
   int cap = 0;
   const int* slot_elem = nullptr;
   const unsigned char* mask = nullptr;
+  typedef KView<int> kkLidView;
+  typedef KView<long> kkGidView;
+  MemberViews* members = nullptr;
+  virtual ~ParticleStructure() {}
   int capacity() const { return cap; }
+  template <std::size_t N> MemberAccessor<typename DataTypes::template type<N>> get() {
+    return getMemberView<DataTypes, N>(members);
+  }
 };
 template <class DataTypes, class F>
 void parallel_for(ParticleStructure<DataTypes>* ps, F& fn, std::string = "") {

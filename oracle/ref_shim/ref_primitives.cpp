@@ -118,7 +118,7 @@ template <class T> static o::Write<T> to_write(const T* a, long n) {
   for (long i = 0; i < n; ++i) w[(int)i] = a[i];
   return w;
 }
-struct RefParticle {};
+typedef pumipic::MemberTypes<int> RefParticle;   // the searches never touch member data
 
 extern "C" int ref_search_mesh(int dim, int nverts, const double* coords, int nelems, const int* elem2verts,
                     int nsides, const int* elem2sides, const int* side2verts, const int* side2elem_off,

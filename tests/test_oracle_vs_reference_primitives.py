@@ -333,3 +333,41 @@ def test_legacy_3d_searches_equal_the_reference_loops(ref, meshname, n, mult, va
         f0, i0, p0, x0, st = oracle_fn(slot_elem, mask, X, T, elem_ids=bad, looplimit=40)
         r, i1, p1, x1 = run_ref(bad, 40)
         assert st.aborted == 0 and r == int(f0) and np.array_equal(i0, i1)
+
+
+@pytest.mark.parametrize("meshname,rmax,nrings,ppr,theta", [("tri8_parDiag", 0.2, 2, 6, 15), ("plate15", 0.11, 3, 8, 0),
+                                                            ("xgc24k", 0.038, 3, 8, 0), ("xgc24k", 0.05, 4, 5, 7)])
+def test_gyro_ring_map_and_scatter_equal_the_reference(ref, meshname, rmax, nrings, ppr, theta):
+    """createGyroRingMappings + searchAndBuildMap (test/gyroScatter.hpp:25-166, which builds a throw-away
+    Sell-C-sigma of ring points and runs search_mesh_2d on it) and gyroScatter (:168-229), compiled
+    unmodified: the oracle's ring map must be identical, and its scatter equal to the last bit (the
+    addends are small integers / points-per-ring, summed in the same vertex order)."""
+    from meshes import load_fixture, plate
+    mesh = plate(15) if meshname == "plate15" else load_fixture(meshname)
+    om = orc.OracleMesh(mesh)
+    off, val = om.side2elem_off(), om.side2elem()
+    voff, vval = om.vert2elem_off(), om.vert2elem()
+    npts = mesh.nverts * nrings * ppr
+    fwd = np.full(3 * npts, -9, np.int32)
+    same = C.c_int()
+    n = ref.ref_gyro_ring_map(
+        mesh.nverts, _d(mesh.coords), mesh.nelems, _i(mesh.elem2verts), mesh.nsides, _i(mesh.elem2sides),
+        _i(mesh.side2verts), _i(off), _i(val),
+        np.ascontiguousarray(om.exposed(), np.int8).ctypes.data_as(C.POINTER(C.c_byte)), _d(om.vol()),
+        _i(voff), _i(vval), C.c_double(rmax), nrings, ppr, theta, fwd.ctypes.data_as(ip), C.byref(same))
+    assert n == 3 * npts and same.value == 1
+    found, mine = om.gyro_ring_map(rmax, nrings, ppr, float(theta))
+    assert found and np.array_equal(mine, fwd)
+    assert (fwd >= 0).any() and (meshname == "xgc24k" or (fwd == -1).any())      # ring points outside the domain
+    # scatter: particles on a skewed subset of the elements, some slots empty
+    rng = np.random.default_rng(4)
+    cap = 5000
+    slot_elem = rng.integers(0, mesh.nelems, cap).astype(np.int32)
+    slot_elem[: cap // 3] = slot_elem[0]                          # a crowded element
+    mask = (rng.random(cap) < 0.8).astype(np.uint8)
+    want = np.zeros(mesh.nverts)
+    ref.ref_gyro_scatter(mesh.nverts, mesh.nelems, _i(mesh.elem2verts), cap, _i(slot_elem),
+                         mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _i(fwd), C.c_long(fwd.shape[0]),
+                         C.c_double(rmax), nrings, ppr, _d(want))
+    got = om.gyro_scatter(slot_elem, mask, fwd, rmax, nrings, ppr)
+    assert np.array_equal(got, want) and want.sum() > 0
