@@ -79,6 +79,7 @@ XGCM_FUNCTIONS = [
     ("test/gyroScatter.hpp", r"o::LOs searchAndBuildMap\(", 0),
     ("test/gyroScatter.hpp", r"void createGyroRingMappings\(", 0),
     ("test/gyroScatter.hpp", r"void gyroScatter\(", 0),
+    ("test/ellipticalPush.hpp", r"namespace ellipticalPush \{", 0),
 ]
 XGCM_TYPEDEFS = [r"typedef MemberTypes<[^;]*> Point;", r"typedef ps::ParticleStructure<Point> PSpt;",
                  r"typedef MemberTypes<[^;]*> Particle;", r"typedef ps::ParticleStructure<Particle> PS;"]
@@ -140,6 +141,7 @@ def main():
              os.path.join(HERE, "ref_shim", "omega_h_mesh_shim.hpp"),
              os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "xgcm_shim.hpp"),
              os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"), os.path.join(REF, "test/gyroScatter.hpp"),
+             os.path.join(REF, "test/ellipticalPush.hpp"),
              os.path.abspath(__file__)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0

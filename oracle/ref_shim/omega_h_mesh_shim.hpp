@@ -60,6 +60,7 @@ static inline void popRegion() {}
 
 namespace Omega_h {
 typedef signed char I8;
+typedef int ClassId;
 template <class T>
 class Write {
   std::shared_ptr<std::vector<T>> d_;
@@ -128,6 +129,8 @@ class Mesh {
     return a;
   }
   void set_tag(int, const std::string& name, Reals v) { (*tags)[name] = v; }
+  LOs class_id;
+  template <class T> Read<T> get_array(int, const std::string&) const { return class_id; }   // "class_id" only
   LOs ask_verts_of(int) const { return side_verts; }
   Adj ask_dual() const { Adj a; a.a2ab = dual_off; a.ab2b = dual_vals; return a; }
   const CommStub* comm() const { return &comm_; }

@@ -80,4 +80,32 @@ void ref_gyro_scatter(int nverts, int nelems, const int* elem2verts, int cap, co
   o::Reals w = (*mesh.tags)["w"];
   for (int v = 0; v < nverts; ++v) scatter_w[v] = w[v];
 }
+
+// ellipticalPush::setup / ellipticalPush::push (test/ellipticalPush.hpp:10-70) on a structure whose
+// member arrays are the caller's: x, xtgt [3][stride] doubles, b and phi floats
+static void wrap_particles(PS& ptcls, pumipic::MemberViews& mv, int cap, const int* slot_elem,
+                           const unsigned char* mask, double* x, double* xtgt, long stride, float* b, float* phi,
+                           std::vector<int>& ids) {
+  ids.assign((size_t)cap, 0);
+  mv.arrays = {x, xtgt, ids.data(), b, phi};
+  mv.n = stride;
+  ptcls.cap = cap; ptcls.slot_elem = slot_elem; ptcls.mask = mask; ptcls.members = &mv;
+}
+void ref_elliptical_setup(int cap, const int* slot_elem, const unsigned char* mask, double* x, long stride,
+                          float* b, float* phi, double h, double k, double d) {
+  PS ptcls; pumipic::MemberViews mv; std::vector<int> ids;
+  wrap_particles(ptcls, mv, cap, slot_elem, mask, x, x, stride, b, phi, ids);
+  ellipticalPush::setup(&ptcls, h, k, d);
+}
+void ref_elliptical_push(int cap, const int* slot_elem, const unsigned char* mask, double* xtgt, long stride,
+                         float* b, float* phi, int nelems, const int* class_ids, double h, double k, double d,
+                         double deg) {
+  PS ptcls; pumipic::MemberViews mv; std::vector<int> ids;
+  wrap_particles(ptcls, mv, cap, slot_elem, mask, xtgt, xtgt, stride, b, phi, ids);
+  o::Mesh mesh;
+  mesh.dim_ = 2;
+  mesh.class_id = o::LOs(to_w(class_ids, (long)nelems));
+  ellipticalPush::h = h; ellipticalPush::k = k; ellipticalPush::d = d;
+  ellipticalPush::push(&ptcls, mesh, deg, 0);
+}
 }

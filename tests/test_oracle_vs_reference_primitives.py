@@ -371,3 +371,36 @@ def test_gyro_ring_map_and_scatter_equal_the_reference(ref, meshname, rmax, nrin
                          C.c_double(rmax), nrings, ppr, _d(want))
     got = om.gyro_scatter(slot_elem, mask, fwd, rmax, nrings, ppr)
     assert np.array_equal(got, want) and want.sum() > 0
+
+
+def test_elliptical_push_equals_the_reference(ref):
+    """ellipticalPush::setup / push (test/ellipticalPush.hpp:10-70), compiled unmodified: the major axis
+    and angle (stored as float) and the pushed positions must be identical over several pushes (both
+    sides call the same libm)."""
+    from meshes import load_fixture
+    mesh = load_fixture("xgc24k")
+    rng = np.random.default_rng(6)
+    cap = 4000
+    slot_elem = rng.integers(0, mesh.nelems, cap).astype(np.int32)
+    mask = (rng.random(cap) < 0.9).astype(np.uint8)
+    c = mesh.coords[mesh.elem2verts[slot_elem]].mean(axis=1)
+    X = np.zeros((3, cap))
+    X[0], X[1] = c[:, 0], c[:, 1]
+    h, k, d = 1.6447937, 0.02055826, 0.6                       # pseudoXGCm.cpp:470-473
+    cls = mesh.class_id.astype(np.int32)
+    assert cls.min() >= 1
+    b0, p0 = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    b1, p1 = b0.copy(), p0.copy()
+    orc.elliptical_setup(mask, X, b0, p0, h, k, d)
+    fp = C.POINTER(C.c_float)
+    ref.ref_elliptical_setup(cap, _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _d(X), C.c_long(cap),
+                             b1.ctypes.data_as(fp), p1.ctypes.data_as(fp), C.c_double(h), C.c_double(k), C.c_double(d))
+    assert _same(b0, b1) and _same(p0, p1) and np.abs(b0[mask > 0]).max() > 0
+    T0, T1 = np.zeros((3, cap)), np.zeros((3, cap))
+    for it in range(4):
+        orc.elliptical_push(slot_elem, mask, T0, b0, p0, cls, h, k, d, 0.5)
+        ref.ref_elliptical_push(cap, _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _d(T1), C.c_long(cap),
+                                b1.ctypes.data_as(fp), p1.ctypes.data_as(fp), mesh.nelems, _i(cls), C.c_double(h),
+                                C.c_double(k), C.c_double(d), C.c_double(0.5))
+        assert _same(T0, T1) and _same(p0, p1)
+    assert np.abs(T0[:, mask > 0]).max() > 0 and not T0[:, mask == 0].any()
