@@ -13,7 +13,7 @@ section 2), but its search is free functions and templates over a small vocabula
      Omega_h::Mesh / Write / Read, ps::parallel_for and the Kokkos / MPI calls the loops make
      (omega_h_mesh_shim.hpp: serial, the kernels being data-parallel over slots), and extern "C"
      wrappers with the oracle's signatures (ref_primitives.cpp).
-tests/test_oracle_vs_reference_primitives.py then requires the oracle's restatements -- every
+tests/test_oracle_vs_reference_source.py then requires the oracle's restatements -- every
 primitive and all four searches -- to agree with the reference's own code bit for bit.
 The script is a no-op (exit 0) where /root/reference does not exist (the GPU box: the prebuilt
 library travels with the snapshot).
@@ -81,6 +81,10 @@ XGCM_FUNCTIONS = [
     ("test/gyroScatter.hpp", r"void gyroScatter\(", 0),
     ("test/ellipticalPush.hpp", r"namespace ellipticalPush \{", 0),
 ]
+# src/pumipic_ptcl_ops.hpp (namespace pumipic; needs the pumipic::Mesh stand-in of xgcm_shim.hpp)
+PTCL_OPS_FUNCTIONS = [
+    ("src/pumipic_ptcl_ops.hpp", r"void setUnsafeProcs\(Mesh& mesh", 0),
+]
 XGCM_TYPEDEFS = [r"typedef MemberTypes<[^;]*> Point;", r"typedef ps::ParticleStructure<Point> PSpt;",
                  r"typedef MemberTypes<[^;]*> Particle;", r"typedef ps::ParticleStructure<Particle> PS;"]
 
@@ -141,7 +145,7 @@ def main():
              os.path.join(HERE, "ref_shim", "omega_h_mesh_shim.hpp"),
              os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "xgcm_shim.hpp"),
              os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"), os.path.join(REF, "test/gyroScatter.hpp"),
-             os.path.join(REF, "test/ellipticalPush.hpp"),
+             os.path.join(REF, "test/ellipticalPush.hpp"), os.path.join(REF, "src/pumipic_ptcl_ops.hpp"),
              os.path.abspath(__file__)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0
@@ -174,6 +178,13 @@ def main():
         xparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(OUT, "ref_xgcm.inc"), "w") as fh:
         fh.write("\n".join(xparts))
+    oparts = [parts[0]]
+    for f, pat, which in PTCL_OPS_FUNCTIONS:
+        text = cache.setdefault(f, open(os.path.join(REF, f)).read())
+        body, l0, l1 = extract(text, pat, which)
+        oparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
+    with open(os.path.join(OUT, "ref_ptcl_ops.inc"), "w") as fh:
+        fh.write("\n".join(oparts))
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
            "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", OUT,
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),

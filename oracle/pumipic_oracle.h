@@ -17,8 +17,9 @@
  *       stand-ins for the Omega_h / Kokkos types (oracle/_ref/, built by
  *       oracle/build_ref_primitives.py): every geometric primitive, and the four searches
  *       themselves (search_mesh -> trace_particle_through_mesh, search_mesh_2d, legacy 3D
- *       search_mesh, search_mesh_3d), give bit-identical results to the functions below on
- *       random and degenerate inputs (tests/test_oracle_vs_reference_primitives.py);
+ *       search_mesh, search_mesh_3d), the gyro ring mapping and scatter, the elliptical push
+ *       and setUnsafeProcs give bit-identical results to the functions below on
+ *       random and degenerate inputs (tests/test_oracle_vs_reference_source.py);
  *   (3) on geometry, with test/test_adj.cpp's property checks at a strict tolerance
  *       (tests/test_oracle_properties.py).
  * Not pinned (no reference test or source fixes them): see DESIGN.md section 2 "Unpinned".

@@ -210,6 +210,7 @@ template <class T> class KView {   // Kokkos::View<T*>: ("name", n), (i) indexin
   KView() : d_(std::make_shared<std::vector<T>>()) {}
   KView(const std::string&, int n) : d_(std::make_shared<std::vector<T>>((size_t)n, T())) {}
   T& operator()(int i) const { return (*d_)[(size_t)i]; }
+  T& operator[](int i) const { return (*d_)[(size_t)i]; }
   int size() const { return (int)d_->size(); }
 };
 

@@ -21,6 +21,10 @@ namespace pumipic {
 
 #include "ref_xgcm.inc"
 
+namespace pumipic {
+#include "ref_ptcl_ops.inc"
+}  // namespace pumipic
+
 namespace {
 template <class T> o::Write<T> to_w(const T* a, long n) {
   o::Write<T> w((int)n, T());
@@ -107,5 +111,20 @@ void ref_elliptical_push(int cap, const int* slot_elem, const unsigned char* mas
   mesh.class_id = o::LOs(to_w(class_ids, (long)nelems));
   ellipticalPush::h = h; ellipticalPush::k = k; ellipticalPush::d = d;
   ellipticalPush::push(&ptcls, mesh, deg, 0);
+}
+
+// setUnsafeProcs (src/pumipic_ptcl_ops.hpp:33-53)
+void ref_set_unsafe_procs(int cap, const int* slot_elem, const unsigned char* mask, const int* elems, int nelems,
+                          const int* safe, const int* owner, int self, int* new_elems, int* new_procs) {
+  pumipic::Mesh mesh;
+  mesh.omesh.dim_ = 3;
+  mesh.owners = o::LOs(to_w(owner, (long)nelems));
+  mesh.safe = o::LOs(to_w(safe, (long)nelems));
+  mesh.comm_.rank_ = self;
+  PS ptcls;
+  ptcls.cap = cap; ptcls.slot_elem = slot_elem; ptcls.mask = mask;
+  PS::kkLidView ne("ne", cap), np("np", cap);
+  pumipic::setUnsafeProcs(mesh, &ptcls, o::LOs(to_w(elems, (long)cap)), ne, np);
+  for (int i = 0; i < cap; ++i) { new_elems[i] = ne(i); new_procs[i] = np(i); }
 }
 }

@@ -54,6 +54,18 @@ template <class DataTypes> class SellCSigma : public ParticleStructure<DataTypes
     this->members = particle_info;   // the reference copies; sharing is equivalent here (read back by id)
   }
 };
+// pumipic::Mesh (src/pumipic_mesh.hpp) as far as setUnsafeProcs reads it
+class Mesh {
+ public:
+  struct Comm { int rank_ = 0; int rank() const { return rank_; } };
+  Omega_h::Mesh omesh;
+  Omega_h::LOs owners, safe;
+  Comm comm_;
+  Omega_h::Mesh* operator->() { return &omesh; }
+  Omega_h::LOs entOwners(int) const { return owners; }
+  Omega_h::LOs safeTag() const { return safe; }
+  const Comm* comm() const { return &comm_; }
+};
 static inline Kokkos::TeamPolicy<Kokkos::DefaultExecutionSpace> TeamPolicyAuto(int league, int team) {
   return Kokkos::TeamPolicy<Kokkos::DefaultExecutionSpace>{league, team};
 }

@@ -404,3 +404,19 @@ def test_elliptical_push_equals_the_reference(ref):
                                 C.c_double(k), C.c_double(d), C.c_double(0.5))
         assert _same(T0, T1) and _same(p0, p1)
     assert np.abs(T0[:, mask > 0]).max() > 0 and not T0[:, mask == 0].any()
+
+
+def test_set_unsafe_procs_equals_the_reference(ref):
+    """setUnsafeProcs (src/pumipic_ptcl_ops.hpp:33-53) compiled unmodified."""
+    rng = np.random.default_rng(8)
+    cap, ne = 3000, 500
+    slot_elem = rng.integers(0, ne, cap).astype(np.int32)
+    mask = (rng.random(cap) < 0.85).astype(np.uint8)
+    elems = rng.integers(-1, ne, cap).astype(np.int32)
+    safe = (rng.random(ne) < 0.6).astype(np.int32)
+    owner = rng.integers(0, 4, ne).astype(np.int32)
+    e0, p0 = orc.set_unsafe_procs(mask, elems, safe, owner, 2)
+    e1, p1 = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    ref.ref_set_unsafe_procs(cap, _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _i(elems), ne, _i(safe),
+                             _i(owner), 2, e1.ctypes.data_as(ip), p1.ctypes.data_as(ip))
+    assert np.array_equal(e0, e1) and np.array_equal(p0, p1) and (p0 != 2).any()
