@@ -69,6 +69,17 @@ FUNCTIONS = [
     ("src/pumipic_adjacency.hpp", r"OMEGA_H_DEVICE bool isPointWithinElemTet\(", 1),
     ("src/pumipic_adjacency.hpp", r"bool search_mesh_3d\(o::Mesh& mesh", 0),
     ("src/pumipic_adjacency.hpp", r"bool search_mesh\(o::Mesh& mesh, ParticleStructure< ParticleType >\* ptcls", 0),
+    # gather (field -> particle): tet vertex fields and the regular-grid interpolators
+    ("src/pumipic_adjacency.hpp", r"Omega_h::Real interpolateTetVtx\(", 0),
+    ("src/pumipic_adjacency.hpp", r"void interpolate3dFieldTet\(", 0),
+    ("src/pumipic_adjacency.hpp", r"void findBCCoordsInTet\(", 0),
+    ("src/pumipic_utils.hpp", r"o::Real interpolate2d_base\(", 0),
+    ("src/pumipic_utils.hpp", r"o::Real interpolate2d_baseg\(", 0),
+    ("src/pumipic_utils.hpp", r"o::Real interpolate2d_based\(", 0),
+    ("src/pumipic_utils.hpp", r"o::Real interpolate2d\(const o::Reals& data, const o::Real gridXi", 0),
+    ("src/pumipic_utils.hpp", r"o::Real interpolate2d_field\(", 0),
+    ("src/pumipic_utils.hpp", r"o::Real interpolate3d_field\(", 0),
+    ("src/pumipic_utils.hpp", r"void interp2dVector \(", 0),
 ]
 
 

@@ -29,6 +29,12 @@ static inline double fabs(double a) { return std::fabs(a); }
 static inline double abs(double a) { return std::fabs(a); }
 static inline double min(double a, double b) { return (b < a) ? b : a; }   // std::min
 static inline double max(double a, double b) { return (a < b) ? b : a; }   // std::max
+static inline double floor(double a) { return std::floor(a); }
+static inline double cos(double a) { return std::cos(a); }
+static inline double sin(double a) { return std::sin(a); }
+static inline double sqrt(double a) { return std::sqrt(a); }
+static inline double pow(double a, int b) { return std::pow(a, b); }
+static inline double atan2(double a, double b) { return std::atan2(a, b); }
 }  // namespace Kokkos
 
 namespace Omega_h {

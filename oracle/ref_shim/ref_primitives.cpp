@@ -227,3 +227,41 @@ extern "C" int ref_search_mesh_3d_variants(int variant, int nverts, const double
   for (long i = 0; i < 3L * cap; ++i) xpoints[i] = xp[(int)i];
   return found;
 }
+
+// ---- gather helpers (adjacency.hpp:772-809, utils.hpp:245-456); -2 = an OMEGA_H_CHECK fired
+extern "C" int ref_interpolate_tet_vtx(const int* elem2verts, int nelems, const double* field, long nfield, int elem,
+                                       const double bcc[4], int dof, int comp, double* out) {
+  o::Vector<4> b;
+  for (int i = 0; i < 4; ++i) b[i] = bcc[i];
+  try {
+    *out = pumipic::interpolateTetVtx(o::LOs(to_write(elem2verts, 4L * nelems)), o::Reals(to_write(field, nfield)),
+                                      elem, b, dof, comp);
+  } catch (const RefCheckFailed&) { return -2; }
+  return 0;
+}
+extern "C" int ref_find_bcc_in_tet(const double* coords, int nverts, const int* elem2verts, int nelems,
+                                   const double xyz[3], int elem, double bcc[4]) {
+  o::Vector<4> b;
+  try {
+    pumipic::findBCCoordsInTet(o::Reals(to_write(coords, 3L * nverts)), o::LOs(to_write(elem2verts, 4L * nelems)),
+                               v3(xyz), elem, b);
+  } catch (const RefCheckFailed&) { return -2; }
+  for (int i = 0; i < 4; ++i) bcc[i] = b[i];
+  return 0;
+}
+extern "C" double ref_interpolate2d_field(const double* data, long ndata, double gridx0, double gridz0, double dx,
+                                          double dz, int nx, int nz, const double pos[3], int cyl, int nComp, int comp) {
+  return pumipic::interpolate2d_field(o::Reals(to_write(data, ndata)), gridx0, gridz0, dx, dz, nx, nz, v3(pos), cyl != 0,
+                                      nComp, comp);
+}
+extern "C" void ref_interp2d_vector(const double* data3, long ndata, double gridx0, double gridz0, double dx, double dz,
+                                    int nx, int nz, const double pos[3], double field[3], int cyl) {
+  o::Vector<3> f = o::zero_vector<3>();
+  pumipic::interp2dVector(o::Reals(to_write(data3, ndata)), gridx0, gridz0, dx, dz, nx, nz, v3(pos), f, cyl != 0);
+  for (int i = 0; i < 3; ++i) field[i] = f[i];
+}
+extern "C" double ref_interpolate3d_field(double x, double y, double z, int nx, int ny, int nz, const double* gridx,
+                                          const double* gridy, const double* gridz, const double* data) {
+  return pumipic::interpolate3d_field(x, y, z, nx, ny, nz, o::Reals(to_write(gridx, nx)), o::Reals(to_write(gridy, ny)),
+                                      o::Reals(to_write(gridz, nz)), o::Reals(to_write(data, (long)nx * ny * nz)));
+}

@@ -20,11 +20,6 @@
 
 namespace Kokkos {
 template <class T, class U> T atomic_fetch_add(T* p, U v) { T old = *p; *p += v; return old; }
-static inline double cos(double a) { return std::cos(a); }
-static inline double sin(double a) { return std::sin(a); }
-static inline double sqrt(double a) { return std::sqrt(a); }
-static inline double pow(double a, int b) { return std::pow(a, b); }
-static inline double atan2(double a, double b) { return std::atan2(a, b); }
 struct DefaultExecutionSpace {};
 template <class Space> struct TeamPolicy { int league, team; };
 }  // namespace Kokkos

@@ -420,3 +420,68 @@ def test_set_unsafe_procs_equals_the_reference(ref):
     ref.ref_set_unsafe_procs(cap, _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _i(elems), ne, _i(safe),
                              _i(owner), 2, e1.ctypes.data_as(ip), p1.ctypes.data_as(ip))
     assert np.array_equal(e0, e1) and np.array_equal(p0, p1) and (p0 != 2).any()
+
+
+def test_gather_helpers_equal_the_reference(ref):
+    """interpolateTetVtx / findBCCoordsInTet (adjacency.hpp:772-809) and interpolate2d_field /
+    interp2dVector / interpolate3d_field (utils.hpp:245-456) compiled unmodified.  Where the reference
+    itself reads out of bounds the comparison stays inside its defined range: interpolateTetVtx with
+    dof == 1 (for dof > 1 it indexes a 4-entry gather with d*dof+comp, adjacency.hpp:779-783) and
+    interpolate3d_field with ny, nz >= 2 (utils.hpp:385-404)."""
+    from meshes import kuhn_cube
+    L = orc.lib()
+    L.orc_interpolate_tet_vtx.restype = C.c_double
+    L.orc_interpolate3d_field.restype = C.c_double
+    ref.ref_interpolate2d_field.restype = C.c_double
+    ref.ref_interpolate3d_field.restype = C.c_double
+    rng = np.random.default_rng(9)
+    mesh = kuhn_cube(4)
+    om = orc.OracleMesh(mesh)
+    field = rng.random(mesh.nverts)
+    for k in range(600):
+        e = int(rng.integers(0, mesh.nelems))
+        w = rng.random(4); w /= w.sum()
+        xyz = w @ mesh.coords[mesh.elem2verts[e]]
+        bcc = np.zeros(4)
+        assert ref.ref_find_bcc_in_tet(_d(mesh.coords), mesh.nverts, _i(mesh.elem2verts), mesh.nelems, _d(xyz), e,
+                                       _d(bcc)) == 0
+        mine = np.zeros(4)
+        assert L.orc_find_barycentric_tet(_d(mesh.coords[mesh.elem2verts[e]]), _d(xyz), _d(mine)) == 1
+        assert _same(bcc, mine)
+        out = C.c_double()
+        assert ref.ref_interpolate_tet_vtx(_i(mesh.elem2verts), mesh.nelems, _d(field), C.c_long(field.shape[0]), e,
+                                           _d(bcc), 1, 0, C.byref(out)) == 0
+        assert out.value == L.orc_interpolate_tet_vtx(om.h, _d(field), e, _d(bcc), 1, 0)
+    # a point outside its element: the reference's OMEGA_H_CHECK fires
+    far = mesh.coords[mesh.elem2verts[0]].mean(axis=0) + 5.0
+    assert ref.ref_find_bcc_in_tet(_d(mesh.coords), mesh.nverts, _i(mesh.elem2verts), mesh.nelems, _d(far), 0,
+                                   _d(np.zeros(4))) == -2
+    # regular 2D grids, 1 and 3 components, with and without cylindrical symmetry, points off the grid too
+    nx, nz = 9, 7
+    gx0, gz0, dx, dz = 0.3, -1.0, 0.25, 0.4
+    for ncomp in (1, 3):
+        data = rng.random(nx * nz * ncomp)
+        for k in range(400):
+            pos = np.array([rng.uniform(-0.5, 3.0), rng.uniform(-1.0, 1.0), rng.uniform(-2.0, 2.5)])
+            for cyl in (0, 1):
+                for comp in range(ncomp):
+                    a = orc.interpolate2d_field(data, gx0, gz0, dx, dz, nx, nz, pos, cyl, ncomp, comp)
+                    b = ref.ref_interpolate2d_field(_d(data), C.c_long(data.shape[0]), C.c_double(gx0), C.c_double(gz0),
+                                                    C.c_double(dx), C.c_double(dz), nx, nz, _d(pos), cyl, ncomp, comp)
+                    assert _same(a, b), (pos, cyl, comp)
+                if ncomp == 3:
+                    fa, fb = np.zeros(3), np.zeros(3)
+                    L.orc_interp2d_vector(_d(data), C.c_double(gx0), C.c_double(gz0), C.c_double(dx), C.c_double(dz),
+                                          nx, nz, _d(pos), _d(fa), cyl)
+                    ref.ref_interp2d_vector(_d(data), C.c_long(data.shape[0]), C.c_double(gx0), C.c_double(gz0),
+                                            C.c_double(dx), C.c_double(dz), nx, nz, _d(pos), _d(fb), cyl)
+                    assert _same(fa, fb)
+    # 3D grids
+    gx, gy, gz = np.linspace(0, 1, 6), np.linspace(-1, 1, 5), np.linspace(2, 3, 4)
+    data = rng.random(6 * 5 * 4)
+    for k in range(800):
+        x, y, z = rng.uniform(-0.2, 1.2), rng.uniform(-1.3, 1.3), rng.uniform(1.8, 3.2)
+        a = orc.interpolate3d_field(x, y, z, gx, gy, gz, data)
+        b = ref.ref_interpolate3d_field(C.c_double(x), C.c_double(y), C.c_double(z), 6, 5, 4, _d(gx), _d(gy), _d(gz),
+                                        _d(data))
+        assert _same(a, b)
