@@ -92,6 +92,17 @@ XGCM_FUNCTIONS = [
     ("test/gyroScatter.hpp", r"void gyroScatter\(", 0),
     ("test/ellipticalPush.hpp", r"namespace ellipticalPush \{", 0),
 ]
+# test/test_adj.cpp: the generator of the synthetic inputs (compiled in ref_shim/ref_testadj.cpp)
+TESTADJ_LINES = [r"#define PARTICLE_SEED [^\n]*", r"typedef p::MemberTypes<[^;]*> Particle;",
+                 r"typedef p::ParticleStructure<Particle> PS;"]
+TESTADJ_FUNCTIONS = [
+    ("test/test_adj.cpp", r"int setSourceElements\(", 0),
+    ("test/test_adj.cpp", r"void init2DInternal\(", 0),
+    ("test/test_adj.cpp", r"void init3DInternal\(", 0),
+    ("test/test_adj.cpp", r"o::Real determine_distance\(", 0),
+    ("test/test_adj.cpp", r"o::Real get_push_distance\(", 0),
+    ("test/test_adj.cpp", r"void push_ptcls\(", 0),
+]
 # src/pumipic_ptcl_ops.hpp (namespace pumipic; needs the pumipic::Mesh stand-in of xgcm_shim.hpp)
 PTCL_OPS_FUNCTIONS = [
     ("src/pumipic_ptcl_ops.hpp", r"void setUnsafeProcs\(Mesh& mesh", 0),
@@ -157,6 +168,7 @@ def main():
              os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "xgcm_shim.hpp"),
              os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"), os.path.join(REF, "test/gyroScatter.hpp"),
              os.path.join(REF, "test/ellipticalPush.hpp"), os.path.join(REF, "src/pumipic_ptcl_ops.hpp"),
+             os.path.join(REF, "test/test_adj.cpp"), os.path.join(HERE, "ref_shim", "ref_testadj.cpp"),
              os.path.abspath(__file__)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0
@@ -196,10 +208,22 @@ def main():
         oparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(OUT, "ref_ptcl_ops.inc"), "w") as fh:
         fh.write("\n".join(oparts))
+    tparts = [parts[0]]
+    tadj = open(os.path.join(REF, "test/test_adj.cpp")).read()
+    for pat in TESTADJ_LINES:
+        m = re.search(pat, tadj)
+        if not m:
+            raise SystemExit("build_ref_primitives: %r not found in test_adj.cpp" % pat)
+        tparts.append("// test/test_adj.cpp\n" + m.group(0) + "\n")
+    for f, pat, which in TESTADJ_FUNCTIONS:
+        body, l0, l1 = extract(tadj, pat, which)
+        tparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
+    with open(os.path.join(OUT, "ref_testadj.inc"), "w") as fh:
+        fh.write("\n".join(tparts))
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
            "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", OUT,
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
-           "-o", LIB]
+           os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), "-o", LIB]
     subprocess.check_call(cmd)
     print(LIB)
     return 0

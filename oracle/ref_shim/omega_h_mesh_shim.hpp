@@ -50,6 +50,12 @@ void parallel_reduce(int n, F f, Min<T> out) {
   for (int i = 0; i < n; ++i) f(i, v);
   out.ref = v;
 }
+template <class F, class T>
+void parallel_reduce(int n, F f, T& total) {   // sum reduction into `total`
+  T v = T();
+  for (int i = 0; i < n; ++i) f(i, v);
+  total = v;
+}
 template <class T, class U> void atomic_add(T* p, U v) { *p += v; }
 struct Timer { double seconds() const { return 0.0; } };
 namespace Profiling {
@@ -69,6 +75,7 @@ class Write {
   Write() : d_(std::make_shared<std::vector<T>>()) {}
   Write(int n, T v, const std::string& = "") : d_(std::make_shared<std::vector<T>>((size_t)n, v)) {}
   explicit Write(int n, const std::string& = "") : d_(std::make_shared<std::vector<T>>((size_t)n)) {}
+  template <class H, class = decltype(std::declval<H>().write())> Write(const H& h) : d_(h.write().d_) {}
   int size() const { return (int)d_->size(); }
   T& operator[](int i) const { return (*d_)[(size_t)i]; }
   T* data() const { return d_->data(); }
@@ -89,7 +96,9 @@ class HostWrite {
 
  public:
   explicit HostWrite(Write<T> w) : w_(w) {}
+  explicit HostWrite(int n) : w_(n, T()) {}
   T& operator[](int i) const { return w_[i]; }
+  Write<T> write() const { return w_; }
 };
 typedef Read<LO> LOs;
 typedef Read<Real> Reals;
@@ -117,7 +126,8 @@ class Mesh {
   Bytes exposed;
   CommStub comm_;
   int dim() const { return dim_; }
-  int nelems() const { return measure.size(); }
+  int nelems_ = -1;
+  int nelems() const { return nelems_ >= 0 ? nelems_ : measure.size(); }
   LOs ask_elem_verts() const { return elem_verts; }
   Reals coords() const { return coords_; }
   int nverts() const { return nverts_; }
@@ -135,6 +145,18 @@ class Mesh {
   Adj ask_dual() const { Adj a; a.a2ab = dual_off; a.ab2b = dual_vals; return a; }
   const CommStub* comm() const { return &comm_; }
 };
+template <int n> struct BBox { Vector<n> min, max; };
+template <int n> BBox<n> get_bounding_box(Mesh* m) {
+  BBox<n> b;
+  Reals c = m->coords();
+  for (int j = 0; j < n; ++j) b.min[j] = b.max[j] = c[j];
+  for (int i = 1; i < c.size() / n; ++i)
+    for (int j = 0; j < n; ++j) {
+      if (c[i * n + j] < b.min[j]) b.min[j] = c[i * n + j];
+      if (c[i * n + j] > b.max[j]) b.max[j] = c[i * n + j];
+    }
+  return b;
+}
 static inline Reals measure_elements_real(Mesh* m) { return m->measure; }
 static inline Bytes mark_exposed_sides(Mesh* m) { return m->exposed; }
 

@@ -34,6 +34,7 @@ static inline double cos(double a) { return std::cos(a); }
 static inline double sin(double a) { return std::sin(a); }
 static inline double sqrt(double a) { return std::sqrt(a); }
 static inline double pow(double a, int b) { return std::pow(a, b); }
+static inline double pow(double a, double b) { return std::pow(a, b); }
 static inline double atan2(double a, double b) { return std::atan2(a, b); }
 }  // namespace Kokkos
 

@@ -485,3 +485,48 @@ def test_gather_helpers_equal_the_reference(ref):
         b = ref.ref_interpolate3d_field(C.c_double(x), C.c_double(y), C.c_double(z), 6, 5, 4, _d(gx), _d(gy), _d(gz),
                                         _d(data))
         assert _same(a, b)
+
+
+@pytest.mark.parametrize("meshname", ["kuhn4", "cube7k", "plate15", "xgc24k"])
+def test_workload_generator_equals_the_reference(ref, meshname):
+    """pumi-pic_b200/workloads.py (the synthetic inputs of the tests and of bench.py) against the
+    reference's own generator, test/test_adj.cpp (setSourceElements :27-42, init2DInternal :68-125,
+    init3DInternal :440-507, get_push_distance :543-547, push_ptcls :550-562), compiled unmodified:
+    std::default_random_engine(512*512) drawn per SLOT, the fold into the simplex, the direction, the
+    push distance and the push itself must give identical doubles."""
+    import ptcl_init as pi
+    from meshes import kuhn_cube, load_fixture, plate
+    mesh = {"kuhn4": lambda: kuhn_cube(4), "plate15": lambda: plate(15)}.get(meshname, lambda: load_fixture(meshname))()
+    dim = mesh.dim
+    ref.ref_testadj_push_distance.restype = C.c_double
+    # particles per element
+    for nptcls in (mesh.nelems * 3 + 17, 5):
+        ppe = np.zeros(mesh.nelems, np.int32)
+        assert ref.ref_testadj_ppe(mesh.nelems, nptcls, ppe.ctypes.data_as(ip)) == nptcls
+        assert np.array_equal(ppe, pi.even_ppe(mesh.nelems, nptcls))
+    d_ref = ref.ref_testadj_push_distance(dim, mesh.nverts, _d(mesh.coords), mesh.nelems)
+    assert d_ref == pi.push_distance(mesh)
+    # a padded structure: some slots empty
+    rng = np.random.default_rng(12)
+    cap = 6000
+    slot_elem = np.sort(rng.integers(0, mesh.nelems, cap)).astype(np.int32)
+    mask = (rng.random(cap) < 0.9).astype(np.uint8)
+    init = pi.init3d_internal if dim == 3 else pi.init2d_internal
+    X, D = init(mesh, slot_elem, mask)
+    x, xt, mo = np.zeros((3, cap)), np.full((3, cap), 9.0), np.zeros((3, cap))
+    pids = np.full(cap, -1, np.int32)
+    ref.ref_testadj_init_internal(dim, mesh.nverts, _d(mesh.coords), mesh.nelems, _i(mesh.elem2verts),
+                                  _d(orc.OracleMesh(mesh).vol()), cap, _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_long(cap),
+                                  _d(x), _d(xt), pids.ctypes.data_as(ip), _d(mo))
+    m = mask.astype(bool)
+    assert np.array_equal(X[:, m], x[:, m]) and np.array_equal(D[:, m], mo[:, m])
+    assert np.array_equal(xt[:, m], x[:, m]) and np.array_equal(pids[m], np.flatnonzero(m))
+    # the push: tgt += distance * direction on masked slots (the arithmetic of the fused kernel's PUSH form 1)
+    T = xt.copy()
+    T[:, m] = xt[:, m] + d_ref * mo[:, m]
+    ref.ref_testadj_push(cap, _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_long(cap), _d(x), _d(xt),
+                         pids.ctypes.data_as(ip), _d(mo), C.c_double(d_ref))
+    assert np.array_equal(T, xt)
+    P = np.zeros((3, cap)); P[:, m] = x[:, m]
+    orc.push_direction(mask, P, mo, d_ref)
+    assert np.array_equal(P[:, m], xt[:, m])
