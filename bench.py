@@ -10,6 +10,10 @@ the first step (particles that leave the domain are deleted, as in the reference
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
+CPU legs (`cpu_baseline`, `--impl reference`): the reference's own push_ptcls + search_mesh source,
+compiled unmodified into oracle/_ref over OpenMP stand-ins for Kokkos / Omega_h (kind "reference");
+the OpenMP oracle port where that library is missing (kind "port").
+
 N>1 (torchrun): every rank owns an identical-size independent shard (its own PICpart-sized
 mesh + particles); push+search has no exchange step, so there is no data-path collective and
 scaling is weak.  Prints ONE JSON line on rank 0.
@@ -138,9 +142,29 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_leg(orc, om, wl, m, ppe, sample, steps, warmup):
-    """The reference algorithm (CPU oracle, OpenMP, kernel-per-phase) on a bounded sample:
-    push (xtgt = x + d*dir) + search_mesh BCC per step, ping-pong buffers like the GPU arm."""
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libpumipic_ref_primitives.so")
+REF_NOTE = ("the reference's own push_ptcls (test/test_adj.cpp:550-562) + search_mesh (src/pumipic_adjacency.tpp:642) "
+            "source, compiled unmodified into oracle/_ref over OpenMP stand-ins for Kokkos / Omega_h "
+            "(oracle/ref_shim); Omega_h's per-call mesh derivations are precomputed, which favours the reference")
+PORT_NOTE = "OpenMP oracle (CPU restatement of the reference algorithm)"
+
+
+def load_ref_lib():
+    """oracle/_ref: the reference's search source compiled from /root/reference in the authoring
+    container (oracle/build_ref_primitives.py); the prebuilt library travels to the GPU box."""
+    import ctypes as C
+    if not os.path.exists(REF_LIB):
+        return None
+    L = C.CDLL(REF_LIB)
+    L.ref_bench_create.restype = C.c_void_p
+    return L
+
+
+def cpu_reference_leg(orc, om, wl, m, ppe, sample, steps, warmup, ref=None):
+    """The reference's CPU path on a bounded sample: push (xtgt = x + d*dir) + search_mesh BCC per
+    step, ping-pong buffers like the GPU arm.  With `ref` (oracle/_ref) the reference's own source
+    runs; without it the OpenMP oracle port."""
+    import ctypes as C
     cap = int(sample)
     slot_elem = np.repeat(np.arange(m.nelems, dtype=np.int32), ppe)[:cap]
     mask = np.ones(cap, np.uint8)
@@ -148,18 +172,35 @@ def cpu_reference_leg(orc, om, wl, m, ppe, sample, steps, warmup):
     dist = wl.push_distance(m)
     A, B = X, np.zeros_like(X)
     ids = None
+    handle = None
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    if ref is not None:
+        off, val = om.side2elem_off(), om.side2elem()
+        exposed = np.ascontiguousarray(om.exposed(), np.int8)
+        handle = C.c_void_p(ref.ref_bench_create(
+            3, m.nverts, m.coords.ctypes.data_as(dp), m.nelems, m.elem2verts.ctypes.data_as(ip), m.nsides,
+            m.elem2sides.ctypes.data_as(ip), m.side2verts.ctypes.data_as(ip), off.ctypes.data_as(ip),
+            val.ctypes.data_as(ip), exposed.ctypes.data_as(C.POINTER(C.c_byte)), om.vol().ctypes.data_as(dp),
+            cap, slot_elem.ctypes.data_as(ip), mask.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        ids = np.full(cap, -1, np.int32)
     times, active = [], []
     for it in range(warmup + steps):
         sgn = dist if it % 2 == 0 else -dist
         t0 = time.perf_counter()
-        np.copyto(B, A)                       # xtgt = x ...
-        orc.push_direction(mask, B, D, sgn)   # ... + d*dir   (same arithmetic as the fused push)
-        found, ids, _, _, st = om.search_mesh(slot_elem, mask, A, B, elem_ids=ids)
+        if handle is not None:
+            ref.ref_bench_step(handle, A.ctypes.data_as(dp), B.ctypes.data_as(dp), D.ctypes.data_as(dp),
+                               C.c_long(A.shape[1]), C.c_double(sgn), ids.ctypes.data_as(ip), int(it == 0))
+        else:
+            np.copyto(B, A)                       # xtgt = x ...
+            orc.push_direction(mask, B, D, sgn)   # ... + d*dir   (same arithmetic as the fused push)
+            found, ids, _, _, st = om.search_mesh(slot_elem, mask, A, B, elem_ids=ids)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
             active.append(int((ids >= 0).sum()))
         A, B = B, A
+    if handle is not None:
+        ref.ref_bench_destroy(handle)
     return float(sum(active)) / sum(times), 1e3 * sum(times) / len(times), cap
 
 
@@ -214,15 +255,17 @@ def main():
         from meshes import Mesh as TMesh
         tm = TMesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
         om = orc.OracleMesh(tm)
-        cores = orc.lib().orc_get_max_threads()
-        val, ms, cap = cpu_reference_leg(orc, om, wl, tm, ppe, a.cpu_sample, a.steps, a.warmup)
+        ref = load_ref_lib()
+        cores = ref.ref_get_max_threads() if ref is not None else orc.lib().orc_get_max_threads()
+        val, ms, cap = cpu_reference_leg(orc, om, wl, tm, ppe, a.cpu_sample, a.steps, a.warmup, ref=ref)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "first %d particles of the workload per step, OpenMP oracle "
-                                           "(CPU restatement of the reference algorithm)" % cap},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores,
+                                 "kind": "reference" if ref is not None else "port",
+                                 "sample": "first %d particles of the workload per step; %s"
+                                           % (cap, REF_NOTE if ref is not None else PORT_NOTE)},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -397,11 +440,12 @@ def main():
         from meshes import Mesh as TMesh
         tm = TMesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
         om = orc.OracleMesh(tm)
-        cores = orc.lib().orc_get_max_threads()
-        val, ms, ncap = cpu_reference_leg(orc, om, wl, tm, ppe, min(a.cpu_sample, 4_000_000), 4, 1)
-        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "first %d particles of the workload, 4 timed steps after 1 warm-up, "
-                         "OpenMP oracle (CPU restatement of the reference algorithm)" % ncap,
+        ref = load_ref_lib()
+        cores = ref.ref_get_max_threads() if ref is not None else orc.lib().orc_get_max_threads()
+        val, ms, ncap = cpu_reference_leg(orc, om, wl, tm, ppe, min(a.cpu_sample, 4_000_000), 4, 1, ref=ref)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "reference" if ref is not None else "port",
+               "sample": "first %d particles of the workload, 4 timed steps after 1 warm-up; %s"
+                         % (ncap, REF_NOTE if ref is not None else PORT_NOTE),
                "ms_per_step": ms}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,

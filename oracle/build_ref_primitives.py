@@ -220,7 +220,7 @@ def main():
         tparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(OUT, "ref_testadj.inc"), "w") as fh:
         fh.write("\n".join(tparts))
-    cmd = ["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
+    cmd = ["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
            "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", OUT,
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
            os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), "-o", LIB]

@@ -15,7 +15,8 @@
 //   pumipic::ParticleStructure + parallel_for   a loop over all slots: fn(row element, slot, mask)
 //   Kokkos::parallel_reduce(Min), atomic_add, Timer, Profiling; MPI_Comm_rank; RecordTime ...
 // Every kernel of the reference is data-parallel over slots with no cross-slot dependence other than
-// counters, so a serial loop executes exactly what the Kokkos backends execute.
+// counters (atomics), so the loops run under OpenMP when the file is compiled with -fopenmp -- the
+// role of the reference's Kokkos OpenMP backend -- and give the same results serially.
 #pragma once
 #include <cfloat>
 #include <cstddef>
@@ -56,7 +57,12 @@ void parallel_reduce(int n, F f, T& total) {   // sum reduction into `total`
   for (int i = 0; i < n; ++i) f(i, v);
   total = v;
 }
-template <class T, class U> void atomic_add(T* p, U v) { *p += v; }
+template <class T, class U> void atomic_add(T* p, U v) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+  *p += v;
+}
 struct Timer { double seconds() const { return 0.0; } };
 namespace Profiling {
 static inline void pushRegion(const char*) {}
@@ -67,18 +73,36 @@ static inline void popRegion() {}
 namespace Omega_h {
 typedef signed char I8;
 typedef int ClassId;
+// Omega_h::Write: a ref-counted array whose const copies still write (like a Kokkos view).  Raw
+// pointer + owner so that an access is one load; filled in parallel like Omega_h fills it; `alias`
+// wraps caller memory without copying (used by the timing entry points).
 template <class T>
 class Write {
-  std::shared_ptr<std::vector<T>> d_;
+  std::shared_ptr<T> own_;
+  T* p_ = nullptr;
+  int n_ = 0;
+  void alloc(int n) {
+    n_ = n;
+    own_ = std::shared_ptr<T>(static_cast<T*>(std::malloc(sizeof(T) * (size_t)(n > 0 ? n : 1))), std::free);
+    p_ = own_.get();
+  }
 
  public:
-  Write() : d_(std::make_shared<std::vector<T>>()) {}
-  Write(int n, T v, const std::string& = "") : d_(std::make_shared<std::vector<T>>((size_t)n, v)) {}
-  explicit Write(int n, const std::string& = "") : d_(std::make_shared<std::vector<T>>((size_t)n)) {}
-  template <class H, class = decltype(std::declval<H>().write())> Write(const H& h) : d_(h.write().d_) {}
-  int size() const { return (int)d_->size(); }
-  T& operator[](int i) const { return (*d_)[(size_t)i]; }
-  T* data() const { return d_->data(); }
+  Write() {}
+  Write(int n, T v, const std::string& = "") {
+    alloc(n);
+    T* q = p_;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int i = 0; i < n; ++i) q[i] = v;
+  }
+  explicit Write(int n, const std::string& = "") { alloc(n); }
+  template <class H, class = decltype(std::declval<H>().write())> Write(const H& h) { *this = h.write(); }
+  static Write alias(T* p, int n) { Write w; w.p_ = p; w.n_ = n; return w; }
+  int size() const { return n_; }
+  T& operator[](int i) const { return p_[i]; }
+  T* data() const { return p_; }
 };
 template <class T>
 class Read {
@@ -103,10 +127,25 @@ class HostWrite {
 typedef Read<LO> LOs;
 typedef Read<Real> Reals;
 typedef Read<I8> Bytes;
-template <class F> void parallel_for(int n, F f, const std::string& = "") { for (int i = 0; i < n; ++i) f(i); }
+// a failed OMEGA_H_CHECK (RefCheckFailed) must not leave an OpenMP region as an exception: it is
+// noted inside and rethrown after the loop
+template <class F> void parallel_for(int n, F f, const std::string& = "") {
+  int failed = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (int i = 0; i < n; ++i) {
+    try { f(i); } catch (const RefCheckFailed&) { failed = 1; }
+  }
+  if (failed) throw RefCheckFailed();
+}
 template <class T> T get_min(Read<T> a) {
   T m = a[0];
-  for (int i = 1; i < a.size(); ++i) if (a[i] < m) m = a[i];
+  const int n = a.size();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(min : m)
+#endif
+  for (int i = 1; i < n; ++i) if (a[i] < m) m = a[i];
   return m;
 }
 
@@ -255,7 +294,17 @@ class ParticleStructure {
 };
 template <class DataTypes, class F>
 void parallel_for(ParticleStructure<DataTypes>* ps, F& fn, std::string = "") {
-  for (int s = 0; s < ps->cap; ++s) fn(ps->slot_elem[s], s, ps->mask[s] != 0);
+  const int cap = ps->cap;
+  const int* se = ps->slot_elem;
+  const unsigned char* mk = ps->mask;
+  int failed = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (int s = 0; s < cap; ++s) {
+    try { fn(se[s], s, mk[s] != 0); } catch (const RefCheckFailed&) { failed = 1; }
+  }
+  if (failed) throw RefCheckFailed();
 }
 }  // namespace pumipic
 namespace particle_structs = pumipic;

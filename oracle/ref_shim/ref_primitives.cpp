@@ -3,6 +3,9 @@
 // functions: their text is pulled in from oracle/_ref/ref_primitives.inc, which
 // oracle/build_ref_primitives.py extracts from /root/reference at build time.
 #include "omega_h_mesh_shim.hpp"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace o = Omega_h;
 namespace ps = particle_structs;
@@ -264,4 +267,20 @@ extern "C" double ref_interpolate3d_field(double x, double y, double z, int nx, 
                                           const double* gridy, const double* gridz, const double* data) {
   return pumipic::interpolate3d_field(x, y, z, nx, ny, nz, o::Reals(to_write(gridx, nx)), o::Reals(to_write(gridy, ny)),
                                       o::Reals(to_write(gridz, nz)), o::Reals(to_write(data, (long)nx * ny * nz)));
+}
+
+// threads of the OpenMP loops of the stand-ins (1 = the serial order the oracle uses)
+extern "C" void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+extern "C" int ref_get_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
 }

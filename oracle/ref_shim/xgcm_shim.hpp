@@ -19,7 +19,14 @@
 #define MPI_COMM_WORLD 0
 
 namespace Kokkos {
-template <class T, class U> T atomic_fetch_add(T* p, U v) { T old = *p; *p += v; return old; }
+template <class T, class U> T atomic_fetch_add(T* p, U v) {
+  T old;
+#ifdef _OPENMP
+#pragma omp atomic capture
+#endif
+  { old = *p; *p += v; }
+  return old;
+}
 struct DefaultExecutionSpace {};
 template <class Space> struct TeamPolicy { int league, team; };
 }  // namespace Kokkos

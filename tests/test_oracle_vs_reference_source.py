@@ -365,12 +365,21 @@ def test_gyro_ring_map_and_scatter_equal_the_reference(ref, meshname, rmax, nrin
     slot_elem = rng.integers(0, mesh.nelems, cap).astype(np.int32)
     slot_elem[: cap // 3] = slot_elem[0]                          # a crowded element
     mask = (rng.random(cap) < 0.8).astype(np.uint8)
-    want = np.zeros(mesh.nverts)
-    ref.ref_gyro_scatter(mesh.nverts, mesh.nelems, _i(mesh.elem2verts), cap, _i(slot_elem),
-                         mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _i(fwd), C.c_long(fwd.shape[0]),
-                         C.c_double(rmax), nrings, ppr, _d(want))
     got = om.gyro_scatter(slot_elem, mask, fwd, rmax, nrings, ppr)
-    assert np.array_equal(got, want) and want.sum() > 0
+    nthreads = ref.ref_get_max_threads()
+    for threads in (1, nthreads):
+        # the reference sums with atomics: one thread = ascending vertex order (the oracle's order,
+        # bit-identical); several threads = any order, exact only when 1/ppr is a power of two
+        ref.ref_set_num_threads(threads)
+        want = np.zeros(mesh.nverts)
+        ref.ref_gyro_scatter(mesh.nverts, mesh.nelems, _i(mesh.elem2verts), cap, _i(slot_elem),
+                             mask.ctypes.data_as(C.POINTER(C.c_ubyte)), _i(fwd), C.c_long(fwd.shape[0]),
+                             C.c_double(rmax), nrings, ppr, _d(want))
+        if threads == 1 or ppr == 8:
+            assert np.array_equal(got, want) and want.sum() > 0
+        else:
+            assert np.allclose(got, want, rtol=1e-12, atol=0)
+    ref.ref_set_num_threads(nthreads)
 
 
 def test_elliptical_push_equals_the_reference(ref):
@@ -530,3 +539,41 @@ def test_workload_generator_equals_the_reference(ref, meshname):
     P = np.zeros((3, cap)); P[:, m] = x[:, m]
     orc.push_direction(mask, P, mo, d_ref)
     assert np.array_equal(P[:, m], xt[:, m])
+
+
+def test_bench_cpu_leg_engines_agree(ref):
+    """bench.py's CPU legs: the reference-source engine (ref_bench_step: the reference's push_ptcls +
+    search_mesh, OpenMP stand-ins, carried-over element ids aliased in place) and the oracle port
+    produce the same positions and element ids step after step of the ping-pong loop."""
+    import ptcl_init as pi
+    from meshes import kuhn_cube
+    mesh = kuhn_cube(6)
+    om = orc.OracleMesh(mesh)
+    n = 30000
+    ppe = pi.even_ppe(mesh.nelems, n)
+    slot_elem = np.repeat(np.arange(mesh.nelems, dtype=np.int32), ppe)[:n]
+    mask = np.ones(n, np.uint8)
+    X, D = pi.init3d_internal(mesh, slot_elem, mask)
+    dist = 2.0 * pi.push_distance(mesh)
+    off, val = om.side2elem_off(), om.side2elem()
+    ref.ref_bench_create.restype = C.c_void_p
+    h = C.c_void_p(ref.ref_bench_create(
+        3, mesh.nverts, _d(mesh.coords), mesh.nelems, _i(mesh.elem2verts), mesh.nsides, _i(mesh.elem2sides),
+        _i(mesh.side2verts), _i(off), _i(val),
+        np.ascontiguousarray(om.exposed(), np.int8).ctypes.data_as(C.POINTER(C.c_byte)), _d(om.vol()), n,
+        _i(slot_elem), mask.ctypes.data_as(C.POINTER(C.c_ubyte))))
+    A0, B0 = X.copy(), np.zeros_like(X)
+    A1, B1 = X.copy(), np.zeros_like(X)
+    ids0, ids1 = None, np.full(n, -1, np.int32)
+    for it in range(4):
+        sgn = dist if it % 2 == 0 else -dist
+        np.copyto(B0, A0)
+        orc.push_direction(mask, B0, D, sgn)
+        f0, ids0, _, _, _ = om.search_mesh(slot_elem, mask, A0, B0, elem_ids=ids0)
+        f1 = ref.ref_bench_step(h, _d(A1), _d(B1), _d(D), C.c_long(n), C.c_double(sgn), ids1.ctypes.data_as(ip),
+                                int(it == 0))
+        assert bool(f1) == f0 and np.array_equal(B0, B1) and np.array_equal(ids0, ids1)
+        A0, B0 = B0, A0
+        A1, B1 = B1, A1
+    assert (ids0 == -1).any() and (ids0 >= 0).any()
+    ref.ref_bench_destroy(h)
