@@ -103,6 +103,12 @@ TESTADJ_FUNCTIONS = [
     ("test/test_adj.cpp", r"o::Real get_push_distance\(", 0),
     ("test/test_adj.cpp", r"void push_ptcls\(", 0),
 ]
+# test/pseudoPushAndSearch.cpp: the constant-vector push and the position update (ref_shim/ref_ppas.cpp)
+PPAS_LINES = [r"typedef MemberTypes<Vector3d, Vector3d, int> Particle;", r"typedef ps::ParticleStructure<Particle> PS;"]
+PPAS_FUNCTIONS = [
+    ("test/pseudoPushAndSearch.cpp", r"void push\(PS\* ptcls, int np, fp_t distance", 0),
+    ("test/pseudoPushAndSearch.cpp", r"void updatePtclPositions\(PS\* ptcls\)", 0),
+]
 # src/pumipic_ptcl_ops.hpp (namespace pumipic; needs the pumipic::Mesh stand-in of xgcm_shim.hpp)
 PTCL_OPS_FUNCTIONS = [
     ("src/pumipic_ptcl_ops.hpp", r"void setUnsafeProcs\(Mesh& mesh", 0),
@@ -169,6 +175,7 @@ def main():
              os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"), os.path.join(REF, "test/gyroScatter.hpp"),
              os.path.join(REF, "test/ellipticalPush.hpp"), os.path.join(REF, "src/pumipic_ptcl_ops.hpp"),
              os.path.join(REF, "test/test_adj.cpp"), os.path.join(HERE, "ref_shim", "ref_testadj.cpp"),
+             os.path.join(REF, "test/pseudoPushAndSearch.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
              os.path.abspath(__file__)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0
@@ -220,10 +227,23 @@ def main():
         tparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(OUT, "ref_testadj.inc"), "w") as fh:
         fh.write("\n".join(tparts))
+    pparts = [parts[0]]
+    ppas = open(os.path.join(REF, "test/pseudoPushAndSearch.cpp")).read()
+    for pat in PPAS_LINES:
+        m = re.search(pat, ppas)
+        if not m:
+            raise SystemExit("build_ref_primitives: %r not found in pseudoPushAndSearch.cpp" % pat)
+        pparts.append("// test/pseudoPushAndSearch.cpp\n" + m.group(0) + "\n")
+    for f, pat, which in PPAS_FUNCTIONS:
+        body, l0, l1 = extract(ppas, pat, which)
+        pparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
+    with open(os.path.join(OUT, "ref_ppas.inc"), "w") as fh:
+        fh.write("\n".join(pparts))
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
            "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", OUT,
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
-           os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), "-o", LIB]
+           os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
+           "-o", LIB]
     subprocess.check_call(cmd)
     print(LIB)
     return 0

@@ -63,7 +63,7 @@ template <class T, class U> void atomic_add(T* p, U v) {
 #endif
   *p += v;
 }
-struct Timer { double seconds() const { return 0.0; } };
+struct Timer { void reset() {} double seconds() const { return 0.0; } };
 namespace Profiling {
 static inline void pushRegion(const char*) {}
 static inline void popRegion() {}

@@ -577,3 +577,26 @@ def test_bench_cpu_leg_engines_agree(ref):
         A1, B1 = B1, A1
     assert (ids0 == -1).any() and (ids0 >= 0).any()
     ref.ref_bench_destroy(h)
+
+
+def test_constant_push_and_position_update_equal_the_reference(ref):
+    """push (constant vector) and updatePtclPositions of test/pseudoPushAndSearch.cpp (:87-118,
+    :142-154) compiled unmodified: the oracle's orc_push_constant / orc_update_positions match, including
+    the reference's `+ ptclUnique_d[pid]` (a zero array) and the update running over every slot."""
+    rng = np.random.default_rng(13)
+    cap = 5000
+    slot_elem = rng.integers(0, 100, cap).astype(np.int32)
+    mask = (rng.random(cap) < 0.85).astype(np.uint8)
+    X = rng.normal(0, 3, (3, cap))
+    T0, T1 = rng.normal(0, 1, (3, cap)), None
+    T1 = T0.copy()
+    dist, dvec = 3.275, (0.3, -0.0, 1.0)
+    orc.push_constant(mask, X, T0, dist, dvec)
+    ub = C.POINTER(C.c_ubyte)
+    ref.ref_push_constant(cap, _i(slot_elem), mask.ctypes.data_as(ub), _d(X), _d(T1), C.c_long(cap), C.c_double(dist),
+                          C.c_double(dvec[0]), C.c_double(dvec[1]), C.c_double(dvec[2]))
+    assert np.array_equal(T0, T1) and not np.array_equal(T0[:, mask > 0], X[:, mask > 0])
+    X0, X1 = X.copy(), X.copy()
+    orc.update_positions(X0, T0)
+    ref.ref_update_positions(cap, _i(slot_elem), mask.ctypes.data_as(ub), _d(X1), _d(T1), C.c_long(cap))
+    assert np.array_equal(X0, X1) and np.array_equal(T0, T1) and not T0.any()
