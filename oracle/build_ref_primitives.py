@@ -6,8 +6,9 @@ primitives and the search loops -- compiled unmodified from the sources where th
 The reference as a whole is unbuildable here (Kokkos, Omega_h, EnGPar, MPI are absent; DESIGN.md
 section 2), but its search is free functions and templates over a small vocabulary.  This script
   1. locates each function in the reference tree by its signature and copies its text (brace
-     matching that skips comments and literals) into oracle/_ref/ref_primitives.inc (git-ignored:
-     no reference source enters the repository),
+     matching that skips comments and literals) into a temporary directory that is deleted
+     after the compile: no reference source enters the repository or stays in the tree, only the
+     shared library lands in the git-ignored oracle/_ref/,
   2. compiles it with g++, -ffp-contract=off like the oracle, against oracle/ref_shim/: our
      stand-ins for Omega_h's small-vector types and arithmetic (omega_h_shim.hpp), for
      Omega_h::Mesh / Write / Read, ps::parallel_for and the Kokkos / MPI calls the loops make
@@ -20,8 +21,10 @@ library travels with the snapshot).
 """
 import os
 import re
+import shutil
 import subprocess
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("PUMIPIC_REFERENCE", "/root/reference")
@@ -180,8 +183,9 @@ def main():
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0
     os.makedirs(OUT, exist_ok=True)
-    parts = ["// GENERATED by oracle/build_ref_primitives.py from %s -- reference source text, not part of the\n"
-             "// repository (oracle/_ref/ is git-ignored).\n" % REF]
+    tmp = tempfile.mkdtemp(prefix="pumipic_ref_")     # the extracted reference text never stays on disk
+    parts = ["// GENERATED by oracle/build_ref_primitives.py from %s -- reference source text in a temporary\n"
+             "// directory, deleted after the compile.\n" % REF]
     consts = open(os.path.join(REF, "src/pumipic_constants.hpp")).read()
     for name in ("EPSILON", "DIM", "FDIM"):
         m = re.search(r"^.*\b%s\b\s*=.*;.*$" % name, consts, re.M)
@@ -193,7 +197,7 @@ def main():
         text = cache.setdefault(f, open(os.path.join(REF, f)).read())
         body, l0, l1 = extract(text, pat, which)
         parts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
-    with open(os.path.join(OUT, "ref_primitives.inc"), "w") as fh:
+    with open(os.path.join(tmp, "ref_primitives.inc"), "w") as fh:
         fh.write("\n".join(parts))
     xparts = [parts[0]]
     types = open(os.path.join(REF, "test/pseudoXGCmTypes.hpp")).read()
@@ -206,14 +210,14 @@ def main():
         text = cache.setdefault(f, open(os.path.join(REF, f)).read())
         body, l0, l1 = extract(text, pat, which)
         xparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
-    with open(os.path.join(OUT, "ref_xgcm.inc"), "w") as fh:
+    with open(os.path.join(tmp, "ref_xgcm.inc"), "w") as fh:
         fh.write("\n".join(xparts))
     oparts = [parts[0]]
     for f, pat, which in PTCL_OPS_FUNCTIONS:
         text = cache.setdefault(f, open(os.path.join(REF, f)).read())
         body, l0, l1 = extract(text, pat, which)
         oparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
-    with open(os.path.join(OUT, "ref_ptcl_ops.inc"), "w") as fh:
+    with open(os.path.join(tmp, "ref_ptcl_ops.inc"), "w") as fh:
         fh.write("\n".join(oparts))
     tparts = [parts[0]]
     tadj = open(os.path.join(REF, "test/test_adj.cpp")).read()
@@ -225,7 +229,7 @@ def main():
     for f, pat, which in TESTADJ_FUNCTIONS:
         body, l0, l1 = extract(tadj, pat, which)
         tparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
-    with open(os.path.join(OUT, "ref_testadj.inc"), "w") as fh:
+    with open(os.path.join(tmp, "ref_testadj.inc"), "w") as fh:
         fh.write("\n".join(tparts))
     pparts = [parts[0]]
     ppas = open(os.path.join(REF, "test/pseudoPushAndSearch.cpp")).read()
@@ -237,14 +241,23 @@ def main():
     for f, pat, which in PPAS_FUNCTIONS:
         body, l0, l1 = extract(ppas, pat, which)
         pparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
-    with open(os.path.join(OUT, "ref_ppas.inc"), "w") as fh:
+    with open(os.path.join(tmp, "ref_ppas.inc"), "w") as fh:
         fh.write("\n".join(pparts))
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
-           "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", OUT,
+           "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", tmp,
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
            os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
            "-o", LIB]
-    subprocess.check_call(cmd)
+    try:
+        subprocess.check_call(cmd)
+    finally:
+        if os.environ.get("PUMIPIC_KEEP_REF_TEXT"):
+            print("extracted reference text kept in", tmp)
+        else:
+            shutil.rmtree(tmp, ignore_errors=True)
+    for stale in ("ref_primitives.inc", "ref_xgcm.inc", "ref_ptcl_ops.inc", "ref_testadj.inc", "ref_ppas.inc"):
+        if os.path.exists(os.path.join(OUT, stale)):
+            os.remove(os.path.join(OUT, stale))
     print(LIB)
     return 0
 

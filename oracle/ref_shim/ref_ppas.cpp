@@ -1,6 +1,6 @@
 // ref_ppas.cpp -- TEST INFRASTRUCTURE ONLY.  The constant-vector push and updatePtclPositions of the
 // reference's test/pseudoPushAndSearch.cpp (:87-118, :142-154), extracted into
-// oracle/_ref/ref_ppas.inc and compiled unmodified.
+// ref_ppas.inc (a build-time temporary) and compiled unmodified.
 #include "xgcm_shim.hpp"
 
 namespace o = Omega_h;

@@ -1,6 +1,6 @@
 // ref_primitives.cpp -- TEST INFRASTRUCTURE ONLY.  extern "C" entry points, with the same
 // signatures as the oracle's primitives (oracle/pumipic_oracle.h:60-83), around the reference's own
-// functions: their text is pulled in from oracle/_ref/ref_primitives.inc, which
+// functions: their text is pulled in from ref_primitives.inc (a build-time temporary), which
 // oracle/build_ref_primitives.py extracts from /root/reference at build time.
 #include "omega_h_mesh_shim.hpp"
 #ifdef _OPENMP

@@ -1,6 +1,6 @@
 // ref_testadj.cpp -- TEST INFRASTRUCTURE ONLY.  The generator of the reference's synthetic search
 // workload (test/test_adj.cpp: setSourceElements, init2DInternal, init3DInternal,
-// get_push_distance, push_ptcls), extracted into oracle/_ref/ref_testadj.inc and compiled unmodified:
+// get_push_distance, push_ptcls), extracted into ref_testadj.inc (a build-time temporary) and compiled unmodified:
 // what pumi-pic_b200/workloads.py restates (std::default_random_engine(512*512) drawing per slot,
 // the fold into the simplex, the direction on the sphere, the push distance).
 #include <random>

@@ -1,5 +1,5 @@
 // ref_xgcm.cpp -- TEST INFRASTRUCTURE ONLY.  The reference's gyro ring mapping and gyro scatter
-// (test/gyroScatter.hpp, extracted into oracle/_ref/ref_xgcm.inc by build_ref_primitives.py)
+// (test/gyroScatter.hpp, extracted into ref_xgcm.inc (a build-time temporary) by build_ref_primitives.py)
 // compiled unmodified against xgcm_shim.hpp, behind extern "C" entry points with the oracle's
 // argument lists.
 #include "xgcm_shim.hpp"
