@@ -154,3 +154,65 @@ def test_stepped_walk_user_handler():
     assert np.array_equal(got[m], slot_elem[m]) and np.all(got[~m] == -1)
     le = seen["last_exit"].cpu().numpy()[:cap]
     assert np.all((mesh.elem2sides[slot_elem[m]] == le[m][:, None]).any(axis=1))
+
+
+# ---------------------------------------------------------------- BASELINE configs[0] on the GPU
+def test_c1_pseudo_push_and_search_on_the_gpu():
+    """test/pseudoPushAndSearch on cube/7k.osh as the reference registers it (testing.cmake:106-108, 200
+    particles on model face 156, push (0,0,1) * height/20, legacy search_mesh with maxLoops 100,
+    updatePtclPositions, rebuild, Sell-C-sigma sigma=INT_MAX V=1024 C=32): every iteration the
+    product's particle set -- id, element, position -- equals the oracle's, which
+    tests/test_c1_pseudo_push_and_search.py ties to the reference's own source."""
+    import torch as t
+    import c1_case
+    import oracle_api as orc
+    from gpu_common import dev, make_gpu_mesh
+    P = pp()
+    mesh, ppe, centroid, dist, d, marked = c1_case.setup(200)
+    om = orc.OracleMesh(mesh)
+    gm = make_gpu_mesh(mesh)
+    pel = np.repeat(np.arange(mesh.nelems, dtype=np.int32), ppe)
+    n0 = pel.shape[0]
+    info = [np.ascontiguousarray(centroid[pel].T), np.zeros((3, n0)), np.arange(n0, dtype=np.int32).reshape(1, -1)]
+    ps = P.ParticleStructure(P.capi.PP_PS_SCS, [(np.float64, 3), (np.float64, 3), (np.int32, 1)], ppe,
+                             elem_gids=np.arange(mesh.nelems, dtype=np.int64), particle_elements=pel,
+                             particle_info=info, team_size=32, sigma=0x7fffffff, V=1024)
+    # oracle state, keyed by particle id
+    elem_o, pid_o, X_o = pel.copy(), np.arange(n0, dtype=np.int32), info[0].copy()
+    iters = 0
+    for it in range(1, c1_case.NUM_ITERATIONS + 1):
+        if ps.nptcls == 0:
+            break
+        assert ps.nptcls == elem_o.shape[0]
+        iters += 1
+        cap = ps.capacity
+        x, xt = ps.get(0), ps.get(1)
+        P.push_constant(ps, x, xt, dist, d)
+        ids = t.zeros(cap, dtype=t.int32, device="cuda")
+        xface = t.full((cap,), -1, dtype=t.int32, device="cuda")
+        xpts = t.zeros(3 * cap, dtype=t.float64, device="cuda")
+        r = P.search_mesh(gm, ps, x, xt, ids, elem_ids_empty=True, variant=P.capi.PP_SEARCH_3D_LEGACY,
+                          inter_faces=xface, inter_points=xpts, looplimit=c1_case.MAX_LOOPS)
+        assert r.found == 1 and r.aborted == 0
+        P.update_positions(ps, x, xt)
+        # oracle step
+        n = elem_o.shape[0]
+        mask = np.ones(n, np.uint8)
+        T = np.zeros((3, n))
+        orc.push_constant(mask, X_o, T, dist, d)
+        found, ids_o, _, xf_o, st = om.search_mesh_legacy3d(elem_o, mask, X_o, T, looplimit=c1_case.MAX_LOOPS)
+        assert found and st.loops == r.loops
+        orc.update_positions(X_o, T)
+        # compare by particle id before the rebuild
+        _, m = ps.slot_elem_and_mask()
+        m = m.astype(bool)
+        gp = ps.get(2).cpu().numpy()[0, :cap][m]
+        order = np.argsort(gp)
+        assert np.array_equal(gp[order], pid_o)
+        assert np.array_equal(ids.cpu().numpy()[m][order], ids_o)
+        assert np.array_equal(xface.cpu().numpy()[m][order], xf_o)
+        assert np.array_equal(x.cpu().numpy()[:, :cap][:, m][:, order], X_o)
+        ps.rebuild(ids)
+        keep = ids_o >= 0
+        elem_o, pid_o, X_o = ids_o[keep].astype(np.int32), pid_o[keep], np.ascontiguousarray(X_o[:, keep])
+    assert ps.nptcls == 0 and elem_o.shape[0] == 0 and 10 <= iters <= 21
