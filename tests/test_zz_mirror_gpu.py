@@ -216,3 +216,61 @@ def test_c1_pseudo_push_and_search_on_the_gpu():
         keep = ids_o >= 0
         elem_o, pid_o, X_o = ids_o[keep].astype(np.int32), pid_o[keep], np.ascontiguousarray(X_o[:, keep])
     assert ps.nptcls == 0 and elem_o.shape[0] == 0 and 10 <= iters <= 21
+
+
+# ---------------------------------------------------------------- BASELINE configs[2] as a parity case
+def _combo_draw(rng, dist, ne, n):
+    """particle_structs/test/Distribute.cpp: 1 uniform (:77-89), 2 gaussian mean ne/2 sigma ne/8 clamped
+    (:129-144), 3 exponential via the inverse CDF with gap filling (:171-215) -- numpy draws"""
+    if dist == 1:
+        return rng.integers(0, ne, n).astype(np.int32)
+    if dist == 2:
+        return np.clip(rng.normal(ne / 2.0, ne / 8.0, n).astype(np.int32), 0, ne - 1).astype(np.int32)
+    fm = -np.log(1.0 / ne)
+    uni = rng.integers(0, ne, n)
+    pct = uni / ne
+    start = (-np.log(1 - pct) / fm * ne).astype(np.int64)
+    end = (-np.log(np.maximum(1 - pct - 1.0 / ne, 1e-300)) / fm * ne).astype(np.int64)
+    length = np.maximum(end - start, 1)
+    e = start + np.where(length > 1, np.minimum((rng.random(n) * length).astype(np.int64), length - 1), 0)
+    e = np.where(e >= ne, rng.integers(0, ne, n), e)
+    return np.where(uni == ne - 1, 0, e).astype(np.int32)
+
+
+@pytest.mark.parametrize("dist", [1, 2, 3])
+@pytest.mark.parametrize("ne,npt", [(100, 100000), (5000, 50000)])
+def test_ps_combo160_rebuild_sweep_point(dist, ne, npt):
+    """performance_tests/ps_combo160.cpp in small: 160-byte particles (perfTypes.hpp:7-9), SCS C=32
+    sigma=ne V=1024, the three particle distributions, and rebuilds in which half of the particles are
+    re-drawn from the same distribution (:207-232).  Invariants of test_rebuild.cpp: nothing lost or
+    duplicated, every particle in the element it asked for, its whole 160-byte record intact."""
+    import torch as t
+    from gpu_common import dev
+    P = pp()
+    rng = np.random.default_rng(100 * dist + ne)
+    members = [(np.float64, 17), (np.int32, 4), (np.int64, 1)]
+    pel = _combo_draw(rng, dist, ne, npt)
+    ppe = np.bincount(pel, minlength=ne).astype(np.int32)
+    ids = np.arange(npt, dtype=np.int64)
+    info = [np.ascontiguousarray((ids[None, :] * 1.5 + np.arange(17)[:, None]).astype(np.float64)),
+            np.ascontiguousarray((ids[None, :] % 1000 + np.arange(4)[:, None]).astype(np.int32)),
+            ids.reshape(1, -1)]
+    ps = P.ParticleStructure(P.capi.PP_PS_SCS, members, ppe, particle_elements=pel, particle_info=info,
+                             team_size=32, sigma=ne, V=1024)
+    want = pel.copy()                                           # element per particle id
+    for it in range(4):
+        cap = ps.capacity
+        se, m = ps.slot_elem_and_mask()
+        m = m.astype(bool)
+        pid = ps.get(2).cpu().numpy()[0, :cap]
+        assert np.array_equal(np.sort(pid[m]), ids) and np.array_equal(se[m], want[pid[m]])
+        d17 = ps.get(0).cpu().numpy()[:, :cap][:, m]
+        i4 = ps.get(1).cpu().numpy()[:, :cap][:, m]
+        assert np.array_equal(d17, pid[m][None, :] * 1.5 + np.arange(17)[:, None])
+        assert np.array_equal(i4, (pid[m][None, :] % 1000 + np.arange(4)[:, None]).astype(np.int32))
+        move = rng.random(npt) < 0.5
+        want = np.where(move, _combo_draw(rng, dist, ne, npt), want).astype(np.int32)
+        new = np.full(cap, -1, np.int32)
+        new[m] = want[pid[m]]
+        ps.rebuild(dev(new))
+        assert ps.nptcls == npt
