@@ -155,8 +155,12 @@ def load_ref_lib():
     import ctypes as C
     if not os.path.exists(REF_LIB):
         return None
-    L = C.CDLL(REF_LIB)
-    L.ref_bench_create.restype = C.c_void_p
+    try:
+        L = C.CDLL(REF_LIB)
+        L.ref_bench_create.restype = C.c_void_p
+        L.ref_get_max_threads.restype = C.c_int
+    except (OSError, AttributeError):          # built elsewhere and not loadable here: use the port
+        return None
     return L
 
 
