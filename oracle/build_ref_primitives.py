@@ -112,6 +112,12 @@ PPAS_FUNCTIONS = [
     ("test/pseudoPushAndSearch.cpp", r"void push\(PS\* ptcls, int np, fp_t distance", 0),
     ("test/pseudoPushAndSearch.cpp", r"void updatePtclPositions\(PS\* ptcls\)", 0),
 ]
+# particle_structs/src/scs/SCS_buildFns.h: the Sell-C-sigma geometry (ref_shim/ref_scs.cpp)
+SCS_FUNCTIONS = [
+    ("particle_structs/src/scs/SCS_buildFns.h", r"int SellCSigma<DataTypes, MemSpace>::chooseChunkHeight\(", 0),
+    ("particle_structs/src/scs/SCS_buildFns.h", r"void SellCSigma<DataTypes, MemSpace>::constructChunks\(", 0),
+    ("particle_structs/src/scs/SCS_buildFns.h", r"void SellCSigma<DataTypes, MemSpace>::constructOffsets\(", 0),
+]
 # src/pumipic_ptcl_ops.hpp (namespace pumipic; needs the pumipic::Mesh stand-in of xgcm_shim.hpp)
 PTCL_OPS_FUNCTIONS = [
     ("src/pumipic_ptcl_ops.hpp", r"void setUnsafeProcs\(Mesh& mesh", 0),
@@ -179,6 +185,7 @@ def main():
              os.path.join(REF, "test/ellipticalPush.hpp"), os.path.join(REF, "src/pumipic_ptcl_ops.hpp"),
              os.path.join(REF, "test/test_adj.cpp"), os.path.join(HERE, "ref_shim", "ref_testadj.cpp"),
              os.path.join(REF, "test/pseudoPushAndSearch.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
+             os.path.join(REF, "particle_structs/src/scs/SCS_buildFns.h"), os.path.join(HERE, "ref_shim", "ref_scs.cpp"),
              os.path.abspath(__file__)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0
@@ -231,6 +238,13 @@ def main():
         tparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(tmp, "ref_testadj.inc"), "w") as fh:
         fh.write("\n".join(tparts))
+    sparts = [parts[0]]
+    for f, pat, which in SCS_FUNCTIONS:
+        text = cache.setdefault(f, open(os.path.join(REF, f)).read())
+        body, l0, l1 = extract(text, pat, which)
+        sparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
+    with open(os.path.join(tmp, "ref_scs.inc"), "w") as fh:
+        fh.write("\n".join(sparts))
     pparts = [parts[0]]
     ppas = open(os.path.join(REF, "test/pseudoPushAndSearch.cpp")).read()
     for pat in PPAS_LINES:
@@ -247,7 +261,7 @@ def main():
            "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", tmp,
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
            os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
-           "-o", LIB]
+           os.path.join(HERE, "ref_shim", "ref_scs.cpp"), "-o", LIB]
     try:
         subprocess.check_call(cmd)
     finally:
@@ -255,7 +269,7 @@ def main():
             print("extracted reference text kept in", tmp)
         else:
             shutil.rmtree(tmp, ignore_errors=True)
-    for stale in ("ref_primitives.inc", "ref_xgcm.inc", "ref_ptcl_ops.inc", "ref_testadj.inc", "ref_ppas.inc"):
+    for stale in ("ref_primitives.inc", "ref_xgcm.inc", "ref_ptcl_ops.inc", "ref_testadj.inc", "ref_ppas.inc", "ref_scs.inc"):
         if os.path.exists(os.path.join(OUT, stale)):
             os.remove(os.path.join(OUT, stale))
     print(LIB)

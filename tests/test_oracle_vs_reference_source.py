@@ -600,3 +600,38 @@ def test_constant_push_and_position_update_equal_the_reference(ref):
     orc.update_positions(X0, T0)
     ref.ref_update_positions(cap, _i(slot_elem), mask.ctypes.data_as(ub), _d(X1), _d(T1), C.c_long(cap))
     assert np.array_equal(X0, X1) and np.array_equal(T0, T1) and not T0.any()
+
+
+def test_scs_geometry_of_the_reference_matches_the_measured_run(ref):
+    """chooseChunkHeight / constructChunks / constructOffsets (SCS_buildFns.h:4-153) compiled unmodified:
+    for the bench workload (10 M particles over the 998 250 tets of the Kuhn cube, C = 32, sigma = INT_MAX,
+    V = 1024, PAD_EVENLY 10 %) the reference's geometry has exactly the capacity the product's device
+    build reported in the committed bench line (profiles/r1f_bench_n1.json).  Plus the arithmetic of the
+    three padding strategies on a small hand-checked case."""
+    import json
+    import ptcl_init as pi
+    import scs_ref_layout as srl
+    line = json.load(open(os.path.join(ROOT, "profiles", "r1f_bench_n1.json")))
+    lay = srl.layout(pi.even_ppe(line["config"]["tets_per_gpu"], line["config"]["particles_per_gpu"]))
+    assert lay["capacity"] == line["detail"]["capacity"] == 10998528
+    assert lay["C"] == 32 and lay["nchunks"] == 31196 == lay["nslices"]
+    # 70 rows, C = 4 (sigma = full sort): widths are the maxima of 4 sorted rows, then the padding
+    ppe = np.array([0] * 10 + [1] * 20 + [5] * 30 + [9] * 8 + [40] * 2, np.int32)
+    rng = np.random.default_rng(0)
+    rng.shuffle(ppe)
+    raw = np.sort(ppe).reshape(-1, 1)[: 68].reshape(17, 4).max(axis=1).tolist() + [40]
+    for strat, pad in ((0, 0.1), (1, 0.1), (2, 0.1), (0, 0.0)):
+        lay = srl.layout(ppe, max_c=4, V=8, shuffle_padding=pad, pad_strat=strat)
+        w = np.asarray(raw)
+        if pad > 0:
+            if strat == 0:
+                w = np.where(w > 0, w + int(w.sum() * pad / (w > 0).sum()), w)
+            elif strat == 1:
+                w = (w + w * pad).astype(np.int64)            # int += double: truncation
+            else:
+                cw2 = w.sum() / (1.0 / w[w > 0]).sum() * pad
+                w = np.where(w > 0, (w + cw2 / np.maximum(w, 1)).astype(np.int64), w)
+        assert lay["C"] == 4 and lay["nchunks"] == 18 and lay["chunk_widths"].tolist() == w.tolist(), strat
+        nsl = sum(-(-int(x) // 8) for x in w)
+        assert lay["nslices"] == nsl and lay["capacity"] == 4 * int(w.sum()) == lay["offsets"][-1]
+        assert lay["num_empty"] == 10 + 2                       # empty elements + the 2 padding rows

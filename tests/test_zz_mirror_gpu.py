@@ -274,3 +274,32 @@ def test_ps_combo160_rebuild_sweep_point(dist, ne, npt):
         new[m] = want[pid[m]]
         ps.rebuild(dev(new))
         assert ps.nptcls == npt
+
+
+# ---------------------------------------------------------------- Sell-C-sigma geometry vs the reference's own code
+@pytest.mark.parametrize("kindname", ["scs_c32", "scs_s1_v10", "scs_c4_v2", "scs_s7", "scs_padprop", "scs_padinv"])
+@pytest.mark.parametrize("ne,np_", [(5, 25), (50, 1000), (2500, 100000), (1, 40), (300, 0)])
+def test_scs_geometry_equals_the_reference(kindname, ne, np_):
+    """The device build's chunk height, chunk count, vertical slices, offsets and capacity against the
+    reference's chooseChunkHeight / constructChunks / constructOffsets (SCS_buildFns.h:4-153) compiled
+    unmodified (tests/scs_ref_layout.py): these are functions of the particle counts alone (the order of
+    equally full rows, which the reference leaves to its sort backend, cannot change them)."""
+    import torch as t
+    import scs_ref_layout as srl
+    from test_structures_gpu import _kinds, _ppe
+    if not srl.available():
+        pytest.skip("oracle/_ref not built")
+    P = pp()
+    kw = dict(_kinds()[kindname])
+    kw.pop("kind")
+    ppe = _ppe(ne, np_)
+    ps = P.ParticleStructure(P.capi.PP_PS_SCS, [(np.int32, 1)], ppe, **kw)
+    lay = ps.layout()
+    cfg = kw.get("config", {})
+    ref = srl.layout(ppe, max_c=kw.get("team_size", 32), sigma=kw.get("sigma", 0x7fffffff), V=kw.get("V", 1024),
+                     shuffle_padding=cfg.get("shuffle_padding", 0.1), pad_strat=cfg.get("padding_strat", 0))
+    assert (lay.C, lay.nchunks, lay.nslices, ps.capacity) == (ref["C"], ref["nchunks"], ref["nslices"], ref["capacity"])
+    if lay.nslices:
+        off = P.api._tensor_from_ptr(lay.offsets, (lay.nslices + 1,), t.int32, ps).cpu().numpy()
+        s2c = P.api._tensor_from_ptr(lay.slice_to_chunk, (lay.nslices,), t.int32, ps).cpu().numpy()
+        assert np.array_equal(off, ref["offsets"]) and np.array_equal(s2c, ref["slice_to_chunk"])
