@@ -3,6 +3,8 @@
 No GPU needed.  Every expected value below is copied from a reference *test* (file:line cited),
 not computed by us.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -193,3 +195,23 @@ def test_search_mesh_3d_oracle_consistent_with_the_other_3d_walks():
     # loop limit: stops after `looplimit` iterations, unfinished particles keep their next element
     f2, ids2, _, _, st2 = om.search_mesh_3d(slot_elem, mask, X, T, looplimit=2)
     assert not f2 and st2.loops == 2 and st2.not_found > 0
+
+
+@pytest.mark.parametrize("name", ["cube7k", "xgc24k"])
+def test_reference_generated_search_goldens(name):
+    """tests/golden/ref_search_<mesh>.npz: element ids, wall sides and wall points that THE REFERENCE'S OWN
+    search_mesh code returned (generated by tests/golden/make_ref_search_goldens.py from the source under
+    /root/reference; the reference ships no golden ids for its 3D walk).  The inputs are regenerated
+    here from the seeded workload; the oracle must reproduce the file exactly."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_ref_search_goldens import inputs
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_search_%s.npz" % name))
+    mesh, slot_elem, mask, X, T = inputs(name)
+    om = orc.OracleMesh(mesh)
+    found, ids, _, _, _ = om.search_mesh(slot_elem, mask, X, T)
+    assert found and np.array_equal(ids, g["ids_bcc"])
+    found, ids, faces, pts, _ = om.search_mesh(slot_elem, mask, X, T, require_intersection=True)
+    assert found and np.array_equal(ids, g["ids_int"]) and np.array_equal(faces, g["faces"])
+    assert np.array_equal(pts, g["points"])
+    assert (g["ids_bcc"] >= 0).sum() > 1000 and (g["faces"] >= 0).sum() > 100

@@ -303,3 +303,49 @@ def test_scs_geometry_equals_the_reference(kindname, ne, np_):
         off = P.api._tensor_from_ptr(lay.offsets, (lay.nslices + 1,), t.int32, ps).cpu().numpy()
         s2c = P.api._tensor_from_ptr(lay.slice_to_chunk, (lay.nslices,), t.int32, ps).cpu().numpy()
         assert np.array_equal(off, ref["offsets"]) and np.array_equal(s2c, ref["slice_to_chunk"])
+
+
+# ---------------------------------------------------------------- reference-generated goldens, straight on the GPU
+@pytest.mark.parametrize("kind", ["scs", "csr"])
+@pytest.mark.parametrize("name", ["cube7k", "xgc24k"])
+def test_search_against_reference_generated_goldens(name, kind):
+    """The product against tests/golden/ref_search_<mesh>.npz -- what the reference's own search_mesh code
+    returned for the seeded workload -- with no oracle in between: element ids of the BCC walk, and
+    element ids, wall sides and wall points of the intersection walk, bit for bit."""
+    import os
+    import sys
+    import torch as t
+    from gpu_common import dev, make_gpu_mesh, make_ps
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    from make_ref_search_goldens import inputs
+    g = np.load(os.path.join(gdir, "ref_search_%s.npz" % name))
+    P = pp()
+    mesh, slot_elem, mask, X, T = inputs(name)
+    gm = make_gpu_mesh(mesh)
+    # a structure whose particle i sits in element slot_elem[i]: results are compared by particle
+    n = mask.shape[0]
+    live = np.flatnonzero(mask)
+    pel = slot_elem[live]
+    ppe = np.bincount(pel, minlength=mesh.nelems).astype(np.int32)
+    K = P.capi.PP_PS_SCS if kind == "scs" else P.capi.PP_PS_CSR
+    info = [np.ascontiguousarray(X[:, live]), np.ascontiguousarray(T[:, live]),
+            live.astype(np.int32).reshape(1, -1), np.zeros((3, live.shape[0]))]
+    ps = P.ParticleStructure(K, [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float64, 3)], ppe,
+                             particle_elements=pel, particle_info=info)
+    cap = ps.capacity
+    _, m = ps.slot_elem_and_mask()
+    m = m.astype(bool)
+    pid = ps.get(2).cpu().numpy()[0, :cap][m]
+    for req in (False, True):
+        ids = t.full((cap,), -7, dtype=t.int32, device="cuda")
+        faces = t.full((cap,), -5, dtype=t.int32, device="cuda") if req else None
+        pts = t.zeros(mesh.dim * cap, dtype=t.float64, device="cuda") if req else None
+        r = P.search_mesh(gm, ps, ps.get(0), ps.get(1), ids, elem_ids_empty=True, require_intersection=req,
+                          inter_faces=faces, inter_points=pts)
+        assert r.found == 1
+        got = ids.cpu().numpy()[m]
+        assert np.array_equal(got, g["ids_int" if req else "ids_bcc"][pid])
+        if req:
+            assert np.array_equal(faces.cpu().numpy()[m], g["faces"][pid])
+            assert np.array_equal(pts.cpu().numpy().reshape(cap, mesh.dim)[m], g["points"][pid])
