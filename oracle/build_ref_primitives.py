@@ -112,6 +112,14 @@ PPAS_FUNCTIONS = [
     ("test/pseudoPushAndSearch.cpp", r"void push\(PS\* ptcls, int np, fp_t distance", 0),
     ("test/pseudoPushAndSearch.cpp", r"void updatePtclPositions\(PS\* ptcls\)", 0),
 ]
+# test/pseudoXGCm.cpp: the generator of the poloidal-plane particle load (ref_shim/ref_xgcm_init.cpp)
+XGCINIT_LINES = [r"#define ELEMENT_SEED [^\n]*", r"#define PARTICLE_SEED [^\n]*"]
+XGCINIT_TYPE_LINES = [r"typedef MemberTypes<Vector3d, Vector3d, int, float, float> Particle;",
+                      r"typedef ps::ParticleStructure<Particle> PS;"]
+XGCINIT_FUNCTIONS = [
+    ("test/pseudoXGCm.cpp", r"int setSourceElements\(p::Mesh& picparts", 0),
+    ("test/pseudoXGCm.cpp", r"void setInitialPtclCoords\(p::Mesh& picparts", 0),
+]
 # particle_structs/src/scs/SCS_buildFns.h: the Sell-C-sigma geometry (ref_shim/ref_scs.cpp)
 SCS_FUNCTIONS = [
     ("particle_structs/src/scs/SCS_buildFns.h", r"int SellCSigma<DataTypes, MemSpace>::chooseChunkHeight\(", 0),
@@ -257,11 +265,27 @@ def main():
         pparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(tmp, "ref_ppas.inc"), "w") as fh:
         fh.write("\n".join(pparts))
+    iparts = [parts[0]]
+    xgcm = open(os.path.join(REF, "test/pseudoXGCm.cpp")).read()
+    xtypes = open(os.path.join(REF, "test/pseudoXGCmTypes.hpp")).read()
+    for text, pats, name in ((xgcm, XGCINIT_LINES, "test/pseudoXGCm.cpp"),
+                             (xtypes, XGCINIT_TYPE_LINES, "test/pseudoXGCmTypes.hpp")):
+        for pat in pats:
+            m = re.search(pat, text)
+            if not m:
+                raise SystemExit("build_ref_primitives: %r not found in %s" % (pat, name))
+            iparts.append("// %s\n%s\n" % (name, m.group(0)))
+    for f, pat, which in XGCINIT_FUNCTIONS:
+        body, l0, l1 = extract(xgcm, pat, which)
+        iparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
+    with open(os.path.join(tmp, "ref_xgcm_init.inc"), "w") as fh:
+        fh.write("\n".join(iparts))
     cmd = ["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
            "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", tmp,
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
            os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
-           os.path.join(HERE, "ref_shim", "ref_scs.cpp"), "-o", LIB]
+           os.path.join(HERE, "ref_shim", "ref_scs.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm_init.cpp"),
+           "-o", LIB]
     try:
         subprocess.check_call(cmd)
     finally:

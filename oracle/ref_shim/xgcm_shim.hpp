@@ -27,11 +27,17 @@ template <class T, class U> T atomic_fetch_add(T* p, U v) {
   { old = *p; *p += v; }
   return old;
 }
+static inline double round(double x) { return std::round(x); }
 struct DefaultExecutionSpace {};
 template <class Space> struct TeamPolicy { int league, team; };
 }  // namespace Kokkos
 
 namespace Omega_h {
+template <class T> T get_sum(Read<T> a) {
+  T s = T();
+  for (int i = 0; i < a.size(); ++i) s += a[i];
+  return s;
+}
 template <int dim, int n> Vector<dim> average(Matrix<dim, n> x) {
   Vector<dim> avg = x[0];
   for (int i = 1; i < n; ++i) avg = avg + x[i];
@@ -64,6 +70,8 @@ class Mesh {
   Omega_h::LOs owners, safe;
   Comm comm_;
   Omega_h::Mesh* operator->() { return &omesh; }
+  Omega_h::Mesh* mesh() { return &omesh; }
+  int dim() const { return omesh.dim(); }
   Omega_h::LOs entOwners(int) const { return owners; }
   Omega_h::LOs safeTag() const { return safe; }
   const Comm* comm() const { return &comm_; }

@@ -108,3 +108,80 @@ def even_ppe(nelems, nptcls):
     ppe = np.full(nelems, nptcls // nelems, np.int32)
     ppe[: nptcls % nelems] += 1
     return ppe
+
+
+ELEMENT_SEED = 1024 * 1024
+
+
+def std_normal(seed, n):
+    """The first n variates of libstdc++'s std::normal_distribution<double>(0, 1) driven by
+    std::default_random_engine(seed): Marsaglia's polar method on pairs of
+    generate_canonical<double,53> draws; an accepted pair (x, y) yields y * mult first and keeps
+    x * mult for the next call (bits/random.tcc normal_distribution::operator())."""
+    import math
+    pairs = (n + 1) // 2
+    k = int(pairs * 1.3) + 16                      # acceptance is pi / 4
+    while True:
+        u = std_uniform(seed, 2 * k).reshape(k, 2)
+        x = 2.0 * u[:, 0] - 1.0
+        y = 2.0 * u[:, 1] - 1.0
+        r2 = x * x + y * y
+        ok = ~((r2 > 1.0) | (r2 == 0.0))
+        if int(ok.sum()) >= pairs:
+            break
+        k *= 2
+    x, y, r2 = x[ok][:pairs], y[ok][:pairs], r2[ok][:pairs]
+    # libm's log, element by element: numpy's vector log may differ from it in the last place
+    mult = np.array([math.sqrt(-2 * math.log(v) / v) for v in r2.tolist()], np.float64).reshape(pairs)
+    out = np.empty(2 * pairs)
+    out[0::2] = y * mult
+    out[1::2] = x * mult
+    return out[:n]
+
+
+def _std_round(v):
+    """std::round: to nearest, halves away from zero (v - trunc(v) is exact)."""
+    t = np.trunc(v)
+    return t + np.sign(v) * (np.abs(v - t) >= 0.5)
+
+
+def xgc_source_elements(class_id, owners, rank, mdl_face, nptcls, seed=ELEMENT_SEED):
+    """test/pseudoXGCm.cpp:167-222 setSourceElements: particles per element, normal(mean = nptcls /
+    marked, sigma = mean / 4 in INTEGER arithmetic) on every owned element whose class id is at most
+    mdl_face, in element order until nptcls are placed; the overshoot is cut from the element that
+    crossed the total, a shortfall goes to the last element touched.  Returns (ppe, total)."""
+    nelems = class_id.shape[0]
+    marked = (class_id <= mdl_face) & (owners == rank)
+    ppe = np.zeros(nelems, np.int32)
+    idx = np.flatnonzero(marked)
+    if idx.shape[0] == 0 or nptcls <= 0:
+        return ppe, 0
+    nppe = nptcls // idx.shape[0]
+    cnt = _std_round(std_normal(seed, idx.shape[0]) * float(nppe // 4) + float(nppe)).astype(np.int64)
+    cnt[cnt < 0] = 0
+    cum = np.cumsum(cnt)
+    j = int(np.searchsorted(cum, nptcls, side="left"))        # the element whose draw reaches the total
+    if j < idx.shape[0]:
+        cnt[j] -= cum[j] - nptcls
+        cnt[j + 1:] = 0
+    else:
+        cnt[-1] += nptcls - cum[-1]
+    ppe[idx] = cnt
+    return ppe, int(ppe.sum())
+
+
+def xgc_initial_coords(mesh, slot_elem, mask, seed=PARTICLE_SEED):
+    """test/pseudoXGCm.cpp:224-264 setInitialPtclCoords: two uniforms per SLOT (masked or not) folded
+    into the unit triangle, X = A + r1 (B - A) + r2 (C - A) in the slot's row element, z = 0."""
+    cap = mask.shape[0]
+    r = std_uniform(seed, 2 * cap).reshape(cap, 2)
+    x, y = r[:, 0].copy(), r[:, 1].copy()
+    f = x + y > 1
+    x[f], y[f] = 1 - x[f], 1 - y[f]
+    m = mask.astype(bool)
+    se = np.where(m, slot_elem, 0)
+    V = mesh.coords[mesh.elem2verts[se]]
+    pos = (V[:, 0] + x[:, None] * (V[:, 1] - V[:, 0])) + y[:, None] * (V[:, 2] - V[:, 0])
+    X = np.zeros((3, cap))
+    X[:2, m] = pos[m].T
+    return X

@@ -541,6 +541,54 @@ def test_workload_generator_equals_the_reference(ref, meshname):
     assert np.array_equal(P[:, m], xt[:, m])
 
 
+@pytest.mark.parametrize("meshname,nptcls", [("xgc24k", 100000), ("xgc24k", 1000), ("plate15", 3000), ("plate15", 0)])
+def test_xgcm_load_generator_equals_the_reference(ref, meshname, nptcls):
+    """BASELINE configs[3] (pseudoXGCm): the particle load of test/pseudoXGCm.cpp -- setSourceElements
+    :167-222 (std::normal_distribution on std::default_random_engine(1024*1024), integer sigma, the
+    overshoot / shortfall rules) and setInitialPtclCoords :224-264 (two uniforms per SLOT of
+    engine(512*512), folded) -- compiled unmodified, against workloads.xgc_source_elements /
+    xgc_initial_coords: identical counts and identical doubles."""
+    import ptcl_init as pi
+    from meshes import load_fixture, plate
+    mesh = plate(15) if meshname == "plate15" else load_fixture(meshname)
+    rng = np.random.default_rng(3)
+    cls = mesh.class_id.astype(np.int32) if meshname == "xgc24k" else rng.integers(100, 180, mesh.nelems).astype(np.int32)
+    for self_rank, owners in ((0, np.zeros(mesh.nelems, np.int32)),
+                              (2, rng.integers(0, 4, mesh.nelems).astype(np.int32)),
+                              (7, np.zeros(mesh.nelems, np.int32))):          # rank 7 owns nothing
+        for mdl_face in (141, 1 << 30, -5):
+            ppe_r = np.full(mesh.nelems, -3, np.int32)
+            tot_r = ref.ref_xgcm_source_elements(mesh.nelems, _i(cls), _i(owners), self_rank, mdl_face, nptcls,
+                                                 ppe_r.ctypes.data_as(ip))
+            ppe, tot = pi.xgc_source_elements(cls, owners, self_rank, mdl_face, nptcls)
+            marked = (cls <= mdl_face) & (owners == self_rank)
+            if not marked.any():
+                assert tot_r == 0 and tot == 0          # the reference returns before it writes ppe
+                continue
+            assert tot_r == tot and np.array_equal(ppe_r, ppe)
+            assert tot == nptcls and not ppe[~marked].any()
+    ppe, tot = pi.xgc_source_elements(cls, np.zeros(mesh.nelems, np.int32), 0, 141 if meshname == "xgc24k" else 150, nptcls)
+    # a padded structure over that load: rows of 32 slots, so most rows end in empty slots
+    rows = -(-ppe // 32) * 32
+    slot_elem = np.repeat(np.arange(mesh.nelems, dtype=np.int32), rows)
+    first = np.concatenate(([0], np.cumsum(rows)[:-1]))
+    mask = (np.arange(slot_elem.shape[0]) - np.repeat(first, rows) < np.repeat(ppe, rows)).astype(np.uint8)
+    cap = mask.shape[0]
+    assert int(mask.sum()) == tot
+    x = np.full((3, cap), 9.0)
+    ref.ref_xgcm_initial_coords(mesh.nverts, _d(mesh.coords), mesh.nelems, _i(mesh.elem2verts), cap, _i(slot_elem),
+                                mask.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_long(cap), _d(x))
+    X = pi.xgc_initial_coords(mesh, slot_elem, mask)
+    m = mask.astype(bool)
+    assert np.array_equal(X[:, m], x[:, m]) and (x[:, ~m] == 9.0).all()
+    if tot:
+        om = orc.OracleMesh(mesh)
+        # every particle lies in its row element (what check_initial_parents would test)
+        ids = np.full(cap, -1, np.int32)
+        found, ids, st = om.search_mesh_2d(slot_elem, mask, X, ids, looplimit=5)
+        assert found and np.array_equal(ids[m], slot_elem[m])
+
+
 def test_bench_cpu_leg_engines_agree(ref):
     """bench.py's CPU legs: the reference-source engine (ref_bench_step: the reference's push_ptcls +
     search_mesh, OpenMP stand-ins, carried-over element ids aliased in place) and the oracle port

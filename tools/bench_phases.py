@@ -123,7 +123,10 @@ def c4(pp, wl, torch, steps, nptcls, plate_n, kind):
     m = host_mesh(pp, 2, plate_n)
     gm = pp.Mesh(2, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
     members = [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float64, 3)]
-    ps = pp.ParticleStructure(kind, members, wl.even_ppe(m.nelems, nptcls))
+    # the reference's own load (pseudoXGCm.cpp:167-222, pinned against its compiled source): a normal
+    # number of particles per triangle, the rounding shortfall in the last one
+    ppe, _ = wl.xgc_source_elements(m.class_id, np.zeros(m.nelems, np.int32), 0, 141, nptcls)
+    ps = pp.ParticleStructure(kind, members, ppe)
     cap = ps.capacity
     lay = ps.layout()
     se = pp.api._tensor_from_ptr(lay.slot_elem, (cap,), torch.int32, ps).long().clamp(0, m.nelems - 1)
