@@ -280,7 +280,7 @@ def main():
         iparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(tmp, "ref_xgcm_init.inc"), "w") as fh:
         fh.write("\n".join(iparts))
-    cmd = ["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
+    cmd = ["g++", "-O3", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function",
            "-Wno-deprecated-declarations", "-I", os.path.join(HERE, "ref_shim"), "-I", tmp,
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
            os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
