@@ -137,6 +137,16 @@ pp_status pp_host_picpart_tags(int32_t dim, int32_t nverts, int32_t nelems,
                                int32_t rank, int32_t buffer_method, int32_t safe_method,
                                int32_t buffer_layers, int32_t safe_layers, int32_t* safe_out,
                                int32_t* has_part_out);
+/* The same with the BFS bridged through any entity dimension (pumipic::Input::bridge_dim,
+ * pumipic_input.hpp; part_construct.cpp:424 ask_up(bridge_dim, dim)): the caller hands
+ * elem2bridges[nelems*bridges_per_elem] = the elements' entities of that dimension (vertices,
+ * edges or sides; nbridges of them in the mesh). */
+pp_status pp_host_picpart_tags_bridged(int32_t nbridges, int32_t nelems, int32_t bridges_per_elem,
+                                       const int32_t* elem2bridges, const int32_t* owner,
+                                       int32_t nranks, int32_t rank, int32_t buffer_method,
+                                       int32_t safe_method, int32_t buffer_layers,
+                                       int32_t safe_layers, int32_t* safe_out,
+                                       int32_t* has_part_out);
 /* The sub-mesh of a partially buffered PICpart (constructPICPart, part_construct.cpp:116-262):
  * elements whose owner's core is buffered here (has_part[owner] != 0, from pp_host_picpart_tags)
  * and their vertices, both keeping their relative order in the full mesh (:182-195).
@@ -214,6 +224,13 @@ pp_status pp_host_picpart_build(const pp_host_mesh* full, const int32_t* elem_ow
                                 int32_t nranks, int32_t rank, int32_t buffer_method,
                                 int32_t safe_method, int32_t buffer_layers, int32_t safe_layers,
                                 pp_host_picpart** out);
+/* The same with Input::bridge_dim (0 <= bridge_dim < dim; 0 = vertices is Input's default and what
+ * pp_host_picpart_build uses; test/test_revClass.cpp sets dim-1). */
+pp_status pp_host_picpart_build_bridged(const pp_host_mesh* full, const int32_t* elem_owner,
+                                        int32_t nranks, int32_t rank, int32_t buffer_method,
+                                        int32_t safe_method, int32_t buffer_layers,
+                                        int32_t safe_layers, int32_t bridge_dim,
+                                        pp_host_picpart** out);
 void pp_host_picpart_destroy(pp_host_picpart* pp);
 /* The PICpart's own mesh (Mesh::mesh()), with the tags the reference puts on it: "ownership"
  * (entOwners), "gids" (globalIds), "rank_lids" (rankLocalIndex), "global" (index in the full

@@ -120,6 +120,18 @@ XGCINIT_FUNCTIONS = [
     ("test/pseudoXGCm.cpp", r"int setSourceElements\(p::Mesh& picparts", 0),
     ("test/pseudoXGCm.cpp", r"void setInitialPtclCoords\(p::Mesh& picparts", 0),
 ]
+# src/pumipic_part_construct.cpp: the set-up kernels of PICpart construction (ref_shim/ref_picpart.cpp);
+# index 1 = the definition (index 0 is the forward declaration at the top of the file)
+PICPART_FUNCTIONS = [
+    ("src/pumipic_part_construct.cpp", r"Omega_h::LOs defineOwners\(Omega_h::Mesh& m", 1),
+    ("src/pumipic_part_construct.cpp", r"Omega_h::LOs calculateOwnerOffset\(Omega_h::LOs owner", 1),
+    ("src/pumipic_part_construct.cpp", r"struct GlobalNumberer \{", 0),
+    ("src/pumipic_part_construct.cpp", r"Omega_h::LOs createGlobalNumbering\(Omega_h::LOs owner", 1),
+    ("src/pumipic_part_construct.cpp", r"Omega_h::LOs rankLidNumbering\(Omega_h::LOs owner", 1),
+    ("src/pumipic_part_construct.cpp", r"void BFS\(int nents", 0),
+    ("src/pumipic_part_construct.cpp", r"void bfsBufferLayers\(Omega_h::Mesh& mesh", 1),
+    ("src/pumipic_part_construct.cpp", r"void bfsSafeInward\(Omega_h::Mesh& mesh", 1),
+]
 # particle_structs/src/scs/SCS_buildFns.h: the Sell-C-sigma geometry (ref_shim/ref_scs.cpp)
 SCS_FUNCTIONS = [
     ("particle_structs/src/scs/SCS_buildFns.h", r"int SellCSigma<DataTypes, MemSpace>::chooseChunkHeight\(", 0),
@@ -265,6 +277,13 @@ def main():
         pparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
     with open(os.path.join(tmp, "ref_ppas.inc"), "w") as fh:
         fh.write("\n".join(pparts))
+    cparts = [parts[0]]
+    for f, pat, which in PICPART_FUNCTIONS:
+        text = cache.setdefault(f, open(os.path.join(REF, f)).read())
+        body, l0, l1 = extract(text, pat, which)
+        cparts.append("// %s:%d-%d\n%s\n" % (f, l0, l1, body))
+    with open(os.path.join(tmp, "ref_picpart.inc"), "w") as fh:
+        fh.write("\n".join(cparts))
     iparts = [parts[0]]
     xgcm = open(os.path.join(REF, "test/pseudoXGCm.cpp")).read()
     xtypes = open(os.path.join(REF, "test/pseudoXGCmTypes.hpp")).read()
@@ -285,7 +304,7 @@ def main():
            os.path.join(HERE, "ref_shim", "ref_primitives.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm.cpp"),
            os.path.join(HERE, "ref_shim", "ref_testadj.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
            os.path.join(HERE, "ref_shim", "ref_scs.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm_init.cpp"),
-           "-o", LIB]
+           os.path.join(HERE, "ref_shim", "ref_picpart.cpp"), "-o", LIB]
     try:
         subprocess.check_call(cmd)
     finally:

@@ -172,8 +172,12 @@ class Mesh {
   int nverts() const { return nverts_; }
   Adj ask_down(int, int low) const { Adj a; a.ab2b = low == 0 ? elem_verts : down; return a; }
   Adj get_adj(int from, int to) const { return ask_down(from, to); }
+  int nents_[4] = {-1, -1, -1, -1};
+  int nents(int d) const { return nents_[d]; }
+  std::shared_ptr<std::map<int, Adj>> ups = std::make_shared<std::map<int, Adj>>();   // ask_up(low, dim) per low
   Adj ask_up(int low, int) const {
     Adj a;
+    if (ups->count(low)) return ups->at(low);
     if (low == 0) { a.a2ab = v2e_off; a.ab2b = v2e_vals; } else { a.a2ab = up_off; a.ab2b = up_vals; }
     return a;
   }

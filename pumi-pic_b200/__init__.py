@@ -10,7 +10,7 @@ from .capi import PumipicError, lib                  # noqa: F401
 from .api import (Mesh, ParticleStructure, SearchResult, search_mesh, push_constant,  # noqa: F401
                   push_direction, update_positions, push_direction_search, host_kuhn_cube,
                   host_plate, host_derive_sides, push_from, elliptical_setup, elliptical_push,
-                  set_unsafe_procs, gyro_ring_map, gyro_scatter, gyro_interleave, Comm, migrate, host_picpart_tags,
+                  set_unsafe_procs, gyro_ring_map, gyro_scatter, gyro_interleave, Comm, migrate, host_picpart_tags, host_picpart_tags_bridged,
                   host_entity_owners, push_direction_search_host, push_boris, gather_tet_field, gather_grid2d,
                   gather_grid2d_vector, gather_grid3d, host_picpart_extract, CommPlan, HostMesh, Picpart, host_read_partition,
                   FULL, BFS, MINIMUM, NONE, Balancer, host_lb_plan, trace_particle_through_mesh)

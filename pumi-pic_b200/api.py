@@ -76,6 +76,20 @@ def host_picpart_tags(dim, nverts, elem2verts, owner, nranks, rank, buffer_metho
     return safe, part
 
 
+def host_picpart_tags_bridged(nbridges, elem2bridges, owner, nranks, rank, buffer_method=FULL,
+                              safe_method=BFS, buffer_layers=3, safe_layers=1):
+    """Input::bridge_dim: elem2bridges [nelems, k] = the elements' entities of the bridge dimension."""
+    eb = np.ascontiguousarray(elem2bridges, np.int32)
+    ow = np.ascontiguousarray(owner, np.int32)
+    safe = np.empty(eb.shape[0], np.int32)
+    part = np.empty(nranks, np.int32)
+    check(lib().pp_host_picpart_tags_bridged(nbridges, eb.shape[0], eb.shape[1], eb.ctypes.data_as(capi.c_i32p),
+                                             ow.ctypes.data_as(capi.c_i32p), nranks, rank, buffer_method,
+                                             safe_method, buffer_layers, safe_layers,
+                                             safe.ctypes.data_as(capi.c_i32p), part.ctypes.data_as(capi.c_i32p)))
+    return safe, part
+
+
 def host_entity_owners(nents, elem2ents, elem_owner, nranks):
     ee = np.ascontiguousarray(elem2ents, np.int32)
     ow = np.ascontiguousarray(elem_owner, np.int32)
@@ -227,13 +241,13 @@ class Picpart:
 
     @classmethod
     def build(cls, full, elem_owner, nranks, rank, buffer_method=BFS, safe_method=BFS,
-              buffer_layers=-1, safe_layers=-1):
+              buffer_layers=-1, safe_layers=-1, bridge_dim=0):
         ow = np.ascontiguousarray(elem_owner, np.int32)
         assert ow.shape[0] == full.nents(full.dim)
         h = C.c_void_p()
-        check(lib().pp_host_picpart_build(full.h, ow.ctypes.data_as(capi.c_i32p), nranks, rank,
-                                          buffer_method, safe_method, buffer_layers, safe_layers,
-                                          C.byref(h)))
+        check(lib().pp_host_picpart_build_bridged(full.h, ow.ctypes.data_as(capi.c_i32p), nranks, rank,
+                                                  buffer_method, safe_method, buffer_layers, safe_layers,
+                                                  bridge_dim, C.byref(h)))
         return cls(h)
 
     @classmethod

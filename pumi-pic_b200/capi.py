@@ -115,6 +115,9 @@ PROTOTYPES = {
     "pp_host_picpart_tags": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        c_i32p, c_i32p]),
+    "pp_host_picpart_tags_bridged": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                               c_i32p, c_i32p]),
     "pp_host_entity_owners": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32,
                                         c_i32p]),
     "pp_ps_config_default": (None, [C.POINTER(PsConfig), C.c_int32]),
@@ -232,6 +235,9 @@ PROTOTYPES = {
     "pp_host_read_partition": (C.c_int, [C.c_char_p, C.c_int32, c_i32p, c_i32p]),
     "pp_host_picpart_build": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pp_host_picpart_build_bridged": (C.c_int, [C.c_void_p, c_i32p, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                C.POINTER(C.c_void_p)]),
     "pp_host_picpart_destroy": (None, [C.c_void_p]),
     "pp_host_picpart_mesh": (C.c_void_p, [C.c_void_p]),
     "pp_host_picpart_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(PicpartDim)]),

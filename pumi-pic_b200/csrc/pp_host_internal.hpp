@@ -87,10 +87,12 @@ struct Writer {
 bool read_osh(const char* path, HMesh& m);
 bool write_osh(const HMesh& m, const char* path);
 
-struct Up {  // ask_up(0, dim): vertex -> elements, ascending
+struct Up {  // ask_up(bridge_dim, dim): bridge entity -> elements, ascending
   std::vector<int> off, val;
 };
 Up build_up(int nverts, int nelems, int nv, const int32_t* ev);
+// element -> entities of dimension bridge_dim (vertices, edges or sides), `per_elem` each
+bool elem_bridges(const HMesh& m, int bridge_dim, std::vector<int32_t>& out, int& per_elem);
 void picpart_tags(const Up& u, int nverts, int nelems, const int32_t* owner, int nranks, int rank,
                   int buffer_method, int safe_method, int buffer_layers, int safe_layers,
                   std::vector<int>& is_safe, std::vector<int>& has_part);

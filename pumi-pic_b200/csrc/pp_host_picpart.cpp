@@ -1,7 +1,8 @@
 // pp_host_picpart.cpp -- host-side PICpart tags: which elements are safe on this rank, which
 // other parts are buffered, and entity ownership.  Follows src/pumipic_part_construct.cpp:
 // Mesh::Mesh(Input&) :73-114, bfsBufferLayers :409-441, bfsSafeInward :443-468 (BFS through
-// vertex-bridged adjacency, bridge_dim = 0) and defineOwners :304-323.  Setup-time code that the
+// the elements around every entity of Input::bridge_dim; 0 = vertices is the default) and
+// defineOwners :304-323.  Setup-time code that the
 // reference also runs on the host side of Omega_h; sub-mesh extraction for non-full PICparts is a
 // "next" row.
 #include <stdint.h>
@@ -29,6 +30,43 @@ Up build_up(int nverts, int nelems, int nv, const int32_t* ev) {
       u.val[u.off[v] + fill[v]++] = e;
     }
   return u;
+}
+// ask_down(dim, bridge_dim) as a flat list: vertices and sides are stored, the edges of a tet are
+// the union of the edges of its faces (order inside an element is irrelevant to the BFS)
+bool elem_bridges(const HMesh& m, int bridge_dim, std::vector<int32_t>& out, int& per_elem) {
+  const int dim = m.dim;
+  if (bridge_dim < 0 || bridge_dim >= dim) return false;
+  const int ne = m.nents[dim];
+  if (bridge_dim == 0) {
+    per_elem = dim + 1;
+    out = m.verts[dim];
+    return true;
+  }
+  if (bridge_dim == dim - 1) {
+    per_elem = dim + 1;
+    out = m.down[dim];
+    return true;
+  }
+  per_elem = 6;   // edges of a tet
+  out.assign((size_t)ne * 6, -1);
+  for (int e = 0; e < ne; ++e) {
+    int n = 0;
+    int32_t* mine = out.data() + (size_t)e * 6;
+    for (int f = 0; f < 4; ++f) {
+      const int face = m.down[3][(size_t)e * 4 + f];
+      for (int k = 0; k < 3; ++k) {
+        const int edge = m.down[2][(size_t)face * 3 + k];
+        bool seen = false;
+        for (int j = 0; j < n; ++j) seen = seen || mine[j] == edge;
+        if (!seen) {
+          if (n == 6) return false;
+          mine[n++] = edge;
+        }
+      }
+    }
+    if (n != 6) return false;
+  }
+  return true;
 }
 namespace {
 // one BFS layer (part_construct.cpp:387-405): every element around a bridge that touches a
@@ -101,6 +139,37 @@ extern "C" pp_status pp_host_picpart_tags(int32_t dim, int32_t nverts, int32_t n
                     buffer_layers, safe_layers, is_safe, has_part);
   memcpy(safe_out, is_safe.data(), sizeof(int32_t) * nelems);
   memcpy(has_part_out, has_part.data(), sizeof(int32_t) * nranks);
+  return PP_OK;
+}
+
+extern "C" pp_status pp_host_picpart_tags_bridged(int32_t nbridges, int32_t nelems,
+                                                  int32_t bridges_per_elem,
+                                                  const int32_t* elem2bridges, const int32_t* owner,
+                                                  int32_t nranks, int32_t rank,
+                                                  int32_t buffer_method, int32_t safe_method,
+                                                  int32_t buffer_layers, int32_t safe_layers,
+                                                  int32_t* safe_out, int32_t* has_part_out) {
+  if (nbridges < 0 || nelems < 0 || bridges_per_elem < 1 || !elem2bridges || !owner || !safe_out ||
+      !has_part_out || nranks < 1 || rank < 0 || rank >= nranks) {
+    pp_set_error("pp_host_picpart_tags_bridged: bad argument");
+    return PP_ERR_INVALID;
+  }
+  for (int64_t i = 0; i < (int64_t)nelems * bridges_per_elem; ++i)
+    if (elem2bridges[i] < 0 || elem2bridges[i] >= nbridges) {
+      pp_set_error("pp_host_picpart_tags_bridged: bridge entity %d outside [0,%d)", elem2bridges[i], nbridges);
+      return PP_ERR_INVALID;
+    }
+  for (int e = 0; e < nelems; ++e)
+    if (owner[e] < 0 || owner[e] >= nranks) {
+      pp_set_error("pp_host_picpart_tags_bridged: element %d has owner %d outside [0,%d)", e, owner[e], nranks);
+      return PP_ERR_INVALID;
+    }
+  const pph::Up u = pph::build_up(nbridges, nelems, bridges_per_elem, elem2bridges);
+  std::vector<int> is_safe, has_part;
+  pph::picpart_tags(u, nbridges, nelems, owner, nranks, rank, buffer_method, safe_method,
+                    buffer_layers, safe_layers, is_safe, has_part);
+  if (nelems) memcpy(safe_out, is_safe.data(), sizeof(int32_t) * (size_t)nelems);
+  memcpy(has_part_out, has_part.data(), sizeof(int32_t) * (size_t)nranks);
   return PP_OK;
 }
 

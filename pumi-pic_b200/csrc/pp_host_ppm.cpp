@@ -75,8 +75,8 @@ void kept_entities(const World& w, int s, std::vector<uint8_t> keep[4]) {
   }
 }
 
-void build_world(const HMesh& full, const int32_t* elem_owner, int nranks, int bm, int sm, int bl,
-                 int sl, World& w) {
+bool build_world(const HMesh& full, const int32_t* elem_owner, int nranks, int bm, int sm, int bl,
+                 int sl, int bridge_dim, World& w) {
   const int dim = full.dim;
   w.dim = dim;
   w.nranks = nranks;
@@ -108,15 +108,20 @@ void build_world(const HMesh& full, const int32_t* elem_owner, int nranks, int b
     }
   }
   // safe zone and buffered parts of every rank
-  const Up up = build_up(full.nents[0], full.nents[dim], dim + 1, full.verts[dim].data());
+  std::vector<int32_t> bridges;
+  int per_elem = 0;
+  if (!elem_bridges(full, bridge_dim, bridges, per_elem)) return false;
+  const int nbridges = full.nents[bridge_dim];
+  const Up up = build_up(nbridges, full.nents[dim], per_elem, bridges.data());
   w.safe.resize((size_t)nranks);
   w.has_part.resize((size_t)nranks);
   for (int s = 0; s < nranks; ++s) {
     std::vector<int> is_safe;
-    picpart_tags(up, full.nents[0], full.nents[dim], elem_owner, nranks, s, bm, sm, bl, sl, is_safe,
+    picpart_tags(up, nbridges, full.nents[dim], elem_owner, nranks, s, bm, sm, bl, sl, is_safe,
                  w.has_part[(size_t)s]);
     w.safe[(size_t)s].assign(is_safe.begin(), is_safe.end());
   }
+  return true;
 }
 
 // bufferedRanks(dim) of rank s: the other parts with elements in its PICpart
@@ -326,11 +331,14 @@ void gather_tag(HMesh& part, int d, const char* name, int type, const std::vecto
 }
 
 bool build_picpart(const HMesh& full, const int32_t* elem_owner, int nranks, int rank, int bm,
-                   int sm, int bl, int sl, Picpart& pp) {
+                   int sm, int bl, int sl, int bridge_dim, Picpart& pp) {
   enum { FULL = 0 };
   const int dim = full.dim;
   World w;
-  build_world(full, elem_owner, nranks, bm, sm, bl, sl, w);
+  if (!build_world(full, elem_owner, nranks, bm, sm, bl, sl, bridge_dim, w)) {
+    pp_set_error("pp_host_picpart_build: bridge dimension %d is not below the mesh dimension %d", bridge_dim, dim);
+    return false;
+  }
   pp.nranks = nranks;
   pp.rank = rank;
   pp.is_full_mesh = bm == FULL;
@@ -553,9 +561,19 @@ extern "C" pp_status pp_host_picpart_build(const pp_host_mesh* full, const int32
                                            int32_t nranks, int32_t rank, int32_t buffer_method,
                                            int32_t safe_method, int32_t buffer_layers,
                                            int32_t safe_layers, pp_host_picpart** out) {
+  return pp_host_picpart_build_bridged(full, elem_owner, nranks, rank, buffer_method, safe_method,
+                                       buffer_layers, safe_layers, 0, out);
+}
+
+extern "C" pp_status pp_host_picpart_build_bridged(const pp_host_mesh* full, const int32_t* elem_owner,
+                                                   int32_t nranks, int32_t rank,
+                                                   int32_t buffer_method, int32_t safe_method,
+                                                   int32_t buffer_layers, int32_t safe_layers,
+                                                   int32_t bridge_dim, pp_host_picpart** out) {
   const HMesh* f = reinterpret_cast<const HMesh*>(full);
   if (!f || !elem_owner || !out || nranks < 1 || rank < 0 || rank >= nranks || buffer_method < 0 ||
-      buffer_method > 3 || safe_method < 0 || safe_method > 3 || !(f->dim == 2 || f->dim == 3)) {
+      buffer_method > 3 || safe_method < 0 || safe_method > 3 || !(f->dim == 2 || f->dim == 3) ||
+      bridge_dim < 0 || bridge_dim >= f->dim) {
     pp_set_error("pp_host_picpart_build: bad argument");
     return PP_ERR_INVALID;
   }
@@ -575,7 +593,7 @@ extern "C" pp_status pp_host_picpart_build(const pp_host_mesh* full, const int32
   if (safe_layers < 0) safe_layers = 1;
   Picpart* pp = new Picpart();
   if (!pph::build_picpart(*f, elem_owner, nranks, rank, buffer_method, safe_method, buffer_layers,
-                          safe_layers, *pp)) {
+                          safe_layers, bridge_dim, *pp)) {
     delete pp;
     return PP_ERR_INVALID;
   }

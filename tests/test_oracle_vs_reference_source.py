@@ -683,3 +683,103 @@ def test_scs_geometry_of_the_reference_matches_the_measured_run(ref):
         nsl = sum(-(-int(x) // 8) for x in w)
         assert lay["nslices"] == nsl and lay["capacity"] == 4 * int(w.sum()) == lay["offsets"][-1]
         assert lay["num_empty"] == 10 + 2                       # empty elements + the 2 padding rows
+
+
+def _up_csr(nents, e2k):
+    """ask_up(k, dim): entity -> elements, ascending element ids."""
+    ne, per = e2k.shape
+    flat = e2k.ravel()
+    order = np.argsort(flat, kind="stable")
+    off = np.zeros(nents + 1, np.int32)
+    np.cumsum(np.bincount(flat, minlength=nents), out=off[1:])
+    return off, (order // per).astype(np.int32)
+
+
+def _elem_to(full, k):
+    """elements -> their entities of dimension k"""
+    dim = full.dim
+    if k == 0:
+        return np.ascontiguousarray(full.ent2verts(dim), np.int32)
+    if k == dim - 1:
+        return np.ascontiguousarray(full.down(dim), np.int32)
+    edges = full.down(2)[full.down(3)].reshape(full.nents(3), 12)      # every edge of a tet twice
+    return np.ascontiguousarray(np.sort(edges, axis=1)[:, ::2], np.int32)
+
+
+@pytest.mark.parametrize("case", ["plate2d", "kuhn3d"])
+def test_picpart_setup_kernels_equal_the_reference(ref, case):
+    """the set-up kernels of PICpart construction -- BFS / bfsBufferLayers / bfsSafeInward
+    (src/pumipic_part_construct.cpp:387-468, every Input::bridge_dim), defineOwners :304-323,
+    createGlobalNumbering :366-374, rankLidNumbering :376-385 -- compiled unmodified, against the
+    product's host code (pp_host_picpart_tags_bridged, pp_host_picpart_build_bridged)."""
+    import importlib
+    P = importlib.import_module("pumi-pic_b200")
+    if case == "plate2d":
+        coords, elems = P.host_plate(12)
+        dim, nranks = 2, 4
+    else:
+        coords, elems = P.host_kuhn_cube(5)
+        dim, nranks = 3, 5
+    full = P.HostMesh.from_elems(dim, coords, elems)
+    ne = full.nents(dim)
+    cx = coords[elems].mean(axis=1)
+    rng = np.random.default_rng(8)
+    slabs = np.minimum((cx[:, 0] / cx[:, 0].max() * nranks).astype(np.int32), nranks - 1)
+    blocks = (np.minimum((cx[:, 0] / cx[:, 0].max() * 2).astype(np.int32), 1) * 2
+              + np.minimum((cx[:, 1] / cx[:, 1].max() * 2).astype(np.int32), 1)).astype(np.int32) % nranks
+    noisy = np.where(rng.random(ne) < 0.03, rng.integers(0, nranks, ne), slabs).astype(np.int32)
+    FULL, BFS, MINIMUM, NONE = 0, 1, 2, 3
+    combos = [(BFS, BFS, 3, 1), (BFS, BFS, 1, 2), (BFS, FULL, 2, 1), (BFS, FULL, 1, 3), (MINIMUM, MINIMUM, 3, 1),
+              (FULL, BFS, 3, 2), (FULL, FULL, 3, 1), (NONE, NONE, 3, 1), (BFS, MINIMUM, 2, 2), (MINIMUM, BFS, 1, 1),
+              (BFS, NONE, 2, 1), (FULL, MINIMUM, 0, 0), (BFS, BFS, 0, 0)]
+    for bridge_dim in range(dim):
+        e2b = _elem_to(full, bridge_dim)
+        nb = full.nents(bridge_dim)
+        off, val = _up_csr(nb, e2b)
+        for owner in (slabs, blocks, noisy):
+            if len(np.unique(owner)) < nranks:
+                continue
+            for bm, sm, bl, sl in combos:
+                # the Input constructor's adjustments (pumipic_input.cpp:96-110), applied for the reference call
+                rbm = MINIMUM if bm == NONE else bm
+                rbl = 0 if rbm == MINIMUM else bl
+                rsl = 0 if sm == MINIMUM else sl
+                for rank in range(nranks):
+                    safe_r = np.full(ne, -1, np.int32)
+                    part_r = np.full(nranks, -1, np.int32)
+                    ref.ref_picpart_tags(dim, bridge_dim, nb, _i(off), _i(val), ne, _i(owner), nranks, rank, rbm, sm,
+                                         rbl, rsl, safe_r.ctypes.data_as(ip), part_r.ctypes.data_as(ip))
+                    safe, part = P.host_picpart_tags_bridged(nb, e2b, owner, nranks, rank, bm, sm, bl, sl)
+                    assert np.array_equal(safe != 0, safe_r != 0), (bridge_dim, bm, sm, bl, sl, rank)
+                    assert np.array_equal(part != 0, part_r != 0), (bridge_dim, bm, sm, bl, sl, rank)
+                    if bridge_dim == 0:          # the vertex-bridged entry point is the same function
+                        s0, p0 = P.host_picpart_tags(dim, full.nents(0), elems, owner, nranks, rank, bm, sm, bl, sl)
+                        assert np.array_equal(s0, safe) and np.array_equal(p0, part)
+        # the PICpart record built with this bridge dimension carries the same safe zone and parts
+        for rank in (0, nranks - 1):
+            pic = P.Picpart.build(full, slabs, nranks, rank, BFS, BFS, 2, 1, bridge_dim=bridge_dim)
+            safe, part = P.host_picpart_tags_bridged(nb, e2b, slabs, nranks, rank, BFS, BFS, 2, 1)
+            info = pic.dim_info(dim)
+            l2g = info["ent_l2g"]
+            assert np.array_equal(l2g, np.flatnonzero(part[slabs] != 0))
+            assert np.array_equal(pic.mesh().tag(dim, "safe") != 0, safe[l2g] != 0)
+    # ownership and numbering of every dimension (a fully buffered PICpart keeps the full mesh's order)
+    pic = P.Picpart.build(full, noisy, nranks, 0, FULL, FULL, 3, 1)
+    m = pic.mesh()
+    for k in range(dim + 1):
+        n = full.nents(k)
+        assert m.nents(k) == n
+        if k < dim:
+            off, val = _up_csr(n, _elem_to(full, k))
+            own_r = np.full(n, -1, np.int32)
+            ref.ref_define_owners(dim, k, n, _i(off), _i(val), ne, _i(noisy), nranks, own_r.ctypes.data_as(ip))
+        else:
+            own_r = noisy
+        assert np.array_equal(m.tag(k, "ownership"), own_r)
+        offs = np.zeros(nranks + 1, np.int32)
+        gids = np.zeros(n, np.int64)
+        lids = np.zeros(n, np.int32)
+        ref.ref_global_numbering(n, _i(own_r), nranks, offs.ctypes.data_as(ip),
+                                 gids.ctypes.data_as(C.POINTER(C.c_longlong)), lids.ctypes.data_as(ip))
+        assert np.array_equal(m.tag(k, "gids"), gids) and np.array_equal(m.tag(k, "rank_lids"), lids)
+        assert np.array_equal(pic.dim_info(k)["offset_ents_per_rank"], offs)
