@@ -461,9 +461,17 @@ class Mesh {
   // this rank as pp_host_picpart_build / pp_host_picpart_read made it.  The record stays owned by
   // the caller and must outlive the Mesh.  With a communicator of more than one rank the comm-array
   // plans of setupComm (pumipic_comm.cpp:12-184) are built per entity dimension on first use.
-  Mesh(const pp_host_picpart* record, pp_comm* comm) : dim_(0), comm_(comm), record_(record) {
+  Mesh(const pp_host_picpart* record, pp_comm* comm) : dim_(0), comm_(nullptr) { adopt(record, comm, false); }
+  // an empty Mesh for pumipic::read (pumipic_mesh.hpp:150-151) to fill
+  Mesh() : dim_(0), comm_(nullptr) {}
+  // make this Mesh the PICpart `record`; with own = true the record is destroyed with the Mesh
+  void adopt(const pp_host_picpart* record, pp_comm* comm, bool own) {
+    if (h_ || record_) throw std::runtime_error("Mesh: already holds a mesh");
     const pp_host_mesh* m = pp_host_picpart_mesh(record);
     if (!m) throw std::runtime_error("Mesh: the PICpart record has no mesh");
+    record_ = record;
+    owns_record_ = own;
+    comm_ = comm;
     dim_ = pp_host_mesh_dim(m);
     for (int d = 0; d <= dim_; ++d) nents_[d] = pp_host_mesh_nents(m, d);
     pp_mesh_desc d;
@@ -481,6 +489,7 @@ class Mesh {
   ~Mesh() {
     for (int d = 0; d < 4; ++d) if (plan_[d]) pp_comm_plan_destroy(plan_[d]);
     if (h_) pp_mesh_destroy(h_);
+    if (owns_record_ && record_) pp_host_picpart_destroy(const_cast<pp_host_picpart*>(record_));
   }
   Mesh(const Mesh&) = delete;
   Mesh& operator=(const Mesh&) = delete;
@@ -578,9 +587,30 @@ class Mesh {
   pp_mesh* h_ = nullptr;
   pp_comm* comm_;
   const pp_host_picpart* record_ = nullptr;
+  bool owns_record_ = false;
   pp_comm_plan* plan_[4] = {nullptr, nullptr, nullptr, nullptr};
   ParticleBalancer* balancer_ = nullptr;
 };
+
+// pumipic::write(picparts, prefix) / pumipic::read(lib, comm, prefix, &mesh) (pumipic_mesh.hpp:147-151,
+// src/pumipic_file.cpp:45-205): <prefix>_<nranks>.ppm/ holding one .osh and one .ppm per rank.  The
+// communicator gives the rank and the rank count (null = one rank); `mesh` must be empty and owns the
+// record it reads.
+inline void write(Mesh& picparts, const char* prefix) {
+  if (!picparts.record()) throw std::runtime_error("write: the Mesh was not built from a PICpart record");
+  pp_check(pp_host_picpart_write(picparts.record(), prefix), "write");
+}
+inline void read(pp_comm* comm, const char* prefix, Mesh* mesh) {
+  const int nranks = comm ? pp_comm_size(comm) : 1, rank = comm ? pp_comm_rank(comm) : 0;
+  pp_host_picpart* rec = nullptr;
+  pp_check(pp_host_picpart_read(prefix, nranks, rank, &rec), "read");
+  try {
+    mesh->adopt(rec, comm, true);
+  } catch (...) {
+    pp_host_picpart_destroy(rec);
+    throw;
+  }
+}
 
 // ---------------------------------------------------------------- search
 namespace detail {

@@ -66,6 +66,30 @@ int main() {
   CHECK(ncore == ne / NR && nsafe > ncore && nsafe < nel && gid_ok && perm_ok);
   CHECK((int)picparts.entOwners(0).size() == picparts.nents(0));
 
+  // ---------------------------------------------------------------- pumipic::write / pumipic::read
+  // (pumipic_mesh.hpp:147-151; test/test_file.cpp): every rank's PICpart written under one prefix,
+  // rank 0's read back into an empty Mesh that owns its record
+  {
+    char tmpl[] = "/tmp/pp_mirror_XXXXXX";
+    CHECK(mkdtemp(tmpl) != nullptr);
+    const std::string prefix = std::string(tmpl) + "/plate";
+    p::write(picparts, prefix.c_str());
+    for (int r = 1; r < NR; ++r) {
+      pp_host_picpart* other = nullptr;
+      p::pp_check(pp_host_picpart_build(full, owner.data(), NR, r, 1, 1, -1, 2, &other), "picpart_build");
+      p::pp_check(pp_host_picpart_write(other, prefix.c_str()), "picpart_write");
+      pp_host_picpart_destroy(other);
+    }
+    pp_host_picpart* again = nullptr;
+    p::pp_check(pp_host_picpart_read(prefix.c_str(), NR, 0, &again), "picpart_read");
+    p::Mesh back;
+    back.adopt(again, nullptr, true);
+    CHECK(back.dim() == 2 && back.nelems() == nel && back.nents(0) == picparts.nents(0) && !back.isFullMesh());
+    CHECK(back.safeTag().toHost() == safe && back.entOwners(2).toHost() == own);
+    CHECK(back.globalIds(2).toHost() == gids && back.commArrayIndex(2).toHost() == cai);
+    CHECK(back.bufferedRanks(2) == picparts.bufferedRanks(2));
+  }
+
   // ---------------------------------------------------------------- structure with initial data (getMemberView)
   const int ppe_v = 20;
   std::vector<int> ppe(nel), pel;
