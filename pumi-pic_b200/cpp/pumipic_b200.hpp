@@ -32,6 +32,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cctype>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -435,6 +436,88 @@ void parallel_for(ParticleStructure<DataTypes>* ps, FunctionType& fn, std::strin
 }
 #endif
 
+// ---------------------------------------------------------------- Input (pumipic_input.hpp:8-77)
+// What pumipic::Mesh(Input&) is built from: the full mesh (the host-side container that stands for
+// Omega_h::Mesh on the set-up side), who owns every element, and how buffers and safe zone are made.
+class Mesh;
+class Input {
+ public:
+  enum Method { INVALID = -1, FULL, BFS, MINIMUM, NONE };   // pumipic_input.hpp:33-39
+  enum Ownership { PARTITION, CLASSIFICATION };             // :42-45
+  // partition file: `.ptn` one owner per element, `.cpn` one owner per class id (pumipic_input.cpp:19-89;
+  // the file is read when the communicator has more than one rank, like the reference).  After a
+  // `.cpn` file getPartition() holds the owners already resolved per element.
+  Input(const pp_host_mesh* mesh, const char* partition_filename, Method bufferMethod_, Method safeMethod_,
+        pp_comm* comm_ = nullptr)
+      : m(mesh), ownership_rule(PARTITION), comm(comm_) {
+    const int dim = pp_host_mesh_dim(mesh), ne = pp_host_mesh_nents(mesh, dim);
+    partition.assign((size_t)ne, 0);
+    if (comm && pp_comm_size(comm) > 1) {
+      const std::string f(partition_filename);
+      const size_t dot = f.rfind('.');
+      if (dot == std::string::npos) throw std::runtime_error("Filename has no extension");
+      const bool cpn = f.substr(dot + 1) == "cpn";
+      pp_host_tag t;
+      const int32_t* cls = nullptr;
+      if (cpn && pp_host_mesh_find_tag(mesh, dim, "class_id", &t) == PP_OK) cls = static_cast<const int32_t*>(t.data);
+      pp_check(pp_host_read_partition(partition_filename, ne, cls, partition.data()), "Input");
+      if (cpn) ownership_rule = CLASSIFICATION;
+      resolved = true;
+    }
+    init(bufferMethod_, safeMethod_);
+  }
+  Input(const pp_host_mesh* mesh, Ownership rule, const std::vector<lid_t>& partition_vector, Method bufferMethod_,
+        Method safeMethod_, pp_comm* comm_ = nullptr)
+      : m(mesh), ownership_rule(rule), partition(partition_vector), comm(comm_) {
+    init(bufferMethod_, safeMethod_);
+  }
+  void printMethod() const {
+    static const char* names[] = {"INVALID", "FULL", "BFS", "MINIMUM", "NONE"};
+    std::printf("pumipic buffer method %s\n", names[bufferMethod + 1]);
+    std::printf("pumipic safe method %s\n", names[safeMethod + 1]);
+  }
+  static Method getMethod(std::string s) {   // case-insensitive, pumipic_input.cpp:139-151
+    for (char& c : s) c = (char)std::toupper((unsigned char)c);
+    return s == "FULL" ? FULL : s == "BFS" ? BFS : s == "MINIMUM" ? MINIMUM : s == "NONE" ? NONE : INVALID;
+  }
+  Ownership getRule() const { return ownership_rule; }
+  const std::vector<lid_t>& getPartition() const { return partition; }
+  int bridge_dim;        // entity dimension the BFS goes through (defaults to 0)
+  int bufferBFSLayers;   // Method BFS: layers of the buffer (defaults to 3)
+  int safeBFSLayers;     // Method BFS: layers of the safe zone (defaults to 1)
+  friend class Mesh;
+
+ private:
+  void init(Method b, Method s) {            // pumipic_input.cpp:94-110
+    bufferMethod = b == NONE ? MINIMUM : b;
+    safeMethod = s;
+    bridge_dim = 0;
+    bufferBFSLayers = bufferMethod == MINIMUM ? 0 : 3;
+    safeBFSLayers = safeMethod == MINIMUM ? 0 : 1;
+  }
+  // owner of every element: the partition itself, or through the elements' class ids
+  // (setOwnerByClassification, part_construct.cpp:278-301)
+  std::vector<lid_t> elementOwners() const {
+    if (ownership_rule == PARTITION || resolved) return partition;
+    const int dim = pp_host_mesh_dim(m), ne = pp_host_mesh_nents(m, dim);
+    pp_host_tag t;
+    pp_check(pp_host_mesh_find_tag(m, dim, "class_id", &t), "Input: class_id tag");
+    const int32_t* cls = static_cast<const int32_t*>(t.data);
+    std::vector<lid_t> own((size_t)ne);
+    for (int e = 0; e < ne; ++e) {
+      if (cls[e] < 0 || cls[e] >= (int)partition.size()) throw std::runtime_error("Input: class id outside the partition vector");
+      own[(size_t)e] = partition[(size_t)cls[e]];
+    }
+    return own;
+  }
+  const pp_host_mesh* m;
+  Ownership ownership_rule;
+  std::vector<lid_t> partition;
+  bool resolved = false;
+  Method bufferMethod, safeMethod;
+  pp_comm* comm;
+};
+
 // ---------------------------------------------------------------- Mesh (PICpart handle)
 class ParticleBalancer;
 class Mesh {
@@ -464,13 +547,28 @@ class Mesh {
   Mesh(const pp_host_picpart* record, pp_comm* comm) : dim_(0), comm_(nullptr) { adopt(record, comm, false); }
   // an empty Mesh for pumipic::read (pumipic_mesh.hpp:150-151) to fill
   Mesh() : dim_(0), comm_(nullptr) {}
+  // Mesh(Input&) (part_construct.cpp:73-114): builds this rank's PICpart record and owns it
+  explicit Mesh(Input& in) : dim_(0), comm_(nullptr) {
+    build(in.m, in.elementOwners(), (int)in.bufferMethod, (int)in.safeMethod, in.bufferBFSLayers, in.safeBFSLayers,
+          in.bridge_dim, in.comm);
+  }
+  // Mesh(o::Mesh&, o::LOs owners) (:43-53): every PICpart is the full mesh and all of it is safe
+  Mesh(const pp_host_mesh* full, const std::vector<lid_t>& owners, pp_comm* comm) : dim_(0), comm_(nullptr) {
+    build(full, owners, (int)Input::FULL, (int)Input::FULL, 3, 1, 0, comm);
+  }
+  // Mesh(o::Mesh&, owners, ghost_layers, safe_layers) (:55-71): vertex-bridged BFS buffers and safe zone
+  Mesh(const pp_host_mesh* full, const std::vector<lid_t>& owners, int ghost_layers, int safe_layers, pp_comm* comm)
+      : dim_(0), comm_(nullptr) {
+    if (ghost_layers < safe_layers) throw std::runtime_error("Ghost layers must be >= safe layers");
+    build(full, owners, (int)Input::BFS, (int)Input::BFS, ghost_layers, safe_layers, 0, comm);
+  }
   // make this Mesh the PICpart `record`; with own = true the record is destroyed with the Mesh
   void adopt(const pp_host_picpart* record, pp_comm* comm, bool own) {
     if (h_ || record_) throw std::runtime_error("Mesh: already holds a mesh");
     const pp_host_mesh* m = pp_host_picpart_mesh(record);
     if (!m) throw std::runtime_error("Mesh: the PICpart record has no mesh");
     record_ = record;
-    owns_record_ = own;
+    owns_record_ = false;   // until everything below has worked: on failure the caller keeps the record
     comm_ = comm;
     dim_ = pp_host_mesh_dim(m);
     for (int d = 0; d <= dim_; ++d) nents_[d] = pp_host_mesh_nents(m, d);
@@ -482,9 +580,16 @@ class Mesh {
     d.side2verts = pp_host_mesh_ent2verts(m, dim_ - 1);
     d.elem_class = hostTag<int32_t>(dim_, "class_id", false);
     d.memspace = PP_HOST;
-    pp_check(pp_mesh_create(&d, nullptr, &h_), "Mesh");
-    pp_check(pp_mesh_set_picpart(h_, hostTag<int32_t>(dim_, "safe"), hostTag<int32_t>(dim_, "ownership"),
-                                 pp_host_picpart_rank(record), PP_HOST, nullptr), "Mesh: PICpart tags");
+    try {
+      pp_check(pp_mesh_create(&d, nullptr, &h_), "Mesh");
+      pp_check(pp_mesh_set_picpart(h_, hostTag<int32_t>(dim_, "safe"), hostTag<int32_t>(dim_, "ownership"),
+                                   pp_host_picpart_rank(record), PP_HOST, nullptr), "Mesh: PICpart tags");
+    } catch (...) {
+      if (h_) pp_mesh_destroy(h_);
+      h_ = nullptr; record_ = nullptr; comm_ = nullptr;
+      throw;
+    }
+    owns_record_ = own;
   }
   ~Mesh() {
     for (int d = 0; d < 4; ++d) if (plan_[d]) pp_comm_plan_destroy(plan_[d]);
@@ -562,6 +667,20 @@ class Mesh {
   }
 
  private:
+  void build(const pp_host_mesh* full, const std::vector<lid_t>& owners, int bm, int sm, int bl, int sl, int bridge,
+             pp_comm* comm) {
+    const int nranks = comm ? pp_comm_size(comm) : 1, rank = comm ? pp_comm_rank(comm) : 0;
+    if ((int)owners.size() != pp_host_mesh_nents(full, pp_host_mesh_dim(full)))
+      throw std::runtime_error("Mesh: one owner per element is required");
+    pp_host_picpart* rec = nullptr;
+    pp_check(pp_host_picpart_build_bridged(full, owners.data(), nranks, rank, bm, sm, bl, sl, bridge, &rec), "Mesh");
+    try {
+      adopt(rec, comm, true);
+    } catch (...) {
+      pp_host_picpart_destroy(rec);
+      throw;
+    }
+  }
   template <class T>
   const T* hostTag(int edim, const char* name, bool required = true) const {
     if (!record_) throw std::runtime_error("Mesh: not built from a PICpart record");

@@ -88,6 +88,27 @@ int main() {
     CHECK(back.safeTag().toHost() == safe && back.entOwners(2).toHost() == own);
     CHECK(back.globalIds(2).toHost() == gids && back.commArrayIndex(2).toHost() == cai);
     CHECK(back.bufferedRanks(2) == picparts.bufferedRanks(2));
+    // Mesh(Input&) and the two owner-vector constructors on one rank (no communicator): the PICpart is
+    // the whole mesh, everything is owned by rank 0 and safe
+    std::vector<int> zero((size_t)ne, 0);
+    p::Input in(full, p::Input::PARTITION, zero, p::Input::getMethod("bfs"), p::Input::getMethod("Full"));
+    CHECK(in.bridge_dim == 0 && in.bufferBFSLayers == 3 && in.safeBFSLayers == 1 && in.getRule() == p::Input::PARTITION);
+    CHECK(p::Input::getMethod("minimum") == p::Input::MINIMUM && p::Input::getMethod("x") == p::Input::INVALID);
+    in.bridge_dim = 1;
+    p::Mesh m_in(in);
+    p::Mesh m_full(full, zero, nullptr);
+    p::Mesh m_bfs(full, zero, 3, 1, nullptr);
+    for (p::Mesh* mm : {&m_in, &m_full, &m_bfs}) {
+      CHECK(mm->nelems() == ne && mm->numBuffers(2) == 1);
+      std::vector<int> sf = mm->safeTag().toHost(), ow = mm->entOwners(2).toHost();
+      int bad = 0;
+      for (int e = 0; e < ne; ++e) bad += (sf[e] == 0) + (ow[e] != 0);
+      CHECK(bad == 0);
+    }
+    CHECK(m_full.isFullMesh());
+    bool threw = false;
+    try { p::Mesh m_bad(full, zero, 1, 2, nullptr); } catch (const std::exception&) { threw = true; }
+    CHECK(threw);
   }
 
   // ---------------------------------------------------------------- structure with initial data (getMemberView)
