@@ -67,3 +67,24 @@ def test_compute_call_without_gpu_fails_loudly():
 def meshes_small():
     import meshes
     return meshes.kuhn_cube(2)
+
+
+def test_mirror_header_compiles_on_the_host_and_input_follows_the_reference(tmp_path):
+    """The C++ mirror (pumi-pic_b200/cpp/pumipic_b200.hpp) is usable from a plain g++ translation unit
+    (set-up code of an application), and pumipic::Input behaves like pumipic_input.cpp:94-110."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    if shutil.which("g++") is None or not os.path.isdir(cuda_inc):
+        pytest.skip("g++ or the CUDA headers are not here")
+    importlib.import_module("pumi-pic_b200").lib()          # makes sure the library is built
+    exe = str(tmp_path / "input_host")
+    libdir = os.path.join(root, "pumi-pic_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(root, "include"), "-I", os.path.join(libdir, "cpp"),
+                           "-I", cuda_inc, os.path.join(root, "tests", "cpp", "input_host.cpp"), "-o", exe,
+                           "-L", libdir, "-lpumipic_b200", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe], capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+    out = r.stdout.decode()
+    assert "pumipic buffer method MINIMUM" in out and "pumipic safe method MINIMUM" in out
