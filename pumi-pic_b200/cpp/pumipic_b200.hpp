@@ -606,6 +606,8 @@ class Mesh {
   bool isFullMesh() const { return record_ ? pp_host_picpart_is_full_mesh(record_) != 0 : true; }
   // ---- the PICpart record (pumipic_mesh.hpp:33-52); only for a Mesh made from one
   const pp_host_picpart* record() const { return record_; }
+  // Mesh::mesh(): the PICpart's own mesh with its tags (host side); null for a Mesh made from arrays
+  const pp_host_mesh* mesh() const { return record_ ? pp_host_picpart_mesh(record_) : nullptr; }
   int numBuffers(int edim) const { return dimInfo(edim).num_cores + 1; }
   std::vector<lid_t> bufferedRanks(int edim) const {
     const pp_host_picpart_dim i = dimInfo(edim);
@@ -1095,6 +1097,27 @@ int PS_Comm_Reduce(View<T> send_view, View<T> recv_view, int count, PS_Op op, in
   if (pp_comm_rank(comm) == root) return PS_Comm_Allreduce(send_view, recv_view, count, op, comm);
   View<T> scratch((size_t)count);
   return PS_Comm_Allreduce(send_view, scratch, count, op, comm);
+}
+
+// printPtclImb (src/pumipic_lb.hpp:379-398): max, min, average and imbalance of the particle counts,
+// printed by rank 0 (integer average first, like the reference's `tot_p / comm_size`)
+template <class PS>
+void printPtclImb(PS* ptcls, PS_Comm comm = nullptr) {
+  const int np = ptcls->nPtcls();
+  int min_p = np, max_p = np, tot_p = np, comm_size = 1, comm_rank = 0;
+  if (comm && pp_comm_size(comm) > 1) {
+    comm_size = pp_comm_size(comm);
+    comm_rank = pp_comm_rank(comm);
+    View<int> in(std::vector<int>{np}), out((size_t)1);
+    PS_Comm_Allreduce(in, out, 1, PS_MIN, comm); min_p = out.toHost()[0];
+    PS_Comm_Allreduce(in, out, 1, PS_MAX, comm); max_p = out.toHost()[0];
+    PS_Comm_Allreduce(in, out, 1, PS_SUM, comm); tot_p = out.toHost()[0];
+  }
+  if (comm_rank == 0) {
+    const float avg = (float)(tot_p / comm_size);
+    const float imb = max_p / avg;
+    std::printf("Ptcl LB <max, min, avg, imb>: %d %d %.3f %.3f\n", max_p, min_p, avg, imb);
+  }
 }
 
 // ---------------------------------------------------------------- gather (field -> particle)

@@ -243,6 +243,8 @@ int main() {
     p::ParticleBalancer balancer(picparts);
     picparts.setPtclBalancer(&balancer);
     CHECK(picparts.ptclBalancer() == &balancer && balancer.getSbarIDs(picparts).size() == (size_t)nel);
+    p::printPtclImb(ptcls);                                     // pumipic_lb.hpp:379-398, one rank
+    CHECK(picparts.mesh() == pp_host_picpart_mesh(rec));
     balancer.addWeights(picparts, ptcls, new_elems, new_procs);
     balancer.balance(picparts, 1.05);
     PS::kkLidView procs2(new_procs.toHost());
