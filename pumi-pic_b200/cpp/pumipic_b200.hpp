@@ -383,7 +383,40 @@ class SellCSigma : public ParticleStructure<DataTypes> {
   }
 };
 
-#define PP_B200_FLAT_STRUCTURE(NAME, KIND, LABEL)                                                     \
+// The flat structures and their input classes (csr/CSR_input.hpp:10-42, dps/dps_input.hpp:9-34,
+// cabm/cabm_input.hpp:9-34).  DPS and CabM are constructible from their input class (dps.hpp:48,
+// cabm.hpp:48); the reference declares CSR_Input but gives CSR no constructor for it.
+#define PP_B200_FLAT_INPUT(NAME, STRUCT, EXTRA_MEMBERS)                                               \
+  template <class DataTypes> class STRUCT;                                                            \
+  template <class DataTypes>                                                                          \
+  class NAME {                                                                                        \
+   public:                                                                                            \
+    typedef View<lid_t> kkLidView;                                                                    \
+    typedef View<gid_t> kkGidView;                                                                    \
+    typedef MemberTypeViews MTVs;                                                                     \
+    typedef TeamPolicy PolicyType;                                                                    \
+    NAME(PolicyType& p, lid_t num_elements, lid_t num_particles, kkLidView particles_per_elements,    \
+         kkGidView element_gids, kkLidView particle_elements = kkLidView(), MTVs particle_info = NULL) \
+        : policy(p), ne(num_elements), np(num_particles), ppe(particles_per_elements),                \
+          e_gids(element_gids), particle_elms(particle_elements), p_info(particle_info) {}            \
+    EXTRA_MEMBERS                                                                                     \
+    std::string name = "ptcls";                                                                       \
+                                                                                                      \
+   protected:                                                                                         \
+    PolicyType policy;                                                                                \
+    lid_t ne, np;                                                                                     \
+    kkLidView ppe;                                                                                    \
+    kkGidView e_gids;                                                                                 \
+    kkLidView particle_elms;                                                                          \
+    MTVs p_info;                                                                                      \
+    friend class STRUCT<DataTypes>;                                                                   \
+  };
+PP_B200_FLAT_INPUT(CSR_Input, CSR, bool always_realloc = false; double minimize_size = 0.8; double padding_amount = 1.05;)
+PP_B200_FLAT_INPUT(DPS_Input, DPS, double extra_padding = 0.05;)
+PP_B200_FLAT_INPUT(CabM_Input, CabM, double extra_padding = 0.05;)
+#undef PP_B200_FLAT_INPUT
+
+#define PP_B200_FLAT_STRUCTURE(NAME, KIND, LABEL, INPUT_CTOR)                                         \
   template <class DataTypes>                                                                          \
   class NAME : public ParticleStructure<DataTypes> {                                                  \
    public:                                                                                            \
@@ -392,6 +425,7 @@ class SellCSigma : public ParticleStructure<DataTypes> {
     using typename Base::kkLidView;                                                                   \
     using typename Base::MTVs;                                                                        \
     typedef TeamPolicy PolicyType;                                                                    \
+    typedef NAME##_Input<DataTypes> Input_T;                                                          \
     NAME(PolicyType& p, lid_t num_elements, lid_t num_particles, kkLidView particles_per_element,     \
          kkGidView element_gids, kkLidView particle_elements = kkLidView(), MTVs particle_info = NULL) \
         : Base(LABEL) {                                                                               \
@@ -401,10 +435,20 @@ class SellCSigma : public ParticleStructure<DataTypes> {
       this->create(cfg, num_elements, num_particles, particles_per_element, element_gids,             \
                    particle_elements, particle_info);                                                 \
     }                                                                                                 \
+    INPUT_CTOR                                                                                        \
   };
-PP_B200_FLAT_STRUCTURE(CSR, PP_PS_CSR, "ptcls")     // csr/CSR.hpp:37-44
-PP_B200_FLAT_STRUCTURE(DPS, PP_PS_DPS, "ptcls")     // dps/dps.hpp:41-48
-PP_B200_FLAT_STRUCTURE(CabM, PP_PS_CABM, "ptcls")   // cabm/cabm.hpp:41-48
+#define PP_B200_PADDED_INPUT_CTOR(NAME, KIND)                                                         \
+  explicit NAME(NAME##_Input<DataTypes>& in) : Base(in.name) {                                        \
+    pp_ps_config cfg;                                                                                 \
+    pp_ps_config_default(&cfg, KIND);                                                                 \
+    cfg.team_size = in.policy.team_size();                                                            \
+    cfg.extra_padding = in.extra_padding;                                                             \
+    this->create(cfg, in.ne, in.np, in.ppe, in.e_gids, in.particle_elms, in.p_info);                  \
+  }
+PP_B200_FLAT_STRUCTURE(CSR, PP_PS_CSR, "ptcls", )                                            // csr/CSR.hpp:37-44
+PP_B200_FLAT_STRUCTURE(DPS, PP_PS_DPS, "ptcls", PP_B200_PADDED_INPUT_CTOR(DPS, PP_PS_DPS))    // dps/dps.hpp:41-48
+PP_B200_FLAT_STRUCTURE(CabM, PP_PS_CABM, "ptcls", PP_B200_PADDED_INPUT_CTOR(CabM, PP_PS_CABM)) // cabm/cabm.hpp:41-48
+#undef PP_B200_PADDED_INPUT_CTOR
 #undef PP_B200_FLAT_STRUCTURE
 
 // ---------------------------------------------------------------- parallel_for (nvcc only)

@@ -135,6 +135,20 @@ int main() {
   PS* ptcls = new p::SellCSigma<Particle>(policy, INT_MAX, 1024, nel, np, ppe_d, gids_d, pel_d, info);
   p::destroyViews<Particle>(info);
   CHECK(ptcls->nPtcls() == np && ptcls->nElems() == nel && ptcls->capacity() >= np);
+  {
+    // the input-class constructors of the flat structures (dps/dps_input.hpp, cabm/cabm_input.hpp):
+    // capacity = ceil(ceil(np / 32) * (1 + extra_padding)) * 32 (dps.hpp:129-132)
+    p::DPS_Input<Particle> din(policy, nel, np, ppe_d, gids_d);
+    din.extra_padding = 0.25;
+    din.name = "dps_from_input";
+    p::DPS<Particle> dps(din);
+    CHECK(dps.nPtcls() == np && dps.capacity() == (int)std::ceil(std::ceil(np / 32.0) * 1.25) * 32);
+    p::CabM_Input<Particle> cin(policy, nel, np, ppe_d, gids_d);
+    p::CabM<Particle> cabm(cin);
+    CHECK(cabm.nPtcls() == np && cabm.nElems() == nel);
+    p::CSR_Input<Particle> csr_in(policy, nel, np, ppe_d, gids_d);
+    CHECK(csr_in.padding_amount == 1.05 && !csr_in.always_realloc);
+  }
 
   // every particle sits in the row of its element with its data (test_structure.cpp:326-351)
   const int cap = ptcls->capacity();
