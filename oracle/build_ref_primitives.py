@@ -206,6 +206,8 @@ def main():
              os.path.join(REF, "test/test_adj.cpp"), os.path.join(HERE, "ref_shim", "ref_testadj.cpp"),
              os.path.join(REF, "test/pseudoPushAndSearch.cpp"), os.path.join(HERE, "ref_shim", "ref_ppas.cpp"),
              os.path.join(REF, "particle_structs/src/scs/SCS_buildFns.h"), os.path.join(HERE, "ref_shim", "ref_scs.cpp"),
+             os.path.join(REF, "test/pseudoXGCm.cpp"), os.path.join(HERE, "ref_shim", "ref_xgcm_init.cpp"),
+             os.path.join(REF, "src/pumipic_part_construct.cpp"), os.path.join(HERE, "ref_shim", "ref_picpart.cpp"),
              os.path.abspath(__file__)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return 0
