@@ -123,6 +123,7 @@ XGCINIT_FUNCTIONS = [
 # src/pumipic_part_construct.cpp: the set-up kernels of PICpart construction (ref_shim/ref_picpart.cpp);
 # index 1 = the definition (index 0 is the forward declaration at the top of the file)
 PICPART_FUNCTIONS = [
+    ("src/pumipic_part_construct.cpp", r"void setOwnerByClassification\(Omega_h::Mesh& m", 1),
     ("src/pumipic_part_construct.cpp", r"Omega_h::LOs defineOwners\(Omega_h::Mesh& m", 1),
     ("src/pumipic_part_construct.cpp", r"Omega_h::LOs calculateOwnerOffset\(Omega_h::LOs owner", 1),
     ("src/pumipic_part_construct.cpp", r"struct GlobalNumberer \{", 0),

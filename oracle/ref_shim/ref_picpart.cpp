@@ -1,5 +1,5 @@
 // ref_picpart.cpp -- TEST INFRASTRUCTURE ONLY.  The set-up kernels of PICpart construction
-// (src/pumipic_part_construct.cpp: BFS, bfsBufferLayers, bfsSafeInward, defineOwners,
+// (src/pumipic_part_construct.cpp: setOwnerByClassification, BFS, bfsBufferLayers, bfsSafeInward, defineOwners,
 // calculateOwnerOffset, GlobalNumberer / createGlobalNumbering, rankLidNumbering), extracted into
 // ref_picpart.inc (a build-time temporary) and compiled unmodified: what
 // pumi-pic_b200/csrc/pp_host_picpart.cpp (picpart_tags) and pp_host_ppm.cpp (build_world) restate.
@@ -43,6 +43,14 @@ template <class T, class U> T atomic_fetch_add(T* p, U v) {
   return old;
 }
 }  // namespace Kokkos
+
+#undef printInfo
+#undef printError
+#include <cassert>
+namespace pumipic {
+inline void printInfo(const char*, ...) {}
+inline void printError(const char*, ...) {}
+}  // namespace pumipic
 
 namespace picpart_ref {
 #include "ref_picpart.inc"
@@ -92,6 +100,18 @@ void ref_picpart_tags(int dim, int bridge_dim, int nbridges, const int* up_off, 
     picpart_ref::bfsSafeInward(mesh, bridge_dim, comm, safe_layers, owners, o::LOs(has_part), is_safe);
   for (int e = 0; e < nelems; ++e) safe_out[e] = is_safe[e];
   for (int p = 0; p < nranks; ++p) has_part_out[p] = has_part[p];
+}
+
+// setOwnerByClassification :278-301: element owners through the class ids (`.cpn` partitions)
+void ref_owner_by_classification(int dim, int nelems, const int* class_id, int ntable, const int* class_owners,
+                                 int self, int* owns_out) {
+  o::Mesh mesh;
+  mesh.dim_ = dim;
+  mesh.nelems_ = nelems;
+  mesh.class_id = o::LOs(to_w(class_id, nelems));
+  o::Write<o::LO> owns(nelems, -1);
+  picpart_ref::setOwnerByClassification(mesh, o::LOs(to_w(class_owners, ntable)), self, owns);
+  for (int e = 0; e < nelems; ++e) owns_out[e] = owns[e];
 }
 
 // defineOwners :304-323 for the entities of one dimension

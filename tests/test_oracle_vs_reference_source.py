@@ -783,3 +783,32 @@ def test_picpart_setup_kernels_equal_the_reference(ref, case):
                                  gids.ctypes.data_as(C.POINTER(C.c_longlong)), lids.ctypes.data_as(ip))
         assert np.array_equal(m.tag(k, "gids"), gids) and np.array_equal(m.tag(k, "rank_lids"), lids)
         assert np.array_equal(pic.dim_info(k)["offset_ents_per_rank"], offs)
+
+
+def test_cpn_ownership_equals_the_reference(ref, tmp_path):
+    """`.cpn` partitions: the file reader (pumipic_input.cpp:61-85 builds the class-owner table) followed
+    by setOwnerByClassification (part_construct.cpp:278-301, compiled unmodified) against
+    pp_host_read_partition on the xgc/24k class ids."""
+    import importlib
+    from meshes import load_fixture
+    P = importlib.import_module("pumi-pic_b200")
+    mesh = load_fixture("xgc24k")
+    cls = np.ascontiguousarray(mesh.class_id, np.int32)
+    ids = np.unique(cls)
+    rng = np.random.default_rng(5)
+    nranks = 4
+    owners_of = {int(c): int(rng.integers(0, nranks)) for c in ids}
+    size = int(ids.max())
+    cpn = tmp_path / "xgc.cpn"
+    cpn.write_text("%d\n" % size + "".join("%d %d\n" % (c, o) for c, o in owners_of.items()))
+    got = P.host_read_partition(cpn, mesh.nelems, cls)
+    table = np.zeros(size + 1, np.int32)                      # host_owners(size+1), :73-76
+    for c, o in owners_of.items():
+        table[c] = o
+    for self_rank in range(nranks):
+        if not (got == self_rank).any():
+            continue                                          # the reference asserts on a rank that owns nothing
+        want = np.full(mesh.nelems, -1, np.int32)
+        ref.ref_owner_by_classification(2, mesh.nelems, _i(cls), size + 1, _i(table), self_rank,
+                                        want.ctypes.data_as(ip))
+        assert np.array_equal(got, want)
