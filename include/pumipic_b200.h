@@ -410,8 +410,9 @@ typedef struct pp_search_args {
   const double* x_tgt;           /* [3][stride] target positions (x_ps_tgt)  */
   int64_t stride;
   int32_t* elem_ids;             /* [capacity] in/out parent element per slot */
-  int32_t elem_ids_empty;        /* !=0: behave as if elem_ids.size()==0 (seed from the row element);
-                                  * PP_SEARCH_2D_LEGACY: !=0 promises elem_ids is a fresh array of -1 */
+  int32_t elem_ids_empty;        /* !=0: behave as if elem_ids.size()==0: every particle starts in its row
+                                  * element and the array's old contents are never read (all variants,
+                                  * all structure kinds); every slot of elem_ids is written */
   int32_t require_intersection;  /* PP_SEARCH_NEW only */
   int32_t* inter_faces;          /* [capacity] or NULL (required when require_intersection / legacy 3D and search_mesh_3d xface) */
   double* inter_points;          /* [dim*capacity] AoS or NULL (legacy 3D, search_mesh_3d: xpoints [3*capacity]) */

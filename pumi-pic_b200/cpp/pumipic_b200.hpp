@@ -102,7 +102,10 @@ class View {
  private:
   void alloc() {
     T* q = nullptr;
-    if (n_) cuda_check(cudaMalloc((void**)&q, n_ * sizeof(T)), "View alloc");
+    if (n_) {
+      cuda_check(cudaMalloc((void**)&q, n_ * sizeof(T)), "View alloc");
+      cuda_check(cudaMemset(q, 0, n_ * sizeof(T)), "View zero-fill");   // Kokkos::View zero-initialises
+    }
     p_ = std::shared_ptr<T>(q, [](T* x) { if (x) cudaFree(x); });
     raw_ = q;
   }
@@ -788,7 +791,7 @@ inline bool run_search(Mesh& mesh, PS* ptcls, int variant, Seg3 x_orig, Seg3 x_t
   a.variant = variant;
   a.x_orig = x_orig.data(); a.x_tgt = x_tgt.data(); a.stride = x_tgt.stride();
   a.elem_ids_empty = elem_ids.size() == 0;
-  if (elem_ids.size() == 0) elem_ids = View<lid_t>(cap, "elem_ids");           // tpp:504-509
+  if (elem_ids.size() == 0) elem_ids = View<lid_t>(cap, (lid_t)-1, "elem_ids");   // tpp:504-509 (-1 = "use the row element")
   a.elem_ids = elem_ids.data();
   a.require_intersection = requireIntersection;
   if (inter_faces && (requireIntersection || variant == PP_SEARCH_3D_LEGACY || variant == PP_SEARCH_3D)) {

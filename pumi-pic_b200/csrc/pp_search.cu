@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(128) k_search(SearchParams p) {
         E = p.ids_empty ? erow : p.elem_ids[s];
         live = (E != -1);
       } else if (MODE == M_LEG2D) {          // adjacency.hpp:1045-1062
-        E = p.elem_ids[s];
+        // elem_ids_empty: the caller vouches that every id is -1 ("use the row element"); the
+        // array is not read, so every structure kind and kernel variant starts identically
+        E = p.ids_empty ? -1 : p.elem_ids[s];
         if (E == -1) E = erow;
         live = true;
         if (E == -p.nelems) { E = -1; live = false; }
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(BLOCK, (DIM == 3 ? 3 : 4)) k_walk_bcc(SearchPa
         E = p.ids_empty ? erow : p.elem_ids[slot];
         live = (E != -1);
       } else {                                  // adjacency.hpp:1045-1062
-        E = p.elem_ids[slot];
+        E = p.ids_empty ? -1 : p.elem_ids[slot];   // see k_search
         if (E == -1) E = erow;
         live = true;
         if (E == -p.nelems) { E = -1; live = false; }

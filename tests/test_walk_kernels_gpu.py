@@ -223,3 +223,31 @@ def test_search_mesh_2d_fresh_ids_all_kernels(meshname, nptcls, kind, variant):
         found, ids_o, st = om.search_mesh_2d(slot_elem, mask, T, start, looplimit=limit)
         assert np.array_equal(ids.cpu().numpy(), ids_o)
         assert (r.found, r.loops, r.not_found) == (int(found), st.loops, st.not_found)
+
+
+@pytest.mark.parametrize("variant", [2, 1, 0])
+@pytest.mark.parametrize("kind", ["scs", "csr", "dps"])
+def test_search_mesh_2d_ids_empty_ignores_array_contents(kind, variant):
+    """elem_ids_empty means "behave as if elem_ids.size()==0": the array's old contents (here
+    garbage, including the -nelems sentinel) must not be read by any kernel variant on any
+    structure kind; every particle starts in its row element."""
+    mesh = _mesh("plate20")
+    P = pp()
+    P.lib().pp_search_set_staged(variant)
+    om = orc.OracleMesh(mesh)
+    gm = make_gpu_mesh(mesh)
+    ps = make_ps(_kind(kind), _uneven_ppe(mesh.nelems, 7000, seed=4))
+    slot_elem, mask = ps.slot_elem_and_mask()
+    X, D = pi.init2d_internal(mesh, slot_elem, mask)
+    T = X.copy()
+    orc.push_direction(mask, T, D, 3.0 * pi.push_distance(mesh))
+    rng = np.random.default_rng(9)
+    garbage = rng.integers(-mesh.nelems, mesh.nelems, ps.capacity).astype(np.int32)
+    garbage[::7] = -mesh.nelems
+    ids = dev(garbage)
+    r = P.search_mesh(gm, ps, dev(X), dev(T), ids, elem_ids_empty=True,
+                      variant=P.capi.PP_SEARCH_2D_LEGACY, looplimit=200)
+    found, ids_o, st = om.search_mesh_2d(slot_elem, mask, T, np.full(ps.capacity, -1, np.int32), looplimit=200)
+    assert np.array_equal(ids.cpu().numpy(), ids_o)
+    assert (r.found, r.loops) == (int(found), st.loops)
+    P.lib().pp_search_set_staged(2)

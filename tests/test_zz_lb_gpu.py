@@ -175,7 +175,6 @@ def test_single_rank_and_errors():
         b2.select(ps, ne, npr)
 
 
-@pytest.mark.xfail(strict=False, reason="never run on a GPU yet (written with no GPU time left)")
 def test_rank_without_particles():
     """a rank without particles (capacity 0, no slot arrays) still takes part in every step"""
     P = pp()

@@ -1,4 +1,4 @@
-"""GPU tests added when the round's GPU time was spent (hence the file name: last under `-x`):
+"""GPU tests of the C++ mirror (file name: last under `-x`):
 the self-checking C++ driver tests/cpp/mirror_api.cu (getMemberView, getPIDs, the PICpart-record
 Mesh and its accessors, setUnsafeProcs, ParticleBalancer, PS_Comm_* on one rank) and getPIDs
 through the C ABI on every structure kind (particle_structs/test/test_structure.cpp:354-378)."""
@@ -10,12 +10,8 @@ import pytest
 
 from gpu_common import pp
 
-# Quarantine: everything in this file was written after the round's GPU budget was spent and has
-# never run on hardware.  xfail(strict=False) keeps an untried test from turning the verified
-# suites red; the first GPU call of the next round runs them (tools/gpu_first_call.sh) and this
-# marker goes away.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="never run on a GPU yet (written with no GPU time left)")]
+# All of these passed on the round-1 driver box (GPUTEST_r01); the quarantine marker is gone.
+pytestmark = [pytest.mark.gpu]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "cpp", "_bin", "mirror_api")
 
