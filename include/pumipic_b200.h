@@ -354,9 +354,22 @@ pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
                         const int32_t* new_particle_elements,
                         const void* const* new_particle_info, pp_stream stream);
 
-/* Record move of a full re-layout: 1 (default) = through an array-of-records stage (every DRAM
- * access a full sector), 0 = direct scatter.  Same results as sets of particles; for A/B timing. */
-void pp_ps_set_staged_rebuild(int32_t on);
+/* Record move of a full re-layout.  2 (default): device-side layout with one host read per rebuild;
+ * narrow structures (<= 14 columns per chunk on average) then gather the records in one pass in
+ * destination order, the destination chunks handed out in element order so that gathered source
+ * sectors stay in L2, wider ones go through the record stage (Sell-C-sigma with C = 32 and
+ * sparse rows; other cases use mode 1).  1: through an array-of-records stage behind the host-synchronous
+ * layout code (every structure kind; does not depend on the locality of the element numbering).
+ * 0: direct scatter (A/B).  Same results as sets of particles in every mode. */
+void pp_ps_set_staged_rebuild(int32_t mode);
+/* Mode 2: hand destination chunks to the blocks in ascending order of their first row's element
+ * (default) or in slot order (0, A/B: the gather then re-fetches every source sector from DRAM). */
+void pp_ps_set_rebuild_chunk_order(int32_t on);
+/* Mode 2 A/B knobs.  gather_blocks_per_sm: resident blocks per SM of the gather; <= 0 (default) sizes
+ * the grid so that the source footprint of the chunks in flight fits L2.  gather_max_cols: average
+ * columns per chunk up to which the records are gathered; wider structures go through the record
+ * stage (default 14; 0 = always stage, < 0 keeps the setting). */
+void pp_ps_set_rebuild_tuning(int32_t gather_blocks_per_sm, int32_t gather_max_cols);
 /* SellCSigma::setShuffling (scs/SellCSigma.h:92): try the in-place reshuffle (SCS_rebuild.h:4-120)
  * before a full re-layout.  Default on. */
 void pp_ps_set_shuffling(int32_t on);

@@ -137,6 +137,8 @@ PROTOTYPES = {
     "pp_ps_rebuild": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                 C.POINTER(C.c_void_p), C.c_void_p]),
     "pp_ps_set_staged_rebuild": (None, [C.c_int32]),
+    "pp_ps_set_rebuild_chunk_order": (None, [C.c_int32]),
+    "pp_ps_set_rebuild_tuning": (None, [C.c_int32, C.c_int32]),
     "pp_ps_set_shuffling": (None, [C.c_int32]),
     "pp_ps_set_rank_sort_threshold": (None, [C.c_int32]),
     "pp_push_constant": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,

@@ -196,6 +196,7 @@ struct pp_ps {
   char* stage;              // record stage of the rebuild (grow-only scratch)
   int shuffle_skip = 0;     // rebuilds to wait before the next reshuffle attempt
   int shuffle_streak = 0;   // consecutive failed reshuffle attempts
+  int ppe_bits_hint = 0;    // key bits of the row sort guessed from the last rebuild's largest row (0 = none)
   size_t stage_bytes;
   PsView view() const;
 };

@@ -374,7 +374,8 @@ __global__ void k_dps_fill_holes(uint32_t* mask, long nwords, int cap, const int
 constexpr int kMaxUnits = 40;          // 8-byte units of a particle record (<= 320 B)
 struct UnitTable {
   int nunits;                          // units in use
-  int rec_bytes;                       // record stride in the stage (multiple of 32)
+  int rec_bytes;                       // bytes of a record that are moved (multiple of 32)
+  int rec_stride;                      // record stride in the stage (rec_bytes, or padded to 128-byte lines)
   unsigned char kind[kMaxUnits];       // 0: one 8-byte scalar, 1: two 4-byte scalars (b may be null)
   const char* sa[kMaxUnits];           // source component bases (slot 0)
   const char* sb[kMaxUnits];
@@ -426,20 +427,14 @@ __device__ __forceinline__ void pack_record(const UnitTable& t, long s, uint4* r
 //     Q = rec_bytes/16 consecutive lanes store one record as one contiguous run.  A per-lane
 //     store of 16 bytes to 32 random records costs 32 memory transactions per instruction and the
 //     kernel becomes transaction-bound (measured: lg_throttle, 18 % of DRAM peak at 160 B records).
-__global__ void __launch_bounds__(256) k_stage_pack(PsView v, const int* __restrict__ new_elem,
-                                                    const int* __restrict__ elem2row,
-                                                    const int* __restrict__ chunk_start, int C, int dense,
-                                                    const int* __restrict__ dense_off, int* row_fill,
-                                                    const int* __restrict__ rank,
-                                                    const __grid_constant__ UnitTable t, char* stage) {
-  extern __shared__ __align__(16) unsigned char pack_smem[];
-  const int lane = threadIdx.x & 31;
+// warp-level body: lane packs slot s (m = slot holds a particle), then the warp stores the records
+__device__ __forceinline__ void stage_pack_warp(int s, bool m, const int* __restrict__ new_elem,
+                                                const int* __restrict__ elem2row,
+                                                const int* __restrict__ chunk_start, int C, int dense,
+                                                const int* __restrict__ dense_off, int* row_fill,
+                                                const int* __restrict__ rank, const UnitTable& t, char* stage,
+                                                unsigned char* wsm, int lane) {
   const int stride = t.rec_bytes + 16;                       // bank-conflict-free row stride
-  unsigned char* wsm = pack_smem + (threadIdx.x >> 5) * 32 * stride;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  bool m = false;
-  if (s < v.capacity) m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
-  if (__ballot_sync(0xffffffffu, m) == 0u) return;           // warp-uniform
   const int nq = t.rec_bytes >> 4;
   int ns = -1;
   if (m) {
@@ -475,9 +470,25 @@ __global__ void __launch_bounds__(256) k_stage_pack(PsView v, const int* __restr
     const int rec = base + myrec;
     const int nsr = __shfl_sync(0xffffffffu, ns, rec & 31);
     if (act && rec < 32 && nsr >= 0)
-      *reinterpret_cast<uint4*>(stage + (long)nsr * t.rec_bytes + piece * 16) =
+      *reinterpret_cast<uint4*>(stage + (long)nsr * t.rec_stride + piece * 16) =
           *reinterpret_cast<const uint4*>(wsm + rec * stride + piece * 16);
   }
+  __syncwarp();
+}
+__global__ void __launch_bounds__(256) k_stage_pack(PsView v, const int* __restrict__ new_elem,
+                                                    const int* __restrict__ elem2row,
+                                                    const int* __restrict__ chunk_start, int C, int dense,
+                                                    const int* __restrict__ dense_off, int* row_fill,
+                                                    const int* __restrict__ rank,
+                                                    const __grid_constant__ UnitTable t, char* stage) {
+  extern __shared__ __align__(16) unsigned char pack_smem[];
+  const int lane = threadIdx.x & 31;
+  unsigned char* wsm = pack_smem + (threadIdx.x >> 5) * 32 * (t.rec_bytes + 16);
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  bool m = false;
+  if (s < v.capacity) m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  if (__ballot_sync(0xffffffffu, m) == 0u) return;           // warp-uniform
+  stage_pack_warp(s, m, new_elem, elem2row, chunk_start, C, dense, dense_off, row_fill, rank, t, stage, wsm, lane);
 }
 // pack new particles: member arrays are [ncomp][n], destination slots precomputed
 __global__ void __launch_bounds__(256) k_stage_pack_new(const int* __restrict__ slots, int n,
@@ -486,10 +497,10 @@ __global__ void __launch_bounds__(256) k_stage_pack_new(const int* __restrict__ 
   if (i >= n) return;
   uint4 first[kGroup];
   load_group(t, 0, i, first);
-  pack_record(t, i, reinterpret_cast<uint4*>(stage + (long)slots[i] * t.rec_bytes), first);
+  pack_record(t, i, reinterpret_cast<uint4*>(stage + (long)slots[i] * t.rec_stride), first);
 }
 __device__ __forceinline__ void unpack_record(const UnitTable& t, const char* stage, long slot) {
-  const uint4* rec = reinterpret_cast<const uint4*>(stage + slot * t.rec_bytes);
+  const uint4* rec = reinterpret_cast<const uint4*>(stage + slot * t.rec_stride);
   const int nq = (t.nunits + 1) >> 1;
   for (int q0 = 0; q0 < nq; q0 += kGroup) {
     uint4 r[kGroup];
@@ -568,6 +579,7 @@ bool unit_table(const pp_ps* ps, const void* const* src, long src_stride, const 
       }
     }
   t.rec_bytes = ((t.nunits * 8 + 31) / 32) * 32;
+  t.rec_stride = t.rec_bytes;
   return t.nunits > 0;
 }
 
@@ -709,7 +721,8 @@ __global__ void k_shuffle_move(const int* __restrict__ src, const int* __restric
 }
 
 int g_rank_sort_ppe = 128;   // particles per element from which ranks come from a sort
-int g_staged_rebuild = 1;   // 0: direct scatter (k_move_kept), kept for A/B measurements
+int g_staged_rebuild = 2;   // 2: single-pass gather (SCS, C = 32); 1: record stage; 0: direct scatter (A/B)
+int g_sm_count_scs = 0;
 
 pp_status stage_ensure(pp_ps* ps, size_t bytes, cudaStream_t s) {
   if (ps->stage_bytes >= bytes) return PP_OK;
@@ -984,6 +997,396 @@ pp_status pp_scs_build(pp_ps* ps, const int* ppe_dev, const int* pelems_dev,
 }
 
 // ------------------------------------------------------------------------------------------
+// Single-pass rebuild of a Sell-C-sigma structure (C = 32): device-side layout + gather.
+//
+// The staged move above costs 2 x record (SoA) + 2 x padded record (stage) of DRAM traffic and
+// the layout code around it reads five scalars back to the host.  This path
+//   * derives the whole layout on the device with ONE host read at the end (active particles,
+//     non-empty elements, largest row, slices, capacity), speculating on the two values the host
+//     needs earlier: the chunk height (C = team size unless fewer than C elements hold particles,
+//     SCS_buildFns.h:4-16) and the number of key bits of the row sort (from the previous rebuild's
+//     largest row).  A failed speculation falls back to the synchronous path above;
+//   * moves every record ONCE: the destination slot of each kept particle follows from its rank
+//     in its element (the value the histogram's atomic returned), an inverse map
+//     src_of[destination] = source is written (4-byte scatter into an L2-resident array), and one
+//     warp per destination chunk gathers the records component by component: destination stores
+//     are fully coalesced, source loads are 8-byte gathers;
+//   * hands the chunks to the warps in ascending order of their first row's element id, not in
+//     slot order.  Rows are sorted by particle count, so slot order sweeps the element range
+//     once per count class and the other three particles of a gathered 32-byte source sector
+//     would be needed a whole sweep later; in element order they are needed by chunks that are
+//     resident at the same time, and the sector is served from L2.
+// ------------------------------------------------------------------------------------------
+// key = 1/256-th of the element range the chunk's first row lies in: one radix pass; chunks of one
+// bucket (~4 K elements) are in flight together anyway
+__global__ void k_chunk_keys(const int* __restrict__ row2elem, int nchunks, unsigned* keys, int* vals) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  keys[c] = (unsigned)(((long long)row2elem[c * 32] << 8) / ((long long)nchunks * 32));
+  vals[c] = c;
+}
+// chunks of a C = 32 layout in ascending order of (the bucket of) their first row's element
+pp_status chunk_order_build(const int* row_to_element, int nchunks, cudaStream_t s, int** order) {
+  *order = nullptr;
+  if (nchunks < 2) return PP_OK;
+  unsigned *ck_in, *ck_out;
+  int* cv_in;
+  PP_TRY(pp_dev_alloc(&ck_in, nchunks, s)); PP_TRY(pp_dev_alloc(&ck_out, nchunks, s));
+  PP_TRY(pp_dev_alloc(&cv_in, nchunks, s)); PP_TRY(pp_dev_alloc(order, nchunks, s));
+  k_chunk_keys<<<pp_div_up(nchunks, kBlock), kBlock, 0, s>>>(row_to_element, nchunks, ck_in, cv_in);
+  const int ebits = 8;
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, ck_in, ck_out, cv_in, *order, nchunks, 0, ebits, s);
+  char* tmp;
+  PP_TRY(pp_dev_alloc(&tmp, tb, s));
+  PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, ck_in, ck_out, cv_in, *order, nchunks, 0, ebits, s));
+  pp_dev_free(tmp, s); pp_dev_free(ck_in, s); pp_dev_free(ck_out, s); pp_dev_free(cv_in, s);
+  return PP_OK;
+}
+
+struct FastScal {        // device scalars of one rebuild, read back once
+  int nnz, active, maxcount, bad;
+  int cw_sum, cw_cnt, nslices, capacity;
+  int next_chunk, pad0, pad1, pad2;
+  double inv;
+};
+
+__global__ void k_count_stats(const int* __restrict__ a, int n, FastScal* out) {
+  __shared__ int p_nz[kBlock / 32], p_sum[kBlock / 32], p_max[kBlock / 32];
+  int nz = 0, sum = 0, mx = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int v = a[i];
+    nz += v > 0; sum += v; mx = max(mx, v);
+  }
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) { p_nz[threadIdx.x >> 5] = nz; p_sum[threadIdx.x >> 5] = sum; p_max[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kBlock / 32; ++w) { nz += p_nz[w]; sum += p_sum[w]; mx = max(mx, p_max[w]); }
+    if (nz) atomicAdd(&out->nnz, nz);
+    if (sum) atomicAdd(&out->active, sum);
+    if (mx) atomicMax(&out->maxcount, mx);
+  }
+}
+
+// padding (SCS_buildFns.h:62-97) + slices per chunk + slots per chunk in one pass
+__global__ void k_chunk_sizes(int* width, int nchunks, const FastScal* __restrict__ sc, double pad, int strat,
+                              int V, int C, int2* sizes) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nchunks) return;
+  if (c == nchunks) { sizes[c] = make_int2(0, 0); return; }
+  int w = width[c];
+  if (pad > 0 && sc->cw_sum > 0) {
+    if (strat == PP_PAD_EVENLY) {
+      const int avg_pad = (int)(sc->cw_sum * pad / sc->cw_cnt);
+      if (w > 0) w = w + avg_pad;
+    } else if (strat == PP_PAD_PROPORTIONALLY) {
+      w = (int)(w + w * pad);
+    } else {
+      const double cw_sum2 = sc->cw_sum / sc->inv * pad;
+      if (w != 0) w = (int)(w + cw_sum2 / w);
+    }
+    width[c] = w;
+  }
+  sizes[c] = make_int2(w / V + (w % V != 0), w * C);
+}
+struct Int2Sum {
+  __host__ __device__ int2 operator()(const int2& a, const int2& b) const { return make_int2(a.x + b.x, a.y + b.y); }
+};
+// constructOffsets (SCS_buildFns.h:115-153) from the two prefix sums
+__global__ void k_fill_layout(const int2* __restrict__ pref, const int* __restrict__ width, int nchunks, int V,
+                              int C, int* s2c, int* offsets, int* chunk_start, FastScal* sc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nchunks) return;
+  const int2 p = pref[c];
+  chunk_start[c] = p.y;
+  if (c == nchunks) { offsets[p.x] = p.y; offsets[p.x + 1] = p.y; sc->nslices = p.x; sc->capacity = p.y; return; }
+  const int ns = pref[c + 1].x - p.x;
+  for (int j = 0; j < ns; ++j) { s2c[p.x + j] = c; offsets[p.x + j] = p.y + j * V * C; }
+}
+// kept particles: src_of[destination slot] = source slot
+__global__ void k_invmap(PsView v, const int* __restrict__ new_elem, const int* __restrict__ rank,
+                         const int* __restrict__ elem2row, const int* __restrict__ chunk_start, int* src_of) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.capacity) return;
+  const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+  if (!m) return;
+  const int e = __ldg(new_elem + s);
+  if (e < 0) return;
+  const int row = __ldg(elem2row + e);
+  src_of[__ldg(chunk_start + (row >> 5)) + (__ldg(rank + s) << 5) + (row & 31)] = s;
+}
+__global__ void k_invmap_new(const int* __restrict__ slots, int n, int* src_of) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) src_of[slots[i]] = -i - 1;
+}
+
+// One block per destination chunk, the chunk's columns dealt round-robin to the block's warps
+// (lane = row): gathers the records of the chunk's particles into the new SoA columns and writes
+// the chunk's particle mask.  Few chunks are in flight (one per resident block), each with many
+// loads outstanding (a warp works on two columns at a time): the source sectors touched by the
+// chunks in flight must stay L2-resident until the chunks that own their other three particles
+// have read them too.
+// t: old structure -> new structure; tn: arrays of the particles being added -> new structure.
+__device__ __forceinline__ void gather_new(const UnitTable& tn, long slot, int src) {
+  const long i = -(long)src - 1;
+  for (int u = 0; u < tn.nunits; ++u) unit_store(tn, u, slot, unit_load(tn, u, i));
+}
+template <int kGatherWarps>
+__global__ void __launch_bounds__(kGatherWarps * 32) k_gather_scs(
+    const int* __restrict__ chunk_start, const int* __restrict__ row_ppe, const int* __restrict__ order,
+    int nchunks, const __grid_constant__ UnitTable t, const __grid_constant__ UnitTable tn,
+    const int* __restrict__ src_of, uint32_t* mask, int* next_chunk) {
+  __shared__ int s_k[2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
+  constexpr int U = 10;
+  if (threadIdx.x == 0) s_k[0] = atomicAdd(next_chunk, 1);
+  for (int round = 0;; ++round) {
+    __syncthreads();                                   // s_k[round & 1] is published; the other entry is free
+    const int k = s_k[round & 1];
+    if (k >= nchunks) break;
+    if (threadIdx.x == 0) s_k[(round + 1) & 1] = atomicAdd(next_chunk, 1);   // overlaps this chunk's work
+    const int c = order ? __ldg(order + k) : k;
+    const int cs = __ldg(chunk_start + c);
+    const int ncols = (__ldg(chunk_start + c + 1) - cs) >> 5;
+    const int ppe = __ldg(row_ppe + c * 32 + lane);
+    for (int colA = wid; colA < ncols; colA += 2 * kGatherWarps) {
+      const int colB = colA + kGatherWarps;
+      const bool vA = colA < ppe, vB = colB < ncols && colB < ppe;
+      const unsigned wA = __ballot_sync(full, vA), wB = __ballot_sync(full, vB);
+      if (lane == 0) {
+        mask[(cs >> 5) + colA] = wA;
+        if (colB < ncols) mask[(cs >> 5) + colB] = wB;
+      }
+      const long slotA = (long)cs + colA * 32 + lane, slotB = (long)cs + colB * 32 + lane;
+      const int srcA = vA ? __ldg(src_of + slotA) : -1, srcB = vB ? __ldg(src_of + slotB) : -1;
+      const bool oA = vA && srcA >= 0, oB = vB && srcB >= 0;      // from the old structure
+      for (int u0 = 0; u0 < t.nunits; u0 += U) {
+        unsigned long long a[U], b[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+          if (u0 + q < t.nunits && oA) a[q] = unit_load(t, u0 + q, srcA);
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+          if (u0 + q < t.nunits && oB) b[q] = unit_load(t, u0 + q, srcB);
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+          if (u0 + q < t.nunits && oA) unit_store(t, u0 + q, slotA, a[q]);
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+          if (u0 + q < t.nunits && oB) unit_store(t, u0 + q, slotB, b[q]);
+      }
+      if (vA && !oA) gather_new(tn, slotA, srcA);
+      if (vB && !oB) gather_new(tn, slotB, srcB);
+    }
+  }
+}
+
+int g_rebuild_chunk_order = 1;   // 0: chunks in slot order (A/B)
+int g_gather_bps = 0;            // resident blocks per SM of the gather; 0 = from the chunks' footprint
+double g_gather_l2_bytes = 48e6; // footprint the chunks in flight may have
+double g_gather_max_cols = 14.0; // average columns per chunk up to which the gather beats the record stage
+
+// returns done = false when a speculation failed (nothing of the structure has changed then)
+pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const int* new_particle_elements,
+                             const void* const* new_particle_info, cudaStream_t s, bool& done) {
+  done = false;
+  const int ne = ps->nelems, C = 32, cap = ps->capacity;
+  const pp_ps_config& cfg = ps->cfg;
+  const int nchunks = ne / C + (ne % C != 0), nrows = nchunks * C;
+  const int V = cfg.V > 0 ? cfg.V : 1;
+  const long active_bound = (long)ps->nptcls + n_new;
+  // key bits of the row sort: speculate from the largest row of the previous rebuild
+  int cbits = 1;
+  while (cbits < 31 && (1ll << cbits) <= (long long)active_bound) ++cbits;
+  if (ps->ppe_bits_hint > 0 && ps->ppe_bits_hint < cbits) cbits = ps->ppe_bits_hint;
+  FastScal* sc;
+  PP_TRY(pp_dev_alloc(&sc, 1, s));
+  PP_CUDA(cudaMemsetAsync(sc, 0, sizeof(FastScal), s));
+  int *count, *rank = nullptr, *kept = nullptr;
+  PP_TRY(pp_dev_alloc(&count, ne + 1, s));
+  PP_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ne + 1), s));
+  if (cap > 0) {
+    PP_TRY(pp_dev_alloc(&rank, cap, s));
+    k_hist_kept<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count, rank);
+  }
+  if (n_new > 0) {
+    PP_TRY(pp_dev_alloc(&kept, ne + 1, s));
+    PP_CUDA(cudaMemcpyAsync(kept, count, sizeof(int) * ne, cudaMemcpyDeviceToDevice, s));
+    k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, &sc->bad);
+  }
+  k_count_stats<<<std::min(pp_div_up(ne, kBlock), 592), kBlock, 0, s>>>(count, ne, sc);
+  // ---- layout (scs_layout above, without its host reads)
+  ScsLayout L;
+  L.C = C; L.nchunks = nchunks; L.nrows = nrows;
+  int* sorted_elem = nullptr;
+  if (cfg.sigma > 1) {
+    const int sigma = cfg.sigma < ne ? cfg.sigma : ne;
+    const int nwin = (ne + sigma - 1) / sigma;
+    int wbits = 0;
+    while ((1 << wbits) < nwin) ++wbits;
+    uint64_t *k_in, *k_out;
+    int* v_in;
+    PP_TRY(pp_dev_alloc(&k_in, ne, s)); PP_TRY(pp_dev_alloc(&k_out, ne, s));
+    PP_TRY(pp_dev_alloc(&v_in, ne, s)); PP_TRY(pp_dev_alloc(&sorted_elem, ne, s));
+    k_sort_keys<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(count, ne, sigma, cbits, k_in, v_in);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s);
+    char* tmp;
+    PP_TRY(pp_dev_alloc(&tmp, tb, s));
+    PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s));
+    pp_dev_free(tmp, s); pp_dev_free(k_in, s); pp_dev_free(k_out, s); pp_dev_free(v_in, s);
+  }
+  PP_TRY(pp_dev_alloc(&L.row_to_element, nrows, s));
+  PP_TRY(pp_dev_alloc(&L.element_to_row, nrows, s));
+  PP_TRY(pp_dev_alloc(&L.row_ppe, nrows, s));
+  k_rows<<<pp_div_up(nrows, kBlock), kBlock, 0, s>>>(sorted_elem, count, ne, nrows, L.row_to_element,
+                                                    L.element_to_row, L.row_ppe);
+  pp_dev_free(sorted_elem, s);
+  int* width;
+  int2 *sizes, *pref;
+  PP_TRY(pp_dev_alloc(&width, nchunks, s));
+  PP_TRY(pp_dev_alloc(&sizes, nchunks + 1, s));
+  PP_TRY(pp_dev_alloc(&pref, nchunks + 1, s));
+  k_chunk_widths<<<std::min(pp_div_up((long)nchunks * 32, kBlock), 1184), kBlock, 0, s>>>(
+      L.row_ppe, nchunks, C, width, &sc->cw_sum, &sc->inv);
+  k_chunk_sizes<<<pp_div_up(nchunks + 1, kBlock), kBlock, 0, s>>>(width, nchunks, sc, cfg.shuffle_padding,
+                                                                 cfg.padding_strat, V, C, sizes);
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveScan(nullptr, tb, sizes, pref, Int2Sum(), make_int2(0, 0), nchunks + 1, s);
+    char* tmp;
+    PP_TRY(pp_dev_alloc(&tmp, tb, s));
+    PP_CUDA(cub::DeviceScan::ExclusiveScan(tmp, tb, sizes, pref, Int2Sum(), make_int2(0, 0), nchunks + 1, s));
+    pp_dev_free(tmp, s);
+  }
+  // slices <= one per non-empty chunk + total width / V; total width <= particles * (1 + pad) + chunks
+  const double padf = cfg.shuffle_padding > 0 ? cfg.shuffle_padding : 0.0;
+  const long nslices_bound = nchunks + (long)((((long)cap + n_new) * (1.0 + padf) + nchunks) / V) + 2;
+  PP_TRY(pp_dev_alloc(&L.slice_to_chunk, nslices_bound + 1, s));
+  PP_TRY(pp_dev_alloc(&L.offsets, nslices_bound + 2, s));
+  PP_TRY(pp_dev_alloc(&L.chunk_start, nchunks + 1, s));
+  k_fill_layout<<<pp_div_up(nchunks + 1, kBlock), kBlock, 0, s>>>(pref, width, nchunks, V, C, L.slice_to_chunk,
+                                                                 L.offsets, L.chunk_start, sc);
+  // chunks in ascending order of their first row's element: the order the gather takes them in
+  int* order = nullptr;
+  if (g_rebuild_chunk_order && (double)(cap + n_new) <= g_gather_max_cols * 1.3 * 32.0 * nchunks)
+    PP_TRY(chunk_order_build(L.row_to_element, nchunks, s, &order));
+  pp_dev_free(width, s); pp_dev_free(sizes, s); pp_dev_free(pref, s);
+  // ---- the one host read
+  FastScal h;
+  PP_CUDA(cudaMemcpyAsync(&h, sc, sizeof(FastScal), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  auto drop = [&]() {
+    free_layout(L, s);
+    pp_dev_free(count, s); pp_dev_free(rank, s); pp_dev_free(kept, s); pp_dev_free(order, s); pp_dev_free(sc, s);
+  };
+  if (h.bad) {   // SCS_rebuild.h:147-151 (the reference exits the process)
+    drop();
+    pp_set_error("there are new particles being added that are marked as inactive (element id -1)");
+    return PP_ERR_INVALID;
+  }
+  int mbits = 1;
+  while (mbits < 31 && (1ll << mbits) <= (long long)h.maxcount) ++mbits;
+  ps->ppe_bits_hint = mbits + 1;                 // head room: a row may double before the guess fails
+  if (h.nnz < C || mbits > cbits || h.active == 0 || h.nslices > nslices_bound) {
+    drop();                                      // chunk height / key width guessed wrong, or nothing left
+    return PP_OK;
+  }
+  L.nslices = h.nslices; L.capacity = h.capacity;
+  const int ntiles = (L.capacity + 31) / 32;
+  PP_TRY(pp_dev_alloc(&L.tile_slice, ntiles + 1, s));
+  if (ntiles > 0)
+    k_tile_slice<<<pp_div_up(ntiles, kBlock), kBlock, 0, s>>>(L.offsets, L.nslices, ntiles, L.tile_slice);
+  L.mask_words = ntiles + 1;
+  PP_TRY(pp_dev_alloc(&L.mask, L.mask_words, s));
+  PP_CUDA(cudaMemsetAsync(L.mask + ntiles, 0, sizeof(uint32_t), s));
+  // (re)allocate the swap buffer: SCS_rebuild.h:223-229 (condition reproduced as written)
+  if (cfg.always_realloc || ps->swap.empty() || ps->swap_stride < L.capacity ||
+      ps->swap_stride * cfg.minimize_size < L.capacity) {
+    for (void* p : ps->swap) pp_dev_free((char*)p, s);
+    long nstride = (long)(L.capacity * (1 + cfg.extra_padding));
+    if (nstride < L.capacity) nstride = L.capacity;
+    if (nstride < 1) nstride = 1;
+    PP_TRY(pp_ps_alloc_members(ps, ps->swap, nstride, s));
+    ps->swap_stride = nstride;
+  }
+  std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
+  UnitTable ut, un;
+  unit_table(ps, old_src.data(), ps->stride, &ps->swap, ps->swap_stride, ut);
+  un = ut;
+  if (!g_sm_count_scs) {
+    int dev = 0;
+    PP_CUDA(cudaGetDevice(&dev));
+    PP_CUDA(cudaDeviceGetAttribute(&g_sm_count_scs, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int *row_fill = nullptr, *slots = nullptr;
+  if (n_new > 0) {               // slots of the particles being added: behind the kept ones of their row
+    PP_TRY(pp_dev_alloc(&row_fill, nrows + 1, s));
+    PP_TRY(pp_dev_alloc(&slots, n_new, s));
+    PP_CUDA(cudaMemsetAsync(row_fill, 0, sizeof(int) * (nrows + 1), s));
+    k_fill_from_kept<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(kept, ne, L.element_to_row, row_fill);
+    k_assign_slots<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, L.element_to_row,
+                                                               L.chunk_start, C, row_fill, slots);
+  }
+  // wide rows: the 8-byte gathers of a particle cost one L1 wavefront each and the source footprint of
+  // a chunk outgrows what L2 can keep for its neighbours; the record stage (full sectors both ways)
+  // is faster there (measured: 50 M particles at 25 per element, 5.3 ms staged vs 6.3 ms gathered;
+  // 10 M at 10 per element, 1.08 ms staged vs 0.98 ms gathered)
+  const double avg_cols = (double)L.capacity / (32.0 * nchunks);
+  if (avg_cols <= g_gather_max_cols) {
+    // ---- single-pass gather
+    int* src_of;
+    PP_TRY(pp_dev_alloc(&src_of, (size_t)L.capacity + 1, s));
+    if (cap > 0)
+      k_invmap<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, rank, L.element_to_row,
+                                                        L.chunk_start, src_of);
+    if (n_new > 0) {
+      k_invmap_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, src_of);
+      unit_table(ps, new_particle_info, n_new, &ps->swap, ps->swap_stride, un);
+    }
+    // blocks in flight: their chunks' source sectors (fetched as whole 64-byte DRAM atoms) must fit L2
+    const double foot = 32.0 * avg_cols * (ut.nunits * 8) * 2.0;
+    long blocks = g_gather_bps > 0 ? (long)g_sm_count_scs * g_gather_bps : (long)(g_gather_l2_bytes / (foot > 1 ? foot : 1));
+    blocks = std::max<long>(g_sm_count_scs, std::min<long>(blocks, (long)g_sm_count_scs * 7));
+    const int grid = (int)std::min<long>(nchunks, blocks);
+    k_gather_scs<4><<<grid, 4 * 32, 0, s>>>(L.chunk_start, L.row_ppe, order, nchunks, ut, un, src_of, L.mask,
+                                            &sc->next_chunk);
+    pp_dev_free(src_of, s);
+  } else {
+    // ---- record stage: pack in source order, unpack in destination order
+    PP_TRY(stage_ensure(ps, (size_t)L.capacity * ut.rec_stride, s));
+    if (cap > 0)
+      PP_TRY(launch_stage_pack(ps->view(), new_element, L.element_to_row, L.chunk_start, C, 0, nullptr, nullptr,
+                               rank, ut, ps->stage, s));
+    if (n_new > 0) {
+      unit_table(ps, new_particle_info, n_new, nullptr, 0, un);
+      k_stage_pack_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, un, ps->stage);
+    }
+    k_stage_unpack_scs<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(layout_view(L, ne), L.row_ppe, ut,
+                                                                        ps->stage, L.mask);
+  }
+  pp_dev_free(row_fill, s); pp_dev_free(slots, s);
+  PP_KERNEL_CHECK();
+  adopt_layout(ps, L, s);
+  std::swap(ps->data, ps->swap);
+  std::swap(ps->stride, ps->swap_stride);
+  if (cfg.always_realloc) {
+    for (void* p : ps->swap) pp_dev_free((char*)p, s);
+    ps->swap.clear();
+    ps->swap_stride = 0;
+  }
+  ps->nptcls = h.active;
+  pp_dev_free(order, s);
+  pp_dev_free(count, s); pp_dev_free(rank, s); pp_dev_free(kept, s); pp_dev_free(sc, s);
+  done = true;
+  return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // rebuild (SCS_rebuild.h:123-314; CSR_rebuild.hpp:18-118; dps_rebuild.hpp)
 // ------------------------------------------------------------------------------------------
 extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
@@ -1064,6 +1467,22 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
     return PP_OK;
   }
 
+  // ---- Sell-C-sigma with C = 32, sparse rows: device-side layout + single-pass gather
+  if ((kind == PP_PS_SCS || kind == PP_PS_CABM) && g_staged_rebuild >= 2 && ps->cfg.team_size == 32 &&
+      ne >= 32 && (long)ps->nptcls < (long)g_rank_sort_ppe * ne &&
+      !(g_try_shuffling && ps->capacity > 0 && ps->tile_slice && ps->shuffle_skip == 0)) {
+    UnitTable probe;
+    std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
+    if (unit_table(ps, old_src.data(), ps->stride, nullptr, 0, probe)) {
+      bool done = false;
+      PP_TRY(rebuild_scs_gather(ps, new_element, n_new, new_particle_elements, new_particle_info, s, done));
+      if (done) {
+        if (g_try_shuffling && ps->shuffle_skip > 0) --ps->shuffle_skip;
+        pp_dev_free(scal, s);
+        return PP_OK;
+      }
+    }
+  }
   // ---- element-sorted kinds: histogram of destinations (countNewParticles / rebuild_count)
   int* count;
   PP_TRY(pp_dev_alloc(&count, ne + 1, s));
@@ -1141,7 +1560,7 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
     }
     if (kept) k_fill_from_kept<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(kept, ne, nullptr, fill);
     if (staged) {
-      PP_TRY(stage_ensure(ps, (size_t)new_cap * ut.rec_bytes, s));
+      PP_TRY(stage_ensure(ps, (size_t)new_cap * ut.rec_stride, s));
       if (ps->capacity > 0)
         PP_TRY(launch_stage_pack(ps->view(), new_element, nullptr, nullptr, 1, 1, tot_dev, fill, rank, ut,
                                  ps->stage, s));
@@ -1242,7 +1661,7 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
   }
   if (kept) k_fill_from_kept<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(kept, ne, L.element_to_row, row_fill);
   if (staged) {
-    PP_TRY(stage_ensure(ps, (size_t)L.capacity * ut.rec_bytes, s));
+    PP_TRY(stage_ensure(ps, (size_t)L.capacity * ut.rec_stride, s));
     if (ps->capacity > 0)
       PP_TRY(launch_stage_pack(ps->view(), new_element, L.element_to_row, L.chunk_start, L.C, 0, nullptr,
                                row_fill, rank, ut, ps->stage, s));
@@ -1296,7 +1715,12 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
   return PP_OK;
 }
 
-extern "C" void pp_ps_set_staged_rebuild(int32_t on) { g_staged_rebuild = on ? 1 : 0; }
+extern "C" void pp_ps_set_staged_rebuild(int32_t mode) { g_staged_rebuild = mode < 0 ? 0 : mode > 2 ? 2 : mode; }
+extern "C" void pp_ps_set_rebuild_tuning(int32_t gather_blocks_per_sm, int32_t gather_max_cols) {
+  g_gather_bps = gather_blocks_per_sm > 0 ? gather_blocks_per_sm : 0;
+  if (gather_max_cols >= 0) g_gather_max_cols = gather_max_cols;
+}
+extern "C" void pp_ps_set_rebuild_chunk_order(int32_t on) { g_rebuild_chunk_order = on ? 1 : 0; }
 
 extern "C" void pp_ps_set_rank_sort_threshold(int32_t particles_per_element) {
   g_rank_sort_ppe = particles_per_element > 0 ? particles_per_element : 1;

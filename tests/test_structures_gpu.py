@@ -149,20 +149,23 @@ def _check(ps, new_element, cap0, removed=None, new_elems=None, np_expected=None
 @pytest.fixture
 def _default_rebuild_modes():
     yield
-    pp().lib().pp_ps_set_staged_rebuild(1)
+    pp().lib().pp_ps_set_staged_rebuild(2)
+    pp().lib().pp_ps_set_rebuild_tuning(0, 14)
     pp().lib().pp_ps_set_rank_sort_threshold(128)
     pp().lib().pp_ps_set_shuffling(1)
 
 
-# move = how records travel in a re-layout: staged records + atomics (default for sparse rows),
+# move = how records travel in a re-layout: device-side layout + single-pass gather (default for
+# Sell-C-sigma with sparse rows), staged records + atomics (the other sparse cases),
 # staged records + sort-derived ranks (crowded rows), direct scatter (A/B fallback)
-@pytest.mark.parametrize("move", ["staged", "ranks", "direct"])
+@pytest.mark.parametrize("move", ["gather", "fast_staged", "staged", "ranks", "direct"])
 @pytest.mark.parametrize("kindname", KINDS)
 @pytest.mark.parametrize("ne,np_", [(5, 25), (50, 1000), (2500, 100000)])
 def test_rebuild_scenarios(kindname, ne, np_, move, _default_rebuild_modes):
     """test_rebuild.cpp: no change, new elements, added, deleted, added+deleted."""
     t = torch()
-    pp().lib().pp_ps_set_staged_rebuild(0 if move == "direct" else 1)
+    pp().lib().pp_ps_set_staged_rebuild({"direct": 0, "gather": 2, "fast_staged": 2}.get(move, 1))
+    pp().lib().pp_ps_set_rebuild_tuning(0, 0 if move == "fast_staged" else 1 << 20)
     pp().lib().pp_ps_set_rank_sort_threshold(1 if move == "ranks" else 1 << 30)
     ps, ppe, _, _ = _make(kindname, ne, np_)
 

@@ -167,11 +167,19 @@ def main():
     ap.add_argument("--ps", default="scs")
     ap.add_argument("--c2-particles", type=int, default=10_000_000)
     ap.add_argument("--c4-particles", type=int, default=50_000_000)
+    ap.add_argument("--rebuild-mode", type=int, default=2, help="pp_ps_set_staged_rebuild: 2 gather, 1 stage, 0 scatter")
+    ap.add_argument("--chunk-order", type=int, default=1, help="pp_ps_set_rebuild_chunk_order")
+    ap.add_argument("--shuffling", type=int, default=1, help="pp_ps_set_shuffling")
+    ap.add_argument("--tuning", default="0,-1", help="pp_ps_set_rebuild_tuning: gather blocks/SM, gather max columns")
     a = ap.parse_args()
     import torch
     pp = importlib.import_module("pumi-pic_b200")
     wl = load_module("pp_workloads", os.path.join(ROOT, "pumi-pic_b200", "workloads.py"))
     kind = {"scs": pp.capi.PP_PS_SCS, "csr": pp.capi.PP_PS_CSR, "dps": pp.capi.PP_PS_DPS}[a.ps]
+    pp.lib().pp_ps_set_staged_rebuild(a.rebuild_mode)
+    pp.lib().pp_ps_set_rebuild_chunk_order(a.chunk_order)
+    pp.lib().pp_ps_set_shuffling(a.shuffling)
+    pp.lib().pp_ps_set_rebuild_tuning(*[int(x) for x in a.tuning.split(",")])
     for c in a.configs.split(","):
         if c == "c2":
             r = c2(pp, wl, torch, a.steps, a.c2_particles, 55, kind)
@@ -182,6 +190,8 @@ def main():
         else:
             continue
         r["particle_structure"] = a.ps
+        r["rebuild_mode"], r["chunk_order"], r["shuffling"] = a.rebuild_mode, a.chunk_order, a.shuffling
+        r["tuning"] = a.tuning
         print(json.dumps(r))
         sys.stdout.flush()
         torch.cuda.empty_cache()
