@@ -17,6 +17,13 @@ the OpenMP oracle port where that library is missing (kind "port").
 N>1 (torchrun): every rank owns an identical-size independent shard (its own PICpart-sized
 mesh + particles); push+search has no exchange step, so there is no data-path collective and
 scaling is weak.  Prints ONE JSON line on rank 0.
+
+The same line carries `picstep`: the FULL PIC step of BASELINE configs[4] (push, search,
+updatePtclPositions, setUnsafeProcs, migrate over the library's own NCCL communicator, comm-array
+all-reduce; pumi-pic_b200/picstep.py) on the same N GPUs, with per-phase times, the particles
+migrated per step and an in-run parity check of the multi-rank loop against the serial oracle; and
+`parity`: the element ids of one step of the headline workload at full size compared with the
+reference's own search_mesh source on the same inputs.
 """
 import argparse
 import importlib
@@ -164,19 +171,43 @@ def load_ref_lib():
     return L
 
 
-def cpu_reference_leg(orc, om, wl, m, ppe, sample, steps, warmup, ref=None):
-    """The reference's CPU path on a bounded sample: push (xtgt = x + d*dir) + search_mesh BCC per
-    step, ping-pong buffers like the GPU arm.  With `ref` (oracle/_ref) the reference's own source
-    runs; without it the OpenMP oracle port."""
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_leg(orc, om, wl, m, ppe, sample, steps, warmup, ref=None, loop="seeded", given=None,
+                      threads=None):
+    """The reference's CPU path: push (xtgt = x + d*dir) + search_mesh BCC per step, in the same loop
+    form as the GPU arm (seeded: every step starts from the same positions with elem_ids seeded from
+    the structure rows, +d / -d alternating; pingpong: buffers swap, ids carry over).  With `ref`
+    (oracle/_ref) the reference's own source runs; without it the OpenMP oracle port.
+    given = (slot_elem, mask, X, D): run on exactly these slot arrays (the GPU arm's structure)
+    instead of a dense array of the first `sample` particles.  Returns (particle-steps/s, ms/step,
+    slots, ids after the first timed-or-not step with +d)."""
     import ctypes as C
-    cap = int(sample)
-    slot_elem = np.repeat(np.arange(m.nelems, dtype=np.int32), ppe)[:cap]
-    mask = np.ones(cap, np.uint8)
-    X, D = wl.init3d_internal(m, slot_elem, mask)
+    threads = threads or host_threads()
+    # torchrun exports OMP_NUM_THREADS=1: set the team size explicitly, not from the environment
+    if ref is not None:
+        ref.ref_set_num_threads(int(threads))
+    orc.lib().orc_set_num_threads(int(threads))
+    if given is not None:
+        slot_elem, mask, X, D = given
+        slot_elem = np.ascontiguousarray(slot_elem, np.int32)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        cap = int(mask.shape[0])
+    else:
+        cap = int(sample)
+        slot_elem = np.repeat(np.arange(m.nelems, dtype=np.int32), ppe)[:cap]
+        mask = np.ones(cap, np.uint8)
+        X, D = wl.init3d_internal(m, slot_elem, mask)
     dist = wl.push_distance(m)
     A, B = X, np.zeros_like(X)
     ids = None
     handle = None
+    first_ids = None
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     if ref is not None:
         off, val = om.side2elem_off(), om.side2elem()
@@ -187,25 +218,82 @@ def cpu_reference_leg(orc, om, wl, m, ppe, sample, steps, warmup, ref=None):
             val.ctypes.data_as(ip), exposed.ctypes.data_as(C.POINTER(C.c_byte)), om.vol().ctypes.data_as(dp),
             cap, slot_elem.ctypes.data_as(ip), mask.ctypes.data_as(C.POINTER(C.c_ubyte))))
         ids = np.full(cap, -1, np.int32)
+    seeded = loop == "seeded"
     times, active = [], []
     for it in range(warmup + steps):
         sgn = dist if it % 2 == 0 else -dist
+        fresh = seeded or it == 0
         t0 = time.perf_counter()
         if handle is not None:
             ref.ref_bench_step(handle, A.ctypes.data_as(dp), B.ctypes.data_as(dp), D.ctypes.data_as(dp),
-                               C.c_long(A.shape[1]), C.c_double(sgn), ids.ctypes.data_as(ip), int(it == 0))
+                               C.c_long(A.shape[1]), C.c_double(sgn), ids.ctypes.data_as(ip), int(fresh))
         else:
             np.copyto(B, A)                       # xtgt = x ...
             orc.push_direction(mask, B, D, sgn)   # ... + d*dir   (same arithmetic as the fused push)
-            found, ids, _, _, st = om.search_mesh(slot_elem, mask, A, B, elem_ids=ids)
+            found, ids, _, _, st = om.search_mesh(slot_elem, mask, A, B, elem_ids=None if fresh else ids)
         dt = time.perf_counter() - t0
+        if it == 0:
+            first_ids = ids.copy()
         if it >= warmup:
             times.append(dt)
-            active.append(int((ids >= 0).sum()))
-        A, B = B, A
+            active.append(int(mask.sum()) if seeded else int((ids >= 0).sum()))
+        if not seeded:
+            A, B = B, A
     if handle is not None:
         ref.ref_bench_destroy(handle)
-    return float(sum(active)) / sum(times), 1e3 * sum(times) / len(times), cap
+    return float(sum(active)) / sum(times), 1e3 * sum(times) / len(times), cap, first_ids
+
+
+def numpy_workload(wl, cube_n, nptcls):
+    """The workload's mesh built without the product library (tests/meshes.py, numpy): the
+    reference arm must not load libpumipic_b200.so.  Identical arrays (tests/test_capi_loads.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from meshes import kuhn_cube
+    tm = kuhn_cube(cube_n)
+    return tm, wl.even_ppe(tm.nelems, nptcls)
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's host threads (and so its first-touch pinned buffers) to the CPUs NVML reports
+    as local to its GPU; without it all ranks of a box stage through one memory controller."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def scale_parity(ids_gpu, ids_ref, mask, om, Xnp, Dnp, dist, tol=1e-9):
+    """Element ids of the GPU step vs the reference's on the same slots.  near_face: mismatching
+    particles whose target lies within `tol` (barycentric) of a face of the reference's element --
+    none are expected, the geometry is bit-identical (-fmad=false)."""
+    m = mask.astype(bool)
+    diff = np.nonzero(m & (ids_gpu != ids_ref))[0]
+    near = 0
+    if diff.size:
+        for s_ in diff[:1000]:
+            e = int(ids_ref[s_])
+            if e < 0:
+                continue
+            v = om.mesh.coords[om.mesh.elem2verts[e]]
+            tgt = Xnp[:, s_] + dist * Dnp[:, s_]
+            lam = np.linalg.solve((v[1:] - v[0]).T, tgt - v[0])
+            b = np.concatenate([[1.0 - lam.sum()], lam])
+            if np.min(np.abs(b)) < tol:
+                near += 1
+    return {"compared": int(m.sum()), "mismatch": int(diff.size), "near_face": int(near), "epsilon": tol,
+            "against": "reference search_mesh source (oracle/_ref) on the same slots, first +d step"}
 
 
 def main():
@@ -220,6 +308,8 @@ def main():
     ap.add_argument("--ps", default="scs", choices=["dps", "scs", "csr"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-picstep", action="store_true")
+    ap.add_argument("--picstep-steps", type=int, default=10)
     ap.add_argument("--no-graph", action="store_true",
                     help="launch the timed steps eagerly (one event per step) instead of one CUDA graph")
     ap.add_argument("--e2e-parts", type=int, default=8, help="pieces of the pipelined host-buffer step")
@@ -244,38 +334,41 @@ def main():
               "push": "xtgt = x + d*dir, d = L/(3*nelems^(1/3)), sign alternates per step",
               "l2": "inputs (>=0.8 GB of particle columns per step) are larger than the 126 MB L2",
               "particle_structure": a.ps, "loop": a.loop,
+              "note": "the timed loop is the fused push+search on a freshly rebuilt structure (ids seeded from the "
+                      "rows, positions not advanced); the step WITH position update, rebuild and migration is "
+                      "the `picstep` record of the same line",
               "launch": "eager, one CUDA event per step" if a.no_graph else "the K timed steps replayed as one CUDA graph",
               "parallelism": "independent shard per GPU (no exchange in push+search)"}
 
     if a.impl == "reference":
-        # CPU arm: rank 0 only; the reference's own CPU algorithm via the oracle port (the real
-        # Kokkos/Omega_h reference cannot be built here, DESIGN.md "Oracle").
+        # CPU arm: rank 0 only; the reference's own push_ptcls + search_mesh source (oracle/_ref), or
+        # the oracle port where that library is missing.  Nothing of the product library is loaded:
+        # the mesh comes from tests/meshes.py (numpy).
         if rank != 0:
             return 0
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_api as orc
-        pp = importlib.import_module("pumi-pic_b200")
-        m, ppe = build_workload(pp, wl, a.cube_n, a.particles)
-        from meshes import Mesh as TMesh
-        tm = TMesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
+        tm, ppe = numpy_workload(wl, a.cube_n, a.particles)
         om = orc.OracleMesh(tm)
         ref = load_ref_lib()
-        cores = ref.ref_get_max_threads() if ref is not None else orc.lib().orc_get_max_threads()
-        val, ms, cap = cpu_reference_leg(orc, om, wl, tm, ppe, a.cpu_sample, a.steps, a.warmup, ref=ref)
+        cores = host_threads()
+        val, ms, cap, _ = cpu_reference_leg(orc, om, wl, tm, ppe, a.cpu_sample, a.steps, a.warmup, ref=ref,
+                                            loop=a.loop, threads=cores)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores,
                                  "kind": "reference" if ref is not None else "port",
-                                 "sample": "first %d particles of the workload per step; %s"
-                                           % (cap, REF_NOTE if ref is not None else PORT_NOTE)},
+                                 "sample": "first %d particles of the workload per step, %s loop; %s"
+                                           % (cap, a.loop, REF_NOTE if ref is not None else PORT_NOTE)},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
     import torch
     import torch.distributed as dist
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -305,6 +398,10 @@ def main():
                                        elem_ids_empty=False, from_orig=True, sync=sync)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    # the first +d step from the initial positions: its element ids are what `parity` compares with
+    # the reference arm's first step on the same slots
+    P.push_direction_search(gm, ps, dr, d, xa, xb, ids, elem_ids_empty=True, from_orig=True, sync=True)
+    ids_first = ids.cpu().numpy().copy() if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     # seed element ids from the structure rows, then warm up
     P.push_direction_search(gm, ps, dr, 0.0, xa, xb, ids, elem_ids_empty=True, from_orig=True, sync=True)
     A, B = xa, xb
@@ -316,7 +413,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     # The K timed steps are captured once in a CUDA graph (K fused-kernel launches with their
-    # alternating push sign) and replayed by ONE launch: the step is 0.29 ms of GPU work, and with
+    # alternating push sign) and replayed by ONE launch: the step is 0.27 ms of GPU work, and with
     # N ranks sharing the host the Python/ctypes launch path otherwise shows up as gaps between
     # kernels.  --no-graph times the same K launches eagerly with an event after every step.
     stream = torch.cuda.current_stream()
@@ -325,7 +422,6 @@ def main():
         cs = torch.cuda.Stream()
         cs.wait_stream(stream)
         graph = torch.cuda.CUDAGraph()
-        it0, A0, B0 = it, A, B
         with torch.cuda.graph(graph, stream=cs):
             for k in range(a.steps):
                 step(it, A, B); A, B = B, A; it += 1
@@ -334,7 +430,6 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    active_steps = 0
     if sampler:
         sampler.begin()
     if graph is not None:
@@ -360,7 +455,6 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    # stationary population: count live particles once (the oscillation keeps it constant)
     st = P.capi.SearchStats()
     P.capi.check(P.lib().pp_search_last_stats(gm.h, st, None))
     # particles pushed + searched per step: every masked particle in the seeded loop; in the
@@ -376,7 +470,9 @@ def main():
     value = live_all * a.steps / (total_ms * 1e-3)
 
     # ---- end-to-end through the C ABI with HOST (pinned) buffers: H2D of the step's inputs and
-    # D2H of its results inside the timed region.
+    # D2H of its results inside the timed region.  The direction column is an input of the
+    # structure, not of the step: it is uploaded by the first (untimed) call and stays resident
+    # (h_dir = NULL afterwards), as a caller that keeps `dir` on the device between steps would.
     e2e = None
     if not a.no_e2e:
         hx = torch.empty_like(A, device="cpu").pin_memory(); hx.copy_(A)
@@ -390,8 +486,8 @@ def main():
         def e2e_step(k):
             if seeded:
                 # the reference-facing call with HOST buffers: copies and kernel pipelined inside
-                P.push_direction_search_host(gm, ps, hx, hd, ht, hi, d if (it + k) % 2 == 0 else -d,
-                                             nparts=a.e2e_parts, sync=False)
+                P.push_direction_search_host(gm, ps, hx, hd if k == 0 else None, ht, hi,
+                                             d if (it + k) % 2 == 0 else -d, nparts=a.e2e_parts, sync=False)
                 torch.cuda.synchronize()
                 return
             dx.copy_(hx, non_blocking=True); dd.copy_(hd, non_blocking=True)
@@ -417,12 +513,36 @@ def main():
         if world > 1:
             dist.all_reduce(live2, op=dist.ReduceOp.SUM)
         e2e = {"value": float(live2.item()) * e2e_steps / float(et.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(hx.numel() * 8 + hd.numel() * 8 + (0 if seeded else hi.numel() * 4)),
+               "h2d_bytes_per_step": int(hx.numel() * 8 + (0 if seeded else hd.numel() * 8 + hi.numel() * 4)),
                "d2h_bytes_per_step": int(ht.numel() * 8 + hi.numel() * 4),
-               "steps": e2e_steps,
+               "steps": e2e_steps, "host_cpus_bound": numa_cpus,
                "note": ("pp_push_direction_search_host: pinned host buffers, %d pieces, H2D / kernel / D2H "
-                        "overlapped on three streams" % a.e2e_parts) if seeded else
+                        "overlapped on three streams; positions in, targets + element ids out every step; the "
+                        "direction column is uploaded once (untimed first call) and stays resident"
+                        % a.e2e_parts) if seeded else
                        "pinned host buffers, cudaMemcpyAsync H2D -> fused kernel -> D2H per step"}
+        del hx, hd, hi, ht, dx, dd, dt_, di
+
+    # ---- the full PIC step on the same GPUs (BASELINE configs[4]) + parity of the multi-rank loop
+    picstep = None
+    if not a.no_picstep:
+        del xa, xb, dr, ids, A, B
+        graph = None
+        del ps, gm
+        torch.cuda.empty_cache()
+        ps_mod = importlib.import_module("pumi-pic_b200.picstep")
+        comm = P.Comm()
+        picstep = ps_mod.run_picstep(P, comm, rank, world, a.picstep_steps, 3, cube_per_gpu=a.cube_n,
+                                     ppe=max(1, a.particles // (6 * a.cube_n ** 3)))
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        try:
+            import mgpu_worker
+            par = mgpu_worker.pic_loop_parity(P, comm, rank, world, steps=4)
+        except Exception as ex:  # the checker must not take the measurement down with it
+            par = {"error": repr(ex)[:200]}
+        if picstep is not None:
+            picstep["parity"] = par
+        del comm
 
     if rank != 0:
         if world > 1:
@@ -433,11 +553,13 @@ def main():
     kavg_ms = float(np.mean(kernel_ms))
     live_rank0 = live
     achieved = ALGO_BYTES_PER_PARTICLE_STEP * live_rank0 / (kavg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("k_search_dram_bytes_per_launch")
-    cpu = None
+        tj = json.load(open(tpath))
+        traffic = tj.get("k_search_dram_bytes_per_launch")
+        traffic_src = tj.get("source")
+    cpu, parity = None, None
     if not a.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_api as orc
@@ -445,23 +567,27 @@ def main():
         tm = TMesh(3, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
         om = orc.OracleMesh(tm)
         ref = load_ref_lib()
-        cores = ref.ref_get_max_threads() if ref is not None else orc.lib().orc_get_max_threads()
-        val, ms, ncap = cpu_reference_leg(orc, om, wl, tm, ppe, min(a.cpu_sample, 4_000_000), 4, 1, ref=ref)
+        cores = host_threads()
+        # the same slots, positions and directions as the GPU arm (the whole structure), same loop
+        val, ms, ncap, ids_ref = cpu_reference_leg(orc, om, wl, tm, ppe, cap, 3, 1, ref=ref, loop=a.loop,
+                                                   given=(slot_elem, mask, X, D), threads=cores)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "reference" if ref is not None else "port",
-               "sample": "first %d particles of the workload, 4 timed steps after 1 warm-up; %s"
-                         % (ncap, REF_NOTE if ref is not None else PORT_NOTE),
+               "sample": "the GPU arm's own structure (%d slots, %d particles), %s loop, 3 timed steps after 1 "
+                         "warm-up; %s" % (ncap, int(mask.sum()), a.loop, REF_NOTE if ref is not None else PORT_NOTE),
                "ms_per_step": ms}
+        if ids_first is not None and ids_ref is not None:
+            parity = scale_parity(ids_first, ids_ref, mask, om, X, D, d)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": ["k_search<3,BCC,PUSH>", "k_walk_bcc<3,PUSH>", "k_walk_scs<3,PUSH>"][a.walk_kernel]
                                    + " (fused push + walk)",
                          "algorithmic_bytes_per_particle_step": ALGO_BYTES_PER_PARTICLE_STEP,
                          "kernel_ms": kavg_ms, "peak_source": peak_src},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "parity": parity, "picstep": picstep,
             "detail": {"live_particles_per_gpu": live_rank0, "capacity": cap,
                        "walk_iterations_last_step": st.loops, "hops_last_step": int(st.hops),
                        "active_last_step": st.active}}

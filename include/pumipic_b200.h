@@ -495,6 +495,8 @@ pp_status pp_push_direction_search(pp_mesh* mesh, pp_ps* ps, const double* dir, 
  * recommended): xtgt = x + distance*dir, then search_mesh seeded from the structure rows
  * (elem_ids passed empty, adjacency.tpp:504-515), results written back to host arrays.
  *   h_x_orig, h_dir  host [3][stride] in;  h_x_tgt host [3][stride] out;  h_elem_ids host [capacity] out
+ * h_dir may be NULL when the previous call on this mesh uploaded the directions of the same structure
+ * (same capacity): the column stays resident on the device and is not copied again.
  * The slot range is cut into `nparts` pieces at chunk boundaries (Sell-C-sigma, C = 32; other
  * structures run as one piece); host->device copies, the kernel and device->host copies of
  * successive pieces overlap on internal streams.  nparts <= 0 picks a default.  All work is

@@ -1366,6 +1366,8 @@ struct HostPipe {
   int* ids = nullptr;
   int* sched = nullptr;            // [kMaxParts]
   long stride = 0;
+  const void* dir_owner = nullptr; // structure whose direction column hp->dir holds (h_dir == NULL reuses it)
+  int dir_capacity = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t e_begin = nullptr, e_end = nullptr, e_in[kMaxParts], e_k[kMaxParts];
   std::vector<int> chunk_start;
@@ -1394,6 +1396,7 @@ pp_status hostpipe_get(pp_mesh* mesh, long stride, HostPipe** out) {
     PP_CUDA(cudaMalloc((void**)&hp->xt, 3 * stride * sizeof(double)));
     PP_CUDA(cudaMalloc((void**)&hp->ids, stride * sizeof(int)));
     hp->stride = stride;
+    hp->dir_owner = nullptr;
   }
   *out = hp;
   return PP_OK;
@@ -1417,7 +1420,7 @@ extern "C" pp_status pp_push_direction_search_host(pp_mesh* mesh, pp_ps* ps, con
                                                    double distance, int32_t looplimit,
                                                    int32_t nparts, pp_search_stats* stats_host,
                                                    pp_stream stream) {
-  PP_REQUIRE(mesh && ps && h_x_orig && h_dir && h_x_tgt && h_elem_ids, "null argument");
+  PP_REQUIRE(mesh && ps && h_x_orig && h_x_tgt && h_elem_ids, "null argument");
   PP_REQUIRE(stride >= ps->capacity, "stride smaller than capacity");
   PP_REQUIRE(ps->nelems == mesh->nelems, "particle structure and mesh disagree on nelems");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1430,6 +1433,10 @@ extern "C" pp_status pp_push_direction_search_host(pp_mesh* mesh, pp_ps* ps, con
   PP_TRY(hostpipe_get(mesh, stride, &hp));
   const long dstride = hp->stride;
   const int cap = ps->capacity;
+  // h_dir == NULL: the direction column uploaded by the previous call for this structure stays
+  PP_REQUIRE(h_dir || (hp->dir_owner == (const void*)ps && hp->dir_capacity == cap),
+             "h_dir may only be NULL after a call that uploaded the directions of this structure");
+  if (h_dir) { hp->dir_owner = ps; hp->dir_capacity = cap; }
   pp_search_args a;
   a.variant = PP_SEARCH_NEW;
   a.x_orig = hp->x; a.x_tgt = hp->xt; a.stride = dstride;
@@ -1463,8 +1470,9 @@ extern "C" pp_status pp_push_direction_search_host(pp_mesh* mesh, pp_ps* ps, con
       for (int k = 0; k < 3; ++k) {
         PP_CUDA(cudaMemcpyAsync(hp->x + k * dstride + lo, h_x_orig + k * stride + lo, n * sizeof(double),
                                 cudaMemcpyHostToDevice, hp->s_in));
-        PP_CUDA(cudaMemcpyAsync(hp->dir + k * dstride + lo, h_dir + k * stride + lo, n * sizeof(double),
-                                cudaMemcpyHostToDevice, hp->s_in));
+        if (h_dir)
+          PP_CUDA(cudaMemcpyAsync(hp->dir + k * dstride + lo, h_dir + k * stride + lo, n * sizeof(double),
+                                  cudaMemcpyHostToDevice, hp->s_in));
       }
     PP_CUDA(cudaEventRecord(hp->e_in[i], hp->s_in));
   }

@@ -1,0 +1,160 @@
+"""The full PIC step on N PICparts (BASELINE configs[4]), shared by bench.py and tools/bench_picstep.py.
+
+Global mesh: a Kuhn cube whose elements are owned by bx*by*bz blocks (one PICpart core per GPU,
+~6*cube^3 tets each).  PICparts follow the reference's defaults (pumipic_input.cpp:103-110): BFS
+buffer with 3 layers, BFS safe zone with 1 layer.  With 2x2x2 blocks every core comes within three
+layers of every other, whole cores are buffered (part_construct.cpp:407-437), so every rank holds
+the full mesh and the ghost reduction is the all-reduce branch of Mesh::reduceCommArray
+(pumipic_comm.cpp:234-247).
+
+One step = the loop body of test/pseudoPushAndSearch.cpp:513-542 with the migration of
+src/pumipic_ptcl_ops.hpp:73-85 and the field synchronisation of test/gyroScatter.hpp:231-258:
+    fused push + search_mesh  ->  updatePtclPositions  ->  setUnsafeProcs
+    ->  migrate (pp_ps_migrate over pp_comm: exchange + rebuild)  ->  comm-array all-reduce
+Timed with CUDA events per phase on the current stream; the step time is the max over ranks.
+"""
+import importlib
+
+import numpy as np
+
+MEMBERS = [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float64, 3)]
+PHASES = ["push+search", "updatePtclPositions", "setUnsafeProcs", "migrate", "comm array reduce"]
+
+
+def block_owner(coords, ev, R):
+    """owner rank of every element: centroid -> block of a bx*by*bz grid"""
+    bx = 2 if R >= 2 else 1
+    by = 2 if R >= 4 else 1
+    bz = 2 if R >= 8 else 1
+    cen = coords[ev].mean(axis=1)
+    own = ((cen[:, 0] * bx).astype(np.int64).clip(0, bx - 1)
+           + bx * ((cen[:, 1] * by).astype(np.int64).clip(0, by - 1)
+                   + by * (cen[:, 2] * bz).astype(np.int64).clip(0, bz - 1)))
+    return (own % R).astype(np.int32)
+
+
+class PicStep:
+    def __init__(self, P, comm, rank, R, cube_per_gpu=55, ppe=10, push_mult=3.0, seed=1234):
+        import torch
+        self.P, self.comm, self.rank, self.R, self.torch = P, comm, rank, R, torch
+        n = cube_per_gpu
+        N = int(round(n * R ** (1.0 / 3.0)))
+        coords, ev = P.host_kuhn_cube(N, 1.0)
+        e2s, s2v = P.host_derive_sides(3, ev)
+        ne = ev.shape[0]
+        owner = block_owner(coords, ev, R)
+        safe, part = P.host_picpart_tags(3, coords.shape[0], ev, owner, R, rank, P.api.BFS, P.api.BFS, 3, 1)
+        assert part.all(), "block PICparts of this size buffer every core (full mesh on every rank)"
+        self.gm = P.Mesh(3, coords, ev, e2s, s2v, np.ones(ne, np.int32))
+        self.gm.set_picpart(safe, owner, rank)
+        ppe_arr = np.where(owner == rank, ppe, 0).astype(np.int32)
+        self.ps = ps = P.ParticleStructure(P.capi.PP_PS_SCS, MEMBERS, ppe_arr,
+                                           elem_gids=np.arange(ne, dtype=np.int64))
+        cap = ps.capacity
+        lay = ps.layout()
+        se = P.api._tensor_from_ptr(lay.slot_elem, (cap,), torch.int32, ps).long().clamp(0, ne - 1)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed + rank)
+        w = -torch.log(torch.rand(cap, 4, device="cuda", dtype=torch.float64, generator=g).clamp_min(1e-12))
+        w = w / w.sum(dim=1, keepdim=True)
+        evd = torch.as_tensor(ev).cuda().long()
+        cod = torch.as_tensor(coords).cuda()
+        pos = (cod[evd[se]] * w[:, :, None]).sum(dim=1)
+        for k in range(3):
+            ps.get(0)[k, :cap] = pos[:, k]
+        d = torch.randn(cap, 3, device="cuda", dtype=torch.float64, generator=g)
+        d = d / d.norm(dim=1, keepdim=True)
+        for k in range(3):
+            ps.get(3)[k, :cap] = d[:, k]
+        ps.get(2)[0, :cap] = torch.arange(cap, dtype=torch.int32, device="cuda")
+        del w, evd, cod, pos, d, se
+        self.push = push_mult * 1.0 / (3 * ne ** (1.0 / 3))
+        self.nverts = coords.shape[0]
+        self.ne = ne
+        self.tets_per_gpu = ne // R
+        self.charge = torch.zeros(2 * self.nverts, dtype=torch.float64, device="cuda")
+
+    def step(self, rec=None):
+        """one PIC step; rec: dict phase -> list of (start, stop) events, or None"""
+        P, ps, gm, torch = self.P, self.ps, self.gm, self.torch
+
+        def timed(name, fn):
+            if rec is None:
+                return fn()
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            rec[name].append((a, b))
+            return r
+
+        x, tg, dr = ps.get(0), ps.get(1), ps.get(3)
+        ids = torch.empty(max(ps.capacity, 1), dtype=torch.int32, device="cuda")
+        timed("push+search", lambda: P.push_direction_search(gm, ps, dr, self.push, x, tg, ids, elem_ids_empty=True,
+                                                            from_orig=True, sync=False))
+        timed("updatePtclPositions", lambda: P.update_positions(ps, x, tg))
+        ne_d, np_d = timed("setUnsafeProcs", lambda: P.set_unsafe_procs(gm, ps, ids))
+        sent, recv = timed("migrate", lambda: P.migrate(ps, self.comm, ne_d, np_d))
+        timed("comm array reduce", lambda: self.comm.array_reduce(self.charge, self.nverts, 2, P.capi.PP_SUM))
+        return sent, recv
+
+    def run(self, steps, warmup, barrier=None):
+        """-> dict with per-rank timings (ms) of `steps` timed steps"""
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        torch.cuda.synchronize()
+        n_start = self.ps.nptcls
+        rec = {k: [] for k in PHASES}
+        step_ev, sent_tot = [], 0
+        for _ in range(steps):
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record()
+            sent, _ = self.step(rec)
+            b.record()
+            step_ev.append((a, b))
+            sent_tot += sent
+        torch.cuda.synchronize()
+        return {"step_ms_total": float(sum(a.elapsed_time(b) for a, b in step_ev)),
+                "phase_ms_median": {k: float(np.median([a.elapsed_time(b) for a, b in v])) for k, v in rec.items()},
+                "particles_start": int(n_start), "particles_end": int(self.ps.nptcls), "sent": int(sent_tot)}
+
+
+def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_mult=3.0):
+    """Collective over the ranks of torch.distributed (when R > 1).  Returns the record on rank 0."""
+    import torch
+    import torch.distributed as dist
+    ps = PicStep(P, comm, rank, R, cube_per_gpu, ppe, push_mult)
+    r = ps.run(steps, warmup, barrier=(dist.barrier if R > 1 else None))
+    t = torch.tensor([r["step_ms_total"]] + [r["phase_ms_median"][k] for k in PHASES], dtype=torch.float64,
+                     device="cuda")
+    cnt = torch.tensor([float(r["particles_start"]), float(r["sent"]), float(r["particles_end"])],
+                       dtype=torch.float64, device="cuda")
+    if R > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    tot_ms = float(t[0].item())
+    # algorithmic bytes of the full step per particle: push 49 + search 53 + mesh 7 +
+    # position update 72 + setUnsafeProcs 4 + rebuild 110
+    full_step_bytes = 295.0
+    out = {"workload": "full PIC step (push, search, updatePtclPositions, setUnsafeProcs, migrate over pp_comm "
+                       "[NCCL all-to-all-v + rebuild], comm-array all-reduce), block-partitioned Kuhn cube, "
+                       "BFS 3-layer buffer / 1-layer safe zone, %d particles and %d tets per GPU"
+                       % (ppe * ps.tets_per_gpu, ps.tets_per_gpu),
+           "n_gpus": R, "steps": steps, "warmup": warmup, "tets_global": int(ps.ne),
+           "particles_global_start": cnt[0].item(), "particles_global_end": cnt[2].item(),
+           "migrated_per_step": cnt[1].item() / steps,
+           "ms_per_step": tot_ms / steps,
+           "value": cnt[0].item() * steps / (tot_ms * 1e-3), "unit": "particle full-steps/s",
+           "phase_ms": {k: float(t[1 + i].item()) for i, k in enumerate(PHASES)},
+           "algorithmic_bytes_per_particle_step": full_step_bytes,
+           "achieved_GBs_per_gpu": full_step_bytes * cnt[0].item() / R / (tot_ms / steps * 1e-3) / 1e9,
+           "scaling": "weak", "timing": "CUDA events, max over ranks; phases: median over steps, max over ranks"}
+    del ps
+    torch.cuda.empty_cache()
+    return out

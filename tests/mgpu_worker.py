@@ -149,8 +149,11 @@ def test_comm_array(P, comm, rank, R):
         print("comm arrays ok on %d ranks" % R)
 
 
-def test_pic_loop(P, comm, rank, R, steps=6):
-    n = 8
+def pic_loop_parity(P, comm, rank, R, steps=6, n=8, nptcl=40000):
+    """The multi-rank PIC loop (fused push+search -> updatePtclPositions -> setUnsafeProcs -> migrate)
+    on a block-partitioned Kuhn cube against the serial CPU oracle on the whole particle set, by
+    particle id.  Returns mismatch counts (all ranks return the same dict); also called by bench.py's
+    `picstep` leg as the in-run checker."""
     mesh = kuhn_cube(n)
     ne = mesh.nelems
     # block partition along x (and y for R >= 4): element centroid decides the owner
@@ -166,7 +169,6 @@ def test_pic_loop(P, comm, rank, R, steps=6):
     gm = P.Mesh(3, mesh.coords, mesh.elem2verts, mesh.elem2sides, mesh.side2verts, mesh.class_id)
     gm.set_picpart(safe, owner, rank)
     # global particle set (identical on every rank), each rank keeps those in its own core
-    nptcl = 40000
     ppe_g = pi.even_ppe(ne, nptcl)
     slot_elem_g = np.repeat(np.arange(ne, dtype=np.int32), ppe_g)
     mask_g = np.ones(nptcl, np.uint8)
@@ -182,6 +184,8 @@ def test_pic_loop(P, comm, rank, R, steps=6):
     # serial oracle on the whole set
     om = orc.OracleMesh(mesh)
     Xo = X.copy(); ids_o = None
+    out = {"ranks": R, "steps": steps, "particles": nptcl, "duplicated": 0, "missing_or_extra": 0,
+           "mismatch_element": 0, "mismatch_position": 0, "on_unsafe_rank": 0, "migrated": 0}
     for it in range(steps):
         cap = ps.capacity
         x, tg, pid, dr = ps.get(0), ps.get(1), ps.get(2), ps.get(3)
@@ -189,7 +193,7 @@ def test_pic_loop(P, comm, rank, R, steps=6):
         P.push_direction_search(gm, ps, dr, dist_push, x, tg, ids, elem_ids_empty=True, from_orig=True)
         P.update_positions(ps, x, tg)
         ne_d, np_d = P.set_unsafe_procs(gm, ps, ids)
-        P.migrate(ps, comm, ne_d, np_d)
+        sent, _ = P.migrate(ps, comm, ne_d, np_d)
         # oracle step
         To = Xo + dist_push * D
         found, ids_o, _, _, st = om.search_mesh(slot_elem_g if ids_o is None else np.maximum(ids_o, 0),
@@ -200,21 +204,37 @@ def test_pic_loop(P, comm, rank, R, steps=6):
         se, m = ps.slot_elem_and_mask(); m = m.astype(bool)
         pids = ps.get(2).cpu().numpy()[0, :ps.capacity][m]
         xs = ps.get(0).cpu().numpy()[:, :ps.capacity][:, m]
+        unsafe_here = int(np.sum(~((safe[se[m]] == 1) | (owner[se[m]] == rank))))
         got = {}
-        for d in gather_np((pids, se[m], xs)):
+        parts = gather_np((pids, se[m], xs, unsafe_here, sent)) if R > 1 else [(pids, se[m], xs, unsafe_here, sent)]
+        for d in parts:
+            out["on_unsafe_rank"] += d[3]
+            out["migrated"] += d[4]
             for i, e, xx in zip(d[0].tolist(), d[1].tolist(), d[2].T):
-                assert i not in got, "particle %d lives on two ranks" % i
+                if i in got:
+                    out["duplicated"] += 1
                 got[i] = (e, xx)
         alive = np.nonzero(ids_o >= 0)[0]
-        assert sorted(got) == alive.tolist(), "particle set differs from the serial oracle"
-        for i in alive[:: max(1, len(alive) // 3000)]:
-            assert got[i][0] == ids_o[i] and np.array_equal(got[i][1], Xo[:, i])
-        # after migration every particle sits on a rank where its element is safe... its owner
-        # if it was unsafe; check it is at least buffered+safe or owned here
-        assert np.all((safe[se[m]] == 1) | (owner[se[m]] == rank))
+        out["missing_or_extra"] += len(set(got).symmetric_difference(alive.tolist()))
+        for i in alive:
+            g = got.get(int(i))
+            if g is None:
+                continue
+            out["mismatch_element"] += int(g[0] != ids_o[i])
+            out["mismatch_position"] += int(not np.array_equal(g[1], Xo[:, i]))
+    out["alive_at_end"] = int(len(alive))
+    out["mismatch"] = (out["duplicated"] + out["missing_or_extra"] + out["mismatch_element"]
+                       + out["mismatch_position"] + out["on_unsafe_rank"])
+    return out
+
+
+def test_pic_loop(P, comm, rank, R, steps=6):
+    r = pic_loop_parity(P, comm, rank, R, steps)
+    assert r["mismatch"] == 0, r
+    assert R == 1 or r["migrated"] > 0
     if rank == 0:
-        print("PIC loop parity ok on %d ranks: %d of %d particles still in the domain"
-              % (R, len(alive), nptcl))
+        print("PIC loop parity ok on %d ranks: %d of %d particles still in the domain, %d migrations"
+              % (R, r["alive_at_end"], r["particles"], r["migrated"]))
 
 
 def test_partial_picparts(P, comm, rank, R, steps=6):
@@ -384,6 +404,9 @@ def test_balancer(P, comm, rank, R):
 
 
 def main():
+    import faulthandler
+    import signal
+    faulthandler.register(signal.SIGUSR1, all_threads=True)   # `timeout -s USR1` prints where a rank hangs
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     R = int(os.environ.get("WORLD_SIZE", "1"))

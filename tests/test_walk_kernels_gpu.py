@@ -186,8 +186,10 @@ def test_host_buffer_pipeline_matches_oracle(kind, nparts):
     hx = t.as_tensor(X).pin_memory(); hd = t.as_tensor(D).pin_memory()
     ht = t.zeros_like(hx).pin_memory()
     hi = t.full((ps.capacity,), -9, dtype=t.int32).pin_memory()
-    for rep in range(2):                           # second call reuses the staging buffers
-        r = P.push_direction_search_host(gm, ps, hx, hd, ht, hi, dist, nparts=nparts)
+    for rep in range(3):                           # later calls reuse the staging buffers; the third
+        # one also the direction column already on the device (h_dir = NULL)
+        ht.zero_(); hi.fill_(-9)
+        r = P.push_direction_search_host(gm, ps, hx, hd if rep < 2 else None, ht, hi, dist, nparts=nparts)
         t.cuda.synchronize()
         T = np.zeros_like(X)
         T[:, m] = X[:, m] + dist * D[:, m]
@@ -196,6 +198,10 @@ def test_host_buffer_pipeline_matches_oracle(kind, nparts):
         assert np.array_equal(ht.numpy()[:, m], T[:, m])
         assert (r.found, r.loops, r.not_in_elem) == (int(found), st.loops, st.not_in_elem)
         assert r.active == int(m.sum())
+    # a structure whose directions were never uploaded must be refused
+    ps2 = make_ps(_kind(kind), _uneven_ppe(mesh.nelems, 1000))
+    with pytest.raises(P.PumipicError):
+        P.push_direction_search_host(gm, ps2, hx, None, ht, hi, dist, nparts=nparts)
 
 
 @pytest.mark.parametrize("variant", [2, 1, 0])
