@@ -569,6 +569,17 @@ pp_status pp_gyro_interleave(const double* fwd, const double* bkwd, int32_t nver
 pp_status pp_comm_unique_id(uint8_t id_out[128]);
 pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t id[128], pp_comm** out);
 pp_status pp_comm_destroy(pp_comm* comm);
+/* Migration transport.  Default: a peer-memory window per rank (cudaMalloc + CUDA IPC, mapped into every
+ * peer by the first pp_ps_migrate of the communicator, collectively): the pack kernel stores the leaving
+ * particles straight into the destination GPU's memory over NVLink, counts and a step flag follow, the
+ * receiver's kernels wait on the flag -- no NCCL call, no host round trip in the step.  pp_comm_set_p2p(0)
+ * (process-wide, before the first migration) or a failed IPC mapping selects the NCCL path (AllGather of
+ * counts + grouped Send/Recv).  pp_comm_set_p2p_window sizes the window's segment per (sender, step
+ * parity) in bytes (default 24 MiB, about 260 000 particles of 76 bytes); pp_comm_p2p_active tells which
+ * path the communicator ended up with. */
+void pp_comm_set_p2p(int32_t enable);
+pp_status pp_comm_set_p2p_window(pp_comm* comm, int64_t bytes_per_peer);
+int32_t pp_comm_p2p_active(const pp_comm* comm);
 int32_t pp_comm_size(const pp_comm* comm);
 int32_t pp_comm_rank(const pp_comm* comm);
 
@@ -620,6 +631,8 @@ pp_status pp_comm_plan_reduce(pp_comm_plan* plan, void* comm_array, int32_t nval
  * place exactly like the reference (sent particles become -1).  World distributor only. */
 typedef struct pp_migrate_stats {
   int64_t sent, received;
+  int64_t deferred;   /* peer-memory path: particles that did not fit the destination's window segment and
+                       * stay on this rank (still unsafe) until the next migration; 0 in normal operation */
 } pp_migrate_stats;
 pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_element,
                         const int32_t* new_process, int32_t n_new,

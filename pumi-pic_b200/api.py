@@ -719,6 +719,15 @@ class Comm:
                                          _ptr(ent_owner), _stream()))
         return arr
 
+    def set_p2p_window(self, bytes_per_peer):
+        """size of the peer-memory window's segments; before the first migration"""
+        check(lib().pp_comm_set_p2p_window(self.h, int(bytes_per_peer)))
+
+    @property
+    def p2p_active(self):
+        """True once the first migration has mapped the peer-memory windows (NVLink path)"""
+        return bool(lib().pp_comm_p2p_active(self.h))
+
     def plan(self, ent_gids, ent_owner):
         """Owner fan-in / fan-out plan for comm arrays of a partially buffered PICpart."""
         return CommPlan(self, ent_gids, ent_owner)

@@ -87,7 +87,7 @@ class PicpartDim(C.Structure):
 
 
 class MigrateStats(C.Structure):
-    _fields_ = [("sent", C.c_int64), ("received", C.c_int64)]
+    _fields_ = [("sent", C.c_int64), ("received", C.c_int64), ("deferred", C.c_int64)]
 
 
 PP_INT32, PP_INT64, PP_FLOAT32, PP_FLOAT64 = 0, 1, 2, 3
@@ -163,6 +163,9 @@ PROTOTYPES = {
     "pp_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pp_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "pp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pp_comm_set_p2p": (None, [C.c_int32]),
+    "pp_comm_set_p2p_window": (C.c_int, [C.c_void_p, C.c_int64]),
+    "pp_comm_p2p_active": (C.c_int32, [C.c_void_p]),
     "pp_comm_size": (C.c_int32, [C.c_void_p]),
     "pp_comm_rank": (C.c_int32, [C.c_void_p]),
     "pp_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,

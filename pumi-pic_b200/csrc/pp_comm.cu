@@ -73,9 +73,42 @@ pp_status load_nccl() {
   } while (0)
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// Peer-memory window of the migration (NVLink / NVSwitch, no NCCL and no host in the step).
+// Every rank owns one cudaMalloc'ed window: a header and, for both parities of the step counter,
+// one fixed-size segment per sender.  The windows are mapped into every peer with CUDA IPC once.
+// A migration then is: pack kernel stores each leaving particle's record straight into the
+// destination rank's segment (P2P stores), a publish kernel writes the per-peer counts and the
+// step number into the destinations' headers, a wait kernel spins on this rank's own header until
+// every sender has published, an unpack kernel turns the received records into the rebuild's
+// new-particle arrays -- and the number of received particles never leaves the device (the rebuild
+// takes it from device memory).  Segments are double-buffered by step parity: a sender can only
+// reach step e after it has seen every peer's flag of step e-1, which that peer wrote after it
+// finished unpacking step e-2, so a segment is never overwritten while it is still being read.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 64;
+struct P2PHeader {
+  int counts[2][kMaxRanks];        // [parity][sender]: particles the sender put into its segment
+  unsigned flags[2][kMaxRanks];    // [parity][sender]: step in which the sender finished writing
+};
+struct P2PPeers { char* win[kMaxRanks]; };
+struct P2PWindow {
+  bool tried = false, ok = false;
+  size_t seg_bytes = 24u << 20;    // per (sender, parity)
+  char* local = nullptr;
+  P2PPeers peers;
+  int* dev = nullptr;              // cursor[R] | overflow | err | n_in | n_total | recv_off[R+1] | recv_cnt[R]
+  long long* host_stats = nullptr; // pinned: sent, received, deferred, err
+  long long* dev_stats = nullptr;
+  cudaEvent_t ev = nullptr;
+  unsigned epoch = 0;
+};
+int g_p2p_enable = 1;
+
 struct pp_comm {
   ncclComm_t comm;
   int nranks, rank;
+  P2PWindow p2p;
 };
 
 extern "C" pp_status pp_comm_unique_id(uint8_t id_out[128]) {
@@ -91,6 +124,7 @@ extern "C" pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t 
   PP_REQUIRE(out && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
   pp_comm* c = new pp_comm();
   c->comm = nullptr; c->nranks = nranks; c->rank = rank;
+  for (int p = 0; p < kMaxRanks; ++p) c->p2p.peers.win[p] = nullptr;
   if (nranks > 1) {
     PP_REQUIRE(id, "a unique id is required for more than one rank");
     PP_TRY(load_nccl());
@@ -121,6 +155,14 @@ extern "C" pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t 
 
 extern "C" pp_status pp_comm_destroy(pp_comm* c) {
   if (!c) return PP_OK;
+  if (c->p2p.local) {
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->nranks; ++p)
+      if (p != c->rank && c->p2p.peers.win[p]) cudaIpcCloseMemHandle(c->p2p.peers.win[p]);
+    cudaFree(c->p2p.local); cudaFree(c->p2p.dev); cudaFree(c->p2p.dev_stats);
+    if (c->p2p.host_stats) cudaFreeHost(c->p2p.host_stats);
+    if (c->p2p.ev) cudaEventDestroy(c->p2p.ev);
+  }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   delete c;
   return PP_OK;
@@ -235,12 +277,13 @@ extern "C" pp_status pp_comm_array_reduce(pp_comm* c, void* comm_array, int64_t 
 // migrate (SCS_migrate.h:5-221, identical algorithm in CSR_migrate.hpp / dps / cabm)
 // ------------------------------------------------------------------------------------------
 namespace {
-__global__ void k_count_dest(PsView v, const int* __restrict__ new_proc, int self, int nranks, int* cnt) {
+__global__ void k_count_dest(PsView v, const int* __restrict__ new_proc, const int* __restrict__ new_elem,
+                             int self, int nranks, int* cnt) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   int dest = -1;
   if (s < v.capacity && ((__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u)) {
     const int p = new_proc[s];
-    if (p != self && p >= 0 && p < nranks) dest = p;
+    if (p != self && p >= 0 && p < nranks && new_elem[s] >= 0) dest = p;   // deleted particles are not sent
   }
   const unsigned grp = __match_any_sync(0xffffffffu, dest);
   if (dest >= 0 && (threadIdx.x & 31) == (__ffs(grp) - 1)) atomicAdd(cnt + dest, __popc(grp));
@@ -273,6 +316,7 @@ __global__ void k_pack(PsView v, const int* __restrict__ new_proc, int* new_elem
   const int p = new_proc[s];
   if (p == self || p < 0 || p >= nranks) return;
   const int e = new_elem[s];
+  if (e < 0) return;                       // deleted by the caller: dropped here, not sent
   const int i = atomicAdd(cursor + p, 1);
   const size_t n = (size_t)send_cnt[p];
   char* blk = sendbuf + peer_byte_off[p];
@@ -344,6 +388,320 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
                                    const int32_t* new_particle_elements,
                                    const void* const* new_particle_info, pp_stream stream_);
 
+// ------------------------------------------------------------------------------------------
+// migration over the peer-memory window
+// ------------------------------------------------------------------------------------------
+namespace {
+// layout of the window's device scratch (ints)
+struct P2PScratch {
+  int* cursor; int* overflow; int* err; int* n_in; int* n_total; int* recv_off; int* recv_cnt;
+};
+P2PScratch p2p_scratch(int* base, int R) {
+  P2PScratch x;
+  x.cursor = base; x.overflow = base + R; x.err = x.overflow + 1; x.n_in = x.err + 1; x.n_total = x.n_in + 1;
+  x.recv_off = x.n_total + 1; x.recv_cnt = x.recv_off + R + 1;
+  return x;
+}
+__host__ __device__ inline size_t p2p_rec_bytes(const PackTable& t) {
+  size_t b = 8;
+  for (int k = 0; k < t.n; ++k) b += align8((size_t)t.bytes[k] * t.ncomp[k]);
+  return b;
+}
+__host__ __device__ inline size_t p2p_seg_offset(int parity, int sender, int R, size_t seg_bytes) {
+  return sizeof(P2PHeader) + ((size_t)parity * R + sender) * seg_bytes;
+}
+
+// record of one particle: int64 gid | member 0 components | member 1 ... (members 8-byte aligned)
+__global__ void k_p2p_pack(PsView v, const int* __restrict__ new_proc, int* new_elem,
+                           const long long* __restrict__ elem_gids, int self, int nranks, int* cursor,
+                           int* overflow, P2PPeers peers, int parity, size_t seg_bytes, int seg_cap,
+                           int rec_bytes, PackTable t, long stride) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.capacity) return;
+  if (!((__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u)) return;
+  const int p = new_proc[s];
+  if (p == self || p < 0 || p >= nranks) return;
+  const int e = new_elem[s];
+  if (e < 0) return;                       // deleted by the caller: dropped here, not sent
+  const int i = atomicAdd(cursor + p, 1);
+  if (i >= seg_cap) { atomicAdd(overflow, 1); return; }   // no room: stays on this rank this step
+  char* rec = peers.win[p] + p2p_seg_offset(parity, self, nranks, seg_bytes) + (size_t)i * rec_bytes;
+  *(long long*)rec = elem_gids ? elem_gids[e] : (long long)e;
+  size_t off = 8;
+  for (int k = 0; k < t.n; ++k) {
+    const int sb = t.bytes[k];
+    for (int c = 0; c < t.ncomp[k]; ++c) {
+      const char* a = t.src[k] + ((size_t)c * stride + s) * sb;
+      char* b = rec + off + (size_t)c * sb;
+      if (sb == 8) *(double*)b = *(const double*)a;
+      else if (sb == 4) *(int*)b = *(const int*)a;
+      else for (int q = 0; q < sb; ++q) b[q] = a[q];
+    }
+    off += align8((size_t)sb * t.ncomp[k]);
+  }
+  new_elem[s] = -1;                        // removeSentParticles (SCS_migrate.h:190-196)
+}
+// after the pack kernel has completed (its stores have landed): counts, then the step flag
+__global__ void k_p2p_publish(const int* __restrict__ cursor, const int* __restrict__ overflow, int nranks,
+                              int self, P2PPeers peers, int parity, unsigned epoch, int seg_cap,
+                              long long* stats) {
+  const int p = threadIdx.x;
+  __shared__ long long sent;
+  if (p == 0) sent = 0;
+  __syncthreads();
+  if (p < nranks && p != self) {
+    const int cnt = min(cursor[p], seg_cap);
+    atomicAdd((unsigned long long*)&sent, (unsigned long long)cnt);
+    P2PHeader* h = reinterpret_cast<P2PHeader*>(peers.win[p]);
+    *(volatile int*)&h->counts[parity][self] = cnt;
+    __threadfence_system();
+    *(volatile unsigned*)&h->flags[parity][self] = epoch;
+  }
+  __syncthreads();
+  if (p == 0) { stats[0] = sent; stats[2] = *overflow; }
+}
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin on this rank's header until every sender has published step `epoch`
+__global__ void k_p2p_wait(P2PHeader* local_hdr, int nranks, int self, int parity, unsigned epoch,
+                           int* recv_cnt, int* recv_off, int* n_in, int* n_total, int n_user, int* err,
+                           long long* stats) {
+  __shared__ int cnt[kMaxRanks];
+  const int p = threadIdx.x;
+  if (p < nranks) {
+    int c = 0;
+    if (p != self) {
+      const unsigned long long t0 = p2p_now_ns();
+      bool ok = true;
+      while (*(volatile unsigned*)&local_hdr->flags[parity][p] != epoch) {
+        if (p2p_now_ns() - t0 > 20000000000ull) { ok = false; break; }     // 20 s: a peer is gone
+        __nanosleep(200);
+      }
+      __threadfence_system();
+      if (ok) c = *(volatile int*)&local_hdr->counts[parity][p];
+      else atomicExch(err, 1);
+    }
+    cnt[p] = c;
+  }
+  __syncthreads();
+  if (p == 0) {
+    int tot = 0;
+    for (int r = 0; r < nranks; ++r) { recv_cnt[r] = cnt[r]; recv_off[r] = tot; tot += cnt[r]; }
+    recv_off[nranks] = tot;
+    *n_in = tot;
+    *n_total = tot + n_user;
+    stats[1] = tot;
+    stats[3] = *err;
+  }
+}
+// received records -> [ncomp][ld] member arrays + local element ids (grid-stride, count on device)
+__global__ void k_p2p_unpack(const char* __restrict__ win, int parity, int nranks, size_t seg_bytes,
+                             int rec_bytes, const int* __restrict__ recv_off, const int* __restrict__ n_in,
+                             long ld, PackTable t, char* const* dst, const long long* __restrict__ sorted_gid,
+                             const int* __restrict__ sorted_lid, int ne, int* elems_out) {
+  const int n = *n_in;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    int p = 0;
+    while (p + 1 < nranks && recv_off[p + 1] <= j) ++p;
+    const char* rec = win + p2p_seg_offset(parity, p, nranks, seg_bytes) + (size_t)(j - recv_off[p]) * rec_bytes;
+    const long long gid = *(const long long*)rec;
+    int lid = -1;
+    if (sorted_gid) {                    // gid -> lid (replaces Kokkos::UnorderedMap, SCS_migrate.h:181-187)
+      int lo = 0, hi = ne - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const long long g = sorted_gid[mid];
+        if (g == gid) { lid = sorted_lid[mid]; break; }
+        if (g < gid) lo = mid + 1; else hi = mid - 1;
+      }
+    } else if (gid >= 0 && gid < ne) {
+      lid = (int)gid;
+    }
+    elems_out[j] = lid;                  // -1 (unknown gid) makes the rebuild fail with an error
+    size_t off = 8;
+    for (int k = 0; k < t.n; ++k) {
+      const int sb = t.bytes[k];
+      for (int c = 0; c < t.ncomp[k]; ++c) {
+        const char* a = rec + off + (size_t)c * sb;
+        char* b = dst[k] + ((size_t)c * ld + j) * sb;
+        if (sb == 8) *(double*)b = *(const double*)a;
+        else if (sb == 4) *(int*)b = *(const int*)a;
+        else for (int q = 0; q < sb; ++q) b[q] = a[q];
+      }
+      off += align8((size_t)sb * t.ncomp[k]);
+    }
+  }
+}
+// the caller's own new particles follow the received ones
+__global__ void k_p2p_append(const int* __restrict__ n_in, int n_user, const int* __restrict__ user_elems,
+                             PackTable user, long ld, char* const* dst, int* elems_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_user) return;
+  const long at = (long)*n_in + j;
+  elems_out[at] = user_elems[j];
+  for (int k = 0; k < user.n; ++k) {
+    const int sb = user.bytes[k];
+    for (int c = 0; c < user.ncomp[k]; ++c) {
+      const char* a = user.src[k] + ((size_t)c * n_user + j) * sb;
+      char* b = dst[k] + ((size_t)c * ld + at) * sb;
+      for (int q = 0; q < sb; ++q) b[q] = a[q];
+    }
+  }
+}
+
+// one-time, collective: allocate this rank's window, exchange IPC handles, map the peers
+pp_status p2p_setup(pp_comm* c, cudaStream_t s) {
+  P2PWindow& w = c->p2p;
+  w.tried = true;
+  const int R = c->nranks, me = c->rank;
+  const char* env = getenv("PUMIPIC_P2P");            // PUMIPIC_P2P=0: NCCL path (A/B, tests)
+  int ok = (R <= kMaxRanks && g_p2p_enable && !(env && env[0] == '0')) ? 1 : 0;
+  const size_t bytes = sizeof(P2PHeader) + 2 * (size_t)R * w.seg_bytes;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    if (cudaMalloc((void**)&w.local, bytes) != cudaSuccess) { ok = 0; w.local = nullptr; cudaGetLastError(); }
+  }
+  if (ok) {
+    PP_CUDA(cudaMemset(w.local, 0, sizeof(P2PHeader)));
+    if (cudaIpcGetMemHandle(&mine, w.local) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  // handles (and whether this rank got that far) to everybody
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  static_assert(sizeof(Msg) % 8 == 0, "message size");
+  Msg m; m.h = mine; m.ok = ok; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+  Msg *d_one, *d_all;
+  PP_TRY(pp_dev_alloc(&d_one, 1, s));
+  PP_TRY(pp_dev_alloc(&d_all, (size_t)R, s));
+  PP_CUDA(cudaMemcpyAsync(d_one, &m, sizeof(Msg), cudaMemcpyHostToDevice, s));
+  PP_NCCL(g_nccl.AllGather(d_one, d_all, sizeof(Msg), ncclUint8, c->comm, s));
+  std::vector<Msg> all((size_t)R);
+  PP_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Msg) * R, cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  for (int p = 0; p < R; ++p) ok &= all[(size_t)p].ok;
+  if (ok) {
+    w.peers.win[me] = w.local;
+    for (int p = 0; p < R && ok; ++p) {
+      if (p == me) continue;
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[(size_t)p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0; cudaGetLastError();
+      }
+      w.peers.win[p] = (char*)q;
+    }
+  }
+  // everybody must have mapped everybody (also a barrier: no rank writes before all headers are zero)
+  int* d_ok = (int*)d_one;
+  PP_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
+  PP_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, s));
+  PP_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  pp_dev_free(d_one, s); pp_dev_free(d_all, s);
+  if (ok) {
+    PP_CUDA(cudaMalloc((void**)&w.dev, sizeof(int) * (3 * (size_t)R + 8)));
+    PP_CUDA(cudaMalloc((void**)&w.dev_stats, 4 * sizeof(long long)));
+    PP_CUDA(cudaHostAlloc((void**)&w.host_stats, 4 * sizeof(long long), cudaHostAllocDefault));
+    PP_CUDA(cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming));
+  } else if (w.local) {
+    for (int p = 0; p < R; ++p)
+      if (p != me && w.peers.win[p]) { cudaIpcCloseMemHandle(w.peers.win[p]); w.peers.win[p] = nullptr; }
+    cudaFree(w.local);
+    w.local = nullptr;
+  }
+  w.ok = ok != 0;
+  return PP_OK;
+}
+
+pp_status build_sorted_gids(pp_ps* ps, cudaStream_t s) {
+  if (!ps->elem_gids || ps->sorted_gid) return PP_OK;
+  // lazily build the sorted gid table (createGlobalMapping, SCS_buildFns.h:101-112)
+  long long* keys_in = (long long*)ps->elem_gids;
+  int* vals_in;
+  PP_TRY(pp_dev_alloc(&vals_in, ps->nelems, s));
+  PP_TRY(pp_dev_alloc(&ps->sorted_gid, ps->nelems, s));
+  PP_TRY(pp_dev_alloc(&ps->sorted_lid, ps->nelems, s));
+  k_iota<<<pp_div_up(ps->nelems, kBlock), kBlock, 0, s>>>(vals_in, ps->nelems);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in, (long long*)ps->sorted_gid, vals_in, ps->sorted_lid,
+                                  ps->nelems, 0, 64, s);
+  char* tmp;
+  PP_TRY(pp_dev_alloc(&tmp, tb, s));
+  PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys_in, (long long*)ps->sorted_gid, vals_in, ps->sorted_lid,
+                                          ps->nelems, 0, 64, s));
+  pp_dev_free(tmp, s); pp_dev_free(vals_in, s);
+  return PP_OK;
+}
+
+pp_status migrate_p2p(pp_ps* ps, pp_comm* comm, int32_t* new_element, const int32_t* new_process, int32_t n_user,
+                      const int32_t* user_elems, const void* const* user_info, pp_migrate_stats* stats_host,
+                      const PackTable& pt, cudaStream_t s) {
+  P2PWindow& w = comm->p2p;
+  const int R = comm->nranks, me = comm->rank;
+  const int rec_bytes = (int)p2p_rec_bytes(pt);
+  const int seg_cap = (int)std::min<size_t>(w.seg_bytes / rec_bytes, 0x3fffffff / R);
+  const unsigned epoch = ++w.epoch;
+  const int parity = (int)(epoch & 1u);
+  P2PScratch x = p2p_scratch(w.dev, R);
+  PP_CUDA(cudaMemsetAsync(w.dev, 0, sizeof(int) * (R + 2), s));       // cursor, overflow, err
+  if (ps->capacity > 0)
+    k_p2p_pack<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
+        ps->view(), new_process, new_element, (const long long*)ps->elem_gids, me, R, x.cursor, x.overflow,
+        w.peers, parity, w.seg_bytes, seg_cap, rec_bytes, pt, ps->stride);
+  k_p2p_publish<<<1, kMaxRanks, 0, s>>>(x.cursor, x.overflow, R, me, w.peers, parity, epoch, seg_cap, w.dev_stats);
+  k_p2p_wait<<<1, kMaxRanks, 0, s>>>((P2PHeader*)w.local, R, me, parity, epoch, x.recv_cnt, x.recv_off, x.n_in,
+                                     x.n_total, n_user, x.err, w.dev_stats);
+  PP_KERNEL_CHECK();
+  // new-particle arrays of the rebuild: rows of `ld` slots, received particles first
+  const long ld = (long)(R - 1) * seg_cap + n_user;
+  std::vector<char*> in_data(ps->nmembers, nullptr);
+  int* in_elems;
+  char** d_dst;
+  PP_TRY(pp_dev_alloc(&in_elems, (size_t)ld + 1, s));
+  PP_TRY(pp_dev_alloc(&d_dst, ps->nmembers, s));
+  for (int k = 0; k < ps->nmembers; ++k)
+    PP_TRY(pp_dev_alloc(&in_data[k], (size_t)pt.bytes[k] * pt.ncomp[k] * (size_t)ld + 8, s));
+  PP_CUDA(cudaMemcpyAsync(d_dst, in_data.data(), sizeof(char*) * ps->nmembers, cudaMemcpyHostToDevice, s));
+  PP_TRY(build_sorted_gids(ps, s));
+  k_p2p_unpack<<<256, kBlock, 0, s>>>(w.local, parity, R, w.seg_bytes, rec_bytes, x.recv_off, x.n_in, ld, pt, d_dst,
+                                      (const long long*)ps->sorted_gid, ps->sorted_lid, ps->nelems, in_elems);
+  if (n_user > 0) {
+    PackTable ut = pt;
+    for (int k = 0; k < ut.n; ++k) ut.src[k] = (const char*)user_info[k];
+    k_p2p_append<<<pp_div_up(n_user, kBlock), kBlock, 0, s>>>(x.n_in, n_user, user_elems, ut, ld, d_dst, in_elems);
+  }
+  PP_KERNEL_CHECK();
+  PP_CUDA(cudaMemcpyAsync(w.host_stats, w.dev_stats, 4 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaEventRecord(w.ev, s));
+  std::vector<const void*> info(ps->nmembers, nullptr);
+  for (int k = 0; k < ps->nmembers; ++k) info[k] = in_data[k];
+  pp_status st = pp_ps_rebuild_ex(ps, new_element, (int32_t)ld, x.n_total, ld, in_elems, info.data(), (pp_stream)s);
+  for (char* p : in_data) pp_dev_free(p, s);
+  pp_dev_free(in_elems, s); pp_dev_free(d_dst, s);
+  PP_CUDA(cudaEventSynchronize(w.ev));       // long done: the rebuild read its scalars after this copy
+  if (stats_host) {
+    stats_host->sent = w.host_stats[0]; stats_host->received = w.host_stats[1];
+    stats_host->deferred = w.host_stats[2];
+  }
+  if (w.host_stats[3]) {
+    pp_set_error("migrate: a peer did not publish its particles within 20 s");
+    return PP_ERR_NCCL;
+  }
+  return st;
+}
+}  // namespace
+
+extern "C" void pp_comm_set_p2p(int32_t enable) { g_p2p_enable = enable ? 1 : 0; }
+extern "C" pp_status pp_comm_set_p2p_window(pp_comm* c, int64_t bytes_per_peer) {
+  PP_REQUIRE(c && bytes_per_peer >= 4096, "bad argument");
+  PP_REQUIRE(!c->p2p.tried, "the peer-memory window is sized before the first migration");
+  c->p2p.seg_bytes = (size_t)bytes_per_peer & ~(size_t)15;
+  return PP_OK;
+}
+extern "C" int32_t pp_comm_p2p_active(const pp_comm* c) { return c && c->p2p.ok ? 1 : 0; }
+
 extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_element,
                                    const int32_t* new_process, int32_t n_new,
                                    const int32_t* new_particle_elements,
@@ -351,7 +709,7 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
                                    pp_migrate_stats* stats_host, pp_stream stream_) {
   PP_REQUIRE(ps && comm && (new_element || ps->capacity == 0), "null argument");
   cudaStream_t s = (cudaStream_t)stream_;
-  if (stats_host) { stats_host->sent = 0; stats_host->received = 0; }
+  if (stats_host) { stats_host->sent = 0; stats_host->received = 0; stats_host->deferred = 0; }
   // serial: SCS_migrate.h:20-25
   if (comm->nranks == 1)
     return pp_ps_rebuild(ps, new_element, n_new, new_particle_elements, new_particle_info, stream_);
@@ -365,13 +723,23 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
     pt.bytes[k] = ps->members[k].scalar_bytes;
     pt.ncomp[k] = ps->members[k].ncomp;
   }
+  // peer-memory window (set up collectively by the first migration of this communicator)
+  if (!comm->p2p.tried) PP_TRY(p2p_setup(comm, s));
+  if (comm->p2p.ok) {
+    bool plain = true;                   // members in 1/2/4/8-byte scalars: always
+    if (plain)
+      return migrate_p2p(ps, comm, new_element, new_process, n_new, new_particle_elements, new_particle_info,
+                         stats_host, pt, s);
+  }
+  // ---- NCCL path (no peer access between the GPUs, or pp_comm_set_p2p(0))
   // 1. particles per destination, 2. counts to everybody (PS_Comm_Ialltoall, :48)
   int *send_cnt, *all_cnt;
   PP_TRY(pp_dev_alloc(&send_cnt, R, s));
   PP_TRY(pp_dev_alloc(&all_cnt, (size_t)R * R, s));
   PP_CUDA(cudaMemsetAsync(send_cnt, 0, sizeof(int) * R, s));
   if (ps->capacity > 0)
-    k_count_dest<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_process, me, R, send_cnt);
+    k_count_dest<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_process, new_element, me, R,
+                                                                    send_cnt);
   PP_KERNEL_CHECK();
   PP_NCCL(g_nccl.AllGather(send_cnt, all_cnt, (size_t)R, ncclInt32, comm->comm, s));
   std::vector<int> h_all((size_t)R * R);

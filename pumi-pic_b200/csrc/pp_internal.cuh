@@ -201,6 +201,11 @@ struct pp_ps {
   PsView view() const;
 };
 
+// pp_ps_rebuild with a device-side count of the particles being added (see csrc/pp_scs.cu)
+pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new, const int32_t* n_new_dev,
+                           int64_t new_ld, const int32_t* new_particle_elements,
+                           const void* const* new_particle_info, pp_stream stream);
+
 // slot -> (element of owning row, mask).  Works for every structure kind.
 __device__ __forceinline__ bool pp_slot_lookup(const PsView& v, int slot, int& elem) {
   const uint32_t w = __ldg(v.mask_bits + (slot >> 5));

@@ -187,8 +187,10 @@ __global__ void k_scs_mask(PsView v, const int* __restrict__ row_ppe, int ne, ui
 }
 
 __global__ void k_assign_slots(const int* __restrict__ elems, int n, const int* __restrict__ elem2row,
-                               const int* __restrict__ chunk_start, int C, int* row_fill, int* slots) {
+                               const int* __restrict__ chunk_start, int C, int* row_fill, int* slots,
+                               const int* __restrict__ n_dev = nullptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   const int row = elem2row[elems[i]];
   const int col = atomicAdd(row_fill + row, 1);
@@ -211,8 +213,12 @@ __global__ void k_hist_kept(PsView v, const int* __restrict__ new_elem, int* cou
     else atomicAdd(count + e, 1);
   }
 }
-__global__ void k_hist_new(const int* __restrict__ elems, int n, int* count, int* bad) {
+// n_dev (all *_new kernels): the number of particles being added when only the device knows it
+// (pp_ps_migrate over the peer-memory window); n is then an upper bound that sized the launch
+__global__ void k_hist_new(const int* __restrict__ elems, int n, int* count, int* bad,
+                           const int* __restrict__ n_dev = nullptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   const int e = elems[i];
   if (e < 0) { *bad = 1; return; }
@@ -492,8 +498,10 @@ __global__ void __launch_bounds__(256) k_stage_pack(PsView v, const int* __restr
 }
 // pack new particles: member arrays are [ncomp][n], destination slots precomputed
 __global__ void __launch_bounds__(256) k_stage_pack_new(const int* __restrict__ slots, int n,
-                                                        const __grid_constant__ UnitTable t, char* stage) {
+                                                        const __grid_constant__ UnitTable t, char* stage,
+                                                        const int* __restrict__ n_dev = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   uint4 first[kGroup];
   load_group(t, 0, i, first);
@@ -1118,8 +1126,9 @@ __global__ void k_invmap(PsView v, const int* __restrict__ new_elem, const int* 
   const int row = __ldg(elem2row + e);
   src_of[__ldg(chunk_start + (row >> 5)) + (__ldg(rank + s) << 5) + (row & 31)] = s;
 }
-__global__ void k_invmap_new(const int* __restrict__ slots, int n, int* src_of) {
+__global__ void k_invmap_new(const int* __restrict__ slots, int n, int* src_of, const int* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i < n) src_of[slots[i]] = -i - 1;
 }
 
@@ -1191,8 +1200,9 @@ double g_gather_l2_bytes = 48e6; // footprint the chunks in flight may have
 double g_gather_max_cols = 14.0; // average columns per chunk up to which the gather beats the record stage
 
 // returns done = false when a speculation failed (nothing of the structure has changed then)
-pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const int* new_particle_elements,
-                             const void* const* new_particle_info, cudaStream_t s, bool& done) {
+pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const int* n_new_dev, long new_ld,
+                             const int* new_particle_elements, const void* const* new_particle_info,
+                             cudaStream_t s, bool& done) {
   done = false;
   const int ne = ps->nelems, C = 32, cap = ps->capacity;
   const pp_ps_config& cfg = ps->cfg;
@@ -1216,7 +1226,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   if (n_new > 0) {
     PP_TRY(pp_dev_alloc(&kept, ne + 1, s));
     PP_CUDA(cudaMemcpyAsync(kept, count, sizeof(int) * ne, cudaMemcpyDeviceToDevice, s));
-    k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, &sc->bad);
+    k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, &sc->bad, n_new_dev);
   }
   k_count_stats<<<std::min(pp_div_up(ne, kBlock), 592), kBlock, 0, s>>>(count, ne, sc);
   // ---- layout (scs_layout above, without its host reads)
@@ -1330,7 +1340,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     PP_CUDA(cudaMemsetAsync(row_fill, 0, sizeof(int) * (nrows + 1), s));
     k_fill_from_kept<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(kept, ne, L.element_to_row, row_fill);
     k_assign_slots<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, L.element_to_row,
-                                                               L.chunk_start, C, row_fill, slots);
+                                                               L.chunk_start, C, row_fill, slots, n_new_dev);
   }
   // wide rows: the 8-byte gathers of a particle cost one L1 wavefront each and the source footprint of
   // a chunk outgrows what L2 can keep for its neighbours; the record stage (full sectors both ways)
@@ -1345,8 +1355,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
       k_invmap<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, rank, L.element_to_row,
                                                         L.chunk_start, src_of);
     if (n_new > 0) {
-      k_invmap_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, src_of);
-      unit_table(ps, new_particle_info, n_new, &ps->swap, ps->swap_stride, un);
+      k_invmap_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, src_of, n_new_dev);
+      unit_table(ps, new_particle_info, new_ld, &ps->swap, ps->swap_stride, un);
     }
     // blocks in flight: their chunks' source sectors (fetched as whole 64-byte DRAM atoms) must fit L2
     const double foot = 32.0 * avg_cols * (ut.nunits * 8) * 2.0;
@@ -1363,8 +1373,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
       PP_TRY(launch_stage_pack(ps->view(), new_element, L.element_to_row, L.chunk_start, C, 0, nullptr, nullptr,
                                rank, ut, ps->stage, s));
     if (n_new > 0) {
-      unit_table(ps, new_particle_info, n_new, nullptr, 0, un);
-      k_stage_pack_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, un, ps->stage);
+      unit_table(ps, new_particle_info, new_ld, nullptr, 0, un);
+      k_stage_pack_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, un, ps->stage, n_new_dev);
     }
     k_stage_unpack_scs<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(layout_view(L, ne), L.row_ppe, ut,
                                                                         ps->stage, L.mask);
@@ -1392,13 +1402,64 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
 extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
                                    const int32_t* new_particle_elements,
                                    const void* const* new_particle_info, pp_stream stream_) {
+  return pp_ps_rebuild_ex(ps, new_element, n_new, nullptr, n_new, new_particle_elements, new_particle_info,
+                          stream_);
+}
+
+// n_new_dev != NULL: the number of particles being added is *n_new_dev (device memory), n_new is an
+// upper bound; new_ld: row length of the new_particle_info arrays ([ncomp][new_ld]).
+pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new, const int32_t* n_new_dev,
+                           int64_t new_ld, const int32_t* new_particle_elements,
+                           const void* const* new_particle_info_in, pp_stream stream_) {
   PP_REQUIRE(ps && (new_element || ps->capacity == 0), "null argument");
   PP_REQUIRE(n_new >= 0, "negative number of new particles");
-  PP_REQUIRE(n_new == 0 || (new_particle_elements && new_particle_info),
+  PP_REQUIRE(n_new == 0 || (new_particle_elements && new_particle_info_in),
              "new particles need their elements and member data");
   cudaStream_t s = (cudaStream_t)stream_;
   const int ne = ps->nelems;
   const int kind = ps->cfg.kind;
+  const void* const* new_particle_info = new_particle_info_in;
+  // ---- Sell-C-sigma with C = 32, sparse rows: device-side layout + single-pass move
+  if ((kind == PP_PS_SCS || kind == PP_PS_CABM) && g_staged_rebuild >= 2 && ps->cfg.team_size == 32 &&
+      ne >= 32 && (long)ps->nptcls < (long)g_rank_sort_ppe * ne &&
+      !(g_try_shuffling && ps->capacity > 0 && ps->tile_slice && ps->shuffle_skip == 0)) {
+    UnitTable probe;
+    std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
+    if (unit_table(ps, old_src.data(), ps->stride, nullptr, 0, probe)) {
+      bool done = false;
+      PP_TRY(rebuild_scs_gather(ps, new_element, n_new, n_new_dev, new_ld, new_particle_elements,
+                                new_particle_info, s, done));
+      if (done) {
+        if (g_try_shuffling && ps->shuffle_skip > 0) --ps->shuffle_skip;
+        return PP_OK;
+      }
+    }
+  }
+  // ---- general path: the host needs the count, and compact [ncomp][n_new] arrays
+  std::vector<char*> compacted;
+  std::vector<const void*> compact_ptrs;
+  if (n_new_dev) {
+    int h_n = 0;
+    PP_CUDA(cudaMemcpyAsync(&h_n, n_new_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+    n_new = h_n < n_new ? h_n : n_new;
+  }
+  if (n_new > 0 && new_ld != n_new) {
+    for (int i = 0; i < ps->nmembers; ++i) {
+      const size_t sb = ps->members[i].scalar_bytes;
+      char* q;
+      PP_TRY(pp_dev_alloc(&q, sb * ps->members[i].ncomp * (size_t)n_new, s));
+      PP_CUDA(cudaMemcpy2DAsync(q, sb * n_new, new_particle_info_in[i], sb * new_ld, sb * n_new,
+                                ps->members[i].ncomp, cudaMemcpyDeviceToDevice, s));
+      compacted.push_back(q);
+      compact_ptrs.push_back(q);
+    }
+    new_particle_info = compact_ptrs.data();
+  }
+  struct FreeCompacted {
+    std::vector<char*>& v; cudaStream_t s;
+    ~FreeCompacted() { for (char* q : v) pp_dev_free(q, s); }
+  } free_compacted{compacted, s};
   int* scal;
   PP_TRY(pp_dev_alloc(&scal, 4, s));
   PP_CUDA(cudaMemsetAsync(scal, 0, 4 * sizeof(int), s));
@@ -1467,22 +1528,6 @@ extern "C" pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_
     return PP_OK;
   }
 
-  // ---- Sell-C-sigma with C = 32, sparse rows: device-side layout + single-pass gather
-  if ((kind == PP_PS_SCS || kind == PP_PS_CABM) && g_staged_rebuild >= 2 && ps->cfg.team_size == 32 &&
-      ne >= 32 && (long)ps->nptcls < (long)g_rank_sort_ppe * ne &&
-      !(g_try_shuffling && ps->capacity > 0 && ps->tile_slice && ps->shuffle_skip == 0)) {
-    UnitTable probe;
-    std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
-    if (unit_table(ps, old_src.data(), ps->stride, nullptr, 0, probe)) {
-      bool done = false;
-      PP_TRY(rebuild_scs_gather(ps, new_element, n_new, new_particle_elements, new_particle_info, s, done));
-      if (done) {
-        if (g_try_shuffling && ps->shuffle_skip > 0) --ps->shuffle_skip;
-        pp_dev_free(scal, s);
-        return PP_OK;
-      }
-    }
-  }
   // ---- element-sorted kinds: histogram of destinations (countNewParticles / rebuild_count)
   int* count;
   PP_TRY(pp_dev_alloc(&count, ne + 1, s));

@@ -8,6 +8,7 @@ Checks, following particle_structs/test/test_migrate.cpp and test/test_comm_arra
      Kuhn cube: the union over ranks of (particle id -> element) must equal the serial CPU oracle
   4. the same loop and the comm-array reductions on partially buffered PICparts (sub-meshes)
 """
+import ctypes as C
 import importlib
 import os
 import sys
@@ -355,6 +356,45 @@ def test_partial_picparts(P, comm, rank, R, steps=6):
               % (R, len(el2g), ne, tot))
 
 
+def test_small_window(P, rank, R):
+    """Peer-memory window with room for 100 particles per peer: a step that wants to send more keeps the
+    rest (stats.deferred) with their new_process still set; repeating the migration drains them, and
+    no particle is lost or duplicated."""
+    comm = P.Comm()
+    ne, npr = 64, 3000
+    ppe = np.full(ne, npr // ne, np.int32); ppe[: npr % ne] += 1
+    pel = np.repeat(np.arange(ne, dtype=np.int32), ppe)
+    ids = np.arange(npr, dtype=np.int32) + rank * 1000000
+    info = [ids.reshape(1, -1), np.zeros((3, npr)), (ids % 17).reshape(1, -1).astype(np.int32)]
+    ps = P.ParticleStructure(P.capi.PP_PS_SCS, TYPES, ppe, elem_gids=np.arange(ne, dtype=np.int64),
+                             particle_elements=pel, particle_info=info)
+    comm.set_p2p_window(100 * 48)          # TYPES travels as 48-byte records (gid 8 + 8 + 24 + 8): 100 per peer
+    total_sent = 0
+    for it in range(40):
+        se, m = ps.slot_elem_and_mask(); m = m.astype(bool)
+        pid = ps.get(0).cpu().numpy()[0, :ps.capacity]
+        here = m & (pid // 1000000 == rank)              # my original particles all go to the right
+        new_elem = np.where(m, se, -1).astype(np.int32)
+        new_proc = np.where(here, (rank + 1) % R, rank).astype(np.int32)
+        st = P.capi.MigrateStats()
+        P.capi.check(P.lib().pp_ps_migrate(ps.h, comm.h, P.api._ptr(dev(new_elem)), P.api._ptr(dev(new_proc)), 0,
+                                           None, None, C.byref(st), P.api._stream()))
+        total_sent += st.sent
+        left = gather_np(int(here.sum()) - int(st.sent))
+        if it == 0:
+            assert comm.p2p_active and st.deferred > 0 and st.sent < here.sum()
+        if sum(left) == 0:
+            break
+    assert total_sent == npr, (total_sent, npr)
+    se, m = ps.slot_elem_and_mask(); m = m.astype(bool)
+    pid = ps.get(0).cpu().numpy()[0, :ps.capacity][m]
+    allp = np.concatenate(gather_np(pid))
+    assert len(allp) == R * npr and len(np.unique(allp)) == len(allp)
+    assert np.all(pid // 1000000 == (rank - 1) % R)      # everything I hold came from my left neighbour
+    if rank == 0:
+        print("small window ok on %d ranks: drained in %d migrations" % (R, it + 1))
+
+
 def test_balancer(P, comm, rank, R):
     """testBalancePS (test/test_lb.cpp:132-207): 100 particles per element on the even ranks only,
     two rounds of repartition + migrate; the imbalance must end <= 1.5 and no particle may be lost,
@@ -423,11 +463,13 @@ def main():
         test_pic_loop(P, comm, rank, R)
     if only in ("", "partial"):
         test_partial_picparts(P, comm, rank, R)
-    # One rank: repartition is a no-op (pumipic_lb.hpp:360-361).  Quarantined until its first
-    # successful multi-GPU run (its one attempt hit the call's time limit): only
-    # with MGPU_ONLY=balancer or MGPU_UNVERIFIED=1 (tools/gpu_mg.sh sets the latter).
-    if R > 1 and (only == "balancer" or (only == "" and os.environ.get("MGPU_UNVERIFIED") == "1")):
+    # One rank: repartition is a no-op (pumipic_lb.hpp:360-361)
+    if R > 1 and only in ("", "balancer"):
         test_balancer(P, comm, rank, R)
+    if R > 1 and only == "small_window":
+        test_small_window(P, rank, R)
+    if R > 1 and only != "comm_array" and os.environ.get("MGPU_EXPECT_P2P") == "1":
+        assert comm.p2p_active or only == "small_window", "the peer-memory window was expected to be in use"
     dist.barrier()
     if rank == 0:
         print("MGPU_OK")

@@ -10,8 +10,9 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(n):
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+def _run(n, p2p=True, only=""):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PUMIPIC_P2P="1" if p2p else "0", MGPU_ONLY=only,
+               MGPU_EXPECT_P2P="1" if (p2p and n > 1) else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", str(29511 + n),
            os.path.join(HERE, "mgpu_worker.py")]
@@ -24,10 +25,28 @@ def test_single_rank_paths():
 
 
 def test_two_ranks_nccl():
+    """all scenarios (incl. the balancer) with the migration over the peer-memory window"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     _run(2)
+
+
+def test_two_ranks_nccl_transport():
+    """the migration scenarios again over the NCCL path (AllGather of counts + grouped Send/Recv)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    _run(2, p2p=False, only="migrate")
+    _run(2, p2p=False, only="pic_loop")
+
+
+def test_two_ranks_small_window_defers():
+    """a window too small for a step's particles: the overflow stays and leaves with a later step"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    _run(2, only="small_window")
 
 
 def test_four_ranks_nccl():
