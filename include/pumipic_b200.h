@@ -561,6 +561,25 @@ pp_status pp_gyro_scatter(pp_mesh* mesh, pp_ps* ps, const int32_t* v2v, double r
 pp_status pp_gyro_interleave(const double* fwd, const double* bkwd, int32_t nverts,
                              double* sync_array, pp_stream stream);
 
+/* ============================== phase timers (support/ppTiming.hpp) ====================== */
+
+/* The library's phases carry the reference's labels ("pumipic search_mesh", "SCS rebuild", "SCS
+ * particle migration", "gyro scatter" ...): always as NVTX ranges, and with pp_timing_enable(1)
+ * also as CUDA-event timings on the phase's stream, accumulated per label like
+ * pumipic::RecordTime (ppTiming.cpp:67-100).  Reading the table (count / get / summarize) waits for
+ * the pending phases.  pp_timing_record adds a caller-measured time under a label (RecordTime);
+ * pp_timing_summarize prints the reference's table to stderr (SummarizeTime :168-213; sort: 0
+ * alphabetical, 1 order of first occurrence, 2 longest first, 3 shortest first). */
+void pp_timing_enable(int32_t on);
+void pp_timing_set_verbosity(int32_t verbosity);   /* -1 none, 0 summary (default), 1 every record */
+void pp_timing_set_rank(int32_t rank);             /* the rank printed in front of the lines */
+void pp_timing_record(const char* label, double seconds);
+void pp_timing_reset(void);
+int32_t pp_timing_count(void);
+pp_status pp_timing_get(int32_t i, char* name, int32_t name_cap, double* total_s, double* min_s,
+                        double* max_s, double* sum_sq, int64_t* calls);
+void pp_timing_summarize(int32_t sort);
+
 /* ============================== communication (NCCL over NVLink) ========================= */
 
 /* One process per GPU.  Rank 0 calls pp_comm_unique_id and distributes the 128 bytes by any

@@ -676,6 +676,30 @@ def gyro_interleave(fwd, bkwd):
 
 
 # ------------------------------------------------------------------ communication
+# ------------------------------------------------------------------ phase timers (ppTiming.hpp)
+def timing_enable(on=True, rank=0, verbosity=0):
+    lib().pp_timing_set_rank(rank)
+    lib().pp_timing_set_verbosity(verbosity)
+    lib().pp_timing_enable(1 if on else 0)
+
+
+def timing_reset():
+    lib().pp_timing_reset()
+
+
+def timing_table():
+    """{label: {"total_s", "min_s", "max_s", "calls", "avg_ms"}} of the phases recorded so far"""
+    out = {}
+    for i in range(lib().pp_timing_count()):
+        name = C.create_string_buffer(256)
+        tot, mn, mx, sq = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        n = C.c_int64()
+        check(lib().pp_timing_get(i, name, 256, C.byref(tot), C.byref(mn), C.byref(mx), C.byref(sq), C.byref(n)))
+        out[name.value.decode()] = {"total_s": tot.value, "min_s": mn.value, "max_s": mx.value, "calls": n.value,
+                                    "avg_ms": 1e3 * tot.value / max(1, n.value)}
+    return out
+
+
 class Comm:
     """NCCL communicator of the C ABI.  The unique id travels over torch.distributed (plumbing)."""
 

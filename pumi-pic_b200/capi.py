@@ -163,6 +163,15 @@ PROTOTYPES = {
     "pp_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pp_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "pp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pp_timing_enable": (None, [C.c_int32]),
+    "pp_timing_set_verbosity": (None, [C.c_int32]),
+    "pp_timing_set_rank": (None, [C.c_int32]),
+    "pp_timing_record": (None, [C.c_char_p, C.c_double]),
+    "pp_timing_reset": (None, []),
+    "pp_timing_count": (C.c_int32, []),
+    "pp_timing_get": (C.c_int, [C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "pp_timing_summarize": (None, [C.c_int32]),
     "pp_comm_set_p2p": (None, [C.c_int32]),
     "pp_comm_set_p2p_window": (C.c_int, [C.c_void_p, C.c_int64]),
     "pp_comm_p2p_active": (C.c_int32, [C.c_void_p]),

@@ -402,44 +402,89 @@ P2PScratch p2p_scratch(int* base, int R) {
   x.recv_off = x.n_total + 1; x.recv_cnt = x.recv_off + R + 1;
   return x;
 }
-__host__ __device__ inline size_t p2p_rec_bytes(const PackTable& t) {
+__host__ __device__ inline size_t p2p_rec_bytes(const PackTable& t) {   // multiple of 16: moved in 16-byte pieces
   size_t b = 8;
   for (int k = 0; k < t.n; ++k) b += align8((size_t)t.bytes[k] * t.ncomp[k]);
-  return b;
+  return (b + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t p2p_seg_offset(int parity, int sender, int R, size_t seg_bytes) {
   return sizeof(P2PHeader) + ((size_t)parity * R + sender) * seg_bytes;
 }
 
 // record of one particle: int64 gid | member 0 components | member 1 ... (members 8-byte aligned)
-__global__ void k_p2p_pack(PsView v, const int* __restrict__ new_proc, int* new_elem,
-                           const long long* __restrict__ elem_gids, int self, int nranks, int* cursor,
-                           int* overflow, P2PPeers peers, int parity, size_t seg_bytes, int seg_cap,
-                           int rec_bytes, PackTable t, long stride) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= v.capacity) return;
-  if (!((__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u)) return;
-  const int p = new_proc[s];
-  if (p == self || p < 0 || p >= nranks) return;
-  const int e = new_elem[s];
-  if (e < 0) return;                       // deleted by the caller: dropped here, not sent
-  const int i = atomicAdd(cursor + p, 1);
-  if (i >= seg_cap) { atomicAdd(overflow, 1); return; }   // no room: stays on this rank this step
-  char* rec = peers.win[p] + p2p_seg_offset(parity, self, nranks, seg_bytes) + (size_t)i * rec_bytes;
-  *(long long*)rec = elem_gids ? elem_gids[e] : (long long)e;
-  size_t off = 8;
-  for (int k = 0; k < t.n; ++k) {
-    const int sb = t.bytes[k];
-    for (int c = 0; c < t.ncomp[k]; ++c) {
-      const char* a = t.src[k] + ((size_t)c * stride + s) * sb;
-      char* b = rec + off + (size_t)c * sb;
-      if (sb == 8) *(double*)b = *(const double*)a;
-      else if (sb == 4) *(int*)b = *(const int*)a;
-      else for (int q = 0; q < sb; ++q) b[q] = a[q];
+// A block owns kPackSlots consecutive slots: it counts its leaving particles per destination in
+// shared memory, reserves their places in the destinations' segments with ONE global atomic per
+// destination (thousands of lanes adding to the same few cursors would serialise in L2), then
+// stores the records over NVLink.
+constexpr int kPackThreads = 256, kPackPerThread = 8, kPackSlots = kPackThreads * kPackPerThread;
+__global__ void __launch_bounds__(kPackThreads) k_p2p_pack(
+    PsView v, const int* __restrict__ new_proc, int* new_elem, const long long* __restrict__ elem_gids, int self,
+    int nranks, int* cursor, int* overflow, P2PPeers peers, int parity, size_t seg_bytes, int seg_cap,
+    int rec_bytes, PackTable t, long stride, int debug) {
+  __shared__ int s_cnt[kMaxRanks], s_base[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  // slots of thread t: 4 consecutive ones per 16-byte load of new_proc, kPackPerThread / 4 loads
+  const long sb0 = (long)blockIdx.x * kPackSlots + 4 * threadIdx.x;
+  const bool vec = ((size_t)new_proc & 15) == 0;
+  int dest[kPackPerThread], pos[kPackPerThread];
+#pragma unroll
+  for (int g = 0; g < kPackPerThread / 4; ++g) {
+    const long sg = sb0 + (long)g * 4 * kPackThreads;
+    int pv[4] = {self, self, self, self};
+    if (vec && sg + 3 < v.capacity) {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(new_proc + sg));
+      pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (sg + j < v.capacity) pv[j] = new_proc[sg + j];
     }
-    off += align8((size_t)sb * t.ncomp[k]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 4 * g + j;
+      const long s = sg + j;
+      const int p = pv[j];
+      dest[k] = -1;
+      // most slots stay (p == self): the mask and the element are only read for the others; a
+      // particle the caller deleted (element -1) is dropped here, not sent
+      if (p != self && p >= 0 && p < nranks && s < v.capacity &&
+          ((__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u) && new_elem[s] >= 0)
+        dest[k] = p;
+      if (debug == 2) dest[k] = -1;
+      if (dest[k] >= 0) pos[k] = atomicAdd(&s_cnt[dest[k]], 1);
+    }
   }
-  new_elem[s] = -1;                        // removeSentParticles (SCS_migrate.h:190-196)
+  __syncthreads();
+  if (threadIdx.x < nranks) {
+    const int c = s_cnt[threadIdx.x];
+    s_base[threadIdx.x] = c ? atomicAdd(cursor + threadIdx.x, c) : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kPackPerThread; ++k) {
+    if (dest[k] < 0) continue;
+    const long s = sb0 + (long)(k >> 2) * 4 * kPackThreads + (k & 3);
+    const int p = dest[k];
+    const int i = s_base[p] + pos[k];
+    if (i >= seg_cap) { atomicAdd(overflow, 1); continue; }   // no room: stays on this rank this step
+    const int e = new_elem[s];
+    char* rec = peers.win[debug == 1 ? self : p] + p2p_seg_offset(parity, self, nranks, seg_bytes) + (size_t)i * rec_bytes;
+    *(long long*)rec = elem_gids ? elem_gids[e] : (long long)e;
+    size_t off = 8;
+    for (int m = 0; m < t.n; ++m) {
+      const int sb = t.bytes[m];
+      for (int c = 0; c < t.ncomp[m]; ++c) {
+        const char* a = t.src[m] + ((size_t)c * stride + s) * sb;
+        char* b = rec + off + (size_t)c * sb;
+        if (sb == 8) *(double*)b = *(const double*)a;
+        else if (sb == 4) *(int*)b = *(const int*)a;
+        else for (int q = 0; q < sb; ++q) b[q] = a[q];
+      }
+      off += align8((size_t)sb * t.ncomp[m]);
+    }
+    new_elem[s] = -1;                      // removeSentParticles (SCS_migrate.h:190-196)
+  }
 }
 // after the pack kernel has completed (its stores have landed): counts, then the step flag
 __global__ void k_p2p_publish(const int* __restrict__ cursor, const int* __restrict__ overflow, int nranks,
@@ -646,14 +691,22 @@ pp_status migrate_p2p(pp_ps* ps, pp_comm* comm, int32_t* new_element, const int3
   const int parity = (int)(epoch & 1u);
   P2PScratch x = p2p_scratch(w.dev, R);
   PP_CUDA(cudaMemsetAsync(w.dev, 0, sizeof(int) * (R + 2), s));       // cursor, overflow, err
-  if (ps->capacity > 0)
-    k_p2p_pack<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
+  PPTimeScope* t_x = new PPTimeScope(s, "migration pack + peer stores");
+  if (ps->capacity > 0) {
+    PP_TIME(s, "migration pack kernel");
+    static const int dbg = getenv("PUMIPIC_PACK_DEBUG") ? atoi(getenv("PUMIPIC_PACK_DEBUG")) : 0;   // timing experiments only
+    k_p2p_pack<<<pp_div_up(ps->capacity, kPackSlots), kPackThreads, 0, s>>>(
         ps->view(), new_process, new_element, (const long long*)ps->elem_gids, me, R, x.cursor, x.overflow,
-        w.peers, parity, w.seg_bytes, seg_cap, rec_bytes, pt, ps->stride);
+        w.peers, parity, w.seg_bytes, seg_cap, rec_bytes, pt, ps->stride, dbg);
+  }
   k_p2p_publish<<<1, kMaxRanks, 0, s>>>(x.cursor, x.overflow, R, me, w.peers, parity, epoch, seg_cap, w.dev_stats);
+  delete t_x;
+  t_x = new PPTimeScope(s, "migration wait for peers");
   k_p2p_wait<<<1, kMaxRanks, 0, s>>>((P2PHeader*)w.local, R, me, parity, epoch, x.recv_cnt, x.recv_off, x.n_in,
                                      x.n_total, n_user, x.err, w.dev_stats);
+  delete t_x;
   PP_KERNEL_CHECK();
+  PP_TIME(s, "migration unpack + rebuild");
   // new-particle arrays of the rebuild: rows of `ld` slots, received particles first
   const long ld = (long)(R - 1) * seg_cap + n_user;
   std::vector<char*> in_data(ps->nmembers, nullptr);
@@ -709,6 +762,7 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
                                    pp_migrate_stats* stats_host, pp_stream stream_) {
   PP_REQUIRE(ps && comm && (new_element || ps->capacity == 0), "null argument");
   cudaStream_t s = (cudaStream_t)stream_;
+  PP_TIME_KIND(s, ps->cfg.kind, "particle migration");   // SCS_migrate.h:218 (here including the rebuild)
   if (stats_host) { stats_host->sent = 0; stats_host->received = 0; stats_host->deferred = 0; }
   // serial: SCS_migrate.h:20-25
   if (comm->nranks == 1)

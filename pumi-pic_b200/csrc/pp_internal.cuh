@@ -69,6 +69,30 @@ static inline pp_status pp_dev_import(T** dst, const T* src, size_t n, int memsp
 }
 
 // ------------------------------------------------------------------------------------------
+// phase timers / NVTX ranges (csrc/pp_timing.cu).  A scope is always an NVTX range; with
+// pp_timing_enable(1) it is also bracketed by two CUDA events on `s` whose elapsed time is
+// accumulated under `label` (support/ppTiming.cpp RecordTime).
+// ------------------------------------------------------------------------------------------
+class PPTimeScope {
+ public:
+  PPTimeScope(cudaStream_t s, const char* label);
+  ~PPTimeScope();
+  PPTimeScope(const PPTimeScope&) = delete;
+  PPTimeScope& operator=(const PPTimeScope&) = delete;
+ private:
+  cudaStream_t s_;
+  cudaEvent_t a_;
+  int index_;
+};
+const char* pp_kind_name(int kind);
+#define PP_TIME_CAT2(a, b) a##b
+#define PP_TIME_CAT(a, b) PP_TIME_CAT2(a, b)
+#define PP_TIME(stream, label) PPTimeScope PP_TIME_CAT(pp_time_scope_, __LINE__)((stream), (label))
+#define PP_TIME_KIND(stream, kind, what)                                                       \
+  const std::string PP_TIME_CAT(pp_time_label_, __LINE__) = std::string(pp_kind_name(kind)) + " " + (what); \
+  PPTimeScope PP_TIME_CAT(pp_time_scope_, __LINE__)((stream), PP_TIME_CAT(pp_time_label_, __LINE__).c_str())
+
+// ------------------------------------------------------------------------------------------
 // walk records: everything one hop of the adjacency walk needs, in one aligned gather.
 // ------------------------------------------------------------------------------------------
 // adj[f] >= 0 : element across local side f

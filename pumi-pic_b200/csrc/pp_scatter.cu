@@ -189,6 +189,7 @@ extern "C" pp_status pp_gyro_scatter(pp_mesh* mesh, pp_ps* ps, const int32_t* v2
   PP_REQUIRE(nrings >= 2 && points_per_ring >= 1, "need at least two rings and one point per ring");
   PP_REQUIRE(ps->nelems == mesh->nelems, "particle structure and mesh disagree on nelems");
   cudaStream_t s = (cudaStream_t)stream_;
+  PP_TIME(s, "gyro scatter");
   const int ne = mesh->nelems, nv = mesh->nverts, gnr = nrings, gppr = points_per_ring;
   // ring selection of gyroScatter.hpp:184-192 (the particle radius is the constant 1.125*ringWidth)
   const double ringWidth = rmax / gnr;

@@ -51,11 +51,12 @@ __global__ void k_count_nonzero(const int* __restrict__ a, int n, int* out) {
 }
 
 // sigmaSort keys: ascending particle count inside windows of `sigma` elements (stable)
-__global__ void k_sort_keys(const int* __restrict__ ppe, int ne, int sigma, int cbits, uint64_t* keys, int* vals) {
+template <class Key>
+__global__ void k_sort_keys(const int* __restrict__ ppe, int ne, int sigma, int cbits, Key* keys, int* vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ne) return;
-  const uint64_t win = (uint64_t)(i / sigma);
-  keys[i] = (win << cbits) | (uint32_t)ppe[i];
+  const Key win = (Key)(i / sigma);
+  keys[i] = (win << cbits) | (Key)(uint32_t)ppe[i];
   vals[i] = i;
 }
 
@@ -215,14 +216,30 @@ __global__ void k_hist_kept(PsView v, const int* __restrict__ new_elem, int* cou
 }
 // n_dev (all *_new kernels): the number of particles being added when only the device knows it
 // (pp_ps_migrate over the peer-memory window); n is then an upper bound that sized the launch
+// rank_out: the particle's rank in its element, behind the kept particles counted before (stream order)
 __global__ void k_hist_new(const int* __restrict__ elems, int n, int* count, int* bad,
-                           const int* __restrict__ n_dev = nullptr) {
+                           const int* __restrict__ n_dev = nullptr, int* rank_out = nullptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   const int e = elems[i];
-  if (e < 0) { *bad = 1; return; }
-  atomicAdd(count + e, 1);
+  if (e < 0) { *bad = 1; if (rank_out) rank_out[i] = 0; return; }
+  const int r = atomicAdd(count + e, 1);
+  if (rank_out) rank_out[i] = r;
+}
+// new particles: src_of[slot of (element, rank)] = -(i + 1)
+__global__ void k_invmap_new_ranked(const int* __restrict__ elems, const int* __restrict__ rank, int n,
+                                    const int* __restrict__ elem2row, const int* __restrict__ chunk_start,
+                                    int* src_of, int* slots, const int* __restrict__ n_dev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
+  if (i >= n) return;
+  const int e = elems[i];
+  if (e < 0) return;
+  const int row = __ldg(elem2row + e);
+  const int slot = __ldg(chunk_start + (row >> 5)) + (rank[i] << 5) + (row & 31);
+  if (src_of) src_of[slot] = -i - 1;
+  if (slots) slots[i] = slot;
 }
 
 struct MemberTable {
@@ -795,7 +812,7 @@ pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, long n
     PP_TRY(pp_dev_alloc(&k_out, ne, s));
     PP_TRY(pp_dev_alloc(&v_in, ne, s));
     PP_TRY(pp_dev_alloc(&sorted_elem, ne, s));
-    k_sort_keys<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(ppe_dev, ne, sigma > 0 ? sigma : 1, cbits, k_in, v_in);
+    k_sort_keys<uint64_t><<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(ppe_dev, ne, sigma > 0 ? sigma : 1, cbits, k_in, v_in);
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s);
     char* tmp;
@@ -1126,11 +1143,6 @@ __global__ void k_invmap(PsView v, const int* __restrict__ new_elem, const int* 
   const int row = __ldg(elem2row + e);
   src_of[__ldg(chunk_start + (row >> 5)) + (__ldg(rank + s) << 5) + (row & 31)] = s;
 }
-__global__ void k_invmap_new(const int* __restrict__ slots, int n, int* src_of, const int* __restrict__ n_dev) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n_dev) n = min(n, *n_dev);
-  if (i < n) src_of[slots[i]] = -i - 1;
-}
 
 // One block per destination chunk, the chunk's columns dealt round-robin to the block's warps
 // (lane = row): gathers the records of the chunk's particles into the new SoA columns and writes
@@ -1219,16 +1231,21 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   int *count, *rank = nullptr, *kept = nullptr;
   PP_TRY(pp_dev_alloc(&count, ne + 1, s));
   PP_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ne + 1), s));
-  if (cap > 0) {
-    PP_TRY(pp_dev_alloc(&rank, cap, s));
-    k_hist_kept<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count, rank);
+  int* rank_new = nullptr;
+  {
+    PP_TIME_KIND(s, ps->cfg.kind, "count active particles");       // SCS_rebuild.h:133-166
+    if (cap > 0) {
+      PP_TRY(pp_dev_alloc(&rank, cap, s));
+      k_hist_kept<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count, rank);
+    }
+    if (n_new > 0) {               // counted after the kept particles: their ranks follow the kept ones
+      PP_TRY(pp_dev_alloc(&rank_new, n_new, s));
+      k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, &sc->bad, n_new_dev,
+                                                             rank_new);
+    }
+    k_count_stats<<<std::min(pp_div_up(ne, kBlock), 592), kBlock, 0, s>>>(count, ne, sc);
   }
-  if (n_new > 0) {
-    PP_TRY(pp_dev_alloc(&kept, ne + 1, s));
-    PP_CUDA(cudaMemcpyAsync(kept, count, sizeof(int) * ne, cudaMemcpyDeviceToDevice, s));
-    k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, &sc->bad, n_new_dev);
-  }
-  k_count_stats<<<std::min(pp_div_up(ne, kBlock), 592), kBlock, 0, s>>>(count, ne, sc);
+  PPTimeScope* t_build = new PPTimeScope(s, (std::string(pp_kind_name(ps->cfg.kind)) + " SCS specific building").c_str());
   // ---- layout (scs_layout above, without its host reads)
   ScsLayout L;
   L.C = C; L.nchunks = nchunks; L.nrows = nrows;
@@ -1238,17 +1255,28 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     const int nwin = (ne + sigma - 1) / sigma;
     int wbits = 0;
     while ((1 << wbits) < nwin) ++wbits;
-    uint64_t *k_in, *k_out;
     int* v_in;
-    PP_TRY(pp_dev_alloc(&k_in, ne, s)); PP_TRY(pp_dev_alloc(&k_out, ne, s));
     PP_TRY(pp_dev_alloc(&v_in, ne, s)); PP_TRY(pp_dev_alloc(&sorted_elem, ne, s));
-    k_sort_keys<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(count, ne, sigma, cbits, k_in, v_in);
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s);
     char* tmp;
-    PP_TRY(pp_dev_alloc(&tmp, tb, s));
-    PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s));
-    pp_dev_free(tmp, s); pp_dev_free(k_in, s); pp_dev_free(k_out, s); pp_dev_free(v_in, s);
+    size_t tb = 0;
+    if (cbits + wbits <= 32) {       // the usual case (one window, or few): half the key traffic
+      uint32_t *k_in, *k_out;
+      PP_TRY(pp_dev_alloc(&k_in, ne, s)); PP_TRY(pp_dev_alloc(&k_out, ne, s));
+      k_sort_keys<uint32_t><<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(count, ne, sigma, cbits, k_in, v_in);
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s);
+      PP_TRY(pp_dev_alloc(&tmp, tb, s));
+      PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s));
+      pp_dev_free(k_in, s); pp_dev_free(k_out, s);
+    } else {
+      uint64_t *k_in, *k_out;
+      PP_TRY(pp_dev_alloc(&k_in, ne, s)); PP_TRY(pp_dev_alloc(&k_out, ne, s));
+      k_sort_keys<uint64_t><<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(count, ne, sigma, cbits, k_in, v_in);
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s);
+      PP_TRY(pp_dev_alloc(&tmp, tb, s));
+      PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s));
+      pp_dev_free(k_in, s); pp_dev_free(k_out, s);
+    }
+    pp_dev_free(tmp, s); pp_dev_free(v_in, s);
   }
   PP_TRY(pp_dev_alloc(&L.row_to_element, nrows, s));
   PP_TRY(pp_dev_alloc(&L.element_to_row, nrows, s));
@@ -1286,6 +1314,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   if (g_rebuild_chunk_order && (double)(cap + n_new) <= g_gather_max_cols * 1.3 * 32.0 * nchunks)
     PP_TRY(chunk_order_build(L.row_to_element, nchunks, s, &order));
   pp_dev_free(width, s); pp_dev_free(sizes, s); pp_dev_free(pref, s);
+  delete t_build;                                // SCS_rebuild.h:196-265
   // ---- the one host read
   FastScal h;
   PP_CUDA(cudaMemcpyAsync(&h, sc, sizeof(FastScal), cudaMemcpyDeviceToHost, s));
@@ -1293,6 +1322,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   auto drop = [&]() {
     free_layout(L, s);
     pp_dev_free(count, s); pp_dev_free(rank, s); pp_dev_free(kept, s); pp_dev_free(order, s); pp_dev_free(sc, s);
+    pp_dev_free(rank_new, s);
   };
   if (h.bad) {   // SCS_rebuild.h:147-151 (the reference exits the process)
     drop();
@@ -1333,15 +1363,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     PP_CUDA(cudaGetDevice(&dev));
     PP_CUDA(cudaDeviceGetAttribute(&g_sm_count_scs, cudaDevAttrMultiProcessorCount, dev));
   }
-  int *row_fill = nullptr, *slots = nullptr;
-  if (n_new > 0) {               // slots of the particles being added: behind the kept ones of their row
-    PP_TRY(pp_dev_alloc(&row_fill, nrows + 1, s));
-    PP_TRY(pp_dev_alloc(&slots, n_new, s));
-    PP_CUDA(cudaMemsetAsync(row_fill, 0, sizeof(int) * (nrows + 1), s));
-    k_fill_from_kept<<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(kept, ne, L.element_to_row, row_fill);
-    k_assign_slots<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, L.element_to_row,
-                                                               L.chunk_start, C, row_fill, slots, n_new_dev);
-  }
+  int* slots = nullptr;
+  PP_TIME_KIND(s, ps->cfg.kind, "PSToPs");     // the record move (SCS_rebuild.h:268-271), incl. the new particles
   // wide rows: the 8-byte gathers of a particle cost one L1 wavefront each and the source footprint of
   // a chunk outgrows what L2 can keep for its neighbours; the record stage (full sectors both ways)
   // is faster there (measured: 50 M particles at 25 per element, 5.3 ms staged vs 6.3 ms gathered;
@@ -1355,7 +1378,9 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
       k_invmap<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, rank, L.element_to_row,
                                                         L.chunk_start, src_of);
     if (n_new > 0) {
-      k_invmap_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, src_of, n_new_dev);
+      k_invmap_new_ranked<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, rank_new, n_new,
+                                                                      L.element_to_row, L.chunk_start, src_of,
+                                                                      nullptr, n_new_dev);
       unit_table(ps, new_particle_info, new_ld, &ps->swap, ps->swap_stride, un);
     }
     // blocks in flight: their chunks' source sectors (fetched as whole 64-byte DRAM atoms) must fit L2
@@ -1373,13 +1398,17 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
       PP_TRY(launch_stage_pack(ps->view(), new_element, L.element_to_row, L.chunk_start, C, 0, nullptr, nullptr,
                                rank, ut, ps->stage, s));
     if (n_new > 0) {
+      PP_TRY(pp_dev_alloc(&slots, n_new, s));
+      k_invmap_new_ranked<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, rank_new, n_new,
+                                                                      L.element_to_row, L.chunk_start, nullptr,
+                                                                      slots, n_new_dev);
       unit_table(ps, new_particle_info, new_ld, nullptr, 0, un);
       k_stage_pack_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, un, ps->stage, n_new_dev);
     }
     k_stage_unpack_scs<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(layout_view(L, ne), L.row_ppe, ut,
                                                                         ps->stage, L.mask);
   }
-  pp_dev_free(row_fill, s); pp_dev_free(slots, s);
+  pp_dev_free(slots, s); pp_dev_free(rank_new, s);
   PP_KERNEL_CHECK();
   adopt_layout(ps, L, s);
   std::swap(ps->data, ps->swap);
@@ -1418,11 +1447,15 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
   cudaStream_t s = (cudaStream_t)stream_;
   const int ne = ps->nelems;
   const int kind = ps->cfg.kind;
+  PP_TIME_KIND(s, kind, "rebuild");              // SCS_rebuild.h:312, CSR_rebuild.hpp:116
   const void* const* new_particle_info = new_particle_info_in;
   // ---- Sell-C-sigma with C = 32, sparse rows: device-side layout + single-pass move
   if ((kind == PP_PS_SCS || kind == PP_PS_CABM) && g_staged_rebuild >= 2 && ps->cfg.team_size == 32 &&
       ne >= 32 && (long)ps->nptcls < (long)g_rank_sort_ppe * ne &&
-      !(g_try_shuffling && ps->capacity > 0 && ps->tile_slice && ps->shuffle_skip == 0)) {
+      // a due reshuffle attempt goes through the general path -- unless the number of particles
+      // being added is only known to the device (migration over the peer-memory window): the
+      // attempt would need it on the host, and a step that receives particles rarely fits in place
+      (n_new_dev || !(g_try_shuffling && ps->capacity > 0 && ps->tile_slice && ps->shuffle_skip == 0))) {
     UnitTable probe;
     std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
     if (unit_table(ps, old_src.data(), ps->stride, nullptr, 0, probe)) {
@@ -1663,13 +1696,16 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
     return PP_OK;
   }
   // tryShuffling (SCS_rebuild.h:183-189).  An attempt costs a pass over the slots; after a failure
-  // the next attempts are spaced out (1, 2, 4, ... 64 rebuilds), after a success every rebuild tries.
+  // the next attempts are spaced out (3, 15, 63, 255 rebuilds), after a success every rebuild tries.
   if (g_try_shuffling && ps->capacity > 0 && ps->tile_slice) {
     if (ps->shuffle_skip > 0) {
       --ps->shuffle_skip;
     } else {
       bool done = false;
-      PP_TRY(try_reshuffle(ps, new_element, n_new, new_particle_elements, new_particle_info, mt_new, s, done));
+      {
+        PP_TIME_KIND(s, kind, "shuffle attempt");   // SCS_rebuild.h:190
+        PP_TRY(try_reshuffle(ps, new_element, n_new, new_particle_elements, new_particle_info, mt_new, s, done));
+      }
       if (done) {
         ps->shuffle_streak = 0;
         ps->nptcls = active;
@@ -1677,8 +1713,8 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
         pp_dev_free(kept, s);
         return PP_OK;
       }
-      ps->shuffle_streak = ps->shuffle_streak < 6 ? ps->shuffle_streak + 1 : 6;
-      ps->shuffle_skip = (1 << ps->shuffle_streak) - 1;
+      ps->shuffle_streak = ps->shuffle_streak < 4 ? ps->shuffle_streak + 1 : 4;
+      ps->shuffle_skip = (1 << (2 * ps->shuffle_streak)) - 1;      // 3, 15, 63, 255 rebuilds
     }
   }
   ScsLayout L;

@@ -1240,6 +1240,9 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
   PP_REQUIRE(a->x_tgt && a->elem_ids, "x_tgt and elem_ids are required");
   PP_REQUIRE(a->stride >= view.capacity, "stride smaller than capacity");
   PP_REQUIRE(ps_nelems == mesh->nelems, "particle structure and mesh disagree on nelems");
+  // labels of adjacency.tpp:609, adjacency.hpp:1152, :553
+  PP_TIME(s, a->variant == PP_SEARCH_2D_LEGACY ? "pumipic search_2d"
+             : a->variant == PP_SEARCH_3D ? "Search Mesh 3d" : "pumipic search_mesh");
   struct { int capacity; } ps_{view.capacity};
   auto* ps = &ps_;
   SearchParams p;

@@ -40,9 +40,22 @@ class PicStep:
         n = cube_per_gpu
         N = int(round(n * R ** (1.0 / 3.0)))
         coords, ev = P.host_kuhn_cube(N, 1.0)
-        e2s, s2v = P.host_derive_sides(3, ev)
         ne = ev.shape[0]
         owner = block_owner(coords, ev, R)
+        if R > 1:
+            # owner-major numbering, as a partitioned mesh has it (global ids are owner-major,
+            # part_construct.cpp:335-374): every core is one contiguous range of elements, and the
+            # vertices are numbered in the order the elements first touch them
+            perm = np.argsort(owner, kind="stable")
+            ev, owner = ev[perm], owner[perm]
+            uniq, first = np.unique(ev.ravel(), return_index=True)
+            new_id = np.empty(coords.shape[0], np.int32)
+            new_id[uniq[np.argsort(first, kind="stable")]] = np.arange(uniq.shape[0], dtype=np.int32)
+            ev = np.ascontiguousarray(new_id[ev])
+            inv = np.empty_like(new_id)
+            inv[new_id] = np.arange(new_id.shape[0], dtype=np.int32)
+            coords = np.ascontiguousarray(coords[inv])
+        e2s, s2v = P.host_derive_sides(3, ev)
         safe, part = P.host_picpart_tags(3, coords.shape[0], ev, owner, R, rank, P.api.BFS, P.api.BFS, 3, 1)
         assert part.all(), "block PICparts of this size buffer every core (full mesh on every rank)"
         self.gm = P.Mesh(3, coords, ev, e2s, s2v, np.ones(ne, np.int32))
@@ -125,12 +138,24 @@ class PicStep:
                 "particles_start": int(n_start), "particles_end": int(self.ps.nptcls), "sent": int(sent_tot)}
 
 
-def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_mult=3.0):
-    """Collective over the ranks of torch.distributed (when R > 1).  Returns the record on rank 0."""
+def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_mult=3.0, timing=False):
+    """Collective over the ranks of torch.distributed (when R > 1).  Returns the record on rank 0.
+    timing: also record the library's own phase timers (pp_timing_*, rank 0's table in the record)."""
     import torch
     import torch.distributed as dist
     ps = PicStep(P, comm, rank, R, cube_per_gpu, ppe, push_mult)
+    if timing:
+        for _ in range(warmup):
+            ps.step()
+        warmup = 0
+        torch.cuda.synchronize()
+        P.api.timing_reset()
+        P.api.timing_enable(True, rank)
     r = ps.run(steps, warmup, barrier=(dist.barrier if R > 1 else None))
+    table = None
+    if timing:
+        table = {k: round(v["avg_ms"], 4) for k, v in P.api.timing_table().items()}
+        P.api.timing_enable(False)
     t = torch.tensor([r["step_ms_total"]] + [r["phase_ms_median"][k] for k in PHASES], dtype=torch.float64,
                      device="cuda")
     cnt = torch.tensor([float(r["particles_start"]), float(r["sent"]), float(r["particles_end"])],
@@ -154,7 +179,11 @@ def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_m
            "phase_ms": {k: float(t[1 + i].item()) for i, k in enumerate(PHASES)},
            "algorithmic_bytes_per_particle_step": full_step_bytes,
            "achieved_GBs_per_gpu": full_step_bytes * cnt[0].item() / R / (tot_ms / steps * 1e-3) / 1e9,
-           "scaling": "weak", "timing": "CUDA events, max over ranks; phases: median over steps, max over ranks"}
+           "scaling": "weak", "timing": "CUDA events, max over ranks; phases: median over steps, max over ranks",
+           "transport": "peer-memory window (NVLink P2P stores, no host round trip)" if comm.p2p_active
+                        else ("NCCL AllGather + grouped Send/Recv" if R > 1 else "single rank")}
+    if table is not None:
+        out["library_phase_avg_ms_rank0"] = table
     del ps
     torch.cuda.empty_cache()
     return out
