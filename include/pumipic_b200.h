@@ -594,8 +594,10 @@ pp_status pp_comm_destroy(pp_comm* comm);
  * receiver's kernels wait on the flag -- no NCCL call, no host round trip in the step.  pp_comm_set_p2p(0)
  * (process-wide, before the first migration) or a failed IPC mapping selects the NCCL path (AllGather of
  * counts + grouped Send/Recv).  pp_comm_set_p2p_window sizes the window's segment per (sender, step
- * parity) in bytes (default 24 MiB, about 260 000 particles of 76 bytes); pp_comm_p2p_active tells which
- * path the communicator ended up with. */
+ * parity) in bytes (default: room for 1/16 of the first migrated structure's slots, at least 24 MiB, the
+ * largest request of any rank; a rank's window is 2 * nranks segments); particles that do not fit a
+ * segment stay where they are for that step (pp_migrate_stats.deferred).  pp_comm_p2p_active tells
+ * which path the communicator ended up with. */
 void pp_comm_set_p2p(int32_t enable);
 pp_status pp_comm_set_p2p_window(pp_comm* comm, int64_t bytes_per_peer);
 int32_t pp_comm_p2p_active(const pp_comm* comm);

@@ -94,7 +94,8 @@ struct P2PHeader {
 struct P2PPeers { char* win[kMaxRanks]; };
 struct P2PWindow {
   bool tried = false, ok = false;
-  size_t seg_bytes = 24u << 20;    // per (sender, parity)
+  size_t seg_bytes = 24u << 20;    // per (sender, parity); the same on every rank after the set-up
+  bool seg_set = false;            // sized by pp_comm_set_p2p_window
   char* local = nullptr;
   P2PPeers peers;
   int* dev = nullptr;              // cursor[R] | overflow | err | n_in | n_total | recv_off[R+1] | recv_cnt[R]
@@ -598,12 +599,26 @@ __global__ void k_p2p_append(const int* __restrict__ n_in, int n_user, const int
 }
 
 // one-time, collective: allocate this rank's window, exchange IPC handles, map the peers
-pp_status p2p_setup(pp_comm* c, cudaStream_t s) {
+pp_status p2p_setup(pp_comm* c, size_t want_seg_bytes, cudaStream_t s) {
   P2PWindow& w = c->p2p;
   w.tried = true;
   const int R = c->nranks, me = c->rank;
   const char* env = getenv("PUMIPIC_P2P");            // PUMIPIC_P2P=0: NCCL path (A/B, tests)
   int ok = (R <= kMaxRanks && g_p2p_enable && !(env && env[0] == '0')) ? 1 : 0;
+  // one segment size for every rank: the largest any rank asks for (senders address the receivers'
+  // windows with it)
+  if (!w.seg_set && want_seg_bytes > w.seg_bytes) w.seg_bytes = (want_seg_bytes + 15) & ~(size_t)15;
+  {
+    long long* d_sz;
+    long long h_sz = (long long)w.seg_bytes;
+    PP_TRY(pp_dev_alloc(&d_sz, 1, s));
+    PP_CUDA(cudaMemcpyAsync(d_sz, &h_sz, sizeof(h_sz), cudaMemcpyHostToDevice, s));
+    PP_NCCL(g_nccl.AllReduce(d_sz, d_sz, 1, ncclInt64, ncclMax, c->comm, s));
+    PP_CUDA(cudaMemcpyAsync(&h_sz, d_sz, sizeof(h_sz), cudaMemcpyDeviceToHost, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+    pp_dev_free(d_sz, s);
+    w.seg_bytes = (size_t)h_sz;
+  }
   const size_t bytes = sizeof(P2PHeader) + 2 * (size_t)R * w.seg_bytes;
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
@@ -751,6 +766,7 @@ extern "C" pp_status pp_comm_set_p2p_window(pp_comm* c, int64_t bytes_per_peer) 
   PP_REQUIRE(c && bytes_per_peer >= 4096, "bad argument");
   PP_REQUIRE(!c->p2p.tried, "the peer-memory window is sized before the first migration");
   c->p2p.seg_bytes = (size_t)bytes_per_peer & ~(size_t)15;
+  c->p2p.seg_set = true;
   return PP_OK;
 }
 extern "C" int32_t pp_comm_p2p_active(const pp_comm* c) { return c && c->p2p.ok ? 1 : 0; }
@@ -778,7 +794,8 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
     pt.ncomp[k] = ps->members[k].ncomp;
   }
   // peer-memory window (set up collectively by the first migration of this communicator)
-  if (!comm->p2p.tried) PP_TRY(p2p_setup(comm, s));
+  // default segment: room for 1/16 of this structure's slots per peer, at least 24 MiB
+  if (!comm->p2p.tried) PP_TRY(p2p_setup(comm, (size_t)ps->capacity / 16 * p2p_rec_bytes(pt), s));
   if (comm->p2p.ok) {
     bool plain = true;                   // members in 1/2/4/8-byte scalars: always
     if (plain)

@@ -1370,7 +1370,9 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   // is faster there (measured: 50 M particles at 25 per element, 5.3 ms staged vs 6.3 ms gathered;
   // 10 M at 10 per element, 1.08 ms staged vs 0.98 ms gathered)
   const double avg_cols = (double)L.capacity / (32.0 * nchunks);
-  if (avg_cols <= g_gather_max_cols) {
+  // (a chunk wider than V columns -- more slices than chunks -- would be gathered by a single block:
+  //  the stage's kernels are thread-per-slot and do not care)
+  if (avg_cols <= g_gather_max_cols && L.nslices <= nchunks) {
     // ---- single-pass gather
     int* src_of;
     PP_TRY(pp_dev_alloc(&src_of, (size_t)L.capacity + 1, s));

@@ -1052,13 +1052,36 @@ __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchPara
     cp_async_commit();
   };
 
+  // Work unit = one vertical slice of a chunk (at most V columns, SellCSigma.h:26-60), not a whole
+  // chunk: a row that holds a large share of the particles (pseudoXGCm's load puts the rounding
+  // shortfall of ~1 M particles into ONE element, test/pseudoXGCm.cpp:253-263) is spread over the
+  // warps instead of being walked by one.  Slices of chunks [chunk_begin, chunk_end): the slices
+  // are sorted by chunk, the range is found by bisection once per warp.
+  // When every chunk fits one slice (the usual case) the unit is the chunk itself.
+  const int* __restrict__ s2c = p.ps.slice_to_chunk;
+  const int* __restrict__ soff = p.ps.offsets;
   const int* __restrict__ cstart = p.ps.chunk_start;
+  const bool by_slice = p.ps.nslices > p.ps.nchunks;
+  int unit_lo = p.chunk_begin, unit_hi = p.chunk_end;
+  if (by_slice) {
+    unit_lo = 0; unit_hi = p.ps.nslices;
+    if (p.chunk_begin > 0 || p.chunk_end < p.ps.nchunks) {
+      int lo = 0, hi = p.ps.nslices;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(s2c + mid) < p.chunk_begin) lo = mid + 1; else hi = mid; }
+      unit_lo = lo;
+      hi = p.ps.nslices;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(s2c + mid) < p.chunk_end) lo = mid + 1; else hi = mid; }
+      unit_hi = lo;
+    }
+  }
   while (true) {
-    int c = 0;
-    if (lane == 0) c = p.chunk_begin + atomicAdd(p.sched, 1);
-    c = __shfl_sync(full, c, 0);
-    if (c >= p.chunk_end) break;
-    const int s0 = __ldg(cstart + c), s1 = __ldg(cstart + c + 1);
+    int sl = 0;
+    if (lane == 0) sl = unit_lo + atomicAdd(p.sched, 1);
+    sl = __shfl_sync(full, sl, 0);
+    if (sl >= unit_hi) break;
+    const int c = by_slice ? __ldg(s2c + sl) : sl;
+    const int s0 = by_slice ? __ldg(soff + sl) : __ldg(cstart + c);
+    const int s1 = by_slice ? __ldg(soff + sl + 1) : __ldg(cstart + c + 1);
     if (s1 <= s0) continue;
     const int ncols = (s1 - s0) >> 5;
     const int rowE = __ldg(p.ps.row_to_element + c * 32 + lane);
@@ -1166,7 +1189,7 @@ pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
     PP_CUDA(cudaGetDevice(&dev));
     PP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int want = pp_div_up(p.chunk_end - p.chunk_begin, WARPS);
+  const int want = pp_div_up(p.ps.nslices > p.ps.nchunks ? p.ps.nslices : p.chunk_end - p.chunk_begin, WARPS);
   const int persistent = g_sm_count * PP_SCS_MINB;
   const int grid = want < persistent ? want : persistent;
   if (push && !LEG && p.push_from_orig) {

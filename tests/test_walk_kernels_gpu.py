@@ -257,3 +257,41 @@ def test_search_mesh_2d_ids_empty_ignores_array_contents(kind, variant):
     assert np.array_equal(ids.cpu().numpy(), ids_o)
     assert (r.found, r.loops) == (int(found), st.loops)
     P.lib().pp_search_set_staged(2)
+
+
+@pytest.mark.parametrize("V", [32, 100, 1024])
+@pytest.mark.parametrize("meshname", ["kuhn8", "plate20"])
+def test_chunk_walk_sliced_wide_rows(meshname, V):
+    """The chunk walk's work unit is a vertical slice (at most V columns): a structure whose widest rows
+    span many slices (pseudoXGCm's load puts ~1 M particles into one element) gives the oracle's ids,
+    also through the host-buffer pipeline that cuts the structure at chunk boundaries."""
+    mesh = _mesh(meshname)
+    P = pp()
+    P.lib().pp_search_set_staged(2)
+    om = orc.OracleMesh(mesh)
+    gm = make_gpu_mesh(mesh)
+    ppe = _uneven_ppe(mesh.nelems, 30000, seed=12)
+    ppe[mesh.nelems // 3] += 4000
+    ppe[mesh.nelems - 1] += 2500
+    ps = make_ps(_kind("scs"), ppe, V=V)
+    slot_elem, mask = ps.slot_elem_and_mask()
+    init = pi.init3d_internal if mesh.dim == 3 else pi.init2d_internal
+    X, D = init(mesh, slot_elem, mask)
+    m = mask.astype(bool)
+    t = torch()
+    dist = 3.0 * pi.push_distance(mesh)
+    T = np.zeros_like(X)
+    T[:, m] = X[:, m] + dist * D[:, m]
+    found, ids_o, _, _, st = om.search_mesh(slot_elem, mask, X, T)
+    ids = t.full((ps.capacity,), -7, dtype=t.int32, device="cuda")
+    tg = t.zeros(3, ps.capacity, dtype=t.float64, device="cuda")
+    r = P.push_direction_search(gm, ps, dev(D), dist, dev(X), tg, ids, elem_ids_empty=True, from_orig=True)
+    assert np.array_equal(ids.cpu().numpy(), ids_o)
+    assert (r.found, r.loops, r.active) == (int(found), st.loops, int(m.sum()))
+    if mesh.dim == 3:
+        hx = t.as_tensor(X).pin_memory(); hd = t.as_tensor(D).pin_memory()
+        ht = t.zeros_like(hx).pin_memory()
+        hi = t.full((ps.capacity,), -9, dtype=t.int32).pin_memory()
+        P.push_direction_search_host(gm, ps, hx, hd, ht, hi, dist, nparts=5)
+        t.cuda.synchronize()
+        assert np.array_equal(hi.numpy(), ids_o)

@@ -160,6 +160,54 @@ def c4(pp, wl, torch, steps, nptcls, plate_n, kind):
             "full_step_ms": tot, "full_steps_per_s": nptcls / (tot * 1e-3), "particles_after": ps.nptcls}
 
 
+def c4x(pp, wl, torch, steps, nptcls, mdl_face, kind):
+    """BASELINE configs[3] on its named mesh: pseudoXGCm's step (test/pseudoXGCm.cpp:504-534) on
+    pumipic-data/xgc/2M.osh (tests/golden/_large/mesh_xgc2M.npz, made by make_large_fixtures.py): the
+    reference's class-limited normal particle load (:167-222) and initial coordinates (:224-264),
+    ellipticalPush 0.5 degrees per step (h, k, d of :470-473), search_mesh_2d(maxLoops = 200),
+    updatePtclPositions, rebuild, gyroScatter forward + backward (3 rings x 8 points, rmax 0.038)."""
+    P = pp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    z = np.load(os.path.join(ROOT, "tests", "golden", "_large", "mesh_xgc2M.npz"))
+    m = HostMesh()
+    m.dim, m.coords, m.elem2verts = 2, z["coords"], z["elem2verts"]
+    m.elem2sides, m.side2verts, m.class_id = z["elem2sides"], z["side2verts"], z["class_id_2"].astype(np.int32)
+    m.nelems, m.nverts = m.elem2verts.shape[0], m.coords.shape[0]
+    gm = pp.Mesh(2, m.coords, m.elem2verts, m.elem2sides, m.side2verts, m.class_id)
+    members = [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float32, 1), (np.float32, 1)]   # pseudoXGCm_types.hpp
+    ppe, total = wl.xgc_source_elements(m.class_id, np.zeros(m.nelems, np.int32), 0, mdl_face, nptcls)
+    ps = pp.ParticleStructure(kind, members, ppe, V=1024, config={"extra_padding": 0.0})   # pseudoXGCm.cpp:452-465
+    cap = ps.capacity
+    slot_elem, mask = ps.slot_elem_and_mask()
+    X = wl.xgc_initial_coords(m, slot_elem, mask)
+    ps.get(0)[:, :cap] = torch.as_tensor(X).cuda()
+    ps.get(2)[0, :cap] = torch.arange(cap, dtype=torch.int32, device="cuda")
+    del X, slot_elem, mask
+    h, k, d = 1.72479370 - .08, .020558260, 0.6
+    P.elliptical_setup(ps, ps.get(0), ps.get(3), ps.get(4), h, k, d)
+    rings, ppr, rmax = 3, 8, 0.038
+    T = Timer(torch)
+    fmap, st = T.run("gyro ring map (setup)", lambda: P.gyro_ring_map(gm, rmax, rings, ppr, 0.0))
+    counts = [ps.nptcls]
+    for it in range(steps + 1):
+        ids = torch.full((ps.capacity,), -1, dtype=torch.int32, device="cuda")
+        T.run("ellipticalPush", lambda: P.elliptical_push(gm, ps, ps.get(1), ps.get(3), ps.get(4), h, k, d, 0.5))
+        T.run("search_mesh_2d", lambda: P.search_mesh(gm, ps, ps.get(0), ps.get(1), ids,
+                                                       variant=P.capi.PP_SEARCH_2D_LEGACY, elem_ids_empty=True,
+                                                       looplimit=200, sync=False))
+        T.run("updatePtclPositions", lambda: P.update_positions(ps, ps.get(0), ps.get(1)))
+        T.run("rebuild", lambda: ps.rebuild(ids))
+        T.run("gyroScatter x2", lambda: (P.gyro_scatter(gm, ps, fmap, rmax, rings, ppr),
+                                         P.gyro_scatter(gm, ps, fmap, rmax, rings, ppr)))
+        counts.append(ps.nptcls)
+    s = T.summary()
+    tot = sum(v["median_ms"] for k_, v in s.items() if "setup" not in k_)
+    return {"config": "c4 on xgc/2M.osh", "particles": int(total), "triangles": m.nelems, "verts": m.nverts,
+            "mdl_face": mdl_face, "elements_loaded": int((ppe > 0).sum()), "max_ppe": int(ppe.max()),
+            "phases": s, "full_step_ms": tot, "full_steps_per_s": total / (tot * 1e-3),
+            "particles_after": counts[-1], "capacity": ps.capacity}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c2,c3,c4")
@@ -167,6 +215,7 @@ def main():
     ap.add_argument("--ps", default="scs")
     ap.add_argument("--c2-particles", type=int, default=10_000_000)
     ap.add_argument("--c4-particles", type=int, default=50_000_000)
+    ap.add_argument("--mdl-face", type=int, default=426, help="c4x: particles go to elements with class id <= this")
     ap.add_argument("--rebuild-mode", type=int, default=2, help="pp_ps_set_staged_rebuild: 2 gather, 1 stage, 0 scatter")
     ap.add_argument("--chunk-order", type=int, default=1, help="pp_ps_set_rebuild_chunk_order")
     ap.add_argument("--shuffling", type=int, default=1, help="pp_ps_set_shuffling")
@@ -187,6 +236,8 @@ def main():
             r = c3(pp, wl, torch, a.steps, 5500, 55_000_000 // 2, kind)
         elif c == "c4":
             r = c4(pp, wl, torch, a.steps, a.c4_particles, 1000, kind)
+        elif c == "c4x":
+            r = c4x(pp, wl, torch, a.steps, a.c4_particles, a.mdl_face, kind)
         else:
             continue
         r["particle_structure"] = a.ps
