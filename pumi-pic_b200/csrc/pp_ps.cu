@@ -80,6 +80,7 @@ PsView pp_ps::view() const {
   v.chunk_start = chunk_start;
   v.nchunks = (cfg.kind == PP_PS_SCS || cfg.kind == PP_PS_CABM) ? nchunks : 0;
   v.nelems = nelems;
+  v.first_chunk = first_chunk;
   return v;
 }
 

@@ -890,6 +890,7 @@ void adopt_layout(pp_ps* ps, ScsLayout& L, cudaStream_t s) {
   if (ps->slot_elem) { pp_dev_free(ps->slot_elem, s); ps->slot_elem = nullptr; }
   ps->slot_elem_valid = false;
   ps->slot_elem_materialized = false;
+  ps->first_chunk = 0;
 }
 
 pp_status member_table(const pp_ps* ps, const std::vector<void*>& src, const std::vector<void*>& dst,
@@ -1044,22 +1045,29 @@ pp_status pp_scs_build(pp_ps* ps, const int* ppe_dev, const int* pelems_dev,
 // ------------------------------------------------------------------------------------------
 // key = 1/256-th of the element range the chunk's first row lies in: one radix pass; chunks of one
 // bucket (~4 K elements) are in flight together anyway
-__global__ void k_chunk_keys(const int* __restrict__ row2elem, int nchunks, unsigned* keys, int* vals) {
+// empty chunks (width 0; on a PICpart that buffers the whole mesh most of them) sort behind all others:
+// the gather only takes the non-empty ones.  nb buckets of the element range (+ 1 for the empty chunks).
+__global__ void k_chunk_keys(const int* __restrict__ row2elem, const int* __restrict__ width, int nchunks,
+                             unsigned nb, unsigned* keys, int* vals) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchunks) return;
-  keys[c] = (unsigned)(((long long)row2elem[c * 32] << 8) / ((long long)nchunks * 32));
+  const unsigned b = (unsigned)(((long long)row2elem[c * 32] * nb) / ((long long)nchunks * 32));
+  keys[c] = (width && width[c] == 0) ? nb : (b < nb - 1 ? b : nb - 1);
   vals[c] = c;
 }
 // chunks of a C = 32 layout in ascending order of (the bucket of) their first row's element
-pp_status chunk_order_build(const int* row_to_element, int nchunks, cudaStream_t s, int** order) {
+pp_status chunk_order_build(const int* row_to_element, const int* width, int nchunks, cudaStream_t s, int** order) {
   *order = nullptr;
   if (nchunks < 2) return PP_OK;
   unsigned *ck_in, *ck_out;
   int* cv_in;
   PP_TRY(pp_dev_alloc(&ck_in, nchunks, s)); PP_TRY(pp_dev_alloc(&ck_out, nchunks, s));
   PP_TRY(pp_dev_alloc(&cv_in, nchunks, s)); PP_TRY(pp_dev_alloc(order, nchunks, s));
-  k_chunk_keys<<<pp_div_up(nchunks, kBlock), kBlock, 0, s>>>(row_to_element, nchunks, ck_in, cv_in);
-  const int ebits = 8;
+  // one radix pass (255 buckets) for structures of up to 64 K chunks, two passes (65535 buckets) above:
+  // on a full-mesh PICpart the particles sit in a small part of the element range
+  const int ebits = nchunks > 65536 ? 16 : 8;
+  k_chunk_keys<<<pp_div_up(nchunks, kBlock), kBlock, 0, s>>>(row_to_element, width, nchunks, (1u << ebits) - 1u,
+                                                             ck_in, cv_in);
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, ck_in, ck_out, cv_in, *order, nchunks, 0, ebits, s);
   char* tmp;
@@ -1311,8 +1319,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
                                                                  L.offsets, L.chunk_start, sc);
   // chunks in ascending order of their first row's element: the order the gather takes them in
   int* order = nullptr;
-  if (g_rebuild_chunk_order && (double)(cap + n_new) <= g_gather_max_cols * 1.3 * 32.0 * nchunks)
-    PP_TRY(chunk_order_build(L.row_to_element, nchunks, s, &order));
+  if (g_rebuild_chunk_order) PP_TRY(chunk_order_build(L.row_to_element, width, nchunks, s, &order));
   pp_dev_free(width, s); pp_dev_free(sizes, s); pp_dev_free(pref, s);
   delete t_build;                                // SCS_rebuild.h:196-265
   // ---- the one host read
@@ -1369,7 +1376,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   // a chunk outgrows what L2 can keep for its neighbours; the record stage (full sectors both ways)
   // is faster there (measured: 50 M particles at 25 per element, 5.3 ms staged vs 6.3 ms gathered;
   // 10 M at 10 per element, 1.08 ms staged vs 0.98 ms gathered)
-  const double avg_cols = (double)L.capacity / (32.0 * nchunks);
+  const int nfull = h.cw_cnt > 0 ? h.cw_cnt : 1;              // chunks that hold particles
+  const double avg_cols = (double)L.capacity / (32.0 * nfull);
   // (a chunk wider than V columns -- more slices than chunks -- would be gathered by a single block:
   //  the stage's kernels are thread-per-slot and do not care)
   if (avg_cols <= g_gather_max_cols && L.nslices <= nchunks) {
@@ -1389,8 +1397,10 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     const double foot = 32.0 * avg_cols * (ut.nunits * 8) * 2.0;
     long blocks = g_gather_bps > 0 ? (long)g_sm_count_scs * g_gather_bps : (long)(g_gather_l2_bytes / (foot > 1 ? foot : 1));
     blocks = std::max<long>(g_sm_count_scs, std::min<long>(blocks, (long)g_sm_count_scs * 7));
-    const int grid = (int)std::min<long>(nchunks, blocks);
-    k_gather_scs<4><<<grid, 4 * 32, 0, s>>>(L.chunk_start, L.row_ppe, order, nchunks, ut, un, src_of, L.mask,
+    // with the chunk order, the non-empty chunks are its first `nfull` entries
+    const int ngather = order ? nfull : nchunks;
+    const int grid = (int)std::min<long>(ngather, blocks);
+    k_gather_scs<4><<<grid, 4 * 32, 0, s>>>(L.chunk_start, L.row_ppe, order, ngather, ut, un, src_of, L.mask,
                                             &sc->next_chunk);
     pp_dev_free(src_of, s);
   } else {
@@ -1421,6 +1431,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     ps->swap_stride = 0;
   }
   ps->nptcls = h.active;
+  ps->first_chunk = (cfg.sigma >= ne && h.cw_cnt <= nchunks) ? nchunks - h.cw_cnt : 0;
   pp_dev_free(order, s);
   pp_dev_free(count, s); pp_dev_free(rank, s); pp_dev_free(kept, s); pp_dev_free(sc, s);
   done = true;

@@ -1190,6 +1190,7 @@ pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
     PP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   const int want = pp_div_up(p.ps.nslices > p.ps.nchunks ? p.ps.nslices : p.chunk_end - p.chunk_begin, WARPS);
+  if (want <= 0) return PP_OK;                         // nothing but empty chunks in the range
   const int persistent = g_sm_count * PP_SCS_MINB;
   const int grid = want < persistent ? want : persistent;
   if (push && !LEG && p.push_from_orig) {
@@ -1283,7 +1284,9 @@ pp_status do_search(pp_mesh* mesh, const PsView& view, int ps_nelems, const pp_s
   p.push_from_orig = push_from_orig;
   p.elem2sides = mesh->elem2sides; p.dual = mesh->dual; p.ndual = 0;
   p.chunk_begin = part ? part->begin : 0;
+  if (p.chunk_begin < view.first_chunk) p.chunk_begin = view.first_chunk;   // leading empty chunks
   p.chunk_end = part ? part->end : view.nchunks;
+  if (p.chunk_begin > p.chunk_end) p.chunk_begin = p.chunk_end;
   p.sched = part ? part->sched : &p.counters->next_chunk;
   if (!part) PP_CUDA(cudaMemsetAsync(mesh->stats_dev, 0, sizeof(SearchCounters), s));
   if (ps->capacity > 0) {

@@ -34,7 +34,7 @@ def block_owner(coords, ev, R):
 
 
 class PicStep:
-    def __init__(self, P, comm, rank, R, cube_per_gpu=55, ppe=10, push_mult=3.0, seed=1234):
+    def __init__(self, P, comm, rank, R, cube_per_gpu=55, ppe=10, push_mult=3.0, seed=1234, overlap_reduce=False):
         import torch
         self.P, self.comm, self.rank, self.R, self.torch = P, comm, rank, R, torch
         n = cube_per_gpu
@@ -86,6 +86,14 @@ class PicStep:
         self.ne = ne
         self.tets_per_gpu = ne // R
         self.charge = torch.zeros(2 * self.nverts, dtype=torch.float64, device="cuda")
+        # overlap_reduce (A/B option, off by default): the field synchronisation runs on its own stream;
+        # nothing of the next step's push + search reads the reduced array (as in pseudoXGCm, whose push
+        # does not use the field), so it may overlap with them; the next step's scatter point, and the
+        # end of the run, wait for it.  Measured on 2 B200: no gain (1.86 vs 1.83 ms per step), the NCCL
+        # kernel competes with the persistent walk kernel for SMs.
+        self.overlap_reduce = overlap_reduce and R > 1
+        self.comm_stream = torch.cuda.Stream() if self.overlap_reduce else None
+        self.reduce_done = None
 
     def step(self, rec=None):
         """one PIC step; rec: dict phase -> list of (start, stop) events, or None"""
@@ -109,8 +117,25 @@ class PicStep:
         timed("updatePtclPositions", lambda: P.update_positions(ps, x, tg))
         ne_d, np_d = timed("setUnsafeProcs", lambda: P.set_unsafe_procs(gm, ps, ids))
         sent, recv = timed("migrate", lambda: P.migrate(ps, self.comm, ne_d, np_d))
-        timed("comm array reduce", lambda: self.comm.array_reduce(self.charge, self.nverts, 2, P.capi.PP_SUM))
+        if not self.overlap_reduce:
+            timed("comm array reduce", lambda: self.comm.array_reduce(self.charge, self.nverts, 2, P.capi.PP_SUM))
+        else:
+            main = torch.cuda.current_stream()
+            if self.reduce_done is not None:         # a scatter of this step would write the array here:
+                main.wait_event(self.reduce_done)    # the previous step's reduction must be through
+            ready = torch.cuda.Event()
+            ready.record(main)                       # the array is complete once the step's work is done
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ready)
+                timed("comm array reduce", lambda: self.comm.array_reduce(self.charge, self.nverts, 2, P.capi.PP_SUM))
+                self.reduce_done = torch.cuda.Event()
+                self.reduce_done.record(self.comm_stream)
         return sent, recv
+
+    def finish(self):
+        """the main stream waits for the last field synchronisation"""
+        if self.reduce_done is not None:
+            self.torch.cuda.current_stream().wait_event(self.reduce_done)
 
     def run(self, steps, warmup, barrier=None):
         """-> dict with per-rank timings (ms) of `steps` timed steps"""
@@ -123,27 +148,28 @@ class PicStep:
         torch.cuda.synchronize()
         n_start = self.ps.nptcls
         rec = {k: [] for k in PHASES}
-        step_ev, sent_tot = [], 0
+        sent_tot = 0
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
         for _ in range(steps):
-            a = torch.cuda.Event(enable_timing=True)
-            b = torch.cuda.Event(enable_timing=True)
-            a.record()
-            sent, _ = self.step(rec)
-            b.record()
-            step_ev.append((a, b))
+            sent, _r = self.step(rec)
             sent_tot += sent
+        self.finish()                                # includes the last (overlapped) field synchronisation
+        t1.record()
         torch.cuda.synchronize()
-        return {"step_ms_total": float(sum(a.elapsed_time(b) for a, b in step_ev)),
+        return {"step_ms_total": float(t0.elapsed_time(t1)),
                 "phase_ms_median": {k: float(np.median([a.elapsed_time(b) for a, b in v])) for k, v in rec.items()},
                 "particles_start": int(n_start), "particles_end": int(self.ps.nptcls), "sent": int(sent_tot)}
 
 
-def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_mult=3.0, timing=False):
+def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_mult=3.0, timing=False,
+                overlap_reduce=False):
     """Collective over the ranks of torch.distributed (when R > 1).  Returns the record on rank 0.
     timing: also record the library's own phase timers (pp_timing_*, rank 0's table in the record)."""
     import torch
     import torch.distributed as dist
-    ps = PicStep(P, comm, rank, R, cube_per_gpu, ppe, push_mult)
+    ps = PicStep(P, comm, rank, R, cube_per_gpu, ppe, push_mult, overlap_reduce=overlap_reduce)
     if timing:
         for _ in range(warmup):
             ps.step()
@@ -179,7 +205,10 @@ def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_m
            "phase_ms": {k: float(t[1 + i].item()) for i, k in enumerate(PHASES)},
            "algorithmic_bytes_per_particle_step": full_step_bytes,
            "achieved_GBs_per_gpu": full_step_bytes * cnt[0].item() / R / (tot_ms / steps * 1e-3) / 1e9,
-           "scaling": "weak", "timing": "CUDA events, max over ranks; phases: median over steps, max over ranks",
+           "scaling": "weak", "timing": "CUDA events around the K steps (incl. the last field synchronisation), max "
+                                        "over ranks; phases: median over steps, max over ranks",
+           "comm_array_reduce": ("on its own stream, overlapped with the next step's push + search + migration"
+                                 if ps.overlap_reduce else "in line"),
            "transport": "peer-memory window (NVLink P2P stores, no host round trip)" if comm.p2p_active
                         else ("NCCL AllGather + grouped Send/Recv" if R > 1 else "single rank")}
     if table is not None:
