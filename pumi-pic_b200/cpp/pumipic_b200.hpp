@@ -72,6 +72,18 @@ inline void cuda_check(cudaError_t e, const char* what) {
   }
 }
 
+// ---------------------------------------------------------------- timing (support/ppTiming.hpp:28-75)
+// The library's phases record themselves under the reference's labels; these are the calls an
+// application already makes.
+enum TimingSortOption { SORT_ALPHA, SORT_ORDER, SORT_LONGEST, SORT_SHORTEST };
+inline void SetTimingVerbosity(int verbosity) { pp_timing_set_verbosity(verbosity); }
+inline void EnableTiming() { pp_timing_enable(1); }
+inline void DisableTiming() { pp_timing_enable(0); }
+inline void RecordTime(const std::string& str, double seconds, double /*prebarrierTime*/ = 0.0) {
+  pp_timing_record(str.c_str(), seconds);
+}
+inline void SummarizeTime(TimingSortOption sort = SORT_ALPHA) { pp_timing_summarize((int)sort); }
+
 // ---------------------------------------------------------------- device array
 template <class T>
 class View {

@@ -869,10 +869,10 @@ __global__ void __launch_bounds__(BLOCK, (DIM == 3 ? 3 : 4)) k_walk_bcc(SearchPa
 //     once, 2 % need four hops or more);
 //   * chunks are handed out by an atomic counter, there is no block-level synchronisation.
 #ifndef PP_SCS_MINB
-#define PP_SCS_MINB 4        // resident 128-thread blocks per SM the chunk walk is compiled for
+#define PP_SCS_MINB 5        // resident 128-thread blocks per SM the chunk walk is compiled for (20 warps: measured +6.6 % over 4)
 #endif
 #ifndef PP_SCS_RING
-#define PP_SCS_RING 3
+#define PP_SCS_RING 1        // depth 1..3 measured equal at 16 warps/SM; 1 leaves shared memory for the fifth block
 #endif
 constexpr int kQCap = 64;    // queue entries per warp; a full warp of work is drained at once
 constexpr int kRing = PP_SCS_RING;   // particle columns in flight per warp (cp.async ring)
