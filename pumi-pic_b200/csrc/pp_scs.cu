@@ -219,27 +219,27 @@ __global__ void k_hist_kept(PsView v, const int* __restrict__ new_elem, int* cou
 // rank_out: the particle's rank in its element, behind the kept particles counted before (stream order)
 __global__ void k_hist_new(const int* __restrict__ elems, int n, int* count, int* bad,
                            const int* __restrict__ n_dev = nullptr, int* rank_out = nullptr) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
-  if (i >= n) return;
-  const int e = elems[i];
-  if (e < 0) { *bad = 1; if (rank_out) rank_out[i] = 0; return; }
-  const int r = atomicAdd(count + e, 1);
-  if (rank_out) rank_out[i] = r;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int e = elems[i];
+    if (e < 0) { *bad = 1; if (rank_out) rank_out[i] = 0; continue; }
+    const int r = atomicAdd(count + e, 1);
+    if (rank_out) rank_out[i] = r;
+  }
 }
 // new particles: src_of[slot of (element, rank)] = -(i + 1)
 __global__ void k_invmap_new_ranked(const int* __restrict__ elems, const int* __restrict__ rank, int n,
                                     const int* __restrict__ elem2row, const int* __restrict__ chunk_start,
                                     int* src_of, int* slots, const int* __restrict__ n_dev) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
-  if (i >= n) return;
-  const int e = elems[i];
-  if (e < 0) return;
-  const int row = __ldg(elem2row + e);
-  const int slot = __ldg(chunk_start + (row >> 5)) + (rank[i] << 5) + (row & 31);
-  if (src_of) src_of[slot] = -i - 1;
-  if (slots) slots[i] = slot;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int e = elems[i];
+    if (e < 0) continue;
+    const int row = __ldg(elem2row + e);
+    const int slot = __ldg(chunk_start + (row >> 5)) + (rank[i] << 5) + (row & 31);
+    if (src_of) src_of[slot] = -i - 1;
+    if (slots) slots[i] = slot;
+  }
 }
 
 struct MemberTable {
@@ -517,12 +517,12 @@ __global__ void __launch_bounds__(256) k_stage_pack(PsView v, const int* __restr
 __global__ void __launch_bounds__(256) k_stage_pack_new(const int* __restrict__ slots, int n,
                                                         const __grid_constant__ UnitTable t, char* stage,
                                                         const int* __restrict__ n_dev = nullptr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = min(n, *n_dev);
-  if (i >= n) return;
-  uint4 first[kGroup];
-  load_group(t, 0, i, first);
-  pack_record(t, i, reinterpret_cast<uint4*>(stage + (long)slots[i] * t.rec_stride), first);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint4 first[kGroup];
+    load_group(t, 0, i, first);
+    pack_record(t, i, reinterpret_cast<uint4*>(stage + (long)slots[i] * t.rec_stride), first);
+  }
 }
 __device__ __forceinline__ void unpack_record(const UnitTable& t, const char* stage, long slot) {
   const uint4* rec = reinterpret_cast<const uint4*>(stage + slot * t.rec_stride);
@@ -1104,6 +1104,63 @@ __global__ void k_count_stats(const int* __restrict__ a, int n, FastScal* out) {
   }
 }
 
+// k_count_stats + k_sort_keys in one pass over the counts
+template <class Key>
+__global__ void k_stats_keys(const int* __restrict__ a, int n, int sigma, int cbits, Key* keys, int* vals,
+                             FastScal* out) {
+  __shared__ int p_nz[kBlock / 32], p_sum[kBlock / 32], p_max[kBlock / 32];
+  int nz = 0, sum = 0, mx = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int v = a[i];
+    nz += v > 0; sum += v; mx = max(mx, v);
+    const Key win = (Key)(i / sigma);
+    keys[i] = (win << cbits) | (Key)(uint32_t)v;
+    vals[i] = (int)i;
+  }
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) { p_nz[threadIdx.x >> 5] = nz; p_sum[threadIdx.x >> 5] = sum; p_max[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kBlock / 32; ++w) { nz += p_nz[w]; sum += p_sum[w]; mx = max(mx, p_max[w]); }
+    if (nz) atomicAdd(&out->nnz, nz);
+    if (sum) atomicAdd(&out->active, sum);
+    if (mx) atomicMax(&out->maxcount, mx);
+  }
+}
+// k_rows + k_chunk_widths for C = 32: one warp per chunk, lane = row
+__global__ void k_rows_widths(const int* __restrict__ sorted_elem, const int* __restrict__ ppe, int ne, int nchunks,
+                              int* row2elem, int* elem2row, int* row_ppe, int* width, int* cw, double* inv) {
+  __shared__ int p_sum[kBlock / 32], p_cnt[kBlock / 32];
+  __shared__ double p_inv[kBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int sum = 0, cnt = 0;
+  double isum = 0.0;
+  for (long c = blockIdx.x * (long)(kBlock / 32) + wid; c < nchunks; c += (long)gridDim.x * (kBlock / 32)) {
+    const int i = (int)c * 32 + lane;
+    int np = 0;
+    if (i < ne) {
+      const int e = sorted_elem ? sorted_elem[i] : i;
+      np = ppe[e];
+      row2elem[i] = e; elem2row[e] = i; row_ppe[i] = np;
+    } else {               // padding rows up to a multiple of C (SCS_buildFns.h:39-44)
+      row2elem[i] = i; elem2row[i] = i; row_ppe[i] = 0;
+    }
+    const int w = __reduce_max_sync(0xffffffffu, np);
+    if (lane == 0) {
+      width[c] = w;
+      if (w > 0) { sum += w; cnt += 1; isum += 1.0 / w; }
+    }
+  }
+  if (lane == 0) { p_sum[wid] = sum; p_cnt[wid] = cnt; p_inv[wid] = isum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kBlock / 32; ++w) { sum += p_sum[w]; cnt += p_cnt[w]; isum += p_inv[w]; }
+    if (cnt) { atomicAdd(cw, sum); atomicAdd(cw + 1, cnt); atomicAdd(inv, isum); }
+  }
+}
+
 // padding (SCS_buildFns.h:62-97) + slices per chunk + slots per chunk in one pass
 __global__ void k_chunk_sizes(int* width, int nchunks, const FastScal* __restrict__ sc, double pad, int strat,
                               int V, int C, int2* sizes) {
@@ -1240,6 +1297,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   PP_TRY(pp_dev_alloc(&count, ne + 1, s));
   PP_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ne + 1), s));
   int* rank_new = nullptr;
+  // new-particle kernels: grid-stride; a device-side count (n_new is only a bound then) gets a fixed grid
+  const int new_grid = n_new_dev ? std::min(pp_div_up(n_new, kBlock), 1184) : pp_div_up(n_new, kBlock);
   {
     PP_TIME_KIND(s, ps->cfg.kind, "count active particles");       // SCS_rebuild.h:133-166
     if (cap > 0) {
@@ -1248,10 +1307,9 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     }
     if (n_new > 0) {               // counted after the kept particles: their ranks follow the kept ones
       PP_TRY(pp_dev_alloc(&rank_new, n_new, s));
-      k_hist_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, n_new, count, &sc->bad, n_new_dev,
-                                                             rank_new);
+      k_hist_new<<<new_grid, kBlock, 0, s>>>(new_particle_elements, n_new, count, &sc->bad, n_new_dev, rank_new);
     }
-    k_count_stats<<<std::min(pp_div_up(ne, kBlock), 592), kBlock, 0, s>>>(count, ne, sc);
+    if (cfg.sigma <= 1) k_count_stats<<<std::min(pp_div_up(ne, kBlock), 592), kBlock, 0, s>>>(count, ne, sc);
   }
   PPTimeScope* t_build = new PPTimeScope(s, (std::string(pp_kind_name(ps->cfg.kind)) + " SCS specific building").c_str());
   // ---- layout (scs_layout above, without its host reads)
@@ -1270,7 +1328,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     if (cbits + wbits <= 32) {       // the usual case (one window, or few): half the key traffic
       uint32_t *k_in, *k_out;
       PP_TRY(pp_dev_alloc(&k_in, ne, s)); PP_TRY(pp_dev_alloc(&k_out, ne, s));
-      k_sort_keys<uint32_t><<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(count, ne, sigma, cbits, k_in, v_in);
+      k_stats_keys<uint32_t><<<std::min(pp_div_up(ne, kBlock), 1184), kBlock, 0, s>>>(count, ne, sigma, cbits, k_in, v_in, sc);
       cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s);
       PP_TRY(pp_dev_alloc(&tmp, tb, s));
       PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s));
@@ -1278,7 +1336,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     } else {
       uint64_t *k_in, *k_out;
       PP_TRY(pp_dev_alloc(&k_in, ne, s)); PP_TRY(pp_dev_alloc(&k_out, ne, s));
-      k_sort_keys<uint64_t><<<pp_div_up(ne, kBlock), kBlock, 0, s>>>(count, ne, sigma, cbits, k_in, v_in);
+      k_stats_keys<uint64_t><<<std::min(pp_div_up(ne, kBlock), 1184), kBlock, 0, s>>>(count, ne, sigma, cbits, k_in, v_in, sc);
       cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s);
       PP_TRY(pp_dev_alloc(&tmp, tb, s));
       PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, sorted_elem, ne, 0, cbits + wbits, s));
@@ -1289,16 +1347,14 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   PP_TRY(pp_dev_alloc(&L.row_to_element, nrows, s));
   PP_TRY(pp_dev_alloc(&L.element_to_row, nrows, s));
   PP_TRY(pp_dev_alloc(&L.row_ppe, nrows, s));
-  k_rows<<<pp_div_up(nrows, kBlock), kBlock, 0, s>>>(sorted_elem, count, ne, nrows, L.row_to_element,
-                                                    L.element_to_row, L.row_ppe);
-  pp_dev_free(sorted_elem, s);
   int* width;
   int2 *sizes, *pref;
   PP_TRY(pp_dev_alloc(&width, nchunks, s));
   PP_TRY(pp_dev_alloc(&sizes, nchunks + 1, s));
   PP_TRY(pp_dev_alloc(&pref, nchunks + 1, s));
-  k_chunk_widths<<<std::min(pp_div_up((long)nchunks * 32, kBlock), 1184), kBlock, 0, s>>>(
-      L.row_ppe, nchunks, C, width, &sc->cw_sum, &sc->inv);
+  k_rows_widths<<<std::min(pp_div_up((long)nchunks * 32, kBlock), 2368), kBlock, 0, s>>>(
+      sorted_elem, count, ne, nchunks, L.row_to_element, L.element_to_row, L.row_ppe, width, &sc->cw_sum, &sc->inv);
+  pp_dev_free(sorted_elem, s);
   k_chunk_sizes<<<pp_div_up(nchunks + 1, kBlock), kBlock, 0, s>>>(width, nchunks, sc, cfg.shuffle_padding,
                                                                  cfg.padding_strat, V, C, sizes);
   {
@@ -1388,9 +1444,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
       k_invmap<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, rank, L.element_to_row,
                                                         L.chunk_start, src_of);
     if (n_new > 0) {
-      k_invmap_new_ranked<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, rank_new, n_new,
-                                                                      L.element_to_row, L.chunk_start, src_of,
-                                                                      nullptr, n_new_dev);
+      k_invmap_new_ranked<<<new_grid, kBlock, 0, s>>>(new_particle_elements, rank_new, n_new, L.element_to_row,
+                                                      L.chunk_start, src_of, nullptr, n_new_dev);
       unit_table(ps, new_particle_info, new_ld, &ps->swap, ps->swap_stride, un);
     }
     // blocks in flight: their chunks' source sectors (fetched as whole 64-byte DRAM atoms) must fit L2
@@ -1411,11 +1466,10 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
                                rank, ut, ps->stage, s));
     if (n_new > 0) {
       PP_TRY(pp_dev_alloc(&slots, n_new, s));
-      k_invmap_new_ranked<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(new_particle_elements, rank_new, n_new,
-                                                                      L.element_to_row, L.chunk_start, nullptr,
-                                                                      slots, n_new_dev);
+      k_invmap_new_ranked<<<new_grid, kBlock, 0, s>>>(new_particle_elements, rank_new, n_new, L.element_to_row,
+                                                      L.chunk_start, nullptr, slots, n_new_dev);
       unit_table(ps, new_particle_info, new_ld, nullptr, 0, un);
-      k_stage_pack_new<<<pp_div_up(n_new, kBlock), kBlock, 0, s>>>(slots, n_new, un, ps->stage, n_new_dev);
+      k_stage_pack_new<<<new_grid, kBlock, 0, s>>>(slots, n_new, un, ps->stage, n_new_dev);
     }
     k_stage_unpack_scs<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(layout_view(L, ne), L.row_ppe, ut,
                                                                         ps->stage, L.mask);
