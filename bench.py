@@ -537,7 +537,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         try:
             import mgpu_worker
-            par = mgpu_worker.pic_loop_parity(P, comm, rank, world, steps=4)
+            par = mgpu_worker.pic_loop_parity(P, comm, rank, world, steps=4, fuse_update=True)
         except Exception as ex:  # the checker must not take the measurement down with it
             par = {"error": repr(ex)[:200]}
         if picstep is not None:

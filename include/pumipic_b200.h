@@ -354,6 +354,15 @@ pp_status pp_ps_rebuild(pp_ps* ps, const int32_t* new_element, int32_t n_new,
                         const int32_t* new_particle_elements,
                         const void* const* new_particle_info, pp_stream stream);
 
+/* One-shot member remap of the NEXT pp_ps_rebuild / pp_ps_migrate of this structure: in the rebuilt
+ * structure member i holds what member src_member[i] held before (-1: zeros); src_member[i] must have
+ * member i's type and feed at most one destination; n = number of members (0 clears).  Particles
+ * received or added by that call are remapped the same way (they travel in the old member order).
+ * This folds the reference drivers' updatePtclPositions (x <- xtgt, xtgt <- 0,
+ * test/pseudoPushAndSearch.cpp:142-154) into the record move the rebuild does anyway: one pass over the
+ * particles less, and the zero-filled members are not read at all.  Same result for every particle
+ * that survives the rebuild. */
+pp_status pp_ps_set_rebuild_remap(pp_ps* ps, const int32_t* src_member, int32_t n);
 /* Record move of a full re-layout.  2 (default): device-side layout with one host read per rebuild;
  * narrow structures (<= 14 columns per chunk on average) then gather the records in one pass in
  * destination order, the destination chunks handed out in element order so that gathered source

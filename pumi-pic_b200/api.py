@@ -428,6 +428,12 @@ class ParticleStructure:
             return torch.empty((nc, 0), dtype=tdt, device="cuda")
         return _tensor_from_ptr(base.value, (nc, stride.value), tdt, self)
 
+    def set_rebuild_remap(self, src_member):
+        """one-shot: after the next rebuild / migrate member i holds what member src_member[i] held
+        (-1: zeros); e.g. [1, -1, 2, 3] = updatePtclPositions folded into the record move"""
+        a = np.ascontiguousarray(src_member, np.int32)
+        check(lib().pp_ps_set_rebuild_remap(self.h, _np_ptr(a), int(a.shape[0])))
+
     def rebuild(self, new_element, new_particle_elements=None, new_particle_info=None):
         """ParticleStructure::rebuild: all arguments are device tensors ([ncomp, n_new] members)."""
         n_new = 0 if new_particle_elements is None else int(new_particle_elements.shape[0])

@@ -136,6 +136,7 @@ PROTOTYPES = {
     "pp_ps_get_pids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pp_ps_rebuild": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                 C.POINTER(C.c_void_p), C.c_void_p]),
+    "pp_ps_set_rebuild_remap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "pp_ps_set_staged_rebuild": (None, [C.c_int32]),
     "pp_ps_set_rebuild_chunk_order": (None, [C.c_int32]),
     "pp_ps_set_rebuild_tuning": (None, [C.c_int32, C.c_int32]),

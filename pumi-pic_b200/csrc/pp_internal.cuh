@@ -189,6 +189,7 @@ struct PsView {  // what kernels need to map slot -> (row element, mask)
   const int* chunk_start = nullptr;   // [nchunks+1]
   int nchunks = 0;
   int nelems = 0;
+  std::vector<int> rebuild_remap;   // one-shot member remap of the next rebuild (pp_ps_set_rebuild_remap)
   int first_chunk = 0;                // chunks [0, first_chunk) hold no particle
 };
 
@@ -221,6 +222,7 @@ struct pp_ps {
   char* stage;              // record stage of the rebuild (grow-only scratch)
   int shuffle_skip = 0;     // rebuilds to wait before the next reshuffle attempt
   int shuffle_streak = 0;   // consecutive failed reshuffle attempts
+  std::vector<int> rebuild_remap;   // one-shot member remap of the next rebuild (pp_ps_set_rebuild_remap)
   int first_chunk = 0;      // chunks before this one are empty (single sort window: empty rows lead)
   int ppe_bits_hint = 0;    // key bits of the row sort guessed from the last rebuild's largest row (0 = none)
   size_t stage_bytes;

@@ -406,9 +406,10 @@ struct UnitTable {
   char* db[kMaxUnits];
 };
 
+// a null source is a member that the rebuild zero-fills (pp_ps_set_rebuild_remap)
 __device__ __forceinline__ unsigned long long unit_load(const UnitTable& t, int u, long s) {
-  if (t.kind[u] == 0) return *reinterpret_cast<const unsigned long long*>(t.sa[u] + 8 * s);
-  const unsigned lo = *reinterpret_cast<const unsigned*>(t.sa[u] + 4 * s);
+  if (t.kind[u] == 0) return t.sa[u] ? *reinterpret_cast<const unsigned long long*>(t.sa[u] + 8 * s) : 0ull;
+  const unsigned lo = t.sa[u] ? *reinterpret_cast<const unsigned*>(t.sa[u] + 4 * s) : 0u;
   const unsigned hi = t.sb[u] ? *reinterpret_cast<const unsigned*>(t.sb[u] + 4 * s) : 0u;
   return (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
@@ -577,8 +578,9 @@ pp_status launch_stage_pack(const PsView& v, const int* new_elem, const int* ele
 }
 
 // Build the unit table of a structure; false if a member cannot be expressed in 4/8-byte units.
+// remap (or null): destination member i is read from source member remap[i], -1 = zero-filled
 bool unit_table(const pp_ps* ps, const void* const* src, long src_stride, const std::vector<void*>* dst,
-                long dst_stride, UnitTable& t) {
+                long dst_stride, UnitTable& t, const int* remap = nullptr) {
   t.nunits = 0;
   int n4 = 0;
   // 8-byte scalars first, then pairs of 4-byte scalars: natural alignment inside the record
@@ -588,7 +590,8 @@ bool unit_table(const pp_ps* ps, const void* const* src, long src_stride, const 
       if (sb != 4 && sb != 8) return false;
       if ((pass == 0) != (sb == 8)) continue;
       for (int c = 0; c < ps->members[i].ncomp; ++c) {
-        const char* sp = src ? (const char*)src[i] + (size_t)c * src_stride * sb : nullptr;
+        const int si = remap ? remap[i] : i;
+        const char* sp = (src && si >= 0) ? (const char*)src[si] + (size_t)c * src_stride * sb : nullptr;
         char* dp = dst ? (char*)(*dst)[i] + (size_t)c * dst_stride * sb : nullptr;
         if (sb == 8) {
           if (t.nunits >= kMaxUnits) return false;
@@ -1279,7 +1282,7 @@ double g_gather_max_cols = 14.0; // average columns per chunk up to which the ga
 // returns done = false when a speculation failed (nothing of the structure has changed then)
 pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const int* n_new_dev, long new_ld,
                              const int* new_particle_elements, const void* const* new_particle_info,
-                             cudaStream_t s, bool& done) {
+                             const int* remap, cudaStream_t s, bool& done) {
   done = false;
   const int ne = ps->nelems, C = 32, cap = ps->capacity;
   const pp_ps_config& cfg = ps->cfg;
@@ -1419,7 +1422,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   }
   std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
   UnitTable ut, un;
-  unit_table(ps, old_src.data(), ps->stride, &ps->swap, ps->swap_stride, ut);
+  unit_table(ps, old_src.data(), ps->stride, &ps->swap, ps->swap_stride, ut, remap);
   un = ut;
   if (!g_sm_count_scs) {
     int dev = 0;
@@ -1446,7 +1449,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     if (n_new > 0) {
       k_invmap_new_ranked<<<new_grid, kBlock, 0, s>>>(new_particle_elements, rank_new, n_new, L.element_to_row,
                                                       L.chunk_start, src_of, nullptr, n_new_dev);
-      unit_table(ps, new_particle_info, new_ld, &ps->swap, ps->swap_stride, un);
+      unit_table(ps, new_particle_info, new_ld, &ps->swap, ps->swap_stride, un, remap);
     }
     // blocks in flight: their chunks' source sectors (fetched as whole 64-byte DRAM atoms) must fit L2
     const double foot = 32.0 * avg_cols * (ut.nunits * 8) * 2.0;
@@ -1468,7 +1471,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
       PP_TRY(pp_dev_alloc(&slots, n_new, s));
       k_invmap_new_ranked<<<new_grid, kBlock, 0, s>>>(new_particle_elements, rank_new, n_new, L.element_to_row,
                                                       L.chunk_start, nullptr, slots, n_new_dev);
-      unit_table(ps, new_particle_info, new_ld, nullptr, 0, un);
+      unit_table(ps, new_particle_info, new_ld, nullptr, 0, un, remap);
       k_stage_pack_new<<<new_grid, kBlock, 0, s>>>(slots, n_new, un, ps->stage, n_new_dev);
     }
     k_stage_unpack_scs<<<pp_div_up(L.capacity, kBlock), kBlock, 0, s>>>(layout_view(L, ne), L.row_ppe, ut,
@@ -1516,6 +1519,9 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
   const int kind = ps->cfg.kind;
   PP_TIME_KIND(s, kind, "rebuild");              // SCS_rebuild.h:312, CSR_rebuild.hpp:116
   const void* const* new_particle_info = new_particle_info_in;
+  std::vector<int> remap_v;
+  remap_v.swap(ps->rebuild_remap);               // one-shot (pp_ps_set_rebuild_remap)
+  const int* remap = remap_v.empty() ? nullptr : remap_v.data();
   // ---- Sell-C-sigma with C = 32, sparse rows: device-side layout + single-pass move
   if ((kind == PP_PS_SCS || kind == PP_PS_CABM) && g_staged_rebuild >= 2 && ps->cfg.team_size == 32 &&
       ne >= 32 && (long)ps->nptcls < (long)g_rank_sort_ppe * ne &&
@@ -1528,7 +1534,7 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
     if (unit_table(ps, old_src.data(), ps->stride, nullptr, 0, probe)) {
       bool done = false;
       PP_TRY(rebuild_scs_gather(ps, new_element, n_new, n_new_dev, new_ld, new_particle_elements,
-                                new_particle_info, s, done));
+                                new_particle_info, remap, s, done));
       if (done) {
         if (g_try_shuffling && ps->shuffle_skip > 0) --ps->shuffle_skip;
         return PP_OK;
@@ -1555,6 +1561,41 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
       compact_ptrs.push_back(q);
     }
     new_particle_info = compact_ptrs.data();
+  }
+  // member remap on the general path: permute the member arrays (each source feeds at most one
+  // destination), zero-fill the rest; the arrays of the particles being added are permuted the same way
+  std::vector<const void*> remapped_info;
+  if (remap) {
+    const int nm = ps->nmembers;
+    std::vector<void*> nd(nm, nullptr);
+    std::vector<char> used(nm, 0);
+    for (int i = 0; i < nm; ++i)
+      if (remap[i] >= 0) { nd[i] = ps->data[remap[i]]; used[remap[i]] = 1; }
+    for (int i = 0; i < nm; ++i) {
+      if (remap[i] >= 0) continue;
+      const size_t bytes = (size_t)ps->members[i].scalar_bytes * ps->members[i].ncomp * (size_t)ps->stride;
+      for (int j = 0; j < nm && !nd[i]; ++j)
+        if (!used[j] && ps->members[j].scalar_bytes == ps->members[i].scalar_bytes &&
+            ps->members[j].ncomp == ps->members[i].ncomp) { nd[i] = ps->data[j]; used[j] = 1; }
+      if (!nd[i]) { char* q; PP_TRY(pp_dev_alloc(&q, bytes, s)); nd[i] = q; }
+      PP_CUDA(cudaMemsetAsync(nd[i], 0, bytes ? bytes : 1, s));
+    }
+    for (int j = 0; j < nm; ++j)
+      if (!used[j]) pp_dev_free((char*)ps->data[j], s);
+    ps->data = nd;
+    if (n_new > 0) {
+      remapped_info.assign(nm, nullptr);
+      for (int i = 0; i < nm; ++i) {
+        if (remap[i] >= 0) { remapped_info[i] = new_particle_info[remap[i]]; continue; }
+        const size_t bytes = (size_t)ps->members[i].scalar_bytes * ps->members[i].ncomp * (size_t)n_new;
+        char* q;
+        PP_TRY(pp_dev_alloc(&q, bytes, s));
+        PP_CUDA(cudaMemsetAsync(q, 0, bytes ? bytes : 1, s));
+        compacted.push_back(q);
+        remapped_info[i] = q;
+      }
+      new_particle_info = remapped_info.data();
+    }
   }
   struct FreeCompacted {
     std::vector<char*>& v; cudaStream_t s;
@@ -1860,6 +1901,28 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
   ps->nptcls = active;
   pp_dev_free(row_fill, s); pp_dev_free(count, s); pp_dev_free(tot_dev, s); pp_dev_free(scal, s);
   pp_dev_free(rank, s); pp_dev_free(kept, s);
+  return PP_OK;
+}
+
+// one-shot member remap of the next rebuild / migrate: destination member i <- source member
+// src_member[i] (-1: zero).  updatePtclPositions (x <- xtgt, xtgt <- 0) folded into the record move.
+extern "C" pp_status pp_ps_set_rebuild_remap(pp_ps* ps, const int32_t* src_member, int32_t n) {
+  PP_REQUIRE(ps && (n == 0 || (src_member && n == ps->nmembers)), "one entry per member");
+  std::vector<int> m(src_member, src_member + n);
+  std::vector<char> used((size_t)n, 0);
+  bool identity = true;
+  for (int i = 0; i < n; ++i) {
+    PP_REQUIRE(m[i] >= -1 && m[i] < n, "source member out of range");
+    if (m[i] != i) identity = false;
+    if (m[i] < 0) continue;
+    PP_REQUIRE(!used[m[i]], "a member may feed at most one destination");
+    used[m[i]] = 1;
+    PP_REQUIRE(ps->members[m[i]].scalar_bytes == ps->members[i].scalar_bytes &&
+                   ps->members[m[i]].ncomp == ps->members[i].ncomp,
+               "source and destination member must have the same type");
+  }
+  if (identity) m.clear();
+  ps->rebuild_remap = m;
   return PP_OK;
 }
 

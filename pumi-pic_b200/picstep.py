@@ -34,7 +34,7 @@ def block_owner(coords, ev, R):
 
 
 class PicStep:
-    def __init__(self, P, comm, rank, R, cube_per_gpu=55, ppe=10, push_mult=3.0, seed=1234, overlap_reduce=False):
+    def __init__(self, P, comm, rank, R, cube_per_gpu=55, ppe=10, push_mult=3.0, seed=1234, overlap_reduce=False, fuse_update=True):
         import torch
         self.P, self.comm, self.rank, self.R, self.torch = P, comm, rank, R, torch
         n = cube_per_gpu
@@ -86,6 +86,9 @@ class PicStep:
         self.ne = ne
         self.tets_per_gpu = ne // R
         self.charge = torch.zeros(2 * self.nverts, dtype=torch.float64, device="cuda")
+        # fuse_update: updatePtclPositions (x <- xtgt, xtgt <- 0) is not a pass of its own but a member
+        # remap of the record move that ends the migration (pp_ps_set_rebuild_remap)
+        self.fuse_update = fuse_update
         # overlap_reduce (A/B option, off by default): the field synchronisation runs on its own stream;
         # nothing of the next step's push + search reads the reduced array (as in pseudoXGCm, whose push
         # does not use the field), so it may overlap with them; the next step's scatter point, and the
@@ -114,7 +117,10 @@ class PicStep:
         ids = torch.empty(max(ps.capacity, 1), dtype=torch.int32, device="cuda")
         timed("push+search", lambda: P.push_direction_search(gm, ps, dr, self.push, x, tg, ids, elem_ids_empty=True,
                                                             from_orig=True, sync=False))
-        timed("updatePtclPositions", lambda: P.update_positions(ps, x, tg))
+        if self.fuse_update:
+            timed("updatePtclPositions", lambda: ps.set_rebuild_remap([1, -1, 2, 3]))
+        else:
+            timed("updatePtclPositions", lambda: P.update_positions(ps, x, tg))
         ne_d, np_d = timed("setUnsafeProcs", lambda: P.set_unsafe_procs(gm, ps, ids))
         sent, recv = timed("migrate", lambda: P.migrate(ps, self.comm, ne_d, np_d))
         if not self.overlap_reduce:
@@ -164,12 +170,13 @@ class PicStep:
 
 
 def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_mult=3.0, timing=False,
-                overlap_reduce=False):
+                overlap_reduce=False, fuse_update=True):
     """Collective over the ranks of torch.distributed (when R > 1).  Returns the record on rank 0.
     timing: also record the library's own phase timers (pp_timing_*, rank 0's table in the record)."""
     import torch
     import torch.distributed as dist
-    ps = PicStep(P, comm, rank, R, cube_per_gpu, ppe, push_mult, overlap_reduce=overlap_reduce)
+    ps = PicStep(P, comm, rank, R, cube_per_gpu, ppe, push_mult, overlap_reduce=overlap_reduce,
+                 fuse_update=fuse_update)
     if timing:
         for _ in range(warmup):
             ps.step()
@@ -207,6 +214,9 @@ def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_m
            "achieved_GBs_per_gpu": full_step_bytes * cnt[0].item() / R / (tot_ms / steps * 1e-3) / 1e9,
            "scaling": "weak", "timing": "CUDA events around the K steps (incl. the last field synchronisation), max "
                                         "over ranks; phases: median over steps, max over ranks",
+           "updatePtclPositions": ("folded into the record move of the migration's rebuild (pp_ps_set_rebuild_remap: "
+                                   "x <- xtgt, xtgt <- 0 as a member remap; the phase time is the setter call)"
+                                   if ps.fuse_update else "own pass (pp_update_positions)"),
            "comm_array_reduce": ("on its own stream, overlapped with the next step's push + search + migration"
                                  if ps.overlap_reduce else "in line"),
            "transport": "peer-memory window (NVLink P2P stores, no host round trip)" if comm.p2p_active

@@ -150,7 +150,7 @@ def test_comm_array(P, comm, rank, R):
         print("comm arrays ok on %d ranks" % R)
 
 
-def pic_loop_parity(P, comm, rank, R, steps=6, n=8, nptcl=40000):
+def pic_loop_parity(P, comm, rank, R, steps=6, n=8, nptcl=40000, fuse_update=False):
     """The multi-rank PIC loop (fused push+search -> updatePtclPositions -> setUnsafeProcs -> migrate)
     on a block-partitioned Kuhn cube against the serial CPU oracle on the whole particle set, by
     particle id.  Returns mismatch counts (all ranks return the same dict); also called by bench.py's
@@ -192,7 +192,10 @@ def pic_loop_parity(P, comm, rank, R, steps=6, n=8, nptcl=40000):
         x, tg, pid, dr = ps.get(0), ps.get(1), ps.get(2), ps.get(3)
         ids = torch.zeros(max(cap, 1), dtype=torch.int32, device="cuda")
         P.push_direction_search(gm, ps, dr, dist_push, x, tg, ids, elem_ids_empty=True, from_orig=True)
-        P.update_positions(ps, x, tg)
+        if fuse_update and it % 2 == 0:         # updatePtclPositions as a member remap of the rebuild
+            ps.set_rebuild_remap([1, -1, 2, 3])
+        else:
+            P.update_positions(ps, x, tg)
         ne_d, np_d = P.set_unsafe_procs(gm, ps, ids)
         sent, _ = P.migrate(ps, comm, ne_d, np_d)
         # oracle step
@@ -232,6 +235,8 @@ def pic_loop_parity(P, comm, rank, R, steps=6, n=8, nptcl=40000):
 def test_pic_loop(P, comm, rank, R, steps=6):
     r = pic_loop_parity(P, comm, rank, R, steps)
     assert r["mismatch"] == 0, r
+    r2 = pic_loop_parity(P, comm, rank, R, steps, fuse_update=True)
+    assert r2["mismatch"] == 0 and r2["alive_at_end"] == r["alive_at_end"], r2
     assert R == 1 or r["migrated"] > 0
     if rank == 0:
         print("PIC loop parity ok on %d ranks: %d of %d particles still in the domain, %d migrations"

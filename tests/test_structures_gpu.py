@@ -356,3 +356,64 @@ def test_reshuffle_keeps_the_layout_when_movers_fit(kindname, _default_rebuild_m
     new_element = np.where(m, slot_elem, -1).astype(np.int32)
     ps.rebuild(dev(new_element))
     _check(ps, new_element, cap, np_expected=int(m.sum()))
+
+
+PIC_TYPES = [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float64, 3)]   # x, xtgt, pid, dir
+
+
+@pytest.mark.parametrize("move", ["gather", "fast_staged", "staged", "direct"])
+@pytest.mark.parametrize("kindname", ["scs_c32", "csr", "dps", "scs_s7"])
+def test_rebuild_remap_folds_update_positions(kindname, move, _default_rebuild_modes):
+    """pp_ps_set_rebuild_remap([1, -1, 2, 3]): the rebuilt structure holds x = old xtgt, xtgt = 0 --
+    updatePtclPositions (pseudoPushAndSearch.cpp:142-154) folded into the record move -- for kept and
+    for added particles, on every structure kind and move mode; the remap is one-shot."""
+    t = torch()
+    P = pp()
+    P.lib().pp_ps_set_staged_rebuild({"direct": 0, "gather": 2, "fast_staged": 2}.get(move, 1))
+    P.lib().pp_ps_set_rebuild_tuning(0, 0 if move == "fast_staged" else 1 << 20)
+    ne, np_ = 400, 9000
+    ppe = _ppe(ne, np_, seed=5)
+    kw = dict(_kinds()[kindname])
+    kind = kw.pop("kind")
+    pel = np.repeat(np.arange(ne, dtype=np.int32), ppe)
+    rng = np.random.default_rng(17)
+    X, T, D = rng.random((3, np_)), rng.random((3, np_)) + 2.0, rng.random((3, np_)) + 5.0
+    ids = np.arange(np_, dtype=np.int32).reshape(1, -1)
+    ps = P.ParticleStructure(kind, PIC_TYPES, ppe, particle_elements=pel, particle_info=[X, T, ids, D], **kw)
+    for rnd in range(2):            # second round: no remap set any more
+        se, m = ps.slot_elem_and_mask(); m = m.astype(bool)
+        cap = ps.capacity
+        pid = ps.get(2).cpu().numpy()[0, :cap]
+        x0 = ps.get(0).cpu().numpy()[:, :cap].copy(); t0 = ps.get(1).cpu().numpy()[:, :cap].copy()
+        d0 = ps.get(3).cpu().numpy()[:, :cap].copy()
+        new_elem = np.where(m, (se * 5 + pid) % ne, -1).astype(np.int32)
+        new_elem[m & (pid % 11 == 0)] = -1
+        nnew = 700
+        nel = rng.integers(0, ne, nnew).astype(np.int32)
+        nX, nT, nD = rng.random((3, nnew)), rng.random((3, nnew)) + 2.0, rng.random((3, nnew)) + 5.0
+        nid = (np.arange(nnew, dtype=np.int32) + 1000000 * (rnd + 1)).reshape(1, -1)
+        if rnd == 0:
+            ps.set_rebuild_remap([1, -1, 2, 3])
+        ps.rebuild(dev(new_elem), dev(nel), [dev(nX), dev(nT), dev(nid), dev(nD)])
+        want = {}
+        for s_ in np.nonzero(m & (new_elem >= 0))[0]:
+            want[int(pid[s_])] = (int(new_elem[s_]), x0[:, s_], t0[:, s_], d0[:, s_])
+        for j in range(nnew):
+            want[int(nid[0, j])] = (int(nel[j]), nX[:, j], nT[:, j], nD[:, j])
+        se2, m2 = ps.slot_elem_and_mask(); m2 = m2.astype(bool)
+        cap2 = ps.capacity
+        pid2 = ps.get(2).cpu().numpy()[0, :cap2][m2]
+        x2 = ps.get(0).cpu().numpy()[:, :cap2][:, m2]; t2 = ps.get(1).cpu().numpy()[:, :cap2][:, m2]
+        d2 = ps.get(3).cpu().numpy()[:, :cap2][:, m2]
+        assert sorted(pid2.tolist()) == sorted(want)
+        for k, q in enumerate(pid2.tolist()):
+            e, xo, to, do = want[q]
+            assert se2[m2][k] == e and np.array_equal(d2[:, k], do)
+            if rnd == 0:
+                assert np.array_equal(x2[:, k], to) and not t2[:, k].any()
+            else:
+                assert np.array_equal(x2[:, k], xo) and np.array_equal(t2[:, k], to)
+    with pytest.raises(P.PumipicError):
+        ps.set_rebuild_remap([2, -1, 2, 3])          # member 2 has another type
+    with pytest.raises(P.PumipicError):
+        ps.set_rebuild_remap([1, 1, 2, 3])           # a member may feed one destination only

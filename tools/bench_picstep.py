@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--push-mult", type=float, default=3.0, help="push distance in units of L/(3*nelems^(1/3))")
+    ap.add_argument("--separate-update", action="store_true",
+                    help="updatePtclPositions as its own pass instead of a member remap of the rebuild (A/B)")
     ap.add_argument("--overlap-reduce", action="store_true",
                     help="comm-array reduction on its own stream, overlapped with the next step (A/B)")
     ap.add_argument("--timing", action="store_true", help="record the library's phase timers (pp_timing_*)")
@@ -38,7 +40,7 @@ def main():
     mod = importlib.import_module("pumi-pic_b200.picstep")
     comm = P.Comm()
     r = mod.run_picstep(P, comm, rank, R, a.steps, a.warmup, a.cube_per_gpu, a.ppe, a.push_mult, timing=a.timing,
-                        overlap_reduce=a.overlap_reduce)
+                        overlap_reduce=a.overlap_reduce, fuse_update=not a.separate_update)
     if rank == 0:
         print(json.dumps(r))
     if R > 1:
