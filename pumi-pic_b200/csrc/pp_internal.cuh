@@ -15,6 +15,7 @@
 // ------------------------------------------------------------------------------------------
 void pp_set_error(const char* fmt, ...);
 void pp_runtime_init();   // once per device: keep the async allocation pool cached
+void* pp_pinned_scratch();  // 256 bytes of pinned host memory per thread (or null)
 
 #define PP_CUDA(call)                                                                     \
   do {                                                                                    \
@@ -202,6 +203,7 @@ struct pp_ps {
   std::vector<void*> data;  // one device array per member: [ncomp][stride]
   std::vector<void*> swap;  // SCS double buffer
   long swap_stride;
+  long data_alloc = 0, swap_alloc = 0;   // slots per component the SCS arrays were allocated with (>= stride)
   uint32_t* mask_bits;
   long mask_words_alloc;
   int* slot_elem;           // [capacity] (DPS parent array; CSR/SCS materialised map)

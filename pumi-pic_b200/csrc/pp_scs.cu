@@ -995,10 +995,12 @@ pp_status pp_scs_build(pp_ps* ps, const int* ppe_dev, const int* pelems_dev,
   if (ps->cfg.extra_padding > 0) cap = (long)(cap * (1 + ps->cfg.extra_padding));
   if (cap < 1) cap = 1;
   ps->stride = cap;
+  ps->data_alloc = cap;
   PP_TRY(pp_ps_alloc_members(ps, ps->data, ps->stride, s));
   if (!ps->cfg.always_realloc) {
     PP_TRY(pp_ps_alloc_members(ps, ps->swap, ps->stride, s));
     ps->swap_stride = ps->stride;
+    ps->swap_alloc = ps->stride;
   }
   // initSCSData (SCS_buildFns.h:202-225)
   if (np > 0 && pelems_dev && pinfo) {
@@ -1077,6 +1079,31 @@ pp_status chunk_order_build(const int* row_to_element, const int* width, int nch
   PP_TRY(pp_dev_alloc(&tmp, tb, s));
   PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, ck_in, ck_out, cv_in, *order, nchunks, 0, ebits, s));
   pp_dev_free(tmp, s); pp_dev_free(ck_in, s); pp_dev_free(ck_out, s); pp_dev_free(cv_in, s);
+  return PP_OK;
+}
+
+// (Re)size the swap copy of the member arrays for a structure of `capacity` slots.  The condition
+// is SCS_rebuild.h:223-229 as written; with the default minimize_size = 0.8 it holds on nearly every
+// rebuild, and the reference then frees and re-creates (zero-filled) views of capacity * (1 +
+// extra_padding) slots.  The sizes follow the reference; the memory is only exchanged when the
+// existing allocation is too small: otherwise the same arrays are reinterpreted with the new stride
+// and not cleared (slots that hold no particle keep stale bytes instead of zeros; nothing reads them).
+pp_status ensure_swap(pp_ps* ps, long capacity, cudaStream_t s) {
+  const pp_ps_config& cfg = ps->cfg;
+  if (!(cfg.always_realloc || ps->swap.empty() || ps->swap_stride < capacity ||
+        ps->swap_stride * cfg.minimize_size < capacity))
+    return PP_OK;
+  long nstride = (long)(capacity * (1 + cfg.extra_padding));
+  if (nstride < capacity) nstride = capacity;
+  if (nstride < 1) nstride = 1;
+  if (!cfg.always_realloc && !ps->swap.empty() && ps->swap_alloc >= nstride) {
+    ps->swap_stride = nstride;
+    return PP_OK;
+  }
+  for (void* p : ps->swap) pp_dev_free((char*)p, s);
+  PP_TRY(pp_ps_alloc_members(ps, ps->swap, nstride, s));
+  ps->swap_stride = nstride;
+  ps->swap_alloc = nstride;
   return PP_OK;
 }
 
@@ -1383,8 +1410,14 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   delete t_build;                                // SCS_rebuild.h:196-265
   // ---- the one host read
   FastScal h;
-  PP_CUDA(cudaMemcpyAsync(&h, sc, sizeof(FastScal), cudaMemcpyDeviceToHost, s));
-  PP_CUDA(cudaStreamSynchronize(s));
+  {
+    PP_TIME_KIND(s, ps->cfg.kind, "rebuild host read");   // the GPU idles from the copy until the host is back
+    static_assert(sizeof(FastScal) <= 256, "FastScal must fit the pinned scratch");
+    FastScal* hp = static_cast<FastScal*>(pp_pinned_scratch());
+    PP_CUDA(cudaMemcpyAsync(hp ? hp : &h, sc, sizeof(FastScal), cudaMemcpyDeviceToHost, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+    if (hp) h = *hp;
+  }
   auto drop = [&]() {
     free_layout(L, s);
     pp_dev_free(count, s); pp_dev_free(rank, s); pp_dev_free(kept, s); pp_dev_free(order, s); pp_dev_free(sc, s);
@@ -1402,6 +1435,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     drop();                                      // chunk height / key width guessed wrong, or nothing left
     return PP_OK;
   }
+  PPTimeScope* t_fin = new PPTimeScope(s, (std::string(pp_kind_name(ps->cfg.kind)) + " layout finish").c_str());
   L.nslices = h.nslices; L.capacity = h.capacity;
   const int ntiles = (L.capacity + 31) / 32;
   PP_TRY(pp_dev_alloc(&L.tile_slice, ntiles + 1, s));
@@ -1410,16 +1444,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   L.mask_words = ntiles + 1;
   PP_TRY(pp_dev_alloc(&L.mask, L.mask_words, s));
   PP_CUDA(cudaMemsetAsync(L.mask + ntiles, 0, sizeof(uint32_t), s));
-  // (re)allocate the swap buffer: SCS_rebuild.h:223-229 (condition reproduced as written)
-  if (cfg.always_realloc || ps->swap.empty() || ps->swap_stride < L.capacity ||
-      ps->swap_stride * cfg.minimize_size < L.capacity) {
-    for (void* p : ps->swap) pp_dev_free((char*)p, s);
-    long nstride = (long)(L.capacity * (1 + cfg.extra_padding));
-    if (nstride < L.capacity) nstride = L.capacity;
-    if (nstride < 1) nstride = 1;
-    PP_TRY(pp_ps_alloc_members(ps, ps->swap, nstride, s));
-    ps->swap_stride = nstride;
-  }
+  PP_TRY(ensure_swap(ps, L.capacity, s));
+  delete t_fin;
   std::vector<const void*> old_src(ps->data.begin(), ps->data.end());
   UnitTable ut, un;
   unit_table(ps, old_src.data(), ps->stride, &ps->swap, ps->swap_stride, ut, remap);
@@ -1482,6 +1508,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   adopt_layout(ps, L, s);
   std::swap(ps->data, ps->swap);
   std::swap(ps->stride, ps->swap_stride);
+  std::swap(ps->data_alloc, ps->swap_alloc);
   if (cfg.always_realloc) {
     for (void* p : ps->swap) pp_dev_free((char*)p, s);
     ps->swap.clear();
@@ -1573,7 +1600,9 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
       if (remap[i] >= 0) { nd[i] = ps->data[remap[i]]; used[remap[i]] = 1; }
     for (int i = 0; i < nm; ++i) {
       if (remap[i] >= 0) continue;
-      const size_t bytes = (size_t)ps->members[i].scalar_bytes * ps->members[i].ncomp * (size_t)ps->stride;
+      // (a fresh array must be as large as the arrays it joins: they may be reinterpreted later)
+      const size_t bytes = (size_t)ps->members[i].scalar_bytes * ps->members[i].ncomp *
+                           (size_t)std::max<long>(ps->stride, ps->data_alloc);
       for (int j = 0; j < nm && !nd[i]; ++j)
         if (!used[j] && ps->members[j].scalar_bytes == ps->members[i].scalar_bytes &&
             ps->members[j].ncomp == ps->members[i].ncomp) { nd[i] = ps->data[j]; used[j] = 1; }
@@ -1827,16 +1856,7 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
   }
   ScsLayout L;
   PP_TRY(scs_layout(ps->cfg, ne, count, active, s, L));
-  // (re)allocate the swap buffer: SCS_rebuild.h:223-229 (condition reproduced as written)
-  if (ps->cfg.always_realloc || ps->swap.empty() || ps->swap_stride < L.capacity ||
-      ps->swap_stride * ps->cfg.minimize_size < L.capacity) {
-    for (void* p : ps->swap) pp_dev_free((char*)p, s);
-    long nstride = (long)(L.capacity * (1 + ps->cfg.extra_padding));
-    if (nstride < L.capacity) nstride = L.capacity;
-    if (nstride < 1) nstride = 1;
-    PP_TRY(pp_ps_alloc_members(ps, ps->swap, nstride, s));
-    ps->swap_stride = nstride;
-  }
+  PP_TRY(ensure_swap(ps, L.capacity, s));
   int* row_fill;
   PP_TRY(pp_dev_alloc(&row_fill, L.nrows + 1, s));
   PP_CUDA(cudaMemsetAsync(row_fill, 0, sizeof(int) * (L.nrows + 1), s));
@@ -1893,6 +1913,7 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
   adopt_layout(ps, L, s);
   std::swap(ps->data, ps->swap);
   std::swap(ps->stride, ps->swap_stride);
+  std::swap(ps->data_alloc, ps->swap_alloc);
   if (ps->cfg.always_realloc) {
     for (void* p : ps->swap) pp_dev_free((char*)p, s);
     ps->swap.clear();

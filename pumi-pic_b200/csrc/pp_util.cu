@@ -20,6 +20,14 @@ extern "C" const char* pp_build_arch(void) { return "sm_100a"; }
 // The library allocates its scratch with cudaMallocAsync.  The default pool returns freed memory
 // to the driver at every synchronisation (release threshold 0), which turns the scratch arrays
 // of each rebuild into fresh cudaMalloc calls; keep freed blocks cached instead.
+// 256 bytes of pinned host memory per thread for the small device->host reads of the hot path (a copy
+// into pageable memory is staged by the driver and costs tens of microseconds more)
+void* pp_pinned_scratch() {
+  static thread_local void* p = nullptr;
+  if (!p && cudaHostAlloc(&p, 256, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cudaGetLastError(); }
+  return p;
+}
+
 void pp_runtime_init() {
   static thread_local int done_for = -1;
   int dev = 0;
