@@ -630,7 +630,13 @@ pp_status pp_comm_group_end(void);
 /* Mesh::reduceCommArray (src/pumipic_comm.cpp:223-440) for full-mesh PICparts: every rank holds
  * a copy of all nents entities; after the call every copy holds the SUM/MAX/MIN over ranks, or
  * for PP_BCAST the owner's value (ent_owner = Mesh::entOwners(edim), device int32[nents]).
- * comm_array: device [nents*nvals], entity-major (createCommArray, pumipic_comm.cpp:187-192). */
+ * comm_array: device [nents*nvals], entity-major (createCommArray, pumipic_comm.cpp:187-192).
+ * Between GPUs with peer access (the default; PUMIPIC_P2P=0 / pp_comm_set_p2p(0) select ncclAllReduce) the
+ * reduction runs over a peer-memory window: every rank copies its array into its window, reduces ITS
+ * slice of all ranks' copies with direct NVLink loads in ascending rank order and stores the result
+ * into every rank's window -- the same bits on every rank and in every run (the reference's
+ * MPI_Allreduce / atomic merges are order-dependent).  The first call (and a later call with a larger
+ * array) maps the windows, collectively; successive calls on one communicator must use one stream. */
 pp_status pp_comm_array_reduce(pp_comm* comm, void* comm_array, int64_t nents, int32_t nvals,
                                int32_t dtype, int32_t op, const int32_t* ent_owner,
                                pp_stream stream);

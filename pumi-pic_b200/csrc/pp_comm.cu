@@ -104,12 +104,29 @@ struct P2PWindow {
   cudaEvent_t ev = nullptr;
   unsigned epoch = 0;
 };
+// Peer-memory window of the comm-array reduction (Mesh::reduceCommArray, all-reduce branch): header,
+// input copy A, result B.  Reduce-scatter + all-gather by direct loads / stores over NVLink: rank r
+// reduces slice r of everybody's A in ascending rank order (the same bits on every rank and in every
+// run) and stores the result into everybody's B.
+struct P2PReduceHeader {
+  unsigned ready[kMaxRanks];       // [rank]: call number whose input copy that rank has finished
+  unsigned done[kMaxRanks];        // [rank]: call number whose slice that rank has stored everywhere
+};
+struct P2PReduce {
+  bool tried = false, ok = false;
+  size_t cap_bytes = 0;            // bytes of A (and of B)
+  char* local = nullptr;
+  P2PPeers peers;
+  int* err = nullptr;              // device flag: a peer did not show up
+  unsigned epoch = 0;
+};
 int g_p2p_enable = 1;
 
 struct pp_comm {
   ncclComm_t comm;
   int nranks, rank;
   P2PWindow p2p;
+  P2PReduce red;
 };
 
 extern "C" pp_status pp_comm_unique_id(uint8_t id_out[128]) {
@@ -125,7 +142,7 @@ extern "C" pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t 
   PP_REQUIRE(out && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
   pp_comm* c = new pp_comm();
   c->comm = nullptr; c->nranks = nranks; c->rank = rank;
-  for (int p = 0; p < kMaxRanks; ++p) c->p2p.peers.win[p] = nullptr;
+  for (int p = 0; p < kMaxRanks; ++p) { c->p2p.peers.win[p] = nullptr; c->red.peers.win[p] = nullptr; }
   if (nranks > 1) {
     PP_REQUIRE(id, "a unique id is required for more than one rank");
     PP_TRY(load_nccl());
@@ -163,6 +180,12 @@ extern "C" pp_status pp_comm_destroy(pp_comm* c) {
     cudaFree(c->p2p.local); cudaFree(c->p2p.dev); cudaFree(c->p2p.dev_stats);
     if (c->p2p.host_stats) cudaFreeHost(c->p2p.host_stats);
     if (c->p2p.ev) cudaEventDestroy(c->p2p.ev);
+  }
+  if (c->red.local) {
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->nranks; ++p)
+      if (p != c->rank && c->red.peers.win[p]) cudaIpcCloseMemHandle(c->red.peers.win[p]);
+    cudaFree(c->red.local); cudaFree(c->red.err);
   }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   delete c;
@@ -250,6 +273,171 @@ __global__ void k_mask_not_owned(T* a, const int* __restrict__ owner, int self, 
 }
 }  // namespace
 
+namespace {
+constexpr size_t kRedHdr = 1024;      // header bytes in front of A
+__device__ __forceinline__ unsigned long long red_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// every block: wait until all ranks' flags show `epoch` (flags live in this rank's own window)
+__device__ __forceinline__ void red_wait(const unsigned* flags, int nranks, unsigned epoch, int* err) {
+  if (threadIdx.x < nranks) {
+    const unsigned long long t0 = red_now_ns();
+    while (*(volatile const unsigned*)(flags + threadIdx.x) != epoch) {
+      if (red_now_ns() - t0 > 20000000000ull) { atomicExch(err, 1); break; }
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+__global__ void k_red_flag(P2PPeers peers, int self, int nranks, unsigned epoch, int which) {
+  const int p = threadIdx.x;
+  if (p >= nranks) return;
+  __threadfence_system();
+  P2PReduceHeader* h = reinterpret_cast<P2PReduceHeader*>(peers.win[p]);
+  *(volatile unsigned*)(which == 0 ? &h->ready[self] : &h->done[self]) = epoch;
+}
+template <class T>
+__device__ __forceinline__ T red_op(T a, T b, int op) {
+  return op == PP_SUM ? a + b : op == PP_MAX ? (a < b ? b : a) : (b < a ? b : a);
+}
+// slice `self` of all ranks' inputs, reduced in ascending rank order, stored into all ranks' results
+template <class T>
+__global__ void __launch_bounds__(256) k_red_slice(P2PPeers peers, int self, int nranks, long n, size_t cap_bytes,
+                                                    unsigned epoch, int op, int* err) {
+  const P2PReduceHeader* h = reinterpret_cast<const P2PReduceHeader*>(peers.win[self]);
+  red_wait(h->ready, nranks, epoch, err);
+  const long per = ((n + nranks - 1) / nranks + 1) & ~1l;       // even: slices stay 16-byte aligned for doubles
+  const long lo = min(n, per * self), hi = min(n, lo + per);
+  if (sizeof(T) == 8 && ((hi - lo) & 1) == 0) {
+    // two elements per 16-byte access (NVLink packets of 16 bytes and more)
+    typedef typename std::conditional<std::is_same<T, double>::value, double2, longlong2>::type T2;
+    const long lo2 = lo >> 1, hi2 = hi >> 1;
+    for (long i = lo2 + blockIdx.x * (long)blockDim.x + threadIdx.x; i < hi2; i += (long)gridDim.x * blockDim.x) {
+      T2 acc = reinterpret_cast<const T2*>(peers.win[0] + kRedHdr)[i];
+      for (int p = 1; p < nranks; ++p) {
+        const T2 v = reinterpret_cast<const T2*>(peers.win[p] + kRedHdr)[i];
+        acc.x = red_op(acc.x, v.x, op); acc.y = red_op(acc.y, v.y, op);
+      }
+      for (int q = 0; q < nranks; ++q) reinterpret_cast<T2*>(peers.win[q] + kRedHdr + cap_bytes)[i] = acc;
+    }
+    return;
+  }
+  for (long i = lo + blockIdx.x * (long)blockDim.x + threadIdx.x; i < hi; i += (long)gridDim.x * blockDim.x) {
+    T acc = reinterpret_cast<const T*>(peers.win[0] + kRedHdr)[i];
+    for (int p = 1; p < nranks; ++p) acc = red_op(acc, reinterpret_cast<const T*>(peers.win[p] + kRedHdr)[i], op);
+    for (int q = 0; q < nranks; ++q) reinterpret_cast<T*>(peers.win[q] + kRedHdr + cap_bytes)[i] = acc;
+  }
+}
+template <class T>
+__global__ void __launch_bounds__(256) k_red_copy_out(T* __restrict__ arr, const char* local, long n, size_t cap_bytes,
+                                                       int nranks, unsigned epoch, int* err) {
+  const P2PReduceHeader* h = reinterpret_cast<const P2PReduceHeader*>(local);
+  red_wait(h->done, nranks, epoch, err);
+  const T* B = reinterpret_cast<const T*>(local + kRedHdr + cap_bytes);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) arr[i] = B[i];
+}
+
+// collective: (re)create the reduction window for arrays of want_bytes (every rank calls it with the
+// same size: the comm arrays of an all-reduce have the same length everywhere)
+pp_status red_setup(pp_comm* c, size_t want_bytes, cudaStream_t s) {
+  P2PReduce& w = c->red;
+  const int R = c->nranks, me = c->rank;
+  if (w.local) {                       // grow: nobody touches the old windows once every device is idle
+    PP_CUDA(cudaDeviceSynchronize());
+    for (int p = 0; p < R; ++p)
+      if (p != me && w.peers.win[p]) { cudaIpcCloseMemHandle(w.peers.win[p]); w.peers.win[p] = nullptr; }
+    int* d_b;                          // barrier: all mappings are closed before an owner frees its window
+    PP_TRY(pp_dev_alloc(&d_b, 1, s));
+    PP_CUDA(cudaMemsetAsync(d_b, 0, sizeof(int), s));
+    PP_NCCL(g_nccl.AllReduce(d_b, d_b, 1, ncclInt32, ncclSum, c->comm, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+    pp_dev_free(d_b, s);
+    cudaFree(w.local); w.local = nullptr;
+    if (w.err) { cudaFree(w.err); w.err = nullptr; }
+    w.ok = false;
+    want_bytes += want_bytes / 2;      // head room: do not come back for every few per cent
+  }
+  w.tried = true;
+  const char* env = getenv("PUMIPIC_P2P");
+  int ok = (R <= kMaxRanks && g_p2p_enable && !(env && env[0] == '0')) ? 1 : 0;
+  long long h_sz = (long long)((want_bytes + 255) & ~(size_t)255);
+  {
+    long long* d_sz;
+    PP_TRY(pp_dev_alloc(&d_sz, 1, s));
+    PP_CUDA(cudaMemcpyAsync(d_sz, &h_sz, sizeof(h_sz), cudaMemcpyHostToDevice, s));
+    PP_NCCL(g_nccl.AllReduce(d_sz, d_sz, 1, ncclInt64, ncclMax, c->comm, s));
+    PP_CUDA(cudaMemcpyAsync(&h_sz, d_sz, sizeof(h_sz), cudaMemcpyDeviceToHost, s));
+    PP_CUDA(cudaStreamSynchronize(s));
+    pp_dev_free(d_sz, s);
+  }
+  w.cap_bytes = (size_t)h_sz;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMalloc((void**)&w.local, kRedHdr + 2 * w.cap_bytes) != cudaSuccess) { ok = 0; w.local = nullptr; cudaGetLastError(); }
+  if (ok) {
+    PP_CUDA(cudaMemset(w.local, 0, kRedHdr));
+    if (cudaIpcGetMemHandle(&mine, w.local) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  Msg m; m.h = mine; m.ok = ok; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+  Msg *d_one, *d_all;
+  PP_TRY(pp_dev_alloc(&d_one, 1, s));
+  PP_TRY(pp_dev_alloc(&d_all, (size_t)R, s));
+  PP_CUDA(cudaMemcpyAsync(d_one, &m, sizeof(Msg), cudaMemcpyHostToDevice, s));
+  PP_NCCL(g_nccl.AllGather(d_one, d_all, sizeof(Msg), ncclUint8, c->comm, s));
+  std::vector<Msg> all((size_t)R);
+  PP_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Msg) * R, cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  for (int p = 0; p < R; ++p) ok &= all[(size_t)p].ok;
+  if (ok) {
+    w.peers.win[me] = w.local;
+    for (int p = 0; p < R && ok; ++p) {
+      if (p == me) continue;
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[(size_t)p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+      w.peers.win[p] = (char*)q;
+    }
+  }
+  int* d_ok = (int*)d_one;
+  PP_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
+  PP_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, s));
+  PP_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  pp_dev_free(d_one, s); pp_dev_free(d_all, s);
+  if (ok) {
+    PP_CUDA(cudaMalloc((void**)&w.err, sizeof(int)));
+    PP_CUDA(cudaMemset(w.err, 0, sizeof(int)));
+  } else if (w.local) {
+    for (int p = 0; p < R; ++p)
+      if (p != me && w.peers.win[p]) { cudaIpcCloseMemHandle(w.peers.win[p]); w.peers.win[p] = nullptr; }
+    cudaFree(w.local);
+    w.local = nullptr;
+  }
+  w.ok = ok != 0;
+  return PP_OK;
+}
+
+template <class T>
+pp_status red_run(pp_comm* c, T* arr, long n, int op, cudaStream_t s) {
+  P2PReduce& w = c->red;
+  const int R = c->nranks, me = c->rank;
+  const unsigned epoch = ++w.epoch;
+  PP_CUDA(cudaMemcpyAsync(w.local + kRedHdr, arr, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  k_red_flag<<<1, kMaxRanks, 0, s>>>(w.peers, me, R, epoch, 0);
+  const long per = (n + R - 1) / R;
+  const int grid = (int)std::max<long>(1, std::min<long>((per + 255) / 256, 148 * 8));
+  k_red_slice<T><<<grid, 256, 0, s>>>(w.peers, me, R, n, w.cap_bytes, epoch, op, w.err);
+  k_red_flag<<<1, kMaxRanks, 0, s>>>(w.peers, me, R, epoch, 1);
+  const int grid2 = (int)std::max<long>(1, std::min<long>((n + 255) / 256, 148 * 8));
+  k_red_copy_out<T><<<grid2, 256, 0, s>>>(arr, w.local, n, w.cap_bytes, R, epoch, w.err);
+  PP_KERNEL_CHECK();
+  return PP_OK;
+}
+}  // namespace
+
 extern "C" pp_status pp_comm_array_reduce(pp_comm* c, void* comm_array, int64_t nents, int32_t nvals,
                                           int32_t dtype, int32_t op, const int32_t* ent_owner,
                                           pp_stream stream) {
@@ -270,6 +458,22 @@ extern "C" pp_status pp_comm_array_reduce(pp_comm* c, void* comm_array, int64_t 
       PP_KERNEL_CHECK();
     }
     nccl_op = PP_SUM;
+  }
+  // peer-memory reduction (default between GPUs with peer access): reduce-scatter + all-gather by
+  // direct NVLink loads / stores, fixed rank order; the window is sized by the first call
+  const long n = (long)(nents * nvals);
+  const size_t esz = (dtype == PP_INT32 || dtype == PP_FLOAT32) ? 4 : 8;
+  if (n > 0 && (nccl_op == PP_SUM || nccl_op == PP_MAX || nccl_op == PP_MIN)) {
+    if (!c->red.tried || (c->red.ok && (size_t)n * esz > c->red.cap_bytes)) PP_TRY(red_setup(c, (size_t)n * esz, s));
+    if (c->red.ok && (size_t)n * esz <= c->red.cap_bytes) {
+      switch (dtype) {
+        case PP_INT32: return red_run(c, (int*)comm_array, n, nccl_op, s);
+        case PP_INT64: return red_run(c, (long long*)comm_array, n, nccl_op, s);
+        case PP_FLOAT32: return red_run(c, (float*)comm_array, n, nccl_op, s);
+        case PP_FLOAT64: return red_run(c, (double*)comm_array, n, nccl_op, s);
+        default: break;
+      }
+    }
   }
   return pp_comm_allreduce(c, comm_array, comm_array, nents * nvals, dtype, nccl_op, stream);
 }

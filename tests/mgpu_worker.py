@@ -146,6 +146,20 @@ def test_comm_array(P, comm, rank, R):
     comm.alltoall(a, b)
     want = np.concatenate([np.arange(3) + 3 * rank + 100 * p for p in range(R)])
     assert np.array_equal(b.cpu().numpy(), want)
+    # a larger array (the window grows, collectively), random doubles: the sum in ascending rank order,
+    # bit for bit, on every rank
+    for n2 in (50000, 777777):
+        rng = np.random.default_rng(100 + rank)
+        mine = rng.standard_normal(n2)
+        got = comm.array_reduce(dev(mine), n2, 1, P.capi.PP_SUM).cpu().numpy()
+        parts = gather_np(mine)
+        want = parts[0].copy()
+        for q in range(1, R):
+            want = want + parts[q]
+        assert np.array_equal(got, want), "rank-ordered sum differs"
+        f = dev(mine.astype(np.float32))
+        got32 = comm.array_reduce(f, n2, 1, P.capi.PP_MAX).cpu().numpy()
+        assert np.array_equal(got32, np.max(np.stack([q.astype(np.float32) for q in parts]), axis=0))
     if rank == 0:
         print("comm arrays ok on %d ranks" % R)
 
