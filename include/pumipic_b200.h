@@ -263,6 +263,11 @@ pp_status pp_host_picpart_write(const pp_host_picpart* pp, const char* prefix);
 /* pumipic::read(lib, comm, prefix, &mesh) (src/pumipic_file.cpp:118-205), versions 1 and 2. */
 pp_status pp_host_picpart_read(const char* prefix, int32_t nranks, int32_t rank,
                                pp_host_picpart** out);
+/* The reference compresses the .ppm arrays only when Omega_h was built with zlib (OMEGA_H_USE_ZLIB,
+ * src/pumipic_file.cpp:76-80) and the file carries no flag.  on = 1 (default) writes compressed
+ * arrays, 0 raw ones (also PUMIPIC_PPM_ZLIB=0); the reader tries the configured form first and the
+ * other one when the arrays do not decode, so files of either build are read. */
+void pp_host_ppm_set_compression(int32_t on);
 /* The safe-zone overlap regions ("sbars") this part belongs to (ParticleBalancer,
  * src/pumipic_lb.hpp:97-101): global sbar id and the sorted parts sharing it.  parts of sbar i
  * are parts[off[i] .. off[i+1]).  Pointers are owned by the PICpart. */
@@ -488,6 +493,12 @@ pp_status pp_trace_pending(pp_mesh* mesh, pp_ps* ps, const pp_search_args* args,
  * applies (C = 32, elem_ids seeded from the rows), 1 = block-staged kernel, 0 = the simple
  * thread-per-slot kernel.  All give identical results; the switch exists for A/B measurements. */
 void pp_search_set_staged(int32_t on);
+/* L2 access-policy window of the chunk walk over the mesh's walk table: `fraction` (0..1) of the
+ * device's persisting L2 carve-out is given to the table's lines (hit property "persisting"), the
+ * rest of the kernel's accesses stream.  0 (default) = no window; also PUMIPIC_L2_WINDOW in the
+ * environment.  Results do not change.  Measured without gain on the headline workload (the kernel's
+ * DRAM traffic is at its floor already); kept as a tuning switch for meshes much smaller than L2. */
+void pp_search_set_l2_window(double fraction);
 /* Counters of the most recent search on this mesh handle (synchronises the stream). */
 pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host, pp_stream stream);
 
@@ -596,6 +607,19 @@ void pp_timing_summarize(int32_t sort);
  * needs no id and never loads NCCL.  Replaces the MPI_Comm of support/ViewComm.h. */
 pp_status pp_comm_unique_id(uint8_t id_out[128]);
 pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t id[128], pp_comm** out);
+/* The application's own bootstrap instead of a hand-carried NCCL id -- the reference's world is MPI
+ * (support/ViewComm.h takes an MPI_Comm; an MPI code passes a wrapper of MPI_Allgather on that
+ * communicator).  `allgather(ctx, send, recv, bytes)`: every rank contributes `bytes` bytes of host
+ * memory, recv receives nranks * bytes in rank order; returns 0 on success.  It is called collectively,
+ * on the host, while the communicator or one of its peer-memory windows is being set up -- never in a
+ * step.  use_nccl != 0: the NCCL id travels through it; the communicator then equals pp_comm_create's.
+ * use_nccl == 0: no NCCL is loaded at all; migration (pp_ps_migrate), pp_comm_array_reduce and
+ * pp_comm_allreduce run over the peer-memory windows (CUDA IPC -- also between several processes that
+ * share ONE GPU, which is how the multi-rank tests run on a single-GPU box); alltoall / send / recv and
+ * the comm plans need NCCL and fail with PP_ERR_INVALID on such a communicator. */
+typedef int32_t (*pp_host_allgather_fn)(void* ctx, const void* send, void* recv, int64_t bytes);
+pp_status pp_comm_create_hosted(int32_t nranks, int32_t rank, pp_host_allgather_fn allgather, void* ctx,
+                                int32_t use_nccl, pp_comm** out);
 pp_status pp_comm_destroy(pp_comm* comm);
 /* Migration transport.  Default: a peer-memory window per rank (cudaMalloc + CUDA IPC, mapped into every
  * peer by the first pp_ps_migrate of the communicator, collectively): the pack kernel stores the leaving

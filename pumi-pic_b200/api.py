@@ -707,17 +707,39 @@ def timing_table():
 
 
 class Comm:
-    """NCCL communicator of the C ABI.  The unique id travels over torch.distributed (plumbing)."""
+    """Communicator of the C ABI.
+    Default: NCCL; the unique id travels over torch.distributed (plumbing).
+    hosted=True: pp_comm_create_hosted with torch.distributed's all-gather as the application's
+    bootstrap callback (what an MPI code does with MPI_Allgather); nccl=False then builds a
+    communicator without NCCL (peer-memory windows only), which also works between processes that
+    share one GPU."""
 
     _DT = None
 
-    def __init__(self, nranks=None, rank=None):
+    def __init__(self, nranks=None, rank=None, hosted=False, nccl=True):
         torch = _torch()
         import torch.distributed as dist
         if nranks is None:
             nranks = dist.get_world_size() if dist.is_initialized() else 1
             rank = dist.get_rank() if dist.is_initialized() else 0
         self.nranks, self.rank = nranks, rank
+        self.h = C.c_void_p()
+        self._cb = None
+        if hosted:
+            def allgather(_ctx, send, recv, nbytes):
+                try:
+                    parts = [None] * nranks
+                    dist.all_gather_object(parts, C.string_at(send, nbytes))
+                    C.memmove(recv, b"".join(parts), nbytes * nranks)
+                    return 0
+                except Exception:          # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._cb = capi.HOST_ALLGATHER_FN(allgather)   # kept alive with the communicator
+            check(lib().pp_comm_create_hosted(nranks, rank, C.cast(self._cb, C.c_void_p), None,
+                                              1 if nccl else 0, C.byref(self.h)))
+            return
         uid = None
         if nranks > 1:
             buf = (C.c_uint8 * 128)()
@@ -726,7 +748,6 @@ class Comm:
             obj = [bytes(buf)]
             dist.broadcast_object_list(obj, src=0)
             uid = (C.c_uint8 * 128).from_buffer_copy(obj[0])
-        self.h = C.c_void_p()
         check(lib().pp_comm_create(nranks, rank, uid, C.byref(self.h)))
 
     @staticmethod

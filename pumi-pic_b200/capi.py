@@ -8,6 +8,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# pp_host_allgather_fn of include/pumipic_b200.h
+HOST_ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
 LIB_PATH = os.environ.get("PUMIPIC_B200_LIB", os.path.join(HERE, "libpumipic_b200.so"))
 
 PP_OK = 0
@@ -163,6 +166,8 @@ PROTOTYPES = {
                                  C.POINTER(SearchStats), C.c_void_p]),
     "pp_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pp_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pp_comm_create_hosted": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.POINTER(C.c_void_p)]),
     "pp_comm_destroy": (C.c_int, [C.c_void_p]),
     "pp_timing_enable": (None, [C.c_int32]),
     "pp_timing_set_verbosity": (None, [C.c_int32]),
@@ -209,6 +214,7 @@ PROTOTYPES = {
     "pp_trace_pending": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SearchArgs), C.c_void_p, C.c_void_p,
                                    C.c_int32, c_i32p, C.c_void_p]),
     "pp_search_set_staged": (None, [C.c_int32]),
+    "pp_search_set_l2_window": (None, [C.c_double]),
     "pp_search_last_stats": (C.c_int, [C.c_void_p, C.POINTER(SearchStats), C.c_void_p]),
     "pp_push_direction_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                            C.c_int32, C.POINTER(SearchArgs),
@@ -261,6 +267,7 @@ PROTOTYPES = {
     "pp_host_picpart_rank": (C.c_int32, [C.c_void_p]),
     "pp_host_picpart_write": (C.c_int, [C.c_void_p, C.c_char_p]),
     "pp_host_picpart_read": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pp_host_ppm_set_compression": (None, [C.c_int32]),
     "pp_host_picpart_sbars": (C.c_int, [C.c_void_p, c_i32p, C.POINTER(c_i32p), C.POINTER(c_i32p),
                                         C.POINTER(c_i32p), c_i32p]),
     "pp_push_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -123,11 +123,109 @@ struct P2PReduce {
 int g_p2p_enable = 1;
 
 struct pp_comm {
-  ncclComm_t comm;
+  ncclComm_t comm;                 // null: one rank, or a hosted communicator without NCCL
   int nranks, rank;
+  pp_host_allgather_fn host_ag = nullptr;   // hosted: the application's all-gather (MPI_Allgather, ...)
+  void* host_ctx = nullptr;
   P2PWindow p2p;
   P2PReduce red;
 };
+#define PP_NEED_NCCL(c)                                                                               \
+  PP_REQUIRE((c)->comm, "this communicator has no NCCL transport (pp_comm_create_hosted without NCCL): only " \
+                        "the peer-memory paths (migrate, array_reduce, allreduce) are available")
+
+namespace {
+// Set-up collective of the communicator: every rank contributes `bytes` bytes of HOST memory, all ranks
+// get the nranks blocks in rank order.  Hosted communicators use the application's function, the
+// others NCCL on staging buffers.  Only the one-time window set-ups use it, never a step.
+pp_status boot_allgather(pp_comm* c, const void* h_send, void* h_recv, size_t bytes, cudaStream_t s) {
+  if (c->nranks == 1) { memcpy(h_recv, h_send, bytes); return PP_OK; }
+  if (c->host_ag) {
+    PP_CUDA(cudaStreamSynchronize(s));
+    if (c->host_ag(c->host_ctx, h_send, h_recv, (int64_t)bytes) != 0) {
+      pp_set_error("the application's all-gather callback failed");
+      return PP_ERR_NCCL;
+    }
+    return PP_OK;
+  }
+  PP_NEED_NCCL(c);
+  char *d_one, *d_all;
+  PP_TRY(pp_dev_alloc(&d_one, bytes, s));
+  PP_TRY(pp_dev_alloc(&d_all, bytes * (size_t)c->nranks, s));
+  PP_CUDA(cudaMemcpyAsync(d_one, h_send, bytes, cudaMemcpyHostToDevice, s));
+  PP_NCCL(g_nccl.AllGather(d_one, d_all, bytes, ncclUint8, c->comm, s));
+  PP_CUDA(cudaMemcpyAsync(h_recv, d_all, bytes * (size_t)c->nranks, cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaStreamSynchronize(s));
+  pp_dev_free(d_one, s); pp_dev_free(d_all, s);
+  return PP_OK;
+}
+pp_status boot_max(pp_comm* c, long long* v, cudaStream_t s) {
+  std::vector<long long> all((size_t)c->nranks);
+  PP_TRY(boot_allgather(c, v, all.data(), sizeof(long long), s));
+  for (long long x : all) *v = x > *v ? x : *v;
+  return PP_OK;
+}
+pp_status boot_min(pp_comm* c, int* v, cudaStream_t s) {       // also a barrier
+  std::vector<int> all((size_t)c->nranks);
+  PP_TRY(boot_allgather(c, v, all.data(), sizeof(int), s));
+  for (int x : all) *v = x < *v ? x : *v;
+  return PP_OK;
+}
+
+// device scratch of one call, released (stream-ordered) when the scope ends -- on error returns too
+struct DevScope {
+  cudaStream_t s;
+  std::vector<void*> held;
+  explicit DevScope(cudaStream_t s_) : s(s_) {}
+  ~DevScope() { for (void* p : held) cudaFreeAsync(p, s); }
+  template <class T>
+  pp_status alloc(T** out, size_t n) {
+    PP_TRY(pp_dev_alloc(out, n, s));
+    held.push_back((void*)*out);
+    return PP_OK;
+  }
+};
+// ncclGroupStart / ncclGroupEnd as a scope: an early return between the two must still close the group
+struct NcclGroup {
+  bool open = false;
+  pp_status begin() { PP_NCCL(g_nccl.GroupStart()); open = true; return PP_OK; }
+  pp_status end() { open = false; PP_NCCL(g_nccl.GroupEnd()); return PP_OK; }
+  ~NcclGroup() { if (open) g_nccl.GroupEnd(); }
+};
+
+pp_status init_nccl(pp_comm* c, const uint8_t id[128]) {
+  const int nranks = c->nranks, rank = c->rank;
+  PP_TRY(load_nccl());
+  ncclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  PP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
+  // NCCL connects point-to-point and collective channels lazily, on the first call that uses
+  // them (tens of milliseconds per new peer): a migration that reaches a diagonal neighbour for
+  // the first time in step 40 would stall that step.  Touch every peer and both collectives now.
+  char* w = nullptr;
+  PP_CUDA(cudaMalloc(&w, (size_t)(2 * nranks + 2) * 8));
+  PP_CUDA(cudaMemset(w, 0, (size_t)(2 * nranks + 2) * 8));
+  NcclGroup group1;
+  PP_TRY(group1.begin());
+  for (int p = 0; p < nranks; ++p) {
+    if (p == rank) continue;
+    PP_NCCL(g_nccl.Send(w + 8 * p, 8, ncclUint8, p, c->comm, 0));
+    PP_NCCL(g_nccl.Recv(w + 8 * (nranks + p), 8, ncclUint8, p, c->comm, 0));
+  }
+  PP_TRY(group1.end());
+  PP_NCCL(g_nccl.AllReduce(w, w, 1, ncclInt64, ncclSum, c->comm, 0));
+  PP_NCCL(g_nccl.AllGather(w + 8 * 2 * nranks, w, 2, ncclInt32, c->comm, 0));
+  PP_CUDA(cudaStreamSynchronize(0));
+  PP_CUDA(cudaFree(w));
+  return PP_OK;
+}
+pp_comm* new_comm(int nranks, int rank) {
+  pp_comm* c = new pp_comm();
+  c->comm = nullptr; c->nranks = nranks; c->rank = rank;
+  for (int p = 0; p < kMaxRanks; ++p) { c->p2p.peers.win[p] = nullptr; c->red.peers.win[p] = nullptr; }
+  return c;
+}
+}  // namespace
 
 extern "C" pp_status pp_comm_unique_id(uint8_t id_out[128]) {
   PP_REQUIRE(id_out, "null argument");
@@ -140,32 +238,37 @@ extern "C" pp_status pp_comm_unique_id(uint8_t id_out[128]) {
 
 extern "C" pp_status pp_comm_create(int32_t nranks, int32_t rank, const uint8_t id[128], pp_comm** out) {
   PP_REQUIRE(out && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
-  pp_comm* c = new pp_comm();
-  c->comm = nullptr; c->nranks = nranks; c->rank = rank;
-  for (int p = 0; p < kMaxRanks; ++p) { c->p2p.peers.win[p] = nullptr; c->red.peers.win[p] = nullptr; }
+  PP_REQUIRE(nranks == 1 || id, "a unique id is required for more than one rank");
+  pp_comm* c = new_comm(nranks, rank);
   if (nranks > 1) {
-    PP_REQUIRE(id, "a unique id is required for more than one rank");
-    PP_TRY(load_nccl());
-    ncclUniqueId uid;
-    memcpy(uid.internal, id, 128);
-    PP_NCCL(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
-    // NCCL connects point-to-point and collective channels lazily, on the first call that uses
-    // them (tens of milliseconds per new peer): a migration that reaches a diagonal neighbour for
-    // the first time in step 40 would stall that step.  Touch every peer and both collectives now.
-    char* w = nullptr;
-    PP_CUDA(cudaMalloc(&w, (size_t)(2 * nranks + 2) * 8));
-    PP_CUDA(cudaMemset(w, 0, (size_t)(2 * nranks + 2) * 8));
-    PP_NCCL(g_nccl.GroupStart());
-    for (int p = 0; p < nranks; ++p) {
-      if (p == rank) continue;
-      PP_NCCL(g_nccl.Send(w + 8 * p, 8, ncclUint8, p, c->comm, 0));
-      PP_NCCL(g_nccl.Recv(w + 8 * (nranks + p), 8, ncclUint8, p, c->comm, 0));
-    }
-    PP_NCCL(g_nccl.GroupEnd());
-    PP_NCCL(g_nccl.AllReduce(w, w, 1, ncclInt64, ncclSum, c->comm, 0));
-    PP_NCCL(g_nccl.AllGather(w + 8 * 2 * nranks, w, 2, ncclInt32, c->comm, 0));
-    PP_CUDA(cudaStreamSynchronize(0));
-    PP_CUDA(cudaFree(w));
+    const pp_status st = init_nccl(c, id);
+    if (st != PP_OK) { delete c; return st; }
+  }
+  *out = c;
+  return PP_OK;
+}
+
+// The application brings its own bootstrap (the reference's world is MPI: support/ViewComm.h takes an
+// MPI_Comm): `allgather` is called on the host, collectively, only while a communicator or one of its
+// peer-memory windows is being set up.  use_nccl != 0: the NCCL id travels through it and the
+// communicator is the same as pp_comm_create's.  use_nccl == 0: no NCCL at all -- migration and the
+// comm-array reductions run over the peer-memory windows (CUDA IPC), which also works between several
+// processes on ONE GPU (how the multi-rank tests run on a single-GPU box).
+extern "C" pp_status pp_comm_create_hosted(int32_t nranks, int32_t rank, pp_host_allgather_fn allgather,
+                                           void* ctx, int32_t use_nccl, pp_comm** out) {
+  PP_REQUIRE(out && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
+  PP_REQUIRE(nranks == 1 || allgather, "an all-gather callback is required for more than one rank");
+  PP_REQUIRE(nranks <= kMaxRanks || use_nccl, "a communicator without NCCL holds at most 64 ranks");
+  pp_comm* c = new_comm(nranks, rank);
+  c->host_ag = allgather; c->host_ctx = ctx;
+  if (nranks > 1 && use_nccl) {
+    std::vector<uint8_t> mine(128, 0), all((size_t)nranks * 128);
+    pp_status st = rank == 0 ? pp_comm_unique_id(mine.data()) : PP_OK;
+    // the gather is entered by every rank, also when rank 0 failed (its id stays zero and NCCL rejects it)
+    const pp_status st2 = boot_allgather(c, mine.data(), all.data(), 128, 0);
+    if (st == PP_OK) st = st2;
+    if (st == PP_OK) st = init_nccl(c, all.data());
+    if (st != PP_OK) { delete c; return st; }
   }
   *out = c;
   return PP_OK;
@@ -204,6 +307,10 @@ static pp_status nccl_type(int32_t dtype, ncclDataType_t* t, size_t* bytes) {
   }
 }
 
+namespace {
+// the peer-memory reduction of pp_comm_array_reduce, in place on `arr`; *done = false: not available
+pp_status red_try(pp_comm* c, void* arr, long n, int32_t dtype, int32_t op, cudaStream_t s, bool* done);
+}
 // PS_Comm_Allreduce (support/ViewComm_gpu.hpp:184-210) on device memory, in place allowed
 extern "C" pp_status pp_comm_allreduce(pp_comm* c, const void* send, void* recv, int64_t count,
                                        int32_t dtype, int32_t op, pp_stream stream) {
@@ -215,6 +322,15 @@ extern "C" pp_status pp_comm_allreduce(pp_comm* c, const void* send, void* recv,
     return PP_OK;
   }
   PP_REQUIRE(op == PP_SUM || op == PP_MAX || op == PP_MIN, "unsupported reduction");
+  if (!c->comm) {                    // hosted communicator without NCCL: the peer-memory reduction
+    cudaStream_t s = (cudaStream_t)stream;
+    if (send != recv) PP_CUDA(cudaMemcpyAsync(recv, send, b * count, cudaMemcpyDeviceToDevice, s));
+    bool done = false;
+    PP_TRY(red_try(c, recv, (long)count, dtype, op, s, &done));
+    PP_REQUIRE(done || count == 0, "no transport: the peer-memory window could not be mapped and this "
+                                   "communicator was created without NCCL");
+    return PP_OK;
+  }
   const ncclRedOp_t o = op == PP_SUM ? ncclSum : op == PP_MAX ? ncclMax : ncclMin;
   PP_NCCL(g_nccl.AllReduce(send, recv, (size_t)count, t, o, c->comm, (cudaStream_t)stream));
   return PP_OK;
@@ -231,12 +347,14 @@ extern "C" pp_status pp_comm_alltoall(pp_comm* c, const void* send, void* recv, 
     if (send != recv) PP_CUDA(cudaMemcpyAsync(recv, send, b * count, cudaMemcpyDeviceToDevice, s));
     return PP_OK;
   }
-  PP_NCCL(g_nccl.GroupStart());
+  PP_NEED_NCCL(c);
+  NcclGroup group2;
+  PP_TRY(group2.begin());
   for (int p = 0; p < c->nranks; ++p) {
     PP_NCCL(g_nccl.Send((const char*)send + (size_t)p * count * b, (size_t)count, t, p, c->comm, s));
     PP_NCCL(g_nccl.Recv((char*)recv + (size_t)p * count * b, (size_t)count, t, p, c->comm, s));
   }
-  PP_NCCL(g_nccl.GroupEnd());
+  PP_TRY(group2.end());
   return PP_OK;
 }
 
@@ -247,6 +365,7 @@ extern "C" pp_status pp_comm_send(pp_comm* c, const void* buf, int64_t count, in
   PP_REQUIRE(c && c->nranks > 1 && (buf || count == 0) && peer >= 0 && peer < c->nranks, "bad argument");
   ncclDataType_t t; size_t b;
   PP_TRY(nccl_type(dtype, &t, &b));
+  PP_NEED_NCCL(c);
   PP_NCCL(g_nccl.Send(buf, (size_t)count, t, peer, c->comm, (cudaStream_t)stream));
   return PP_OK;
 }
@@ -255,6 +374,7 @@ extern "C" pp_status pp_comm_recv(pp_comm* c, void* buf, int64_t count, int32_t 
   PP_REQUIRE(c && c->nranks > 1 && (buf || count == 0) && peer >= 0 && peer < c->nranks, "bad argument");
   ncclDataType_t t; size_t b;
   PP_TRY(nccl_type(dtype, &t, &b));
+  PP_NEED_NCCL(c);
   PP_NCCL(g_nccl.Recv(buf, (size_t)count, t, peer, c->comm, (cudaStream_t)stream));
   return PP_OK;
 }
@@ -349,12 +469,8 @@ pp_status red_setup(pp_comm* c, size_t want_bytes, cudaStream_t s) {
     PP_CUDA(cudaDeviceSynchronize());
     for (int p = 0; p < R; ++p)
       if (p != me && w.peers.win[p]) { cudaIpcCloseMemHandle(w.peers.win[p]); w.peers.win[p] = nullptr; }
-    int* d_b;                          // barrier: all mappings are closed before an owner frees its window
-    PP_TRY(pp_dev_alloc(&d_b, 1, s));
-    PP_CUDA(cudaMemsetAsync(d_b, 0, sizeof(int), s));
-    PP_NCCL(g_nccl.AllReduce(d_b, d_b, 1, ncclInt32, ncclSum, c->comm, s));
-    PP_CUDA(cudaStreamSynchronize(s));
-    pp_dev_free(d_b, s);
+    int closed = 1;                    // barrier: all mappings are closed before an owner frees its window
+    PP_TRY(boot_min(c, &closed, s));
     cudaFree(w.local); w.local = nullptr;
     if (w.err) { cudaFree(w.err); w.err = nullptr; }
     w.ok = false;
@@ -364,15 +480,7 @@ pp_status red_setup(pp_comm* c, size_t want_bytes, cudaStream_t s) {
   const char* env = getenv("PUMIPIC_P2P");
   int ok = (R <= kMaxRanks && g_p2p_enable && !(env && env[0] == '0')) ? 1 : 0;
   long long h_sz = (long long)((want_bytes + 255) & ~(size_t)255);
-  {
-    long long* d_sz;
-    PP_TRY(pp_dev_alloc(&d_sz, 1, s));
-    PP_CUDA(cudaMemcpyAsync(d_sz, &h_sz, sizeof(h_sz), cudaMemcpyHostToDevice, s));
-    PP_NCCL(g_nccl.AllReduce(d_sz, d_sz, 1, ncclInt64, ncclMax, c->comm, s));
-    PP_CUDA(cudaMemcpyAsync(&h_sz, d_sz, sizeof(h_sz), cudaMemcpyDeviceToHost, s));
-    PP_CUDA(cudaStreamSynchronize(s));
-    pp_dev_free(d_sz, s);
-  }
+  PP_TRY(boot_max(c, &h_sz, s));
   w.cap_bytes = (size_t)h_sz;
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
@@ -383,14 +491,8 @@ pp_status red_setup(pp_comm* c, size_t want_bytes, cudaStream_t s) {
   }
   struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
   Msg m; m.h = mine; m.ok = ok; m.pad[0] = m.pad[1] = m.pad[2] = 0;
-  Msg *d_one, *d_all;
-  PP_TRY(pp_dev_alloc(&d_one, 1, s));
-  PP_TRY(pp_dev_alloc(&d_all, (size_t)R, s));
-  PP_CUDA(cudaMemcpyAsync(d_one, &m, sizeof(Msg), cudaMemcpyHostToDevice, s));
-  PP_NCCL(g_nccl.AllGather(d_one, d_all, sizeof(Msg), ncclUint8, c->comm, s));
   std::vector<Msg> all((size_t)R);
-  PP_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Msg) * R, cudaMemcpyDeviceToHost, s));
-  PP_CUDA(cudaStreamSynchronize(s));
+  PP_TRY(boot_allgather(c, &m, all.data(), sizeof(Msg), s));
   for (int p = 0; p < R; ++p) ok &= all[(size_t)p].ok;
   if (ok) {
     w.peers.win[me] = w.local;
@@ -401,12 +503,7 @@ pp_status red_setup(pp_comm* c, size_t want_bytes, cudaStream_t s) {
       w.peers.win[p] = (char*)q;
     }
   }
-  int* d_ok = (int*)d_one;
-  PP_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
-  PP_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, s));
-  PP_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PP_CUDA(cudaStreamSynchronize(s));
-  pp_dev_free(d_one, s); pp_dev_free(d_all, s);
+  PP_TRY(boot_min(c, &ok, s));         // everybody mapped everybody (also a barrier: all headers are zero)
   if (ok) {
     PP_CUDA(cudaMalloc((void**)&w.err, sizeof(int)));
     PP_CUDA(cudaMemset(w.err, 0, sizeof(int)));
@@ -438,6 +535,24 @@ pp_status red_run(pp_comm* c, T* arr, long n, int op, cudaStream_t s) {
 }
 }  // namespace
 
+namespace {
+pp_status red_try(pp_comm* c, void* arr, long n, int32_t dtype, int32_t op, cudaStream_t s, bool* done) {
+  *done = false;
+  const size_t esz = (dtype == PP_INT32 || dtype == PP_FLOAT32) ? 4 : 8;
+  if (n <= 0 || !(op == PP_SUM || op == PP_MAX || op == PP_MIN)) return PP_OK;
+  if (!c->red.tried || (c->red.ok && (size_t)n * esz > c->red.cap_bytes)) PP_TRY(red_setup(c, (size_t)n * esz, s));
+  if (!c->red.ok || (size_t)n * esz > c->red.cap_bytes) return PP_OK;
+  *done = true;
+  switch (dtype) {
+    case PP_INT32: return red_run(c, (int*)arr, n, op, s);
+    case PP_INT64: return red_run(c, (long long*)arr, n, op, s);
+    case PP_FLOAT32: return red_run(c, (float*)arr, n, op, s);
+    case PP_FLOAT64: return red_run(c, (double*)arr, n, op, s);
+    default: *done = false; return PP_OK;
+  }
+}
+}  // namespace
+
 extern "C" pp_status pp_comm_array_reduce(pp_comm* c, void* comm_array, int64_t nents, int32_t nvals,
                                           int32_t dtype, int32_t op, const int32_t* ent_owner,
                                           pp_stream stream) {
@@ -461,20 +576,9 @@ extern "C" pp_status pp_comm_array_reduce(pp_comm* c, void* comm_array, int64_t 
   }
   // peer-memory reduction (default between GPUs with peer access): reduce-scatter + all-gather by
   // direct NVLink loads / stores, fixed rank order; the window is sized by the first call
-  const long n = (long)(nents * nvals);
-  const size_t esz = (dtype == PP_INT32 || dtype == PP_FLOAT32) ? 4 : 8;
-  if (n > 0 && (nccl_op == PP_SUM || nccl_op == PP_MAX || nccl_op == PP_MIN)) {
-    if (!c->red.tried || (c->red.ok && (size_t)n * esz > c->red.cap_bytes)) PP_TRY(red_setup(c, (size_t)n * esz, s));
-    if (c->red.ok && (size_t)n * esz <= c->red.cap_bytes) {
-      switch (dtype) {
-        case PP_INT32: return red_run(c, (int*)comm_array, n, nccl_op, s);
-        case PP_INT64: return red_run(c, (long long*)comm_array, n, nccl_op, s);
-        case PP_FLOAT32: return red_run(c, (float*)comm_array, n, nccl_op, s);
-        case PP_FLOAT64: return red_run(c, (double*)comm_array, n, nccl_op, s);
-        default: break;
-      }
-    }
-  }
+  bool done = false;
+  PP_TRY(red_try(c, comm_array, (long)(nents * nvals), dtype, nccl_op, s, &done));
+  if (done) return PP_OK;
   return pp_comm_allreduce(c, comm_array, comm_array, nents * nvals, dtype, nccl_op, stream);
 }
 
@@ -813,14 +917,8 @@ pp_status p2p_setup(pp_comm* c, size_t want_seg_bytes, cudaStream_t s) {
   // windows with it)
   if (!w.seg_set && want_seg_bytes > w.seg_bytes) w.seg_bytes = (want_seg_bytes + 15) & ~(size_t)15;
   {
-    long long* d_sz;
     long long h_sz = (long long)w.seg_bytes;
-    PP_TRY(pp_dev_alloc(&d_sz, 1, s));
-    PP_CUDA(cudaMemcpyAsync(d_sz, &h_sz, sizeof(h_sz), cudaMemcpyHostToDevice, s));
-    PP_NCCL(g_nccl.AllReduce(d_sz, d_sz, 1, ncclInt64, ncclMax, c->comm, s));
-    PP_CUDA(cudaMemcpyAsync(&h_sz, d_sz, sizeof(h_sz), cudaMemcpyDeviceToHost, s));
-    PP_CUDA(cudaStreamSynchronize(s));
-    pp_dev_free(d_sz, s);
+    PP_TRY(boot_max(c, &h_sz, s));
     w.seg_bytes = (size_t)h_sz;
   }
   const size_t bytes = sizeof(P2PHeader) + 2 * (size_t)R * w.seg_bytes;
@@ -837,14 +935,8 @@ pp_status p2p_setup(pp_comm* c, size_t want_seg_bytes, cudaStream_t s) {
   struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
   static_assert(sizeof(Msg) % 8 == 0, "message size");
   Msg m; m.h = mine; m.ok = ok; m.pad[0] = m.pad[1] = m.pad[2] = 0;
-  Msg *d_one, *d_all;
-  PP_TRY(pp_dev_alloc(&d_one, 1, s));
-  PP_TRY(pp_dev_alloc(&d_all, (size_t)R, s));
-  PP_CUDA(cudaMemcpyAsync(d_one, &m, sizeof(Msg), cudaMemcpyHostToDevice, s));
-  PP_NCCL(g_nccl.AllGather(d_one, d_all, sizeof(Msg), ncclUint8, c->comm, s));
   std::vector<Msg> all((size_t)R);
-  PP_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Msg) * R, cudaMemcpyDeviceToHost, s));
-  PP_CUDA(cudaStreamSynchronize(s));
+  PP_TRY(boot_allgather(c, &m, all.data(), sizeof(Msg), s));
   for (int p = 0; p < R; ++p) ok &= all[(size_t)p].ok;
   if (ok) {
     w.peers.win[me] = w.local;
@@ -858,12 +950,7 @@ pp_status p2p_setup(pp_comm* c, size_t want_seg_bytes, cudaStream_t s) {
     }
   }
   // everybody must have mapped everybody (also a barrier: no rank writes before all headers are zero)
-  int* d_ok = (int*)d_one;
-  PP_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
-  PP_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, s));
-  PP_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PP_CUDA(cudaStreamSynchronize(s));
-  pp_dev_free(d_one, s); pp_dev_free(d_all, s);
+  PP_TRY(boot_min(c, &ok, s));
   if (ok) {
     PP_CUDA(cudaMalloc((void**)&w.dev, sizeof(int) * (3 * (size_t)R + 8)));
     PP_CUDA(cudaMalloc((void**)&w.dev_stats, 4 * sizeof(long long)));
@@ -1007,10 +1094,12 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
                          stats_host, pt, s);
   }
   // ---- NCCL path (no peer access between the GPUs, or pp_comm_set_p2p(0))
+  PP_NEED_NCCL(comm);
+  DevScope scratch(s);                 // every early return below frees what was allocated so far
   // 1. particles per destination, 2. counts to everybody (PS_Comm_Ialltoall, :48)
   int *send_cnt, *all_cnt;
-  PP_TRY(pp_dev_alloc(&send_cnt, R, s));
-  PP_TRY(pp_dev_alloc(&all_cnt, (size_t)R * R, s));
+  PP_TRY(scratch.alloc(&send_cnt, R));
+  PP_TRY(scratch.alloc(&all_cnt, (size_t)R * R));
   PP_CUDA(cudaMemsetAsync(send_cnt, 0, sizeof(int) * R, s));
   if (ps->capacity > 0)
     k_count_dest<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_process, new_element, me, R,
@@ -1037,13 +1126,13 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
   char *sendbuf, *recvbuf;
   size_t *d_sbo, *d_rbo;
   int *cursor, *d_recv_cnt, *d_recv_off;
-  PP_TRY(pp_dev_alloc(&sendbuf, h_sbo[R] + 8, s));
-  PP_TRY(pp_dev_alloc(&recvbuf, h_rbo[R] + 8, s));
-  PP_TRY(pp_dev_alloc(&d_sbo, R + 1, s));
-  PP_TRY(pp_dev_alloc(&d_rbo, R + 1, s));
-  PP_TRY(pp_dev_alloc(&cursor, R, s));
-  PP_TRY(pp_dev_alloc(&d_recv_cnt, R, s));
-  PP_TRY(pp_dev_alloc(&d_recv_off, R + 1, s));
+  PP_TRY(scratch.alloc(&sendbuf, h_sbo[R] + 8));
+  PP_TRY(scratch.alloc(&recvbuf, h_rbo[R] + 8));
+  PP_TRY(scratch.alloc(&d_sbo, R + 1));
+  PP_TRY(scratch.alloc(&d_rbo, R + 1));
+  PP_TRY(scratch.alloc(&cursor, R));
+  PP_TRY(scratch.alloc(&d_recv_cnt, R));
+  PP_TRY(scratch.alloc(&d_recv_off, R + 1));
   PP_CUDA(cudaMemcpyAsync(d_sbo, h_sbo.data(), sizeof(size_t) * (R + 1), cudaMemcpyHostToDevice, s));
   PP_CUDA(cudaMemcpyAsync(d_rbo, h_rbo.data(), sizeof(size_t) * (R + 1), cudaMemcpyHostToDevice, s));
   PP_CUDA(cudaMemcpyAsync(d_recv_cnt, h_recv.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s));
@@ -1055,38 +1144,41 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
         cursor, pt, ps->stride, sendbuf);
   PP_KERNEL_CHECK();
   // 4. all-to-all-v: grouped send/recv, one message per peer (:148-175 uses 1+num_types per peer)
-  PP_NCCL(g_nccl.GroupStart());
-  for (int p = 0; p < R; ++p) {
-    if (p == me) continue;
-    if (h_send[p] > 0)
-      PP_NCCL(g_nccl.Send(sendbuf + h_sbo[p], h_sbo[p + 1] - h_sbo[p], ncclUint8, p, comm->comm, s));
-    if (h_recv[p] > 0)
-      PP_NCCL(g_nccl.Recv(recvbuf + h_rbo[p], h_rbo[p + 1] - h_rbo[p], ncclUint8, p, comm->comm, s));
+  {
+    NcclGroup group;                   // closes the group on every path: an open group would hang the peers
+    PP_TRY(group.begin());
+    for (int p = 0; p < R; ++p) {
+      if (p == me) continue;
+      if (h_send[p] > 0)
+        PP_NCCL(g_nccl.Send(sendbuf + h_sbo[p], h_sbo[p + 1] - h_sbo[p], ncclUint8, p, comm->comm, s));
+      if (h_recv[p] > 0)
+        PP_NCCL(g_nccl.Recv(recvbuf + h_rbo[p], h_rbo[p + 1] - h_rbo[p], ncclUint8, p, comm->comm, s));
+    }
+    PP_TRY(group.end());
   }
-  PP_NCCL(g_nccl.GroupEnd());
   // 5. unpack into contiguous new-particle arrays, gid -> lid, append the caller's new particles
   const int n_in = (int)tot_recv + n_new;
   std::vector<char*> in_data(ps->nmembers, nullptr);
   int* in_elems = nullptr;
   int* bad;
-  PP_TRY(pp_dev_alloc(&bad, 1, s));
+  PP_TRY(scratch.alloc(&bad, 1));
   PP_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
   pp_status st = PP_OK;
   if (n_in > 0) {
-    PP_TRY(pp_dev_alloc(&in_elems, n_in, s));
+    PP_TRY(scratch.alloc(&in_elems, n_in));
     for (int k = 0; k < ps->nmembers; ++k)
-      PP_TRY(pp_dev_alloc(&in_data[k], (size_t)pt.bytes[k] * pt.ncomp[k] * n_in, s));
+      PP_TRY(scratch.alloc(&in_data[k], (size_t)pt.bytes[k] * pt.ncomp[k] * n_in));
     // [ncomp][n_in] with received particles first; the caller's new particles follow
     if (tot_recv > 0) {
       // received particles are written with row length n_in so both groups share one array
       char** d_dst;
-      PP_TRY(pp_dev_alloc(&d_dst, ps->nmembers, s));
+      PP_TRY(scratch.alloc(&d_dst, ps->nmembers));
       PP_CUDA(cudaMemcpyAsync(d_dst, in_data.data(), sizeof(char*) * ps->nmembers, cudaMemcpyHostToDevice, s));
       if (ps->elem_gids && !ps->sorted_gid) {
         // lazily build the sorted gid table (createGlobalMapping, SCS_buildFns.h:101-112)
         long long* keys_in = (long long*)ps->elem_gids;
         int* vals_in;
-        PP_TRY(pp_dev_alloc(&vals_in, ps->nelems, s));
+        PP_TRY(scratch.alloc(&vals_in, ps->nelems));
         PP_TRY(pp_dev_alloc(&ps->sorted_gid, ps->nelems, s));
         PP_TRY(pp_dev_alloc(&ps->sorted_lid, ps->nelems, s));
         k_iota<<<pp_div_up(ps->nelems, kBlock), kBlock, 0, s>>>(vals_in, ps->nelems);
@@ -1094,16 +1186,14 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
         cub::DeviceRadixSort::SortPairs(nullptr, tb, keys_in, (long long*)ps->sorted_gid, vals_in,
                                         ps->sorted_lid, ps->nelems, 0, 64, s);
         char* tmp;
-        PP_TRY(pp_dev_alloc(&tmp, tb, s));
+        PP_TRY(scratch.alloc(&tmp, tb));
         PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, keys_in, (long long*)ps->sorted_gid, vals_in,
                                                 ps->sorted_lid, ps->nelems, 0, 64, s));
-        pp_dev_free(tmp, s); pp_dev_free(vals_in, s);
       }
       // rows are n_in long so that the caller's new particles can follow the received ones
       k_unpack<<<pp_div_up(tot_recv, kBlock), kBlock, 0, s>>>(
           recvbuf, d_rbo, d_recv_cnt, d_recv_off, R, (int)tot_recv, n_in, pt, d_dst,
           (const long long*)ps->sorted_gid, ps->sorted_lid, ps->nelems, in_elems, bad);
-      pp_dev_free(d_dst, s);
     }
     if (n_new > 0) {
       PP_CUDA(cudaMemcpyAsync(in_elems + tot_recv, new_particle_elements, sizeof(int) * n_new,
@@ -1131,11 +1221,6 @@ extern "C" pp_status pp_ps_migrate(pp_ps* ps, pp_comm* comm, int32_t* new_elemen
     for (int k = 0; k < ps->nmembers; ++k) info[k] = in_data[k];
     st = pp_ps_rebuild(ps, new_element, n_in, in_elems, n_in > 0 ? info.data() : nullptr, stream_);
   }
-  for (char* p : in_data) pp_dev_free(p, s);
-  pp_dev_free(in_elems, s); pp_dev_free(bad, s);
-  pp_dev_free(send_cnt, s); pp_dev_free(all_cnt, s); pp_dev_free(sendbuf, s); pp_dev_free(recvbuf, s);
-  pp_dev_free(d_sbo, s); pp_dev_free(d_rbo, s); pp_dev_free(cursor, s);
-  pp_dev_free(d_recv_cnt, s); pp_dev_free(d_recv_off, s);
   return st;
 }
 
@@ -1198,7 +1283,8 @@ pp_status plan_reduce_t(pp_comm_plan* pl, T* arr, int nvals, int op, ncclDataTyp
     // fan in: every copy goes to the owner of its entity
     if (ns) k_plan_pack<<<blocks(ns), kBlock, 0, s>>>(arr, pl->d_send_idx, ns, nvals, sbuf);
     PP_KERNEL_CHECK();
-    PP_NCCL(g_nccl.GroupStart());
+    NcclGroup group3;
+    PP_TRY(group3.begin());
     for (int p = 0; p < R; ++p) {
       if (p == me) continue;
       const int64_t a = pl->send_off[p], b = pl->send_off[p + 1];
@@ -1206,7 +1292,7 @@ pp_status plan_reduce_t(pp_comm_plan* pl, T* arr, int nvals, int op, ncclDataTyp
       const int64_t ra = pl->recv_off[p], rb = pl->recv_off[p + 1];
       if (rb > ra) PP_NCCL(g_nccl.Recv(rbuf + ra * nvals, (size_t)(rb - ra) * nvals, nt, p, c->comm, s));
     }
-    PP_NCCL(g_nccl.GroupEnd());
+    PP_TRY(group3.end());
     for (int p = 0; p < R; ++p) {          // ascending rank order: bit-reproducible sums
       const int64_t ra = pl->recv_off[p], rb = pl->recv_off[p + 1];
       if (rb > ra)
@@ -1218,7 +1304,8 @@ pp_status plan_reduce_t(pp_comm_plan* pl, T* arr, int nvals, int op, ncclDataTyp
   // fan out: the owner's value (the total) goes back to every copy
   if (nr) k_plan_pack<<<blocks(nr), kBlock, 0, s>>>(arr, pl->d_recv_idx, nr, nvals, rbuf);
   PP_KERNEL_CHECK();
-  PP_NCCL(g_nccl.GroupStart());
+  NcclGroup group4;
+  PP_TRY(group4.begin());
   for (int p = 0; p < R; ++p) {
     if (p == me) continue;
     const int64_t ra = pl->recv_off[p], rb = pl->recv_off[p + 1];
@@ -1226,7 +1313,7 @@ pp_status plan_reduce_t(pp_comm_plan* pl, T* arr, int nvals, int op, ncclDataTyp
     const int64_t a = pl->send_off[p], b = pl->send_off[p + 1];
     if (b > a) PP_NCCL(g_nccl.Recv(sbuf + a * nvals, (size_t)(b - a) * nvals, nt, p, c->comm, s));
   }
-  PP_NCCL(g_nccl.GroupEnd());
+  PP_TRY(group4.end());
   if (ns) k_plan_unpack<<<blocks(ns), kBlock, 0, s>>>(arr, pl->d_send_idx, ns, nvals, sbuf);
   PP_KERNEL_CHECK();
   pp_dev_free(sbuf, s); pp_dev_free(rbuf, s);
@@ -1241,6 +1328,7 @@ extern "C" pp_status pp_comm_plan_create(pp_comm* c, int64_t nents, const int64_
   PP_REQUIRE(nents < (int64_t)1 << 31, "too many entities");
   cudaStream_t s = (cudaStream_t)stream;
   const int R = c->nranks, me = c->rank;
+  PP_REQUIRE(c->nranks == 1 || c->comm, "comm plans (owner fan-in / fan-out) use NCCL: create the communicator with NCCL");
   pp_comm_plan* pl = new pp_comm_plan();
   pl->comm = c; pl->nents = nents; pl->d_send_idx = nullptr; pl->d_recv_idx = nullptr;
   pl->send_off.assign(R + 1, 0); pl->recv_off.assign(R + 1, 0);
@@ -1286,7 +1374,8 @@ extern "C" pp_status pp_comm_plan_create(pp_comm* c, int64_t nents, const int64_
   PP_TRY(pp_dev_alloc(&d_sg, (size_t)ns, s));
   PP_TRY(pp_dev_alloc(&d_rg, (size_t)nr, s));
   if (ns) PP_CUDA(cudaMemcpyAsync(d_sg, send_gid.data(), sizeof(int64_t) * ns, cudaMemcpyHostToDevice, s));
-  PP_NCCL(g_nccl.GroupStart());
+  NcclGroup group5;
+  PP_TRY(group5.begin());
   for (int p = 0; p < R; ++p) {
     if (p == me) continue;
     const int64_t a = pl->send_off[p], b = pl->send_off[p + 1];
@@ -1294,7 +1383,7 @@ extern "C" pp_status pp_comm_plan_create(pp_comm* c, int64_t nents, const int64_
     const int64_t ra = pl->recv_off[p], rb = pl->recv_off[p + 1];
     if (rb > ra) PP_NCCL(g_nccl.Recv(d_rg + ra, (size_t)(rb - ra), ncclInt64, p, c->comm, s));
   }
-  PP_NCCL(g_nccl.GroupEnd());
+  PP_TRY(group5.end());
   std::vector<int64_t> recv_gid((size_t)nr);
   if (nr) PP_CUDA(cudaMemcpyAsync(recv_gid.data(), d_rg, sizeof(int64_t) * nr, cudaMemcpyDeviceToHost, s));
   PP_CUDA(cudaStreamSynchronize(s));

@@ -241,13 +241,16 @@ bool Reader::array(int elem_bytes, bool compressed, std::vector<char>& out) {
     ok = false;
     return false;
   }
-  out.resize((size_t)n * elem_bytes);
+  const size_t want = (size_t)n * elem_bytes;
   if (compressed) {
     const int64_t nb = value<int64_t>();
-    if (!ok || nb < 0 || pos + (size_t)nb > buf.size()) {
+    // a deflate stream expands by at most ~1032:1: a count that the stream cannot produce is a
+    // corrupt file, not a reason to allocate
+    if (!ok || nb < 0 || (size_t)nb > buf.size() - pos || want > (size_t)nb * 1040 + 64) {
       ok = false;
       return false;
     }
+    out.resize(want);
     uLongf dest = (uLongf)out.size();
     // zlib wants a non-null destination even for empty arrays
     char dummy = 0;
@@ -258,8 +261,13 @@ bool Reader::array(int elem_bytes, bool compressed, std::vector<char>& out) {
       return false;
     }
     pos += (size_t)nb;
-  } else if (!raw(out.data(), out.size())) {
-    return false;
+  } else {
+    if (want > buf.size() - pos) {
+      ok = false;
+      return false;
+    }
+    out.resize(want);
+    if (!raw(out.data(), out.size())) return false;
   }
   return true;
 }
@@ -283,8 +291,8 @@ bool Writer::save(const char* path) const {
   FILE* f = fopen(path, "wb");
   if (!f) return false;
   const size_t put = buf.empty() ? 0 : fwrite(buf.data(), 1, buf.size(), f);
-  const bool good = put == buf.size() && fclose(f) == 0;
-  return good;
+  const bool closed = fclose(f) == 0;      // on every path: a short write must not leak the handle
+  return put == buf.size() && closed;
 }
 
 bool read_small_int(const std::string& path, int* out) {

@@ -411,6 +411,17 @@ bool build_picpart(const HMesh& full, const int32_t* elem_owner, int nranks, int
 }
 
 // ------------------------------------------------------------------ .ppm files
+// Array compression of the .ppm stream: the reference's OMEGA_H_USE_ZLIB build switch
+// (pumipic_file.cpp:76-80), here a run-time setting (pp_host_ppm_set_compression, or
+// PUMIPIC_PPM_ZLIB=0 in the environment); default on, like the reference's usual build.
+int g_ppm_compress = -1;
+bool ppm_compression() {
+  if (g_ppm_compress < 0) {
+    const char* env = getenv("PUMIPIC_PPM_ZLIB");
+    g_ppm_compress = (env && env[0] == '0') ? 0 : 1;
+  }
+  return g_ppm_compress != 0;
+}
 const char* split_path(const char* full_path) {
   const char* s = strrchr(full_path, '/');
   return s ? s + 1 : full_path;
@@ -428,7 +439,7 @@ bool write_ppm(const Picpart& pp, const char* prefix) {
   const std::string base = dir + "/" + name + "_" + std::to_string(pp.rank);
   if (!write_osh(pp.mesh, (base + ".osh").c_str())) return false;
   Writer w;
-  const bool comp = true;
+  const bool comp = ppm_compression();      // the file carries no flag: it must match the reader's build
   w.value<int8_t>(2);                       // version
   w.value<int8_t>(pp.is_full_mesh ? 1 : 0);
   for (int i = 0; i < 4; ++i) {
@@ -513,34 +524,50 @@ bool read_ppm(const char* prefix, int nranks, int rank, Picpart& pp) {
     pp_set_error("Cannot open file %s.ppm", base.c_str());
     return false;
   }
-  const bool comp = true;
-  const int8_t version = r.value<int8_t>();
-  pp.is_full_mesh = r.value<int8_t>() != 0;
+  // The reference compresses the arrays only when Omega_h was built with zlib
+  // (pumipic_file.cpp:76-80) and the file does not say which: parse with the configured setting
+  // first and, if the arrays do not decode, once more the other way.
+  int8_t version = 0;
+  auto parse = [&](bool comp) -> bool {
+    r.pos = 0;
+    r.ok = true;
+    version = r.value<int8_t>();
+    pp.is_full_mesh = r.value<int8_t>() != 0;
+    if (!r.ok || version < 1 || version > 2) return false;
+    for (int i = 0; i < 4 && r.ok; ++i) {
+      PicpartDim& d = pp.d[i];
+      d = PicpartDim();
+      if (version >= 2) d.num_entities = r.value<int64_t>();
+      d.num_cores = r.value<int32_t>();
+      r.typed_array(comp, d.buffered_parts);
+      r.typed_array(comp, d.offset_ents_per_rank);
+      r.typed_array(comp, d.ent_to_comm_arr_index);
+      r.typed_array(comp, d.is_complete_part);
+      d.num_bounds = r.value<int32_t>();
+      d.num_boundaries = r.value<int32_t>();
+      r.typed_array(comp, d.boundary_parts);
+      r.typed_array(comp, d.offset_bounded);
+      r.typed_array(comp, d.bounded_ent_ids);
+    }
+    return r.ok && r.pos == r.buf.size();
+  };
   pp.nranks = nranks;
   pp.rank = rank;
-  if (version < 1 || version > 2) {
-    pp_set_error("%s.ppm: unsupported version %d", base.c_str(), (int)version);
+  const bool first = ppm_compression();
+  if (!parse(first) && !parse(!first)) {
+    if (r.buf.size() >= 1 && (r.buf[0] < 1 || r.buf[0] > 2))
+      pp_set_error("%s.ppm: unsupported version %d", base.c_str(), (int)r.buf[0]);
+    else
+      pp_set_error("%s.ppm is truncated or corrupt", base.c_str());
     return false;
   }
-  for (int i = 0; i < 4 && r.ok; ++i) {
-    PicpartDim& d = pp.d[i];
-    d = PicpartDim();
-    if (version >= 2) d.num_entities = r.value<int64_t>();
-    d.num_cores = r.value<int32_t>();
-    r.typed_array(comp, d.buffered_parts);
-    r.typed_array(comp, d.offset_ents_per_rank);
-    r.typed_array(comp, d.ent_to_comm_arr_index);
-    r.typed_array(comp, d.is_complete_part);
-    d.num_bounds = r.value<int32_t>();
-    d.num_boundaries = r.value<int32_t>();
-    r.typed_array(comp, d.boundary_parts);
-    r.typed_array(comp, d.offset_bounded);
-    r.typed_array(comp, d.bounded_ent_ids);
-  }
-  if (!r.ok) {
-    pp_set_error("%s.ppm is truncated or corrupt", base.c_str());
-    return false;
-  }
+  for (int i = 0; i <= pp.mesh.dim; ++i)
+    if ((int)pp.d[i].offset_ents_per_rank.size() != nranks + 1 || (int)pp.d[i].is_complete_part.size() != nranks) {
+      pp_set_error("%s.ppm was not written for %d ranks (dimension %d: %d offsets, %d completeness flags)",
+                   base.c_str(), nranks, i, (int)pp.d[i].offset_ents_per_rank.size(),
+                   (int)pp.d[i].is_complete_part.size());
+      return false;
+    }
   for (int i = 0; i <= pp.mesh.dim; ++i)
     if ((int)pp.d[i].ent_to_comm_arr_index.size() != pp.mesh.nents[i]) {
       pp_set_error("%s.ppm does not match its mesh (dimension %d: %d entries for %d entities)",
@@ -556,6 +583,8 @@ bool read_ppm(const char* prefix, int nranks, int rank, Picpart& pp) {
 
 using pph::HMesh;
 using pph::Picpart;
+
+extern "C" void pp_host_ppm_set_compression(int32_t on) { pph::g_ppm_compress = on ? 1 : 0; }
 
 extern "C" pp_status pp_host_picpart_build(const pp_host_mesh* full, const int32_t* elem_owner,
                                            int32_t nranks, int32_t rank, int32_t buffer_method,

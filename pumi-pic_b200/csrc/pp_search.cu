@@ -1180,6 +1180,56 @@ double unmoved_threshold(double tol) {
 
 int g_sm_count = 0;
 
+// Optional L2 access-policy window over the walk table (pp_search_set_l2_window / PUMIPIC_L2_WINDOW):
+// a fraction of the table's lines is marked persisting, everything else the kernel touches (the
+// particle columns, read once) streams.  Off by default: the fused kernel's DRAM traffic is already
+// within 2 % of its floor (every record comes from DRAM about once, profiles/r2l_ncu_k_walk_scs.txt),
+// so there is nothing for the window to save -- measured, profiles/r2F_l2_window_ab.txt.
+double g_l2_window = -1.0;      // < 0: read the environment on first use
+size_t g_l2_persist_max = 0, g_l2_window_max = 0;
+
+template <class K>
+pp_status launch_with_window(K kernel, int grid, int block, size_t smem, cudaStream_t s, const SearchParams& p,
+                             const void* table, size_t table_bytes) {
+  if (g_l2_window < 0) {
+    const char* env = getenv("PUMIPIC_L2_WINDOW");
+    g_l2_window = env ? atof(env) : 0.0;
+    if (g_l2_window < 0) g_l2_window = 0;
+  }
+  if (g_l2_window <= 0 || !table || !table_bytes) {
+    kernel<<<grid, block, smem, s>>>(p);
+    return PP_OK;
+  }
+  if (!g_l2_persist_max) {
+    int dev = 0, v = 0;
+    PP_CUDA(cudaGetDevice(&dev));
+    PP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    g_l2_persist_max = (size_t)v;
+    PP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    g_l2_window_max = (size_t)v;
+    if (g_l2_persist_max) PP_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g_l2_persist_max));
+  }
+  if (!g_l2_persist_max || !g_l2_window_max) {      // no persisting L2 on this device
+    kernel<<<grid, block, smem, s>>>(p);
+    return PP_OK;
+  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+  cudaAccessPolicyWindow& w = attr[0].val.accessPolicyWindow;
+  w.base_ptr = const_cast<void*>(table);
+  w.num_bytes = table_bytes < g_l2_window_max ? table_bytes : g_l2_window_max;
+  // the share of the window's lines that may persist: the requested fraction of the persisting carve-out
+  const double ratio = g_l2_window * (double)g_l2_persist_max / (double)w.num_bytes;
+  w.hitRatio = (float)(ratio < 1.0 ? ratio : 1.0);
+  w.hitProp = cudaAccessPropertyPersisting;
+  w.missProp = cudaAccessPropertyStreaming;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = 1;
+  PP_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  return PP_OK;
+}
+
 template <int DIM, bool LEG>
 pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
   constexpr int WARPS = 4;
@@ -1193,18 +1243,20 @@ pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
   if (want <= 0) return PP_OK;                         // nothing but empty chunks in the range
   const int persistent = g_sm_count * PP_SCS_MINB;
   const int grid = want < persistent ? want : persistent;
+  const void* table = DIM == 3 ? p.walk_bcc : p.walk;
+  const size_t table_bytes = (size_t)p.nelems * sizeof(typename StageCfg<DIM>::Raw);
   if (push && !LEG && p.push_from_orig) {
     auto k = k_walk_scs<DIM, 2, false, WARPS>;
     PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, s>>>(p);
+    PP_TRY(launch_with_window(k, grid, WARPS * 32, smem, s, p, table, table_bytes));
   } else if (push && !LEG) {
     auto k = k_walk_scs<DIM, 1, false, WARPS>;
     PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, s>>>(p);
+    PP_TRY(launch_with_window(k, grid, WARPS * 32, smem, s, p, table, table_bytes));
   } else {
     auto k = k_walk_scs<DIM, 0, LEG, WARPS>;
     PP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, s>>>(p);
+    PP_TRY(launch_with_window(k, grid, WARPS * 32, smem, s, p, table, table_bytes));
   }
   return PP_OK;
 }
@@ -1362,6 +1414,8 @@ extern "C" pp_status pp_search_mesh(pp_mesh* mesh, pp_ps* ps, const pp_search_ar
   return do_search(mesh, ps->view(), ps->nelems, args, nullptr, 0.0, false, 0, stats_host,
                    (cudaStream_t)stream);
 }
+
+extern "C" void pp_search_set_l2_window(double fraction) { g_l2_window = fraction > 0 ? (fraction < 1 ? fraction : 1.0) : 0.0; }
 
 extern "C" void pp_search_set_staged(int32_t on) { g_staged_walk = on < 0 ? 0 : (on > 2 ? 2 : on); }
 

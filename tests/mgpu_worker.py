@@ -29,6 +29,18 @@ TYPES = [(np.int32, 1), (np.float64, 3), (np.int32, 1)]
 PIC = [(np.float64, 3), (np.float64, 3), (np.int32, 1), (np.float64, 3)]
 
 
+SHARED_GPU = os.environ.get("MGPU_SHARED_GPU") == "1"   # all ranks on cuda:0, no NCCL (single-GPU box)
+HOSTED = SHARED_GPU or os.environ.get("MGPU_HOSTED") == "1"
+
+
+def make_comm(P):
+    """NCCL id over torch.distributed (default), or the hosted bootstrap (pp_comm_create_hosted) with
+    torch.distributed's all-gather as the application's callback -- without NCCL when the ranks share a GPU."""
+    if HOSTED:
+        return P.Comm(hosted=True, nccl=not SHARED_GPU)
+    return P.Comm()
+
+
 def dev(a):
     return torch.as_tensor(np.ascontiguousarray(a)).cuda()
 
@@ -143,9 +155,21 @@ def test_comm_array(P, comm, rank, R):
     assert np.array_equal(val.cpu().numpy(), want)
     a = torch.arange(R * 3, dtype=torch.int32, device="cuda") + 100 * rank
     b = torch.empty_like(a)
-    comm.alltoall(a, b)
-    want = np.concatenate([np.arange(3) + 3 * rank + 100 * p for p in range(R)])
-    assert np.array_equal(b.cpu().numpy(), want)
+    if not SHARED_GPU:
+        comm.alltoall(a, b)
+        want = np.concatenate([np.arange(3) + 3 * rank + 100 * p for p in range(R)])
+        assert np.array_equal(b.cpu().numpy(), want)
+    elif R > 1:
+        # a communicator without NCCL says so instead of crashing
+        try:
+            comm.alltoall(a, b)
+            raise AssertionError("alltoall on a communicator without NCCL must fail")
+        except P.PumipicError as e:
+            assert "no NCCL transport" in str(e)
+        # PS_Comm_Allreduce runs over the peer-memory window there
+        t = dev(np.arange(5, dtype=np.float64) + rank)
+        comm.allreduce(t)
+        assert np.array_equal(t.cpu().numpy(), R * np.arange(5.0) + R * (R - 1) / 2)
     # a larger array (the window grows, collectively), random doubles: the sum in ascending rank order,
     # bit for bit, on every rank
     for n2 in (50000, 777777):
@@ -379,7 +403,7 @@ def test_small_window(P, rank, R):
     """Peer-memory window with room for 100 particles per peer: a step that wants to send more keeps the
     rest (stats.deferred) with their new_process still set; repeating the migration drains them, and
     no particle is lost or duplicated."""
-    comm = P.Comm()
+    comm = make_comm(P)
     ne, npr = 64, 3000
     ppe = np.full(ne, npr // ne, np.int32); ppe[: npr % ne] += 1
     pel = np.repeat(np.arange(ne, dtype=np.int32), ppe)
@@ -469,10 +493,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     R = int(os.environ.get("WORLD_SIZE", "1"))
+    if SHARED_GPU:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl" if R > 1 else "gloo", device_id=torch.device("cuda", local) if R > 1 else None)
+    nccl = R > 1 and not SHARED_GPU
+    dist.init_process_group("nccl" if nccl else "gloo", device_id=torch.device("cuda", local) if nccl else None)
     P = importlib.import_module("pumi-pic_b200")
-    comm = P.Comm()
+    comm = make_comm(P)
     only = os.environ.get("MGPU_ONLY", "")       # e.g. MGPU_ONLY=balancer for one scenario
     if only in ("", "comm_array"):
         test_comm_array(P, comm, rank, R)
@@ -480,7 +507,7 @@ def main():
         test_migrate(P, comm, rank, R)
     if only in ("", "pic_loop"):
         test_pic_loop(P, comm, rank, R)
-    if only in ("", "partial"):
+    if only in ("", "partial") and not SHARED_GPU:     # comm plans are NCCL send/recv
         test_partial_picparts(P, comm, rank, R)
     # One rank: repartition is a no-op (pumipic_lb.hpp:360-361)
     if R > 1 and only in ("", "balancer"):

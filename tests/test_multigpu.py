@@ -1,5 +1,6 @@
-"""Launches tests/mgpu_worker.py: one rank on a single-GPU box (serial paths of migrate /
-reduceCommArray), and 2 (or 4) NCCL ranks when the box has that many GPUs."""
+"""Launches tests/mgpu_worker.py: one rank (serial paths of migrate / reduceCommArray), two ranks that
+share one GPU (peer-memory transport between two processes, no NCCL: runs on a single-GPU box), and 2
+(or 4) ranks on as many GPUs (NCCL + peer memory over NVLink) when the box has them."""
 import os
 import subprocess
 import sys
@@ -10,9 +11,10 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(n, p2p=True, only=""):
+def _run(n, p2p=True, only="", shared_gpu=False, hosted=False):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", PUMIPIC_P2P="1" if p2p else "0", MGPU_ONLY=only,
-               MGPU_EXPECT_P2P="1" if (p2p and n > 1) else "0")
+               MGPU_EXPECT_P2P="1" if (p2p and n > 1) else "0", MGPU_SHARED_GPU="1" if shared_gpu else "0",
+               MGPU_HOSTED="1" if hosted else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", str(29511 + n),
            os.path.join(HERE, "mgpu_worker.py")]
@@ -22,6 +24,24 @@ def _run(n, p2p=True, only=""):
 
 def test_single_rank_paths():
     _run(1)
+
+
+def test_two_ranks_on_one_gpu():
+    """Two ranks that SHARE cuda:0 (what a single-GPU box can run): communicator from the hosted
+    bootstrap without NCCL, migration and comm-array reduction over the peer-memory windows (CUDA IPC
+    between the two processes), PIC loop against the serial oracle by particle id, balancer scenario,
+    window overflow."""
+    _run(2, shared_gpu=True)                            # comm arrays, migrate, PIC loop, balancer
+    _run(2, shared_gpu=True, only="small_window")
+
+
+def test_two_ranks_hosted_bootstrap():
+    """pp_comm_create_hosted with NCCL: the id travels through the application's all-gather"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    _run(2, hosted=True, only="comm_array")
+    _run(2, hosted=True, only="migrate")
 
 
 def test_two_ranks_nccl():

@@ -189,6 +189,58 @@ def test_ppm_write_read_round_trip(tmp_path):
         pp.Picpart.read(str(tmp_path / "nothing"), 4, 0)
 
 
+def test_ppm_uncompressed_files_and_corrupt_input(tmp_path):
+    """A reference built without zlib writes raw arrays (src/pumipic_file.cpp:76-80) and the file
+    carries no flag: both forms are written on request and read whatever the setting; a file for
+    another rank count or with damaged arrays is an error, never an allocation by a bogus count."""
+    full, d = _full_mesh("24k")
+    exp = json.load(open(os.path.join(GOLD, "picpart_xgc24k_4.json")))
+    owner = np.asarray(exp["class_owner"], np.int32)[d["class_id_2"]]
+    built = [pp.Picpart.build(full, owner, 4, r, pp.BFS, pp.BFS) for r in range(2)]
+    lib = pp.capi.lib()
+    raw_prefix, z_prefix = str(tmp_path / "raw"), str(tmp_path / "z")
+    try:
+        lib.pp_host_ppm_set_compression(0)
+        for p in built:
+            p.write(raw_prefix)
+        lib.pp_host_ppm_set_compression(1)
+        for p in built:
+            p.write(z_prefix)
+        raw_file = os.path.join(raw_prefix + "_4.ppm", "raw_0.ppm")
+        z_file = os.path.join(z_prefix + "_4.ppm", "z_0.ppm")
+        assert os.path.getsize(raw_file) > os.path.getsize(z_file)
+        for setting in (1, 0):                       # either file under either setting
+            lib.pp_host_ppm_set_compression(setting)
+            for prefix in (raw_prefix, z_prefix):
+                for r, p in enumerate(built):
+                    q = pp.Picpart.read(prefix, 4, r)
+                    for k in range(3):
+                        a, b = p.dim_info(k), q.dim_info(k)
+                        for key in a:
+                            if key != "ent_l2g":
+                                assert np.array_equal(a[key], b[key]), key
+    finally:
+        lib.pp_host_ppm_set_compression(1)
+    # the files of a 4-rank run are not a 2-rank PICpart
+    os.rename(z_prefix + "_4.ppm", z_prefix + "_2.ppm")
+    with pytest.raises(pp.PumipicError, match="not written for 2 ranks"):
+        pp.Picpart.read(z_prefix, 2, 0)
+    os.rename(z_prefix + "_2.ppm", z_prefix + "_4.ppm")
+    # damaged arrays: a huge entry count in front of a short stream, and a truncated file
+    blob = bytearray(open(raw_file, "rb").read())
+    bad = bytearray(blob)
+    bad[14:18] = (0x7fffffff).to_bytes(4, "little")   # first array's count (after version, flag, i64, i32)
+    open(raw_file, "wb").write(bytes(bad))
+    with pytest.raises(pp.PumipicError, match="truncated or corrupt"):
+        pp.Picpart.read(raw_prefix, 4, 0)
+    open(raw_file, "wb").write(bytes(blob[: len(blob) // 2]))
+    with pytest.raises(pp.PumipicError, match="truncated or corrupt"):
+        pp.Picpart.read(raw_prefix, 4, 0)
+    open(raw_file, "wb").write(bytes([9]) + bytes(blob[1:]))
+    with pytest.raises(pp.PumipicError, match="unsupported version 9"):
+        pp.Picpart.read(raw_prefix, 4, 0)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/pumipic-data/xgc/120k_4.ppm"),
                     reason="reference data only exists in the authoring container")
 def test_reads_reference_ppm_files_directly():
