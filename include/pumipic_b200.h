@@ -379,6 +379,10 @@ void pp_ps_set_staged_rebuild(int32_t mode);
 /* Mode 2: hand destination chunks to the blocks in ascending order of their first row's element
  * (default) or in slot order (0, A/B: the gather then re-fetches every source sector from DRAM). */
 void pp_ps_set_rebuild_chunk_order(int32_t on);
+/* Layout of a mostly empty structure (one sort window, fewer than 40 % of the rows non-empty after the
+ * previous rebuild -- a PICpart that buffers the whole mesh): 1 (default) sorts only the non-empty rows and
+ * places the empty ones by a prefix sum, 0 sorts all rows.  Same layout either way; A/B switch. */
+void pp_ps_set_rebuild_split_rows(int32_t on);
 /* Mode 2 A/B knobs.  gather_blocks_per_sm: resident blocks per SM of the gather; <= 0 (default) sizes
  * the grid so that the source footprint of the chunks in flight fits L2.  gather_max_cols: average
  * columns per chunk up to which the records are gathered; wider structures go through the record
@@ -496,8 +500,9 @@ void pp_search_set_staged(int32_t on);
 /* L2 access-policy window of the chunk walk over the mesh's walk table: `fraction` (0..1) of the
  * device's persisting L2 carve-out is given to the table's lines (hit property "persisting"), the
  * rest of the kernel's accesses stream.  0 (default) = no window; also PUMIPIC_L2_WINDOW in the
- * environment.  Results do not change.  Measured without gain on the headline workload (the kernel's
- * DRAM traffic is at its floor already); kept as a tuning switch for meshes much smaller than L2. */
+ * environment.  Results do not change.  Measured on the headline workload: a loss (0.252 -> 0.464 ms per
+ * 10 M particles, profiles/r2F_l2_window_ab.txt) -- the records are served from L2 without it (DRAM traffic
+ * is at its floor) and the carve-out takes L2 away from the particle columns; off unless asked for. */
 void pp_search_set_l2_window(double fraction);
 /* Counters of the most recent search on this mesh handle (synchronises the stream). */
 pp_status pp_search_last_stats(pp_mesh* mesh, pp_search_stats* stats_host, pp_stream stream);

@@ -227,6 +227,7 @@ struct pp_ps {
   std::vector<int> rebuild_remap;   // one-shot member remap of the next rebuild (pp_ps_set_rebuild_remap)
   int first_chunk = 0;      // chunks before this one are empty (single sort window: empty rows lead)
   int ppe_bits_hint = 0;    // key bits of the row sort guessed from the last rebuild's largest row (0 = none)
+  int nnz_hint = 0;         // non-empty rows of the last rebuild (0 = none): a mostly empty structure only sorts those
   size_t stage_bytes;
   PsView view() const;
 };

@@ -1052,32 +1052,37 @@ pp_status pp_scs_build(pp_ps* ps, const int* ppe_dev, const int* pelems_dev,
 // bucket (~4 K elements) are in flight together anyway
 // empty chunks (width 0; on a PICpart that buffers the whole mesh most of them) sort behind all others:
 // the gather only takes the non-empty ones.  nb buckets of the element range (+ 1 for the empty chunks).
-__global__ void k_chunk_keys(const int* __restrict__ row2elem, const int* __restrict__ width, int nchunks,
+__global__ void k_chunk_keys(const int* __restrict__ row2elem, const int* __restrict__ width, int nchunks, int clo,
                              unsigned nb, unsigned* keys, int* vals) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = clo + k;
   if (c >= nchunks) return;
   const unsigned b = (unsigned)(((long long)row2elem[c * 32] * nb) / ((long long)nchunks * 32));
-  keys[c] = (width && width[c] == 0) ? nb : (b < nb - 1 ? b : nb - 1);
-  vals[c] = c;
+  keys[k] = (width && width[c] == 0) ? nb : (b < nb - 1 ? b : nb - 1);
+  vals[k] = c;
 }
 // chunks of a C = 32 layout in ascending order of (the bucket of) their first row's element
-pp_status chunk_order_build(const int* row_to_element, const int* width, int nchunks, cudaStream_t s, int** order) {
+// clo: chunks below it are known to be empty (a mostly empty structure: the caller's bound on the rows
+// that hold particles); only chunks [clo, nchunks) are ordered, the non-empty ones first
+pp_status chunk_order_build(const int* row_to_element, const int* width, int nchunks, cudaStream_t s, int** order,
+                            int clo = 0) {
   *order = nullptr;
   if (nchunks < 2) return PP_OK;
+  const int n = nchunks - clo;
   unsigned *ck_in, *ck_out;
   int* cv_in;
-  PP_TRY(pp_dev_alloc(&ck_in, nchunks, s)); PP_TRY(pp_dev_alloc(&ck_out, nchunks, s));
-  PP_TRY(pp_dev_alloc(&cv_in, nchunks, s)); PP_TRY(pp_dev_alloc(order, nchunks, s));
+  PP_TRY(pp_dev_alloc(&ck_in, n, s)); PP_TRY(pp_dev_alloc(&ck_out, n, s));
+  PP_TRY(pp_dev_alloc(&cv_in, n, s)); PP_TRY(pp_dev_alloc(order, n, s));
   // one radix pass (255 buckets) for structures of up to 64 K chunks, two passes (65535 buckets) above:
   // on a full-mesh PICpart the particles sit in a small part of the element range
   const int ebits = nchunks > 65536 ? 16 : 8;
-  k_chunk_keys<<<pp_div_up(nchunks, kBlock), kBlock, 0, s>>>(row_to_element, width, nchunks, (1u << ebits) - 1u,
-                                                             ck_in, cv_in);
+  k_chunk_keys<<<pp_div_up(n, kBlock), kBlock, 0, s>>>(row_to_element, width, nchunks, clo, (1u << ebits) - 1u,
+                                                       ck_in, cv_in);
   size_t tb = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, ck_in, ck_out, cv_in, *order, nchunks, 0, ebits, s);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, ck_in, ck_out, cv_in, *order, n, 0, ebits, s);
   char* tmp;
   PP_TRY(pp_dev_alloc(&tmp, tb, s));
-  PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, ck_in, ck_out, cv_in, *order, nchunks, 0, ebits, s));
+  PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, ck_in, ck_out, cv_in, *order, n, 0, ebits, s));
   pp_dev_free(tmp, s); pp_dev_free(ck_in, s); pp_dev_free(ck_out, s); pp_dev_free(cv_in, s);
   return PP_OK;
 }
@@ -1176,6 +1181,83 @@ __global__ void k_rows_widths(const int* __restrict__ sorted_elem, const int* __
       row2elem[i] = e; elem2row[e] = i; row_ppe[i] = np;
     } else {               // padding rows up to a multiple of C (SCS_buildFns.h:39-44)
       row2elem[i] = i; elem2row[i] = i; row_ppe[i] = 0;
+    }
+    const int w = __reduce_max_sync(0xffffffffu, np);
+    if (lane == 0) {
+      width[c] = w;
+      if (w > 0) { sum += w; cnt += 1; isum += 1.0 / w; }
+    }
+  }
+  if (lane == 0) { p_sum[wid] = sum; p_cnt[wid] = cnt; p_inv[wid] = isum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kBlock / 32; ++w) { sum += p_sum[w]; cnt += p_cnt[w]; isum += p_inv[w]; }
+    if (cnt) { atomicAdd(cw, sum); atomicAdd(cw + 1, cnt); atomicAdd(inv, isum); }
+  }
+}
+
+// ---- mostly empty structures (a PICpart that buffers the whole mesh holds particles in its own share of
+// the rows only): the stable ascending sort of ONE window puts the empty rows first, in element order,
+// and the others behind them by count.  The empty rows need no sort: row = number of empty elements in
+// front (from a prefix sum of the non-empty flags); only the non-empty ones, compacted, are sorted.
+struct NonZeroFlag {
+  __host__ __device__ int operator()(const int& v) const { return v > 0 ? 1 : 0; }
+};
+// pos[i] = non-empty elements in front of i.  Empty element: its row arrays are written here.
+// Non-empty element: (count, element) goes to entry pos[i] of the sort's input (if the bound m holds).
+__global__ void k_split_rows(const int* __restrict__ a, const int* __restrict__ pos, int n, int m, uint32_t* keys,
+                             int* vals, int* row2elem, int* elem2row, int* row_ppe, FastScal* out) {
+  __shared__ int p_nz[kBlock / 32], p_sum[kBlock / 32], p_max[kBlock / 32];
+  int nz = 0, sum = 0, mx = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int v = a[i];
+    const int p = pos[i];
+    nz += v > 0; sum += v; mx = max(mx, v);
+    if (v > 0) {
+      if (p < m) { keys[p] = (uint32_t)v; vals[p] = (int)i; }
+    } else {
+      const int row = (int)i - p;
+      row2elem[row] = (int)i; elem2row[i] = row; row_ppe[row] = 0;
+    }
+  }
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) { p_nz[threadIdx.x >> 5] = nz; p_sum[threadIdx.x >> 5] = sum; p_max[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kBlock / 32; ++w) { nz += p_nz[w]; sum += p_sum[w]; mx = max(mx, p_max[w]); }
+    if (nz) atomicAdd(&out->nnz, nz);
+    if (sum) atomicAdd(&out->active, sum);
+    if (mx) atomicMax(&out->maxcount, mx);
+  }
+}
+// k_rows_widths for the split layout: rows [0, z) are the empty ones (written by k_split_rows), row z + k is
+// entry (m - nnz) + k of the sorted non-empty elements (the first m - nnz entries are key-0 fillers)
+__global__ void k_rows_widths_split(const int* __restrict__ sorted_nz, const int* __restrict__ ppe, int ne, int nchunks,
+                                    int m, const FastScal* __restrict__ sc, int* row2elem, int* elem2row, int* row_ppe,
+                                    int* width, int* cw, double* inv) {
+  __shared__ int p_sum[kBlock / 32], p_cnt[kBlock / 32];
+  __shared__ double p_inv[kBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nnz = sc->nnz;
+  const bool good = nnz <= m;                  // else the host drops this layout (speculation failed)
+  const int z = ne - nnz;
+  int sum = 0, cnt = 0;
+  double isum = 0.0;
+  for (long c = blockIdx.x * (long)(kBlock / 32) + wid; c < nchunks; c += (long)gridDim.x * (kBlock / 32)) {
+    const int i = (int)c * 32 + lane;
+    int np = 0;
+    if (!good || (int)c * 32 + 31 < z) {       // a chunk of empty rows: nothing to read
+      if (lane == 0) width[c] = 0;
+      continue;
+    }
+    if (i >= ne) {                             // padding rows up to a multiple of C (SCS_buildFns.h:39-44)
+      row2elem[i] = i; elem2row[i] = i; row_ppe[i] = 0;
+    } else if (i >= z) {
+      const int e = sorted_nz[(i - z) + (m - nnz)];
+      np = ppe[e];
+      row2elem[i] = e; elem2row[e] = i; row_ppe[i] = np;
     }
     const int w = __reduce_max_sync(0xffffffffu, np);
     if (lane == 0) {
@@ -1302,6 +1384,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_gather_scs(
 }
 
 int g_rebuild_chunk_order = 1;   // 0: chunks in slot order (A/B)
+int g_rebuild_split_rows = 1;    // 0: always sort all rows (A/B)
 int g_gather_bps = 0;            // resident blocks per SM of the gather; 0 = from the chunks' footprint
 double g_gather_l2_bytes = 48e6; // footprint the chunks in flight may have
 double g_gather_max_cols = 14.0; // average columns per chunk up to which the gather beats the record stage
@@ -1346,7 +1429,43 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   ScsLayout L;
   L.C = C; L.nchunks = nchunks; L.nrows = nrows;
   int* sorted_elem = nullptr;
-  if (cfg.sigma > 1) {
+  PP_TRY(pp_dev_alloc(&L.row_to_element, nrows, s));
+  PP_TRY(pp_dev_alloc(&L.element_to_row, nrows, s));
+  PP_TRY(pp_dev_alloc(&L.row_ppe, nrows, s));
+  int* width;
+  int2 *sizes, *pref;
+  PP_TRY(pp_dev_alloc(&width, nchunks, s));
+  PP_TRY(pp_dev_alloc(&sizes, nchunks + 1, s));
+  PP_TRY(pp_dev_alloc(&pref, nchunks + 1, s));
+  // A mostly empty structure (one sort window; the previous rebuild left fewer than 40 % of the rows
+  // non-empty): only the non-empty rows are sorted, see k_split_rows.  m bounds their number -- a
+  // speculation like the key width, checked in the one host read.
+  const long m_want = (long)ps->nnz_hint + ps->nnz_hint / 4 + 4096;
+  const bool split = g_rebuild_split_rows && cfg.sigma >= ne && ps->nnz_hint > 0 && m_want * 2 < ne && cbits <= 31;
+  const int m_split = split ? (int)m_want : 0;
+  if (split) {
+    int *pos, *v_in, *sorted_nz;
+    uint32_t *k_in, *k_out;
+    PP_TRY(pp_dev_alloc(&pos, ne, s));
+    PP_TRY(pp_dev_alloc(&k_in, m_split, s)); PP_TRY(pp_dev_alloc(&k_out, m_split, s));
+    PP_TRY(pp_dev_alloc(&v_in, m_split, s)); PP_TRY(pp_dev_alloc(&sorted_nz, m_split, s));
+    PP_CUDA(cudaMemsetAsync(k_in, 0, sizeof(uint32_t) * m_split, s));     // fillers: key 0 sorts first
+    cub::TransformInputIterator<int, NonZeroFlag, const int*> flags(count, NonZeroFlag());
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, pos, ne, s);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, k_in, k_out, v_in, sorted_nz, m_split, 0, cbits, s);
+    char* tmp;
+    PP_TRY(pp_dev_alloc(&tmp, tb > tb2 ? tb : tb2, s));
+    PP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, flags, pos, ne, s));
+    k_split_rows<<<std::min(pp_div_up(ne, kBlock), 2368), kBlock, 0, s>>>(count, pos, ne, m_split, k_in, v_in,
+                                                                          L.row_to_element, L.element_to_row, L.row_ppe, sc);
+    PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, k_in, k_out, v_in, sorted_nz, m_split, 0, cbits, s));
+    k_rows_widths_split<<<std::min(pp_div_up((long)nchunks * 32, kBlock), 2368), kBlock, 0, s>>>(
+        sorted_nz, count, ne, nchunks, m_split, sc, L.row_to_element, L.element_to_row, L.row_ppe, width, &sc->cw_sum,
+        &sc->inv);
+    pp_dev_free(tmp, s); pp_dev_free(pos, s); pp_dev_free(k_in, s); pp_dev_free(k_out, s);
+    pp_dev_free(v_in, s); pp_dev_free(sorted_nz, s);
+  } else if (cfg.sigma > 1) {
     const int sigma = cfg.sigma < ne ? cfg.sigma : ne;
     const int nwin = (ne + sigma - 1) / sigma;
     int wbits = 0;
@@ -1374,16 +1493,9 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     }
     pp_dev_free(tmp, s); pp_dev_free(v_in, s);
   }
-  PP_TRY(pp_dev_alloc(&L.row_to_element, nrows, s));
-  PP_TRY(pp_dev_alloc(&L.element_to_row, nrows, s));
-  PP_TRY(pp_dev_alloc(&L.row_ppe, nrows, s));
-  int* width;
-  int2 *sizes, *pref;
-  PP_TRY(pp_dev_alloc(&width, nchunks, s));
-  PP_TRY(pp_dev_alloc(&sizes, nchunks + 1, s));
-  PP_TRY(pp_dev_alloc(&pref, nchunks + 1, s));
-  k_rows_widths<<<std::min(pp_div_up((long)nchunks * 32, kBlock), 2368), kBlock, 0, s>>>(
-      sorted_elem, count, ne, nchunks, L.row_to_element, L.element_to_row, L.row_ppe, width, &sc->cw_sum, &sc->inv);
+  if (!split)
+    k_rows_widths<<<std::min(pp_div_up((long)nchunks * 32, kBlock), 2368), kBlock, 0, s>>>(
+        sorted_elem, count, ne, nchunks, L.row_to_element, L.element_to_row, L.row_ppe, width, &sc->cw_sum, &sc->inv);
   pp_dev_free(sorted_elem, s);
   k_chunk_sizes<<<pp_div_up(nchunks + 1, kBlock), kBlock, 0, s>>>(width, nchunks, sc, cfg.shuffle_padding,
                                                                  cfg.padding_strat, V, C, sizes);
@@ -1405,7 +1517,9 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
                                                                  L.offsets, L.chunk_start, sc);
   // chunks in ascending order of their first row's element: the order the gather takes them in
   int* order = nullptr;
-  if (g_rebuild_chunk_order) PP_TRY(chunk_order_build(L.row_to_element, width, nchunks, s, &order));
+  // split layout: rows in front of ne - m are empty for certain, their chunks need no ordering
+  const int order_lo = split ? (ne - m_split) / 32 : 0;
+  if (g_rebuild_chunk_order) PP_TRY(chunk_order_build(L.row_to_element, width, nchunks, s, &order, order_lo));
   pp_dev_free(width, s); pp_dev_free(sizes, s); pp_dev_free(pref, s);
   delete t_build;                                // SCS_rebuild.h:196-265
   // ---- the one host read
@@ -1431,7 +1545,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   int mbits = 1;
   while (mbits < 31 && (1ll << mbits) <= (long long)h.maxcount) ++mbits;
   ps->ppe_bits_hint = mbits + 1;                 // head room: a row may double before the guess fails
-  if (h.nnz < C || mbits > cbits || h.active == 0 || h.nslices > nslices_bound) {
+  ps->nnz_hint = h.nnz;
+  if (h.nnz < C || mbits > cbits || h.active == 0 || h.nslices > nslices_bound || (split && h.nnz > m_split)) {
     drop();                                      // chunk height / key width guessed wrong, or nothing left
     return PP_OK;
   }
@@ -1953,6 +2068,7 @@ extern "C" void pp_ps_set_rebuild_tuning(int32_t gather_blocks_per_sm, int32_t g
   if (gather_max_cols >= 0) g_gather_max_cols = gather_max_cols;
 }
 extern "C" void pp_ps_set_rebuild_chunk_order(int32_t on) { g_rebuild_chunk_order = on ? 1 : 0; }
+extern "C" void pp_ps_set_rebuild_split_rows(int32_t on) { g_rebuild_split_rows = on ? 1 : 0; }
 
 extern "C" void pp_ps_set_rank_sort_threshold(int32_t particles_per_element) {
   g_rank_sort_ppe = particles_per_element > 0 ? particles_per_element : 1;

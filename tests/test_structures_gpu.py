@@ -153,6 +153,7 @@ def _default_rebuild_modes():
     pp().lib().pp_ps_set_rebuild_tuning(0, 14)
     pp().lib().pp_ps_set_rank_sort_threshold(128)
     pp().lib().pp_ps_set_shuffling(1)
+    pp().lib().pp_ps_set_rebuild_split_rows(1)
 
 
 # move = how records travel in a re-layout: device-side layout + single-pass gather (default for
@@ -417,3 +418,85 @@ def test_rebuild_remap_folds_update_positions(kindname, move, _default_rebuild_m
         ps.set_rebuild_remap([2, -1, 2, 3])          # member 2 has another type
     with pytest.raises(P.PumipicError):
         ps.set_rebuild_remap([1, 1, 2, 3])           # a member may feed one destination only
+
+
+def _layout_arrays(ps):
+    """row_to_element, offsets, slice_to_chunk of a Sell-C-sigma structure as numpy arrays"""
+    t = torch()
+    from importlib import import_module
+    api = import_module("pumi-pic_b200").api
+    lay = ps.layout()
+    off = api._tensor_from_ptr(lay.offsets, (lay.nslices + 1,), t.int32, ps).cpu().numpy().copy()
+    s2c = api._tensor_from_ptr(lay.slice_to_chunk, (lay.nslices,), t.int32, ps).cpu().numpy().copy()
+    r2e = api._tensor_from_ptr(lay.row_to_element, (lay.nrows,), t.int32, ps).cpu().numpy().copy()
+    return r2e, off, s2c
+
+
+@pytest.mark.parametrize("ne,frac", [(40000, 0.1), (60000, 0.3), (300000, 0.01)])
+def test_rebuild_of_a_mostly_empty_structure_sorts_only_the_occupied_rows(ne, frac, _default_rebuild_modes):
+    """A PICpart that buffers the whole mesh holds particles in its own share of the rows only.  After a
+    rebuild has seen that, the layout code sorts the non-empty rows alone and places the empty ones by a
+    prefix sum (k_split_rows).  The layout must be the one the full stable sort gives -- row for row --
+    and the particles must arrive (ids, payload, elements), also when the occupied set drifts, shrinks,
+    and when it grows past the bound the previous rebuild suggested (fallback)."""
+    t = torch()
+    P = pp()
+    lib = P.lib()
+    lib.pp_ps_set_shuffling(0)
+    rng = np.random.default_rng(ne)
+    occupied = np.sort(rng.choice(ne, max(40, int(ne * frac)), replace=False))
+    ppe = np.zeros(ne, np.int32)
+    ppe[occupied] = rng.integers(1, 9, occupied.shape[0])
+
+    def u01(e, rank, step, salt):
+        """deterministic per (element, rank in its row, step): the order of a row's particles differs from run to run"""
+        h = (e.astype(np.uint64) * np.uint64(2654435761) + rank.astype(np.uint64) * np.uint64(40503)
+             + np.uint64(step * 97 + salt * 1000003)) * np.uint64(0x9E3779B97F4A7C15)
+        return ((h >> np.uint64(40)) & np.uint64(0xFFFFFF)).astype(np.float64) / float(1 << 24)
+
+    def run(split):
+        lib.pp_ps_set_rebuild_split_rows(1 if split else 0)
+        ps = P.ParticleStructure(P.capi.PP_PS_SCS, TYPES, ppe, team_size=32, sigma=0x7fffffff, V=1024)
+        out = []
+        occ = occupied
+        for step in range(6):
+            _set_ids(ps)
+            slot_elem, m = _state(ps)
+            cap = ps.capacity
+            slots = np.arange(cap)
+            # rank of a particle inside its element (by slot): decisions depend on (element, rank) only
+            idx = slots[m][np.lexsort((slots[m], slot_elem[m]))]
+            es = slot_elem[idx]
+            first = np.r_[0, np.flatnonzero(np.diff(es)) + 1]
+            rank = np.zeros(cap, np.int64)
+            rank[idx] = np.arange(idx.shape[0]) - np.repeat(first, np.diff(np.r_[first, idx.shape[0]]))
+            e64 = slot_elem.astype(np.int64)
+            # most particles stay, some hop to another occupied element, a few leave; step 3 moves half of
+            # them into arbitrary elements (more non-empty rows than the previous rebuild's bound allows:
+            # the speculation fails and the rebuild falls back), step 4 removes most of them again
+            dest = slot_elem.copy()
+            hop = m & (u01(e64, rank, step, 1) < 0.3)
+            dest[hop] = occ[(u01(e64, rank, step, 2)[hop] * occ.shape[0]).astype(np.int64) % occ.shape[0]]
+            if step == 3:
+                grow = m & (u01(e64, rank, step, 3) < 0.5)
+                dest[grow] = (u01(e64, rank, step, 4)[grow] * ne).astype(np.int64) % ne
+            gone = m & (u01(e64, rank, step, 5) < (0.6 if step == 4 else 0.03))
+            new_element = np.where(m & ~gone, dest, -1).astype(np.int32)
+            nnp = 50
+            new_elems = occ[(np.arange(nnp) * 7919 + step) % occ.shape[0]].astype(np.int32)
+            info = [dev((np.arange(nnp) + cap).astype(np.int32).reshape(1, -1)),
+                    t.zeros((3, nnp), dtype=t.float64, device="cuda"),
+                    t.zeros((1, nnp), dtype=t.int32, device="cuda")]
+            ps.rebuild(dev(new_element), dev(new_elems), info)
+            _check(ps, new_element, cap, removed=gone, new_elems=new_elems,
+                   np_expected=int((m & ~gone).sum()) + nnp)
+            se, mk = _state(ps)
+            occ = np.unique(se[mk])
+            out.append(_layout_arrays(ps) + (np.bincount(se[mk], minlength=ne),))
+        return out
+
+    a, b = run(True), run(False)
+    for step, (x, y) in enumerate(zip(a, b)):
+        for k, name in enumerate(("row_to_element", "offsets", "slice_to_chunk", "particles per element")):
+            assert np.array_equal(x[k], y[k]), (step, name)
+    lib.pp_ps_set_rebuild_split_rows(1)
