@@ -726,12 +726,15 @@ __host__ __device__ inline size_t p2p_seg_offset(int parity, int sender, int R, 
 // destination (thousands of lanes adding to the same few cursors would serialise in L2), then
 // stores the records over NVLink.
 constexpr int kPackThreads = 256, kPackPerThread = 8, kPackSlots = kPackThreads * kPackPerThread;
+constexpr int kPackCoopMin = 32;    // leavers per block (of 2048 slots) from which the warp-cooperative stores pay
 __global__ void __launch_bounds__(kPackThreads) k_p2p_pack(
     PsView v, const int* __restrict__ new_proc, int* new_elem, const long long* __restrict__ elem_gids, int self,
     int nranks, int* cursor, int* overflow, P2PPeers peers, int parity, size_t seg_bytes, int seg_cap,
     int rec_bytes, PackTable t, long stride, int debug) {
   __shared__ int s_cnt[kMaxRanks], s_base[kMaxRanks];
+  __shared__ int s_total;
   if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_total = 0;
   __syncthreads();
   // slots of thread t: 4 consecutive ones per 16-byte load of new_proc, kPackPerThread / 4 loads
   const long sb0 = (long)blockIdx.x * kPackSlots + 4 * threadIdx.x;
@@ -768,17 +771,21 @@ __global__ void __launch_bounds__(kPackThreads) k_p2p_pack(
   if (threadIdx.x < nranks) {
     const int c = s_cnt[threadIdx.x];
     s_base[threadIdx.x] = c ? atomicAdd(cursor + threadIdx.x, c) : 0;
+    if (c) atomicAdd(&s_total, c);
   }
   __syncthreads();
-  // Records leave the GPU as whole records: the WARP stores one leaving particle at a time, lane i
-  // carrying scalar i of the record (gid, then the members' components), so the record's bytes
-  // cross NVLink as one contiguous run instead of one 8-byte store per scalar from a single lane
-  // (measured before: 16 ms for 5.5 M records of 168 bytes, 7 G remote stores/s).
+  if (s_total == 0) return;
+  // Bulk migrations (a block with many leavers): records leave the GPU as whole records -- the WARP
+  // stores one leaving particle at a time, lane i carrying scalar i of the record (gid, then the
+  // members' components), so the record's bytes cross NVLink as one contiguous run instead of one
+  // 8-byte store per scalar from a single lane (ps_combo160's migrate series, 5.5 M records of 168
+  // bytes per step: 32.8 -> 17.4 ms).  A PIC step's handful of leavers per block (0.3 % of the slots)
+  // is cheaper the plain way below: the warp-wide loop costs every thread its ballots.
   const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   int nsc = 1;
   for (int m = 0; m < t.n; ++m) nsc += t.ncomp[m];
-  if (nsc <= 2 * 32 && debug != 3) {
+  if (nsc <= 2 * 32 && s_total >= kPackCoopMin && debug != 3) {
     // scalar `i` of a record: source column base, byte offset in the record, scalar size (0 = none, -1 = gid)
     auto describe = [&](int i, const char*& base, int& off, int& sb) {
       base = nullptr; off = 0; sb = 0;
@@ -837,7 +844,7 @@ __global__ void __launch_bounds__(kPackThreads) k_p2p_pack(
     }
     return;
   }
-  // more than 64 scalars per record: one lane stores its own record
+  // few leavers in this block, or more than 64 scalars per record: one lane stores its own record
 #pragma unroll
   for (int k = 0; k < kPackPerThread; ++k) {
     if (dest[k] < 0) continue;
