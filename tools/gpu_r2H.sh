@@ -15,4 +15,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-fil
 python tools/launch_list.py gpurun_out/${tag}_launches_bench.csv 8 > gpurun_out/${tag}_launches_bench.txt 2>/dev/null; cat gpurun_out/${tag}_launches_bench.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${tag}_launches_picstep.csv python tools/bench_picstep.py --steps 3 --warmup 1 > /dev/null 2>&1
 python tools/launch_list.py gpurun_out/${tag}_launches_picstep.csv > gpurun_out/${tag}_launches_picstep.txt 2>/dev/null; head -40 gpurun_out/${tag}_launches_picstep.txt
+timeout 300 python tools/bench_phases.py --configs c2 --steps 12 2>/dev/null | tee gpurun_out/${tag}_phases_c2.jsonl | python -c "
+import sys,json
+for l in sys.stdin:
+    r=json.loads(l); print(r['config'],{k:round(v['median_ms'],4) for k,v in r['phases'].items()})"
 ls -la gpurun_out/${tag}_*.ncu-rep
