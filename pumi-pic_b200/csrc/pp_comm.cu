@@ -141,7 +141,6 @@ namespace {
 pp_status boot_allgather(pp_comm* c, const void* h_send, void* h_recv, size_t bytes, cudaStream_t s) {
   if (c->nranks == 1) { memcpy(h_recv, h_send, bytes); return PP_OK; }
   if (c->host_ag) {
-    PP_CUDA(cudaStreamSynchronize(s));
     if (c->host_ag(c->host_ctx, h_send, h_recv, (int64_t)bytes) != 0) {
       pp_set_error("the application's all-gather callback failed");
       return PP_ERR_NCCL;
@@ -487,6 +486,7 @@ pp_status red_setup(pp_comm* c, size_t want_bytes, cudaStream_t s) {
   if (ok && cudaMalloc((void**)&w.local, kRedHdr + 2 * w.cap_bytes) != cudaSuccess) { ok = 0; w.local = nullptr; cudaGetLastError(); }
   if (ok) {
     PP_CUDA(cudaMemset(w.local, 0, kRedHdr));
+    PP_CUDA(cudaDeviceSynchronize());   // the header is zero before any peer can learn the handle
     if (cudaIpcGetMemHandle(&mine, w.local) != cudaSuccess) { ok = 0; cudaGetLastError(); }
   }
   struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
@@ -1004,6 +1004,7 @@ pp_status p2p_setup(pp_comm* c, size_t want_seg_bytes, cudaStream_t s) {
   }
   if (ok) {
     PP_CUDA(cudaMemset(w.local, 0, sizeof(P2PHeader)));
+    PP_CUDA(cudaDeviceSynchronize());   // the header is zero before any peer can learn the handle
     if (cudaIpcGetMemHandle(&mine, w.local) != cudaSuccess) { ok = 0; cudaGetLastError(); }
   }
   // handles (and whether this rank got that far) to everybody
