@@ -31,6 +31,13 @@ def test_two_ranks_on_one_gpu():
     bootstrap without NCCL, migration and comm-array reduction over the peer-memory windows (CUDA IPC
     between the two processes), PIC loop against the serial oracle by particle id, balancer scenario,
     window overflow."""
+    try:
+        mode = subprocess.run(["nvidia-smi", "--query-gpu=compute_mode", "--format=csv,noheader", "-i", "0"],
+                              capture_output=True, text=True, timeout=60).stdout.strip()
+    except Exception:
+        mode = ""
+    if mode and mode != "Default":
+        pytest.skip("GPU 0 is in compute mode %r: two processes cannot share it" % mode)
     _run(2, shared_gpu=True)                            # comm arrays, migrate, PIC loop, balancer
     _run(2, shared_gpu=True, only="small_window")
 
