@@ -21,7 +21,9 @@ scaling is weak.  Prints ONE JSON line on rank 0.
 The same line carries `picstep`: the FULL PIC step of BASELINE configs[4] (push, search,
 updatePtclPositions, setUnsafeProcs, migrate over the library's own NCCL communicator, comm-array
 all-reduce; pumi-pic_b200/picstep.py) on the same N GPUs, with per-phase times, the particles
-migrated per step and an in-run parity check of the multi-rank loop against the serial oracle; and
+migrated per step, an in-run parity check of the multi-rank loop against the serial oracle (small
+case) and `full_size_check` (two untimed steps at full size: the multiset of particle records before
+the migration equals the multiset in the rebuilt structures after it, count + checksum); and
 `parity`: the element ids of one step of the headline workload at full size compared with the
 reference's own search_mesh source on the same inputs.
 """

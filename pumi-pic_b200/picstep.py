@@ -138,6 +138,80 @@ class PicStep:
                 self.reduce_done.record(self.comm_stream)
         return sent, recv
 
+    # ---- full-size check of one step's record move (rebuild + migration), untimed
+    _HK = (-7046029254386353131, -4417276706812531889, 1609587929392839161, -8796714831421723037,
+           2685821657736338717, -3335678366873096957, 7046029254386353087, 6364136223846793005)
+
+    def _record_hash(self, cols):
+        """order-independent checksum of a set of records: every record (a tuple of int64 columns) is
+        mixed into one 64-bit word (wrap-around arithmetic), the words are summed in two 31-bit halves
+        so that neither a rank's sum nor the sum over ranks can overflow"""
+        torch = self.torch
+        acc = torch.zeros_like(cols[0])
+        for k, c in enumerate(cols):
+            c = c ^ (c >> 29)
+            acc = (acc ^ (acc >> 31)) * 1099511628211 + c * self._HK[k % len(self._HK)]
+        acc = acc ^ (acc >> 32)
+        return torch.stack([(acc & 0x7fffffff).sum(), ((acc >> 31) & 0x7fffffff).sum()])
+
+    def _mask_and_elements(self):
+        torch, P, ps = self.torch, self.P, self.ps
+        cap = ps.capacity
+        lay = ps.layout()
+        se = P.api._tensor_from_ptr(lay.slot_elem, (cap,), torch.int32, ps)
+        mb = P.api._tensor_from_ptr(lay.mask_bits, ((cap + 31) // 32,), torch.int32, ps)
+        sh = torch.arange(32, device="cuda", dtype=torch.int32)
+        m = (((mb[:, None] >> sh[None, :]) & 1) != 0).reshape(-1)[:cap]
+        return m, se
+
+    def check_step(self, reduce_sum=None):
+        """One more (untimed) step at FULL size with a complete check of what the rebuild and the migration
+        did with the records: before the migration every surviving particle is the record (id, element the
+        search found, target position, direction) -- bit patterns; after it every particle of the structure is
+        (id, element of its row, position, direction).  The two multisets must be equal over all ranks
+        (particles change rank, full-mesh PICparts number the elements alike everywhere): compared as the
+        count and a 62-bit order-independent checksum.  Also: every target column is zero afterwards
+        (updatePtclPositions).  reduce_sum: all-reduce (SUM) of an int64 cuda tensor over the ranks."""
+        torch, P, ps, gm = self.torch, self.P, self.ps, self.gm
+        x, tg, dr = ps.get(0), ps.get(1), ps.get(3)
+        cap = ps.capacity
+        ids = torch.empty(max(cap, 1), dtype=torch.int32, device="cuda")
+        P.push_direction_search(gm, ps, dr, self.push, x, tg, ids, elem_ids_empty=True, from_orig=True, sync=False)
+        if self.fuse_update:
+            ps.set_rebuild_remap([1, -1, 2, 3])
+            newx = tg
+        else:
+            P.update_positions(ps, x, tg)
+            newx = x
+        ne_d, np_d = P.set_unsafe_procs(gm, ps, ids)
+        m, _se = self._mask_and_elements()
+        alive = m & (ne_d[:cap] >= 0)
+        i64 = torch.int64
+
+        def cols(pid, elem, pos, dirs, sel):
+            c = [pid[sel].to(i64), elem[sel].to(i64)]
+            c += [pos[k, :sel.shape[0]].contiguous().view(i64)[sel] for k in range(3)]
+            c += [dirs[k, :sel.shape[0]].contiguous().view(i64)[sel] for k in range(3)]
+            return c
+
+        before = torch.cat([alive.sum().to(i64).reshape(1),
+                            self._record_hash(cols(ps.get(2)[0, :cap], ne_d[:cap], newx, dr, alive))])
+        P.migrate(ps, self.comm, ne_d, np_d)
+        self.comm.array_reduce(self.charge, self.nverts, 2, P.capi.PP_SUM)
+        cap2 = ps.capacity
+        m2, se2 = self._mask_and_elements()
+        x2, tg2, dr2 = ps.get(0), ps.get(1), ps.get(3)
+        after = torch.cat([m2.sum().to(i64).reshape(1),
+                           self._record_hash(cols(ps.get(2)[0, :cap2], se2, x2, dr2, m2))])
+        tg_nonzero = sum(int((tg2[k, :cap2][m2] != 0).sum().item()) for k in range(3))
+        local = torch.cat([before, after, torch.tensor([tg_nonzero, int(ps.nptcls)], dtype=i64, device="cuda")])
+        if reduce_sum is not None:
+            local = reduce_sum(local)
+        v = [int(q) for q in local.cpu().tolist()]
+        return {"particles_before": v[0], "particles_after": v[3], "count_mismatch": int(v[0] != v[3]),
+                "record_checksum_mismatch": int(v[1:3] != v[4:6]), "targets_not_zeroed": v[6],
+                "structure_count_mismatch": int(v[3] != v[7])}
+
     def finish(self):
         """the main stream waits for the last field synchronisation"""
         if self.reduce_done is not None:
@@ -170,7 +244,7 @@ class PicStep:
 
 
 def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_mult=3.0, timing=False,
-                overlap_reduce=False, fuse_update=True):
+                overlap_reduce=False, fuse_update=True, full_size_check=2):
     """Collective over the ranks of torch.distributed (when R > 1).  Returns the record on rank 0.
     timing: also record the library's own phase timers (pp_timing_*, rank 0's table in the record)."""
     import torch
@@ -193,9 +267,17 @@ def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_m
                      device="cuda")
     cnt = torch.tensor([float(r["particles_start"]), float(r["sent"]), float(r["particles_end"])],
                        dtype=torch.float64, device="cuda")
+    def allreduce(v, op):
+        """torch.distributed plumbing; host tensors when the process group is gloo (ranks sharing one GPU)"""
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(v, op=op)
+            return v
+        h = v.cpu()
+        dist.all_reduce(h, op=op)
+        return h.cuda()
     if R > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        t = allreduce(t, dist.ReduceOp.MAX)
+        cnt = allreduce(cnt, dist.ReduceOp.SUM)
     tot_ms = float(t[0].item())
     # algorithmic bytes of the full step per particle (SURVEY 8d): push 49 + search 53 + mesh 7 +
     # position update 72 + setUnsafeProcs 4 + rebuild 110
@@ -223,6 +305,18 @@ def run_picstep(P, comm, rank, R, steps, warmup, cube_per_gpu=55, ppe=10, push_m
                         else ("NCCL AllGather + grouped Send/Recv" if R > 1 else "single rank")}
     if table is not None:
         out["library_phase_avg_ms_rank0"] = table
+    if full_size_check:
+        chk = [ps.check_step((lambda v: allreduce(v, dist.ReduceOp.SUM)) if R > 1 else None)
+               for _ in range(full_size_check)]
+        out["full_size_check"] = {
+            "steps": len(chk), "particles_per_step": [c["particles_after"] for c in chk],
+            "count_mismatch": sum(c["count_mismatch"] + c["structure_count_mismatch"] for c in chk),
+            "record_checksum_mismatch": sum(c["record_checksum_mismatch"] for c in chk),
+            "targets_not_zeroed": sum(c["targets_not_zeroed"] for c in chk),
+            "what": "untimed extra steps at full size: the multiset of records (id, element, position, direction: bit "
+                    "patterns) of the surviving particles before the migration equals the multiset in the rebuilt "
+                    "structures after it, over all ranks (count + 62-bit order-independent checksum); element = the "
+                    "row's element after, the search's result before; targets are zero afterwards"}
     del ps
     torch.cuda.empty_cache()
     return out

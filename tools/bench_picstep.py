@@ -30,17 +30,28 @@ def main():
     ap.add_argument("--overlap-reduce", action="store_true",
                     help="comm-array reduction on its own stream, overlapped with the next step (A/B)")
     ap.add_argument("--timing", action="store_true", help="record the library's phase timers (pp_timing_*)")
+    ap.add_argument("--check-steps", type=int, default=2,
+                    help="untimed extra steps with the full-size record-multiset check (picstep.check_step)")
+    ap.add_argument("--shared-gpu", action="store_true",
+                    help="all ranks on cuda:0 (a single-GPU box): hosted communicator without NCCL, gloo for the "
+                         "plumbing; the times mean nothing then (the ranks time-slice one GPU), the checks do")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     R = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.shared_gpu:
+        local = 0
     torch.cuda.set_device(local)
     if R > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if a.shared_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P = importlib.import_module("pumi-pic_b200")
     mod = importlib.import_module("pumi-pic_b200.picstep")
-    comm = P.Comm()
+    comm = P.Comm(hosted=True, nccl=False) if (a.shared_gpu and R > 1) else P.Comm()
     r = mod.run_picstep(P, comm, rank, R, a.steps, a.warmup, a.cube_per_gpu, a.ppe, a.push_mult, timing=a.timing,
-                        overlap_reduce=a.overlap_reduce, fuse_update=not a.separate_update)
+                        overlap_reduce=a.overlap_reduce, fuse_update=not a.separate_update,
+                        full_size_check=a.check_steps)
     if rank == 0:
         print(json.dumps(r))
     if R > 1:
