@@ -152,35 +152,73 @@ __device__ __forceinline__ int lb_target(const int* __restrict__ plan_off,
 
 // selectNonCoreParticles / selectParticles (pumipic_lb.hpp:246-288): non_core_only restricts the
 // pass to particles whose new element belongs to another part.
-__global__ void k_lb_select_ps(int cap, const uint32_t* __restrict__ mask,
-                               const int* __restrict__ new_elems, int* __restrict__ new_procs,
-                               const int* __restrict__ elem_vert, const int* __restrict__ elem_owner,
-                               int me, int non_core_only, const int* __restrict__ plan_off,
-                               const int* __restrict__ plan_tgt, const int* __restrict__ plan_cum,
-                               const int* __restrict__ plan_total, int* __restrict__ taken) {
-  const long slot = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  int v = -1;
-  if (slot < cap && mask_bit(mask, (int)slot) && new_procs[slot] == me) {
-    const int e = new_elems[slot];
-    if (e != -1 && !(non_core_only && __ldg(elem_owner + e) == me)) {
-      v = __ldg(elem_vert + e);
-      if (v >= 0) {
-        const int total = __ldg(plan_total + v);
-        // the counter only grows: a filled quota stays filled
-        if (total <= 0 || *(volatile int*)(taken + v) >= total) v = -1;
+// A block owns kSelSlots consecutive slots.  Its candidates are counted per sbar vertex in a small
+// shared-memory hash table (the atomic's return value is the candidate's rank inside the block), the
+// block reserves its share of each vertex's quota with ONE global atomic per vertex, then every
+// candidate whose rank lies inside the quota takes the target the plan names for that rank.  (One
+// atomic per warp and vertex on the few dozen quota counters serialised in L2: 3.6 ms for 8.75 M
+// re-targeted particles over 64 vertices.)
+constexpr int kSelPer = 16, kSelSlots = kBlock * kSelPer, kSelTable = 128;
+__global__ void __launch_bounds__(kBlock) k_lb_select_ps(
+    int cap, const uint32_t* __restrict__ mask, const int* __restrict__ new_elems, int* __restrict__ new_procs,
+    const int* __restrict__ elem_vert, const int* __restrict__ elem_owner, int me, int non_core_only,
+    const int* __restrict__ plan_off, const int* __restrict__ plan_tgt, const int* __restrict__ plan_cum,
+    const int* __restrict__ plan_total, int* __restrict__ taken) {
+  __shared__ int s_key[kSelTable], s_cnt[kSelTable], s_base[kSelTable], s_tot[kSelTable];
+  for (int i = threadIdx.x; i < kSelTable; i += kBlock) { s_key[i] = -1; s_cnt[i] = 0; }
+  __syncthreads();
+  int vv[kSelPer], ent[kSelPer], pos[kSelPer];
+  const long s0 = (long)blockIdx.x * kSelSlots + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < kSelPer; ++j) {
+    const long slot = s0 + (long)j * kBlock;
+    int v = -1;
+    if (slot < cap && mask_bit(mask, (int)slot) && new_procs[slot] == me) {
+      const int e = new_elems[slot];
+      if (e != -1 && !(non_core_only && __ldg(elem_owner + e) == me)) {
+        v = __ldg(elem_vert + e);
+        if (v >= 0) {
+          const int total = __ldg(plan_total + v);
+          // the counter only grows: a filled quota stays filled
+          if (total <= 0 || *(volatile int*)(taken + v) >= total) v = -1;
+        }
       }
     }
+    vv[j] = v; ent[j] = -1; pos[j] = 0;
+    if (v >= 0) {
+      unsigned h = ((unsigned)v * 2654435761u) >> 25;          // 7 bits
+      for (int probe = 0; probe < kSelTable; ++probe) {
+        const int k = atomicCAS(&s_key[h], -1, v);
+        if (k == -1 || k == v) { ent[j] = (int)h; break; }
+        h = (h + 1) & (kSelTable - 1);
+      }
+      if (ent[j] >= 0) pos[j] = atomicAdd(&s_cnt[ent[j]], 1);
+    }
   }
-  const unsigned active = __ballot_sync(0xffffffffu, v >= 0);
-  if (v < 0) return;
-  const unsigned peers = __match_any_sync(active, v);
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(peers) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(taken + v, __popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  const int r = base + __popc(peers & ((1u << lane) - 1u));
-  if (r < __ldg(plan_total + v)) new_procs[slot] = lb_target(plan_off, plan_tgt, plan_cum, v, r);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSelTable; i += kBlock) {
+    const int v = s_key[i];
+    if (v < 0) continue;
+    const int total = __ldg(plan_total + v);
+    s_tot[i] = total;
+    s_base[i] = (*(volatile int*)(taken + v) >= total) ? total : atomicAdd(taken + v, s_cnt[i]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kSelPer; ++j) {
+    const int v = vv[j];
+    if (v < 0) continue;
+    const long slot = s0 + (long)j * kBlock;
+    int r, total;
+    if (ent[j] >= 0) {
+      r = s_base[ent[j]] + pos[j];
+      total = s_tot[ent[j]];
+    } else {                                   // more than kSelTable vertices in one block: on its own
+      total = __ldg(plan_total + v);
+      r = atomicAdd(taken + v, 1);
+    }
+    if (r < total) new_procs[slot] = lb_target(plan_off, plan_tgt, plan_cum, v, r);
+  }
 }
 
 // selectParticles over particles per element (pumipic_lb.hpp:316-337): element e owns the entries
@@ -470,7 +508,7 @@ extern "C" pp_status pp_balancer_select_ps(pp_balancer* b, pp_ps* ps, const int3
   if (b->nranks == 1 || b->plan_sbar.empty() || ps->capacity <= 0) return PP_OK;
   cudaStream_t s = (cudaStream_t)stream_;
   for (int non_core_only = 1; non_core_only >= 0; --non_core_only) {
-    k_lb_select_ps<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(
+    k_lb_select_ps<<<pp_div_up(ps->capacity, kSelSlots), kBlock, 0, s>>>(
         ps->capacity, ps->mask_bits, new_elems, new_procs, b->elem_vert, b->elem_owner, b->rank,
         non_core_only, b->plan_off, b->plan_tgt, b->plan_cum, b->plan_total, b->taken);
     PP_KERNEL_CHECK();
