@@ -383,6 +383,10 @@ void pp_ps_set_rebuild_chunk_order(int32_t on);
  * previous rebuild -- a PICpart that buffers the whole mesh): 1 (default) sorts only the non-empty rows and
  * places the empty ones by a prefix sum, 0 sorts all rows.  Same layout either way; A/B switch. */
 void pp_ps_set_rebuild_split_rows(int32_t on);
+/* Destination histogram of the rebuild (the particle's rank in its new element): 1 (default) counts a block's
+ * particles per destination in shared memory and reserves their ranks with one global atomic per
+ * destination, 0 uses one global atomic per particle.  Same ranks as sets; A/B switch. */
+void pp_ps_set_rebuild_block_histogram(int32_t on);
 /* Mode 2 A/B knobs.  gather_blocks_per_sm: resident blocks per SM of the gather; <= 0 (default) sizes
  * the grid so that the source footprint of the chunks in flight fits L2.  gather_max_cols: average
  * columns per chunk up to which the records are gathered; wider structures go through the record

@@ -143,6 +143,7 @@ PROTOTYPES = {
     "pp_ps_set_staged_rebuild": (None, [C.c_int32]),
     "pp_ps_set_rebuild_chunk_order": (None, [C.c_int32]),
     "pp_ps_set_rebuild_split_rows": (None, [C.c_int32]),
+    "pp_ps_set_rebuild_block_histogram": (None, [C.c_int32]),
     "pp_ps_set_rebuild_tuning": (None, [C.c_int32, C.c_int32]),
     "pp_ps_set_shuffling": (None, [C.c_int32]),
     "pp_ps_set_rank_sort_threshold": (None, [C.c_int32]),

@@ -190,8 +190,8 @@ struct PsView {  // what kernels need to map slot -> (row element, mask)
   const int* chunk_start = nullptr;   // [nchunks+1]
   int nchunks = 0;
   int nelems = 0;
-  std::vector<int> rebuild_remap;   // one-shot member remap of the next rebuild (pp_ps_set_rebuild_remap)
   int first_chunk = 0;                // chunks [0, first_chunk) hold no particle
+  int sliced = 0;                     // some chunk is wider than V columns: it spans several slices
 };
 
 struct pp_ps {
@@ -226,6 +226,7 @@ struct pp_ps {
   int shuffle_streak = 0;   // consecutive failed reshuffle attempts
   std::vector<int> rebuild_remap;   // one-shot member remap of the next rebuild (pp_ps_set_rebuild_remap)
   int first_chunk = 0;      // chunks before this one are empty (single sort window: empty rows lead)
+  int sliced = 0;           // some chunk spans several slices (more slices than non-empty chunks)
   int ppe_bits_hint = 0;    // key bits of the row sort guessed from the last rebuild's largest row (0 = none)
   int nnz_hint = 0;         // non-empty rows of the last rebuild (0 = none): a mostly empty structure only sorts those
   size_t stage_bytes;

@@ -81,6 +81,7 @@ PsView pp_ps::view() const {
   v.nchunks = (cfg.kind == PP_PS_SCS || cfg.kind == PP_PS_CABM) ? nchunks : 0;
   v.nelems = nelems;
   v.first_chunk = first_chunk;
+  v.sliced = sliced;
   return v;
 }
 

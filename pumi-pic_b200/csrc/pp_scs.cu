@@ -32,6 +32,7 @@ struct ScsLayout {
   int* row_ppe = nullptr;       // particles per row (sorted order)
   uint32_t* mask = nullptr;
   long mask_words = 0;
+  int nonempty_chunks = -1;     // chunks that hold particles (-1: unknown)
 };
 
 // grid-stride, one atomic per block: per-warp atomics on one address serialise (25 us for 1 M elements)
@@ -212,6 +213,51 @@ __global__ void k_hist_kept(PsView v, const int* __restrict__ new_elem, int* cou
   if (e >= 0) {
     if (rank) rank[s] = atomicAdd(count + e, 1);
     else atomicAdd(count + e, 1);
+  }
+}
+// The same with the destinations of a block's kHistSlots slots counted in shared memory first: a block
+// reserves the ranks of all its particles that go to one element with ONE global atomic (its return
+// value + the particle's rank inside the block = the particle's rank in the element).  Particles of a
+// row mostly stay in their element, so the 32 rows a block sees fold their stayers into 32 atomics; a
+// row that holds a large share of all particles (pseudoXGCm's load: ~1 M in one element) no longer
+// serialises a million atomics on one counter.
+constexpr int kHistPer = 4, kHistSlots = 256 * kHistPer, kHistTable = 2048, kHistProbes = 48;
+__global__ void __launch_bounds__(256) k_hist_kept_block(PsView v, const int* __restrict__ new_elem, int* count,
+                                                         int* rank) {
+  __shared__ int s_key[kHistTable], s_cnt[kHistTable], s_base[kHistTable];
+  for (int i = threadIdx.x; i < kHistTable; i += 256) { s_key[i] = -1; s_cnt[i] = 0; }
+  __syncthreads();
+  int el[kHistPer], ent[kHistPer], pos[kHistPer];
+  const long s0 = (long)blockIdx.x * kHistSlots + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < kHistPer; ++j) {
+    const long s = s0 + (long)j * 256;
+    int e = -1;
+    if (s < v.capacity) {
+      const bool m = (__ldg(v.mask_bits + (s >> 5)) >> (s & 31)) & 1u;
+      if (m) e = new_elem[s];
+    }
+    el[j] = e; ent[j] = -1; pos[j] = 0;
+    if (e >= 0) {
+      unsigned h = ((unsigned)e * 2654435761u) >> 21;            // 11 bits
+      for (int probe = 0; probe < kHistProbes; ++probe) {
+        const int k = atomicCAS(&s_key[h], -1, e);
+        if (k == -1 || k == e) { ent[j] = (int)h; break; }
+        h = (h + 1) & (kHistTable - 1);
+      }
+      if (ent[j] >= 0) pos[j] = atomicAdd(&s_cnt[ent[j]], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kHistTable; i += 256)
+    if (s_key[i] >= 0) s_base[i] = atomicAdd(count + s_key[i], s_cnt[i]);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kHistPer; ++j) {
+    if (el[j] < 0) continue;
+    const long s = s0 + (long)j * 256;
+    const int r = ent[j] >= 0 ? s_base[ent[j]] + pos[j] : atomicAdd(count + el[j], 1);   // table full: on its own
+    if (rank) rank[s] = r;
   }
 }
 // n_dev (all *_new kernels): the number of particles being added when only the device knows it
@@ -749,6 +795,7 @@ __global__ void k_shuffle_move(const int* __restrict__ src, const int* __restric
 }
 
 int g_rank_sort_ppe = 128;   // particles per element from which ranks come from a sort
+int g_hist_block = 1;        // destination histogram with block-level reservation (0: one atomic per particle, A/B)
 int g_staged_rebuild = 2;   // 2: single-pass gather (SCS, C = 32); 1: record stage; 0: direct scatter (A/B)
 int g_sm_count_scs = 0;
 
@@ -843,6 +890,7 @@ pp_status scs_layout(const pp_ps_config& cfg, int ne, const int* ppe_dev, long n
   k_slices_per_chunk<<<pp_div_up(L.nchunks + 1, kBlock), kBlock, 0, s>>>(width, L.nchunks, V, spc);
   PP_TRY(scan_exclusive(spc, slice_off, L.nchunks + 1, s));
   PP_CUDA(cudaMemcpyAsync(&L.nslices, slice_off + L.nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PP_CUDA(cudaMemcpyAsync(&L.nonempty_chunks, scal + 1, sizeof(int), cudaMemcpyDeviceToHost, s));   // k_chunk_widths
   PP_CUDA(cudaStreamSynchronize(s));
   int* slice_size;
   PP_TRY(pp_dev_alloc(&slice_size, L.nslices + 1, s));
@@ -889,6 +937,9 @@ void adopt_layout(pp_ps* ps, ScsLayout& L, cudaStream_t s) {
   ps->row_to_element = L.row_to_element; ps->element_to_row = L.element_to_row;
   ps->tile_slice = L.tile_slice; ps->mask_bits = L.mask; ps->mask_words_alloc = L.mask_words;
   ps->chunk_start = L.chunk_start; ps->row_ppe = L.row_ppe;
+  // Empty chunks have no slice: "more slices than chunks" would miss a wide chunk in a structure that also
+  // has empty ones (pseudoXGCm's load: 47 K slices, 63 K chunks, one chunk of 924 slices).
+  ps->sliced = L.nslices > (L.nonempty_chunks >= 0 ? L.nonempty_chunks : L.nchunks) ? 1 : 0;
   L = ScsLayout();
   if (ps->slot_elem) { pp_dev_free(ps->slot_elem, s); ps->slot_elem = nullptr; }
   ps->slot_elem_valid = false;
@@ -1416,7 +1467,8 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     PP_TIME_KIND(s, ps->cfg.kind, "count active particles");       // SCS_rebuild.h:133-166
     if (cap > 0) {
       PP_TRY(pp_dev_alloc(&rank, cap, s));
-      k_hist_kept<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count, rank);
+      if (g_hist_block) k_hist_kept_block<<<pp_div_up(cap, kHistSlots), 256, 0, s>>>(ps->view(), new_element, count, rank);
+      else k_hist_kept<<<pp_div_up(cap, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count, rank);
     }
     if (n_new > 0) {               // counted after the kept particles: their ranks follow the kept ones
       PP_TRY(pp_dev_alloc(&rank_new, n_new, s));
@@ -1551,7 +1603,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
     return PP_OK;
   }
   PPTimeScope* t_fin = new PPTimeScope(s, (std::string(pp_kind_name(ps->cfg.kind)) + " layout finish").c_str());
-  L.nslices = h.nslices; L.capacity = h.capacity;
+  L.nslices = h.nslices; L.capacity = h.capacity; L.nonempty_chunks = h.cw_cnt;
   const int ntiles = (L.capacity + 31) / 32;
   PP_TRY(pp_dev_alloc(&L.tile_slice, ntiles + 1, s));
   if (ntiles > 0)
@@ -1580,7 +1632,7 @@ pp_status rebuild_scs_gather(pp_ps* ps, const int* new_element, int n_new, const
   const double avg_cols = (double)L.capacity / (32.0 * nfull);
   // (a chunk wider than V columns -- more slices than chunks -- would be gathered by a single block:
   //  the stage's kernels are thread-per-slot and do not care)
-  if (avg_cols <= g_gather_max_cols && L.nslices <= nchunks) {
+  if (avg_cols <= g_gather_max_cols && L.nslices <= nfull) {
     // ---- single-pass gather
     int* src_of;
     PP_TRY(pp_dev_alloc(&src_of, (size_t)L.capacity + 1, s));
@@ -1852,7 +1904,8 @@ pp_status pp_ps_rebuild_ex(pp_ps* ps, const int32_t* new_element, int32_t n_new,
       PP_TRY(pp_dev_alloc(&rank, ps->capacity, s));
       if (n_new > 0) PP_TRY(pp_dev_alloc(&kept, ne + 1, s));
     }
-    k_hist_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count, rank);
+    if (g_hist_block) k_hist_kept_block<<<pp_div_up(ps->capacity, kHistSlots), 256, 0, s>>>(ps->view(), new_element, count, rank);
+    else k_hist_kept<<<pp_div_up(ps->capacity, kBlock), kBlock, 0, s>>>(ps->view(), new_element, count, rank);
     if (kept) PP_CUDA(cudaMemcpyAsync(kept, count, sizeof(int) * ne, cudaMemcpyDeviceToDevice, s));
   }
   if (n_new > 0)
@@ -2069,6 +2122,7 @@ extern "C" void pp_ps_set_rebuild_tuning(int32_t gather_blocks_per_sm, int32_t g
 }
 extern "C" void pp_ps_set_rebuild_chunk_order(int32_t on) { g_rebuild_chunk_order = on ? 1 : 0; }
 extern "C" void pp_ps_set_rebuild_split_rows(int32_t on) { g_rebuild_split_rows = on ? 1 : 0; }
+extern "C" void pp_ps_set_rebuild_block_histogram(int32_t on) { g_hist_block = on ? 1 : 0; }
 
 extern "C" void pp_ps_set_rank_sort_threshold(int32_t particles_per_element) {
   g_rank_sort_ppe = particles_per_element > 0 ? particles_per_element : 1;

@@ -1061,7 +1061,7 @@ __global__ void __launch_bounds__(WARPS * 32, PP_SCS_MINB) k_walk_scs(SearchPara
   const int* __restrict__ s2c = p.ps.slice_to_chunk;
   const int* __restrict__ soff = p.ps.offsets;
   const int* __restrict__ cstart = p.ps.chunk_start;
-  const bool by_slice = p.ps.nslices > p.ps.nchunks;
+  const bool by_slice = p.ps.sliced != 0;
   int unit_lo = p.chunk_begin, unit_hi = p.chunk_end;
   if (by_slice) {
     unit_lo = 0; unit_hi = p.ps.nslices;
@@ -1240,7 +1240,7 @@ pp_status launch_walk_scs(const SearchParams& p, bool push, cudaStream_t s) {
     PP_CUDA(cudaGetDevice(&dev));
     PP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int want = pp_div_up(p.ps.nslices > p.ps.nchunks ? p.ps.nslices : p.chunk_end - p.chunk_begin, WARPS);
+  const int want = pp_div_up(p.ps.sliced ? p.ps.nslices : p.chunk_end - p.chunk_begin, WARPS);
   if (want <= 0) return PP_OK;                         // nothing but empty chunks in the range
   const int persistent = g_sm_count * PP_SCS_MINB;
   const int grid = want < persistent ? want : persistent;

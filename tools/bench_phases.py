@@ -160,7 +160,29 @@ def c4(pp, wl, torch, steps, nptcls, plate_n, kind):
             "full_step_ms": tot, "full_steps_per_s": nptcls / (tot * 1e-3), "particles_after": ps.nptcls}
 
 
-def c4x(pp, wl, torch, steps, nptcls, mdl_face, kind):
+def scatter_conservation(pp, torch, gm, ps, m, fmap, rmax, rings, ppr):
+    """full-size property of the gyro scatter (gyroScatter.hpp:168-229): every particle puts 1 on rings 0 and 1
+    of its element's 3 vertices, and a ring's value reaches the mesh once per mapped (point, vertex) pair divided
+    by the points per ring -- the total over the vertices is known from the map and the particles per element"""
+    cap = ps.capacity
+    lay = ps.layout()
+    se = pp.api._tensor_from_ptr(lay.slot_elem, (cap,), torch.int32, ps).long()
+    mb = pp.api._tensor_from_ptr(lay.mask_bits, ((cap + 31) // 32,), torch.int32, ps)
+    sh = torch.arange(32, device="cuda", dtype=torch.int32)
+    mask = (((mb[:, None] >> sh[None, :]) & 1) != 0).reshape(-1)[:cap]
+    ppe = torch.bincount(se[mask], minlength=m.nelems).to(torch.float64)
+    ev = torch.as_tensor(m.elem2verts).cuda().long()
+    acc = torch.zeros(m.nverts, dtype=torch.float64, device="cuda")
+    for k in range(3):
+        acc.index_add_(0, ev[:, k], ppe)
+    pairs = (fmap.reshape(m.nverts, rings, ppr, 3)[:, :2] >= 0).sum(dim=(1, 2, 3)).to(torch.float64)
+    expect = float((acc * pairs).sum().item()) / ppr
+    got = float(pp.gyro_scatter(gm, ps, fmap, rmax, rings, ppr).sum().item())
+    return {"particles": int(mask.sum().item()), "total_scattered": got, "total_expected": expect,
+            "relative_error": abs(got - expect) / max(1.0, abs(expect))}
+
+
+def c4x(pp, wl, torch, steps, nptcls, mdl_face, kind, fold_update=True):
     """BASELINE configs[3] on its named mesh: pseudoXGCm's step (test/pseudoXGCm.cpp:504-534) on
     pumipic-data/xgc/2M.osh (tests/golden/_large/mesh_xgc2M.npz, made by make_large_fixtures.py): the
     reference's class-limited normal particle load (:167-222) and initial coordinates (:224-264),
@@ -195,7 +217,10 @@ def c4x(pp, wl, torch, steps, nptcls, mdl_face, kind):
         T.run("search_mesh_2d", lambda: P.search_mesh(gm, ps, ps.get(0), ps.get(1), ids,
                                                        variant=P.capi.PP_SEARCH_2D_LEGACY, elem_ids_empty=True,
                                                        looplimit=200, sync=False))
-        T.run("updatePtclPositions", lambda: P.update_positions(ps, ps.get(0), ps.get(1)))
+        if fold_update:      # the reference's rebuild() starts with updatePtclPositions (pseudoXGCm.cpp:116-118):
+            T.run("updatePtclPositions", lambda: ps.set_rebuild_remap([1, -1, 2, 3, 4]))   # folded into the record move
+        else:
+            T.run("updatePtclPositions", lambda: P.update_positions(ps, ps.get(0), ps.get(1)))
         T.run("rebuild", lambda: ps.rebuild(ids))
         T.run("gyroScatter x2", lambda: (P.gyro_scatter(gm, ps, fmap, rmax, rings, ppr),
                                          P.gyro_scatter(gm, ps, fmap, rmax, rings, ppr)))
@@ -205,7 +230,9 @@ def c4x(pp, wl, torch, steps, nptcls, mdl_face, kind):
     return {"config": "c4 on xgc/2M.osh", "particles": int(total), "triangles": m.nelems, "verts": m.nverts,
             "mdl_face": mdl_face, "elements_loaded": int((ppe > 0).sum()), "max_ppe": int(ppe.max()),
             "phases": s, "full_step_ms": tot, "full_steps_per_s": total / (tot * 1e-3),
-            "particles_after": counts[-1], "capacity": ps.capacity}
+            "particles_after": counts[-1], "capacity": ps.capacity,
+            "updatePtclPositions": "member remap of the rebuild's record move" if fold_update else "own pass",
+            "scatter_conservation_full_size": scatter_conservation(pp, torch, gm, ps, m, fmap, rmax, rings, ppr)}
 
 
 def main():
@@ -220,6 +247,8 @@ def main():
     ap.add_argument("--chunk-order", type=int, default=1, help="pp_ps_set_rebuild_chunk_order")
     ap.add_argument("--shuffling", type=int, default=1, help="pp_ps_set_shuffling")
     ap.add_argument("--tuning", default="0,-1", help="pp_ps_set_rebuild_tuning: gather blocks/SM, gather max columns")
+    ap.add_argument("--separate-update", action="store_true", help="c4x: updatePtclPositions as its own pass (A/B)")
+    ap.add_argument("--block-histogram", type=int, default=1, help="pp_ps_set_rebuild_block_histogram (A/B)")
     a = ap.parse_args()
     import torch
     pp = importlib.import_module("pumi-pic_b200")
@@ -228,6 +257,7 @@ def main():
     pp.lib().pp_ps_set_staged_rebuild(a.rebuild_mode)
     pp.lib().pp_ps_set_rebuild_chunk_order(a.chunk_order)
     pp.lib().pp_ps_set_shuffling(a.shuffling)
+    pp.lib().pp_ps_set_rebuild_block_histogram(a.block_histogram)
     pp.lib().pp_ps_set_rebuild_tuning(*[int(x) for x in a.tuning.split(",")])
     for c in a.configs.split(","):
         if c == "c2":
@@ -237,12 +267,13 @@ def main():
         elif c == "c4":
             r = c4(pp, wl, torch, a.steps, a.c4_particles, 1000, kind)
         elif c == "c4x":
-            r = c4x(pp, wl, torch, a.steps, a.c4_particles, a.mdl_face, kind)
+            r = c4x(pp, wl, torch, a.steps, a.c4_particles, a.mdl_face, kind, fold_update=not a.separate_update)
         else:
             continue
         r["particle_structure"] = a.ps
         r["rebuild_mode"], r["chunk_order"], r["shuffling"] = a.rebuild_mode, a.chunk_order, a.shuffling
         r["tuning"] = a.tuning
+        r["block_histogram"] = a.block_histogram
         print(json.dumps(r))
         sys.stdout.flush()
         torch.cuda.empty_cache()
